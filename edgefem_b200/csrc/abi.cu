@@ -1,0 +1,592 @@
+// Context, mesh and system handles: upload, CSR pattern construction, gather maps.
+// Pattern rules follow the reference bit-exactly:
+// union of the 6x6 edge cliques of all tets (Eigen setFromTriplets,
+// src/assemble_maxwell.cpp:205) plus caller-listed extra entries (coeffRef insertions),
+// row-major, columns sorted ascending.
+#include <stdarg.h>
+
+#include <algorithm>
+#include <mutex>
+#include <thread>
+
+#include "common.cuh"
+
+namespace efb {
+
+static std::mutex g_err_mu;
+static std::string g_err;
+
+void set_global_error(const std::string &s) {
+  std::lock_guard<std::mutex> lk(g_err_mu);
+  g_err = s;
+}
+
+int fail(Ctx *ctx, int code, const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf;
+  set_global_error(buf);
+  return code;
+}
+
+template <typename F>
+static void parallel_for(int64_t n, F f) {
+  unsigned hw = std::thread::hardware_concurrency();
+  int nt = (int)std::min<int64_t>(std::max(1u, std::min(hw, 32u)), std::max<int64_t>(1, n / 4096));
+  if (nt <= 1) {
+    f(0, n);
+    return;
+  }
+  std::vector<std::thread> th;
+  int64_t step = (n + nt - 1) / nt;
+  for (int t = 0; t < nt; ++t) {
+    int64_t a = t * step, b = std::min<int64_t>(n, a + step);
+    if (a >= b) break;
+    th.emplace_back([=] { f(a, b); });
+  }
+  for (auto &x : th) x.join();
+}
+
+// ---------------------------------------------------------------- kernels used here
+__global__ void k_slot_bbox(const int4 *__restrict__ tet_nodes, const uint8_t *__restrict__ tet_slot,
+                            const double4 *__restrict__ xyz, int n_tet, unsigned long long *bbox_enc) {
+  // order-preserving encoding of doubles into uint64 so atomicMin/Max work
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tet) return;
+  int4 nd = tet_nodes[t];
+  int s = tet_slot[t];
+  int ids[4] = {nd.x, nd.y, nd.z, nd.w};
+  double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    double4 p = xyz[ids[i]];
+    mn[0] = fmin(mn[0], p.x); mx[0] = fmax(mx[0], p.x);
+    mn[1] = fmin(mn[1], p.y); mx[1] = fmax(mx[1], p.y);
+    mn[2] = fmin(mn[2], p.z); mx[2] = fmax(mx[2], p.z);
+  }
+  auto enc = [](double d) {
+    unsigned long long u = (unsigned long long)__double_as_longlong(d);
+    return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+  };
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    atomicMin(&bbox_enc[s * 6 + a], enc(mn[a]));
+    atomicMax(&bbox_enc[s * 6 + 3 + a], enc(mx[a]));
+  }
+}
+
+__global__ void k_bbox_decode(unsigned long long *enc, double *out, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long u = enc[i];
+  u = (u & 0x8000000000000000ull) ? (u & 0x7fffffffffffffffull) : ~u;
+  out[i] = __longlong_as_double((long long)u);
+}
+
+__global__ void k_node_dir(const int2 *__restrict__ edge_nodes, const uint8_t *__restrict__ dir, int m,
+                           uint8_t *node_dir) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= m) return;
+  if (dir[e]) {
+    int2 n = edge_nodes[e];
+    node_dir[n.x] = 1;
+    node_dir[n.y] = 1;
+  }
+}
+
+}  // namespace efb
+
+using namespace efb;
+
+extern "C" {
+
+int efb_abi_version(void) { return EFB_ABI_VERSION; }
+
+int efb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+const char *efb_last_error(const efb_ctx *ctx) {
+  if (ctx) return ((const Ctx *)ctx)->err.c_str();
+  static thread_local std::string copy;
+  std::lock_guard<std::mutex> lk(g_err_mu);
+  copy = g_err;
+  return copy.c_str();
+}
+
+int efb_ctx_create(int device, efb_ctx **out) {
+  if (!out) return fail(nullptr, EFB_ERR_INVALID, "efb_ctx_create: out is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(nullptr, EFB_ERR_CUDA,
+                "efb_ctx_create: no CUDA device available (%s); this library has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  }
+  if (device < 0 || device >= n) return fail(nullptr, EFB_ERR_INVALID, "efb_ctx_create: device %d out of range [0,%d)", device, n);
+  Ctx *c = new Ctx();
+  c->device = device;
+  EFB_CUDA(c, cudaSetDevice(device));
+  EFB_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  EFB_CUDA(c, cudaEventCreate(&c->ev0));
+  EFB_CUDA(c, cudaEventCreate(&c->ev1));
+  cudaDeviceProp prop;
+  EFB_CUDA(c, cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  *out = (efb_ctx *)c;
+  return EFB_OK;
+}
+
+void efb_ctx_destroy(efb_ctx *ctx_) {
+  Ctx *c = (Ctx *)ctx_;
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int efb_ctx_sync(efb_ctx *ctx_) {
+  Ctx *c = (Ctx *)ctx_;
+  if (!c) return EFB_ERR_INVALID;
+  EFB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return EFB_OK;
+}
+
+double efb_last_kernel_ms(const efb_ctx *ctx_) {
+  Ctx *c = (Ctx *)ctx_;
+  if (!c || !c->ev_valid) return -1.0;
+  if (cudaEventSynchronize(c->ev1) != cudaSuccess) return -1.0;
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) != cudaSuccess) return -1.0;
+  return (double)ms;
+}
+
+int64_t efb_launch_count(const efb_ctx *ctx_) { return ctx_ ? ((const Ctx *)ctx_)->launches : 0; }
+
+// ------------------------------------------------------------------ mesh
+int efb_mesh_create(efb_ctx *ctx_, const efb_mesh_desc *d, efb_mesh **out) {
+  Ctx *c = (Ctx *)ctx_;
+  if (!c || !d || !out) return fail(c, EFB_ERR_INVALID, "efb_mesh_create: NULL argument");
+  *out = nullptr;
+  if (d->n_node <= 0 || d->n_tet < 0 || d->n_edge <= 0 || !d->xyz || !d->edge_nodes ||
+      (d->n_tet > 0 && (!d->tet_nodes || !d->tet_edges || !d->tet_orient || !d->tet_phys)))
+    return fail(c, EFB_ERR_INVALID, "efb_mesh_create: bad descriptor");
+  if ((int64_t)d->n_tet >= (1ll << 28)) return fail(c, EFB_ERR_LIMIT, "efb_mesh_create: n_tet >= 2^28");
+  EFB_CUDA(c, cudaSetDevice(c->device));
+  Mesh *M = new Mesh();
+  M->ctx = c;
+  M->n_node = d->n_node;
+  M->n_tet = d->n_tet;
+  M->m = d->n_edge;
+  const int64_t nt = d->n_tet;
+  // validate indices
+  for (int64_t i = 0; i < 4 * nt; ++i)
+    if (d->tet_nodes[i] < 0 || d->tet_nodes[i] >= d->n_node) {
+      delete M;
+      return fail(c, EFB_ERR_INVALID, "efb_mesh_create: tet_nodes[%lld] out of range", (long long)i);
+    }
+  for (int64_t i = 0; i < 6 * nt; ++i)
+    if (d->tet_edges[i] < 0 || d->tet_edges[i] >= d->n_edge) {
+      delete M;
+      return fail(c, EFB_ERR_INVALID, "efb_mesh_create: tet_edges[%lld] out of range", (long long)i);
+    }
+  // slots = distinct tags ascending
+  {
+    std::vector<int32_t> tags(d->tet_phys, d->tet_phys + nt);
+    std::sort(tags.begin(), tags.end());
+    tags.erase(std::unique(tags.begin(), tags.end()), tags.end());
+    if ((int)tags.size() > MAX_SLOTS) {
+      delete M;
+      return fail(c, EFB_ERR_LIMIT, "efb_mesh_create: %zu distinct physical tags > %d", tags.size(), MAX_SLOTS);
+    }
+    M->slot_tags = tags;
+    M->n_slots = (int)tags.size();
+  }
+  std::vector<uint8_t> slot(nt), sign(nt);
+  for (int64_t t = 0; t < nt; ++t) {
+    slot[t] = (uint8_t)(std::lower_bound(M->slot_tags.begin(), M->slot_tags.end(), d->tet_phys[t]) - M->slot_tags.begin());
+    uint8_t s = 0;
+    for (int k = 0; k < 6; ++k)
+      if (d->tet_orient[6 * t + k] < 0) s |= (uint8_t)(1u << k);
+    sign[t] = s;
+  }
+  M->h_tet_edges.assign(d->tet_edges, d->tet_edges + 6 * nt);
+  M->h_edge_nodes.assign(d->edge_nodes, d->edge_nodes + 2 * (int64_t)d->n_edge);
+  // edge -> incident (tet, local) lists, ascending tet (deterministic summation order)
+  M->h_e2t_ptr.assign((size_t)M->m + 1, 0);
+  for (int64_t i = 0; i < 6 * nt; ++i) M->h_e2t_ptr[d->tet_edges[i] + 1]++;
+  for (int e = 0; e < M->m; ++e) M->h_e2t_ptr[e + 1] += M->h_e2t_ptr[e];
+  M->h_e2t_item.resize((size_t)6 * nt);
+  {
+    std::vector<int32_t> cur(M->h_e2t_ptr.begin(), M->h_e2t_ptr.end() - 1);
+    for (int64_t t = 0; t < nt; ++t)
+      for (int k = 0; k < 6; ++k) M->h_e2t_item[cur[d->tet_edges[6 * t + k]]++] = (int32_t)((t << 3) | k);
+  }
+  std::vector<double4> xyz4(d->n_node);
+  for (int i = 0; i < d->n_node; ++i) xyz4[i] = make_double4(d->xyz[3 * i], d->xyz[3 * i + 1], d->xyz[3 * i + 2], 0.0);
+  int rc;
+  if ((rc = dev_upload(c, &M->d_xyz, xyz4.data(), xyz4.size()))) return rc;
+  if ((rc = dev_upload(c, &M->d_tet_nodes, (const int4 *)d->tet_nodes, (size_t)nt))) return rc;
+  if ((rc = dev_upload(c, &M->d_tet_sign, sign.data(), sign.size()))) return rc;
+  if ((rc = dev_upload(c, &M->d_tet_slot, slot.data(), slot.size()))) return rc;
+  if ((rc = dev_upload(c, &M->d_e2t_ptr, M->h_e2t_ptr.data(), M->h_e2t_ptr.size()))) return rc;
+  if ((rc = dev_upload(c, &M->d_e2t_item, M->h_e2t_item.data(), M->h_e2t_item.size()))) return rc;
+  // per-slot bounding boxes (PML profile, src/assemble_maxwell.cpp:66-89) on device
+  if ((rc = dev_alloc(c, &M->d_slot_bbox, (size_t)std::max(1, M->n_slots) * 6))) return rc;
+  if (nt > 0) {
+    unsigned long long *enc = nullptr;
+    if ((rc = dev_alloc(c, &enc, (size_t)M->n_slots * 6))) return rc;
+    std::vector<unsigned long long> init((size_t)M->n_slots * 6);
+    for (int s = 0; s < M->n_slots; ++s)
+      for (int a = 0; a < 6; ++a) init[s * 6 + a] = a < 3 ? ~0ull : 0ull;
+    EFB_CUDA(c, cudaMemcpyAsync(enc, init.data(), init.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    k_slot_bbox<<<(unsigned)((nt + 255) / 256), 256, 0, c->stream>>>(M->d_tet_nodes, M->d_tet_slot, M->d_xyz, (int)nt, enc);
+    EFB_CHECK_LAUNCH(c);
+    k_bbox_decode<<<(M->n_slots * 6 + 63) / 64, 64, 0, c->stream>>>(enc, M->d_slot_bbox, M->n_slots * 6);
+    EFB_CHECK_LAUNCH(c);
+    EFB_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(enc);
+  }
+  EFB_CUDA(c, cudaStreamSynchronize(c->stream));
+  *out = (efb_mesh *)M;
+  return EFB_OK;
+}
+
+void efb_mesh_destroy(efb_mesh *mesh_) {
+  Mesh *M = (Mesh *)mesh_;
+  if (!M) return;
+  cudaSetDevice(M->ctx->device);
+  cudaFree(M->d_xyz); cudaFree(M->d_tet_nodes); cudaFree(M->d_tet_sign); cudaFree(M->d_tet_slot);
+  cudaFree(M->d_e2t_ptr); cudaFree(M->d_e2t_item); cudaFree(M->d_slot_bbox);
+  delete M;
+}
+
+int efb_mesh_num_slots(const efb_mesh *mesh_) { return mesh_ ? ((const Mesh *)mesh_)->n_slots : 0; }
+
+int efb_mesh_get_slot_tags(const efb_mesh *mesh_, int32_t *tags) {
+  const Mesh *M = (const Mesh *)mesh_;
+  if (!M || !tags) return EFB_ERR_INVALID;
+  for (int i = 0; i < M->n_slots; ++i) tags[i] = M->slot_tags[i];
+  return EFB_OK;
+}
+
+// ------------------------------------------------------------------ system
+static int system_alloc_common(System *S) {
+  Ctx *c = S->ctx;
+  int rc;
+  S->n_sys = S->n_matrix * S->n_rhs;
+  if ((rc = dev_upload(c, &S->d_rowptr, S->h_rowptr.data(), S->h_rowptr.size()))) return rc;
+  if ((rc = dev_upload(c, &S->d_colidx, S->h_colidx.data(), S->h_colidx.size()))) return rc;
+  std::vector<int32_t> diag(S->m, -1);
+  parallel_for(S->m, [&](int64_t a, int64_t b) {
+    for (int64_t r = a; r < b; ++r) {
+      const int32_t *beg = S->h_colidx.data() + S->h_rowptr[r], *end = S->h_colidx.data() + S->h_rowptr[r + 1];
+      const int32_t *it = std::lower_bound(beg, end, (int32_t)r);
+      if (it != end && *it == r) diag[r] = (int32_t)(it - S->h_colidx.data());
+    }
+  });
+  if ((rc = dev_upload(c, &S->d_diag_pos, diag.data(), diag.size()))) return rc;
+  if ((rc = dev_alloc(c, &S->d_vals, (size_t)S->n_matrix * S->nnz))) return rc;
+  if ((rc = dev_alloc(c, &S->d_b, (size_t)S->n_sys * S->m))) return rc;
+  if ((rc = dev_alloc(c, &S->d_x, (size_t)S->n_sys * S->m))) return rc;
+  if ((rc = dev_alloc(c, &S->d_dir, (size_t)S->m))) return rc;
+  if ((rc = dev_alloc(c, &S->d_flag, (size_t)1))) return rc;
+  EFB_CUDA(c, cudaMemsetAsync(S->d_flag, 0, sizeof(int32_t), c->stream));
+  EFB_CUDA(c, cudaMemsetAsync(S->d_vals, 0, (size_t)S->n_matrix * S->nnz * sizeof(c128), c->stream));
+  EFB_CUDA(c, cudaMemsetAsync(S->d_b, 0, (size_t)S->n_sys * S->m * sizeof(c128), c->stream));
+  EFB_CUDA(c, cudaMemsetAsync(S->d_x, 0, (size_t)S->n_sys * S->m * sizeof(c128), c->stream));
+  EFB_CUDA(c, cudaMemsetAsync(S->d_dir, 0, (size_t)S->m, c->stream));
+  return EFB_OK;
+}
+
+static int system_set_gradient(System *S, int n_node, const int32_t *edge_nodes) {
+  Ctx *c = S->ctx;
+  int rc;
+  S->n_node = n_node;
+  cudaFree(S->d_edge_nodes); cudaFree(S->d_n2e_ptr); cudaFree(S->d_n2e_item); cudaFree(S->d_node_dir);
+  S->d_edge_nodes = nullptr; S->d_n2e_ptr = nullptr; S->d_n2e_item = nullptr; S->d_node_dir = nullptr;
+  for (int64_t i = 0; i < 2 * (int64_t)S->m; ++i)
+    if (edge_nodes[i] < 0 || edge_nodes[i] >= n_node) return fail(c, EFB_ERR_INVALID, "edge_nodes[%lld] out of range", (long long)i);
+  if ((rc = dev_upload(c, &S->d_edge_nodes, (const int2 *)edge_nodes, (size_t)S->m))) return rc;
+  std::vector<int32_t> ptr((size_t)n_node + 1, 0), item((size_t)2 * S->m);
+  for (int64_t i = 0; i < 2 * (int64_t)S->m; ++i) ptr[edge_nodes[i] + 1]++;
+  for (int n = 0; n < n_node; ++n) ptr[n + 1] += ptr[n];
+  {
+    std::vector<int32_t> cur(ptr.begin(), ptr.end() - 1);
+    for (int e = 0; e < S->m; ++e) {
+      item[cur[edge_nodes[2 * e]]++] = (e << 1);          // tail: G = -1
+      item[cur[edge_nodes[2 * e + 1]]++] = (e << 1) | 1;  // head: G = +1
+    }
+  }
+  if ((rc = dev_upload(c, &S->d_n2e_ptr, ptr.data(), ptr.size()))) return rc;
+  if ((rc = dev_upload(c, &S->d_n2e_item, item.data(), item.size()))) return rc;
+  if ((rc = dev_alloc(c, &S->d_node_dir, (size_t)n_node))) return rc;
+  EFB_CUDA(c, cudaMemsetAsync(S->d_node_dir, 0, (size_t)n_node, c->stream));
+  EFB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return EFB_OK;
+}
+
+int efb_system_create(efb_mesh *mesh_, int64_t n_extra, const int32_t *extra_rows, const int32_t *extra_cols,
+                      int32_t n_matrix, int32_t n_rhs, efb_system **out) {
+  Mesh *M = (Mesh *)mesh_;
+  if (!M || !out) return fail(M ? M->ctx : nullptr, EFB_ERR_INVALID, "efb_system_create: NULL argument");
+  Ctx *c = M->ctx;
+  *out = nullptr;
+  if (n_matrix <= 0 || n_rhs <= 0 || n_extra < 0 || (n_extra > 0 && (!extra_rows || !extra_cols)))
+    return fail(c, EFB_ERR_INVALID, "efb_system_create: bad arguments");
+  EFB_CUDA(c, cudaSetDevice(c->device));
+  const int m = M->m;
+  for (int64_t i = 0; i < n_extra; ++i)
+    if (extra_rows[i] < 0 || extra_rows[i] >= m || extra_cols[i] < 0 || extra_cols[i] >= m)
+      return fail(c, EFB_ERR_INVALID, "efb_system_create: extra entry %lld out of range", (long long)i);
+  System *S = new System();
+  S->ctx = c;
+  S->mesh = M;
+  S->m = m;
+  S->n_matrix = n_matrix;
+  S->n_rhs = n_rhs;
+  // extras bucketed by row
+  std::vector<int64_t> xptr((size_t)m + 1, 0);
+  for (int64_t i = 0; i < n_extra; ++i) xptr[extra_rows[i] + 1]++;
+  for (int r = 0; r < m; ++r) xptr[r + 1] += xptr[r];
+  std::vector<int32_t> xcol((size_t)n_extra);
+  {
+    std::vector<int64_t> cur(xptr.begin(), xptr.end() - 1);
+    for (int64_t i = 0; i < n_extra; ++i) xcol[cur[extra_rows[i]]++] = extra_cols[i];
+  }
+  // pass 1: row lengths ; pass 2: fill
+  S->h_rowptr.assign((size_t)m + 1, 0);
+  const int32_t *te = M->h_tet_edges.data();
+  auto row_cols = [&](int r, std::vector<int32_t> &buf) {
+    buf.clear();
+    for (int32_t k = M->h_e2t_ptr[r]; k < M->h_e2t_ptr[r + 1]; ++k) {
+      const int32_t *e6 = te + 6 * (int64_t)(M->h_e2t_item[k] >> 3);
+      buf.insert(buf.end(), e6, e6 + 6);
+    }
+    buf.insert(buf.end(), xcol.begin() + xptr[r], xcol.begin() + xptr[r + 1]);
+    std::sort(buf.begin(), buf.end());
+    buf.erase(std::unique(buf.begin(), buf.end()), buf.end());
+  };
+  std::vector<int32_t> rowlen(m);
+  parallel_for(m, [&](int64_t a, int64_t b) {
+    std::vector<int32_t> buf;
+    for (int64_t r = a; r < b; ++r) {
+      row_cols((int)r, buf);
+      rowlen[r] = (int32_t)buf.size();
+    }
+  });
+  int64_t nnz = 0;
+  int32_t maxrow = 0;
+  for (int r = 0; r < m; ++r) {
+    nnz += rowlen[r];
+    maxrow = std::max(maxrow, rowlen[r]);
+  }
+  if (nnz >= (1ll << 31)) {
+    delete S;
+    return fail(c, EFB_ERR_LIMIT, "efb_system_create: nnz %lld >= 2^31 (int32 CSR like Eigen's default index)", (long long)nnz);
+  }
+  if (maxrow > ASM_CHUNK_NNZ || maxrow > 65535) {
+    delete S;
+    return fail(c, EFB_ERR_LIMIT, "efb_system_create: a row has %d entries (limit %d)", maxrow, std::min(ASM_CHUNK_NNZ, 65535));
+  }
+  S->nnz = nnz;
+  for (int r = 0; r < m; ++r) S->h_rowptr[r + 1] = S->h_rowptr[r] + rowlen[r];
+  S->h_colidx.resize((size_t)nnz);
+  std::vector<uint16_t> pos((size_t)M->h_e2t_item.size() * 6);
+  parallel_for(m, [&](int64_t a, int64_t b) {
+    std::vector<int32_t> buf;
+    for (int64_t r = a; r < b; ++r) {
+      row_cols((int)r, buf);
+      int32_t *dst = S->h_colidx.data() + S->h_rowptr[r];
+      std::copy(buf.begin(), buf.end(), dst);
+      for (int32_t k = M->h_e2t_ptr[r]; k < M->h_e2t_ptr[r + 1]; ++k) {
+        const int32_t *e6 = te + 6 * (int64_t)(M->h_e2t_item[k] >> 3);
+        for (int j = 0; j < 6; ++j)
+          pos[(size_t)k * 6 + j] = (uint16_t)(std::lower_bound(buf.begin(), buf.end(), e6[j]) - buf.begin());
+      }
+    }
+  });
+  // assembly chunks: consecutive rows with <= ASM_CHUNK_NNZ entries and <= ASM_CHUNK_ROWS rows
+  std::vector<int32_t> chunk{0};
+  {
+    int64_t acc = 0;
+    int rows = 0;
+    for (int r = 0; r < m; ++r) {
+      if (acc + rowlen[r] > ASM_CHUNK_NNZ || rows >= ASM_CHUNK_ROWS) {
+        chunk.push_back(r);
+        acc = 0;
+        rows = 0;
+      }
+      acc += rowlen[r];
+      rows++;
+    }
+    chunk.push_back(m);
+  }
+  S->n_chunks = (int)chunk.size() - 1;
+  int rc;
+  if ((rc = system_alloc_common(S))) return rc;
+  if ((rc = dev_upload(c, &S->d_e2t_pos, pos.data(), pos.size()))) return rc;
+  if ((rc = dev_upload(c, &S->d_chunk_row, chunk.data(), chunk.size()))) return rc;
+  if ((rc = system_set_gradient(S, M->n_node, M->h_edge_nodes.data()))) return rc;
+  EFB_CUDA(c, cudaStreamSynchronize(c->stream));
+  *out = (efb_system *)S;
+  return EFB_OK;
+}
+
+int efb_system_create_csr(efb_ctx *ctx_, int32_t m, int64_t nnz, const int32_t *rowptr, const int32_t *colidx,
+                          const double *vals, int32_t n_matrix, int32_t n_rhs, efb_system **out) {
+  Ctx *c = (Ctx *)ctx_;
+  if (!c || !out || !rowptr || !colidx) return fail(c, EFB_ERR_INVALID, "efb_system_create_csr: NULL argument");
+  *out = nullptr;
+  if (m <= 0 || nnz < 0 || nnz >= (1ll << 31) || n_matrix <= 0 || n_rhs <= 0 || rowptr[0] != 0 || rowptr[m] != nnz)
+    return fail(c, EFB_ERR_INVALID, "efb_system_create_csr: bad dimensions");
+  for (int r = 0; r < m; ++r) {
+    if (rowptr[r + 1] < rowptr[r]) return fail(c, EFB_ERR_INVALID, "efb_system_create_csr: rowptr not monotone");
+    for (int64_t k = rowptr[r]; k < rowptr[r + 1]; ++k) {
+      if (colidx[k] < 0 || colidx[k] >= m) return fail(c, EFB_ERR_INVALID, "efb_system_create_csr: column out of range");
+      if (k > rowptr[r] && colidx[k] <= colidx[k - 1])
+        return fail(c, EFB_ERR_INVALID, "efb_system_create_csr: columns must be strictly ascending per row");
+    }
+  }
+  EFB_CUDA(c, cudaSetDevice(c->device));
+  System *S = new System();
+  S->ctx = c;
+  S->m = m;
+  S->nnz = nnz;
+  S->n_matrix = n_matrix;
+  S->n_rhs = n_rhs;
+  S->h_rowptr.assign(rowptr, rowptr + m + 1);
+  S->h_colidx.assign(colidx, colidx + nnz);
+  int rc;
+  if ((rc = system_alloc_common(S))) return rc;
+  if (vals)
+    for (int f = 0; f < n_matrix; ++f)
+      EFB_CUDA(c, cudaMemcpyAsync(S->d_vals + (size_t)f * nnz, vals, (size_t)nnz * sizeof(c128), cudaMemcpyHostToDevice, c->stream));
+  EFB_CUDA(c, cudaStreamSynchronize(c->stream));
+  S->assembled = vals != nullptr;
+  *out = (efb_system *)S;
+  return EFB_OK;
+}
+
+void efb_system_destroy(efb_system *sys_) {
+  System *S = (System *)sys_;
+  if (!S) return;
+  cudaSetDevice(S->ctx->device);
+  cudaStreamSynchronize(S->ctx->stream);
+  solver_free(S);
+  cudaFree(S->d_rowptr); cudaFree(S->d_colidx); cudaFree(S->d_diag_pos); cudaFree(S->d_vals);
+  cudaFree(S->d_b); cudaFree(S->d_x); cudaFree(S->d_dir); cudaFree(S->d_e2t_pos); cudaFree(S->d_chunk_row);
+  cudaFree(S->d_edge_nodes); cudaFree(S->d_n2e_ptr); cudaFree(S->d_n2e_item); cudaFree(S->d_node_dir);
+  cudaFree(S->d_mat_blob);
+  delete S;
+}
+
+int efb_system_dims(const efb_system *sys_, int32_t *m, int64_t *nnz, int32_t *n_matrix, int32_t *n_rhs) {
+  const System *S = (const System *)sys_;
+  if (!S) return EFB_ERR_INVALID;
+  if (m) *m = S->m;
+  if (nnz) *nnz = S->nnz;
+  if (n_matrix) *n_matrix = S->n_matrix;
+  if (n_rhs) *n_rhs = S->n_rhs;
+  return EFB_OK;
+}
+
+int efb_system_get_pattern(const efb_system *sys_, int32_t *rowptr, int32_t *colidx) {
+  const System *S = (const System *)sys_;
+  if (!S) return EFB_ERR_INVALID;
+  if (rowptr) memcpy(rowptr, S->h_rowptr.data(), S->h_rowptr.size() * sizeof(int32_t));
+  if (colidx) memcpy(colidx, S->h_colidx.data(), S->h_colidx.size() * sizeof(int32_t));
+  return EFB_OK;
+}
+
+int efb_system_get_values(efb_system *sys_, int32_t f, double *vals) {
+  System *S = (System *)sys_;
+  if (!S || !vals || f < 0 || f >= S->n_matrix) return fail(S ? S->ctx : nullptr, EFB_ERR_INVALID, "efb_system_get_values: bad argument");
+  Ctx *c = S->ctx;
+  EFB_CUDA(c, cudaSetDevice(c->device));
+  EFB_CUDA(c, cudaMemcpyAsync(vals, S->d_vals + (size_t)f * S->nnz, (size_t)S->nnz * sizeof(c128), cudaMemcpyDeviceToHost, c->stream));
+  EFB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return EFB_OK;
+}
+
+int efb_system_set_values(efb_system *sys_, int32_t f, const double *vals) {
+  System *S = (System *)sys_;
+  if (!S || !vals || f < 0 || f >= S->n_matrix) return fail(S ? S->ctx : nullptr, EFB_ERR_INVALID, "efb_system_set_values: bad argument");
+  Ctx *c = S->ctx;
+  EFB_CUDA(c, cudaSetDevice(c->device));
+  EFB_CUDA(c, cudaMemcpyAsync(S->d_vals + (size_t)f * S->nnz, vals, (size_t)S->nnz * sizeof(c128), cudaMemcpyHostToDevice, c->stream));
+  EFB_CUDA(c, cudaStreamSynchronize(c->stream));
+  S->assembled = true;
+  return EFB_OK;
+}
+
+int efb_system_set_dirichlet(efb_system *sys_, const uint8_t *flags) {
+  System *S = (System *)sys_;
+  if (!S || !flags) return fail(S ? S->ctx : nullptr, EFB_ERR_INVALID, "efb_system_set_dirichlet: bad argument");
+  Ctx *c = S->ctx;
+  EFB_CUDA(c, cudaSetDevice(c->device));
+  EFB_CUDA(c, cudaMemcpyAsync(S->d_dir, flags, (size_t)S->m, cudaMemcpyHostToDevice, c->stream));
+  S->has_dir = true;
+  if (S->d_node_dir) {
+    EFB_CUDA(c, cudaMemsetAsync(S->d_node_dir, 0, (size_t)S->n_node, c->stream));
+    k_node_dir<<<(S->m + 255) / 256, 256, 0, c->stream>>>(S->d_edge_nodes, S->d_dir, S->m, S->d_node_dir);
+    EFB_CHECK_LAUNCH(c);
+  }
+  EFB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return EFB_OK;
+}
+
+int efb_system_set_gradient(efb_system *sys_, int32_t n_node, const int32_t *edge_nodes) {
+  System *S = (System *)sys_;
+  if (!S || !edge_nodes || n_node <= 0) return fail(S ? S->ctx : nullptr, EFB_ERR_INVALID, "efb_system_set_gradient: bad argument");
+  EFB_CUDA(S->ctx, cudaSetDevice(S->ctx->device));
+  int rc = system_set_gradient(S, n_node, edge_nodes);
+  if (rc) return rc;
+  if (S->has_dir) {
+    k_node_dir<<<(S->m + 255) / 256, 256, 0, S->ctx->stream>>>(S->d_edge_nodes, S->d_dir, S->m, S->d_node_dir);
+    EFB_CHECK_LAUNCH(S->ctx);
+    EFB_CUDA(S->ctx, cudaStreamSynchronize(S->ctx->stream));
+  }
+  return EFB_OK;
+}
+
+// ------------------------------------------------------------------ rhs / x
+static int vec_io(System *S, c128 *base, int32_t idx, double *out, const double *in, const char *who) {
+  if (!S || idx < 0 || idx >= S->n_sys || (!out && !in)) return fail(S ? S->ctx : nullptr, EFB_ERR_INVALID, "%s: bad argument", who);
+  Ctx *c = S->ctx;
+  EFB_CUDA(c, cudaSetDevice(c->device));
+  c128 *p = base + (size_t)idx * S->m;
+  if (out)
+    EFB_CUDA(c, cudaMemcpyAsync(out, p, (size_t)S->m * sizeof(c128), cudaMemcpyDeviceToHost, c->stream));
+  else
+    EFB_CUDA(c, cudaMemcpyAsync(p, in, (size_t)S->m * sizeof(c128), cudaMemcpyHostToDevice, c->stream));
+  EFB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return EFB_OK;
+}
+
+int efb_rhs_zero(efb_system *sys_, int32_t rhs) {
+  System *S = (System *)sys_;
+  if (!S || rhs < 0 || rhs >= S->n_sys) return fail(S ? S->ctx : nullptr, EFB_ERR_INVALID, "efb_rhs_zero: bad argument");
+  EFB_CUDA(S->ctx, cudaSetDevice(S->ctx->device));
+  EFB_CUDA(S->ctx, cudaMemsetAsync(S->d_b + (size_t)rhs * S->m, 0, (size_t)S->m * sizeof(c128), S->ctx->stream));
+  return EFB_OK;
+}
+int efb_rhs_set(efb_system *s, int32_t rhs, const double *b) { return vec_io((System *)s, s ? ((System *)s)->d_b : nullptr, rhs, nullptr, b, "efb_rhs_set"); }
+int efb_rhs_get(efb_system *s, int32_t rhs, double *b) { return vec_io((System *)s, s ? ((System *)s)->d_b : nullptr, rhs, b, nullptr, "efb_rhs_get"); }
+int efb_x_get(efb_system *s, int32_t rhs, double *x) { return vec_io((System *)s, s ? ((System *)s)->d_x : nullptr, rhs, x, nullptr, "efb_x_get"); }
+int efb_x_set(efb_system *s, int32_t rhs, const double *x) { return vec_io((System *)s, s ? ((System *)s)->d_x : nullptr, rhs, nullptr, x, "efb_x_set"); }
+
+}  // extern "C"

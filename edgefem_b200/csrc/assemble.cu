@@ -1,0 +1,735 @@
+// K1 volume assembly (row-gather, no atomics), K6 K/M combine, K2 boundary terms, K5 port
+// projections.  All FP64 / complex128 on the CUDA cores (nothing here is a dense
+// contraction).  Reference semantics: src/assemble_maxwell.cpp:114-347,
+// src/edge_basis.cpp:14-86, include/edgefem/materials/dispersive.hpp, src/sweep.cpp:82-172.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace efb {
+
+constexpr double C0 = 299792458.0;  // src/assemble_maxwell.cpp:39
+
+struct SlotMat {  // one per physical-tag slot, device copy of efb_materials
+  c128 eps_s, mu_s;
+  efb_model em, mm;
+  efb_pml pml;
+};
+
+// ---------------------------------------------------------------- dispersive models
+// include/edgefem/materials/dispersive.hpp:62-66 (Debye), :127-138 (Lorentz),
+// :182-194 (Drude), :251-273 (Drude-Lorentz).  e^{+jwt} convention: loss => Im eps < 0.
+__device__ c128 eval_model_eps(const efb_model &md, const efb_pole *__restrict__ poles, double w) {
+  c128 eps;
+  switch (md.kind) {
+    case EFB_MODEL_DEBYE:
+      eps = cdiv(cmake(md.p0 - md.p1, 0.0), cmake(1.0, w * md.p2));
+      eps.x += md.p1;
+      return eps;
+    case EFB_MODEL_LORENTZ:
+      eps = cmake(md.p0, 0.0);
+      break;
+    case EFB_MODEL_DRUDE:
+      if (w == 0.0) return cmake(-1e30, 0.0);
+      eps = cdiv(cmake(md.p0 * md.p0, 0.0), cmake(w * w, md.p1 * w));
+      return cmake(1.0 - eps.x, -eps.y);
+    case EFB_MODEL_DRUDE_LORENTZ:
+      eps = cmake(md.p0, 0.0);
+      if (w != 0.0) {
+        c128 d = cdiv(cmake(md.p1 * md.p1, 0.0), cmake(w * w, md.p2 * w));
+        eps = csub(eps, d);
+      } else {
+        eps = cmake(-1e30, 0.0);
+      }
+      break;
+    default:
+      return cmake(1.0, 0.0);
+  }
+  const double w2 = w * w;
+  for (int k = 0; k < md.n_poles; ++k) {
+    const efb_pole p = poles[md.pole_begin + k];
+    const double w02 = p.omega0 * p.omega0;
+    eps = cadd(eps, cdiv(cmake(p.delta_eps * w02, 0.0), cmake(w02 - w2, p.gamma * w)));
+  }
+  return eps;
+}
+
+// ---------------------------------------------------------------- element row
+struct V3 {
+  double x, y, z;
+};
+__device__ __forceinline__ V3 vsub(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ V3 vcross(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+__device__ __forceinline__ double vdot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ V3 vscale(double s, V3 a) { return {s * a.x, s * a.y, s * a.z}; }
+
+// Row `li` of the real 6x6 curl-curl (K) and mass (M) element matrices of one tet
+// (src/edge_basis.cpp:14-86): g = cols of B^-T, V = |det B|/6, c = 2 g_a x g_b,
+// K = V c_i.c_j, M = sum of four g.g terms weighted with V/10 (equal) or V/20.
+__device__ __forceinline__ void element_row(const V3 v[4], int li, double K[6], double M[6], V3 &centroid) {
+  const V3 b0 = vsub(v[0], v[3]), b1 = vsub(v[1], v[3]), b2 = vsub(v[2], v[3]);
+  const V3 c12 = vcross(b1, b2), c20 = vcross(b2, b0), c01 = vcross(b0, b1);
+  const double det = vdot(b0, c12);
+  const double inv = 1.0 / det;
+  V3 g[4];
+  g[0] = vscale(inv, c12);
+  g[1] = vscale(inv, c20);
+  g[2] = vscale(inv, c01);
+  g[3] = {-g[0].x - g[1].x - g[2].x, -g[0].y - g[1].y - g[2].y, -g[0].z - g[1].z - g[2].z};
+  const double V = fabs(det) / 6.0;
+  centroid = {(v[0].x + v[1].x + v[2].x + v[3].x) / 4.0, (v[0].y + v[1].y + v[2].y + v[3].y) / 4.0,
+              (v[0].z + v[1].z + v[2].z + v[3].z) / 4.0};
+  const int a = (li < 3) ? 0 : (li < 5 ? 1 : 2);
+  const int b = (li == 0) ? 1 : ((li == 1 || li == 3) ? 2 : 3);
+  const V3 ga = (a == 0) ? g[0] : (a == 1 ? g[1] : g[2]);
+  const V3 gb = (b == 1) ? g[1] : (b == 2 ? g[2] : g[3]);
+  const V3 ci = vscale(2.0, vcross(ga, gb));
+  double gad[4], gbd[4];
+#pragma unroll
+  for (int d = 0; d < 4; ++d) {
+    gad[d] = vdot(ga, g[d]);
+    gbd[d] = vdot(gb, g[d]);
+  }
+  const double Ieq = V / 10.0, Ine = V / 20.0;
+  constexpr int PA[6] = {0, 0, 0, 1, 1, 2}, PB[6] = {1, 2, 3, 2, 3, 3};
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    const int c = PA[j], d = PB[j];
+    const V3 cj = vscale(2.0, vcross(g[c], g[d]));
+    K[j] = V * vdot(ci, cj);
+    double term = 0.0;
+    term += gbd[d] * ((a == c) ? Ieq : Ine);
+    term -= gbd[c] * ((a == d) ? Ieq : Ine);
+    term -= gad[d] * ((b == c) ? Ieq : Ine);
+    term += gad[c] * ((b == d) ? Ieq : Ine);
+    M[j] = term;
+  }
+}
+
+// PML scalar stretch of one tet (src/assemble_maxwell.cpp:121-172)
+__device__ c128 pml_stretch(const efb_pml &pm, const double *__restrict__ bbox, V3 cen, double omega) {
+  if (omega == 0.0 || pm.kind == EFB_PML_NONE) return cmake(1.0, 0.0);
+  if (pm.kind == EFB_PML_UNIFORM) return cmake(1.0, pm.sigma[0] / omega);
+  const double cc[3] = {cen.x, cen.y, cen.z};
+  double im = 0.0;
+#pragma unroll
+  for (int ax = 0; ax < 3; ++ax) {
+    const double smax = pm.sigma[ax], th = pm.thickness[ax];
+    double sig = 0.0;
+    if (smax > 0.0 && th > 0.0) {
+      const double dmin = cc[ax] - bbox[ax], dmax = bbox[3 + ax] - cc[ax];
+      const double md = fmin(dmin, dmax);
+      double xi = 0.0;
+      if (md < th) xi = 1.0 - md / th;
+      if (pm.enforce_heuristics && xi > 0.0) xi = fmax(xi, 1e-3);
+      sig = smax * pow(xi, pm.grading_order);
+      if (pm.enforce_heuristics && sig < smax * 1e-3) sig = smax * 1e-3;
+      im += sig / omega;
+    }
+  }
+  return cmake(1.0, im / 3.0);  // mean of (1 + j sigma_ax / omega)
+}
+
+// ---------------------------------------------------------------- K1: volume assembly
+// grid (n_chunks, count).  One CTA owns a contiguous row chunk: every thread walks the
+// incident tets of its rows (ascending tet index => deterministic sums), recomputes the
+// needed element-matrix row and accumulates into shared memory; the chunk is then written
+// once, coalesced, with the Dirichlet mask applied.
+__global__ void __launch_bounds__(ASM_THREADS, 2)
+k_assemble_volume(const double4 *__restrict__ xyz, const int4 *__restrict__ tet_nodes,
+                  const uint8_t *__restrict__ tet_sign, const uint8_t *__restrict__ tet_slot,
+                  const int32_t *__restrict__ e2t_ptr, const int32_t *__restrict__ e2t_item,
+                  const uint16_t *__restrict__ e2t_pos, const int32_t *__restrict__ chunk_row,
+                  const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
+                  const uint8_t *__restrict__ dir, const SlotMat *__restrict__ slots,
+                  const efb_pole *__restrict__ poles, const double *__restrict__ slot_bbox,
+                  const double *__restrict__ omegas, int n_slots, int mode, int first, long long nnz,
+                  c128 *__restrict__ vals) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  c128 *acc = (c128 *)smem_raw;                                   // [ASM_CHUNK_NNZ]
+  c128 *s_kf = acc + ASM_CHUNK_NNZ;                               // [n_slots]
+  c128 *s_mf = s_kf + n_slots;                                    // [n_slots]
+  int32_t *s_rowptr = (int32_t *)(s_mf + n_slots);                // [ASM_CHUNK_ROWS+1]
+  uint8_t *s_pml = (uint8_t *)(s_rowptr + ASM_CHUNK_ROWS + 1);    // [n_slots]
+
+  const int chunk = blockIdx.x, fi = blockIdx.y;
+  const int r0 = chunk_row[chunk], r1 = chunk_row[chunk + 1];
+  const int base = rowptr[r0];
+  const int cnt = rowptr[r1] - base;
+  const double omega = omegas[fi];
+  const double k0 = omega / C0;
+  const double k0sq = k0 * k0;
+
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) acc[i] = cmake(0.0, 0.0);
+  for (int i = threadIdx.x; i <= r1 - r0; i += blockDim.x) s_rowptr[i] = rowptr[r0 + i] - base;
+  for (int s = threadIdx.x; s < n_slots; s += blockDim.x) {
+    const SlotMat sm = slots[s];
+    c128 eps = sm.eps_s, mu = sm.mu_s;
+    if (mode == 0) {
+      if (sm.em.kind != EFB_MODEL_NONE) eps = eval_model_eps(sm.em, poles, omega);
+      // every shipped model's eval_mu is the base-class 1.0 (dispersive.hpp:28-31)
+      if (sm.mm.kind != EFB_MODEL_NONE) mu = cmake(1.0, 0.0);
+    }
+    c128 kf, mf;
+    if (mode == 0) {
+      kf = cdiv(cmake(1.0, 0.0), mu);
+      mf = cscale(-k0sq, eps);
+    } else if (mode == 1) {
+      kf = cdiv(cmake(1.0, 0.0), mu);
+      mf = cmake(0.0, 0.0);
+    } else {
+      kf = cmake(0.0, 0.0);
+      mf = eps;
+    }
+    s_kf[s] = kf;
+    s_mf[s] = mf;
+    s_pml[s] = (mode == 0) ? (uint8_t)sm.pml.kind : (uint8_t)0;
+  }
+  __syncthreads();
+
+  for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
+    if (dir[r]) continue;  // Dirichlet row: identity, written below
+    c128 *arow = acc + s_rowptr[r - r0];
+    const int kb = e2t_ptr[r], ke = e2t_ptr[r + 1];
+    for (int k = kb; k < ke; ++k) {
+      const int item = e2t_item[k];
+      const int t = item >> 3, li = item & 7;
+      const int4 nd = __ldg(&tet_nodes[t]);
+      const unsigned sg = tet_sign[t];
+      const int slot = tet_slot[t];
+      const uint16_t *pp = e2t_pos + (size_t)k * 6;
+      // 6 x uint16 = 12 bytes, 4-byte aligned
+      const uint32_t p01 = *(const uint32_t *)(pp), p23 = *(const uint32_t *)(pp + 2), p45 = *(const uint32_t *)(pp + 4);
+      const int pos[6] = {(int)(p01 & 0xffff), (int)(p01 >> 16), (int)(p23 & 0xffff), (int)(p23 >> 16), (int)(p45 & 0xffff), (int)(p45 >> 16)};
+      V3 v[4];
+      {
+        const double4 q0 = xyz[nd.x], q1 = xyz[nd.y], q2 = xyz[nd.z], q3 = xyz[nd.w];
+        v[0] = {q0.x, q0.y, q0.z};
+        v[1] = {q1.x, q1.y, q1.z};
+        v[2] = {q2.x, q2.y, q2.z};
+        v[3] = {q3.x, q3.y, q3.z};
+      }
+      double K[6], M[6];
+      V3 cen;
+      element_row(v, li, K, M, cen);
+      c128 kf = s_kf[slot], mf = s_mf[slot];
+      if (s_pml[slot]) {
+        const c128 st = pml_stretch(slots[slot].pml, slot_bbox + slot * 6, cen, omega);
+        kf = cdiv(kf, st);
+        mf = cmul(mf, st);
+      }
+      const unsigned si = (sg >> li) & 1u;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const double sgn = (((sg >> j) & 1u) ^ si) ? -1.0 : 1.0;
+        const double kk = K[j] * sgn, mm = M[j] * sgn;
+        c128 a = arow[pos[j]];
+        a.x += kk * kf.x + mm * mf.x;
+        a.y += kk * kf.y + mm * mf.y;
+        arow[pos[j]] = a;
+      }
+    }
+  }
+  __syncthreads();
+
+  c128 *out = vals + (size_t)(first + fi) * (size_t)nnz + base;
+  const double diag_one = (mode == 2) ? 0.0 : 1.0;
+  const int nrow = r1 - r0;
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+    // local row of entry i: last lr with s_rowptr[lr] <= i
+    int lo = 0, hi = nrow;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (s_rowptr[mid] <= i) lo = mid; else hi = mid;
+    }
+    const int r = r0 + lo;
+    const int c = colidx[base + i];
+    c128 v = acc[i];
+    if (dir[r] | dir[c]) v = cmake(r == c ? diag_one : 0.0, 0.0);
+    out[i] = v;
+  }
+}
+
+size_t assemble_smem_bytes(int n_slots) {
+  return (size_t)ASM_CHUNK_NNZ * sizeof(c128) + 2 * (size_t)n_slots * sizeof(c128) + (ASM_CHUNK_ROWS + 1) * sizeof(int32_t) + (size_t)n_slots + 16;
+}
+
+// blob layout: [SlotMat x n_slots][efb_pole x n_poles][double omega x count]
+int assemble_launch(System *S, int first, int count, int mode) {
+  Ctx *c = S->ctx;
+  Mesh *M = S->mesh;
+  const int ns = M->n_slots;
+  const size_t off_poles = (size_t)ns * sizeof(SlotMat);
+  const size_t total = S->last_mat_blob.size();
+  const size_t off_om = total - (size_t)count * sizeof(double);
+  if (S->mat_blob_bytes < total) {
+    cudaFree(S->d_mat_blob);
+    S->d_mat_blob = nullptr;
+    unsigned char *p = nullptr;
+    int rc = dev_alloc(c, &p, total);
+    if (rc) return rc;
+    S->d_mat_blob = p;
+    S->mat_blob_bytes = total;
+  }
+  EFB_CUDA(c, cudaMemcpyAsync(S->d_mat_blob, S->last_mat_blob.data(), total, cudaMemcpyHostToDevice, c->stream));
+  const unsigned char *blob = (const unsigned char *)S->d_mat_blob;
+  const size_t smem = assemble_smem_bytes(ns);
+  EFB_CUDA(c, cudaFuncSetAttribute(k_assemble_volume, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)assemble_smem_bytes(MAX_SLOTS)));
+  dim3 grid((unsigned)S->n_chunks, (unsigned)count);
+  k_assemble_volume<<<grid, ASM_THREADS, smem, c->stream>>>(
+      M->d_xyz, M->d_tet_nodes, M->d_tet_sign, M->d_tet_slot, M->d_e2t_ptr, M->d_e2t_item, S->d_e2t_pos,
+      S->d_chunk_row, S->d_rowptr, S->d_colidx, S->d_dir, (const SlotMat *)blob, (const efb_pole *)(blob + off_poles),
+      M->d_slot_bbox, (const double *)(blob + off_om), ns, mode, first, (long long)S->nnz, S->d_vals);
+  EFB_CHECK_LAUNCH(c);
+  return EFB_OK;
+}
+
+// ---------------------------------------------------------------- small kernels
+__device__ __forceinline__ int csr_find(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx, int r, int c) {
+  int lo = rowptr[r], hi = rowptr[r + 1];
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const int v = colidx[mid];
+    if (v == c) return mid;
+    if (v < c) lo = mid + 1; else hi = mid;
+  }
+  return -1;
+}
+
+__device__ __forceinline__ void atomic_cadd(c128 *p, c128 v) {
+  atomicAdd(&p->x, v.x);
+  atomicAdd(&p->y, v.y);
+}
+
+__global__ void k_combine_km(c128 *__restrict__ vals, long long nnz, int dst_first, int count,
+                             const double *__restrict__ k0sq, int src_k, int src_m) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= nnz) return;
+  const c128 K = vals[(size_t)src_k * nnz + i], Mv = vals[(size_t)src_m * nnz + i];
+  for (int f = 0; f < count; ++f) {
+    const double q = k0sq[f];
+    vals[(size_t)(dst_first + f) * nnz + i] = cmake(K.x - q * Mv.x, K.y - q * Mv.y);
+  }
+}
+
+__global__ void k_add_diag(c128 *__restrict__ vals, long long nnz, int first, const int32_t *__restrict__ edges, int n,
+                           const c128 *__restrict__ coef, const int32_t *__restrict__ diag_pos,
+                           const uint8_t *__restrict__ dir, int32_t *flag) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x, f = blockIdx.y;
+  if (k >= n) return;
+  const int e = edges[k];
+  if (dir[e]) return;
+  const int p = diag_pos[e];
+  if (p < 0) {
+    atomicExch(flag, 1);
+    return;
+  }
+  atomic_cadd(&vals[(size_t)(first + f) * nnz + p], coef[f]);
+}
+
+__global__ void k_port_prepare(const int32_t *__restrict__ edges, c128 *w, int n, const uint8_t *__restrict__ dir, c128 *e_dense) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int e = edges[k];
+  c128 v = w[k];
+  if (dir[e]) v = cmake(0.0, 0.0);
+  w[k] = v;
+  e_dense[e] = v;
+}
+
+__global__ void k_ms_pos(const int32_t *__restrict__ rows, const int32_t *__restrict__ cols, long long n,
+                         const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx, int32_t *pos) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  pos[i] = csr_find(rowptr, colidx, rows[i], cols[i]);
+}
+
+__global__ void k_port_block(c128 *__restrict__ vals, long long nnz, int first, const int32_t *__restrict__ edges,
+                             const c128 *__restrict__ w, int n, const c128 *__restrict__ coef,
+                             const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
+                             const uint8_t *__restrict__ dir, int32_t *flag) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)n * n) return;
+  const int a = (int)(idx / n), b = (int)(idx % n);
+  const int ea = edges[a], eb = edges[b];
+  if (dir[ea] | dir[eb]) return;
+  const int p = csr_find(rowptr, colidx, ea, eb);
+  if (p < 0) {
+    atomicExch(flag, 1);
+    return;
+  }
+  const c128 wab = cmul(w[a], cconj(w[b]));
+  atomic_cadd(&vals[(size_t)(first + blockIdx.y) * nnz + p], cmul(coef[blockIdx.y], wab));
+}
+
+__global__ void k_port_mass(c128 *__restrict__ vals, long long nnz, int first, const int32_t *__restrict__ pos,
+                            const double *__restrict__ mv, long long n, const c128 *__restrict__ coef, int32_t *flag) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int p = pos[i];
+  if (p < 0) {
+    atomicExch(flag, 1);
+    return;
+  }
+  atomic_cadd(&vals[(size_t)(first + blockIdx.y) * nnz + p], cscale(mv[i], coef[blockIdx.y]));
+}
+
+__global__ void k_rhs_weights(c128 *b, const int32_t *__restrict__ edges, const c128 *__restrict__ w, int n, c128 coef,
+                              const uint8_t *__restrict__ dir) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int e = edges[k];
+  if (dir[e]) return;
+  atomic_cadd(&b[e], cmul(coef, w[k]));
+}
+
+__global__ void k_rhs_mass(c128 *b, const int32_t *__restrict__ rows, const int32_t *__restrict__ cols,
+                           const double *__restrict__ mv, long long n, const c128 *__restrict__ e_dense, c128 coef) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  atomic_cadd(&b[rows[i]], cmul(coef, cscale(mv[i], e_dense[cols[i]])));
+}
+
+// single-CTA deterministic reductions (ports have O(100) edges)
+__device__ c128 block_sum(c128 v) {
+  __shared__ c128 sh[32];
+  for (int o = 16; o > 0; o >>= 1) {
+    v.x += __shfl_down_sync(0xffffffffu, v.x, o);
+    v.y += __shfl_down_sync(0xffffffffu, v.y, o);
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[wid] = v;
+  __syncthreads();
+  c128 r = cmake(0.0, 0.0);
+  if (wid == 0) {
+    r = (lane < (blockDim.x + 31) / 32) ? sh[lane] : cmake(0.0, 0.0);
+    for (int o = 16; o > 0; o >>= 1) {
+      r.x += __shfl_down_sync(0xffffffffu, r.x, o);
+      r.y += __shfl_down_sync(0xffffffffu, r.y, o);
+    }
+  }
+  return r;  // valid in thread 0
+}
+
+__global__ void k_project_weights(const c128 *__restrict__ x, const int32_t *__restrict__ edges, const c128 *__restrict__ w,
+                                  int n, const uint8_t *__restrict__ dir, c128 *out) {
+  c128 acc = cmake(0.0, 0.0);
+  for (int k = threadIdx.x; k < n; k += blockDim.x) {
+    const int e = edges[k];
+    if (!dir[e]) acc = cadd(acc, cmulconj(w[k], x[e]));
+  }
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) *out = acc;
+}
+
+// out = sum conj(u[row]) * val * v[col]
+__global__ void k_bilinear_mass(const c128 *__restrict__ u, const c128 *__restrict__ v, const int32_t *__restrict__ rows,
+                                const int32_t *__restrict__ cols, const double *__restrict__ mv, long long n, c128 *out) {
+  c128 acc = cmake(0.0, 0.0);
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) acc = cadd(acc, cmulconj(u[rows[i]], cscale(mv[i], v[cols[i]])));
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) *out = acc;
+}
+
+__global__ void k_port_scale(c128 *w, int n, c128 *e_dense, const int32_t *__restrict__ edges, const c128 *__restrict__ nsq) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const double ns = nsq->x;
+  if (!(ns > 1e-30)) return;
+  const double s = 1.0 / sqrt(ns);
+  const c128 v = cscale(s, w[k]);
+  w[k] = v;
+  e_dense[edges[k]] = v;
+}
+
+__global__ void k_x_recover(c128 *x, const int32_t *__restrict__ dst, const int32_t *__restrict__ src,
+                            const c128 *__restrict__ phase, int n) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  x[dst[k]] = cmul(phase[k], x[src[k]]);
+}
+
+static int check_flag(System *S, const char *who) {
+  Ctx *c = S->ctx;
+  int32_t h = 0;
+  EFB_CUDA(c, cudaMemcpyAsync(&h, S->d_flag, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+  EFB_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (h) {
+    EFB_CUDA(c, cudaMemsetAsync(S->d_flag, 0, sizeof h, c->stream));
+    return fail(c, EFB_ERR_STATE, "%s: an entry is missing from the CSR pattern (pass it as an extra entry to efb_system_create)", who);
+  }
+  return EFB_OK;
+}
+
+// uploads `n` c128 to a temporary device buffer
+struct TmpBuf {
+  void *p = nullptr;
+  ~TmpBuf() { cudaFree(p); }
+};
+
+}  // namespace efb
+
+using namespace efb;
+
+extern "C" {
+
+int efb_assemble_volume(efb_system *sys_, int32_t first, int32_t count, const double *omega, const efb_materials *mat, int32_t mode) {
+  System *S = (System *)sys_;
+  if (!S) return fail(nullptr, EFB_ERR_INVALID, "efb_assemble_volume: NULL system");
+  Ctx *c = S->ctx;
+  if (!S->mesh) return fail(c, EFB_ERR_STATE, "efb_assemble_volume: system was not created from a mesh");
+  Mesh *M = S->mesh;
+  if (!omega || !mat || first < 0 || count <= 0 || first + count > S->n_matrix || mode < 0 || mode > 2)
+    return fail(c, EFB_ERR_INVALID, "efb_assemble_volume: bad arguments");
+  if (mat->n_slots != M->n_slots || !mat->eps_static_c128 || !mat->mu_static_c128 || (mat->n_poles > 0 && !mat->poles))
+    return fail(c, EFB_ERR_INVALID, "efb_assemble_volume: material table must have one entry per mesh slot (%d)", M->n_slots);
+  EFB_CUDA(c, cudaSetDevice(c->device));
+  const int ns = M->n_slots;
+  std::vector<uint8_t> blob((size_t)ns * sizeof(SlotMat) + (size_t)std::max(0, mat->n_poles) * sizeof(efb_pole) + (size_t)count * sizeof(double));
+  SlotMat *sm = (SlotMat *)blob.data();
+  for (int s = 0; s < ns; ++s) {
+    memset(&sm[s], 0, sizeof(SlotMat));
+    sm[s].eps_s = cmake(mat->eps_static_c128[2 * s], mat->eps_static_c128[2 * s + 1]);
+    sm[s].mu_s = cmake(mat->mu_static_c128[2 * s], mat->mu_static_c128[2 * s + 1]);
+    if (mat->eps_models) sm[s].em = mat->eps_models[s];
+    if (mat->mu_models) sm[s].mm = mat->mu_models[s];
+    if (mat->pml) sm[s].pml = mat->pml[s];
+    for (const efb_model *md : {&sm[s].em, &sm[s].mm})
+      if (md->n_poles < 0 || md->pole_begin < 0 || md->pole_begin + md->n_poles > std::max(0, mat->n_poles))
+        return fail(c, EFB_ERR_INVALID, "efb_assemble_volume: pole range of slot %d out of bounds", s);
+  }
+  if (mat->n_poles > 0) memcpy(blob.data() + (size_t)ns * sizeof(SlotMat), mat->poles, (size_t)mat->n_poles * sizeof(efb_pole));
+  memcpy(blob.data() + blob.size() - (size_t)count * sizeof(double), omega, (size_t)count * sizeof(double));
+  S->last_mat_blob.swap(blob);
+  S->last_omega.assign(omega, omega + count);
+  S->last_mode = mode;
+  Timed tm(c);
+  int rc = assemble_launch(S, first, count, mode);
+  if (rc) return rc;
+  EFB_CUDA(c, cudaMemsetAsync(S->d_b + (size_t)first * S->n_rhs * S->m, 0, (size_t)count * S->n_rhs * S->m * sizeof(c128), c->stream));
+  S->assembled = true;
+  return EFB_OK;
+}
+
+int efb_combine_km(efb_system *sys_, int32_t dst_first, int32_t count, const double *k0sq, int32_t src_k, int32_t src_m) {
+  System *S = (System *)sys_;
+  if (!S) return fail(nullptr, EFB_ERR_INVALID, "efb_combine_km: NULL system");
+  Ctx *c = S->ctx;
+  if (!k0sq || count <= 0 || dst_first < 0 || dst_first + count > S->n_matrix || src_k < 0 || src_k >= S->n_matrix || src_m < 0 ||
+      src_m >= S->n_matrix || (src_k >= dst_first && src_k < dst_first + count) || (src_m >= dst_first && src_m < dst_first + count))
+    return fail(c, EFB_ERR_INVALID, "efb_combine_km: bad arguments (sources must lie outside the destination range)");
+  EFB_CUDA(c, cudaSetDevice(c->device));
+  TmpBuf tb;
+  EFB_CUDA(c, cudaMalloc(&tb.p, (size_t)count * sizeof(double)));
+  EFB_CUDA(c, cudaMemcpyAsync(tb.p, k0sq, (size_t)count * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  {
+    Timed tm(c);
+    k_combine_km<<<(unsigned)((S->nnz + 255) / 256), 256, 0, c->stream>>>(S->d_vals, (long long)S->nnz, dst_first, count, (const double *)tb.p, src_k, src_m);
+    EFB_CHECK_LAUNCH(c);
+    EFB_CUDA(c, cudaMemsetAsync(S->d_b + (size_t)dst_first * S->n_rhs * S->m, 0, (size_t)count * S->n_rhs * S->m * sizeof(c128), c->stream));
+  }
+  EFB_CUDA(c, cudaStreamSynchronize(c->stream));
+  S->assembled = true;
+  return EFB_OK;
+}
+
+int efb_add_diag(efb_system *sys_, int32_t first, int32_t count, int32_t n, const int32_t *edges, const double *coef) {
+  System *S = (System *)sys_;
+  if (!S) return fail(nullptr, EFB_ERR_INVALID, "efb_add_diag: NULL system");
+  Ctx *c = S->ctx;
+  if (n < 0 || (n > 0 && !edges) || !coef || first < 0 || count <= 0 || first + count > S->n_matrix)
+    return fail(c, EFB_ERR_INVALID, "efb_add_diag: bad arguments");
+  if (n == 0) return EFB_OK;
+  for (int k = 0; k < n; ++k)
+    if (edges[k] < 0 || edges[k] >= S->m) return fail(c, EFB_ERR_INVALID, "efb_add_diag: edge out of range");
+  EFB_CUDA(c, cudaSetDevice(c->device));
+  TmpBuf te, tc;
+  EFB_CUDA(c, cudaMalloc(&te.p, (size_t)n * sizeof(int32_t)));
+  EFB_CUDA(c, cudaMalloc(&tc.p, (size_t)count * sizeof(c128)));
+  EFB_CUDA(c, cudaMemcpyAsync(te.p, edges, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  EFB_CUDA(c, cudaMemcpyAsync(tc.p, coef, (size_t)count * sizeof(c128), cudaMemcpyHostToDevice, c->stream));
+  dim3 grid((unsigned)((n + 127) / 128), (unsigned)count);
+  k_add_diag<<<grid, 128, 0, c->stream>>>(S->d_vals, (long long)S->nnz, first, (const int32_t *)te.p, n, (const c128 *)tc.p, S->d_diag_pos, S->d_dir, S->d_flag);
+  EFB_CHECK_LAUNCH(c);
+  return check_flag(S, "efb_add_diag");
+}
+
+// ------------------------------------------------------------------ ports
+int efb_port_create(efb_system *sys_, int32_t n_edges, const int32_t *edges, const double *weights, int64_t n_ms,
+                    const int32_t *ms_rows, const int32_t *ms_cols, const double *ms_vals, efb_port **out) {
+  System *S = (System *)sys_;
+  if (!S || !out) return fail(S ? S->ctx : nullptr, EFB_ERR_INVALID, "efb_port_create: NULL argument");
+  Ctx *c = S->ctx;
+  *out = nullptr;
+  if (n_edges <= 0 || !edges || !weights || n_ms < 0 || (n_ms > 0 && (!ms_rows || !ms_cols || !ms_vals)))
+    return fail(c, EFB_ERR_INVALID, "efb_port_create: bad arguments");
+  for (int k = 0; k < n_edges; ++k)
+    if (edges[k] < 0 || edges[k] >= S->m) return fail(c, EFB_ERR_INVALID, "efb_port_create: edge out of range");
+  for (int64_t i = 0; i < n_ms; ++i)
+    if (ms_rows[i] < 0 || ms_rows[i] >= S->m || ms_cols[i] < 0 || ms_cols[i] >= S->m)
+      return fail(c, EFB_ERR_INVALID, "efb_port_create: M_s entry out of range");
+  EFB_CUDA(c, cudaSetDevice(c->device));
+  Port *P = new Port();
+  P->sys = S;
+  P->n_edges = n_edges;
+  P->n_ms = n_ms;
+  int rc;
+  if ((rc = dev_upload(c, &P->d_edges, edges, (size_t)n_edges))) return rc;
+  if ((rc = dev_upload(c, &P->d_w, (const c128 *)weights, (size_t)n_edges))) return rc;
+  if ((rc = dev_upload(c, &P->d_ms_row, ms_rows, (size_t)n_ms))) return rc;
+  if ((rc = dev_upload(c, &P->d_ms_col, ms_cols, (size_t)n_ms))) return rc;
+  if ((rc = dev_upload(c, &P->d_ms_val, ms_vals, (size_t)n_ms))) return rc;
+  if ((rc = dev_alloc(c, &P->d_ms_pos, (size_t)n_ms))) return rc;
+  if ((rc = dev_alloc(c, &P->d_e, (size_t)S->m))) return rc;
+  if ((rc = dev_alloc(c, &P->d_tmp, (size_t)4))) return rc;
+  EFB_CUDA(c, cudaMemsetAsync(P->d_e, 0, (size_t)S->m * sizeof(c128), c->stream));
+  k_port_prepare<<<(n_edges + 127) / 128, 128, 0, c->stream>>>(P->d_edges, P->d_w, n_edges, S->d_dir, P->d_e);
+  EFB_CHECK_LAUNCH(c);
+  if (n_ms > 0) {
+    k_ms_pos<<<(unsigned)((n_ms + 127) / 128), 128, 0, c->stream>>>(P->d_ms_row, P->d_ms_col, (long long)n_ms, S->d_rowptr, S->d_colidx, P->d_ms_pos);
+    EFB_CHECK_LAUNCH(c);
+  }
+  EFB_CUDA(c, cudaStreamSynchronize(c->stream));
+  *out = (efb_port *)P;
+  return EFB_OK;
+}
+
+void efb_port_destroy(efb_port *port_) {
+  Port *P = (Port *)port_;
+  if (!P) return;
+  cudaSetDevice(P->sys->ctx->device);
+  cudaFree(P->d_edges); cudaFree(P->d_w); cudaFree(P->d_ms_row); cudaFree(P->d_ms_col); cudaFree(P->d_ms_pos);
+  cudaFree(P->d_ms_val); cudaFree(P->d_e); cudaFree(P->d_tmp); cudaFree(P->d_blk_pos);
+  delete P;
+}
+
+int efb_port_normalize_mass(efb_port *port_, double *norm_sq) {
+  Port *P = (Port *)port_;
+  if (!P) return fail(nullptr, EFB_ERR_INVALID, "efb_port_normalize_mass: NULL port");
+  System *S = P->sys;
+  Ctx *c = S->ctx;
+  EFB_CUDA(c, cudaSetDevice(c->device));
+  k_bilinear_mass<<<1, 256, 0, c->stream>>>(P->d_e, P->d_e, P->d_ms_row, P->d_ms_col, P->d_ms_val, (long long)P->n_ms, P->d_tmp);
+  EFB_CHECK_LAUNCH(c);
+  k_port_scale<<<(P->n_edges + 127) / 128, 128, 0, c->stream>>>(P->d_w, P->n_edges, P->d_e, P->d_edges, P->d_tmp);
+  EFB_CHECK_LAUNCH(c);
+  c128 h;
+  EFB_CUDA(c, cudaMemcpyAsync(&h, P->d_tmp, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+  EFB_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (norm_sq) *norm_sq = h.x;
+  return EFB_OK;
+}
+
+static int upload_coef(Ctx *c, TmpBuf &tb, const double *coef, int count) {
+  EFB_CUDA(c, cudaMalloc(&tb.p, (size_t)count * sizeof(c128)));
+  EFB_CUDA(c, cudaMemcpyAsync(tb.p, coef, (size_t)count * sizeof(c128), cudaMemcpyHostToDevice, c->stream));
+  return EFB_OK;
+}
+
+int efb_port_add_block(efb_system *sys_, efb_port *port_, int32_t first, int32_t count, const double *coef) {
+  System *S = (System *)sys_;
+  Port *P = (Port *)port_;
+  if (!S || !P || P->sys != S || !coef || first < 0 || count <= 0 || first + count > S->n_matrix)
+    return fail(S ? S->ctx : nullptr, EFB_ERR_INVALID, "efb_port_add_block: bad arguments");
+  Ctx *c = S->ctx;
+  EFB_CUDA(c, cudaSetDevice(c->device));
+  TmpBuf tc;
+  int rc = upload_coef(c, tc, coef, count);
+  if (rc) return rc;
+  const long long nn = (long long)P->n_edges * P->n_edges;
+  dim3 grid((unsigned)((nn + 127) / 128), (unsigned)count);
+  k_port_block<<<grid, 128, 0, c->stream>>>(S->d_vals, (long long)S->nnz, first, P->d_edges, P->d_w, P->n_edges, (const c128 *)tc.p, S->d_rowptr, S->d_colidx, S->d_dir, S->d_flag);
+  EFB_CHECK_LAUNCH(c);
+  return check_flag(S, "efb_port_add_block");
+}
+
+int efb_port_add_mass(efb_system *sys_, efb_port *port_, int32_t first, int32_t count, const double *coef) {
+  System *S = (System *)sys_;
+  Port *P = (Port *)port_;
+  if (!S || !P || P->sys != S || !coef || first < 0 || count <= 0 || first + count > S->n_matrix)
+    return fail(S ? S->ctx : nullptr, EFB_ERR_INVALID, "efb_port_add_mass: bad arguments");
+  Ctx *c = S->ctx;
+  if (P->n_ms == 0) return EFB_OK;
+  EFB_CUDA(c, cudaSetDevice(c->device));
+  TmpBuf tc;
+  int rc = upload_coef(c, tc, coef, count);
+  if (rc) return rc;
+  dim3 grid((unsigned)((P->n_ms + 127) / 128), (unsigned)count);
+  k_port_mass<<<grid, 128, 0, c->stream>>>(S->d_vals, (long long)S->nnz, first, P->d_ms_pos, P->d_ms_val, (long long)P->n_ms, (const c128 *)tc.p, S->d_flag);
+  EFB_CHECK_LAUNCH(c);
+  return check_flag(S, "efb_port_add_mass");
+}
+
+int efb_port_rhs_weights(efb_system *sys_, efb_port *port_, int32_t rhs, const double *coef) {
+  System *S = (System *)sys_;
+  Port *P = (Port *)port_;
+  if (!S || !P || P->sys != S || !coef || rhs < 0 || rhs >= S->n_sys) return fail(S ? S->ctx : nullptr, EFB_ERR_INVALID, "efb_port_rhs_weights: bad arguments");
+  Ctx *c = S->ctx;
+  EFB_CUDA(c, cudaSetDevice(c->device));
+  k_rhs_weights<<<(P->n_edges + 127) / 128, 128, 0, c->stream>>>(S->d_b + (size_t)rhs * S->m, P->d_edges, P->d_w, P->n_edges, cmake(coef[0], coef[1]), S->d_dir);
+  EFB_CHECK_LAUNCH(c);
+  return EFB_OK;
+}
+
+int efb_port_rhs_mass(efb_system *sys_, efb_port *port_, int32_t rhs, const double *coef) {
+  System *S = (System *)sys_;
+  Port *P = (Port *)port_;
+  if (!S || !P || P->sys != S || !coef || rhs < 0 || rhs >= S->n_sys) return fail(S ? S->ctx : nullptr, EFB_ERR_INVALID, "efb_port_rhs_mass: bad arguments");
+  Ctx *c = S->ctx;
+  if (P->n_ms == 0) return EFB_OK;
+  EFB_CUDA(c, cudaSetDevice(c->device));
+  k_rhs_mass<<<(unsigned)((P->n_ms + 127) / 128), 128, 0, c->stream>>>(S->d_b + (size_t)rhs * S->m, P->d_ms_row, P->d_ms_col, P->d_ms_val, (long long)P->n_ms, P->d_e, cmake(coef[0], coef[1]));
+  EFB_CHECK_LAUNCH(c);
+  return EFB_OK;
+}
+
+int efb_port_project_weights(efb_system *sys_, efb_port *port_, int32_t rhs, double *v) {
+  System *S = (System *)sys_;
+  Port *P = (Port *)port_;
+  if (!S || !P || P->sys != S || !v || rhs < 0 || rhs >= S->n_sys) return fail(S ? S->ctx : nullptr, EFB_ERR_INVALID, "efb_port_project_weights: bad arguments");
+  Ctx *c = S->ctx;
+  EFB_CUDA(c, cudaSetDevice(c->device));
+  k_project_weights<<<1, 256, 0, c->stream>>>(S->d_x + (size_t)rhs * S->m, P->d_edges, P->d_w, P->n_edges, S->d_dir, P->d_tmp + 1);
+  EFB_CHECK_LAUNCH(c);
+  EFB_CUDA(c, cudaMemcpyAsync(v, P->d_tmp + 1, sizeof(c128), cudaMemcpyDeviceToHost, c->stream));
+  EFB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return EFB_OK;
+}
+
+int efb_port_project_mass(efb_system *sys_, efb_port *port_, int32_t rhs, double *v) {
+  System *S = (System *)sys_;
+  Port *P = (Port *)port_;
+  if (!S || !P || P->sys != S || !v || rhs < 0 || rhs >= S->n_sys) return fail(S ? S->ctx : nullptr, EFB_ERR_INVALID, "efb_port_project_mass: bad arguments");
+  Ctx *c = S->ctx;
+  EFB_CUDA(c, cudaSetDevice(c->device));
+  k_bilinear_mass<<<1, 256, 0, c->stream>>>(P->d_e, S->d_x + (size_t)rhs * S->m, P->d_ms_row, P->d_ms_col, P->d_ms_val, (long long)P->n_ms, P->d_tmp + 2);
+  EFB_CHECK_LAUNCH(c);
+  EFB_CUDA(c, cudaMemcpyAsync(v, P->d_tmp + 2, sizeof(c128), cudaMemcpyDeviceToHost, c->stream));
+  EFB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return EFB_OK;
+}
+
+int efb_x_recover(efb_system *sys_, int32_t rhs, int32_t n, const int32_t *dst, const int32_t *src, const double *phase) {
+  System *S = (System *)sys_;
+  if (!S || rhs < 0 || rhs >= S->n_sys || n < 0 || (n > 0 && (!dst || !src || !phase)))
+    return fail(S ? S->ctx : nullptr, EFB_ERR_INVALID, "efb_x_recover: bad arguments");
+  if (n == 0) return EFB_OK;
+  Ctx *c = S->ctx;
+  for (int k = 0; k < n; ++k)
+    if (dst[k] < 0 || dst[k] >= S->m || src[k] < 0 || src[k] >= S->m) return fail(c, EFB_ERR_INVALID, "efb_x_recover: index out of range");
+  EFB_CUDA(c, cudaSetDevice(c->device));
+  TmpBuf td, ts, tp;
+  EFB_CUDA(c, cudaMalloc(&td.p, (size_t)n * 4));
+  EFB_CUDA(c, cudaMalloc(&ts.p, (size_t)n * 4));
+  EFB_CUDA(c, cudaMalloc(&tp.p, (size_t)n * 16));
+  EFB_CUDA(c, cudaMemcpyAsync(td.p, dst, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+  EFB_CUDA(c, cudaMemcpyAsync(ts.p, src, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+  EFB_CUDA(c, cudaMemcpyAsync(tp.p, phase, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
+  k_x_recover<<<(n + 127) / 128, 128, 0, c->stream>>>(S->d_x + (size_t)rhs * S->m, (const int32_t *)td.p, (const int32_t *)ts.p, (const c128 *)tp.p, n);
+  EFB_CHECK_LAUNCH(c);
+  EFB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return EFB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,196 @@
+// Shared internals of libedgefem_b200 (sm_100a only).  Not part of the public ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "edgefem_b200.h"
+
+namespace efb {
+
+typedef double2 c128;  // (re, im)
+
+// ------------------------------------------------------------------ complex helpers
+__host__ __device__ __forceinline__ c128 cmake(double re, double im) { return make_double2(re, im); }
+__host__ __device__ __forceinline__ c128 cadd(c128 a, c128 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__host__ __device__ __forceinline__ c128 csub(c128 a, c128 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__host__ __device__ __forceinline__ c128 cmul(c128 a, c128 b) {
+  return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__host__ __device__ __forceinline__ c128 cmulconj(c128 a, c128 b) {  // conj(a) * b
+  return make_double2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x);
+}
+__host__ __device__ __forceinline__ c128 cscale(double s, c128 a) { return make_double2(s * a.x, s * a.y); }
+__host__ __device__ __forceinline__ c128 cconj(c128 a) { return make_double2(a.x, -a.y); }
+__host__ __device__ __forceinline__ c128 cneg(c128 a) { return make_double2(-a.x, -a.y); }
+__host__ __device__ __forceinline__ double cabs2(c128 a) { return a.x * a.x + a.y * a.y; }
+// Smith's algorithm (what std::complex<double> division does without -ffast-math)
+__host__ __device__ __forceinline__ c128 cdiv(c128 a, c128 b) {
+  if (fabs(b.x) >= fabs(b.y)) {
+    double r = b.y / b.x, den = b.x + b.y * r;
+    return make_double2((a.x + a.y * r) / den, (a.y - a.x * r) / den);
+  } else {
+    double r = b.x / b.y, den = b.x * r + b.y;
+    return make_double2((a.x * r + a.y) / den, (a.y * r - a.x) / den);
+  }
+}
+__host__ __device__ __forceinline__ c128 cfma(c128 a, c128 b, c128 acc) {  // acc + a*b
+  acc.x = fma(a.x, b.x, acc.x);
+  acc.x = fma(-a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y);
+  acc.y = fma(a.y, b.x, acc.y);
+  return acc;
+}
+
+// ------------------------------------------------------------------ limits
+constexpr int ASM_CHUNK_NNZ = 6144;   // accumulators per assembly CTA (96 KB of c128)
+constexpr int ASM_CHUNK_ROWS = 1024;  // rows per assembly CTA (rowptr slice in smem)
+constexpr int ASM_THREADS = 384;
+constexpr int MAX_SLOTS = 256;        // distinct physical tags
+constexpr int NSCAL = 16;             // per-system device scalars (c128)
+constexpr int RED_MAX_BLOCKS = 1184;  // 148 SMs x 8
+
+// ------------------------------------------------------------------ handles
+struct Ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool ev_valid = false;
+  int64_t launches = 0;
+  int sm_count = 148;
+  std::string err;
+};
+
+struct Mesh {
+  Ctx *ctx = nullptr;
+  int n_node = 0, n_tet = 0, m = 0, n_slots = 0;
+  std::vector<int32_t> slot_tags;
+  // host copies needed to build per-system maps
+  std::vector<int32_t> h_tet_edges;  // [6*n_tet]
+  std::vector<int32_t> h_e2t_ptr;    // [m+1]
+  std::vector<int32_t> h_e2t_item;   // [6*n_tet]  tet<<3 | local
+  std::vector<int32_t> h_edge_nodes; // [2*m]
+  // device
+  double4 *d_xyz = nullptr;          // [n_node] (x,y,z,0)
+  int4 *d_tet_nodes = nullptr;       // [n_tet]
+  uint8_t *d_tet_sign = nullptr;     // [n_tet] bit k set => orient[k] == -1
+  uint8_t *d_tet_slot = nullptr;     // [n_tet]
+  int32_t *d_e2t_ptr = nullptr;      // [m+1]
+  int32_t *d_e2t_item = nullptr;     // [6*n_tet]
+  double *d_slot_bbox = nullptr;     // [n_slots*6] min xyz, max xyz over the slot's tets
+};
+
+struct Port;
+
+struct System {
+  Ctx *ctx = nullptr;
+  Mesh *mesh = nullptr;  // may be null (generic CSR system)
+  int m = 0, n_matrix = 0, n_rhs = 0, n_sys = 0, n_node = 0;
+  int64_t nnz = 0;
+  std::vector<int32_t> h_rowptr, h_colidx;
+  int32_t *d_rowptr = nullptr, *d_colidx = nullptr, *d_diag_pos = nullptr;
+  c128 *d_vals = nullptr;      // [n_matrix][nnz]
+  c128 *d_b = nullptr;         // [n_sys][m]
+  c128 *d_x = nullptr;         // [n_sys][m]
+  uint8_t *d_dir = nullptr;    // [m] Dirichlet flags
+  bool has_dir = false;
+  // assembly maps (mesh-born systems)
+  uint16_t *d_e2t_pos = nullptr;   // [6*n_tet*6] column offsets inside the row
+  int32_t *d_chunk_row = nullptr;  // [n_chunks+1]
+  int n_chunks = 0;
+  // gradient (aux preconditioner)
+  int2 *d_edge_nodes = nullptr;    // [m]
+  int32_t *d_n2e_ptr = nullptr;    // [n_node+1]
+  int32_t *d_n2e_item = nullptr;   // [2m]  edge<<1 | (1 if node is n1 (head, +1) else 0 (tail, -1))
+  uint8_t *d_node_dir = nullptr;   // [n_node] node touches a Dirichlet edge
+  // solver workspace (lazy)
+  c128 *d_work = nullptr;      // [n_vec][n_sys][m]
+  int n_work_vec = 0;
+  c128 *d_dinv = nullptr;      // [n_matrix][m]
+  c128 *d_linv = nullptr;      // [n_matrix][n_node]
+  c128 *d_w = nullptr;         // [n_sys][n_node]
+  c128 *d_scal = nullptr;      // [n_sys][NSCAL]
+  double *d_partial = nullptr; // [n_sys][RED_MAX_BLOCKS][4]
+  unsigned *d_counter = nullptr; // [n_sys]
+  int32_t *d_state = nullptr;  // [n_sys][4]: active, iters, flag, pad
+  int32_t *d_flag = nullptr;   // [1] device error flag (entry missing from the pattern)
+  // last assembly inputs (for efb_bench_kernel which=3)
+  std::vector<double> last_omega;
+  bool assembled = false;
+  // materials scratch
+  void *d_mat_blob = nullptr;
+  size_t mat_blob_bytes = 0;
+  std::vector<uint8_t> last_mat_blob;
+  int last_mode = 0;
+};
+
+struct Port {
+  System *sys = nullptr;
+  int n_edges = 0;
+  int64_t n_ms = 0;
+  int32_t *d_edges = nullptr;
+  c128 *d_w = nullptr;        // weights, zero on Dirichlet edges
+  int32_t *d_ms_row = nullptr, *d_ms_col = nullptr, *d_ms_pos = nullptr;  // pos in the CSR pattern (-1: absent)
+  double *d_ms_val = nullptr;
+  c128 *d_e = nullptr;        // [m] dense port vector (weights scattered)
+  c128 *d_tmp = nullptr;      // [m] M_s * v scratch
+  int32_t *d_blk_pos = nullptr; // [n_edges*n_edges] CSR positions of the dense block (-1 absent)
+};
+
+// ------------------------------------------------------------------ error handling
+void set_global_error(const std::string &s);
+int fail(Ctx *ctx, int code, const char *fmt, ...);
+
+#define EFB_CUDA(ctx, expr)                                                              \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess)                                                               \
+      return ::efb::fail((ctx), EFB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,            \
+                         cudaGetErrorString(_e), __FILE__, __LINE__);                    \
+  } while (0)
+
+#define EFB_CHECK_LAUNCH(ctx)                                                            \
+  do {                                                                                   \
+    (ctx)->launches++;                                                                   \
+    cudaError_t _e = cudaGetLastError();                                                 \
+    if (_e != cudaSuccess)                                                               \
+      return ::efb::fail((ctx), EFB_ERR_CUDA, "kernel launch failed: %s (%s:%d)",        \
+                         cudaGetErrorString(_e), __FILE__, __LINE__);                    \
+  } while (0)
+
+template <typename T>
+int dev_alloc(Ctx *ctx, T **p, size_t n) {
+  *p = nullptr;
+  if (n == 0) n = 1;
+  cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
+  if (e != cudaSuccess)
+    return fail(ctx, e == cudaErrorMemoryAllocation ? EFB_ERR_NOMEM : EFB_ERR_CUDA,
+                "cudaMalloc(%zu bytes) failed: %s", n * sizeof(T), cudaGetErrorString(e));
+  return EFB_OK;
+}
+template <typename T>
+int dev_upload(Ctx *ctx, T **p, const T *h, size_t n) {
+  int rc = dev_alloc(ctx, p, n);
+  if (rc) return rc;
+  if (n) EFB_CUDA(ctx, cudaMemcpyAsync(*p, h, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  return EFB_OK;
+}
+
+struct Timed {  // records CUDA events around a compute call on the ctx stream
+  Ctx *c;
+  explicit Timed(Ctx *ctx) : c(ctx) { cudaEventRecord(c->ev0, c->stream); }
+  ~Timed() {
+    cudaEventRecord(c->ev1, c->stream);
+    c->ev_valid = true;
+  }
+};
+
+// internal entry points shared across translation units
+int solver_free(System *s);
+int assemble_launch(System *s, int first, int count, int mode);
+
+}  // namespace efb

@@ -1,0 +1,820 @@
+// K3 CSR complex128 SpMV (batched: many matrices on one pattern, several right-hand sides per
+// matrix) and K4 fused Krylov phases: COCG (complex symmetric A) and BiCGSTAB (general A) with
+// Jacobi or Jacobi + nodal gradient-space ("auxiliary space", Hiptmair) preconditioning.
+// Replaces Eigen's BiCGSTAB/IncompleteLUT/SparseLU behind solve_linear (src/solver.cpp:35-193);
+// the contract kept is SolveResult's (iterations, TRUE relative residual, converged).
+// Reductions are deterministic: per-block partials + last-block finalisation in fixed order;
+// scalars (alpha, beta, omega, rho) never leave the device inside the iteration loop.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace efb {
+
+enum Scal { S_RHO0 = 0, S_RHO1 = 1, S_PQ = 2, S_RR = 3, S_BB = 4, S_R0V = 5, S_TS = 6, S_TT = 7, S_ALPHA = 8, S_OMEGA = 9 };
+enum State { ST_ACTIVE = 0, ST_ITERS = 1, ST_CONV = 2, ST_REC = 3 };
+enum Vecs { V_R = 0, V_P = 1, V_Q = 2, V_Z = 3, V_R0 = 4, V_T = 5, V_Y = 6, V_NUM = 7 };
+
+constexpr int VEC_THREADS = 256;
+
+// ---------------------------------------------------------------- reductions
+template <int NV>
+__device__ bool reduce_and_ticket(double (&v)[NV], double *partial_sys, unsigned *counter_sys, double (&tot)[NV]) {
+  __shared__ double sh[4][32];
+  __shared__ int s_last;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double a = v[k];
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
+    if (lane == 0) sh[k][wid] = a;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      double a = 0.0;
+      for (int w = 0; w < nw; ++w) a += sh[k][w];
+      partial_sys[blockIdx.x * 4 + k] = a;
+    }
+    __threadfence();
+    const unsigned t = atomicAdd(counter_sys, 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return false;
+  __threadfence();
+  double loc[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) loc[k] = 0.0;
+  for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) loc[k] += __ldcg(&partial_sys[b * 4 + k]);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double a = loc[k];
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
+    if (lane == 0) sh[k][wid] = a;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      double a = 0.0;
+      for (int w = 0; w < nw; ++w) a += sh[k][w];
+      tot[k] = a;
+    }
+    *counter_sys = 0u;
+    return true;
+  }
+  return false;
+}
+
+struct SolveDev {  // kernel-side view of the solver workspace
+  int m, n_rhs, n_node;
+  long long nnz;
+  const int32_t *rowptr, *colidx;
+  const c128 *vals;
+  const uint8_t *dir, *node_dir;
+  const int2 *edge_nodes;
+  const int32_t *n2e_ptr, *n2e_item;
+  c128 *dinv, *linv, *w;
+  c128 *scal;
+  double *partial;
+  unsigned *counter;
+  int32_t *state;
+  double tol2;
+  int max_it;
+};
+
+__device__ __forceinline__ c128 *scal_of(const SolveDev &D, int s) { return D.scal + (size_t)s * NSCAL; }
+__device__ __forceinline__ double *partial_of(const SolveDev &D, int s) { return D.partial + (size_t)s * RED_MAX_BLOCKS * 4; }
+
+// ---------------------------------------------------------------- K3: SpMV
+// y[s] = A[f] x[s] for the NR right-hand sides s = f*n_rhs + z*NR + {0..NR-1}.
+// LPR lanes cooperate on a row (coalesced 16-byte value loads, warp-shuffle row reduction).
+// DOT: 0 none | 1: scal[slot0] = sum w.y (unconjugated) | 2: scal[slot0] = sum conj(w) y
+//      3: scal[slot0] = sum conj(y) w , scal[slot1] = sum |y|^2
+template <int LPR, int NR, int DOT>
+__global__ void __launch_bounds__(256)
+k_spmv(SolveDev D, int first_matrix, const c128 *__restrict__ x, c128 *__restrict__ y, const c128 *__restrict__ wv,
+       int slot0, int slot1, int use_active) {
+  const int f = first_matrix + blockIdx.y;
+  const int s0 = f * D.n_rhs + blockIdx.z * NR;
+  bool any = false;
+#pragma unroll
+  for (int r = 0; r < NR; ++r) any |= (!use_active) || D.state[(s0 + r) * 4 + ST_ACTIVE];
+  if (!any) return;
+  const c128 *__restrict__ av = D.vals + (size_t)f * D.nnz;
+  constexpr int RPB = 256 / LPR;
+  const int lane = threadIdx.x % LPR, rl = threadIdx.x / LPR;
+  double dots[NR][4];
+#pragma unroll
+  for (int r = 0; r < NR; ++r)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dots[r][k] = 0.0;
+  const int ntile = (D.m + RPB - 1) / RPB;
+  for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+    const int row = tile * RPB + rl;
+    c128 acc[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) acc[r] = cmake(0.0, 0.0);
+    if (row < D.m) {
+      const int kb = D.rowptr[row], ke = D.rowptr[row + 1];
+      for (int k = kb + lane; k < ke; k += LPR) {
+        const c128 a = __ldg(&av[k]);
+        const int c = __ldg(&D.colidx[k]);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) acc[r] = cfma(a, __ldg(&x[(size_t)(s0 + r) * D.m + c]), acc[r]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) {
+        acc[r].x += __shfl_xor_sync(0xffffffffu, acc[r].x, o);
+        acc[r].y += __shfl_xor_sync(0xffffffffu, acc[r].y, o);
+      }
+    }
+    if (lane == 0 && row < D.m) {
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        const size_t idx = (size_t)(s0 + r) * D.m + row;
+        y[idx] = acc[r];
+        if (DOT == 1) {
+          const c128 q = cmul(wv[idx], acc[r]);
+          dots[r][0] += q.x; dots[r][1] += q.y;
+        } else if (DOT == 2) {
+          const c128 q = cmulconj(wv[idx], acc[r]);
+          dots[r][0] += q.x; dots[r][1] += q.y;
+        } else if (DOT == 3) {
+          const c128 q = cmulconj(acc[r], wv[idx]);
+          dots[r][0] += q.x; dots[r][1] += q.y;
+          dots[r][2] += cabs2(acc[r]);
+        }
+      }
+    }
+  }
+  if (DOT != 0) {
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      const int s = s0 + r;
+      double tot[4];
+      if (reduce_and_ticket<4>(dots[r], partial_of(D, s), D.counter + s, tot)) {
+        c128 *sc = scal_of(D, s);
+        sc[slot0] = cmake(tot[0], tot[1]);
+        if (DOT == 3) sc[slot1] = cmake(tot[2], 0.0);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- preconditioner pieces
+// dinv = 1/diag(A) (1 where the diagonal is missing or zero)
+__global__ void k_dinv(SolveDev D, int first_matrix, const int32_t *__restrict__ diag_pos, int jacobi) {
+  const int f = first_matrix + blockIdx.y;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < D.m; i += gridDim.x * blockDim.x) {
+    c128 v = cmake(1.0, 0.0);
+    if (jacobi) {
+      const int p = diag_pos[i];
+      if (p >= 0) {
+        const c128 a = D.vals[(size_t)f * D.nnz + p];
+        if (a.x != 0.0 || a.y != 0.0) v = cdiv(cmake(1.0, 0.0), a);
+      }
+    }
+    D.dinv[(size_t)f * D.m + i] = v;
+  }
+}
+
+// nodal diagonal of G^T A G (G = discrete gradient, -1 at the tail node, +1 at the head node)
+__global__ void k_nodal_diag(SolveDev D, int first_matrix) {
+  const int f = first_matrix + blockIdx.y;
+  c128 *L = D.linv + (size_t)f * D.n_node;
+  const c128 *__restrict__ av = D.vals + (size_t)f * D.nnz;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < D.m; e += gridDim.x * blockDim.x) {
+    if (D.dir[e]) continue;
+    const int2 ab = D.edge_nodes[e];
+    c128 la = cmake(0.0, 0.0), lb = cmake(0.0, 0.0);
+    for (int k = D.rowptr[e]; k < D.rowptr[e + 1]; ++k) {
+      const int e2 = D.colidx[k];
+      if (D.dir[e2]) continue;
+      const int2 cd = D.edge_nodes[e2];
+      const c128 a = av[k];
+      if (ab.x == cd.x) la = cadd(la, a);
+      if (ab.x == cd.y) la = csub(la, a);
+      if (ab.y == cd.y) lb = cadd(lb, a);
+      if (ab.y == cd.x) lb = csub(lb, a);
+    }
+    atomicAdd(&L[ab.x].x, la.x); atomicAdd(&L[ab.x].y, la.y);
+    atomicAdd(&L[ab.y].x, lb.x); atomicAdd(&L[ab.y].y, lb.y);
+  }
+}
+
+__global__ void k_linv(SolveDev D, int first_matrix) {
+  const int f = first_matrix + blockIdx.y;
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < D.n_node; n += gridDim.x * blockDim.x) {
+    c128 *p = D.linv + (size_t)f * D.n_node + n;
+    const c128 a = *p;
+    c128 v = cmake(0.0, 0.0);
+    if (!D.node_dir[n] && (a.x != 0.0 || a.y != 0.0)) v = cdiv(cmake(1.0, 0.0), a);
+    *p = v;
+  }
+}
+
+// w[s][n] = linv[f][n] * sum_e G[e][n] in[s][e]
+__global__ void k_prec_node(SolveDev D, int first_sys, const c128 *__restrict__ in) {
+  const int s = first_sys + blockIdx.y;
+  if (!D.state[s * 4 + ST_ACTIVE]) return;
+  const int f = s / D.n_rhs;
+  const c128 *__restrict__ v = in + (size_t)s * D.m;
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < D.n_node; n += gridDim.x * blockDim.x) {
+    c128 acc = cmake(0.0, 0.0);
+    const c128 li = D.linv[(size_t)f * D.n_node + n];
+    if (li.x != 0.0 || li.y != 0.0) {
+      for (int k = D.n2e_ptr[n]; k < D.n2e_ptr[n + 1]; ++k) {
+        const int it = D.n2e_item[k];
+        const int e = it >> 1;
+        if (D.dir[e]) continue;
+        const c128 a = v[e];
+        acc = (it & 1) ? cadd(acc, a) : csub(acc, a);
+      }
+      acc = cmul(li, acc);
+    }
+    D.w[(size_t)s * D.n_node + n] = acc;
+  }
+}
+
+// out = dinv .* in (+ G w when aux) ; DOT 1: scal[slot] = sum in.out (unconjugated) ; COPY: p = out too
+template <int DOT, int COPY>
+__global__ void __launch_bounds__(VEC_THREADS)
+k_prec_edge(SolveDev D, int first_sys, const c128 *__restrict__ in, c128 *__restrict__ out, c128 *__restrict__ out2, int aux, int slot) {
+  const int s = first_sys + blockIdx.y;
+  if (!D.state[s * 4 + ST_ACTIVE]) return;
+  const int f = s / D.n_rhs;
+  const size_t off = (size_t)s * D.m;
+  double d[2] = {0.0, 0.0};
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < D.m; e += gridDim.x * blockDim.x) {
+    const c128 a = in[off + e];
+    c128 z = cmul(D.dinv[(size_t)f * D.m + e], a);
+    if (aux && !D.dir[e]) {
+      const int2 ab = D.edge_nodes[e];
+      const c128 *w = D.w + (size_t)s * D.n_node;
+      z = cadd(z, csub(w[ab.y], w[ab.x]));
+    }
+    out[off + e] = z;
+    if (COPY) out2[off + e] = z;
+    if (DOT) {
+      const c128 q = cmul(a, z);
+      d[0] += q.x; d[1] += q.y;
+    }
+  }
+  if (DOT) {
+    double tot[2];
+    if (reduce_and_ticket<2>(d, partial_of(D, s), D.counter + s, tot)) scal_of(D, s)[slot] = cmake(tot[0], tot[1]);
+  }
+}
+
+// ---------------------------------------------------------------- init / residual
+// r = b - y (y = A x), rr = |r|^2, bb = |b|^2.  Finalise: true-residual convergence test.
+// BICG: also r0 = r and rho = r0^H r = rr.
+template <int BICG>
+__global__ void __launch_bounds__(VEC_THREADS)
+k_init_residual(SolveDev D, int first_sys, const c128 *__restrict__ b, const c128 *__restrict__ y, c128 *__restrict__ r,
+                c128 *__restrict__ r0, int zero_x) {
+  const int s = first_sys + blockIdx.y;
+  if (!D.state[s * 4 + ST_ACTIVE]) return;
+  const size_t off = (size_t)s * D.m;
+  double d[2] = {0.0, 0.0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < D.m; i += gridDim.x * blockDim.x) {
+    const c128 bi = b[off + i];
+    const c128 ri = zero_x ? bi : csub(bi, y[off + i]);
+    r[off + i] = ri;
+    if (BICG) r0[off + i] = ri;
+    d[0] += cabs2(ri);
+    d[1] += cabs2(bi);
+  }
+  double tot[2];
+  if (reduce_and_ticket<2>(d, partial_of(D, s), D.counter + s, tot)) {
+    c128 *sc = scal_of(D, s);
+    sc[S_RR] = cmake(tot[0], 0.0);
+    sc[S_BB] = cmake(tot[1], 0.0);
+    sc[S_RHO0] = cmake(tot[0], 0.0);  // BiCGSTAB rho = r0^H r (COCG overwrites it with r^T z)
+    sc[S_ALPHA] = cmake(1.0, 0.0);
+    sc[S_OMEGA] = cmake(1.0, 0.0);
+    int32_t *st = D.state + s * 4;
+    st[ST_REC] = 0;
+    if (tot[0] <= D.tol2 * tot[1]) {  // also covers b == 0
+      st[ST_ACTIVE] = 0;
+      st[ST_CONV] = 1;
+    }
+  }
+}
+
+__global__ void k_fill_zero(c128 *x, int m, int first_sys) {
+  const size_t off = (size_t)(first_sys + blockIdx.y) * m;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) x[off + i] = cmake(0.0, 0.0);
+}
+
+__global__ void k_state_begin(int32_t *state, int first_sys, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int32_t *st = state + (first_sys + i) * 4;
+  st[ST_ACTIVE] = 1; st[ST_ITERS] = 0; st[ST_CONV] = 0; st[ST_REC] = 0;
+}
+
+// after an iteration phase: systems whose recursive residual converged are re-activated so the
+// next k_init_residual verifies the TRUE residual; systems that ran out of iterations stop.
+__global__ void k_state_reactivate(int32_t *state, int first_sys, int n, int max_it) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int32_t *st = state + (first_sys + i) * 4;
+  if (st[ST_CONV]) { st[ST_ACTIVE] = 0; return; }
+  if (st[ST_REC]) { st[ST_ACTIVE] = 1; return; }
+  if (st[ST_ITERS] >= max_it) st[ST_ACTIVE] = 0;
+}
+
+// ---------------------------------------------------------------- COCG phases
+// x += alpha p ; r -= alpha q ; rr = |r|^2      alpha = rho / (p^T q)
+__global__ void __launch_bounds__(VEC_THREADS)
+k_cocg_update(SolveDev D, int first_sys, c128 *__restrict__ x, c128 *__restrict__ r, const c128 *__restrict__ p,
+              const c128 *__restrict__ q, int par) {
+  const int s = first_sys + blockIdx.y;
+  int32_t *st = D.state + s * 4;
+  if (!st[ST_ACTIVE]) return;
+  c128 *sc = scal_of(D, s);
+  const c128 rho = sc[S_RHO0 + par], pq = sc[S_PQ];
+  const bool brk = (pq.x == 0.0 && pq.y == 0.0) || !(isfinite(pq.x) && isfinite(pq.y));
+  const c128 alpha = brk ? cmake(0.0, 0.0) : cdiv(rho, pq);
+  const size_t off = (size_t)s * D.m;
+  double d[2] = {0.0, 0.0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < D.m; i += gridDim.x * blockDim.x) {
+    x[off + i] = cfma(alpha, p[off + i], x[off + i]);
+    const c128 ri = cfma(cneg(alpha), q[off + i], r[off + i]);
+    r[off + i] = ri;
+    d[0] += cabs2(ri);
+  }
+  double tot[2];
+  if (reduce_and_ticket<2>(d, partial_of(D, s), D.counter + s, tot)) {
+    sc[S_RR] = cmake(tot[0], 0.0);
+    st[ST_ITERS] += 1;
+    if (tot[0] <= D.tol2 * sc[S_BB].x) { st[ST_ACTIVE] = 0; st[ST_REC] = 1; }
+    else if (brk || st[ST_ITERS] >= D.max_it) st[ST_ACTIVE] = 0;
+  }
+}
+
+// p = z + beta p     beta = rho_new / rho
+__global__ void __launch_bounds__(VEC_THREADS)
+k_cocg_p(SolveDev D, int first_sys, c128 *__restrict__ p, const c128 *__restrict__ z, int par) {
+  const int s = first_sys + blockIdx.y;
+  if (!D.state[s * 4 + ST_ACTIVE]) return;
+  const c128 *sc = scal_of(D, s);
+  const c128 rho = sc[S_RHO0 + par], rho_new = sc[S_RHO0 + (par ^ 1)];
+  const c128 beta = (rho.x == 0.0 && rho.y == 0.0) ? cmake(0.0, 0.0) : cdiv(rho_new, rho);
+  const size_t off = (size_t)s * D.m;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < D.m; i += gridDim.x * blockDim.x)
+    p[off + i] = cfma(beta, p[off + i], z[off + i]);
+}
+
+// ---------------------------------------------------------------- BiCGSTAB phases
+// p = r + beta (p - omega v)   beta = (rho_new/rho_old)(alpha/omega)   (first: p = r)
+__global__ void __launch_bounds__(VEC_THREADS)
+k_bicg_p(SolveDev D, int first_sys, c128 *__restrict__ p, const c128 *__restrict__ r, const c128 *__restrict__ v, int par, int first_it) {
+  const int s = first_sys + blockIdx.y;
+  if (!D.state[s * 4 + ST_ACTIVE]) return;
+  const c128 *sc = scal_of(D, s);
+  const size_t off = (size_t)s * D.m;
+  if (first_it) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < D.m; i += gridDim.x * blockDim.x) p[off + i] = r[off + i];
+    return;
+  }
+  const c128 rho_new = sc[S_RHO0 + par], rho_old = sc[S_RHO0 + (par ^ 1)];
+  const c128 omega = sc[S_OMEGA], alpha = sc[S_ALPHA];
+  c128 beta = cmake(0.0, 0.0);
+  if ((rho_old.x != 0.0 || rho_old.y != 0.0) && (omega.x != 0.0 || omega.y != 0.0)) beta = cmul(cdiv(rho_new, rho_old), cdiv(alpha, omega));
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < D.m; i += gridDim.x * blockDim.x) {
+    const c128 t = cfma(cneg(omega), v[off + i], p[off + i]);
+    p[off + i] = cfma(beta, t, r[off + i]);
+  }
+}
+
+// s = r - alpha v (in place in r)     alpha = rho / (r0^H v)
+__global__ void __launch_bounds__(VEC_THREADS)
+k_bicg_s(SolveDev D, int first_sys, c128 *__restrict__ r, const c128 *__restrict__ v, int par) {
+  const int s = first_sys + blockIdx.y;
+  if (!D.state[s * 4 + ST_ACTIVE]) return;
+  const c128 *sc = scal_of(D, s);
+  const c128 rho = sc[S_RHO0 + par], r0v = sc[S_R0V];
+  const c128 alpha = (r0v.x == 0.0 && r0v.y == 0.0) ? cmake(0.0, 0.0) : cdiv(rho, r0v);
+  const size_t off = (size_t)s * D.m;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < D.m; i += gridDim.x * blockDim.x)
+    r[off + i] = cfma(cneg(alpha), v[off + i], r[off + i]);
+}
+
+// omega = (t^H s)/(t^H t) ; x += alpha y + omega z ; r = s - omega t ; rr, rho_new = r0^H r
+__global__ void __launch_bounds__(VEC_THREADS)
+k_bicg_x(SolveDev D, int first_sys, c128 *__restrict__ x, c128 *__restrict__ r, const c128 *__restrict__ y,
+         const c128 *__restrict__ z, const c128 *__restrict__ t, const c128 *__restrict__ r0, int par) {
+  const int s = first_sys + blockIdx.y;
+  int32_t *st = D.state + s * 4;
+  if (!st[ST_ACTIVE]) return;
+  c128 *sc = scal_of(D, s);
+  const c128 rho = sc[S_RHO0 + par], r0v = sc[S_R0V], ts = sc[S_TS];
+  const double tt = sc[S_TT].x;
+  const bool brk = (r0v.x == 0.0 && r0v.y == 0.0) || !(isfinite(r0v.x) && isfinite(r0v.y));
+  const c128 alpha = brk ? cmake(0.0, 0.0) : cdiv(rho, r0v);
+  const c128 omega = (tt > 0.0) ? cmake(ts.x / tt, ts.y / tt) : cmake(0.0, 0.0);
+  const size_t off = (size_t)s * D.m;
+  double d[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < D.m; i += gridDim.x * blockDim.x) {
+    c128 xi = cfma(alpha, y[off + i], x[off + i]);
+    x[off + i] = cfma(omega, z[off + i], xi);
+    const c128 ri = cfma(cneg(omega), t[off + i], r[off + i]);
+    r[off + i] = ri;
+    d[0] += cabs2(ri);
+    const c128 q = cmulconj(r0[off + i], ri);
+    d[1] += q.x; d[2] += q.y;
+  }
+  double tot[4];
+  if (reduce_and_ticket<4>(d, partial_of(D, s), D.counter + s, tot)) {
+    sc[S_RR] = cmake(tot[0], 0.0);
+    sc[S_RHO0 + (par ^ 1)] = cmake(tot[1], tot[2]);
+    sc[S_ALPHA] = alpha;
+    sc[S_OMEGA] = omega;
+    st[ST_ITERS] += 1;
+    if (tot[0] <= D.tol2 * sc[S_BB].x) { st[ST_ACTIVE] = 0; st[ST_REC] = 1; }
+    else if (brk || (omega.x == 0.0 && omega.y == 0.0) || st[ST_ITERS] >= D.max_it) st[ST_ACTIVE] = 0;
+  }
+}
+
+// ---------------------------------------------------------------- host side
+static int vec_grid(const Ctx *c, int m) {
+  int nb = (m + VEC_THREADS - 1) / VEC_THREADS;
+  return std::max(1, std::min(nb, std::min(RED_MAX_BLOCKS, c->sm_count * 8)));
+}
+
+static int pick_lpr(const System *S) {
+  const double avg = (double)S->nnz / std::max(1, S->m);
+  if (avg <= 6.0) return 4;
+  if (avg <= 12.0) return 8;
+  if (avg <= 48.0) return 16;
+  return 32;
+}
+
+int solver_free(System *S) {
+  cudaFree(S->d_work); cudaFree(S->d_dinv); cudaFree(S->d_linv); cudaFree(S->d_w); cudaFree(S->d_scal);
+  cudaFree(S->d_partial); cudaFree(S->d_counter); cudaFree(S->d_state); cudaFree(S->d_flag);
+  S->d_work = nullptr; S->d_dinv = nullptr; S->d_linv = nullptr; S->d_w = nullptr; S->d_scal = nullptr;
+  S->d_partial = nullptr; S->d_counter = nullptr; S->d_state = nullptr; S->d_flag = nullptr;
+  return EFB_OK;
+}
+
+static int solver_alloc(System *S) {
+  Ctx *c = S->ctx;
+  int rc;
+  if (!S->d_work) {
+    if ((rc = dev_alloc(c, &S->d_work, (size_t)V_NUM * S->n_sys * S->m))) return rc;
+    S->n_work_vec = V_NUM;
+    if ((rc = dev_alloc(c, &S->d_dinv, (size_t)S->n_matrix * S->m))) return rc;
+    if ((rc = dev_alloc(c, &S->d_scal, (size_t)S->n_sys * NSCAL))) return rc;
+    if ((rc = dev_alloc(c, &S->d_partial, (size_t)S->n_sys * RED_MAX_BLOCKS * 4))) return rc;
+    if ((rc = dev_alloc(c, &S->d_counter, (size_t)S->n_sys))) return rc;
+    if ((rc = dev_alloc(c, &S->d_state, (size_t)S->n_sys * 4))) return rc;
+    EFB_CUDA(c, cudaMemsetAsync(S->d_counter, 0, (size_t)S->n_sys * sizeof(unsigned), c->stream));
+    EFB_CUDA(c, cudaMemsetAsync(S->d_scal, 0, (size_t)S->n_sys * NSCAL * sizeof(c128), c->stream));
+    EFB_CUDA(c, cudaMemsetAsync(S->d_state, 0, (size_t)S->n_sys * 4 * sizeof(int32_t), c->stream));
+  }
+  if (S->n_node > 0 && !S->d_linv) {
+    if ((rc = dev_alloc(c, &S->d_linv, (size_t)S->n_matrix * S->n_node))) return rc;
+    if ((rc = dev_alloc(c, &S->d_w, (size_t)S->n_sys * S->n_node))) return rc;
+  }
+  return EFB_OK;
+}
+
+static SolveDev make_dev(System *S, double tol, int max_it) {
+  SolveDev D;
+  D.m = S->m; D.n_rhs = S->n_rhs; D.n_node = S->n_node; D.nnz = (long long)S->nnz;
+  D.rowptr = S->d_rowptr; D.colidx = S->d_colidx; D.vals = S->d_vals;
+  D.dir = S->d_dir; D.node_dir = S->d_node_dir; D.edge_nodes = S->d_edge_nodes;
+  D.n2e_ptr = S->d_n2e_ptr; D.n2e_item = S->d_n2e_item;
+  D.dinv = S->d_dinv; D.linv = S->d_linv; D.w = S->d_w;
+  D.scal = S->d_scal; D.partial = S->d_partial; D.counter = S->d_counter; D.state = S->d_state;
+  D.tol2 = tol * tol; D.max_it = max_it;
+  return D;
+}
+
+template <int NR, int DOT>
+static void launch_spmv_lpr(Ctx *c, const SolveDev &D, int lpr, dim3 grid, int first_matrix, const c128 *x, c128 *y, const c128 *w,
+                            int slot0, int slot1, int use_active) {
+  switch (lpr) {
+    case 4: k_spmv<4, NR, DOT><<<grid, 256, 0, c->stream>>>(D, first_matrix, x, y, w, slot0, slot1, use_active); break;
+    case 8: k_spmv<8, NR, DOT><<<grid, 256, 0, c->stream>>>(D, first_matrix, x, y, w, slot0, slot1, use_active); break;
+    case 16: k_spmv<16, NR, DOT><<<grid, 256, 0, c->stream>>>(D, first_matrix, x, y, w, slot0, slot1, use_active); break;
+    default: k_spmv<32, NR, DOT><<<grid, 256, 0, c->stream>>>(D, first_matrix, x, y, w, slot0, slot1, use_active); break;
+  }
+}
+
+// y = A x over matrices [first, first+count) and all their right-hand sides
+static int launch_spmv(System *S, const SolveDev &D, int first, int count, const c128 *x, c128 *y, const c128 *w, int dot, int slot0,
+                       int slot1, int use_active) {
+  Ctx *c = S->ctx;
+  const int lpr = pick_lpr(S);
+  const int rpb = 256 / lpr;
+  int nbx = std::max(1, std::min((S->m + rpb - 1) / rpb, std::min(RED_MAX_BLOCKS, c->sm_count * 8)));
+  const bool two = (S->n_rhs % 2 == 0);
+  dim3 grid((unsigned)nbx, (unsigned)count, (unsigned)(two ? S->n_rhs / 2 : S->n_rhs));
+#define EFB_SPMV(NR)                                                                              \
+  switch (dot) {                                                                                  \
+    case 0: launch_spmv_lpr<NR, 0>(c, D, lpr, grid, first, x, y, w, slot0, slot1, use_active); break; \
+    case 1: launch_spmv_lpr<NR, 1>(c, D, lpr, grid, first, x, y, w, slot0, slot1, use_active); break; \
+    case 2: launch_spmv_lpr<NR, 2>(c, D, lpr, grid, first, x, y, w, slot0, slot1, use_active); break; \
+    default: launch_spmv_lpr<NR, 3>(c, D, lpr, grid, first, x, y, w, slot0, slot1, use_active); break; \
+  }
+  if (two) { EFB_SPMV(2) } else { EFB_SPMV(1) }
+#undef EFB_SPMV
+  EFB_CHECK_LAUNCH(c);
+  return EFB_OK;
+}
+
+struct SolvePlan {
+  System *S;
+  SolveDev D;
+  int first_matrix, n_matrix, first_sys, n_sys;
+  int method, precond;
+  bool aux;
+  c128 *vec[V_NUM];
+  dim3 vgrid, ngrid;
+};
+
+static int apply_precond(SolvePlan &P, const c128 *in, c128 *out, c128 *out2, int dot_slot) {
+  Ctx *c = P.S->ctx;
+  if (P.aux) {
+    k_prec_node<<<P.ngrid, VEC_THREADS, 0, c->stream>>>(P.D, P.first_sys, in);
+    EFB_CHECK_LAUNCH(c);
+  }
+  if (dot_slot >= 0) {
+    if (out2) k_prec_edge<1, 1><<<P.vgrid, VEC_THREADS, 0, c->stream>>>(P.D, P.first_sys, in, out, out2, P.aux, dot_slot);
+    else k_prec_edge<1, 0><<<P.vgrid, VEC_THREADS, 0, c->stream>>>(P.D, P.first_sys, in, out, out2, P.aux, dot_slot);
+  } else {
+    k_prec_edge<0, 0><<<P.vgrid, VEC_THREADS, 0, c->stream>>>(P.D, P.first_sys, in, out, out2, P.aux, 0);
+  }
+  EFB_CHECK_LAUNCH(c);
+  return EFB_OK;
+}
+
+static int setup_precond(SolvePlan &P) {
+  System *S = P.S;
+  Ctx *c = S->ctx;
+  dim3 g((unsigned)vec_grid(c, S->m), (unsigned)P.n_matrix);
+  k_dinv<<<g, VEC_THREADS, 0, c->stream>>>(P.D, P.first_matrix, S->d_diag_pos, P.precond != EFB_PRECOND_NONE);
+  EFB_CHECK_LAUNCH(c);
+  if (P.aux) {
+    EFB_CUDA(c, cudaMemsetAsync(S->d_linv + (size_t)P.first_matrix * S->n_node, 0, (size_t)P.n_matrix * S->n_node * sizeof(c128), c->stream));
+    k_nodal_diag<<<g, VEC_THREADS, 0, c->stream>>>(P.D, P.first_matrix);
+    EFB_CHECK_LAUNCH(c);
+    dim3 gn((unsigned)vec_grid(c, S->n_node), (unsigned)P.n_matrix);
+    k_linv<<<gn, VEC_THREADS, 0, c->stream>>>(P.D, P.first_matrix);
+    EFB_CHECK_LAUNCH(c);
+  }
+  return EFB_OK;
+}
+
+// r = b - A x (true residual), convergence test, method-specific start vectors
+static int init_cycle(SolvePlan &P, bool zero_x) {
+  System *S = P.S;
+  Ctx *c = S->ctx;
+  int rc;
+  if (!zero_x)
+    if ((rc = launch_spmv(S, P.D, P.first_matrix, P.n_matrix, S->d_x, P.vec[V_Q], nullptr, 0, 0, 0, 1))) return rc;
+  if (P.method == EFB_METHOD_BICGSTAB)
+    k_init_residual<1><<<P.vgrid, VEC_THREADS, 0, c->stream>>>(P.D, P.first_sys, S->d_b, P.vec[V_Q], P.vec[V_R], P.vec[V_R0], zero_x);
+  else
+    k_init_residual<0><<<P.vgrid, VEC_THREADS, 0, c->stream>>>(P.D, P.first_sys, S->d_b, P.vec[V_Q], P.vec[V_R], P.vec[V_R0], zero_x);
+  EFB_CHECK_LAUNCH(c);
+  if (P.method == EFB_METHOD_COCG) {
+    // z = M^-1 r ; p = z ; rho(par 0) = r^T z
+    if ((rc = apply_precond(P, P.vec[V_R], P.vec[V_Z], P.vec[V_P], S_RHO0))) return rc;
+  }
+  return EFB_OK;
+}
+
+static int cocg_iteration(SolvePlan &P, int par) {
+  System *S = P.S;
+  Ctx *c = S->ctx;
+  int rc;
+  if ((rc = launch_spmv(S, P.D, P.first_matrix, P.n_matrix, P.vec[V_P], P.vec[V_Q], P.vec[V_P], 1, S_PQ, 0, 1))) return rc;
+  k_cocg_update<<<P.vgrid, VEC_THREADS, 0, c->stream>>>(P.D, P.first_sys, S->d_x, P.vec[V_R], P.vec[V_P], P.vec[V_Q], par);
+  EFB_CHECK_LAUNCH(c);
+  if ((rc = apply_precond(P, P.vec[V_R], P.vec[V_Z], nullptr, S_RHO0 + (par ^ 1)))) return rc;
+  k_cocg_p<<<P.vgrid, VEC_THREADS, 0, c->stream>>>(P.D, P.first_sys, P.vec[V_P], P.vec[V_Z], par);
+  EFB_CHECK_LAUNCH(c);
+  return EFB_OK;
+}
+
+static int bicg_iteration(SolvePlan &P, int par, bool first_it) {
+  System *S = P.S;
+  Ctx *c = S->ctx;
+  int rc;
+  // V_Q holds v, V_P holds p, V_Y = M^-1 p, V_Z = M^-1 s, V_T = t, s lives in V_R
+  k_bicg_p<<<P.vgrid, VEC_THREADS, 0, c->stream>>>(P.D, P.first_sys, P.vec[V_P], P.vec[V_R], P.vec[V_Q], par, first_it ? 1 : 0);
+  EFB_CHECK_LAUNCH(c);
+  if ((rc = apply_precond(P, P.vec[V_P], P.vec[V_Y], nullptr, -1))) return rc;
+  if ((rc = launch_spmv(S, P.D, P.first_matrix, P.n_matrix, P.vec[V_Y], P.vec[V_Q], P.vec[V_R0], 2, S_R0V, 0, 1))) return rc;
+  k_bicg_s<<<P.vgrid, VEC_THREADS, 0, c->stream>>>(P.D, P.first_sys, P.vec[V_R], P.vec[V_Q], par);
+  EFB_CHECK_LAUNCH(c);
+  if ((rc = apply_precond(P, P.vec[V_R], P.vec[V_Z], nullptr, -1))) return rc;
+  if ((rc = launch_spmv(S, P.D, P.first_matrix, P.n_matrix, P.vec[V_Z], P.vec[V_T], P.vec[V_R], 3, S_TS, S_TT, 1))) return rc;
+  k_bicg_x<<<P.vgrid, VEC_THREADS, 0, c->stream>>>(P.D, P.first_sys, S->d_x, P.vec[V_R], P.vec[V_Y], P.vec[V_Z], P.vec[V_T], P.vec[V_R0], par);
+  EFB_CHECK_LAUNCH(c);
+  return EFB_OK;
+}
+
+static int make_plan(System *S, int first_matrix, int n_matrix, const efb_solve_opts *o, SolvePlan &P) {
+  Ctx *c = S->ctx;
+  int rc = solver_alloc(S);
+  if (rc) return rc;
+  P.S = S;
+  P.first_matrix = first_matrix;
+  P.n_matrix = n_matrix;
+  P.first_sys = first_matrix * S->n_rhs;
+  P.n_sys = n_matrix * S->n_rhs;
+  P.method = o->method == EFB_METHOD_AUTO ? (o->symmetric_hint ? EFB_METHOD_COCG : EFB_METHOD_BICGSTAB) : o->method;
+  P.precond = o->precond;
+  P.aux = (o->precond == EFB_PRECOND_AUX) && S->n_node > 0 && S->d_edge_nodes;
+  if (o->precond == EFB_PRECOND_AUX && !P.aux) P.precond = EFB_PRECOND_JACOBI;
+  P.D = make_dev(S, o->tolerance, o->max_iterations);
+  for (int v = 0; v < V_NUM; ++v) P.vec[v] = S->d_work + (size_t)v * S->n_sys * S->m;
+  P.vgrid = dim3((unsigned)vec_grid(c, S->m), (unsigned)P.n_sys);
+  P.ngrid = dim3((unsigned)vec_grid(c, std::max(1, S->n_node)), (unsigned)P.n_sys);
+  return EFB_OK;
+}
+
+}  // namespace efb
+
+using namespace efb;
+
+extern "C" {
+
+int efb_solve(efb_system *sys_, int32_t first_matrix, int32_t n_matrix, const efb_solve_opts *opts, efb_solve_result *results) {
+  System *S = (System *)sys_;
+  if (!S) return fail(nullptr, EFB_ERR_INVALID, "efb_solve: NULL system");
+  Ctx *c = S->ctx;
+  if (!opts || !results || first_matrix < 0 || n_matrix <= 0 || first_matrix + n_matrix > S->n_matrix)
+    return fail(c, EFB_ERR_INVALID, "efb_solve: bad arguments");
+  if (!S->assembled) return fail(c, EFB_ERR_STATE, "efb_solve: matrix values were never assembled or set");
+  if (!(opts->tolerance > 0.0) || opts->max_iterations < 0) return fail(c, EFB_ERR_INVALID, "efb_solve: bad tolerance / max_iterations");
+  if (opts->method < 0 || opts->method > EFB_METHOD_COCG || opts->precond < 0 || opts->precond > EFB_PRECOND_NONE)
+    return fail(c, EFB_ERR_INVALID, "efb_solve: unknown method / preconditioner");
+  EFB_CUDA(c, cudaSetDevice(c->device));
+  SolvePlan P;
+  int rc = make_plan(S, first_matrix, n_matrix, opts, P);
+  if (rc) return rc;
+  const int check_every = opts->check_every > 0 ? opts->check_every : 32;
+  const int max_restarts = opts->max_restarts > 0 ? opts->max_restarts : 3;
+  const int nsys = P.n_sys;
+  std::vector<int32_t> hstate((size_t)nsys * 4);
+  Timed tm(c);
+  k_state_begin<<<(nsys + 127) / 128, 128, 0, c->stream>>>(S->d_state, P.first_sys, nsys);
+  EFB_CHECK_LAUNCH(c);
+  if ((rc = setup_precond(P))) return rc;
+  bool zero_x = opts->zero_initial_guess != 0;
+  if (zero_x) {
+    dim3 g((unsigned)vec_grid(c, S->m), (unsigned)nsys);
+    k_fill_zero<<<g, VEC_THREADS, 0, c->stream>>>(S->d_x, S->m, P.first_sys);
+    EFB_CHECK_LAUNCH(c);
+  }
+  auto read_state = [&]() -> int {
+    EFB_CUDA(c, cudaMemcpyAsync(hstate.data(), S->d_state + (size_t)P.first_sys * 4, hstate.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    EFB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return EFB_OK;
+  };
+  auto any_active = [&]() {
+    for (int i = 0; i < nsys; ++i)
+      if (hstate[i * 4 + ST_ACTIVE]) return true;
+    return false;
+  };
+  for (int cycle = 0; cycle <= max_restarts; ++cycle) {
+    if ((rc = init_cycle(P, zero_x))) return rc;
+    zero_x = false;
+    if ((rc = read_state())) return rc;
+    if (!any_active() || opts->max_iterations == 0) break;
+    int it = 0;
+    while (true) {
+      for (int k = 0; k < check_every; ++k, ++it) {
+        const int par = it & 1;
+        if (P.method == EFB_METHOD_COCG) rc = cocg_iteration(P, par);
+        else rc = bicg_iteration(P, par, it == 0);
+        if (rc) return rc;
+      }
+      if ((rc = read_state())) return rc;
+      if (!any_active()) break;
+    }
+    k_state_reactivate<<<(nsys + 127) / 128, 128, 0, c->stream>>>(S->d_state, P.first_sys, nsys, opts->max_iterations);
+    EFB_CHECK_LAUNCH(c);
+    if ((rc = read_state())) return rc;
+    if (!any_active()) break;
+    if (cycle == max_restarts) {
+      // final verification pass for the systems re-activated just now
+      if ((rc = init_cycle(P, false))) return rc;
+      if ((rc = read_state())) return rc;
+    }
+  }
+  // final true residuals: r = b - A x for every system (cheap, and independent of the path taken)
+  std::vector<int32_t> hiters(nsys), hconv(nsys);
+  for (int i = 0; i < nsys; ++i) { hiters[i] = hstate[i * 4 + ST_ITERS]; hconv[i] = hstate[i * 4 + ST_CONV]; }
+  {
+    // activate all, recompute residual norms
+    std::vector<int32_t> act((size_t)nsys * 4);
+    for (int i = 0; i < nsys; ++i) { act[i * 4 + ST_ACTIVE] = 1; act[i * 4 + ST_ITERS] = hiters[i]; act[i * 4 + ST_CONV] = 0; act[i * 4 + ST_REC] = 0; }
+    EFB_CUDA(c, cudaMemcpyAsync(S->d_state + (size_t)P.first_sys * 4, act.data(), act.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    if ((rc = launch_spmv(S, P.D, P.first_matrix, P.n_matrix, S->d_x, P.vec[V_Q], nullptr, 0, 0, 0, 0))) return rc;
+    k_init_residual<0><<<P.vgrid, VEC_THREADS, 0, c->stream>>>(P.D, P.first_sys, S->d_b, P.vec[V_Q], P.vec[V_R], P.vec[V_R0], 0);
+    EFB_CHECK_LAUNCH(c);
+  }
+  std::vector<c128> hscal((size_t)nsys * NSCAL);
+  EFB_CUDA(c, cudaMemcpyAsync(hscal.data(), S->d_scal + (size_t)P.first_sys * NSCAL, hscal.size() * sizeof(c128), cudaMemcpyDeviceToHost, c->stream));
+  EFB_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < nsys; ++i) {
+    const double rr = hscal[(size_t)i * NSCAL + S_RR].x, bb = hscal[(size_t)i * NSCAL + S_BB].x;
+    efb_solve_result &R = results[i];
+    R.iters = hiters[i];
+    R.method = P.method;
+    R.precond = P.aux ? EFB_PRECOND_AUX : P.precond;
+    R.residual = bb > 0.0 ? sqrt(rr / bb) : sqrt(rr);
+    R.converged = (rr <= P.D.tol2 * bb * (1.0 + 1e-6)) && std::isfinite(rr) ? 1 : 0;
+  }
+  return EFB_OK;
+}
+
+int efb_spmv_host(efb_system *sys_, int32_t matrix, const double *x, double *y) {
+  System *S = (System *)sys_;
+  if (!S || !x || !y || matrix < 0 || matrix >= S->n_matrix) return fail(S ? S->ctx : nullptr, EFB_ERR_INVALID, "efb_spmv_host: bad arguments");
+  Ctx *c = S->ctx;
+  EFB_CUDA(c, cudaSetDevice(c->device));
+  int rc = solver_alloc(S);
+  if (rc) return rc;
+  SolveDev D = make_dev(S, 1e-10, 0);
+  // use system slot matrix*n_rhs of work vectors P (in) and Q (out)
+  c128 *vin = S->d_work + (size_t)V_P * S->n_sys * S->m, *vout = S->d_work + (size_t)V_Q * S->n_sys * S->m;
+  const size_t off = (size_t)matrix * S->n_rhs * S->m;
+  EFB_CUDA(c, cudaMemcpyAsync(vin + off, x, (size_t)S->m * sizeof(c128), cudaMemcpyHostToDevice, c->stream));
+  {
+    Timed tm(c);
+    if ((rc = launch_spmv(S, D, matrix, 1, vin, vout, nullptr, 0, 0, 0, 0))) return rc;
+  }
+  EFB_CUDA(c, cudaMemcpyAsync(y, vout + off, (size_t)S->m * sizeof(c128), cudaMemcpyDeviceToHost, c->stream));
+  EFB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return EFB_OK;
+}
+
+int efb_bench_kernel(efb_system *sys_, int32_t which, int32_t reps, double *avg_ms) {
+  System *S = (System *)sys_;
+  if (!S || !avg_ms || reps <= 0 || which < 0 || which > 3) return fail(S ? S->ctx : nullptr, EFB_ERR_INVALID, "efb_bench_kernel: bad arguments");
+  Ctx *c = S->ctx;
+  EFB_CUDA(c, cudaSetDevice(c->device));
+  if (!S->assembled) return fail(c, EFB_ERR_STATE, "efb_bench_kernel: assemble first");
+  int rc;
+  efb_solve_opts o;
+  memset(&o, 0, sizeof o);
+  o.tolerance = 1e-300;  // never converges: the timed iterations stay active
+  o.max_iterations = 1 << 30;
+  o.precond = EFB_PRECOND_JACOBI;
+  o.method = which == 2 ? EFB_METHOD_COCG : EFB_METHOD_BICGSTAB;
+  SolvePlan P;
+  if (which != 3) {
+    if ((rc = make_plan(S, 0, S->n_matrix, &o, P))) return rc;
+    k_state_begin<<<(P.n_sys + 127) / 128, 128, 0, c->stream>>>(S->d_state, 0, P.n_sys);
+    EFB_CHECK_LAUNCH(c);
+    if ((rc = setup_precond(P))) return rc;
+    if (which != 0 && (rc = init_cycle(P, false))) return rc;
+  } else if (!S->mesh || S->last_mat_blob.empty()) {
+    return fail(c, EFB_ERR_STATE, "efb_bench_kernel: no previous efb_assemble_volume call to replay");
+  }
+  cudaEvent_t e0, e1;
+  EFB_CUDA(c, cudaEventCreate(&e0));
+  EFB_CUDA(c, cudaEventCreate(&e1));
+  const int count = (int)S->last_omega.size();
+  for (int pass = 0; pass < 2; ++pass) {  // pass 0 = warm-up
+    const int n = pass == 0 ? std::min(reps, 3) : reps;
+    if (pass == 1) EFB_CUDA(c, cudaEventRecord(e0, c->stream));
+    for (int i = 0; i < n; ++i) {
+      if (which == 0) rc = launch_spmv(S, P.D, 0, S->n_matrix, S->d_x, P.vec[V_Q], nullptr, 0, 0, 0, 0);
+      else if (which == 1) rc = bicg_iteration(P, i & 1, false);
+      else if (which == 2) rc = cocg_iteration(P, i & 1);
+      else rc = assemble_launch(S, 0, count, S->last_mode);
+      if (rc) return rc;
+    }
+    if (pass == 1) EFB_CUDA(c, cudaEventRecord(e1, c->stream));
+  }
+  EFB_CUDA(c, cudaEventSynchronize(e1));
+  float ms = 0.f;
+  EFB_CUDA(c, cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *avg_ms = (double)ms / reps;
+  return EFB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,255 @@
+/*
+ * edgefem_b200.h -- C-ABI of the B200-native EdgeFEM frequency-domain solve hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++
+ * or torch types.  The reference (jman4162/EdgeFEM) has no FFI of its own; the entry
+ * points below are what its C++ functions for this path bind to when the Eigen CPU
+ * arithmetic is replaced by the GPU.  Each group cites the reference code it replaces
+ * (paths relative to the reference root).  The C++ host layer in include/edgefem/ (same
+ * names/signatures as the reference headers) is the only intended caller; INTEGRATION.md
+ * shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - every call returns EFB_OK (0) or a negative efb_status; efb_last_error() gives text
+ *   - complex numbers are interleaved (re, im) doubles ("c128")
+ *   - indices are 0-based int32; node references are node *indices* (not Gmsh ids)
+ *   - host buffers are caller-owned; handles are opaque and owned by the library
+ *   - one efb_ctx per GPU; a ctx and its children are used from one thread at a time
+ *   - no CPU fallback: every compute entry point fails with EFB_ERR_CUDA without a GPU
+ */
+#ifndef EDGEFEM_B200_H
+#define EDGEFEM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EFB_ABI_VERSION 1
+
+typedef enum {
+  EFB_OK = 0,
+  EFB_ERR_INVALID = -1, /* bad argument */
+  EFB_ERR_CUDA = -2,    /* CUDA runtime error / no device */
+  EFB_ERR_NOMEM = -3,
+  EFB_ERR_LIMIT = -4,   /* a structural limit was exceeded (row too long, too many tags) */
+  EFB_ERR_STATE = -5    /* call order (e.g. solve before assemble) */
+} efb_status;
+
+typedef struct efb_ctx efb_ctx;
+typedef struct efb_mesh efb_mesh;
+typedef struct efb_system efb_system;
+typedef struct efb_port efb_port;
+
+/* ------------------------------------------------------------------ context */
+int efb_abi_version(void);
+int efb_device_count(void);
+int efb_ctx_create(int device, efb_ctx **out);
+void efb_ctx_destroy(efb_ctx *ctx);
+const char *efb_last_error(const efb_ctx *ctx); /* ctx may be NULL: last global error */
+int efb_ctx_sync(efb_ctx *ctx);
+/* time of the most recent efb_* compute call's kernels, ms (CUDA events on the ctx stream) */
+double efb_last_kernel_ms(const efb_ctx *ctx);
+/* number of kernels this ctx has launched since creation */
+int64_t efb_launch_count(const efb_ctx *ctx);
+
+/* ------------------------------------------------------------------ mesh
+ * Replaces the in-memory traversal of `Mesh` (include/edgefem/mesh.hpp:43-52) done by
+ * assemble_maxwell (src/assemble_maxwell.cpp:114-204).  Edge numbering (a1,
+ * src/mesh_gmsh.cpp:104-146) is an INPUT: tet_edges/tet_orient carry it bit-exactly.   */
+typedef struct {
+  int32_t n_node;
+  const double *xyz;          /* [3*n_node] */
+  int32_t n_tet;
+  const int32_t *tet_nodes;   /* [4*n_tet] node indices */
+  const int32_t *tet_edges;   /* [6*n_tet] global edge ids, local order (01,02,03,12,13,23) */
+  const int8_t *tet_orient;   /* [6*n_tet] +1/-1 */
+  const int32_t *tet_phys;    /* [n_tet] physical tag */
+  int32_t n_edge;             /* m */
+  const int32_t *edge_nodes;  /* [2*n_edge] node indices (n0,n1) of each global edge */
+} efb_mesh_desc;
+
+int efb_mesh_create(efb_ctx *ctx, const efb_mesh_desc *desc, efb_mesh **out);
+void efb_mesh_destroy(efb_mesh *mesh);
+/* distinct physical tags of the tets, ascending; the material "slots" used below */
+int efb_mesh_num_slots(const efb_mesh *mesh);
+int efb_mesh_get_slot_tags(const efb_mesh *mesh, int32_t *tags /* [n_slots] */);
+
+/* ------------------------------------------------------------------ system
+ * A batch of n_matrix matrices sharing one CSR pattern, each with n_rhs right-hand sides
+ * and solutions.  Pattern = union of the 6x6 edge cliques of all tets (setFromTriplets,
+ * src/assemble_maxwell.cpp:205) plus `extra` entries (coeffRef insertions: port blocks
+ * :229, ABC / Dirichlet diagonals :263,:315,:345), row-major CSR, sorted columns.      */
+int efb_system_create(efb_mesh *mesh, int64_t n_extra, const int32_t *extra_rows,
+                      const int32_t *extra_cols, int32_t n_matrix, int32_t n_rhs,
+                      efb_system **out);
+/* generic system from a caller-supplied CSR matrix (solve_linear, src/solver.cpp:35);
+ * vals may be NULL (set later with efb_system_set_values)                              */
+int efb_system_create_csr(efb_ctx *ctx, int32_t m, int64_t nnz, const int32_t *rowptr,
+                          const int32_t *colidx, const double *vals_c128, int32_t n_matrix,
+                          int32_t n_rhs, efb_system **out);
+void efb_system_destroy(efb_system *sys);
+int efb_system_dims(const efb_system *sys, int32_t *m, int64_t *nnz, int32_t *n_matrix,
+                    int32_t *n_rhs);
+int efb_system_get_pattern(const efb_system *sys, int32_t *rowptr /* [m+1] */,
+                           int32_t *colidx /* [nnz] */);
+int efb_system_get_values(efb_system *sys, int32_t matrix, double *vals_c128 /* [nnz] */);
+int efb_system_set_values(efb_system *sys, int32_t matrix, const double *vals_c128);
+/* Dirichlet (PEC) edge flags, src/assemble_maxwell.cpp:322-347: rows+cols zeroed with the
+ * entries kept, diagonal = 1, b = 0.  flags[m] (0/1).  Applied by efb_assemble_volume. */
+int efb_system_set_dirichlet(efb_system *sys, const uint8_t *flags);
+/* optional: discrete gradient for the auxiliary nodal-space preconditioner of a system
+ * created with efb_system_create_csr (mesh-born systems have it already)               */
+int efb_system_set_gradient(efb_system *sys, int32_t n_node, const int32_t *edge_nodes);
+
+/* ------------------------------------------------------------------ materials / PML
+ * Per-slot table (slot order = efb_mesh_get_slot_tags).  Static values are the
+ * region-or-global resolution of MaxwellParams::get_eps_r(tag) (maxwell.hpp:100-103);
+ * a dispersive model on a slot overrides the static value and is evaluated ON DEVICE
+ * at each omega (materials/dispersive.hpp:62-66,127-138,182-194,251-273).              */
+typedef enum { EFB_MODEL_NONE = 0, EFB_MODEL_DEBYE = 1, EFB_MODEL_LORENTZ = 2,
+               EFB_MODEL_DRUDE = 3, EFB_MODEL_DRUDE_LORENTZ = 4 } efb_model_kind;
+
+typedef struct {
+  int32_t kind;       /* efb_model_kind */
+  int32_t n_poles;    /* Lorentz poles (LORENTZ, DRUDE_LORENTZ) */
+  int32_t pole_begin; /* index into the poles array */
+  int32_t _pad;
+  double p0;          /* DEBYE eps_s | LORENTZ eps_inf | DRUDE omega_p | DL eps_inf */
+  double p1;          /* DEBYE eps_inf |               | DRUDE gamma   | DL omega_p */
+  double p2;          /* DEBYE tau    |                |               | DL gamma_d */
+} efb_model;
+
+typedef struct { double delta_eps, omega0, gamma; } efb_pole;
+
+typedef enum { EFB_PML_NONE = 0, EFB_PML_UNIFORM = 1, EFB_PML_TENSOR = 2 } efb_pml_kind;
+
+typedef struct {
+  int32_t kind;           /* efb_pml_kind; UNIFORM: s = 1 + j*sigma[0]/omega (assemble_maxwell.cpp:168-170) */
+  int32_t enforce_heuristics;
+  double sigma[3];        /* TENSOR: sigma_max per axis (assemble_maxwell.cpp:140-164) */
+  double thickness[3];
+  double grading_order;
+} efb_pml;
+
+typedef struct {
+  int32_t n_slots;
+  const double *eps_static_c128; /* [n_slots] */
+  const double *mu_static_c128;  /* [n_slots] */
+  const efb_model *eps_models;   /* [n_slots] or NULL */
+  const efb_model *mu_models;    /* [n_slots] or NULL (eval_mu == 1 for every shipped model) */
+  int32_t n_poles;
+  const efb_pole *poles;
+  const efb_pml *pml;            /* [n_slots] or NULL */
+} efb_materials;
+
+/* ------------------------------------------------------------------ assembly (K1, K6)
+ * Volume term for matrices [first, first+count): per tet 6x6 K/(mu s) - k0^2 eps s M with
+ * orientation signs, summed into the CSR pattern, Dirichlet mask applied
+ * (src/assemble_maxwell.cpp:114-205,322-347; element matrices src/edge_basis.cpp:14-86).
+ * mode: 0 = A(omega) ; 1 = K only (1/mu, static materials) ; 2 = M only (eps, static)
+ * (src/sweep.cpp:90-172: K(e,e)=1 and M(e,e)=0 on Dirichlet edges).  omega[count].
+ * Also zeroes the right-hand sides of those matrices.                                    */
+int efb_assemble_volume(efb_system *sys, int32_t first, int32_t count, const double *omega,
+                        const efb_materials *mat, int32_t mode);
+/* K6: vals[dst] = vals[srcK] - k0sq * vals[srcM] (KMMatrices::combine, src/sweep.cpp:82-88) */
+int efb_combine_km(efb_system *sys, int32_t dst_first, int32_t count, const double *k0sq,
+                   int32_t src_k, int32_t src_m);
+/* A[first+i](e,e) += coef[i] for e in edges (ABC src/assemble_maxwell.cpp:244-265; port ABC
+ * :274-320).  Dirichlet edges are skipped on device.                                     */
+int efb_add_diag(efb_system *sys, int32_t first, int32_t count, int32_t n,
+                 const int32_t *edges, const double *coef_c128);
+
+/* ------------------------------------------------------------------ ports (K2, K5)
+ * Device-resident port: weights w on `edges` (zeroed on Dirichlet edges) and, optionally,
+ * its surface mass matrix M_s as COO triplets (assemble_port_surface_mass,
+ * src/ports/wave_port.cpp:549-585; duplicates are summed).                               */
+int efb_port_create(efb_system *sys, int32_t n_edges, const int32_t *edges,
+                    const double *weights_c128, int64_t n_ms, const int32_t *ms_rows,
+                    const int32_t *ms_cols, const double *ms_vals, efb_port **out);
+void efb_port_destroy(efb_port *port);
+/* e <- e / sqrt(Re(e^H M_s e)) if that is > 1e-30 (src/assemble_maxwell.cpp:714-728);
+ * returns the pre-normalisation norm_sq                                                  */
+int efb_port_normalize_mass(efb_port *port, double *norm_sq);
+/* A[first+i] += coef[i] * w w^H over non-Dirichlet port edges (src/assemble_maxwell.cpp:219-231) */
+int efb_port_add_block(efb_system *sys, efb_port *port, int32_t first, int32_t count,
+                       const double *coef_c128);
+/* A[first+i] += coef[i] * M_s (src/assemble_maxwell.cpp:738-746) */
+int efb_port_add_mass(efb_system *sys, efb_port *port, int32_t first, int32_t count,
+                      const double *coef_c128);
+/* b[rhs] += coef * w   (src/assemble_maxwell.cpp:233-241);  rhs = matrix*n_rhs + k */
+int efb_port_rhs_weights(efb_system *sys, efb_port *port, int32_t rhs, const double *coef_c128);
+/* b[rhs] += coef * M_s e (src/assemble_maxwell.cpp:749-752) */
+int efb_port_rhs_mass(efb_system *sys, efb_port *port, int32_t rhs, const double *coef_c128);
+/* V = sum conj(w_k) x(edge_k)  (src/assemble_maxwell.cpp:376-384) */
+int efb_port_project_weights(efb_system *sys, efb_port *port, int32_t rhs, double *v_c128);
+/* V = e^H M_s x (src/assemble_maxwell.cpp:774) */
+int efb_port_project_mass(efb_system *sys, efb_port *port, int32_t rhs, double *v_c128);
+
+/* ------------------------------------------------------------------ periodic (a16)
+ * In-place Bloch elimination A <- T A T^H, b <- T b with T = I + sum phase_k e_m e_s^T,
+ * then slave rows/cols -> identity, b[s] = 0 (src/assemble_maxwell.cpp:527-566).  The pair
+ * targets must be in the pattern: pass efb_periodic_extra() entries to efb_system_create. */
+int efb_periodic_extra(const efb_mesh *mesh, int64_t n_base_extra, const int32_t *base_rows,
+                       const int32_t *base_cols, int32_t n_pairs, const int32_t *master,
+                       const int32_t *slave, int64_t *n_out, int32_t *rows_out,
+                       int32_t *cols_out); /* call with rows_out==NULL to size */
+int efb_apply_periodic(efb_system *sys, int32_t first, int32_t count, int32_t n_pairs,
+                       const int32_t *master, const int32_t *slave,
+                       const double *phase_c128 /* [n_pairs]: phi*o_m*o_s */);
+
+/* ------------------------------------------------------------------ rhs / solution */
+int efb_rhs_zero(efb_system *sys, int32_t rhs);
+int efb_rhs_set(efb_system *sys, int32_t rhs, const double *b_c128 /* [m] */);
+int efb_rhs_get(efb_system *sys, int32_t rhs, double *b_c128);
+int efb_x_get(efb_system *sys, int32_t rhs, double *x_c128);
+int efb_x_set(efb_system *sys, int32_t rhs, const double *x_c128);
+/* x[rhs][dst_k] = phase_k * x[rhs][src_k] (slave recovery, src/assemble_maxwell.cpp:607-613) */
+int efb_x_recover(efb_system *sys, int32_t rhs, int32_t n, const int32_t *dst,
+                  const int32_t *src, const double *phase_c128);
+
+/* ------------------------------------------------------------------ solve (K3, K4)
+ * Replaces solve_linear (src/solver.cpp:35-193).  Eigen's BiCGSTAB/IncompleteLUT/SparseLU
+ * are not reproduced; the contract kept is SolveResult's: iterations, relative residual
+ * ||b-Ax||/||b|| (TRUE residual, recomputed), converged flag.                           */
+typedef enum { EFB_METHOD_AUTO = 0, EFB_METHOD_BICGSTAB = 1, EFB_METHOD_COCG = 2 } efb_method;
+typedef enum { EFB_PRECOND_JACOBI = 0, EFB_PRECOND_AUX = 1 /* Jacobi + nodal gradient-space Jacobi */,
+               EFB_PRECOND_NONE = 2 } efb_precond;
+
+typedef struct {
+  int32_t method;        /* efb_method; AUTO = COCG when symmetric_hint else BiCGSTAB */
+  int32_t precond;       /* efb_precond */
+  double tolerance;      /* relative residual (SolveOptions::tolerance, solver.hpp:20) */
+  int32_t max_iterations;
+  int32_t check_every;   /* host convergence poll interval in iterations (0 = default 32) */
+  int32_t symmetric_hint;/* 1: A == A^T (complex symmetric) */
+  int32_t zero_initial_guess; /* 1 (reference behaviour) or 0 to start from x */
+  int32_t max_restarts;  /* true-residual restarts (default 3) */
+  int32_t _pad;
+} efb_solve_opts;
+
+typedef struct {
+  int32_t iters;
+  int32_t converged;
+  int32_t method;   /* efb_method actually used */
+  int32_t precond;
+  double residual;  /* true relative residual */
+} efb_solve_result;
+
+int efb_solve(efb_system *sys, int32_t first_matrix, int32_t n_matrix,
+              const efb_solve_opts *opts, efb_solve_result *results /* [n_matrix*n_rhs] */);
+/* y = A[matrix] x on device, host in/out (test + diagnostics) */
+int efb_spmv_host(efb_system *sys, int32_t matrix, const double *x_c128, double *y_c128);
+
+/* ------------------------------------------------------------------ benchmarking hooks
+ * Run a kernel `reps` times on resident data and return the average ms (CUDA events on the
+ * ctx stream).  which: 0 = SpMV (all matrices, all rhs), 1 = one BiCGSTAB iteration,
+ * 2 = one COCG iteration, 3 = volume assembly (mode 0, last used materials/omegas).      */
+int efb_bench_kernel(efb_system *sys, int32_t which, int32_t reps, double *avg_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EDGEFEM_B200_H */

@@ -256,16 +256,23 @@ def pec_mask(mesh: Mesh, pec: Set[int]) -> np.ndarray:
 def gradients_and_volume(X: np.ndarray):
     """X: [...,4,3] -> g [...,4,3], V [...]   (src/edge_basis.cpp:14-26)."""
     X = np.asarray(X, dtype=np.float64)
-    B = np.stack([X[..., 0, :] - X[..., 3, :], X[..., 1, :] - X[..., 3, :], X[..., 2, :] - X[..., 3, :]], axis=-1)
-    # B.col(k) = v[k]-v[3]  => B[..., :, k]
-    Binv = np.linalg.inv(B)
-    BinvT = np.swapaxes(Binv, -1, -2)
-    g0 = BinvT[..., :, 0]
-    g1 = BinvT[..., :, 1]
-    g2 = BinvT[..., :, 2]
+    # columns of B (B.col(k) = v[k]-v[3]); Eigen's fixed-size 3x3 inverse is cofactors * (1/det),
+    # i.e. rows of B^-1 are cross products of the columns over det -- restated literally so the
+    # oracle rounds like the reference rather than like LAPACK's pivoted LU.
+    b0 = X[..., 0, :] - X[..., 3, :]
+    b1 = X[..., 1, :] - X[..., 3, :]
+    b2 = X[..., 2, :] - X[..., 3, :]
+    c12 = np.cross(b1, b2)
+    c20 = np.cross(b2, b0)
+    c01 = np.cross(b0, b1)
+    det = np.einsum("...k,...k->...", b0, c12)
+    invdet = 1.0 / det
+    g0 = c12 * invdet[..., None]
+    g1 = c20 * invdet[..., None]
+    g2 = c01 * invdet[..., None]
     g3 = -g0 - g1 - g2
     g = np.stack([g0, g1, g2, g3], axis=-2)
-    V = np.abs(np.linalg.det(B)) / 6.0
+    V = np.abs(det) / 6.0
     return g, V
 
 
@@ -631,6 +638,16 @@ def volume_element_values(mesh: Mesh, p: MaxwellParams) -> np.ndarray:
     sg = mesh.tet_orient.astype(np.float64)
     val = val * (sg[:, :, None] * sg[:, None, :])
     return val
+
+
+def volume_abs_scale(mesh: Mesh, p: MaxwellParams) -> sp.csr_matrix:
+    """sum over tets of |element contribution| per entry: the natural scale for comparing two
+    floating-point summations of the same triplets (an entry whose contributions cancel cannot
+    be reproduced to 1e-12 of its own magnitude by ANY summation order, Eigen's included)."""
+    val = np.abs(volume_element_values(mesh, p))
+    gi = np.repeat(mesh.tet_edges[:, :, None], 6, axis=2).reshape(-1)
+    gj = np.repeat(mesh.tet_edges[:, None, :], 6, axis=1).reshape(-1)
+    return triplets_to_csr(gi, gj, val.reshape(-1).astype(np.complex128), mesh.num_edges)
 
 
 def _abc_edges(mesh: Mesh, p: MaxwellParams, pec: Set[int]) -> np.ndarray:

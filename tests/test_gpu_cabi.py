@@ -1,0 +1,92 @@
+"""GPU parity tests through the C-ABI (run with -m gpu on a B200)."""
+import math
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import edgefem_oracle as orc
+from edgefem_b200 import cabi
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = cabi.Ctx(0)
+    yield c
+    c.close()
+
+
+def test_pattern_bit_exact_and_values(ctx, wr90):
+    """CSR pattern identical to the oracle's (setFromTriplets + Dirichlet diag), values within 1e-12 (fp64)."""
+    mesh, pec = wr90
+    p = orc.MaxwellParams(omega=2 * math.pi * 10e9)
+    A, b = orc.assemble_maxwell(mesh, p, pec)
+    dm = H.device_mesh(ctx, mesh)
+    pe = np.nonzero(orc.pec_mask(mesh, pec))[0].astype(np.int32)
+    sysd = cabi.DeviceSystem.from_mesh(dm, pe, pe)
+    sysd.set_dirichlet(H.pec_flags(mesh, pec))
+    mats, keep = cabi.make_materials(len(dm.slot_tags))
+    sysd.assemble_volume([p.omega], mats)
+    rp, ci = sysd.pattern()
+    assert sysd.nnz == A.nnz == 85113
+    assert np.array_equal(rp, A.indptr) and np.array_equal(ci, A.indices)
+    v = sysd.values(0)
+    err = H.rel_entry_err(v, A.data)
+    G0 = sp.csr_matrix((v, ci, rp), shape=A.shape)
+    serr = H.sum_rel_err(G0, A, orc.volume_abs_scale(mesh, p))
+    print("assembly err: vs entry (floored)", err, " vs sum of |contributions|", serr)
+    assert serr < 1e-12   # fp64 bar: 1e-12 relative (tolerance stated by north_star)
+    assert err < 1e-10
+    # explicit zeros are kept and Dirichlet rows are identity
+    pm = orc.pec_mask(mesh, pec)
+    G = sp.csr_matrix((v, ci, rp), shape=A.shape)
+    assert np.allclose(G.diagonal()[pm], 1.0)
+    sysd.close(); dm.close()
+
+
+def test_spmv_matches_scipy(ctx, wr90):
+    mesh, pec = wr90
+    p = orc.MaxwellParams(omega=2 * math.pi * 9e9, eps_r=2.2 - 0.01j)
+    A, _ = orc.assemble_maxwell(mesh, p, pec)
+    sysd = cabi.DeviceSystem.from_csr(ctx, A.indptr, A.indices, A.data)
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(A.shape[0]) + 1j * rng.standard_normal(A.shape[0])
+    y = sysd.spmv(0, x)
+    yr = A @ x
+    assert np.max(np.abs(y - yr)) <= 1e-13 * np.max(np.abs(yr))
+    sysd.close()
+
+
+@pytest.mark.parametrize("method,precond", [(cabi.METHOD_COCG, cabi.PRECOND_AUX), (cabi.METHOD_COCG, cabi.PRECOND_JACOBI),
+                                            (cabi.METHOD_BICGSTAB, cabi.PRECOND_AUX)])
+def test_wr90_sparams_10ghz(ctx, wr90, kat, method, precond):
+    """calculate_sparams_eigenmode at 10 GHz: oracle (SuperLU) within 1e-6, reference table digits."""
+    mesh, pec = wr90
+    f = 10e9
+    ports = orc.wr90_ports(mesh, pec, f)
+    S_ref = orc.wr90_sparams(mesh, pec, f, ports)
+    S, res = H.eigenmode_sweep_gpu(ctx, mesh, pec, ports, [f], method=method, precond=precond)
+    print("iters", [r["iters"] for r in res], "res", [r["residual"] for r in res])
+    assert all(r["converged"] for r in res)
+    assert all(r["residual"] <= 1e-10 * 1.001 for r in res)
+    assert np.max(np.abs(S[0] - S_ref)) <= 1e-6 * np.max(np.abs(S_ref))
+    row = [r for r in kat["wr90_table"]["rows"] if r[0] == 10.0][0]
+    assert abs(abs(S[0][0, 0]) - row[1]) < 5e-4 + 5e-4
+    assert abs(abs(S[0][1, 0]) - row[2]) < 1e-4
+    assert abs(np.angle(S[0][1, 0], deg=True) - row[3]) < 0.06
+
+
+def test_wr90_sweep_batched(ctx, wr90):
+    """8 frequencies x 2 ports solved as ONE batch; each S matches the oracle within 1e-6."""
+    mesh, pec = wr90
+    freqs = np.linspace(8e9, 12e9, 8)
+    ports = orc.wr90_ports(mesh, pec, 10e9)  # port modes are frequency independent (kc, weights)
+    S, res = H.eigenmode_sweep_gpu(ctx, mesh, pec, ports, freqs)
+    assert all(r["converged"] for r in res)
+    for fi, f in enumerate(freqs):
+        S_ref = orc.wr90_sparams(mesh, pec, f, ports)
+        assert np.max(np.abs(S[fi] - S_ref)) <= 1e-6, (f, S[fi], S_ref)
+    print("iters", [r["iters"] for r in res])
