@@ -1,0 +1,410 @@
+#!/usr/bin/env python
+"""bench.py -- EdgeFEM hot path on B200: frequency points/s on the WR-90 sweep (8-12 GHz, 256
+points, BASELINE.json configs[1]), plus assembly Mtets/s and SpMV HBM GB/s on a synthetic cube.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A "step" is one pass of the hot path over one batch: the full 256-point, 2-port eigenmode sweep
+(512 complex sparse solves) -- volume assembly, port terms, right-hand sides, batched Krylov
+solve, S-parameter projection.
+  value : points/s with the mesh, CSR pattern and port operators already resident in HBM
+  e2e   : points/s through the public API (pyedgefem.calculate_sparams_eigenmode_sweep) from host
+          buffers: mesh upload, pattern build, port upload and S read-back inside the timed region
+Multi-GPU (torchrun, one rank per GPU): the sweep shards by frequency with no data-path
+collective; every rank sweeps its own 256-point sub-band ("weak"), S is all-gathered at the end.
+Timing: CUDA events on the library's stream (efb_timer_*), barrier + synchronize on both sides,
+max over ranks.  Working set per step (349 MB of matrix values + 330 MB of Krylov vectors) is
+larger than the 126 MB L2, so no explicit L2 flush is needed between timed iterations.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+C0 = 299792458.0
+WR90_A, WR90_B = 0.02286, 0.01016
+F_LO, F_HI, N_POINTS = 8e9, 12e9, 256
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--points", type=int, default=N_POINTS)
+    ap.add_argument("--cube-n", type=int, default=64, help="synthetic cube (n^3 boxes x 6 tets) for the assembly / SpMV roofline extras; 0 = skip")
+    ap.add_argument("--cpu-sample", type=int, default=12, help="frequency points of the CPU baseline sample")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    def __init__(self, device: int):
+        self.device, self.samples, self.reasons, self.max_mhz = device, [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split("\n")[0]
+                parts = [x.strip() for x in out.split(",")]
+                self.samples.append(float(parts[0]))
+                self.max_mhz = float(parts[1])
+                for n, v in zip(names, parts[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------ reference arm (CPU oracle)
+def _oracle_points(args):
+    """Worker: eigenmode S-parameters of a list of frequencies with the CPU oracle (SuperLU)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import edgefem_oracle as orc
+
+    freqs, = args
+    z = np.load(os.path.join(ROOT, "tests", "golden", "rect_waveguide.npz"))
+    mesh = orc.mesh_from_arrays(z["xyz"], z["tet_conn"], z["tet_phys"], z["tri_conn"], z["tri_phys"], node_ids=z["node_ids"])
+    pec = orc.build_edge_pec(mesh, 1)
+    ports = orc.wr90_ports(mesh, pec, 10e9)
+    t0 = time.perf_counter()
+    out = [orc.wr90_sparams(mesh, pec, f, ports) for f in freqs]
+    return time.perf_counter() - t0, len(out)
+
+
+def cpu_baseline(n_points: int, cores: int):
+    """points/s of the oracle (restated reference path: per-frequency triplet assembly + SuperLU solves)
+    on `cores` host processes; setup (mesh, port modes) excluded like the GPU arm's resident number."""
+    import numpy as np
+
+    freqs = list(np.linspace(F_LO, F_HI, n_points))
+    import multiprocessing as mp
+
+    # one BLAS/OpenMP thread per worker process: `cores` is then the number of threads really used
+    # (and 8 workers x 8 spinning OpenBLAS threads on 8 cores would otherwise livelock)
+    pinned = {k: os.environ.get(k) for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS")}
+    for k in pinned:
+        os.environ[k] = "1"
+    try:
+        chunks = [freqs[i::cores] for i in range(cores)]
+        chunks = [c for c in chunks if c]
+        with mp.get_context("spawn").Pool(len(chunks)) as pool:
+            res = pool.map(_oracle_points, [(c,) for c in chunks])
+    finally:
+        for k, v in pinned.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    # worker start-up (imports, mesh, port eigen-solves) is excluded: use the slowest worker's compute time
+    slowest = max(r[0] for r in res)
+    return sum(r[1] for r in res) / slowest
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = max(cores, min(2 * cores, 64))
+    vals = []
+    for _ in range(a.warmup):
+        cpu_baseline(sample, cores)
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        vals.append(cpu_baseline(sample, cores))
+    wall = time.perf_counter() - t0
+    v = sum(vals) / len(vals)
+    line = {
+        "impl": "reference", "metric": "wr90_sweep_freq_points_per_s", "value": v, "unit": "points/s", "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1000.0 * wall / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "WR-90 eigenmode sweep 8-12 GHz (rect_waveguide fixture, 4227 tets, 2 ports), bounded sample of %d points per step" % sample},
+        "cpu_baseline": {"value": v, "unit": "points/s", "cores": cores, "kind": "port",
+                         "sample": "%d of 256 frequency points per step, %d processes; oracle = numpy/scipy restatement (Eigen is not installable here), "
+                                   "per-frequency assembly + SuperLU factorisation + 2 solves" % (sample, cores)},
+        "e2e": {"value": v, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ B200 arm
+def mesh_arrays(hm):
+    return dict(xyz=hm.xyz_array(), tet_nodes=hm.tet_nodes_array(), tet_edges=hm.tet_edges_array(), tet_orient=hm.tet_orient_array(),
+                tet_phys=hm.tet_phys_array(), edge_nodes=hm.edge_nodes_array())
+
+
+class ResidentSweep:
+    """The hot path with every input already in HBM: one call = one full sweep step."""
+
+    def __init__(self, ctx, pe, hm, bc, ports, freqs):
+        import numpy as np
+        from edgefem_b200 import cabi
+
+        self.np, self.cabi, self.ctx = np, cabi, ctx
+        arr = mesh_arrays(hm)
+        self.dm = cabi.DeviceMesh(ctx, arr["xyz"], arr["tet_nodes"], arr["tet_edges"], arr["tet_orient"], arr["tet_phys"], arr["edge_nodes"])
+        flags = np.zeros(hm.num_edges(), dtype=np.uint8)
+        flags[np.asarray(bc.dirichlet_edges, dtype=np.int64)] = 1
+        pe_idx = np.nonzero(flags)[0].astype(np.int32)
+        self.F, self.P = len(freqs), len(ports)
+        self.sys = cabi.DeviceSystem.from_mesh(self.dm, pe_idx, pe_idx, n_matrix=self.F, n_rhs=self.P)
+        self.sys.set_dirichlet(flags)
+        self.mats, self._keep = cabi.make_materials(len(self.dm.slot_tags))
+        self.omegas = np.array([2 * math.pi * f for f in freqs])
+        self.dports = []
+        for port in ports:
+            rp, ci, va = pe.assemble_port_surface_mass(hm, port.surface_tag, set(bc.dirichlet_edges)).to_csr()
+            rows = np.repeat(np.arange(len(rp) - 1), np.diff(rp)).astype(np.int32)
+            dp = cabi.DevicePort(self.sys, port.edges, port.weights, rows, ci, va)
+            dp.normalize_mass()
+            self.dports.append(dp)
+        k0 = self.omegas / C0
+        self.betas = np.stack([np.sqrt((k0 * k0 - p.mode.kc ** 2).astype(complex)) for p in ports], axis=1)  # [F,P] vacuum ports
+        self.idx = [np.arange(self.F, dtype=np.int32) * self.P + a for a in range(self.P)]
+        self.all_idx = np.arange(self.F * self.P, dtype=np.int32)
+        self.nnz, self.m = self.sys.nnz, self.sys.m
+        self.last = None
+
+    def step(self):
+        np = self.np
+        self.sys.assemble_volume(self.omegas, self.mats)
+        for a, dp in enumerate(self.dports):
+            dp.add_mass(1j * self.betas[:, a])
+        for a, dp in enumerate(self.dports):
+            dp.rhs_batch(self.idx[a], 2j * self.betas[:, a], use_mass=True)
+        res = self.sys.solve(precond=self.cabi.PRECOND_AUX, tol=1e-10, symmetric=True)
+        S = np.zeros((self.F, self.P, self.P), dtype=complex)
+        for j, dp in enumerate(self.dports):
+            v = dp.project_batch(self.all_idx, use_mass=True).reshape(self.F, self.P)
+            S[:, j, :] = v
+        for a in range(self.P):
+            S[:, a, a] -= 1.0
+        self.last = (S, res)
+        return S, res
+
+
+def cube_extras(ctx, pe, n: int):
+    """Assembly Mtets/s and SpMV GB/s on a synthetic PEC cube (Kuhn split, jittered), single frequency."""
+    import numpy as np
+    from edgefem_b200 import cabi, meshgen
+
+    t0 = time.perf_counter()
+    xyz, tets, tp, tris, trp = meshgen.cube_cavity(n, jitter=0.1)
+    hm = pe.mesh_from_arrays(xyz, tets, tp, tris, trp)
+    bc = pe.build_edge_pec(hm, 1)
+    arr = mesh_arrays(hm)
+    dm = cabi.DeviceMesh(ctx, arr["xyz"], arr["tet_nodes"], arr["tet_edges"], arr["tet_orient"], arr["tet_phys"], arr["edge_nodes"])
+    flags = np.zeros(hm.num_edges(), dtype=np.uint8)
+    flags[np.asarray(bc.dirichlet_edges, dtype=np.int64)] = 1
+    pe_idx = np.nonzero(flags)[0].astype(np.int32)
+    sysd = cabi.DeviceSystem.from_mesh(dm, pe_idx, pe_idx, n_matrix=1, n_rhs=1)
+    sysd.set_dirichlet(flags)
+    setup_s = time.perf_counter() - t0
+    h = 1.0 / n
+    omega = (2 * math.pi / (10 * h)) * C0  # k0 h = 2 pi / 10
+    mats, keep = cabi.make_materials(len(dm.slot_tags))
+    sysd.assemble_volume([omega], mats)
+    rng = np.random.default_rng(1234)
+    b = rng.standard_normal(sysd.m) + 1j * rng.standard_normal(sysd.m)
+    b[flags == 1] = 0
+    sysd.rhs_set(0, b)
+    sysd.x_set(0, b)
+    n_tet, n_node, m, nnz = hm.num_tets(), hm.num_nodes(), sysd.m, sysd.nnz
+    ms_asm = sysd.bench_kernel(3, 10)
+    ms_spmv = sysd.bench_kernel(0, 20)
+    ms_bicg = sysd.bench_kernel(1, 10)
+    ms_cocg = sysd.bench_kernel(2, 10)
+    b_asm = 45.0 * n_tet + 24.0 * n_node + 16.0 * nnz
+    b_spmv = nnz * 20.0 + m * 36.0
+    b_bicg = 2 * b_spmv + 21 * 16.0 * m
+    b_cocg = b_spmv + 10 * 16.0 * m
+    out = {
+        "mesh": {"n": n, "tets": n_tet, "nodes": n_node, "edges": m, "nnz": nnz, "host_setup_s": round(setup_s, 2)},
+        "assembly": {"ms": ms_asm, "mtets_per_s": n_tet / ms_asm / 1e3, "algorithmic_gb": b_asm / 1e9, "gbs": b_asm / ms_asm / 1e6},
+        "spmv": {"ms": ms_spmv, "algorithmic_gb": b_spmv / 1e9, "gbs": b_spmv / ms_spmv / 1e6},
+        "bicgstab_jacobi_iteration": {"ms": ms_bicg, "algorithmic_gb": b_bicg / 1e9, "gbs": b_bicg / ms_bicg / 1e6},
+        "cocg_jacobi_iteration": {"ms": ms_cocg, "algorithmic_gb": b_cocg / 1e9, "gbs": b_cocg / ms_cocg / 1e6},
+    }
+    sysd.close()
+    dm.close()
+    return out
+
+
+def run_b200(a):
+    import numpy as np
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ.setdefault("EDGEFEM_B200_DEVICE", str(local))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from edgefem_b200 import cabi, load_pyedgefem
+
+    pe = load_pyedgefem()  # fails loudly if the extension was not built
+    ctx = cabi.Ctx(local)
+    peaks = {}
+    if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fjs:
+            peaks = json.load(fjs)
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+
+    z = np.load(os.path.join(ROOT, "tests", "golden", "rect_waveguide.npz"))
+    hm = pe.mesh_from_arrays(z["xyz"], z["tet_conn"], z["tet_phys"], z["tri_conn"], z["tri_phys"], z["node_ids"].tolist())
+    bc = pe.build_edge_pec(hm, 1)
+    dims = pe.RectWaveguidePort(WR90_A, WR90_B)
+    kc_sq = (math.pi / WR90_A) ** 2
+    ports = [pe.build_wave_port_2d(hm, tag, pe.solve_te10_mode(dims, 10e9), set(bc.dirichlet_edges), kc_sq) for tag in (2, 3)]
+    # weak scaling: rank r sweeps its own 256-point sub-band of 8-12 GHz
+    allf = np.linspace(F_LO, F_HI, a.points * world)
+    freqs = list(allf[rank::world])
+
+    def barrier():
+        ctx.sync()
+        if dist is not None:
+            dist.barrier()
+
+    # ---------------- resident ("value") ----------------
+    rs = ResidentSweep(ctx, pe, hm, bc, ports, freqs)
+    for _ in range(a.warmup):
+        rs.step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = ctx.launch_count()
+    ctx.timer_start()
+    for _ in range(a.steps):
+        S, res = rs.step()
+    ms_total = ctx.timer_stop()
+    launches = ctx.launch_count() - launches0
+    barrier()
+    clocks = sampler.stop()
+    if dist is not None:
+        import torch
+
+        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        gathered = [torch.zeros(S.shape + (2,), dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(gathered, torch.from_numpy(np.stack([S.real, S.imag], axis=-1)).cuda())
+    ms_step = ms_total / a.steps
+    value = a.points * world / (ms_step / 1000.0)
+    iters = [r["iters"] for r in res]
+    assert all(r["converged"] for r in res), "a solve did not converge"
+    # per-kernel roofline of the dominant kernel (batched CSR SpMV), timed live with CUDA events on the launching stream
+    ms_spmv = rs.sys.bench_kernel(0, 50)
+    ms_iter = rs.sys.bench_kernel(2, 50)
+    F, P, nnz, m = rs.F, rs.P, rs.nnz, rs.m
+    spmv_bytes = F * nnz * 16.0 + nnz * 4.0 + (m + 1) * 4.0 + F * P * m * 32.0
+    roof = {"bound": "hbm", "kernel": "k_spmv<16,2,*> (batched CSR complex128 SpMV, %d matrices x %d rhs)" % (F, P),
+            "achieved": spmv_bytes / ms_spmv / 1e6, "peak": hbm_peak, "unit": "GB/s", "frac": spmv_bytes / ms_spmv / 1e6 / hbm_peak,
+            "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": spmv_bytes, "ms_per_launch": ms_spmv,
+            "cocg_iteration_ms": ms_iter}
+
+    # ---------------- end to end through the public API ----------------
+    p = pe.MaxwellParams()
+    for _ in range(max(1, min(a.warmup, 2))):
+        pe.b200_clear_cache()
+        pe.calculate_sparams_eigenmode_sweep(hm, p, bc, ports, freqs)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(a.steps, 3))
+    h2d = d2h = 0
+    for _ in range(e2e_steps):
+        pe.b200_clear_cache()
+        S2, st = pe.calculate_sparams_eigenmode_sweep(hm, p, bc, ports, freqs)
+        h2d, d2h = st.h2d_bytes, st.d2h_bytes
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if dist is not None:
+        import torch
+
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    assert np.max(np.abs(np.array(S2) - S)) < 1e-6, "public API and resident path disagree"
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    extras = {}
+    if a.cube_n > 0:
+        try:
+            extras = cube_extras(ctx, pe, a.cube_n)
+            for k in ("assembly", "spmv", "bicgstab_jacobi_iteration", "cocg_jacobi_iteration"):
+                extras[k]["frac_of_hbm_peak"] = extras[k]["gbs"] / hbm_peak
+        except Exception as e:  # extras never invalidate the headline number
+            extras = {"error": repr(e)}
+    cores = os.cpu_count() or 1
+    cpu1 = cpu_baseline(a.cpu_sample, 1)
+    line = {
+        "metric": "wr90_sweep_freq_points_per_s", "value": value, "unit": "points/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "WR-90 eigenmode S-parameter sweep 8-12 GHz, %d points/GPU x 2 ports (rect_waveguide fixture: 4227 tets, 5745 edges, "
+                               "nnz 85113), tol 1e-10, COCG + auxiliary-space Jacobi" % a.points,
+                   "points_per_gpu": a.points, "total_points": a.points * world, "solves_per_step": a.points * 2 * world,
+                   "l2": "inputs larger than L2 (349 MB values + 330 MB vectors per GPU); no flush",
+                   "krylov_iterations": {"min": int(min(iters)), "median": int(sorted(iters)[len(iters) // 2]), "max": int(max(iters))}},
+        "roofline": roof,
+        "cpu_baseline": {"value": cpu1, "unit": "points/s", "cores": 1, "kind": "port",
+                         "sample": "%d of 256 points, 1 process: oracle (numpy/scipy restatement of the reference path, SuperLU solves); "
+                                   "host has %d cores" % (a.cpu_sample, cores)},
+        "e2e": {"value": a.points * world / e2e_s, "unit": "points/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": 1000.0 * e2e_s, "api": "pyedgefem.calculate_sparams_eigenmode_sweep (mesh cache cleared every step)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "extras": extras,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -76,6 +76,8 @@ SIGNATURES = {
     "efb_ctx_sync": (C.c_int, [C.c_void_p]),
     "efb_last_kernel_ms": (C.c_double, [C.c_void_p]),
     "efb_launch_count": (C.c_int64, [C.c_void_p]),
+    "efb_timer_start": (C.c_int, [C.c_void_p]),
+    "efb_timer_stop": (C.c_int, [C.c_void_p, f64p]),
     "efb_mesh_create": (C.c_int, [C.c_void_p, C.POINTER(MeshDesc), C.POINTER(C.c_void_p)]),
     "efb_mesh_destroy": (None, [C.c_void_p]),
     "efb_mesh_num_slots": (C.c_int, [C.c_void_p]),
@@ -101,6 +103,8 @@ SIGNATURES = {
     "efb_port_rhs_mass": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, f64p]),
     "efb_port_project_weights": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, f64p]),
     "efb_port_project_mass": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, f64p]),
+    "efb_port_rhs_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, i32p, f64p, C.c_int32]),
+    "efb_port_project_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, i32p, f64p, C.c_int32]),
     "efb_periodic_extra": (C.c_int, [C.c_void_p, C.c_int64, i32p, i32p, C.c_int32, i32p, i32p, i64p, i32p, i32p]),
     "efb_apply_periodic": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, i32p, i32p, f64p]),
     "efb_rhs_zero": (C.c_int, [C.c_void_p, C.c_int32]),
@@ -172,6 +176,14 @@ class Ctx:
 
     def launch_count(self) -> int:
         return int(self.lib.efb_launch_count(self.h))
+
+    def timer_start(self):
+        self.check(self.lib.efb_timer_start(self.h), "efb_timer_start")
+
+    def timer_stop(self) -> float:
+        ms = C.c_double()
+        self.check(self.lib.efb_timer_stop(self.h, C.byref(ms)), "efb_timer_stop")
+        return ms.value
 
     def close(self):
         if self.h:
@@ -382,6 +394,19 @@ class DevicePort:
     def rhs_mass(self, rhs, coef):
         cf = self._coef([coef])
         self.sys.ctx.check(self.sys.ctx.lib.efb_port_rhs_mass(self.sys.h, self.h, rhs, _p(cf.view(np.float64), f64p)), "efb_port_rhs_mass")
+
+    def rhs_batch(self, rhs_idx, coef, use_mass: bool):
+        idx, cf = _i32(rhs_idx), self._coef(coef)
+        assert idx.size == cf.size
+        self.sys.ctx.check(self.sys.ctx.lib.efb_port_rhs_batch(self.sys.h, self.h, idx.size, _p(idx, i32p), _p(cf.view(np.float64), f64p),
+                                                               1 if use_mass else 0), "efb_port_rhs_batch")
+
+    def project_batch(self, rhs_idx, use_mass: bool) -> np.ndarray:
+        idx = _i32(rhs_idx)
+        out = np.zeros(idx.size, dtype=np.complex128)
+        self.sys.ctx.check(self.sys.ctx.lib.efb_port_project_batch(self.sys.h, self.h, idx.size, _p(idx, i32p), _p(out.view(np.float64), f64p),
+                                                                   1 if use_mass else 0), "efb_port_project_batch")
+        return out
 
     def project_weights(self, rhs) -> complex:
         out = np.zeros(1, dtype=np.complex128)

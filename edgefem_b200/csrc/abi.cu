@@ -140,6 +140,8 @@ int efb_ctx_create(int device, efb_ctx **out) {
   EFB_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   EFB_CUDA(c, cudaEventCreate(&c->ev0));
   EFB_CUDA(c, cudaEventCreate(&c->ev1));
+  EFB_CUDA(c, cudaEventCreate(&c->tm0));
+  EFB_CUDA(c, cudaEventCreate(&c->tm1));
   cudaDeviceProp prop;
   EFB_CUDA(c, cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
@@ -154,6 +156,8 @@ void efb_ctx_destroy(efb_ctx *ctx_) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->tm0) cudaEventDestroy(c->tm0);
+  if (c->tm1) cudaEventDestroy(c->tm1);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -175,6 +179,26 @@ double efb_last_kernel_ms(const efb_ctx *ctx_) {
 }
 
 int64_t efb_launch_count(const efb_ctx *ctx_) { return ctx_ ? ((const Ctx *)ctx_)->launches : 0; }
+
+int efb_timer_start(efb_ctx *ctx_) {
+  Ctx *c = (Ctx *)ctx_;
+  if (!c) return EFB_ERR_INVALID;
+  EFB_CUDA(c, cudaSetDevice(c->device));
+  EFB_CUDA(c, cudaEventRecord(c->tm0, c->stream));
+  return EFB_OK;
+}
+
+int efb_timer_stop(efb_ctx *ctx_, double *ms) {
+  Ctx *c = (Ctx *)ctx_;
+  if (!c || !ms) return EFB_ERR_INVALID;
+  EFB_CUDA(c, cudaSetDevice(c->device));
+  EFB_CUDA(c, cudaEventRecord(c->tm1, c->stream));
+  EFB_CUDA(c, cudaEventSynchronize(c->tm1));
+  float f = 0.f;
+  EFB_CUDA(c, cudaEventElapsedTime(&f, c->tm0, c->tm1));
+  *ms = (double)f;
+  return EFB_OK;
+}
 
 // ------------------------------------------------------------------ mesh
 int efb_mesh_create(efb_ctx *ctx_, const efb_mesh_desc *d, efb_mesh **out) {

@@ -450,6 +450,42 @@ __global__ void k_x_recover(c128 *x, const int32_t *__restrict__ dst, const int3
   x[dst[k]] = cmul(phase[k], x[src[k]]);
 }
 
+__global__ void k_rhs_weights_batch(c128 *b, int m, const int32_t *__restrict__ rhs_idx, const c128 *__restrict__ coef,
+                                    const int32_t *__restrict__ edges, const c128 *__restrict__ w, int n, const uint8_t *__restrict__ dir) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int e = edges[k];
+  if (dir[e]) return;
+  atomic_cadd(&b[(size_t)rhs_idx[blockIdx.y] * m + e], cmul(coef[blockIdx.y], w[k]));
+}
+
+__global__ void k_rhs_mass_batch(c128 *b, int m, const int32_t *__restrict__ rhs_idx, const c128 *__restrict__ coef,
+                                 const int32_t *__restrict__ rows, const int32_t *__restrict__ cols, const double *__restrict__ mv,
+                                 long long n, const c128 *__restrict__ e_dense) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  atomic_cadd(&b[(size_t)rhs_idx[blockIdx.y] * m + rows[i]], cmul(coef[blockIdx.y], cscale(mv[i], e_dense[cols[i]])));
+}
+
+// one CTA per right-hand side: V = sum conj(w) x (weights) or e^H M_s x (mass)
+__global__ void k_project_batch(const c128 *__restrict__ x, int m, const int32_t *__restrict__ rhs_idx, c128 *out, int use_mass,
+                                const int32_t *__restrict__ edges, const c128 *__restrict__ w, int n_edges,
+                                const uint8_t *__restrict__ dir, const c128 *__restrict__ e_dense, const int32_t *__restrict__ rows,
+                                const int32_t *__restrict__ cols, const double *__restrict__ mv, long long n_ms) {
+  const c128 *xv = x + (size_t)rhs_idx[blockIdx.x] * m;
+  c128 acc = cmake(0.0, 0.0);
+  if (use_mass) {
+    for (long long i = threadIdx.x; i < n_ms; i += blockDim.x) acc = cadd(acc, cmulconj(e_dense[rows[i]], cscale(mv[i], xv[cols[i]])));
+  } else {
+    for (int k = threadIdx.x; k < n_edges; k += blockDim.x) {
+      const int e = edges[k];
+      if (!dir[e]) acc = cadd(acc, cmulconj(w[k], xv[e]));
+    }
+  }
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) out[blockIdx.x] = acc;
+}
+
 static int check_flag(System *S, const char *who) {
   Ctx *c = S->ctx;
   int32_t h = 0;
@@ -706,6 +742,62 @@ int efb_port_project_mass(efb_system *sys_, efb_port *port_, int32_t rhs, double
   k_bilinear_mass<<<1, 256, 0, c->stream>>>(P->d_e, S->d_x + (size_t)rhs * S->m, P->d_ms_row, P->d_ms_col, P->d_ms_val, (long long)P->n_ms, P->d_tmp + 2);
   EFB_CHECK_LAUNCH(c);
   EFB_CUDA(c, cudaMemcpyAsync(v, P->d_tmp + 2, sizeof(c128), cudaMemcpyDeviceToHost, c->stream));
+  EFB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return EFB_OK;
+}
+
+// ---- batched variants: one launch for many right-hand sides (sweeps: F frequencies x P ports)
+static int batch_args(System *S, Port *P, int32_t count, const int32_t *rhs_idx, const char *who) {
+  if (!S || !P || P->sys != S || count <= 0 || !rhs_idx) return fail(S ? S->ctx : nullptr, EFB_ERR_INVALID, "%s: bad arguments", who);
+  for (int i = 0; i < count; ++i)
+    if (rhs_idx[i] < 0 || rhs_idx[i] >= S->n_sys) return fail(S->ctx, EFB_ERR_INVALID, "%s: rhs index out of range", who);
+  return EFB_OK;
+}
+
+int efb_port_rhs_batch(efb_system *sys_, efb_port *port_, int32_t count, const int32_t *rhs_idx, const double *coef, int32_t use_mass) {
+  System *S = (System *)sys_;
+  Port *P = (Port *)port_;
+  int rc = batch_args(S, P, count, rhs_idx, "efb_port_rhs_batch");
+  if (rc) return rc;
+  if (!coef) return fail(S->ctx, EFB_ERR_INVALID, "efb_port_rhs_batch: coef is NULL");
+  Ctx *c = S->ctx;
+  EFB_CUDA(c, cudaSetDevice(c->device));
+  TmpBuf ti, tc;
+  EFB_CUDA(c, cudaMalloc(&ti.p, (size_t)count * 4));
+  EFB_CUDA(c, cudaMalloc(&tc.p, (size_t)count * 16));
+  EFB_CUDA(c, cudaMemcpyAsync(ti.p, rhs_idx, (size_t)count * 4, cudaMemcpyHostToDevice, c->stream));
+  EFB_CUDA(c, cudaMemcpyAsync(tc.p, coef, (size_t)count * 16, cudaMemcpyHostToDevice, c->stream));
+  if (use_mass) {
+    if (P->n_ms > 0) {
+      dim3 g((unsigned)((P->n_ms + 127) / 128), (unsigned)count);
+      k_rhs_mass_batch<<<g, 128, 0, c->stream>>>(S->d_b, S->m, (const int32_t *)ti.p, (const c128 *)tc.p, P->d_ms_row, P->d_ms_col, P->d_ms_val, (long long)P->n_ms, P->d_e);
+      EFB_CHECK_LAUNCH(c);
+    }
+  } else {
+    dim3 g((unsigned)((P->n_edges + 127) / 128), (unsigned)count);
+    k_rhs_weights_batch<<<g, 128, 0, c->stream>>>(S->d_b, S->m, (const int32_t *)ti.p, (const c128 *)tc.p, P->d_edges, P->d_w, P->n_edges, S->d_dir);
+    EFB_CHECK_LAUNCH(c);
+  }
+  EFB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return EFB_OK;
+}
+
+int efb_port_project_batch(efb_system *sys_, efb_port *port_, int32_t count, const int32_t *rhs_idx, double *out, int32_t use_mass) {
+  System *S = (System *)sys_;
+  Port *P = (Port *)port_;
+  int rc = batch_args(S, P, count, rhs_idx, "efb_port_project_batch");
+  if (rc) return rc;
+  if (!out) return fail(S->ctx, EFB_ERR_INVALID, "efb_port_project_batch: out is NULL");
+  Ctx *c = S->ctx;
+  EFB_CUDA(c, cudaSetDevice(c->device));
+  TmpBuf ti, to;
+  EFB_CUDA(c, cudaMalloc(&ti.p, (size_t)count * 4));
+  EFB_CUDA(c, cudaMalloc(&to.p, (size_t)count * 16));
+  EFB_CUDA(c, cudaMemcpyAsync(ti.p, rhs_idx, (size_t)count * 4, cudaMemcpyHostToDevice, c->stream));
+  k_project_batch<<<(unsigned)count, 128, 0, c->stream>>>(S->d_x, S->m, (const int32_t *)ti.p, (c128 *)to.p, use_mass, P->d_edges, P->d_w, P->n_edges,
+                                                          S->d_dir, P->d_e, P->d_ms_row, P->d_ms_col, P->d_ms_val, (long long)P->n_ms);
+  EFB_CHECK_LAUNCH(c);
+  EFB_CUDA(c, cudaMemcpyAsync(out, to.p, (size_t)count * 16, cudaMemcpyDeviceToHost, c->stream));
   EFB_CUDA(c, cudaStreamSynchronize(c->stream));
   return EFB_OK;
 }

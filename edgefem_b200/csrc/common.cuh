@@ -59,6 +59,7 @@ struct Ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t tm0 = nullptr, tm1 = nullptr;  // user stopwatch
   bool ev_valid = false;
   int64_t launches = 0;
   int sm_count = 148;

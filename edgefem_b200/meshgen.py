@@ -1,0 +1,109 @@
+"""Deterministic structured tetrahedral mesh generators + a Gmsh v2 ASCII writer (product-side
+utilities; gmsh itself is not available in this environment).
+
+All generators return plain numpy arrays ``(xyz, tets, tet_phys, tris, tri_phys)`` with 1-based
+node ids implied (node id = index + 1), ready for ``pyedgefem.mesh_from_arrays``.
+Every box is split into 6 tetrahedra with the Kuhn (Freudenthal) triangulation, which is
+face-compatible between neighbouring boxes and translation invariant -- opposite faces of a
+block carry identical triangulations, so periodic face pairs are node-matched by construction.
+"""
+from __future__ import annotations
+
+import itertools
+from typing import Callable, Dict, Optional, Sequence, Tuple
+
+import numpy as np
+
+# the 6 Kuhn tets of the unit cube: paths 000 -> 111 adding one axis at a time
+_KUHN = []
+for perm in itertools.permutations(range(3)):
+    v = [np.zeros(3, dtype=np.int64)]
+    for ax in perm:
+        nxt = v[-1].copy()
+        nxt[ax] = 1
+        v.append(nxt)
+    _KUHN.append(np.array(v))
+_KUHN = np.array(_KUHN)  # [6,4,3]
+
+
+def box_grid(xs: np.ndarray, ys: np.ndarray, zs: np.ndarray):
+    """Tensor-product grid -> (xyz [n,3], tets [6*nc,4] 1-based ids, cell index of every tet [6*nc,3])."""
+    nx, ny, nz = len(xs) - 1, len(ys) - 1, len(zs) - 1
+    X, Y, Z = np.meshgrid(xs, ys, zs, indexing="ij")
+    xyz = np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1)
+
+    def nid(i, j, k):
+        return (i * (ny + 1) + j) * (nz + 1) + k + 1
+
+    I, J, K = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    I, J, K = I.ravel(), J.ravel(), K.ravel()
+    tets = np.empty((I.size, 6, 4), dtype=np.int64)
+    for t in range(6):
+        for c in range(4):
+            o = _KUHN[t, c]
+            tets[:, t, c] = nid(I + o[0], J + o[1], K + o[2])
+    cells = np.repeat(np.stack([I, J, K], axis=1)[:, None, :], 6, axis=1).reshape(-1, 3)
+    return xyz, tets.reshape(-1, 4), cells
+
+
+def boundary_faces(tets: np.ndarray):
+    """All faces that belong to exactly one tet: (tris [k,3] node ids, owning tet index [k])."""
+    f = np.concatenate([tets[:, [0, 1, 2]], tets[:, [0, 1, 3]], tets[:, [0, 2, 3]], tets[:, [1, 2, 3]]], axis=0)
+    owner = np.tile(np.arange(tets.shape[0]), 4)
+    key = np.sort(f, axis=1)
+    uniq, idx, cnt = np.unique(key, axis=0, return_index=True, return_counts=True)
+    sel = idx[cnt == 1]
+    sel.sort()
+    return f[sel], owner[sel]
+
+
+def faces_on_plane(xyz: np.ndarray, tris: np.ndarray, axis: int, value: float, tol: float = 1e-12) -> np.ndarray:
+    c = xyz[tris - 1][:, :, axis]
+    return np.all(np.abs(c - value) <= tol, axis=1)
+
+
+def cube_cavity(n: int, length: float = 1.0, jitter: float = 0.0, seed: int = 1234, pec_tag: int = 1, vol_tag: int = 100):
+    """Unit cube, n^3 boxes x 6 Kuhn tets, every boundary face tagged PEC (SURVEY config C5).
+    ``jitter`` perturbs interior nodes by +-jitter*h (seeded) to avoid structured-mesh luck."""
+    g = np.linspace(0.0, length, n + 1)
+    xyz, tets, _ = box_grid(g, g, g)
+    if jitter > 0.0:
+        rng = np.random.default_rng(seed)
+        h = length / n
+        interior = np.all((xyz > 1e-12) & (xyz < length - 1e-12), axis=1)
+        xyz = xyz.copy()
+        xyz[interior] += (rng.random((int(interior.sum()), 3)) * 2.0 - 1.0) * jitter * h
+    tris, _ = boundary_faces(tets)
+    return xyz, tets, np.full(tets.shape[0], vol_tag, dtype=np.int32), tris, np.full(tris.shape[0], pec_tag, dtype=np.int32)
+
+
+def rect_waveguide(a: float = 0.02286, b: float = 0.01016, length: float = 0.05, nx: int = 8, ny: int = 4, nz: int = 18,
+                   pec_tag: int = 1, port1_tag: int = 2, port2_tag: int = 3, vol_tag: int = 100):
+    """Structured WR-90-like guide along z: walls PEC, z=0 -> port 1, z=L -> port 2."""
+    xyz, tets, _ = box_grid(np.linspace(0, a, nx + 1), np.linspace(0, b, ny + 1), np.linspace(0, length, nz + 1))
+    tris, _ = boundary_faces(tets)
+    tags = np.full(tris.shape[0], pec_tag, dtype=np.int32)
+    tags[faces_on_plane(xyz, tris, 2, 0.0)] = port1_tag
+    tags[faces_on_plane(xyz, tris, 2, length)] = port2_tag
+    return xyz, tets, np.full(tets.shape[0], vol_tag, dtype=np.int32), tris, tags
+
+
+def write_gmsh_v2(path: str, xyz, tets, tet_phys, tris, tri_phys, node_ids=None) -> None:
+    """Gmsh 2.2 ASCII: triangles (type 2) first, then tetrahedra (type 4), two tags each."""
+    xyz = np.asarray(xyz, dtype=np.float64).reshape(-1, 3)
+    ids = np.arange(1, xyz.shape[0] + 1) if node_ids is None else np.asarray(node_ids)
+    tets = np.asarray(tets).reshape(-1, 4)
+    tris = np.asarray(tris).reshape(-1, 3)
+    with open(path, "w") as f:
+        f.write("$MeshFormat\n2.2 0 8\n$EndMeshFormat\n$Nodes\n%d\n" % xyz.shape[0])
+        for i in range(xyz.shape[0]):
+            f.write("%d %.17g %.17g %.17g\n" % (ids[i], xyz[i, 0], xyz[i, 1], xyz[i, 2]))
+        f.write("$EndNodes\n$Elements\n%d\n" % (tets.shape[0] + tris.shape[0]))
+        eid = 1
+        for k in range(tris.shape[0]):
+            f.write("%d 2 2 %d %d %d %d %d\n" % (eid, tri_phys[k], tri_phys[k], tris[k, 0], tris[k, 1], tris[k, 2]))
+            eid += 1
+        for k in range(tets.shape[0]):
+            f.write("%d 4 2 %d %d %d %d %d %d\n" % (eid, tet_phys[k], tet_phys[k], tets[k, 0], tets[k, 1], tets[k, 2], tets[k, 3]))
+            eid += 1
+        f.write("$EndElements\n")

@@ -54,6 +54,10 @@ int efb_ctx_sync(efb_ctx *ctx);
 double efb_last_kernel_ms(const efb_ctx *ctx);
 /* number of kernels this ctx has launched since creation */
 int64_t efb_launch_count(const efb_ctx *ctx);
+/* CUDA-event stopwatch on the ctx stream (the stream every kernel of this ctx is launched on):
+ * start records an event; stop records a second one, synchronises and returns the elapsed ms */
+int efb_timer_start(efb_ctx *ctx);
+int efb_timer_stop(efb_ctx *ctx, double *ms);
 
 /* ------------------------------------------------------------------ mesh
  * Replaces the in-memory traversal of `Mesh` (include/edgefem/mesh.hpp:43-52) done by
@@ -187,6 +191,12 @@ int efb_port_rhs_mass(efb_system *sys, efb_port *port, int32_t rhs, const double
 int efb_port_project_weights(efb_system *sys, efb_port *port, int32_t rhs, double *v_c128);
 /* V = e^H M_s x (src/assemble_maxwell.cpp:774) */
 int efb_port_project_mass(efb_system *sys, efb_port *port, int32_t rhs, double *v_c128);
+/* batched forms for sweeps (one launch for `count` right-hand sides):
+ * b[rhs_idx[i]] += coef[i] * (use_mass ? M_s e : w)   and   out[i] = use_mass ? e^H M_s x : w^H x */
+int efb_port_rhs_batch(efb_system *sys, efb_port *port, int32_t count, const int32_t *rhs_idx,
+                       const double *coef_c128, int32_t use_mass);
+int efb_port_project_batch(efb_system *sys, efb_port *port, int32_t count, const int32_t *rhs_idx,
+                           double *out_c128, int32_t use_mass);
 
 /* ------------------------------------------------------------------ periodic (a16)
  * In-place Bloch elimination A <- T A T^H, b <- T b with T = I + sum phase_k e_m e_s^T,
