@@ -451,13 +451,40 @@ void standard_extras(const Mesh &mesh, const MaxwellParams &p, const std::vector
     }
 }
 
+// pairs that take part in the elimination: both edges free (src/assemble_maxwell.cpp:534-537)
+struct ActivePairs {
+  std::vector<int32_t> master, slave;
+  std::vector<cplx> phase;
+};
+ActivePairs active_pairs(const PeriodicBC &pbc, const std::vector<uint8_t> &dir) {
+  ActivePairs a;
+  for (const auto &pr : pbc.pairs) {
+    if (dir.at(pr.master_edge) || dir.at(pr.slave_edge)) continue;
+    a.master.push_back(pr.master_edge);
+    a.slave.push_back(pr.slave_edge);
+    a.phase.push_back(pbc.phase_shift * static_cast<double>(pr.master_orient * pr.slave_orient));
+  }
+  return a;
+}
+
 StdSystem build_standard(const Mesh &mesh, const MaxwellParams &p, const BC &bc, const std::vector<WavePort> &ports,
-                         const std::vector<double> &omegas, int n_rhs, int extra_matrices = 0) {
+                         const std::vector<double> &omegas, int n_rhs, int extra_matrices = 0, const PeriodicBC *pbc = nullptr) {
   StdSystem S;
   S.dm = device_mesh_for(mesh);
   S.dir = dirichlet_flags(mesh, bc);
   std::vector<int32_t> xr, xc, abc_edges;
   standard_extras(mesh, p, ports, S.dir, true, xr, xc, abc_edges);
+  if (pbc && !pbc->pairs.empty()) {
+    const ActivePairs ap = active_pairs(*pbc, S.dir);
+    int64_t n_more = 0;
+    detail::check(efb_periodic_extra(S.dm->h, (int64_t)xr.size(), xr.data(), xc.data(), (int32_t)ap.master.size(), ap.master.data(),
+                                     ap.slave.data(), &n_more, nullptr, nullptr), "efb_periodic_extra");
+    const size_t base = xr.size();
+    xr.resize(base + (size_t)n_more);
+    xc.resize(base + (size_t)n_more);
+    detail::check(efb_periodic_extra(S.dm->h, (int64_t)base, xr.data(), xc.data(), (int32_t)ap.master.size(), ap.master.data(),
+                                     ap.slave.data(), &n_more, xr.data() + base, xc.data() + base), "efb_periodic_extra");
+  }
   const int F = (int)omegas.size();
   S.sys = make_system(*S.dm, xr, xc, F + extra_matrices, std::max(1, n_rhs));
   detail::check(efb_system_set_dirichlet(S.sys->h, S.dir.data()), "efb_system_set_dirichlet");
@@ -659,6 +686,77 @@ MatrixXcd calculate_sparams(const Mesh &mesh, const MaxwellParams &p, const BC &
       for (int j = 0; j < P; ++j) Smat(j, i) = kNaN;
       continue;
     }
+    fill_sparams_column(Smat, S, ports, i, i);
+  }
+  return Smat;
+}
+
+// ------------------------------------------------------------------ periodic (Bloch) path
+namespace {
+void apply_periodic(StdSystem &S, const PeriodicBC &pbc, int n_matrix) {
+  const ActivePairs ap = active_pairs(pbc, S.dir);
+  if (ap.master.empty()) return;
+  detail::check(efb_apply_periodic(S.sys->h, 0, n_matrix, (int32_t)ap.master.size(), ap.master.data(), ap.slave.data(),
+                                   reinterpret_cast<const double *>(ap.phase.data())), "efb_apply_periodic");
+  if (std::abs(pbc.phase_shift.imag()) > 1e-14 * std::abs(pbc.phase_shift)) S.symmetric = false;  // T A T^H is not symmetric for complex phi
+}
+
+// Eigen's sparseView() (src/assemble_maxwell.cpp:569) keeps only numerically non-zero entries
+SpMatC prune_zeros(const SpMatC &A) {
+  SpMatC B(A.rows(), A.cols());
+  auto &rp = B.rowptr();
+  auto &ci = B.colidx();
+  auto &va = B.values();
+  for (int i = 0; i < A.rows(); ++i) {
+    for (int k = A.rowptr()[i]; k < A.rowptr()[i + 1]; ++k)
+      if (A.values()[k] != cplx(0.0)) {
+        ci.push_back(A.colidx()[k]);
+        va.push_back(A.values()[k]);
+      }
+    rp[i + 1] = (int)ci.size();
+  }
+  return B;
+}
+} // namespace
+
+MaxwellAssembly assemble_maxwell_periodic(const Mesh &mesh, const MaxwellParams &p, const BC &bc, const PeriodicBC &pbc,
+                                          const std::vector<WavePort> &ports, int active_port_idx) {
+  if (pbc.pairs.empty()) return assemble_maxwell(mesh, p, bc, ports, active_port_idx);  // :504-506
+  StdSystem S = build_standard(mesh, p, bc, ports, {p.omega}, 1, 0, &pbc);
+  add_source(S, ports, active_port_idx, 0);
+  apply_periodic(S, pbc, 1);
+  MaxwellAssembly out;
+  out.A = prune_zeros(download_matrix(*S.sys, 0));
+  out.b = download_vec(*S.sys, 0, true);
+  out.diagnostics = pml_diagnostics(p);
+  return out;
+}
+
+MatrixXcd calculate_sparams_periodic(const Mesh &mesh, const MaxwellParams &p, const BC &bc, const PeriodicBC &pbc,
+                                     const std::vector<WavePort> &ports) {
+  const int P = (int)ports.size();  // src/assemble_maxwell.cpp:576-635
+  MatrixXcd Smat(P, P);
+  if (P == 0) return Smat;
+  StdSystem S = build_standard(mesh, p, bc, ports, {p.omega}, P, 0, &pbc);
+  for (int i = 0; i < P; ++i) add_source(S, ports, i, i);
+  apply_periodic(S, pbc, 1);
+  SolveOptions defaults;  // the reference passes {} here (:593)
+  SolveOutcome out = solve_on_device(*S.sys, 0, 1, defaults, S.symmetric);
+  // slave recovery x[s] = phi * o * x[m] for EVERY pair (:583-613)
+  std::vector<int32_t> dst, src;
+  std::vector<cplx> ph;
+  for (const auto &pr : pbc.pairs) {
+    dst.push_back(pr.slave_edge);
+    src.push_back(pr.master_edge);
+    ph.push_back(pbc.phase_shift * static_cast<double>(pr.master_orient * pr.slave_orient));
+  }
+  for (int i = 0; i < P; ++i) {
+    if (!out.res[i].converged) {
+      warn_not_converged(out.res[i], out.method, "calculate_sparams_periodic (active port " + std::to_string(i) + ")");
+      for (int j = 0; j < P; ++j) Smat(j, i) = kNaN;
+      continue;
+    }
+    detail::check(efb_x_recover(S.sys->h, i, (int32_t)dst.size(), dst.data(), src.data(), reinterpret_cast<const double *>(ph.data())), "efb_x_recover");
     fill_sparams_column(Smat, S, ports, i, i);
   }
   return Smat;

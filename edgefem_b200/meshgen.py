@@ -107,3 +107,39 @@ def write_gmsh_v2(path: str, xyz, tets, tet_phys, tris, tri_phys, node_ids=None)
             f.write("%d 4 2 %d %d %d %d %d %d\n" % (eid, tet_phys[k], tet_phys[k], tets[k, 0], tets[k, 1], tets[k, 2], tets[k, 3]))
             eid += 1
         f.write("$EndElements\n")
+
+
+def unit_cell(px: float = 0.005, py: float = 0.005, h_sub: float = 0.0005, h_air: float = 0.004, nx: int = 4, ny: int = 4,
+              nz_sub: int = 1, nz_air: int = 4, patch: Optional[Tuple[float, float]] = None, tags: Optional[Dict[str, int]] = None):
+    """Periodic unit cell (tag scheme of the reference's unit_cell design, python/edgefem/designs/unit_cell.py:62-72):
+    ground plane z=0 -> PEC(1); optional centred patch on the substrate top -> 2 (interior faces); top z=H -> port(4);
+    x=0 / x=px -> periodic master/slave (5/6); y=0 / y=py -> (7/8); substrate volume 100, air 101.
+    Opposite faces are node-matched by construction (translation-invariant Kuhn split)."""
+    t = dict(pec=1, patch=2, port=4, xm=5, xs=6, ym=7, ys=8, sub=100, air=101)
+    if tags:
+        t.update(tags)
+    zs = np.concatenate([np.linspace(0, h_sub, nz_sub + 1), np.linspace(h_sub, h_sub + h_air, nz_air + 1)[1:]])
+    xyz, tets, cells = box_grid(np.linspace(0, px, nx + 1), np.linspace(0, py, ny + 1), zs)
+    tet_phys = np.where(cells[:, 2] < nz_sub, t["sub"], t["air"]).astype(np.int32)
+    tris, _ = boundary_faces(tets)
+    H = h_sub + h_air
+    tri_phys = np.zeros(tris.shape[0], dtype=np.int32)
+    tri_phys[faces_on_plane(xyz, tris, 2, 0.0)] = t["pec"]
+    tri_phys[faces_on_plane(xyz, tris, 2, H, tol=1e-12)] = t["port"]
+    tri_phys[faces_on_plane(xyz, tris, 0, 0.0)] = t["xm"]
+    tri_phys[faces_on_plane(xyz, tris, 0, px)] = t["xs"]
+    tri_phys[faces_on_plane(xyz, tris, 1, 0.0)] = t["ym"]
+    tri_phys[faces_on_plane(xyz, tris, 1, py)] = t["ys"]
+    if patch is not None:
+        # interior faces on z = h_sub inside the centred patch rectangle
+        f = np.concatenate([tets[:, [0, 1, 2]], tets[:, [0, 1, 3]], tets[:, [0, 2, 3]], tets[:, [1, 2, 3]]], axis=0)
+        key = np.sort(f, axis=1)
+        _, idx = np.unique(key, axis=0, return_index=True)
+        f = f[np.sort(idx)]
+        c = xyz[f - 1]
+        on = np.all(np.abs(c[:, :, 2] - h_sub) < 1e-12, axis=1)
+        cx, cy = c[:, :, 0].mean(axis=1), c[:, :, 1].mean(axis=1)
+        inside = on & (np.abs(cx - px / 2) < patch[0] / 2) & (np.abs(cy - py / 2) < patch[1] / 2)
+        tris = np.concatenate([tris, f[inside]], axis=0)
+        tri_phys = np.concatenate([tri_phys, np.full(int(inside.sum()), t["patch"], dtype=np.int32)])
+    return xyz, tets, tet_phys, tris, tri_phys
