@@ -245,13 +245,17 @@ def cube_extras(ctx, pe, n: int):
     ms_spmv = sysd.bench_kernel(0, 20)
     ms_bicg = sysd.bench_kernel(1, 10)
     ms_cocg = sysd.bench_kernel(2, 10)
+    ms_fp64 = sysd.bench_kernel(4, 5)
+    fp64_tflops = 148 * 8 * 256 * 8 * 4096 * 2.0 / ms_fp64 / 1e9  # probe geometry is fixed in solve.cu (sm_count = 148 on B200)
     b_asm = 45.0 * n_tet + 24.0 * n_node + 16.0 * nnz
     b_spmv = nnz * 20.0 + m * 36.0
     b_bicg = 2 * b_spmv + 21 * 16.0 * m
     b_cocg = b_spmv + 10 * 16.0 * m
     out = {
         "mesh": {"n": n, "tets": n_tet, "nodes": n_node, "edges": m, "nnz": nnz, "host_setup_s": round(setup_s, 2)},
-        "assembly": {"ms": ms_asm, "mtets_per_s": n_tet / ms_asm / 1e3, "algorithmic_gb": b_asm / 1e9, "gbs": b_asm / ms_asm / 1e6},
+        "fp64_fma_probe_tflops": fp64_tflops,
+        "assembly": {"ms": ms_asm, "mtets_per_s": n_tet / ms_asm / 1e3, "algorithmic_gb": b_asm / 1e9, "gbs": b_asm / ms_asm / 1e6,
+                     "fp64_gflop_model": 6 * n_tet * 300 / 1e9, "note": "row-gather recomputes each element row per incident edge (~300 FP64 flop x 6 per tet)"},
         "spmv": {"ms": ms_spmv, "algorithmic_gb": b_spmv / 1e9, "gbs": b_spmv / ms_spmv / 1e6},
         "bicgstab_jacobi_iteration": {"ms": ms_bicg, "algorithmic_gb": b_bicg / 1e9, "gbs": b_bicg / ms_bicg / 1e6},
         "cocg_jacobi_iteration": {"ms": ms_cocg, "algorithmic_gb": b_cocg / 1e9, "gbs": b_cocg / ms_cocg / 1e6},

@@ -146,8 +146,10 @@ k_assemble_volume(const double4 *__restrict__ xyz, const int4 *__restrict__ tet_
                   const double *__restrict__ omegas, int n_slots, int mode, int first, long long nnz,
                   c128 *__restrict__ vals) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  c128 *acc = (c128 *)smem_raw;                                   // [ASM_CHUNK_NNZ]
-  c128 *s_kf = acc + ASM_CHUNK_NNZ;                               // [n_slots]
+  // entry i of local row lr lives at acc[i + lr]: the +lr skew spreads the row starts of the 32
+  // lanes of a warp (consecutive rows, ~16 entries = 64 words apart) over the shared-memory banks
+  c128 *acc = (c128 *)smem_raw;                                   // [ASM_ACC_ENTRIES]
+  c128 *s_kf = acc + ASM_ACC_ENTRIES;                             // [n_slots]
   c128 *s_mf = s_kf + n_slots;                                    // [n_slots]
   int32_t *s_rowptr = (int32_t *)(s_mf + n_slots);                // [ASM_CHUNK_ROWS+1]
   uint8_t *s_pml = (uint8_t *)(s_rowptr + ASM_CHUNK_ROWS + 1);    // [n_slots]
@@ -160,7 +162,7 @@ k_assemble_volume(const double4 *__restrict__ xyz, const int4 *__restrict__ tet_
   const double k0 = omega / C0;
   const double k0sq = k0 * k0;
 
-  for (int i = threadIdx.x; i < cnt; i += blockDim.x) acc[i] = cmake(0.0, 0.0);
+  for (int i = threadIdx.x; i < cnt + (r1 - r0); i += blockDim.x) acc[i] = cmake(0.0, 0.0);
   for (int i = threadIdx.x; i <= r1 - r0; i += blockDim.x) s_rowptr[i] = rowptr[r0 + i] - base;
   for (int s = threadIdx.x; s < n_slots; s += blockDim.x) {
     const SlotMat sm = slots[s];
@@ -189,7 +191,7 @@ k_assemble_volume(const double4 *__restrict__ xyz, const int4 *__restrict__ tet_
 
   for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
     if (dir[r]) continue;  // Dirichlet row: identity, written below
-    c128 *arow = acc + s_rowptr[r - r0];
+    c128 *arow = acc + s_rowptr[r - r0] + (r - r0);
     const int kb = e2t_ptr[r], ke = e2t_ptr[r + 1];
     for (int k = kb; k < ke; ++k) {
       const int item = e2t_item[k];
@@ -244,14 +246,14 @@ k_assemble_volume(const double4 *__restrict__ xyz, const int4 *__restrict__ tet_
     }
     const int r = r0 + lo;
     const int c = colidx[base + i];
-    c128 v = acc[i];
+    c128 v = acc[i + lo];
     if (dir[r] | dir[c]) v = cmake(r == c ? diag_one : 0.0, 0.0);
     out[i] = v;
   }
 }
 
 size_t assemble_smem_bytes(int n_slots) {
-  return (size_t)ASM_CHUNK_NNZ * sizeof(c128) + 2 * (size_t)n_slots * sizeof(c128) + (ASM_CHUNK_ROWS + 1) * sizeof(int32_t) + (size_t)n_slots + 16;
+  return (size_t)ASM_ACC_ENTRIES * sizeof(c128) + 2 * (size_t)n_slots * sizeof(c128) + (ASM_CHUNK_ROWS + 1) * sizeof(int32_t) + (size_t)n_slots + 16;
 }
 
 // blob layout: [SlotMat x n_slots][efb_pole x n_poles][double omega x count]

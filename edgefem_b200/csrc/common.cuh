@@ -47,8 +47,9 @@ __host__ __device__ __forceinline__ c128 cfma(c128 a, c128 b, c128 acc) {  // ac
 }
 
 // ------------------------------------------------------------------ limits
-constexpr int ASM_CHUNK_NNZ = 6144;   // accumulators per assembly CTA (96 KB of c128)
-constexpr int ASM_CHUNK_ROWS = 1024;  // rows per assembly CTA (rowptr slice in smem)
+constexpr int ASM_CHUNK_NNZ = 5376;   // matrix entries per assembly CTA
+constexpr int ASM_CHUNK_ROWS = 768;   // rows per assembly CTA (rowptr slice in smem; also the bank-skew padding)
+constexpr int ASM_ACC_ENTRIES = ASM_CHUNK_NNZ + ASM_CHUNK_ROWS;  // 96 KB of c128 accumulators
 constexpr int ASM_THREADS = 384;
 constexpr int MAX_SLOTS = 256;        // distinct physical tags
 constexpr int NSCAL = 16;             // per-system device scalars (c128)

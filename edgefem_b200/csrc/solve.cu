@@ -449,10 +449,29 @@ k_bicg_x(SolveDev D, int first_sys, c128 *__restrict__ x, c128 *__restrict__ r, 
   }
 }
 
+// FP64 FMA throughput probe (roofline denominator for the assembly kernel; MEASURED_PEAKS.json has
+// no FP64 figure): 8 independent chains x FP64_PROBE_ITERS FMAs per thread.
+constexpr int FP64_PROBE_ITERS = 4096;
+__global__ void __launch_bounds__(256) k_fp64_probe(double *out, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 8
+  for (int i = 0; i < FP64_PROBE_ITERS; ++i) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  const double r = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+  if (r == 123.456) out[0] = r;  // never true: keeps the chains alive
+}
+
 // ---------------------------------------------------------------- host side
-static int vec_grid(const Ctx *c, int m) {
-  int nb = (m + VEC_THREADS - 1) / VEC_THREADS;
-  return std::max(1, std::min(nb, std::min(RED_MAX_BLOCKS, c->sm_count * 8)));
+// blocks along x for an elementwise / reduction kernel over `m` items launched for `n_par`
+// independent systems (grid.y): enough CTAs to fill the chip a few times over, but no more --
+// every extra CTA costs a ticketed partial reduction, which dominates for small batched systems.
+static int vec_grid(const Ctx *c, int m, int n_par = 1) {
+  const int nb_max = (m + VEC_THREADS - 1) / VEC_THREADS;
+  const int target = c->sm_count * 16;
+  const int want = (target + std::max(1, n_par) - 1) / std::max(1, n_par);
+  return std::max(1, std::min(std::min(nb_max, want), std::min(RED_MAX_BLOCKS, c->sm_count * 8)));
 }
 
 static int pick_lpr(const System *S) {
@@ -522,8 +541,10 @@ static int launch_spmv(System *S, const SolveDev &D, int first, int count, const
   Ctx *c = S->ctx;
   const int lpr = pick_lpr(S);
   const int rpb = 256 / lpr;
-  int nbx = std::max(1, std::min((S->m + rpb - 1) / rpb, std::min(RED_MAX_BLOCKS, c->sm_count * 8)));
   const bool two = (S->n_rhs % 2 == 0);
+  const int n_par = count * (two ? S->n_rhs / 2 : S->n_rhs);
+  const int want = (c->sm_count * 16 + n_par - 1) / n_par;
+  int nbx = std::max(1, std::min(std::min((S->m + rpb - 1) / rpb, want), std::min(RED_MAX_BLOCKS, c->sm_count * 8)));
   dim3 grid((unsigned)nbx, (unsigned)count, (unsigned)(two ? S->n_rhs / 2 : S->n_rhs));
 #define EFB_SPMV(NR)                                                                              \
   switch (dot) {                                                                                  \
@@ -567,14 +588,14 @@ static int apply_precond(SolvePlan &P, const c128 *in, c128 *out, c128 *out2, in
 static int setup_precond(SolvePlan &P) {
   System *S = P.S;
   Ctx *c = S->ctx;
-  dim3 g((unsigned)vec_grid(c, S->m), (unsigned)P.n_matrix);
+  dim3 g((unsigned)vec_grid(c, S->m, P.n_matrix), (unsigned)P.n_matrix);
   k_dinv<<<g, VEC_THREADS, 0, c->stream>>>(P.D, P.first_matrix, S->d_diag_pos, P.precond != EFB_PRECOND_NONE);
   EFB_CHECK_LAUNCH(c);
   if (P.aux) {
     EFB_CUDA(c, cudaMemsetAsync(S->d_linv + (size_t)P.first_matrix * S->n_node, 0, (size_t)P.n_matrix * S->n_node * sizeof(c128), c->stream));
     k_nodal_diag<<<g, VEC_THREADS, 0, c->stream>>>(P.D, P.first_matrix);
     EFB_CHECK_LAUNCH(c);
-    dim3 gn((unsigned)vec_grid(c, S->n_node), (unsigned)P.n_matrix);
+    dim3 gn((unsigned)vec_grid(c, S->n_node, P.n_matrix), (unsigned)P.n_matrix);
     k_linv<<<gn, VEC_THREADS, 0, c->stream>>>(P.D, P.first_matrix);
     EFB_CHECK_LAUNCH(c);
   }
@@ -646,8 +667,8 @@ static int make_plan(System *S, int first_matrix, int n_matrix, const efb_solve_
   if (o->precond == EFB_PRECOND_AUX && !P.aux) P.precond = EFB_PRECOND_JACOBI;
   P.D = make_dev(S, o->tolerance, o->max_iterations);
   for (int v = 0; v < V_NUM; ++v) P.vec[v] = S->d_work + (size_t)v * S->n_sys * S->m;
-  P.vgrid = dim3((unsigned)vec_grid(c, S->m), (unsigned)P.n_sys);
-  P.ngrid = dim3((unsigned)vec_grid(c, std::max(1, S->n_node)), (unsigned)P.n_sys);
+  P.vgrid = dim3((unsigned)vec_grid(c, S->m, P.n_sys), (unsigned)P.n_sys);
+  P.ngrid = dim3((unsigned)vec_grid(c, std::max(1, S->n_node), P.n_sys), (unsigned)P.n_sys);
   return EFB_OK;
 }
 
@@ -681,7 +702,7 @@ int efb_solve(efb_system *sys_, int32_t first_matrix, int32_t n_matrix, const ef
   if ((rc = setup_precond(P))) return rc;
   bool zero_x = opts->zero_initial_guess != 0;
   if (zero_x) {
-    dim3 g((unsigned)vec_grid(c, S->m), (unsigned)nsys);
+    dim3 g((unsigned)vec_grid(c, S->m, nsys), (unsigned)nsys);
     k_fill_zero<<<g, VEC_THREADS, 0, c->stream>>>(S->d_x, S->m, P.first_sys);
     EFB_CHECK_LAUNCH(c);
   }
@@ -771,9 +792,31 @@ int efb_spmv_host(efb_system *sys_, int32_t matrix, const double *x, double *y) 
 
 int efb_bench_kernel(efb_system *sys_, int32_t which, int32_t reps, double *avg_ms) {
   System *S = (System *)sys_;
-  if (!S || !avg_ms || reps <= 0 || which < 0 || which > 3) return fail(S ? S->ctx : nullptr, EFB_ERR_INVALID, "efb_bench_kernel: bad arguments");
+  if (!S || !avg_ms || reps <= 0 || which < 0 || which > 4) return fail(S ? S->ctx : nullptr, EFB_ERR_INVALID, "efb_bench_kernel: bad arguments");
   Ctx *c = S->ctx;
   EFB_CUDA(c, cudaSetDevice(c->device));
+  if (which == 4) {  // FP64 FMA probe: returns ms per launch of sm_count*8 CTAs x 256 threads x 8 chains x 4096 FMAs
+    int rc0 = solver_alloc(S);
+    if (rc0) return rc0;
+    cudaEvent_t a0, a1;
+    EFB_CUDA(c, cudaEventCreate(&a0));
+    EFB_CUDA(c, cudaEventCreate(&a1));
+    for (int pass = 0; pass < 2; ++pass) {
+      if (pass == 1) EFB_CUDA(c, cudaEventRecord(a0, c->stream));
+      for (int i = 0; i < (pass == 0 ? 2 : reps); ++i) {
+        k_fp64_probe<<<c->sm_count * 8, 256, 0, c->stream>>>(S->d_partial, 1.0000001, 1e-9);
+        EFB_CHECK_LAUNCH(c);
+      }
+      if (pass == 1) EFB_CUDA(c, cudaEventRecord(a1, c->stream));
+    }
+    EFB_CUDA(c, cudaEventSynchronize(a1));
+    float msf = 0.f;
+    EFB_CUDA(c, cudaEventElapsedTime(&msf, a0, a1));
+    cudaEventDestroy(a0);
+    cudaEventDestroy(a1);
+    *avg_ms = (double)msf / reps;
+    return EFB_OK;
+  }
   if (!S->assembled) return fail(c, EFB_ERR_STATE, "efb_bench_kernel: assemble first");
   int rc;
   efb_solve_opts o;

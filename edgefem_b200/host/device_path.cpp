@@ -645,12 +645,15 @@ SolveResult solve_linear(const SpMatC &A, const VecC &b, const SolveOptions &opt
     const auto &rp = A.rowptr();
     const auto &ci = A.colidx();
     const auto &va = A.values();
+    double amax = 0.0;
+    for (const auto &v : va) amax = std::max(amax, std::abs(v));
+    // assembled matrices are symmetric only up to the rounding of two different summation orders
     for (int i = 0; i < A.rows() && symmetric; ++i)
       for (int k = rp[i]; k < rp[i + 1]; ++k) {
         const int j = ci[k];
         if (j <= i) continue;
         const cplx t = A.coeff(j, i);
-        if (std::abs(t - va[k]) > 1e-12 * std::max(std::abs(t), std::abs(va[k]))) {
+        if (std::abs(t - va[k]) > 1e-10 * std::max(std::max(std::abs(t), std::abs(va[k])), 1e-3 * amax)) {
           symmetric = false;
           break;
         }

@@ -256,7 +256,8 @@ int efb_spmv_host(efb_system *sys, int32_t matrix, const double *x_c128, double 
 /* ------------------------------------------------------------------ benchmarking hooks
  * Run a kernel `reps` times on resident data and return the average ms (CUDA events on the
  * ctx stream).  which: 0 = SpMV (all matrices, all rhs), 1 = one BiCGSTAB iteration,
- * 2 = one COCG iteration, 3 = volume assembly (mode 0, last used materials/omegas).      */
+ * 2 = one COCG iteration, 3 = volume assembly (mode 0, last used materials/omegas),
+ * 4 = FP64 FMA throughput probe (sm_count*8 CTAs x 256 threads x 8 chains x 4096 FMAs per launch). */
 int efb_bench_kernel(efb_system *sys, int32_t which, int32_t reps, double *avg_ms);
 
 #ifdef __cplusplus

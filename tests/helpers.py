@@ -32,6 +32,24 @@ def rel_entry_err(v_gpu: np.ndarray, v_ref: np.ndarray) -> float:
     return float(np.max(np.abs(v_gpu - v_ref) / np.maximum(np.abs(v_ref), floor)))
 
 
+def row_rel_err(A_gpu, A_ref) -> float:
+    """max_ij |gpu_ij - ref_ij| / max_j |ref_ij|  (error relative to the largest entry of the row).
+    This is the asserted 1e-12 fp64 bar: an entry that is itself the result of cancellation -- inside
+    c_i.c_j for near-orthogonal curls, or across the tets sharing the edge pair -- cannot match to
+    1e-12 of its OWN magnitude between two correct implementations with different operation order
+    (numpy vs FMA-contracted CUDA vs Eigen's setFromTriplets order); on the scale of its row it does.
+    Both matrices share one CSR pattern (asserted by the callers)."""
+    import scipy.sparse as sp
+
+    A_gpu, A_ref = sp.csr_matrix(A_gpu), sp.csr_matrix(A_ref)
+    m = A_ref.shape[0]
+    rows = np.repeat(np.arange(m), np.diff(A_ref.indptr))
+    rmax = np.zeros(m)
+    np.maximum.at(rmax, rows, np.abs(A_ref.data))
+    rmax = np.maximum(rmax, np.finfo(float).tiny)
+    return float(np.max(np.abs(A_gpu.data - A_ref.data) / rmax[rows]))
+
+
 def sum_rel_err(A_gpu, A_ref, scale) -> float:
     """max |gpu - ref| / sum_of_abs_contributions, entrywise; A_gpu and A_ref share one CSR pattern
     (asserted by the callers).  `scale` (orc.volume_abs_scale, any pattern) is looked up per entry.
