@@ -298,7 +298,7 @@ def run_b200(a):
     ports = [pe.build_wave_port_2d(hm, tag, pe.solve_te10_mode(dims, 10e9), set(bc.dirichlet_edges), kc_sq) for tag in (2, 3)]
     # weak scaling: rank r sweeps its own 256-point sub-band of 8-12 GHz
     allf = np.linspace(F_LO, F_HI, a.points * world)
-    freqs = list(allf[rank::world])
+    freqs = list(allf[rank::world])  # == sharding.shard_indices(len(allf), rank, world)
 
     def barrier():
         ctx.sync()
@@ -326,8 +326,10 @@ def run_b200(a):
         t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
-        gathered = [torch.zeros(S.shape + (2,), dtype=torch.float64, device="cuda") for _ in range(world)]
-        dist.all_gather(gathered, torch.from_numpy(np.stack([S.real, S.imag], axis=-1)).cuda())
+        from edgefem_b200 import sharding
+
+        S_all = sharding.gather_sweep(S, a.points * world, rank, world, dist=dist, device=torch.device("cuda", local))  # NCCL all-gather
+        assert S_all.shape[0] == a.points * world and np.all(np.isfinite(S_all))
     ms_step = ms_total / a.steps
     value = a.points * world / (ms_step / 1000.0)
     iters = [r["iters"] for r in res]

@@ -155,7 +155,7 @@ def test_solve_linear_contract():
     assert np.linalg.norm(x - x_ref) <= 1e-7 * np.linalg.norm(x_ref)
     assert np.linalg.norm(A @ x - b) / np.linalg.norm(b) == pytest.approx(res.residual, rel=1e-3)
     # non-symmetric matrix => BiCGSTAB
-    B = (A + sp.diags(np.linspace(0, 50, A.shape[0]), 1, format="csr")).tocsr()
+    B = (A + sp.diags(np.linspace(0, 50, A.shape[0] - 1), 1, format="csr")).tocsr()
     B.sort_indices()
     Bh = pe.SpMatC.from_csr(B.shape[0], B.indptr, B.indices, B.data.astype(complex))
     r2 = pe.solve_linear(Bh, b)
