@@ -268,6 +268,8 @@ int efb_mesh_create(efb_ctx *ctx_, const efb_mesh_desc *d, efb_mesh **out) {
   if ((rc = dev_upload(c, &M->d_tet_slot, slot.data(), slot.size()))) return rc;
   if ((rc = dev_upload(c, &M->d_e2t_ptr, M->h_e2t_ptr.data(), M->h_e2t_ptr.size()))) return rc;
   if ((rc = dev_upload(c, &M->d_e2t_item, M->h_e2t_item.data(), M->h_e2t_item.size()))) return rc;
+  if ((rc = dev_alloc(c, &M->d_geom, (size_t)std::max<int64_t>(1, nt)))) return rc;
+  if ((rc = launch_tet_geometry(M))) return rc;
   // per-slot bounding boxes (PML profile, src/assemble_maxwell.cpp:66-89) on device
   if ((rc = dev_alloc(c, &M->d_slot_bbox, (size_t)std::max(1, M->n_slots) * 6))) return rc;
   if (nt > 0) {
@@ -294,7 +296,7 @@ void efb_mesh_destroy(efb_mesh *mesh_) {
   if (!M) return;
   cudaSetDevice(M->ctx->device);
   cudaFree(M->d_xyz); cudaFree(M->d_tet_nodes); cudaFree(M->d_tet_sign); cudaFree(M->d_tet_slot);
-  cudaFree(M->d_e2t_ptr); cudaFree(M->d_e2t_item); cudaFree(M->d_slot_bbox);
+  cudaFree(M->d_e2t_ptr); cudaFree(M->d_e2t_item); cudaFree(M->d_slot_bbox); cudaFree(M->d_geom);
   delete M;
 }
 

@@ -54,7 +54,7 @@ __device__ c128 eval_model_eps(const efb_model &md, const efb_pole *__restrict__
   return eps;
 }
 
-// ---------------------------------------------------------------- element row
+// ---------------------------------------------------------------- element geometry
 struct V3 {
   double x, y, z;
 };
@@ -63,11 +63,22 @@ __device__ __forceinline__ V3 vcross(V3 a, V3 b) { return {a.y * b.z - a.z * b.y
 __device__ __forceinline__ double vdot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 __device__ __forceinline__ V3 vscale(double s, V3 a) { return {s * a.x, s * a.y, s * a.z}; }
 
-// Row `li` of the real 6x6 curl-curl (K) and mass (M) element matrices of one tet
-// (src/edge_basis.cpp:14-86): g = cols of B^-T, V = |det B|/6, c = 2 g_a x g_b,
-// K = V c_i.c_j, M = sum of four g.g terms weighted with V/10 (equal) or V/20.
-__device__ __forceinline__ void element_row(const V3 v[4], int li, double K[6], double M[6], V3 &centroid) {
-  const V3 b0 = vsub(v[0], v[3]), b1 = vsub(v[1], v[3]), b2 = vsub(v[2], v[3]);
+// Frequency-independent geometry of one tet, cached on the device when the mesh is uploaded:
+// Gram matrix gg[i][j] = grad(lambda_i).grad(lambda_j) and the volume V
+// (src/edge_basis.cpp:14-26: gradients = columns of B^-T = cofactors/det, V = |det B|/6).
+// Both element matrices are functions of (gg, V) only:
+//   K(i,j) = V c_i.c_j, c_i = 2 g_a x g_b  ==  4V [ gg(a,c) gg(b,d) - gg(a,d) gg(b,c) ]   (Binet-Cauchy)
+//   M(i,j) = gg(b,d) I(a,c) - gg(b,c) I(a,d) - gg(a,d) I(b,c) + gg(a,c) I(b,d),  I = V/10 (equal) | V/20
+// so the per-frequency assembly never touches coordinates (except for tensor-PML tets).
+__global__ void k_tet_geometry(const double4 *__restrict__ xyz, const int4 *__restrict__ tet_nodes,
+                               const uint8_t *__restrict__ tet_sign, const uint8_t *__restrict__ tet_slot, int n_tet,
+                               TetGeom *__restrict__ geom) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tet) return;
+  const int4 nd = tet_nodes[t];
+  const double4 q0 = xyz[nd.x], q1 = xyz[nd.y], q2 = xyz[nd.z], q3 = xyz[nd.w];
+  const V3 v0{q0.x, q0.y, q0.z}, v1{q1.x, q1.y, q1.z}, v2{q2.x, q2.y, q2.z}, v3{q3.x, q3.y, q3.z};
+  const V3 b0 = vsub(v0, v3), b1 = vsub(v1, v3), b2 = vsub(v2, v3);
   const V3 c12 = vcross(b1, b2), c20 = vcross(b2, b0), c01 = vcross(b0, b1);
   const double det = vdot(b0, c12);
   const double inv = 1.0 / det;
@@ -76,34 +87,27 @@ __device__ __forceinline__ void element_row(const V3 v[4], int li, double K[6], 
   g[1] = vscale(inv, c20);
   g[2] = vscale(inv, c01);
   g[3] = {-g[0].x - g[1].x - g[2].x, -g[0].y - g[1].y - g[2].y, -g[0].z - g[1].z - g[2].z};
-  const double V = fabs(det) / 6.0;
-  centroid = {(v[0].x + v[1].x + v[2].x + v[3].x) / 4.0, (v[0].y + v[1].y + v[2].y + v[3].y) / 4.0,
-              (v[0].z + v[1].z + v[2].z + v[3].z) / 4.0};
-  const int a = (li < 3) ? 0 : (li < 5 ? 1 : 2);
-  const int b = (li == 0) ? 1 : ((li == 1 || li == 3) ? 2 : 3);
-  const V3 ga = (a == 0) ? g[0] : (a == 1 ? g[1] : g[2]);
-  const V3 gb = (b == 1) ? g[1] : (b == 2 ? g[2] : g[3]);
-  const V3 ci = vscale(2.0, vcross(ga, gb));
-  double gad[4], gbd[4];
+  TetGeom G;
 #pragma unroll
-  for (int d = 0; d < 4; ++d) {
-    gad[d] = vdot(ga, g[d]);
-    gbd[d] = vdot(gb, g[d]);
-  }
-  const double Ieq = V / 10.0, Ine = V / 20.0;
-  constexpr int PA[6] = {0, 0, 0, 1, 1, 2}, PB[6] = {1, 2, 3, 2, 3, 3};
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
-  for (int j = 0; j < 6; ++j) {
-    const int c = PA[j], d = PB[j];
-    const V3 cj = vscale(2.0, vcross(g[c], g[d]));
-    K[j] = V * vdot(ci, cj);
-    double term = 0.0;
-    term += gbd[d] * ((a == c) ? Ieq : Ine);
-    term -= gbd[c] * ((a == d) ? Ieq : Ine);
-    term -= gad[d] * ((b == c) ? Ieq : Ine);
-    term += gad[c] * ((b == d) ? Ieq : Ine);
-    M[j] = term;
-  }
+    for (int j = i; j < 4; ++j) {
+      const double d = vdot(g[i], g[j]);
+      G.gg[i][j] = d;
+      G.gg[j][i] = d;
+    }
+  G.V = fabs(det) / 6.0;
+  G.sign_slot = (uint32_t)tet_sign[t] | ((uint32_t)tet_slot[t] << 8);
+  G.pad = 0;
+  geom[t] = G;
+}
+
+int launch_tet_geometry(Mesh *M) {
+  Ctx *c = M->ctx;
+  if (M->n_tet == 0) return EFB_OK;
+  k_tet_geometry<<<(M->n_tet + 127) / 128, 128, 0, c->stream>>>(M->d_xyz, M->d_tet_nodes, M->d_tet_sign, M->d_tet_slot, M->n_tet, M->d_geom);
+  EFB_CHECK_LAUNCH(c);
+  return EFB_OK;
 }
 
 // PML scalar stretch of one tet (src/assemble_maxwell.cpp:121-172)
@@ -130,14 +134,21 @@ __device__ c128 pml_stretch(const efb_pml &pm, const double *__restrict__ bbox, 
   return cmake(1.0, im / 3.0);  // mean of (1 + j sigma_ax / omega)
 }
 
+__device__ __noinline__ c128 pml_stretch_of_tet(const efb_pml &pm, const double *__restrict__ bbox, const double4 *__restrict__ xyz,
+                                                const int4 *__restrict__ tet_nodes, int t, double omega) {
+  const int4 nd = tet_nodes[t];
+  const double4 q0 = xyz[nd.x], q1 = xyz[nd.y], q2 = xyz[nd.z], q3 = xyz[nd.w];
+  const V3 cen{(q0.x + q1.x + q2.x + q3.x) / 4.0, (q0.y + q1.y + q2.y + q3.y) / 4.0, (q0.z + q1.z + q2.z + q3.z) / 4.0};
+  return pml_stretch(pm, bbox, cen, omega);
+}
+
 // ---------------------------------------------------------------- K1: volume assembly
-// grid (n_chunks, count).  One CTA owns a contiguous row chunk: every thread walks the
-// incident tets of its rows (ascending tet index => deterministic sums), recomputes the
-// needed element-matrix row and accumulates into shared memory; the chunk is then written
-// once, coalesced, with the Dirichlet mask applied.
+// grid (n_chunks, count).  One CTA owns a contiguous row chunk (<= ASM_CHUNK_NNZ entries): every
+// thread walks the incident tets of its rows (ascending tet index => deterministic sums), forms
+// the needed element-matrix row from the cached Gram record and accumulates into shared memory;
+// the chunk is then written ONCE, fully coalesced, with the Dirichlet mask applied.  No atomics.
 __global__ void __launch_bounds__(ASM_THREADS, 2)
-k_assemble_volume(const double4 *__restrict__ xyz, const int4 *__restrict__ tet_nodes,
-                  const uint8_t *__restrict__ tet_sign, const uint8_t *__restrict__ tet_slot,
+k_assemble_volume(const TetGeom *__restrict__ geom, const double4 *__restrict__ xyz, const int4 *__restrict__ tet_nodes,
                   const int32_t *__restrict__ e2t_ptr, const int32_t *__restrict__ e2t_item,
                   const uint16_t *__restrict__ e2t_pos, const int32_t *__restrict__ chunk_row,
                   const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
@@ -152,18 +163,20 @@ k_assemble_volume(const double4 *__restrict__ xyz, const int4 *__restrict__ tet_
   c128 *s_kf = acc + ASM_ACC_ENTRIES;                             // [n_slots]
   c128 *s_mf = s_kf + n_slots;                                    // [n_slots]
   int32_t *s_rowptr = (int32_t *)(s_mf + n_slots);                // [ASM_CHUNK_ROWS+1]
-  uint8_t *s_pml = (uint8_t *)(s_rowptr + ASM_CHUNK_ROWS + 1);    // [n_slots]
+  uint16_t *s_rowid = (uint16_t *)(s_rowptr + ASM_CHUNK_ROWS + 1); // [ASM_CHUNK_NNZ] local row of every entry
+  uint8_t *s_pml = (uint8_t *)(s_rowid + ASM_CHUNK_NNZ);          // [n_slots]
 
   const int chunk = blockIdx.x, fi = blockIdx.y;
   const int r0 = chunk_row[chunk], r1 = chunk_row[chunk + 1];
   const int base = rowptr[r0];
   const int cnt = rowptr[r1] - base;
+  const int nrow = r1 - r0;
   const double omega = omegas[fi];
   const double k0 = omega / C0;
   const double k0sq = k0 * k0;
 
-  for (int i = threadIdx.x; i < cnt + (r1 - r0); i += blockDim.x) acc[i] = cmake(0.0, 0.0);
-  for (int i = threadIdx.x; i <= r1 - r0; i += blockDim.x) s_rowptr[i] = rowptr[r0 + i] - base;
+  for (int i = threadIdx.x; i < cnt + nrow; i += blockDim.x) acc[i] = cmake(0.0, 0.0);
+  for (int i = threadIdx.x; i <= nrow; i += blockDim.x) s_rowptr[i] = rowptr[r0 + i] - base;
   for (int s = threadIdx.x; s < n_slots; s += blockDim.x) {
     const SlotMat sm = slots[s];
     c128 eps = sm.eps_s, mu = sm.mu_s;
@@ -189,46 +202,55 @@ k_assemble_volume(const double4 *__restrict__ xyz, const int4 *__restrict__ tet_
   }
   __syncthreads();
 
-  for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
+  for (int lr = threadIdx.x; lr < nrow; lr += blockDim.x) {
+    const int r = r0 + lr;
+    const int rs = s_rowptr[lr], re = s_rowptr[lr + 1];
+    for (int i = rs; i < re; ++i) s_rowid[i] = (uint16_t)lr;
     if (dir[r]) continue;  // Dirichlet row: identity, written below
-    c128 *arow = acc + s_rowptr[r - r0] + (r - r0);
+    c128 *arow = acc + rs + lr;
     const int kb = e2t_ptr[r], ke = e2t_ptr[r + 1];
     for (int k = kb; k < ke; ++k) {
       const int item = e2t_item[k];
       const int t = item >> 3, li = item & 7;
-      const int4 nd = __ldg(&tet_nodes[t]);
-      const unsigned sg = tet_sign[t];
-      const int slot = tet_slot[t];
-      const uint16_t *pp = e2t_pos + (size_t)k * 6;
-      // 6 x uint16 = 12 bytes, 4-byte aligned
+      const TetGeom *__restrict__ G = geom + t;
+      const int a = (li < 3) ? 0 : (li < 5 ? 1 : 2);
+      const int b = (li == 0) ? 1 : ((li == 1 || li == 3) ? 2 : 3);
+      // rows a and b of the Gram matrix (32 B each), then (V, sign|slot)
+      const double2 *ra2 = (const double2 *)G->gg[a], *rb2 = (const double2 *)G->gg[b];
+      const double2 a01 = ra2[0], a23 = ra2[1], b01 = rb2[0], b23 = rb2[1];
+      const double2 tail = *(const double2 *)&G->V;
+      const uint16_t *pp = e2t_pos + (size_t)k * 6;  // 6 x uint16 = 12 bytes, 4-byte aligned
       const uint32_t p01 = *(const uint32_t *)(pp), p23 = *(const uint32_t *)(pp + 2), p45 = *(const uint32_t *)(pp + 4);
       const int pos[6] = {(int)(p01 & 0xffff), (int)(p01 >> 16), (int)(p23 & 0xffff), (int)(p23 >> 16), (int)(p45 & 0xffff), (int)(p45 >> 16)};
-      V3 v[4];
-      {
-        const double4 q0 = xyz[nd.x], q1 = xyz[nd.y], q2 = xyz[nd.z], q3 = xyz[nd.w];
-        v[0] = {q0.x, q0.y, q0.z};
-        v[1] = {q1.x, q1.y, q1.z};
-        v[2] = {q2.x, q2.y, q2.z};
-        v[3] = {q3.x, q3.y, q3.z};
-      }
-      double K[6], M[6];
-      V3 cen;
-      element_row(v, li, K, M, cen);
+      const double ra[4] = {a01.x, a01.y, a23.x, a23.y}, rb[4] = {b01.x, b01.y, b23.x, b23.y};
+      const double V = tail.x;
+      const unsigned packed = (unsigned)__double2loint(tail.y);
+      const unsigned sg = packed & 0xffu;
+      const int slot = (int)((packed >> 8) & 0xffu);
       c128 kf = s_kf[slot], mf = s_mf[slot];
       if (s_pml[slot]) {
-        const c128 st = pml_stretch(slots[slot].pml, slot_bbox + slot * 6, cen, omega);
+        const c128 st = pml_stretch_of_tet(slots[slot].pml, slot_bbox + slot * 6, xyz, tet_nodes, t, omega);
         kf = cdiv(kf, st);
         mf = cmul(mf, st);
       }
+      const double V4 = 4.0 * V, Ieq = V / 10.0, Ine = V / 20.0;
       const unsigned si = (sg >> li) & 1u;
+      constexpr int PA[6] = {0, 0, 0, 1, 1, 2}, PB[6] = {1, 2, 3, 2, 3, 3};
 #pragma unroll
       for (int j = 0; j < 6; ++j) {
+        const int c = PA[j], d = PB[j];
+        const double Kj = V4 * (ra[c] * rb[d] - ra[d] * rb[c]);
+        double Mj = 0.0;
+        Mj += rb[d] * ((a == c) ? Ieq : Ine);
+        Mj -= rb[c] * ((a == d) ? Ieq : Ine);
+        Mj -= ra[d] * ((b == c) ? Ieq : Ine);
+        Mj += ra[c] * ((b == d) ? Ieq : Ine);
         const double sgn = (((sg >> j) & 1u) ^ si) ? -1.0 : 1.0;
-        const double kk = K[j] * sgn, mm = M[j] * sgn;
-        c128 a = arow[pos[j]];
-        a.x += kk * kf.x + mm * mf.x;
-        a.y += kk * kf.y + mm * mf.y;
-        arow[pos[j]] = a;
+        const double kk = Kj * sgn, mm = Mj * sgn;
+        c128 v = arow[pos[j]];
+        v.x += kk * kf.x + mm * mf.x;
+        v.y += kk * kf.y + mm * mf.y;
+        arow[pos[j]] = v;
       }
     }
   }
@@ -236,24 +258,19 @@ k_assemble_volume(const double4 *__restrict__ xyz, const int4 *__restrict__ tet_
 
   c128 *out = vals + (size_t)(first + fi) * (size_t)nnz + base;
   const double diag_one = (mode == 2) ? 0.0 : 1.0;
-  const int nrow = r1 - r0;
   for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
-    // local row of entry i: last lr with s_rowptr[lr] <= i
-    int lo = 0, hi = nrow;
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (s_rowptr[mid] <= i) lo = mid; else hi = mid;
-    }
-    const int r = r0 + lo;
+    const int lr = s_rowid[i];
+    const int r = r0 + lr;
     const int c = colidx[base + i];
-    c128 v = acc[i + lo];
+    c128 v = acc[i + lr];
     if (dir[r] | dir[c]) v = cmake(r == c ? diag_one : 0.0, 0.0);
     out[i] = v;
   }
 }
 
 size_t assemble_smem_bytes(int n_slots) {
-  return (size_t)ASM_ACC_ENTRIES * sizeof(c128) + 2 * (size_t)n_slots * sizeof(c128) + (ASM_CHUNK_ROWS + 1) * sizeof(int32_t) + (size_t)n_slots + 16;
+  return (size_t)ASM_ACC_ENTRIES * sizeof(c128) + 2 * (size_t)n_slots * sizeof(c128) + (ASM_CHUNK_ROWS + 1) * sizeof(int32_t) +
+         (size_t)ASM_CHUNK_NNZ * sizeof(uint16_t) + (size_t)n_slots + 16;
 }
 
 // blob layout: [SlotMat x n_slots][efb_pole x n_poles][double omega x count]
@@ -279,7 +296,7 @@ int assemble_launch(System *S, int first, int count, int mode) {
   EFB_CUDA(c, cudaFuncSetAttribute(k_assemble_volume, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)assemble_smem_bytes(MAX_SLOTS)));
   dim3 grid((unsigned)S->n_chunks, (unsigned)count);
   k_assemble_volume<<<grid, ASM_THREADS, smem, c->stream>>>(
-      M->d_xyz, M->d_tet_nodes, M->d_tet_sign, M->d_tet_slot, M->d_e2t_ptr, M->d_e2t_item, S->d_e2t_pos,
+      M->d_geom, M->d_xyz, M->d_tet_nodes, M->d_e2t_ptr, M->d_e2t_item, S->d_e2t_pos,
       S->d_chunk_row, S->d_rowptr, S->d_colidx, S->d_dir, (const SlotMat *)blob, (const efb_pole *)(blob + off_poles),
       M->d_slot_bbox, (const double *)(blob + off_om), ns, mode, first, (long long)S->nnz, S->d_vals);
   EFB_CHECK_LAUNCH(c);

@@ -55,6 +55,15 @@ constexpr int MAX_SLOTS = 256;        // distinct physical tags
 constexpr int NSCAL = 16;             // per-system device scalars (c128)
 constexpr int RED_MAX_BLOCKS = 1184;  // 148 SMs x 8
 
+// cached per-tet geometry record (144 B, 16-byte aligned rows): see k_tet_geometry
+struct alignas(16) TetGeom {
+  double gg[4][4];     // Gram matrix of the barycentric gradients
+  double V;            // volume
+  uint32_t sign_slot;  // bits 0-5: edge k stored with orientation -1 ; bits 8-15: material slot
+  uint32_t pad;
+};
+static_assert(sizeof(TetGeom) == 144, "TetGeom layout");
+
 // ------------------------------------------------------------------ handles
 struct Ctx {
   int device = 0;
@@ -84,6 +93,7 @@ struct Mesh {
   int32_t *d_e2t_ptr = nullptr;      // [m+1]
   int32_t *d_e2t_item = nullptr;     // [6*n_tet]
   double *d_slot_bbox = nullptr;     // [n_slots*6] min xyz, max xyz over the slot's tets
+  TetGeom *d_geom = nullptr;         // [n_tet] frequency-independent element geometry
 };
 
 struct Port;
@@ -120,6 +130,7 @@ struct System {
   unsigned *d_counter = nullptr; // [n_sys]
   int32_t *d_state = nullptr;  // [n_sys][4]: active, iters, flag, pad
   int32_t *d_flag = nullptr;   // [1] device error flag (entry missing from the pattern)
+  int32_t *d_job = nullptr;    // [1] work-queue counter of the persistent small-system solver
   // last assembly inputs (for efb_bench_kernel which=3)
   std::vector<double> last_omega;
   bool assembled = false;
@@ -194,5 +205,6 @@ struct Timed {  // records CUDA events around a compute call on the ctx stream
 // internal entry points shared across translation units
 int solver_free(System *s);
 int assemble_launch(System *s, int first, int count, int mode);
+int launch_tet_geometry(Mesh *m);
 
 }  // namespace efb

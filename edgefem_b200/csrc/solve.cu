@@ -6,6 +6,7 @@
 // Reductions are deterministic: per-block partials + last-block finalisation in fixed order;
 // scalars (alpha, beta, omega, rho) never leave the device inside the iteration loop.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -449,6 +450,266 @@ k_bicg_x(SolveDev D, int first_sys, c128 *__restrict__ x, c128 *__restrict__ r, 
   }
 }
 
+// ---------------------------------------------------------------- persistent small-system COCG
+// Sweep regime (SURVEY hard part 2): hundreds of small systems (m ~ 6e3) sharing one pattern.  One
+// CTA owns one matrix and NR of its right-hand sides for the WHOLE solve: the search direction p
+// lives in shared memory (SpMV gathers hit smem instead of L2), r/q/x live in this CTA's private
+// slice of global memory (L2 resident), matrix values stream from HBM once per iteration, every
+// reduction is CTA-local (no tickets, no grid-wide barriers, no kernel launches inside the loop)
+// and CTAs pull the next matrix from an atomic queue when theirs has converged.
+constexpr int SMALL_THREADS = 1024;
+constexpr int SMALL_LPR = 16;
+
+template <int N>
+__device__ __forceinline__ void block_allreduce(double (&v)[N], double *red /* smem [33*N] */) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    double a = v[k];
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) red[wid * N + k] = a;
+  }
+  __syncthreads();
+  if (wid == 0) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      double a = (lane < nw) ? red[lane * N + k] : 0.0;
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (lane == 0) red[32 * N + k] = a;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < N; ++k) v[k] = red[32 * N + k];
+  __syncthreads();
+}
+
+template <int NR>
+__global__ void __launch_bounds__(SMALL_THREADS, 1)
+k_cocg_small(SolveDev D, int first_matrix, int n_jobs, int groups_per_matrix, int *job_counter, const c128 *__restrict__ bvec,
+             c128 *xvec, c128 *rvec, c128 *qvec, int aux, int zero_x, int max_restarts) {
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  const int m = D.m, nn = aux ? D.n_node : 0;
+  c128 *p_s = (c128 *)sm_raw;                 // [NR][m]
+  c128 *w_s = p_s + (size_t)NR * m;           // [NR][nn]
+  double *red = (double *)(w_s + (size_t)NR * nn);  // [33*8]
+  __shared__ int s_job;
+  const int tid = threadIdx.x, nth = blockDim.x;
+  const int lane = tid % SMALL_LPR, sw = tid / SMALL_LPR, nsw = nth / SMALL_LPR;
+
+  for (;;) {
+    if (tid == 0) s_job = atomicAdd(job_counter, 1);
+    __syncthreads();
+    const int job = s_job;
+    __syncthreads();
+    if (job >= n_jobs) break;
+    const int f = first_matrix + job / groups_per_matrix;
+    const int s0 = f * D.n_rhs + (job % groups_per_matrix) * NR;
+    const c128 *__restrict__ av = D.vals + (size_t)f * D.nnz;
+    const c128 *__restrict__ dinv = D.dinv + (size_t)f * m;
+    const c128 *__restrict__ linv = D.linv + (size_t)f * (aux ? D.n_node : 0);
+    c128 *xg[NR], *rg[NR], *qg[NR];
+    const c128 *bg[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      const size_t off = (size_t)(s0 + r) * m;
+      xg[r] = xvec + off; rg[r] = rvec + off; qg[r] = qvec + off; bg[r] = bvec + off;
+    }
+    double bb[NR], rr[NR];
+    c128 rho[NR];
+    int iters[NR];
+    bool act[NR], conv[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) { iters[r] = 0; act[r] = false; conv[r] = false; bb[r] = 0.0; rr[r] = 0.0; rho[r] = cmake(0.0, 0.0); }
+
+    // q = A * (vector in p_s), optional dot p.q
+    auto spmv = [&](bool want_dot, double (&dots)[2 * NR]) {
+#pragma unroll
+      for (int k = 0; k < 2 * NR; ++k) dots[k] = 0.0;
+      for (int row = sw; row < m; row += nsw) {
+        const int kb = __ldg(&D.rowptr[row]), ke = __ldg(&D.rowptr[row + 1]);
+        c128 acc[NR];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) acc[r] = cmake(0.0, 0.0);
+        for (int k = kb + lane; k < ke; k += SMALL_LPR) {
+          const c128 a = __ldg(&av[k]);
+          const int c = __ldg(&D.colidx[k]);
+#pragma unroll
+          for (int r = 0; r < NR; ++r) acc[r] = cfma(a, p_s[(size_t)r * m + c], acc[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+#pragma unroll
+          for (int o = SMALL_LPR / 2; o > 0; o >>= 1) {
+            acc[r].x += __shfl_xor_sync(0xffffffffu, acc[r].x, o);
+            acc[r].y += __shfl_xor_sync(0xffffffffu, acc[r].y, o);
+          }
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int r = 0; r < NR; ++r) {
+            qg[r][row] = acc[r];
+            if (want_dot) {
+              const c128 t = cmul(p_s[(size_t)r * m + row], acc[r]);
+              dots[2 * r] += t.x; dots[2 * r + 1] += t.y;
+            }
+          }
+        }
+      }
+    };
+
+    for (int cycle = 0;; ++cycle) {
+      // (1) true residual r = b - A x from the current iterate
+      double d4[2 * NR];
+      if (cycle == 0 && zero_x) {
+        for (int i = tid; i < m; i += nth)
+#pragma unroll
+          for (int r = 0; r < NR; ++r) { xg[r][i] = cmake(0.0, 0.0); qg[r][i] = cmake(0.0, 0.0); }
+      } else {
+        for (int i = tid; i < m; i += nth)
+#pragma unroll
+          for (int r = 0; r < NR; ++r) p_s[(size_t)r * m + i] = xg[r][i];
+        __syncthreads();
+        spmv(false, d4);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 2 * NR; ++k) d4[k] = 0.0;
+      for (int i = tid; i < m; i += nth)
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          const c128 bi = bg[r][i];
+          const c128 ri = csub(bi, qg[r][i]);
+          rg[r][i] = ri;
+          d4[2 * r] += cabs2(ri);
+          d4[2 * r + 1] += cabs2(bi);
+        }
+      block_allreduce<2 * NR>(d4, red);
+      bool any = false;
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        rr[r] = d4[2 * r]; bb[r] = d4[2 * r + 1];
+        conv[r] = (rr[r] <= D.tol2 * bb[r]);
+        act[r] = !conv[r] && iters[r] < D.max_it && cycle <= max_restarts && isfinite(rr[r]);
+        any |= act[r];
+      }
+      if (!any) break;
+
+      // (2)+(3) preconditioned COCG until the recursive residual converges
+      bool fresh = true;  // p = z on entry, p = z + beta p afterwards
+      for (;;) {
+        // z = M^-1 r  (z parked in q), rho_new = r^T z
+        if (aux) {
+          for (int n = tid; n < nn; n += nth) {
+            const c128 li = __ldg(&linv[n]);
+            c128 a2[NR];
+#pragma unroll
+            for (int r = 0; r < NR; ++r) a2[r] = cmake(0.0, 0.0);
+            if (li.x != 0.0 || li.y != 0.0) {
+              for (int k = __ldg(&D.n2e_ptr[n]); k < __ldg(&D.n2e_ptr[n + 1]); ++k) {
+                const int it = __ldg(&D.n2e_item[k]);
+                const int e = it >> 1;
+                if (D.dir[e]) continue;
+#pragma unroll
+                for (int r = 0; r < NR; ++r) {
+                  const c128 v = rg[r][e];
+                  a2[r] = (it & 1) ? cadd(a2[r], v) : csub(a2[r], v);
+                }
+              }
+            }
+#pragma unroll
+            for (int r = 0; r < NR; ++r) w_s[(size_t)r * nn + n] = cmul(li, a2[r]);
+          }
+          __syncthreads();
+        }
+        double dz[2 * NR];
+#pragma unroll
+        for (int k = 0; k < 2 * NR; ++k) dz[k] = 0.0;
+        for (int e = tid; e < m; e += nth) {
+          const c128 di = __ldg(&dinv[e]);
+          int2 ab = make_int2(0, 0);
+          const bool g = aux && !D.dir[e];
+          if (g) ab = D.edge_nodes[e];
+#pragma unroll
+          for (int r = 0; r < NR; ++r) {
+            const c128 ri = rg[r][e];
+            c128 z = cmul(di, ri);
+            if (g) z = cadd(z, csub(w_s[(size_t)r * nn + ab.y], w_s[(size_t)r * nn + ab.x]));
+            qg[r][e] = z;
+            const c128 t = cmul(ri, z);
+            dz[2 * r] += t.x; dz[2 * r + 1] += t.y;
+          }
+        }
+        block_allreduce<2 * NR>(dz, red);
+        c128 beta[NR];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          const c128 rho_new = cmake(dz[2 * r], dz[2 * r + 1]);
+          beta[r] = (fresh || (rho[r].x == 0.0 && rho[r].y == 0.0)) ? cmake(0.0, 0.0) : cdiv(rho_new, rho[r]);
+          rho[r] = rho_new;
+        }
+        for (int e = tid; e < m; e += nth)
+#pragma unroll
+          for (int r = 0; r < NR; ++r) {
+            const c128 z = qg[r][e];
+            p_s[(size_t)r * m + e] = fresh ? z : cfma(beta[r], p_s[(size_t)r * m + e], z);
+          }
+        fresh = false;
+        __syncthreads();
+        // q = A p ; alpha = rho / p^T q
+        double dq[2 * NR];
+        spmv(true, dq);
+        block_allreduce<2 * NR>(dq, red);
+        c128 alpha[NR];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          const c128 pq = cmake(dq[2 * r], dq[2 * r + 1]);
+          const bool brk = (pq.x == 0.0 && pq.y == 0.0) || !(isfinite(pq.x) && isfinite(pq.y));
+          if (brk) act[r] = false;
+          alpha[r] = act[r] ? cdiv(rho[r], pq) : cmake(0.0, 0.0);
+        }
+        // x += alpha p ; r -= alpha q ; rr = |r|^2
+        double dr[NR];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) dr[r] = 0.0;
+        for (int i = tid; i < m; i += nth)
+#pragma unroll
+          for (int r = 0; r < NR; ++r) {
+            if (!act[r]) continue;
+            xg[r][i] = cfma(alpha[r], p_s[(size_t)r * m + i], xg[r][i]);
+            const c128 ri = cfma(cneg(alpha[r]), qg[r][i], rg[r][i]);
+            rg[r][i] = ri;
+            dr[r] += cabs2(ri);
+          }
+        block_allreduce<NR>(dr, red);
+        bool still = false;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          if (!act[r]) continue;
+          iters[r] += 1;
+          rr[r] = dr[r];
+          if (rr[r] <= D.tol2 * bb[r] || iters[r] >= D.max_it || !isfinite(rr[r])) act[r] = false;
+          still |= act[r];
+        }
+        if (!still) break;
+      }
+    }
+    if (tid == 0) {
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        int32_t *st = D.state + (s0 + r) * 4;
+        st[ST_ACTIVE] = 0; st[ST_ITERS] = iters[r]; st[ST_CONV] = conv[r] ? 1 : 0; st[ST_REC] = 0;
+        c128 *sc = scal_of(D, s0 + r);
+        sc[S_RR] = cmake(rr[r], 0.0);
+        sc[S_BB] = cmake(bb[r], 0.0);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+static size_t small_smem_bytes(int nr, int m, int nn) { return ((size_t)nr * m + (size_t)nr * nn) * sizeof(c128) + 33 * 8 * sizeof(double) + 64; }
+
 // FP64 FMA throughput probe (roofline denominator for the assembly kernel; MEASURED_PEAKS.json has
 // no FP64 figure): 8 independent chains x FP64_PROBE_ITERS FMAs per thread.
 constexpr int FP64_PROBE_ITERS = 4096;
@@ -484,9 +745,9 @@ static int pick_lpr(const System *S) {
 
 int solver_free(System *S) {
   cudaFree(S->d_work); cudaFree(S->d_dinv); cudaFree(S->d_linv); cudaFree(S->d_w); cudaFree(S->d_scal);
-  cudaFree(S->d_partial); cudaFree(S->d_counter); cudaFree(S->d_state); cudaFree(S->d_flag);
+  cudaFree(S->d_partial); cudaFree(S->d_counter); cudaFree(S->d_state); cudaFree(S->d_flag); cudaFree(S->d_job);
   S->d_work = nullptr; S->d_dinv = nullptr; S->d_linv = nullptr; S->d_w = nullptr; S->d_scal = nullptr;
-  S->d_partial = nullptr; S->d_counter = nullptr; S->d_state = nullptr; S->d_flag = nullptr;
+  S->d_partial = nullptr; S->d_counter = nullptr; S->d_state = nullptr; S->d_flag = nullptr; S->d_job = nullptr;
   return EFB_OK;
 }
 
@@ -501,6 +762,7 @@ static int solver_alloc(System *S) {
     if ((rc = dev_alloc(c, &S->d_partial, (size_t)S->n_sys * RED_MAX_BLOCKS * 4))) return rc;
     if ((rc = dev_alloc(c, &S->d_counter, (size_t)S->n_sys))) return rc;
     if ((rc = dev_alloc(c, &S->d_state, (size_t)S->n_sys * 4))) return rc;
+    if ((rc = dev_alloc(c, &S->d_job, (size_t)1))) return rc;
     EFB_CUDA(c, cudaMemsetAsync(S->d_counter, 0, (size_t)S->n_sys * sizeof(unsigned), c->stream));
     EFB_CUDA(c, cudaMemsetAsync(S->d_scal, 0, (size_t)S->n_sys * NSCAL * sizeof(c128), c->stream));
     EFB_CUDA(c, cudaMemsetAsync(S->d_state, 0, (size_t)S->n_sys * 4 * sizeof(int32_t), c->stream));
@@ -672,6 +934,38 @@ static int make_plan(System *S, int first_matrix, int n_matrix, const efb_solve_
   return EFB_OK;
 }
 
+// Persistent path: used whenever p (+ nodal scratch) of NR right-hand sides fits in shared memory.
+static int run_cocg_small(SolvePlan &P, const efb_solve_opts *o, bool zero_x, bool *ran) {
+  System *S = P.S;
+  Ctx *c = S->ctx;
+  *ran = false;
+  const char *off = getenv("EDGEFEM_B200_NO_PERSISTENT");
+  if (off && off[0] == '1') return EFB_OK;
+  int dev_smem = 0;
+  EFB_CUDA(c, cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+  const int nn = P.aux ? S->n_node : 0;
+  int nr = (S->n_rhs % 2 == 0) ? 2 : 1;
+  if (small_smem_bytes(nr, S->m, nn) > (size_t)dev_smem) nr = 1;
+  const size_t smem = small_smem_bytes(nr, S->m, nn);
+  if (smem > (size_t)dev_smem) return EFB_OK;  // system too large for one CTA: generic multi-kernel path
+  const int groups = S->n_rhs / nr;
+  const int n_jobs = P.n_matrix * groups;
+  EFB_CUDA(c, cudaMemsetAsync(S->d_job, 0, sizeof(int32_t), c->stream));
+  const int grid = std::max(1, std::min(n_jobs, c->sm_count));
+  if (nr == 2) {
+    EFB_CUDA(c, cudaFuncSetAttribute(k_cocg_small<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_cocg_small<2><<<grid, SMALL_THREADS, smem, c->stream>>>(P.D, P.first_matrix, n_jobs, groups, S->d_job, S->d_b, S->d_x, P.vec[V_R], P.vec[V_Q],
+                                                                P.aux ? 1 : 0, zero_x ? 1 : 0, o->max_restarts > 0 ? o->max_restarts : 3);
+  } else {
+    EFB_CUDA(c, cudaFuncSetAttribute(k_cocg_small<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_cocg_small<1><<<grid, SMALL_THREADS, smem, c->stream>>>(P.D, P.first_matrix, n_jobs, groups, S->d_job, S->d_b, S->d_x, P.vec[V_R], P.vec[V_Q],
+                                                                P.aux ? 1 : 0, zero_x ? 1 : 0, o->max_restarts > 0 ? o->max_restarts : 3);
+  }
+  EFB_CHECK_LAUNCH(c);
+  *ran = true;
+  return EFB_OK;
+}
+
 }  // namespace efb
 
 using namespace efb;
@@ -716,7 +1010,12 @@ int efb_solve(efb_system *sys_, int32_t first_matrix, int32_t n_matrix, const ef
       if (hstate[i * 4 + ST_ACTIVE]) return true;
     return false;
   };
-  for (int cycle = 0; cycle <= max_restarts; ++cycle) {
+  bool ran_small = false;
+  if (P.method == EFB_METHOD_COCG && opts->max_iterations > 0) {
+    if ((rc = run_cocg_small(P, opts, zero_x, &ran_small))) return rc;
+    if (ran_small && (rc = read_state())) return rc;
+  }
+  for (int cycle = 0; !ran_small && cycle <= max_restarts; ++cycle) {
     if ((rc = init_cycle(P, zero_x))) return rc;
     zero_x = false;
     if ((rc = read_state())) return rc;

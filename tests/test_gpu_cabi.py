@@ -91,3 +91,30 @@ def test_wr90_sweep_batched(ctx, wr90):
         S_ref = orc.wr90_sparams(mesh, pec, f, ports)
         assert np.max(np.abs(S[fi] - S_ref)) <= 1e-6, (f, S[fi], S_ref)
     print("iters", [r["iters"] for r in res])
+
+
+def test_generic_multikernel_cocg_path(ctx, wr90, monkeypatch):
+    """The large-system (multi-kernel, ticketed reductions) COCG path gives the same S as the persistent one."""
+    mesh, pec = wr90
+    f = 9.5e9
+    ports = orc.wr90_ports(mesh, pec, f)
+    S_ref = orc.wr90_sparams(mesh, pec, f, ports)
+    S_p, res_p = H.eigenmode_sweep_gpu(ctx, mesh, pec, ports, [f])
+    monkeypatch.setenv("EDGEFEM_B200_NO_PERSISTENT", "1")
+    S_g, res_g = H.eigenmode_sweep_gpu(ctx, mesh, pec, ports, [f])
+    assert all(r["converged"] for r in res_p + res_g)
+    assert np.max(np.abs(S_p[0] - S_ref)) <= 1e-6 and np.max(np.abs(S_g[0] - S_ref)) <= 1e-6
+    print("iters persistent", [r["iters"] for r in res_p], "generic", [r["iters"] for r in res_g])
+
+
+def test_single_rhs_and_odd_batch(ctx, wr90):
+    """n_rhs = 1 (NR=1 kernels) and a 3-matrix batch."""
+    mesh, pec = wr90
+    freqs = [8.2e9, 9.9e9, 11.7e9]
+    ports = orc.wr90_ports(mesh, pec, 10e9)[:1]
+    S, res = H.eigenmode_sweep_gpu(ctx, mesh, pec, ports, freqs)
+    assert all(r["converged"] for r in res)
+    for fi, f in enumerate(freqs):
+        p = orc.MaxwellParams(omega=2 * math.pi * f)
+        S_o = orc.calculate_sparams_eigenmode(mesh, p, pec, ports)
+        assert np.max(np.abs(S[fi] - S_o)) <= 1e-6
