@@ -99,6 +99,19 @@ __device__ __forceinline__ double *partial_of(const SolveDev &D, int s) { return
 // LPR lanes cooperate on a row (coalesced 16-byte value loads, warp-shuffle row reduction).
 // DOT: 0 none | 1: scal[slot0] = sum w.y (unconjugated) | 2: scal[slot0] = sum conj(w) y
 //      3: scal[slot0] = sum conj(y) w , scal[slot1] = sum |y|^2
+constexpr int SPMV_UNR = 2;  // rows in flight per lane group (memory-level parallelism)
+
+__device__ __forceinline__ c128 ldg_stream(const c128 *p) {  // streaming 16-byte load: read-only path, do not pollute L1
+  c128 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int ldg_stream(const int32_t *p) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
 template <int LPR, int NR, int DOT>
 __global__ void __launch_bounds__(256)
 k_spmv(SolveDev D, int first_matrix, const c128 *__restrict__ x, c128 *__restrict__ y, const c128 *__restrict__ wv,
@@ -118,43 +131,68 @@ k_spmv(SolveDev D, int first_matrix, const c128 *__restrict__ x, c128 *__restric
 #pragma unroll
     for (int k = 0; k < 4; ++k) dots[r][k] = 0.0;
   const int ntile = (D.m + RPB - 1) / RPB;
-  for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
-    const int row = tile * RPB + rl;
-    c128 acc[NR];
+  for (int tile = blockIdx.x * SPMV_UNR; tile < ntile; tile += gridDim.x * SPMV_UNR) {
+    int row[SPMV_UNR], kb[SPMV_UNR], ke[SPMV_UNR];
+    int len = 0;
 #pragma unroll
-    for (int r = 0; r < NR; ++r) acc[r] = cmake(0.0, 0.0);
-    if (row < D.m) {
-      const int kb = D.rowptr[row], ke = D.rowptr[row + 1];
-      for (int k = kb + lane; k < ke; k += LPR) {
-        const c128 a = __ldg(&av[k]);
-        const int c = __ldg(&D.colidx[k]);
-#pragma unroll
-        for (int r = 0; r < NR; ++r) acc[r] = cfma(a, __ldg(&x[(size_t)(s0 + r) * D.m + c]), acc[r]);
+    for (int u = 0; u < SPMV_UNR; ++u) {
+      row[u] = (tile + u) * RPB + rl;
+      kb[u] = 0; ke[u] = 0;
+      if (tile + u < ntile && row[u] < D.m) {
+        kb[u] = __ldg(&D.rowptr[row[u]]);
+        ke[u] = __ldg(&D.rowptr[row[u] + 1]);
       }
+      len = max(len, ke[u] - kb[u]);
+    }
+    c128 acc[SPMV_UNR][NR];
+#pragma unroll
+    for (int u = 0; u < SPMV_UNR; ++u)
+#pragma unroll
+      for (int r = 0; r < NR; ++r) acc[u][r] = cmake(0.0, 0.0);
+    for (int off = lane; off < len; off += LPR) {
+      c128 a[SPMV_UNR];
+      int c[SPMV_UNR];
+#pragma unroll
+      for (int u = 0; u < SPMV_UNR; ++u) {  // issue every independent load first
+        const int k = kb[u] + off;
+        const bool in = k < ke[u];
+        a[u] = in ? ldg_stream(&av[k]) : cmake(0.0, 0.0);
+        c[u] = in ? ldg_stream(&D.colidx[k]) : 0;
+      }
+#pragma unroll
+      for (int u = 0; u < SPMV_UNR; ++u)
+#pragma unroll
+        for (int r = 0; r < NR; ++r) acc[u][r] = cfma(a[u], __ldg(&x[(size_t)(s0 + r) * D.m + c[u]]), acc[u][r]);
     }
 #pragma unroll
-    for (int r = 0; r < NR; ++r) {
-#pragma unroll
-      for (int o = LPR / 2; o > 0; o >>= 1) {
-        acc[r].x += __shfl_xor_sync(0xffffffffu, acc[r].x, o);
-        acc[r].y += __shfl_xor_sync(0xffffffffu, acc[r].y, o);
-      }
-    }
-    if (lane == 0 && row < D.m) {
+    for (int u = 0; u < SPMV_UNR; ++u)
 #pragma unroll
       for (int r = 0; r < NR; ++r) {
-        const size_t idx = (size_t)(s0 + r) * D.m + row;
-        y[idx] = acc[r];
-        if (DOT == 1) {
-          const c128 q = cmul(wv[idx], acc[r]);
-          dots[r][0] += q.x; dots[r][1] += q.y;
-        } else if (DOT == 2) {
-          const c128 q = cmulconj(wv[idx], acc[r]);
-          dots[r][0] += q.x; dots[r][1] += q.y;
-        } else if (DOT == 3) {
-          const c128 q = cmulconj(acc[r], wv[idx]);
-          dots[r][0] += q.x; dots[r][1] += q.y;
-          dots[r][2] += cabs2(acc[r]);
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) {
+          acc[u][r].x += __shfl_xor_sync(0xffffffffu, acc[u][r].x, o);
+          acc[u][r].y += __shfl_xor_sync(0xffffffffu, acc[u][r].y, o);
+        }
+      }
+    if (lane == 0) {
+#pragma unroll
+      for (int u = 0; u < SPMV_UNR; ++u) {
+        if (!(tile + u < ntile && row[u] < D.m)) continue;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          const size_t idx = (size_t)(s0 + r) * D.m + row[u];
+          y[idx] = acc[u][r];
+          if (DOT == 1) {
+            const c128 q = cmul(wv[idx], acc[u][r]);
+            dots[r][0] += q.x; dots[r][1] += q.y;
+          } else if (DOT == 2) {
+            const c128 q = cmulconj(wv[idx], acc[u][r]);
+            dots[r][0] += q.x; dots[r][1] += q.y;
+          } else if (DOT == 3) {
+            const c128 q = cmulconj(acc[u][r], wv[idx]);
+            dots[r][0] += q.x; dots[r][1] += q.y;
+            dots[r][2] += cabs2(acc[u][r]);
+          }
         }
       }
     }
@@ -496,6 +534,9 @@ k_cocg_small(SolveDev D, int first_matrix, int n_jobs, int groups_per_matrix, in
   __shared__ int s_job;
   const int tid = threadIdx.x, nth = blockDim.x;
   const int lane = tid % SMALL_LPR, sw = tid / SMALL_LPR, nsw = nth / SMALL_LPR;
+  // the two 16-lane groups of a warp own different rows and may run different trip counts: every
+  // row-reduction shuffle is restricted to the group's own lanes
+  const unsigned swmask = (SMALL_LPR == 32) ? 0xffffffffu : (((1u << SMALL_LPR) - 1u) << (((tid & 31) / SMALL_LPR) * SMALL_LPR));
 
   for (;;) {
     if (tid == 0) s_job = atomicAdd(job_counter, 1);
@@ -541,8 +582,8 @@ k_cocg_small(SolveDev D, int first_matrix, int n_jobs, int groups_per_matrix, in
         for (int r = 0; r < NR; ++r) {
 #pragma unroll
           for (int o = SMALL_LPR / 2; o > 0; o >>= 1) {
-            acc[r].x += __shfl_xor_sync(0xffffffffu, acc[r].x, o);
-            acc[r].y += __shfl_xor_sync(0xffffffffu, acc[r].y, o);
+            acc[r].x += __shfl_xor_sync(swmask, acc[r].x, o);
+            acc[r].y += __shfl_xor_sync(swmask, acc[r].y, o);
           }
         }
         if (lane == 0) {

@@ -3,6 +3,7 @@
 // Host code only marshals inputs and calls the C-ABI (include/edgefem_b200.h); all element
 // integration, boundary terms, Krylov iterations and projections run on the device.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -59,6 +60,19 @@ std::mutex g_mu;
 efb_ctx *g_ctx = nullptr;
 std::vector<std::shared_ptr<DeviceMesh>> g_mesh_cache;  // most recent first, at most 2
 long long g_bytes_h2d = 0, g_bytes_d2h = 0;
+
+// EDGEFEM_B200_TRACE=1: wall-clock stage log of the drivers on stderr
+struct StageTrace {
+  bool on;
+  std::chrono::steady_clock::time_point t;
+  explicit StageTrace() : on(std::getenv("EDGEFEM_B200_TRACE") != nullptr), t(std::chrono::steady_clock::now()) {}
+  void mark(const char *what) {
+    if (!on) return;
+    const auto n = std::chrono::steady_clock::now();
+    std::cerr << "[edgefem-b200 trace] " << what << ": " << std::chrono::duration<double, std::milli>(n - t).count() << " ms\n";
+    t = n;
+  }
+};
 
 std::uint64_t mesh_fingerprint(const Mesh &mesh) {
   std::uint64_t h = 1469598103934665603ull;
@@ -817,7 +831,9 @@ std::vector<MatrixXcd> calculate_sparams_eigenmode_sweep(const Mesh &mesh, const
   std::vector<MatrixXcd> result(F, MatrixXcd(P, P));
   if (P == 0 || F == 0) return result;
   const long long h2d0 = g_bytes_h2d, d2h0 = g_bytes_d2h, launches0 = detail::launch_count();
+  StageTrace tr;
   auto dm = device_mesh_for(mesh);
+  tr.mark("device mesh (flatten + upload + incidence lists + geometry)");
   const std::vector<uint8_t> dir = dirichlet_flags(mesh, bc);
   std::vector<int32_t> xr, xc;
   for (size_t e = 0; e < dir.size(); ++e)
@@ -838,10 +854,11 @@ std::vector<MatrixXcd> calculate_sparams_eigenmode_sweep(const Mesh &mesh, const
       }
   }
   const std::vector<PortRegion> regions = port_regions(mesh, ports);
+  tr.mark("port surface mass + port regions (host)");
   // frequencies are processed in device batches that fit comfortably in HBM
-  auto probe = make_system(*dm, xr, xc, 1, 1);
-  const double bytes_per_matrix = (double)probe->nnz * 16.0 + (double)probe->m * 16.0 * P * 10.0;
-  probe.reset();
+  // upper bound of nnz without building the pattern: 36 triplets per tet + extras
+  const double nnz_bound = 36.0 * (double)mesh.tets.size() + (double)xr.size();
+  const double bytes_per_matrix = nnz_bound * 16.0 + (double)mesh.edges.size() * 16.0 * P * 10.0;
   const int max_batch = (int)std::max(1.0, std::min((double)F, 24e9 / bytes_per_matrix));
   double device_ms = 0.0;
   if (stats) {
@@ -878,8 +895,10 @@ std::vector<MatrixXcd> calculate_sparams_eigenmode_sweep(const Mesh &mesh, const
     auto sys = make_system(*dm, xr, xc, nb, P);
     detail::check(efb_system_set_dirichlet(sys->h, dir.data()), "efb_system_set_dirichlet");
     g_bytes_h2d += (long long)dir.size();
+    tr.mark("system (pattern + maps + allocations)");
     MaxwellParams pf = p;
     assemble_volume(*sys, *dm, pf, omegas, 0, 0);
+    tr.mark("volume assembly launch");
     std::vector<std::unique_ptr<DevicePort>> dp(P);
     for (int i = 0; i < P; ++i) {
       dp[i] = make_port(*sys, ports[i], &Ms[i]);
@@ -897,8 +916,10 @@ std::vector<MatrixXcd> calculate_sparams_eigenmode_sweep(const Mesh &mesh, const
       }
       detail::check(efb_port_rhs_batch(sys->h, dp[a]->h, nb, idx.data(), reinterpret_cast<const double *>(coef.data()), 1), "efb_port_rhs_batch");
     }
+    tr.mark("port terms + right-hand sides");
     SolveOptions defaults;  // the reference ignores caller options here: solve_linear(A, b, {}) (assemble_maxwell.cpp:755)
     SolveOutcome out = solve_on_device(*sys, 0, nb, defaults, true);
+    tr.mark("solve");
     // V[j][f,a] = e_j^H M_s,j x[f,a] for every solution: one launch per port
     std::vector<std::vector<cplx>> V(P, std::vector<cplx>((size_t)nb * P));
     {
@@ -936,6 +957,10 @@ std::vector<MatrixXcd> calculate_sparams_eigenmode_sweep(const Mesh &mesh, const
     double ms = 0.0;
     detail::check(efb_timer_stop(ctx, &ms), "efb_timer_stop");
     device_ms += ms;
+    tr.mark("projection + S");
+    dp.clear();
+    sys.reset();
+    tr.mark("release");
   }
   if (stats) {
     stats->device_ms = device_ms;

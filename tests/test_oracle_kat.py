@@ -121,3 +121,16 @@ def test_edge_numbering_fast_equals_literal():
         b = load_fixture_mesh(name, fast=True)
         assert np.array_equal(a.tet_edges, b.tet_edges) and np.array_equal(a.tri_edges, b.tri_edges)
         assert np.array_equal(a.edges, b.edges) and np.array_equal(a.tet_orient, b.tet_orient)
+
+
+def test_c_restatement_matches_numpy_oracle(wr90):
+    """oracle/oracle_assembly.c (literal loop restatement) == vectorised numpy oracle on the unmasked volume matrix."""
+    import edgefem_oracle_c as occ
+
+    mesh, pec = wr90
+    w = 2 * math.pi * 10e9
+    p = orc.MaxwellParams(omega=w, eps_r=2.2 - 0.1j, mu_r=1.3 - 0.05j)
+    A_c = occ.volume_matrix(mesh, w, p.eps_r, p.mu_r)
+    A_n, _ = orc.assemble_maxwell(mesh, p, set())
+    assert np.array_equal(A_c.indptr, A_n.indptr) and np.array_equal(A_c.indices, A_n.indices)
+    assert np.max(np.abs(A_c.data - A_n.data)) <= 1e-13 * np.max(np.abs(A_n.data))
