@@ -114,6 +114,7 @@ SIGNATURES = {
     "efb_x_set": (C.c_int, [C.c_void_p, C.c_int32, f64p]),
     "efb_x_recover": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, i32p, i32p, f64p]),
     "efb_solve": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(SolveOpts), C.POINTER(SolveResult)]),
+    "efb_system_last_solve_kernel_ms": (C.c_int, [C.c_void_p, f64p]),
     "efb_spmv_host": (C.c_int, [C.c_void_p, C.c_int32, f64p, f64p]),
     "efb_bench_kernel": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, f64p]),
 }
@@ -341,6 +342,11 @@ class DeviceSystem:
         res = (SolveResult * (count * self.n_rhs))()
         self.ctx.check(self.ctx.lib.efb_solve(self.h, first, count, C.byref(o), res), "efb_solve")
         return [dict(iters=r.iters, converged=bool(r.converged), method=r.method, precond=r.precond, residual=r.residual) for r in res]
+
+    def last_solve_kernel_ms(self) -> float:
+        ms = C.c_double()
+        self.ctx.check(self.ctx.lib.efb_system_last_solve_kernel_ms(self.h, C.byref(ms)), "efb_system_last_solve_kernel_ms")
+        return ms.value
 
     def spmv(self, matrix, x) -> np.ndarray:
         xv = _c128(x)

@@ -325,6 +325,55 @@ static int system_alloc_common(System *S) {
     }
   });
   if ((rc = dev_upload(c, &S->d_diag_pos, diag.data(), diag.size()))) return rc;
+  if (S->m <= 16384) {  // SELL-32 structure (only systems small enough for the persistent one-CTA solver)
+    std::vector<int32_t> order(S->m);
+    for (int r = 0; r < S->m; ++r) order[r] = r;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+      return (S->h_rowptr[a + 1] - S->h_rowptr[a]) > (S->h_rowptr[b + 1] - S->h_rowptr[b]);
+    });
+    const int ns = (S->m + 31) / 32;
+    std::vector<int32_t> sptr((size_t)ns + 1, 0), perm((size_t)ns * 32, -1);
+    for (int i = 0; i < S->m; ++i) perm[i] = order[i];
+    for (int sl = 0; sl < ns; ++sl) {
+      int w = 0;
+      for (int l = 0; l < 32; ++l) {
+        const int r = perm[(size_t)sl * 32 + l];
+        if (r >= 0) w = std::max(w, S->h_rowptr[r + 1] - S->h_rowptr[r]);
+      }
+      sptr[sl + 1] = sptr[sl] + 32 * w;
+    }
+    std::vector<int32_t> scol((size_t)sptr[ns], 0);
+    for (int sl = 0; sl < ns; ++sl)
+      for (int l = 0; l < 32; ++l) {
+        const int r = perm[(size_t)sl * 32 + l];
+        if (r < 0) continue;
+        for (int k = S->h_rowptr[r], j = 0; k < S->h_rowptr[r + 1]; ++k, ++j) scol[(size_t)sptr[sl] + (size_t)j * 32 + l] = S->h_colidx[k];
+      }
+    S->n_slices = ns;
+    S->sell_total = sptr[ns];
+    if ((rc = dev_upload(c, &S->d_sell_ptr, sptr.data(), sptr.size()))) return rc;
+    if ((rc = dev_upload(c, &S->d_sell_col, scol.data(), scol.size()))) return rc;
+    if ((rc = dev_upload(c, &S->d_sell_perm, perm.data(), perm.size()))) return rc;
+  }
+  {  // CSR-stream chunks: consecutive whole rows with <= SPMV_STREAM_W entries per warp
+    std::vector<int32_t> ch{0};
+    bool ok = true;
+    int acc = 0;
+    for (int r = 0; r < S->m; ++r) {
+      const int len = S->h_rowptr[r + 1] - S->h_rowptr[r];
+      if (len > SPMV_STREAM_W) { ok = false; break; }
+      if (acc + len > SPMV_STREAM_W || r - ch.back() >= 31) {  // <= 31 rows: lanes 0..nrow hold rowptr[r0..r1]
+        ch.push_back(r);
+        acc = 0;
+      }
+      acc += len;
+    }
+    if (ok) {
+      ch.push_back(S->m);
+      S->n_sp_chunks = (int)ch.size() - 1;
+      if ((rc = dev_upload(c, &S->d_sp_chunk, ch.data(), ch.size()))) return rc;
+    }
+  }
   if ((rc = dev_alloc(c, &S->d_vals, (size_t)S->n_matrix * S->nnz))) return rc;
   if ((rc = dev_alloc(c, &S->d_b, (size_t)S->n_sys * S->m))) return rc;
   if ((rc = dev_alloc(c, &S->d_x, (size_t)S->n_sys * S->m))) return rc;
@@ -514,7 +563,8 @@ void efb_system_destroy(efb_system *sys_) {
   cudaStreamSynchronize(S->ctx->stream);
   solver_free(S);
   cudaFree(S->d_rowptr); cudaFree(S->d_colidx); cudaFree(S->d_diag_pos); cudaFree(S->d_vals);
-  cudaFree(S->d_b); cudaFree(S->d_x); cudaFree(S->d_dir); cudaFree(S->d_e2t_pos); cudaFree(S->d_chunk_row);
+  cudaFree(S->d_b); cudaFree(S->d_x); cudaFree(S->d_dir); cudaFree(S->d_e2t_pos); cudaFree(S->d_chunk_row); cudaFree(S->d_sp_chunk);
+  cudaFree(S->d_sell_ptr); cudaFree(S->d_sell_col); cudaFree(S->d_sell_perm); cudaFree(S->d_sell_vals);
   cudaFree(S->d_edge_nodes); cudaFree(S->d_n2e_ptr); cudaFree(S->d_n2e_item); cudaFree(S->d_node_dir);
   cudaFree(S->d_mat_blob);
   delete S;

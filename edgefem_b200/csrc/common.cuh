@@ -54,6 +54,7 @@ constexpr int ASM_THREADS = 384;
 constexpr int MAX_SLOTS = 256;        // distinct physical tags
 constexpr int NSCAL = 16;             // per-system device scalars (c128)
 constexpr int RED_MAX_BLOCKS = 1184;  // 148 SMs x 8
+constexpr int SPMV_STREAM_W = 256;    // entries per warp in the CSR-stream SpMV
 
 // cached per-tet geometry record (144 B, 16-byte aligned rows): see k_tet_geometry
 struct alignas(16) TetGeom {
@@ -114,6 +115,19 @@ struct System {
   uint16_t *d_e2t_pos = nullptr;   // [6*n_tet*6] column offsets inside the row
   int32_t *d_chunk_row = nullptr;  // [n_chunks+1]
   int n_chunks = 0;
+  // CSR-stream SpMV: row-aligned chunks of <= SPMV_STREAM_W entries (one warp each); null if a row is longer
+  int32_t *d_sp_chunk = nullptr;   // [n_sp_chunks+1]
+  int n_sp_chunks = 0;
+  // SELL-32 copy of the pattern for the persistent small-system solver: rows sorted by length (desc),
+  // slices of 32 rows stored column-major and padded to the slice's longest row
+  int32_t *d_sell_ptr = nullptr;   // [n_slices+1] entry offsets (multiples of 32)
+  int32_t *d_sell_col = nullptr;   // [sell_total] column of every slot (0 for padding)
+  int32_t *d_sell_perm = nullptr;  // [n_slices*32] original row of every SELL row (-1 for padding rows)
+  c128 *d_sell_vals = nullptr;     // [n_matrix][sell_total] (lazy)
+  int n_slices = 0;
+  long long sell_total = 0;
+  cudaEvent_t ev_s0 = nullptr, ev_s1 = nullptr;  // around the persistent solver kernel
+  bool small_timed = false;
   // gradient (aux preconditioner)
   int2 *d_edge_nodes = nullptr;    // [m]
   int32_t *d_n2e_ptr = nullptr;    // [n_node+1]

@@ -211,6 +211,90 @@ k_spmv(SolveDev D, int first_matrix, const c128 *__restrict__ x, c128 *__restric
   }
 }
 
+// CSR-stream SpMV (large matrices): a warp owns a row-aligned chunk of <= SPMV_STREAM_W entries and at
+// most 32 rows.  Phase 1 streams the chunk's values/columns with fully coalesced, independent
+// 16-byte loads (8 in flight per lane), gathers x and parks the products in shared memory;
+// phase 2 gives one lane per row and sums that row's products in order (deterministic).
+template <int NR, int DOT>
+__global__ void __launch_bounds__(256)
+k_spmv_stream(SolveDev D, const int32_t *__restrict__ sp_chunk, int n_chunks, int first_matrix, const c128 *__restrict__ x,
+              c128 *__restrict__ y, const c128 *__restrict__ wv, int slot0, int slot1, int use_active) {
+  __shared__ c128 prod[8][NR][SPMV_STREAM_W];
+  const int f = first_matrix + blockIdx.y;
+  const int s0 = f * D.n_rhs + blockIdx.z * NR;
+  bool any = false;
+#pragma unroll
+  for (int r = 0; r < NR; ++r) any |= (!use_active) || D.state[(s0 + r) * 4 + ST_ACTIVE];
+  if (!any) return;
+  const c128 *__restrict__ av = D.vals + (size_t)f * D.nnz;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double dots[NR][4];
+#pragma unroll
+  for (int r = 0; r < NR; ++r)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dots[r][k] = 0.0;
+  for (int ch = blockIdx.x * 8 + wid; ch < n_chunks; ch += gridDim.x * 8) {
+    const int r0 = __ldg(&sp_chunk[ch]), r1 = __ldg(&sp_chunk[ch + 1]);
+    const int nrow = r1 - r0;
+    int rs = 0, re = 0;
+    if (lane <= nrow) rs = __ldg(&D.rowptr[r0 + lane]);
+    const int k0 = __shfl_sync(0xffffffffu, rs, 0);
+    const int k1 = __shfl_sync(0xffffffffu, rs, nrow);
+    re = __shfl_down_sync(0xffffffffu, rs, 1);
+    c128 a[SPMV_STREAM_W / 32];
+    int c[SPMV_STREAM_W / 32];
+#pragma unroll
+    for (int j = 0; j < SPMV_STREAM_W / 32; ++j) {
+      const int k = k0 + lane + 32 * j;
+      const bool in = k < k1;
+      a[j] = in ? ldg_stream(&av[k]) : cmake(0.0, 0.0);
+      c[j] = in ? ldg_stream(&D.colidx[k]) : -1;
+    }
+#pragma unroll
+    for (int j = 0; j < SPMV_STREAM_W / 32; ++j) {
+      if (c[j] >= 0) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) prod[wid][r][lane + 32 * j] = cmul(a[j], __ldg(&x[(size_t)(s0 + r) * D.m + c[j]]));
+      }
+    }
+    __syncwarp();
+    if (lane < nrow) {
+      const int row = r0 + lane;
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        c128 acc = cmake(0.0, 0.0);
+        for (int k = rs - k0; k < re - k0; ++k) acc = cadd(acc, prod[wid][r][k]);
+        const size_t idx = (size_t)(s0 + r) * D.m + row;
+        y[idx] = acc;
+        if (DOT == 1) {
+          const c128 q = cmul(wv[idx], acc);
+          dots[r][0] += q.x; dots[r][1] += q.y;
+        } else if (DOT == 2) {
+          const c128 q = cmulconj(wv[idx], acc);
+          dots[r][0] += q.x; dots[r][1] += q.y;
+        } else if (DOT == 3) {
+          const c128 q = cmulconj(acc, wv[idx]);
+          dots[r][0] += q.x; dots[r][1] += q.y;
+          dots[r][2] += cabs2(acc);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if (DOT != 0) {
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      const int s = s0 + r;
+      double tot[4];
+      if (reduce_and_ticket<4>(dots[r], partial_of(D, s), D.counter + s, tot)) {
+        c128 *sc = scal_of(D, s);
+        sc[slot0] = cmake(tot[0], tot[1]);
+        if (DOT == 3) sc[slot1] = cmake(tot[2], 0.0);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------- preconditioner pieces
 // dinv = 1/diag(A) (1 where the diagonal is missing or zero)
 __global__ void k_dinv(SolveDev D, int first_matrix, const int32_t *__restrict__ diag_pos, int jacobi) {
@@ -495,7 +579,7 @@ k_bicg_x(SolveDev D, int first_sys, c128 *__restrict__ x, c128 *__restrict__ r, 
 // slice of global memory (L2 resident), matrix values stream from HBM once per iteration, every
 // reduction is CTA-local (no tickets, no grid-wide barriers, no kernel launches inside the loop)
 // and CTAs pull the next matrix from an atomic queue when theirs has converged.
-constexpr int SMALL_THREADS = 1024;
+constexpr int SMALL_THREADS = 512;
 constexpr int SMALL_LPR = 16;
 
 template <int N>
@@ -524,8 +608,9 @@ __device__ __forceinline__ void block_allreduce(double (&v)[N], double *red /* s
 
 template <int NR>
 __global__ void __launch_bounds__(SMALL_THREADS, 1)
-k_cocg_small(SolveDev D, int first_matrix, int n_jobs, int groups_per_matrix, int *job_counter, const c128 *__restrict__ bvec,
-             c128 *xvec, c128 *rvec, c128 *qvec, int aux, int zero_x, int max_restarts) {
+k_cocg_small(SolveDev D, const int32_t *__restrict__ sell_ptr, const int32_t *__restrict__ sell_col, const int32_t *__restrict__ sell_perm,
+             const c128 *__restrict__ sell_vals, long long sell_total, int n_slices, int first_matrix, int n_jobs, int groups_per_matrix,
+             int *job_counter, const c128 *__restrict__ bvec, c128 *xvec, c128 *rvec, c128 *qvec, int aux, int zero_x, int max_restarts) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
   const int m = D.m, nn = aux ? D.n_node : 0;
   c128 *p_s = (c128 *)sm_raw;                 // [NR][m]
@@ -533,10 +618,7 @@ k_cocg_small(SolveDev D, int first_matrix, int n_jobs, int groups_per_matrix, in
   double *red = (double *)(w_s + (size_t)NR * nn);  // [33*8]
   __shared__ int s_job;
   const int tid = threadIdx.x, nth = blockDim.x;
-  const int lane = tid % SMALL_LPR, sw = tid / SMALL_LPR, nsw = nth / SMALL_LPR;
-  // the two 16-lane groups of a warp own different rows and may run different trip counts: every
-  // row-reduction shuffle is restricted to the group's own lanes
-  const unsigned swmask = (SMALL_LPR == 32) ? 0xffffffffu : (((1u << SMALL_LPR) - 1u) << (((tid & 31) / SMALL_LPR) * SMALL_LPR));
+  const int lane = tid & 31, wid = tid >> 5, nwarp = nth >> 5;
 
   for (;;) {
     if (tid == 0) s_job = atomicAdd(job_counter, 1);
@@ -563,30 +645,30 @@ k_cocg_small(SolveDev D, int first_matrix, int n_jobs, int groups_per_matrix, in
 #pragma unroll
     for (int r = 0; r < NR; ++r) { iters[r] = 0; act[r] = false; conv[r] = false; bb[r] = 0.0; rr[r] = 0.0; rho[r] = cmake(0.0, 0.0); }
 
-    // q = A * (vector in p_s), optional dot p.q
+    // q = A * (vector in p_s), optional dot p.q.  SELL-32: a lane owns a row, a warp a slice; the slice is
+    // stored column-major so every step is one coalesced 512-byte value load + one 128-byte column load,
+    // all steps of a row are independent (deep memory-level parallelism), no shuffles, no divergence.
+    const c128 *__restrict__ sv = sell_vals + (size_t)f * (size_t)sell_total;
     auto spmv = [&](bool want_dot, double (&dots)[2 * NR]) {
 #pragma unroll
       for (int k = 0; k < 2 * NR; ++k) dots[k] = 0.0;
-      for (int row = sw; row < m; row += nsw) {
-        const int kb = __ldg(&D.rowptr[row]), ke = __ldg(&D.rowptr[row + 1]);
+      for (int sl = wid; sl < n_slices; sl += nwarp) {
+        const int base = __ldg(&sell_ptr[sl]);
+        const int width = (__ldg(&sell_ptr[sl + 1]) - base) >> 5;
+        const int row = __ldg(&sell_perm[sl * 32 + lane]);
+        const c128 *vp = sv + base + lane;
+        const int32_t *cp = sell_col + base + lane;
         c128 acc[NR];
 #pragma unroll
         for (int r = 0; r < NR; ++r) acc[r] = cmake(0.0, 0.0);
-        for (int k = kb + lane; k < ke; k += SMALL_LPR) {
-          const c128 a = __ldg(&av[k]);
-          const int c = __ldg(&D.colidx[k]);
+#pragma unroll 4
+        for (int j = 0; j < width; ++j) {
+          const c128 a = ldg_stream(vp + 32 * j);
+          const int c = __ldg(cp + 32 * j);
 #pragma unroll
           for (int r = 0; r < NR; ++r) acc[r] = cfma(a, p_s[(size_t)r * m + c], acc[r]);
         }
-#pragma unroll
-        for (int r = 0; r < NR; ++r) {
-#pragma unroll
-          for (int o = SMALL_LPR / 2; o > 0; o >>= 1) {
-            acc[r].x += __shfl_xor_sync(swmask, acc[r].x, o);
-            acc[r].y += __shfl_xor_sync(swmask, acc[r].y, o);
-          }
-        }
-        if (lane == 0) {
+        if (row >= 0) {
 #pragma unroll
           for (int r = 0; r < NR; ++r) {
             qg[r][row] = acc[r];
@@ -749,6 +831,26 @@ k_cocg_small(SolveDev D, int first_matrix, int n_jobs, int groups_per_matrix, in
   }
 }
 
+// vals (CSR order) -> SELL-32 order, zero padding; grid (slices, matrices), 256 threads
+__global__ void k_csr_to_sell(const c128 *__restrict__ vals, long long nnz, const int32_t *__restrict__ rowptr,
+                              const int32_t *__restrict__ sell_ptr, const int32_t *__restrict__ sell_perm, c128 *__restrict__ sell_vals,
+                              long long sell_total, int first_matrix) {
+  const int sl = blockIdx.x, f = first_matrix + blockIdx.y;
+  const int base = sell_ptr[sl], cnt = sell_ptr[sl + 1] - base;
+  const c128 *__restrict__ src = vals + (size_t)f * nnz;
+  c128 *dst = sell_vals + (size_t)f * sell_total + base;
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const int l = i & 31, j = i >> 5;
+    const int row = sell_perm[sl * 32 + l];
+    c128 v = cmake(0.0, 0.0);
+    if (row >= 0) {
+      const int k = rowptr[row] + j;
+      if (k < rowptr[row + 1]) v = src[k];
+    }
+    dst[i] = v;
+  }
+}
+
 static size_t small_smem_bytes(int nr, int m, int nn) { return ((size_t)nr * m + (size_t)nr * nn) * sizeof(c128) + 33 * 8 * sizeof(double) + 64; }
 
 // FP64 FMA throughput probe (roofline denominator for the assembly kernel; MEASURED_PEAKS.json has
@@ -787,6 +889,9 @@ static int pick_lpr(const System *S) {
 int solver_free(System *S) {
   cudaFree(S->d_work); cudaFree(S->d_dinv); cudaFree(S->d_linv); cudaFree(S->d_w); cudaFree(S->d_scal);
   cudaFree(S->d_partial); cudaFree(S->d_counter); cudaFree(S->d_state); cudaFree(S->d_flag); cudaFree(S->d_job);
+  if (S->ev_s0) cudaEventDestroy(S->ev_s0);
+  if (S->ev_s1) cudaEventDestroy(S->ev_s1);
+  S->ev_s0 = nullptr; S->ev_s1 = nullptr;
   S->d_work = nullptr; S->d_dinv = nullptr; S->d_linv = nullptr; S->d_w = nullptr; S->d_scal = nullptr;
   S->d_partial = nullptr; S->d_counter = nullptr; S->d_state = nullptr; S->d_flag = nullptr; S->d_job = nullptr;
   return EFB_OK;
@@ -842,6 +947,18 @@ static void launch_spmv_lpr(Ctx *c, const SolveDev &D, int lpr, dim3 grid, int f
 static int launch_spmv(System *S, const SolveDev &D, int first, int count, const c128 *x, c128 *y, const c128 *w, int dot, int slot0,
                        int slot1, int use_active) {
   Ctx *c = S->ctx;
+  if (S->d_sp_chunk && S->n_rhs == 1 && !getenv("EDGEFEM_B200_NO_STREAM_SPMV")) {
+    const int nb = std::max(1, std::min((S->n_sp_chunks + 7) / 8, std::min(RED_MAX_BLOCKS, c->sm_count * 8)));
+    dim3 grid((unsigned)nb, (unsigned)count, 1u);
+    switch (dot) {
+      case 0: k_spmv_stream<1, 0><<<grid, 256, 0, c->stream>>>(D, S->d_sp_chunk, S->n_sp_chunks, first, x, y, w, slot0, slot1, use_active); break;
+      case 1: k_spmv_stream<1, 1><<<grid, 256, 0, c->stream>>>(D, S->d_sp_chunk, S->n_sp_chunks, first, x, y, w, slot0, slot1, use_active); break;
+      case 2: k_spmv_stream<1, 2><<<grid, 256, 0, c->stream>>>(D, S->d_sp_chunk, S->n_sp_chunks, first, x, y, w, slot0, slot1, use_active); break;
+      default: k_spmv_stream<1, 3><<<grid, 256, 0, c->stream>>>(D, S->d_sp_chunk, S->n_sp_chunks, first, x, y, w, slot0, slot1, use_active); break;
+    }
+    EFB_CHECK_LAUNCH(c);
+    return EFB_OK;
+  }
   const int lpr = pick_lpr(S);
   const int rpb = 256 / lpr;
   const bool two = (S->n_rhs % 2 == 0);
@@ -988,21 +1105,37 @@ static int run_cocg_small(SolvePlan &P, const efb_solve_opts *o, bool zero_x, bo
   int nr = (S->n_rhs % 2 == 0) ? 2 : 1;
   if (small_smem_bytes(nr, S->m, nn) > (size_t)dev_smem) nr = 1;
   const size_t smem = small_smem_bytes(nr, S->m, nn);
-  if (smem > (size_t)dev_smem) return EFB_OK;  // system too large for one CTA: generic multi-kernel path
+  if (smem > (size_t)dev_smem || !S->d_sell_ptr) return EFB_OK;  // system too large for one CTA: generic multi-kernel path
+  if (!S->d_sell_vals) {
+    int rc0 = dev_alloc(c, &S->d_sell_vals, (size_t)S->n_matrix * (size_t)S->sell_total);
+    if (rc0) return rc0;
+  }
+  {
+    dim3 g((unsigned)S->n_slices, (unsigned)P.n_matrix);
+    k_csr_to_sell<<<g, 256, 0, c->stream>>>(S->d_vals, (long long)S->nnz, S->d_rowptr, S->d_sell_ptr, S->d_sell_perm, S->d_sell_vals, S->sell_total, P.first_matrix);
+    EFB_CHECK_LAUNCH(c);
+  }
   const int groups = S->n_rhs / nr;
   const int n_jobs = P.n_matrix * groups;
   EFB_CUDA(c, cudaMemsetAsync(S->d_job, 0, sizeof(int32_t), c->stream));
+  if (!S->ev_s0) {
+    EFB_CUDA(c, cudaEventCreate(&S->ev_s0));
+    EFB_CUDA(c, cudaEventCreate(&S->ev_s1));
+  }
+  EFB_CUDA(c, cudaEventRecord(S->ev_s0, c->stream));
   const int grid = std::max(1, std::min(n_jobs, c->sm_count));
   if (nr == 2) {
     EFB_CUDA(c, cudaFuncSetAttribute(k_cocg_small<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_cocg_small<2><<<grid, SMALL_THREADS, smem, c->stream>>>(P.D, P.first_matrix, n_jobs, groups, S->d_job, S->d_b, S->d_x, P.vec[V_R], P.vec[V_Q],
+    k_cocg_small<2><<<grid, SMALL_THREADS, smem, c->stream>>>(P.D, S->d_sell_ptr, S->d_sell_col, S->d_sell_perm, S->d_sell_vals, S->sell_total, S->n_slices, P.first_matrix, n_jobs, groups, S->d_job, S->d_b, S->d_x, P.vec[V_R], P.vec[V_Q],
                                                                 P.aux ? 1 : 0, zero_x ? 1 : 0, o->max_restarts > 0 ? o->max_restarts : 3);
   } else {
     EFB_CUDA(c, cudaFuncSetAttribute(k_cocg_small<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_cocg_small<1><<<grid, SMALL_THREADS, smem, c->stream>>>(P.D, P.first_matrix, n_jobs, groups, S->d_job, S->d_b, S->d_x, P.vec[V_R], P.vec[V_Q],
+    k_cocg_small<1><<<grid, SMALL_THREADS, smem, c->stream>>>(P.D, S->d_sell_ptr, S->d_sell_col, S->d_sell_perm, S->d_sell_vals, S->sell_total, S->n_slices, P.first_matrix, n_jobs, groups, S->d_job, S->d_b, S->d_x, P.vec[V_R], P.vec[V_Q],
                                                                 P.aux ? 1 : 0, zero_x ? 1 : 0, o->max_restarts > 0 ? o->max_restarts : 3);
   }
   EFB_CHECK_LAUNCH(c);
+  EFB_CUDA(c, cudaEventRecord(S->ev_s1, c->stream));
+  S->small_timed = true;
   *ran = true;
   return EFB_OK;
 }
@@ -1052,6 +1185,7 @@ int efb_solve(efb_system *sys_, int32_t first_matrix, int32_t n_matrix, const ef
     return false;
   };
   bool ran_small = false;
+  S->small_timed = false;
   if (P.method == EFB_METHOD_COCG && opts->max_iterations > 0) {
     if ((rc = run_cocg_small(P, opts, zero_x, &ran_small))) return rc;
     if (ran_small && (rc = read_state())) return rc;
@@ -1106,6 +1240,18 @@ int efb_solve(efb_system *sys_, int32_t first_matrix, int32_t n_matrix, const ef
     R.residual = bb > 0.0 ? sqrt(rr / bb) : sqrt(rr);
     R.converged = (rr <= P.D.tol2 * bb * (1.0 + 1e-6)) && std::isfinite(rr) ? 1 : 0;
   }
+  return EFB_OK;
+}
+
+int efb_system_last_solve_kernel_ms(efb_system *sys_, double *ms) {
+  System *S = (System *)sys_;
+  if (!S || !ms) return fail(S ? S->ctx : nullptr, EFB_ERR_INVALID, "efb_system_last_solve_kernel_ms: bad arguments");
+  *ms = -1.0;
+  if (!S->small_timed) return EFB_OK;  // the last solve did not use the persistent kernel
+  EFB_CUDA(S->ctx, cudaEventSynchronize(S->ev_s1));
+  float f = 0.f;
+  EFB_CUDA(S->ctx, cudaEventElapsedTime(&f, S->ev_s0, S->ev_s1));
+  *ms = (double)f;
   return EFB_OK;
 }
 

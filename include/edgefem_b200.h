@@ -250,6 +250,9 @@ typedef struct {
 
 int efb_solve(efb_system *sys, int32_t first_matrix, int32_t n_matrix,
               const efb_solve_opts *opts, efb_solve_result *results /* [n_matrix*n_rhs] */);
+/* device time (ms, CUDA events on the ctx stream) of the persistent one-CTA-per-matrix COCG kernel of the
+ * most recent efb_solve on this system, or -1 if that solve used the multi-kernel path */
+int efb_system_last_solve_kernel_ms(efb_system *sys, double *ms);
 /* y = A[matrix] x on device, host in/out (test + diagnostics) */
 int efb_spmv_host(efb_system *sys, int32_t matrix, const double *x_c128, double *y_c128);
 
