@@ -154,10 +154,14 @@ def test_solve_linear_contract():
     x = res.x.to_numpy()
     assert np.linalg.norm(x - x_ref) <= 1e-7 * np.linalg.norm(x_ref)
     assert np.linalg.norm(A @ x - b) / np.linalg.norm(b) == pytest.approx(res.residual, rel=1e-3)
-    # non-symmetric matrix => BiCGSTAB
-    B = (A + sp.diags(np.linspace(0, 50, A.shape[0] - 1), 1, format="csr")).tocsr()
+    # non-symmetric (diagonally dominant) matrix => BiCGSTAB branch
+    rng = np.random.default_rng(5)
+    n = A.shape[0]
+    R = sp.random(n, n, density=4.0 / n, random_state=rng, format="csr")
+    R.data = R.data + 1j * rng.standard_normal(R.nnz)
+    B = (R + sp.diags(np.full(n, 12.0 + 3.0j))).tocsr()
     B.sort_indices()
-    Bh = pe.SpMatC.from_csr(B.shape[0], B.indptr, B.indices, B.data.astype(complex))
+    Bh = pe.SpMatC.from_csr(n, B.indptr, B.indices, B.data.astype(complex))
     r2 = pe.solve_linear(Bh, b)
     assert r2.method.startswith("B200:BiCGSTAB") and r2.converged
     assert np.linalg.norm(B @ r2.x.to_numpy() - b) / np.linalg.norm(b) < 2e-10
