@@ -86,18 +86,6 @@ __global__ void k_bbox_decode(unsigned long long *enc, double *out, int n) {
   out[i] = __longlong_as_double((long long)u);
 }
 
-// per-entry Dirichlet action (frequency independent): 0 keep, 1 -> 0, 2 -> Dirichlet diagonal
-__global__ void k_entry_flags(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx, const uint8_t *__restrict__ dir, int m,
-                              uint8_t *__restrict__ flag) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= m) return;
-  const uint8_t dr = dir[r];
-  for (int k = rowptr[r]; k < rowptr[r + 1]; ++k) {
-    const int c = colidx[k];
-    flag[k] = (dr | dir[c]) ? (uint8_t)(c == r ? 2 : 1) : (uint8_t)0;
-  }
-}
-
 __global__ void k_node_dir(const int2 *__restrict__ edge_nodes, const uint8_t *__restrict__ dir, int m,
                            uint8_t *node_dir) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -278,6 +266,8 @@ int efb_mesh_create(efb_ctx *ctx_, const efb_mesh_desc *d, efb_mesh **out) {
   if ((rc = dev_upload(c, &M->d_tet_nodes, (const int4 *)d->tet_nodes, (size_t)nt))) return rc;
   if ((rc = dev_upload(c, &M->d_tet_sign, sign.data(), sign.size()))) return rc;
   if ((rc = dev_upload(c, &M->d_tet_slot, slot.data(), slot.size()))) return rc;
+  if ((rc = dev_upload(c, &M->d_e2t_ptr, M->h_e2t_ptr.data(), M->h_e2t_ptr.size()))) return rc;
+  if ((rc = dev_upload(c, &M->d_e2t_item, M->h_e2t_item.data(), M->h_e2t_item.size()))) return rc;
   if ((rc = dev_alloc(c, &M->d_geom, (size_t)std::max<int64_t>(1, nt)))) return rc;
   if ((rc = launch_tet_geometry(M))) return rc;
   // per-slot bounding boxes (PML profile, src/assemble_maxwell.cpp:66-89) on device
@@ -306,7 +296,7 @@ void efb_mesh_destroy(efb_mesh *mesh_) {
   if (!M) return;
   cudaSetDevice(M->ctx->device);
   cudaFree(M->d_xyz); cudaFree(M->d_tet_nodes); cudaFree(M->d_tet_sign); cudaFree(M->d_tet_slot);
-  cudaFree(M->d_slot_bbox); cudaFree(M->d_geom);
+  cudaFree(M->d_e2t_ptr); cudaFree(M->d_e2t_item); cudaFree(M->d_slot_bbox); cudaFree(M->d_geom);
   delete M;
 }
 
@@ -483,17 +473,14 @@ int efb_system_create(efb_mesh *mesh_, int64_t n_extra, const int32_t *extra_row
     delete S;
     return fail(c, EFB_ERR_LIMIT, "efb_system_create: nnz %lld >= 2^31 (int32 CSR like Eigen's default index)", (long long)nnz);
   }
-  if ((int64_t)M->n_tet >= (1ll << 26)) {
+  if (maxrow > ASM_CHUNK_NNZ || maxrow > 65535) {
     delete S;
-    return fail(c, EFB_ERR_LIMIT, "efb_system_create: n_tet >= 2^26 (entry-incidence items pack the tet id in 26 bits)");
+    return fail(c, EFB_ERR_LIMIT, "efb_system_create: a row has %d entries (limit %d)", maxrow, std::min(ASM_CHUNK_NNZ, 65535));
   }
   S->nnz = nnz;
   for (int r = 0; r < m; ++r) S->h_rowptr[r + 1] = S->h_rowptr[r] + rowlen[r];
   S->h_colidx.resize((size_t)nnz);
-  // Entry-incidence map for the gather assembly: for every CSR entry (r, c) the list of (tet, li, lj)
-  // whose local edges li, lj are the global edges r, c -- ascending tet index, so every entry is a
-  // fixed-order (deterministic) sum.  36 items per tet in total.
-  std::vector<int32_t> ent_cnt((size_t)nnz + 1, 0);
+  std::vector<uint16_t> pos((size_t)M->h_e2t_item.size() * 6);
   parallel_for(m, [&](int64_t a, int64_t b) {
     std::vector<int32_t> buf;
     for (int64_t r = a; r < b; ++r) {
@@ -502,35 +489,32 @@ int efb_system_create(efb_mesh *mesh_, int64_t n_extra, const int32_t *extra_row
       std::copy(buf.begin(), buf.end(), dst);
       for (int32_t k = M->h_e2t_ptr[r]; k < M->h_e2t_ptr[r + 1]; ++k) {
         const int32_t *e6 = te + 6 * (int64_t)(M->h_e2t_item[k] >> 3);
-        for (int j = 0; j < 6; ++j) ent_cnt[(size_t)S->h_rowptr[r] + (std::lower_bound(buf.begin(), buf.end(), e6[j]) - buf.begin()) + 1]++;
+        for (int j = 0; j < 6; ++j)
+          pos[(size_t)k * 6 + j] = (uint16_t)(std::lower_bound(buf.begin(), buf.end(), e6[j]) - buf.begin());
       }
     }
   });
-  for (int64_t i = 0; i < nnz; ++i) ent_cnt[i + 1] += ent_cnt[i];  // now ent_ptr
-  std::vector<uint32_t> ent_item((size_t)ent_cnt[nnz]);
-  parallel_for(m, [&](int64_t a, int64_t b) {
-    std::vector<int32_t> fill;
-    for (int64_t r = a; r < b; ++r) {
-      const int32_t *cols = S->h_colidx.data() + S->h_rowptr[r];
-      const int len = S->h_rowptr[r + 1] - S->h_rowptr[r];
-      fill.assign(len, 0);
-      for (int32_t k = M->h_e2t_ptr[r]; k < M->h_e2t_ptr[r + 1]; ++k) {
-        const int32_t item = M->h_e2t_item[k];
-        const int32_t t = item >> 3, li = item & 7;
-        const int32_t *e6 = te + 6 * (int64_t)t;
-        for (int j = 0; j < 6; ++j) {
-          const int p = (int)(std::lower_bound(cols, cols + len, e6[j]) - cols);
-          ent_item[(size_t)ent_cnt[(size_t)S->h_rowptr[r] + p] + fill[p]++] = ((uint32_t)t << 6) | ((uint32_t)li << 3) | (uint32_t)j;
-        }
+  // assembly chunks: consecutive rows with <= ASM_CHUNK_NNZ entries and <= ASM_CHUNK_ROWS rows
+  std::vector<int32_t> chunk{0};
+  {
+    int64_t acc = 0;
+    int rows = 0;
+    for (int r = 0; r < m; ++r) {
+      if (acc + rowlen[r] > ASM_CHUNK_NNZ || rows >= ASM_CHUNK_ROWS) {
+        chunk.push_back(r);
+        acc = 0;
+        rows = 0;
       }
+      acc += rowlen[r];
+      rows++;
     }
-  });
+    chunk.push_back(m);
+  }
+  S->n_chunks = (int)chunk.size() - 1;
   int rc;
   if ((rc = system_alloc_common(S))) return rc;
-  if ((rc = dev_upload(c, &S->d_ent_ptr, ent_cnt.data(), ent_cnt.size()))) return rc;
-  if ((rc = dev_upload(c, &S->d_ent_item, ent_item.data(), ent_item.size()))) return rc;
-  if ((rc = dev_alloc(c, &S->d_ent_flag, (size_t)nnz))) return rc;
-  EFB_CUDA(c, cudaMemsetAsync(S->d_ent_flag, 0, (size_t)nnz, c->stream));
+  if ((rc = dev_upload(c, &S->d_e2t_pos, pos.data(), pos.size()))) return rc;
+  if ((rc = dev_upload(c, &S->d_chunk_row, chunk.data(), chunk.size()))) return rc;
   if ((rc = system_set_gradient(S, M->n_node, M->h_edge_nodes.data()))) return rc;
   EFB_CUDA(c, cudaStreamSynchronize(c->stream));
   *out = (efb_system *)S;
@@ -579,7 +563,7 @@ void efb_system_destroy(efb_system *sys_) {
   cudaStreamSynchronize(S->ctx->stream);
   solver_free(S);
   cudaFree(S->d_rowptr); cudaFree(S->d_colidx); cudaFree(S->d_diag_pos); cudaFree(S->d_vals);
-  cudaFree(S->d_b); cudaFree(S->d_x); cudaFree(S->d_dir); cudaFree(S->d_ent_ptr); cudaFree(S->d_ent_item); cudaFree(S->d_ent_flag); cudaFree(S->d_sp_chunk);
+  cudaFree(S->d_b); cudaFree(S->d_x); cudaFree(S->d_dir); cudaFree(S->d_e2t_pos); cudaFree(S->d_chunk_row); cudaFree(S->d_sp_chunk);
   cudaFree(S->d_sell_ptr); cudaFree(S->d_sell_col); cudaFree(S->d_sell_perm); cudaFree(S->d_sell_vals);
   cudaFree(S->d_edge_nodes); cudaFree(S->d_n2e_ptr); cudaFree(S->d_n2e_item); cudaFree(S->d_node_dir);
   cudaFree(S->d_mat_blob);
@@ -632,10 +616,6 @@ int efb_system_set_dirichlet(efb_system *sys_, const uint8_t *flags) {
   EFB_CUDA(c, cudaSetDevice(c->device));
   EFB_CUDA(c, cudaMemcpyAsync(S->d_dir, flags, (size_t)S->m, cudaMemcpyHostToDevice, c->stream));
   S->has_dir = true;
-  if (S->d_ent_flag) {
-    k_entry_flags<<<(S->m + 127) / 128, 128, 0, c->stream>>>(S->d_rowptr, S->d_colidx, S->d_dir, S->m, S->d_ent_flag);
-    EFB_CHECK_LAUNCH(c);
-  }
   if (S->d_node_dir) {
     EFB_CUDA(c, cudaMemsetAsync(S->d_node_dir, 0, (size_t)S->n_node, c->stream));
     k_node_dir<<<(S->m + 255) / 256, 256, 0, c->stream>>>(S->d_edge_nodes, S->d_dir, S->m, S->d_node_dir);

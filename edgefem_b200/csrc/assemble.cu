@@ -143,26 +143,40 @@ __device__ __noinline__ c128 pml_stretch_of_tet(const efb_pml &pm, const double 
 }
 
 // ---------------------------------------------------------------- K1: volume assembly
-// Entry gather.  One thread per CSR entry (r, c): it walks the entry's (tet, li, lj) list (ascending
-// tet => fixed summation order, bit-reproducible), reads the four Gram values + volume it needs from
-// the cached tet record, forms K(li,lj) and M(li,lj), applies the orientation sign and the per-slot
-// material factors and writes the entry ONCE with a coalesced 16-byte store.  No atomics, no shared
-// memory accumulators, no barriers in the hot loop => full occupancy; lanes of a warp own adjacent
-// entries of the same rows, so their Gram-record reads hit the same few cache lines.
-// grid (blocks, count): blockIdx.y = frequency.
-__global__ void __launch_bounds__(ASM_THREADS, 4)
+// grid (n_chunks, count).  One CTA owns a contiguous row chunk (<= ASM_CHUNK_NNZ entries): every
+// thread walks the incident tets of its rows (ascending tet index => deterministic sums), forms
+// the needed element-matrix row from the cached Gram record and accumulates into shared memory;
+// the chunk is then written ONCE, fully coalesced, with the Dirichlet mask applied.  No atomics.
+__global__ void __launch_bounds__(ASM_THREADS, 2)
 k_assemble_volume(const TetGeom *__restrict__ geom, const double4 *__restrict__ xyz, const int4 *__restrict__ tet_nodes,
-                  const int32_t *__restrict__ ent_ptr, const uint32_t *__restrict__ ent_item, const uint8_t *__restrict__ ent_flag,
-                  const SlotMat *__restrict__ slots, const efb_pole *__restrict__ poles, const double *__restrict__ slot_bbox,
-                  const double *__restrict__ omegas, int n_slots, int mode, int first, long long nnz, c128 *__restrict__ vals) {
+                  const int32_t *__restrict__ e2t_ptr, const int32_t *__restrict__ e2t_item,
+                  const uint16_t *__restrict__ e2t_pos, const int32_t *__restrict__ chunk_row,
+                  const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
+                  const uint8_t *__restrict__ dir, const SlotMat *__restrict__ slots,
+                  const efb_pole *__restrict__ poles, const double *__restrict__ slot_bbox,
+                  const double *__restrict__ omegas, int n_slots, int mode, int first, long long nnz,
+                  c128 *__restrict__ vals) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  c128 *s_kf = (c128 *)smem_raw;             // [n_slots]
-  c128 *s_mf = s_kf + n_slots;               // [n_slots]
-  uint8_t *s_pml = (uint8_t *)(s_mf + n_slots);  // [n_slots]
-  const int fi = blockIdx.y;
+  // entry i of local row lr lives at acc[i + lr]: the +lr skew spreads the row starts of the 32
+  // lanes of a warp (consecutive rows, ~16 entries = 64 words apart) over the shared-memory banks
+  c128 *acc = (c128 *)smem_raw;                                   // [ASM_ACC_ENTRIES]
+  c128 *s_kf = acc + ASM_ACC_ENTRIES;                             // [n_slots]
+  c128 *s_mf = s_kf + n_slots;                                    // [n_slots]
+  int32_t *s_rowptr = (int32_t *)(s_mf + n_slots);                // [ASM_CHUNK_ROWS+1]
+  uint16_t *s_rowid = (uint16_t *)(s_rowptr + ASM_CHUNK_ROWS + 1); // [ASM_CHUNK_NNZ] local row of every entry
+  uint8_t *s_pml = (uint8_t *)(s_rowid + ASM_CHUNK_NNZ);          // [n_slots]
+
+  const int chunk = blockIdx.x, fi = blockIdx.y;
+  const int r0 = chunk_row[chunk], r1 = chunk_row[chunk + 1];
+  const int base = rowptr[r0];
+  const int cnt = rowptr[r1] - base;
+  const int nrow = r1 - r0;
   const double omega = omegas[fi];
   const double k0 = omega / C0;
   const double k0sq = k0 * k0;
+
+  for (int i = threadIdx.x; i < cnt + nrow; i += blockDim.x) acc[i] = cmake(0.0, 0.0);
+  for (int i = threadIdx.x; i <= nrow; i += blockDim.x) s_rowptr[i] = rowptr[r0 + i] - base;
   for (int s = threadIdx.x; s < n_slots; s += blockDim.x) {
     const SlotMat sm = slots[s];
     c128 eps = sm.eps_s, mu = sm.mu_s;
@@ -187,52 +201,103 @@ k_assemble_volume(const TetGeom *__restrict__ geom, const double4 *__restrict__ 
     s_pml[s] = (mode == 0) ? (uint8_t)sm.pml.kind : (uint8_t)0;
   }
   __syncthreads();
-  c128 *__restrict__ out = vals + (size_t)(first + fi) * (size_t)nnz;
-  const double diag_one = (mode == 2) ? 0.0 : 1.0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (long long)gridDim.x * blockDim.x) {
-    const int flag = ent_flag[i];
-    c128 acc = cmake(0.0, 0.0);
-    if (flag) {
-      acc.x = (flag == 2) ? diag_one : 0.0;
-    } else {
-      const int kb = ent_ptr[i], ke = ent_ptr[i + 1];
-      for (int k = kb; k < ke; ++k) {
-        const uint32_t it = ent_item[k];
-        const int t = (int)(it >> 6), li = (int)((it >> 3) & 7u), lj = (int)(it & 7u);
-        const int a = (li < 3) ? 0 : (li < 5 ? 1 : 2);
-        const int b = (li == 0) ? 1 : ((li == 1 || li == 3) ? 2 : 3);
-        const int c = (lj < 3) ? 0 : (lj < 5 ? 1 : 2);
-        const int d = (lj == 0) ? 1 : ((lj == 1 || lj == 3) ? 2 : 3);
-        const TetGeom *__restrict__ G = geom + t;
-        const double gac = G->gg[a][c], gad = G->gg[a][d], gbc = G->gg[b][c], gbd = G->gg[b][d];
-        const double V = G->V;
-        const unsigned packed = G->sign_slot;
-        const unsigned sg = packed & 0xffu;
-        const int slot = (int)((packed >> 8) & 0xffu);
-        c128 kf = s_kf[slot], mf = s_mf[slot];
-        if (s_pml[slot]) {
-          const c128 st = pml_stretch_of_tet(slots[slot].pml, slot_bbox + slot * 6, xyz, tet_nodes, t, omega);
-          kf = cdiv(kf, st);
-          mf = cmul(mf, st);
-        }
-        const double Ieq = V / 10.0, Ine = V / 20.0;
-        const double Kv = 4.0 * V * (gac * gbd - gad * gbc);
-        double Mv = 0.0;
-        Mv += gbd * ((a == c) ? Ieq : Ine);
-        Mv -= gbc * ((a == d) ? Ieq : Ine);
-        Mv -= gad * ((b == c) ? Ieq : Ine);
-        Mv += gac * ((b == d) ? Ieq : Ine);
-        const double sgn = (((sg >> li) ^ (sg >> lj)) & 1u) ? -1.0 : 1.0;
-        const double kk = Kv * sgn, mm = Mv * sgn;
-        acc.x += kk * kf.x + mm * mf.x;
-        acc.y += kk * kf.y + mm * mf.y;
-      }
+
+  // one (edge, tet) incidence: everything the row contribution needs, fetched with 8 independent loads
+  struct Rec {
+    double2 a01, a23, b01, b23, tail;
+    uint32_t p01, p23, p45;
+    int item;
+  };
+  auto fetch = [&](int item, int k) {
+    Rec q;
+    q.item = item;
+    const int t = item >> 3, li = item & 7;
+    const TetGeom *__restrict__ G = geom + t;
+    const int a = (li < 3) ? 0 : (li < 5 ? 1 : 2);
+    const int b = (li == 0) ? 1 : ((li == 1 || li == 3) ? 2 : 3);
+    const double2 *ra2 = (const double2 *)G->gg[a], *rb2 = (const double2 *)G->gg[b];
+    q.a01 = ra2[0]; q.a23 = ra2[1]; q.b01 = rb2[0]; q.b23 = rb2[1];
+    q.tail = *(const double2 *)&G->V;
+    const uint32_t *pp = (const uint32_t *)(e2t_pos + (size_t)k * 6);  // 6 x uint16 = 12 bytes, 4-byte aligned
+    q.p01 = pp[0]; q.p23 = pp[1]; q.p45 = pp[2];
+    return q;
+  };
+  auto accumulate = [&](const Rec &q, c128 *arow) {
+    const int t = q.item >> 3, li = q.item & 7;
+    const int a = (li < 3) ? 0 : (li < 5 ? 1 : 2);
+    const int b = (li == 0) ? 1 : ((li == 1 || li == 3) ? 2 : 3);
+    const int pos[6] = {(int)(q.p01 & 0xffff), (int)(q.p01 >> 16), (int)(q.p23 & 0xffff), (int)(q.p23 >> 16), (int)(q.p45 & 0xffff), (int)(q.p45 >> 16)};
+    const double ra[4] = {q.a01.x, q.a01.y, q.a23.x, q.a23.y}, rb[4] = {q.b01.x, q.b01.y, q.b23.x, q.b23.y};
+    const double V = q.tail.x;
+    const unsigned packed = (unsigned)__double2loint(q.tail.y);
+    const unsigned sg = packed & 0xffu;
+    const int slot = (int)((packed >> 8) & 0xffu);
+    c128 kf = s_kf[slot], mf = s_mf[slot];
+    if (s_pml[slot]) {
+      const c128 st = pml_stretch_of_tet(slots[slot].pml, slot_bbox + slot * 6, xyz, tet_nodes, t, omega);
+      kf = cdiv(kf, st);
+      mf = cmul(mf, st);
     }
-    out[i] = acc;
+    const double V4 = 4.0 * V, Ieq = V / 10.0, Ine = V / 20.0;
+    const unsigned si = (sg >> li) & 1u;
+    constexpr int PA[6] = {0, 0, 0, 1, 1, 2}, PB[6] = {1, 2, 3, 2, 3, 3};
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      const int c = PA[j], d = PB[j];
+      const double Kj = V4 * (ra[c] * rb[d] - ra[d] * rb[c]);
+      double Mj = 0.0;
+      Mj += rb[d] * ((a == c) ? Ieq : Ine);
+      Mj -= rb[c] * ((a == d) ? Ieq : Ine);
+      Mj -= ra[d] * ((b == c) ? Ieq : Ine);
+      Mj += ra[c] * ((b == d) ? Ieq : Ine);
+      const double sgn = (((sg >> j) & 1u) ^ si) ? -1.0 : 1.0;
+      const double kk = Kj * sgn, mm = Mj * sgn;
+      c128 v = arow[pos[j]];
+      v.x += kk * kf.x + mm * mf.x;
+      v.y += kk * kf.y + mm * mf.y;
+      arow[pos[j]] = v;
+    }
+  };
+
+  for (int lr = threadIdx.x; lr < nrow; lr += blockDim.x) {
+    const int r = r0 + lr;
+    const int rs = s_rowptr[lr], re = s_rowptr[lr + 1];
+    const int kb = e2t_ptr[r], ke = e2t_ptr[r + 1];
+    // software pipeline (rolled): the id of incidence k+2 and the record of incidence k+1 are in
+    // flight while incidence k is accumulated
+    const bool live = !dir[r];  // Dirichlet row: identity, written below
+    for (int i = rs; i < re; ++i) s_rowid[i] = (uint16_t)lr;
+    if (!live || kb >= ke) continue;
+    c128 *arow = acc + rs + lr;
+    int it1 = (kb + 1 < ke) ? e2t_item[kb + 1] : -1;
+    Rec cur = fetch(e2t_item[kb], kb);
+    for (int k = kb; k < ke; ++k) {
+      const int it2 = (k + 2 < ke) ? e2t_item[k + 2] : -1;
+      Rec nxt = cur;
+      if (it1 >= 0) nxt = fetch(it1, k + 1);
+      accumulate(cur, arow);
+      cur = nxt;
+      it1 = it2;
+    }
+  }
+  __syncthreads();
+
+  c128 *out = vals + (size_t)(first + fi) * (size_t)nnz + base;
+  const double diag_one = (mode == 2) ? 0.0 : 1.0;
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const int lr = s_rowid[i];
+    const int r = r0 + lr;
+    const int c = colidx[base + i];
+    c128 v = acc[i + lr];
+    if (dir[r] | dir[c]) v = cmake(r == c ? diag_one : 0.0, 0.0);
+    out[i] = v;
   }
 }
 
-size_t assemble_smem_bytes(int n_slots) { return 2 * (size_t)n_slots * sizeof(c128) + (size_t)n_slots + 16; }
+size_t assemble_smem_bytes(int n_slots) {
+  return (size_t)ASM_ACC_ENTRIES * sizeof(c128) + 2 * (size_t)n_slots * sizeof(c128) + (ASM_CHUNK_ROWS + 1) * sizeof(int32_t) +
+         (size_t)ASM_CHUNK_NNZ * sizeof(uint16_t) + (size_t)n_slots + 16;
+}
 
 // blob layout: [SlotMat x n_slots][efb_pole x n_poles][double omega x count]
 int assemble_launch(System *S, int first, int count, int mode) {
@@ -254,13 +319,12 @@ int assemble_launch(System *S, int first, int count, int mode) {
   EFB_CUDA(c, cudaMemcpyAsync(S->d_mat_blob, S->last_mat_blob.data(), total, cudaMemcpyHostToDevice, c->stream));
   const unsigned char *blob = (const unsigned char *)S->d_mat_blob;
   const size_t smem = assemble_smem_bytes(ns);
-  // enough CTAs to fill the chip several times over; grid-stride beyond that
-  const long long want = (S->nnz + ASM_THREADS - 1) / ASM_THREADS;
-  const int per_f = (int)std::max<long long>(1, std::min<long long>(want, (long long)c->sm_count * 64 / std::max(1, std::min(count, 8))));
-  dim3 grid((unsigned)per_f, (unsigned)count);
+  EFB_CUDA(c, cudaFuncSetAttribute(k_assemble_volume, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)assemble_smem_bytes(MAX_SLOTS)));
+  dim3 grid((unsigned)S->n_chunks, (unsigned)count);
   k_assemble_volume<<<grid, ASM_THREADS, smem, c->stream>>>(
-      M->d_geom, M->d_xyz, M->d_tet_nodes, S->d_ent_ptr, S->d_ent_item, S->d_ent_flag, (const SlotMat *)blob,
-      (const efb_pole *)(blob + off_poles), M->d_slot_bbox, (const double *)(blob + off_om), ns, mode, first, (long long)S->nnz, S->d_vals);
+      M->d_geom, M->d_xyz, M->d_tet_nodes, M->d_e2t_ptr, M->d_e2t_item, S->d_e2t_pos,
+      S->d_chunk_row, S->d_rowptr, S->d_colidx, S->d_dir, (const SlotMat *)blob, (const efb_pole *)(blob + off_poles),
+      M->d_slot_bbox, (const double *)(blob + off_om), ns, mode, first, (long long)S->nnz, S->d_vals);
   EFB_CHECK_LAUNCH(c);
   return EFB_OK;
 }

@@ -47,7 +47,10 @@ __host__ __device__ __forceinline__ c128 cfma(c128 a, c128 b, c128 acc) {  // ac
 }
 
 // ------------------------------------------------------------------ limits
-constexpr int ASM_THREADS = 256;
+constexpr int ASM_CHUNK_NNZ = 5376;   // matrix entries per assembly CTA
+constexpr int ASM_CHUNK_ROWS = 768;   // rows per assembly CTA (rowptr slice in smem; also the bank-skew padding)
+constexpr int ASM_ACC_ENTRIES = ASM_CHUNK_NNZ + ASM_CHUNK_ROWS;  // 96 KB of c128 accumulators
+constexpr int ASM_THREADS = 384;
 constexpr int MAX_SLOTS = 256;        // distinct physical tags
 constexpr int NSCAL = 16;             // per-system device scalars (c128)
 constexpr int RED_MAX_BLOCKS = 1184;  // 148 SMs x 8
@@ -88,6 +91,8 @@ struct Mesh {
   int4 *d_tet_nodes = nullptr;       // [n_tet]
   uint8_t *d_tet_sign = nullptr;     // [n_tet] bit k set => orient[k] == -1
   uint8_t *d_tet_slot = nullptr;     // [n_tet]
+  int32_t *d_e2t_ptr = nullptr;      // [m+1]
+  int32_t *d_e2t_item = nullptr;     // [6*n_tet]
   double *d_slot_bbox = nullptr;     // [n_slots*6] min xyz, max xyz over the slot's tets
   TetGeom *d_geom = nullptr;         // [n_tet] frequency-independent element geometry
 };
@@ -106,10 +111,10 @@ struct System {
   c128 *d_x = nullptr;         // [n_sys][m]
   uint8_t *d_dir = nullptr;    // [m] Dirichlet flags
   bool has_dir = false;
-  // assembly maps (mesh-born systems): CSR entry -> its (tet, li, lj) contributions, ascending tet
-  int32_t *d_ent_ptr = nullptr;    // [nnz+1]
-  uint32_t *d_ent_item = nullptr;  // [36*n_tet]  tet<<6 | li<<3 | lj
-  uint8_t *d_ent_flag = nullptr;   // [nnz] Dirichlet action: 0 keep, 1 zero, 2 Dirichlet diagonal
+  // assembly maps (mesh-born systems)
+  uint16_t *d_e2t_pos = nullptr;   // [6*n_tet*6] column offsets inside the row
+  int32_t *d_chunk_row = nullptr;  // [n_chunks+1]
+  int n_chunks = 0;
   // CSR-stream SpMV: row-aligned chunks of <= SPMV_STREAM_W entries (one warp each); null if a row is longer
   int32_t *d_sp_chunk = nullptr;   // [n_sp_chunks+1]
   int n_sp_chunks = 0;
