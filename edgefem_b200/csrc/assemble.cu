@@ -202,82 +202,56 @@ k_assemble_volume(const TetGeom *__restrict__ geom, const double4 *__restrict__ 
   }
   __syncthreads();
 
-  // one (edge, tet) incidence: everything the row contribution needs, fetched with 8 independent loads
-  struct Rec {
-    double2 a01, a23, b01, b23, tail;
-    uint32_t p01, p23, p45;
-    int item;
-  };
-  auto fetch = [&](int item, int k) {
-    Rec q;
-    q.item = item;
-    const int t = item >> 3, li = item & 7;
-    const TetGeom *__restrict__ G = geom + t;
-    const int a = (li < 3) ? 0 : (li < 5 ? 1 : 2);
-    const int b = (li == 0) ? 1 : ((li == 1 || li == 3) ? 2 : 3);
-    const double2 *ra2 = (const double2 *)G->gg[a], *rb2 = (const double2 *)G->gg[b];
-    q.a01 = ra2[0]; q.a23 = ra2[1]; q.b01 = rb2[0]; q.b23 = rb2[1];
-    q.tail = *(const double2 *)&G->V;
-    const uint32_t *pp = (const uint32_t *)(e2t_pos + (size_t)k * 6);  // 6 x uint16 = 12 bytes, 4-byte aligned
-    q.p01 = pp[0]; q.p23 = pp[1]; q.p45 = pp[2];
-    return q;
-  };
-  auto accumulate = [&](const Rec &q, c128 *arow) {
-    const int t = q.item >> 3, li = q.item & 7;
-    const int a = (li < 3) ? 0 : (li < 5 ? 1 : 2);
-    const int b = (li == 0) ? 1 : ((li == 1 || li == 3) ? 2 : 3);
-    const int pos[6] = {(int)(q.p01 & 0xffff), (int)(q.p01 >> 16), (int)(q.p23 & 0xffff), (int)(q.p23 >> 16), (int)(q.p45 & 0xffff), (int)(q.p45 >> 16)};
-    const double ra[4] = {q.a01.x, q.a01.y, q.a23.x, q.a23.y}, rb[4] = {q.b01.x, q.b01.y, q.b23.x, q.b23.y};
-    const double V = q.tail.x;
-    const unsigned packed = (unsigned)__double2loint(q.tail.y);
-    const unsigned sg = packed & 0xffu;
-    const int slot = (int)((packed >> 8) & 0xffu);
-    c128 kf = s_kf[slot], mf = s_mf[slot];
-    if (s_pml[slot]) {
-      const c128 st = pml_stretch_of_tet(slots[slot].pml, slot_bbox + slot * 6, xyz, tet_nodes, t, omega);
-      kf = cdiv(kf, st);
-      mf = cmul(mf, st);
-    }
-    const double V4 = 4.0 * V, Ieq = V / 10.0, Ine = V / 20.0;
-    const unsigned si = (sg >> li) & 1u;
-    constexpr int PA[6] = {0, 0, 0, 1, 1, 2}, PB[6] = {1, 2, 3, 2, 3, 3};
-#pragma unroll
-    for (int j = 0; j < 6; ++j) {
-      const int c = PA[j], d = PB[j];
-      const double Kj = V4 * (ra[c] * rb[d] - ra[d] * rb[c]);
-      double Mj = 0.0;
-      Mj += rb[d] * ((a == c) ? Ieq : Ine);
-      Mj -= rb[c] * ((a == d) ? Ieq : Ine);
-      Mj -= ra[d] * ((b == c) ? Ieq : Ine);
-      Mj += ra[c] * ((b == d) ? Ieq : Ine);
-      const double sgn = (((sg >> j) & 1u) ^ si) ? -1.0 : 1.0;
-      const double kk = Kj * sgn, mm = Mj * sgn;
-      c128 v = arow[pos[j]];
-      v.x += kk * kf.x + mm * mf.x;
-      v.y += kk * kf.y + mm * mf.y;
-      arow[pos[j]] = v;
-    }
-  };
-
   for (int lr = threadIdx.x; lr < nrow; lr += blockDim.x) {
     const int r = r0 + lr;
     const int rs = s_rowptr[lr], re = s_rowptr[lr + 1];
-    const int kb = e2t_ptr[r], ke = e2t_ptr[r + 1];
-    // software pipeline (rolled): the id of incidence k+2 and the record of incidence k+1 are in
-    // flight while incidence k is accumulated
-    const bool live = !dir[r];  // Dirichlet row: identity, written below
     for (int i = rs; i < re; ++i) s_rowid[i] = (uint16_t)lr;
-    if (!live || kb >= ke) continue;
+    if (dir[r]) continue;  // Dirichlet row: identity, written below
     c128 *arow = acc + rs + lr;
-    int it1 = (kb + 1 < ke) ? e2t_item[kb + 1] : -1;
-    Rec cur = fetch(e2t_item[kb], kb);
+    const int kb = e2t_ptr[r], ke = e2t_ptr[r + 1];
     for (int k = kb; k < ke; ++k) {
-      const int it2 = (k + 2 < ke) ? e2t_item[k + 2] : -1;
-      Rec nxt = cur;
-      if (it1 >= 0) nxt = fetch(it1, k + 1);
-      accumulate(cur, arow);
-      cur = nxt;
-      it1 = it2;
+      const int item = e2t_item[k];
+      const int t = item >> 3, li = item & 7;
+      const TetGeom *__restrict__ G = geom + t;
+      const int a = (li < 3) ? 0 : (li < 5 ? 1 : 2);
+      const int b = (li == 0) ? 1 : ((li == 1 || li == 3) ? 2 : 3);
+      // rows a and b of the Gram matrix (32 B each), then (V, sign|slot)
+      const double2 *ra2 = (const double2 *)G->gg[a], *rb2 = (const double2 *)G->gg[b];
+      const double2 a01 = ra2[0], a23 = ra2[1], b01 = rb2[0], b23 = rb2[1];
+      const double2 tail = *(const double2 *)&G->V;
+      const uint16_t *pp = e2t_pos + (size_t)k * 6;  // 6 x uint16 = 12 bytes, 4-byte aligned
+      const uint32_t p01 = *(const uint32_t *)(pp), p23 = *(const uint32_t *)(pp + 2), p45 = *(const uint32_t *)(pp + 4);
+      const int pos[6] = {(int)(p01 & 0xffff), (int)(p01 >> 16), (int)(p23 & 0xffff), (int)(p23 >> 16), (int)(p45 & 0xffff), (int)(p45 >> 16)};
+      const double ra[4] = {a01.x, a01.y, a23.x, a23.y}, rb[4] = {b01.x, b01.y, b23.x, b23.y};
+      const double V = tail.x;
+      const unsigned packed = (unsigned)__double2loint(tail.y);
+      const unsigned sg = packed & 0xffu;
+      const int slot = (int)((packed >> 8) & 0xffu);
+      c128 kf = s_kf[slot], mf = s_mf[slot];
+      if (s_pml[slot]) {
+        const c128 st = pml_stretch_of_tet(slots[slot].pml, slot_bbox + slot * 6, xyz, tet_nodes, t, omega);
+        kf = cdiv(kf, st);
+        mf = cmul(mf, st);
+      }
+      const double V4 = 4.0 * V, Ieq = V / 10.0, Ine = V / 20.0;
+      const unsigned si = (sg >> li) & 1u;
+      constexpr int PA[6] = {0, 0, 0, 1, 1, 2}, PB[6] = {1, 2, 3, 2, 3, 3};
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const int c = PA[j], d = PB[j];
+        const double Kj = V4 * (ra[c] * rb[d] - ra[d] * rb[c]);
+        double Mj = 0.0;
+        Mj += rb[d] * ((a == c) ? Ieq : Ine);
+        Mj -= rb[c] * ((a == d) ? Ieq : Ine);
+        Mj -= ra[d] * ((b == c) ? Ieq : Ine);
+        Mj += ra[c] * ((b == d) ? Ieq : Ine);
+        const double sgn = (((sg >> j) & 1u) ^ si) ? -1.0 : 1.0;
+        const double kk = Kj * sgn, mm = Mj * sgn;
+        c128 v = arow[pos[j]];
+        v.x += kk * kf.x + mm * mf.x;
+        v.y += kk * kf.y + mm * mf.y;
+        arow[pos[j]] = v;
+      }
     }
   }
   __syncthreads();
