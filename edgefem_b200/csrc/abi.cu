@@ -86,6 +86,18 @@ __global__ void k_bbox_decode(unsigned long long *enc, double *out, int n) {
   out[i] = __longlong_as_double((long long)u);
 }
 
+// per-entry Dirichlet action (frequency independent): 0 keep, 1 -> 0, 2 -> Dirichlet diagonal
+__global__ void k_entry_flags(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx, const uint8_t *__restrict__ dir, int m,
+                              uint8_t *__restrict__ flag) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= m) return;
+  const uint8_t dr = dir[r];
+  for (int k = rowptr[r]; k < rowptr[r + 1]; ++k) {
+    const int c = colidx[k];
+    flag[k] = (dr | dir[c]) ? (uint8_t)(c == r ? 2 : 1) : (uint8_t)0;
+  }
+}
+
 __global__ void k_node_dir(const int2 *__restrict__ edge_nodes, const uint8_t *__restrict__ dir, int m,
                            uint8_t *node_dir) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -515,6 +527,8 @@ int efb_system_create(efb_mesh *mesh_, int64_t n_extra, const int32_t *extra_row
   if ((rc = system_alloc_common(S))) return rc;
   if ((rc = dev_upload(c, &S->d_e2t_pos, pos.data(), pos.size()))) return rc;
   if ((rc = dev_upload(c, &S->d_chunk_row, chunk.data(), chunk.size()))) return rc;
+  if ((rc = dev_alloc(c, &S->d_ent_flag, (size_t)nnz))) return rc;
+  EFB_CUDA(c, cudaMemsetAsync(S->d_ent_flag, 0, (size_t)nnz, c->stream));
   if ((rc = system_set_gradient(S, M->n_node, M->h_edge_nodes.data()))) return rc;
   EFB_CUDA(c, cudaStreamSynchronize(c->stream));
   *out = (efb_system *)S;
@@ -563,7 +577,7 @@ void efb_system_destroy(efb_system *sys_) {
   cudaStreamSynchronize(S->ctx->stream);
   solver_free(S);
   cudaFree(S->d_rowptr); cudaFree(S->d_colidx); cudaFree(S->d_diag_pos); cudaFree(S->d_vals);
-  cudaFree(S->d_b); cudaFree(S->d_x); cudaFree(S->d_dir); cudaFree(S->d_e2t_pos); cudaFree(S->d_chunk_row); cudaFree(S->d_sp_chunk);
+  cudaFree(S->d_b); cudaFree(S->d_x); cudaFree(S->d_dir); cudaFree(S->d_e2t_pos); cudaFree(S->d_chunk_row); cudaFree(S->d_ent_flag); cudaFree(S->d_sp_chunk);
   cudaFree(S->d_sell_ptr); cudaFree(S->d_sell_col); cudaFree(S->d_sell_perm); cudaFree(S->d_sell_vals);
   cudaFree(S->d_edge_nodes); cudaFree(S->d_n2e_ptr); cudaFree(S->d_n2e_item); cudaFree(S->d_node_dir);
   cudaFree(S->d_mat_blob);
@@ -616,6 +630,10 @@ int efb_system_set_dirichlet(efb_system *sys_, const uint8_t *flags) {
   EFB_CUDA(c, cudaSetDevice(c->device));
   EFB_CUDA(c, cudaMemcpyAsync(S->d_dir, flags, (size_t)S->m, cudaMemcpyHostToDevice, c->stream));
   S->has_dir = true;
+  if (S->d_ent_flag) {
+    k_entry_flags<<<(S->m + 127) / 128, 128, 0, c->stream>>>(S->d_rowptr, S->d_colidx, S->d_dir, S->m, S->d_ent_flag);
+    EFB_CHECK_LAUNCH(c);
+  }
   if (S->d_node_dir) {
     EFB_CUDA(c, cudaMemsetAsync(S->d_node_dir, 0, (size_t)S->n_node, c->stream));
     k_node_dir<<<(S->m + 255) / 256, 256, 0, c->stream>>>(S->d_edge_nodes, S->d_dir, S->m, S->d_node_dir);

@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(ASM_THREADS, 2)
 k_assemble_volume(const TetGeom *__restrict__ geom, const double4 *__restrict__ xyz, const int4 *__restrict__ tet_nodes,
                   const int32_t *__restrict__ e2t_ptr, const int32_t *__restrict__ e2t_item,
                   const uint16_t *__restrict__ e2t_pos, const int32_t *__restrict__ chunk_row,
-                  const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
+                  const int32_t *__restrict__ rowptr, const uint8_t *__restrict__ ent_flag,
                   const uint8_t *__restrict__ dir, const SlotMat *__restrict__ slots,
                   const efb_pole *__restrict__ poles, const double *__restrict__ slot_bbox,
                   const double *__restrict__ omegas, int n_slots, int mode, int first, long long nnz,
@@ -256,14 +256,16 @@ k_assemble_volume(const TetGeom *__restrict__ geom, const double4 *__restrict__ 
   }
   __syncthreads();
 
-  c128 *out = vals + (size_t)(first + fi) * (size_t)nnz + base;
+  // write-out: fully coalesced 16-byte stores; the Dirichlet action of every entry is a precomputed byte
+  // (no column/flag gathers here), four independent entries in flight per thread
+  c128 *__restrict__ out = vals + (size_t)(first + fi) * (size_t)nnz + base;
+  const uint8_t *__restrict__ fl = ent_flag + base;
   const double diag_one = (mode == 2) ? 0.0 : 1.0;
+#pragma unroll 4
   for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
-    const int lr = s_rowid[i];
-    const int r = r0 + lr;
-    const int c = colidx[base + i];
-    c128 v = acc[i + lr];
-    if (dir[r] | dir[c]) v = cmake(r == c ? diag_one : 0.0, 0.0);
+    const int f = fl[i];
+    c128 v = acc[i + s_rowid[i]];
+    if (f) v = cmake(f == 2 ? diag_one : 0.0, 0.0);
     out[i] = v;
   }
 }
@@ -297,7 +299,7 @@ int assemble_launch(System *S, int first, int count, int mode) {
   dim3 grid((unsigned)S->n_chunks, (unsigned)count);
   k_assemble_volume<<<grid, ASM_THREADS, smem, c->stream>>>(
       M->d_geom, M->d_xyz, M->d_tet_nodes, M->d_e2t_ptr, M->d_e2t_item, S->d_e2t_pos,
-      S->d_chunk_row, S->d_rowptr, S->d_colidx, S->d_dir, (const SlotMat *)blob, (const efb_pole *)(blob + off_poles),
+      S->d_chunk_row, S->d_rowptr, S->d_ent_flag, S->d_dir, (const SlotMat *)blob, (const efb_pole *)(blob + off_poles),
       M->d_slot_bbox, (const double *)(blob + off_om), ns, mode, first, (long long)S->nnz, S->d_vals);
   EFB_CHECK_LAUNCH(c);
   return EFB_OK;
