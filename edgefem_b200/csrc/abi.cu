@@ -86,16 +86,18 @@ __global__ void k_bbox_decode(unsigned long long *enc, double *out, int n) {
   out[i] = __longlong_as_double((long long)u);
 }
 
-// per-entry Dirichlet action (frequency independent): 0 keep, 1 -> 0, 2 -> Dirichlet diagonal
-__global__ void k_entry_flags(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx, const uint8_t *__restrict__ dir, int m,
-                              uint8_t *__restrict__ flag) {
+// bake the Dirichlet COLUMN mask into the assembly map: bit 15 of an incidence's column offset says
+// "this column is a Dirichlet edge" (the entry then stays an explicit zero)
+__global__ void k_pos_dirichlet(const int32_t *__restrict__ e2t_ptr, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
+                                const uint8_t *__restrict__ dir, int m, uint16_t *pos) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= m) return;
-  const uint8_t dr = dir[r];
-  for (int k = rowptr[r]; k < rowptr[r + 1]; ++k) {
-    const int c = colidx[k];
-    flag[k] = (dr | dir[c]) ? (uint8_t)(c == r ? 2 : 1) : (uint8_t)0;
-  }
+  const int rb = rowptr[r];
+  for (int k = e2t_ptr[r]; k < e2t_ptr[r + 1]; ++k)
+    for (int j = 0; j < 6; ++j) {
+      const uint16_t p = pos[(size_t)k * 6 + j] & 0x7fffu;
+      pos[(size_t)k * 6 + j] = p | (dir[colidx[rb + p]] ? 0x8000u : 0u);
+    }
 }
 
 __global__ void k_node_dir(const int2 *__restrict__ edge_nodes, const uint8_t *__restrict__ dir, int m,
@@ -485,9 +487,9 @@ int efb_system_create(efb_mesh *mesh_, int64_t n_extra, const int32_t *extra_row
     delete S;
     return fail(c, EFB_ERR_LIMIT, "efb_system_create: nnz %lld >= 2^31 (int32 CSR like Eigen's default index)", (long long)nnz);
   }
-  if (maxrow > ASM_CHUNK_NNZ || maxrow > 65535) {
+  if (maxrow > ASM_CHUNK_NNZ || maxrow > 32767) {
     delete S;
-    return fail(c, EFB_ERR_LIMIT, "efb_system_create: a row has %d entries (limit %d)", maxrow, std::min(ASM_CHUNK_NNZ, 65535));
+    return fail(c, EFB_ERR_LIMIT, "efb_system_create: a row has %d entries (limit %d)", maxrow, std::min(ASM_CHUNK_NNZ, 32767));
   }
   S->nnz = nnz;
   for (int r = 0; r < m; ++r) S->h_rowptr[r + 1] = S->h_rowptr[r] + rowlen[r];
@@ -527,8 +529,7 @@ int efb_system_create(efb_mesh *mesh_, int64_t n_extra, const int32_t *extra_row
   if ((rc = system_alloc_common(S))) return rc;
   if ((rc = dev_upload(c, &S->d_e2t_pos, pos.data(), pos.size()))) return rc;
   if ((rc = dev_upload(c, &S->d_chunk_row, chunk.data(), chunk.size()))) return rc;
-  if ((rc = dev_alloc(c, &S->d_ent_flag, (size_t)nnz))) return rc;
-  EFB_CUDA(c, cudaMemsetAsync(S->d_ent_flag, 0, (size_t)nnz, c->stream));
+
   if ((rc = system_set_gradient(S, M->n_node, M->h_edge_nodes.data()))) return rc;
   EFB_CUDA(c, cudaStreamSynchronize(c->stream));
   *out = (efb_system *)S;
@@ -577,7 +578,7 @@ void efb_system_destroy(efb_system *sys_) {
   cudaStreamSynchronize(S->ctx->stream);
   solver_free(S);
   cudaFree(S->d_rowptr); cudaFree(S->d_colidx); cudaFree(S->d_diag_pos); cudaFree(S->d_vals);
-  cudaFree(S->d_b); cudaFree(S->d_x); cudaFree(S->d_dir); cudaFree(S->d_e2t_pos); cudaFree(S->d_chunk_row); cudaFree(S->d_ent_flag); cudaFree(S->d_sp_chunk);
+  cudaFree(S->d_b); cudaFree(S->d_x); cudaFree(S->d_dir); cudaFree(S->d_e2t_pos); cudaFree(S->d_chunk_row); cudaFree(S->d_sp_chunk);
   cudaFree(S->d_sell_ptr); cudaFree(S->d_sell_col); cudaFree(S->d_sell_perm); cudaFree(S->d_sell_vals);
   cudaFree(S->d_edge_nodes); cudaFree(S->d_n2e_ptr); cudaFree(S->d_n2e_item); cudaFree(S->d_node_dir);
   cudaFree(S->d_mat_blob);
@@ -630,8 +631,8 @@ int efb_system_set_dirichlet(efb_system *sys_, const uint8_t *flags) {
   EFB_CUDA(c, cudaSetDevice(c->device));
   EFB_CUDA(c, cudaMemcpyAsync(S->d_dir, flags, (size_t)S->m, cudaMemcpyHostToDevice, c->stream));
   S->has_dir = true;
-  if (S->d_ent_flag) {
-    k_entry_flags<<<(S->m + 127) / 128, 128, 0, c->stream>>>(S->d_rowptr, S->d_colidx, S->d_dir, S->m, S->d_ent_flag);
+  if (S->d_e2t_pos && S->mesh) {
+    k_pos_dirichlet<<<(S->m + 127) / 128, 128, 0, c->stream>>>(S->mesh->d_e2t_ptr, S->d_rowptr, S->d_colidx, S->d_dir, S->m, S->d_e2t_pos);
     EFB_CHECK_LAUNCH(c);
   }
   if (S->d_node_dir) {

@@ -110,6 +110,11 @@ int launch_tet_geometry(Mesh *M) {
   return EFB_OK;
 }
 
+__device__ __forceinline__ void prefetch_l2(const void *p) {  // a TetGeom record is 144 B: at most 2 lines
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+  asm volatile("prefetch.global.L2 [%0];" ::"l"((const char *)p + 128));
+}
+
 // PML scalar stretch of one tet (src/assemble_maxwell.cpp:121-172)
 __device__ c128 pml_stretch(const efb_pml &pm, const double *__restrict__ bbox, V3 cen, double omega) {
   if (omega == 0.0 || pm.kind == EFB_PML_NONE) return cmake(1.0, 0.0);
@@ -151,7 +156,7 @@ __global__ void __launch_bounds__(ASM_THREADS, 2)
 k_assemble_volume(const TetGeom *__restrict__ geom, const double4 *__restrict__ xyz, const int4 *__restrict__ tet_nodes,
                   const int32_t *__restrict__ e2t_ptr, const int32_t *__restrict__ e2t_item,
                   const uint16_t *__restrict__ e2t_pos, const int32_t *__restrict__ chunk_row,
-                  const int32_t *__restrict__ rowptr, const uint8_t *__restrict__ ent_flag,
+                  const int32_t *__restrict__ rowptr, const int32_t *__restrict__ diag_pos,
                   const uint8_t *__restrict__ dir, const SlotMat *__restrict__ slots,
                   const efb_pole *__restrict__ poles, const double *__restrict__ slot_bbox,
                   const double *__restrict__ omegas, int n_slots, int mode, int first, long long nnz,
@@ -175,6 +180,12 @@ k_assemble_volume(const TetGeom *__restrict__ geom, const double4 *__restrict__ 
   const double k0 = omega / C0;
   const double k0sq = k0 * k0;
 
+  // get the first Gram record of this thread's row moving towards L2 while the CTA sets up
+  if ((int)threadIdx.x < nrow) {
+    const int r = r0 + threadIdx.x;
+    const int kb = e2t_ptr[r];
+    if (kb < e2t_ptr[r + 1]) prefetch_l2(geom + (e2t_item[kb] >> 3));
+  }
   for (int i = threadIdx.x; i < cnt + nrow; i += blockDim.x) acc[i] = cmake(0.0, 0.0);
   for (int i = threadIdx.x; i <= nrow; i += blockDim.x) s_rowptr[i] = rowptr[r0 + i] - base;
   for (int s = threadIdx.x; s < n_slots; s += blockDim.x) {
@@ -202,15 +213,27 @@ k_assemble_volume(const TetGeom *__restrict__ geom, const double4 *__restrict__ 
   }
   __syncthreads();
 
+  const double diag_one = (mode == 2) ? 0.0 : 1.0;
   for (int lr = threadIdx.x; lr < nrow; lr += blockDim.x) {
     const int r = r0 + lr;
     const int rs = s_rowptr[lr], re = s_rowptr[lr + 1];
     for (int i = rs; i < re; ++i) s_rowid[i] = (uint16_t)lr;
-    if (dir[r]) continue;  // Dirichlet row: identity, written below
     c128 *arow = acc + rs + lr;
+    if (dir[r]) {  // Dirichlet row: zeros (kept in the pattern) and the unit diagonal
+      const int dp = diag_pos[r];
+      if (dp >= 0) arow[dp - (base + rs)] = cmake(diag_one, 0.0);
+      continue;
+    }
     const int kb = e2t_ptr[r], ke = e2t_ptr[r + 1];
+    if (kb >= ke) continue;
+    // the id of incidence k+2 is in flight and the Gram record of incidence k+1 is being pulled into L2
+    // while incidence k is accumulated (no extra registers: prefetch, not load)
+    int it_cur = e2t_item[kb];
+    int it_nxt = (kb + 1 < ke) ? e2t_item[kb + 1] : -1;
     for (int k = kb; k < ke; ++k) {
-      const int item = e2t_item[k];
+      const int it_n2 = (k + 2 < ke) ? e2t_item[k + 2] : -1;
+      if (it_nxt >= 0) prefetch_l2(geom + (it_nxt >> 3));
+      const int item = it_cur;
       const int t = item >> 3, li = item & 7;
       const TetGeom *__restrict__ G = geom + t;
       const int a = (li < 3) ? 0 : (li < 5 ? 1 : 2);
@@ -221,6 +244,7 @@ k_assemble_volume(const TetGeom *__restrict__ geom, const double4 *__restrict__ 
       const double2 tail = *(const double2 *)&G->V;
       const uint16_t *pp = e2t_pos + (size_t)k * 6;  // 6 x uint16 = 12 bytes, 4-byte aligned
       const uint32_t p01 = *(const uint32_t *)(pp), p23 = *(const uint32_t *)(pp + 2), p45 = *(const uint32_t *)(pp + 4);
+      // bit 15 of a position: the column is a Dirichlet edge (entry stays an explicit zero)
       const int pos[6] = {(int)(p01 & 0xffff), (int)(p01 >> 16), (int)(p23 & 0xffff), (int)(p23 >> 16), (int)(p45 & 0xffff), (int)(p45 >> 16)};
       const double ra[4] = {a01.x, a01.y, a23.x, a23.y}, rb[4] = {b01.x, b01.y, b23.x, b23.y};
       const double V = tail.x;
@@ -238,6 +262,7 @@ k_assemble_volume(const TetGeom *__restrict__ geom, const double4 *__restrict__ 
       constexpr int PA[6] = {0, 0, 0, 1, 1, 2}, PB[6] = {1, 2, 3, 2, 3, 3};
 #pragma unroll
       for (int j = 0; j < 6; ++j) {
+        if (pos[j] & 0x8000) continue;
         const int c = PA[j], d = PB[j];
         const double Kj = V4 * (ra[c] * rb[d] - ra[d] * rb[c]);
         double Mj = 0.0;
@@ -252,22 +277,17 @@ k_assemble_volume(const TetGeom *__restrict__ geom, const double4 *__restrict__ 
         v.y += kk * kf.y + mm * mf.y;
         arow[pos[j]] = v;
       }
+      it_cur = it_nxt;
+      it_nxt = it_n2;
     }
   }
   __syncthreads();
 
-  // write-out: fully coalesced 16-byte stores; the Dirichlet action of every entry is a precomputed byte
-  // (no column/flag gathers here), four independent entries in flight per thread
+  // write-out: a pure shared -> global copy, fully coalesced 16-byte stores (the Dirichlet mask was
+  // applied while accumulating)
   c128 *__restrict__ out = vals + (size_t)(first + fi) * (size_t)nnz + base;
-  const uint8_t *__restrict__ fl = ent_flag + base;
-  const double diag_one = (mode == 2) ? 0.0 : 1.0;
 #pragma unroll 4
-  for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
-    const int f = fl[i];
-    c128 v = acc[i + s_rowid[i]];
-    if (f) v = cmake(f == 2 ? diag_one : 0.0, 0.0);
-    out[i] = v;
-  }
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) out[i] = acc[i + s_rowid[i]];
 }
 
 size_t assemble_smem_bytes(int n_slots) {
@@ -299,7 +319,7 @@ int assemble_launch(System *S, int first, int count, int mode) {
   dim3 grid((unsigned)S->n_chunks, (unsigned)count);
   k_assemble_volume<<<grid, ASM_THREADS, smem, c->stream>>>(
       M->d_geom, M->d_xyz, M->d_tet_nodes, M->d_e2t_ptr, M->d_e2t_item, S->d_e2t_pos,
-      S->d_chunk_row, S->d_rowptr, S->d_ent_flag, S->d_dir, (const SlotMat *)blob, (const efb_pole *)(blob + off_poles),
+      S->d_chunk_row, S->d_rowptr, S->d_diag_pos, S->d_dir, (const SlotMat *)blob, (const efb_pole *)(blob + off_poles),
       M->d_slot_bbox, (const double *)(blob + off_om), ns, mode, first, (long long)S->nnz, S->d_vals);
   EFB_CHECK_LAUNCH(c);
   return EFB_OK;

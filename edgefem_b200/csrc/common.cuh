@@ -112,9 +112,8 @@ struct System {
   uint8_t *d_dir = nullptr;    // [m] Dirichlet flags
   bool has_dir = false;
   // assembly maps (mesh-born systems)
-  uint16_t *d_e2t_pos = nullptr;   // [6*n_tet*6] column offsets inside the row
+  uint16_t *d_e2t_pos = nullptr;   // [6*n_tet*6] column offsets inside the row (bit 15: Dirichlet column)
   int32_t *d_chunk_row = nullptr;  // [n_chunks+1]
-  uint8_t *d_ent_flag = nullptr;   // [nnz] Dirichlet action per entry: 0 keep, 1 -> 0, 2 -> Dirichlet diagonal
   int n_chunks = 0;
   // CSR-stream SpMV: row-aligned chunks of <= SPMV_STREAM_W entries (one warp each); null if a row is longer
   int32_t *d_sp_chunk = nullptr;   // [n_sp_chunks+1]
