@@ -100,6 +100,13 @@ __global__ void k_pos_dirichlet(const int32_t *__restrict__ e2t_ptr, const int32
     }
 }
 
+__global__ void k_n2e_dirichlet(int32_t *n2e_item, long long n, const uint8_t *__restrict__ dir) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int it = n2e_item[i] & ~2;
+  n2e_item[i] = it | (dir[it >> 2] ? 2 : 0);
+}
+
 __global__ void k_node_dir(const int2 *__restrict__ edge_nodes, const uint8_t *__restrict__ dir, int m,
                            uint8_t *node_dir) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -416,8 +423,8 @@ static int system_set_gradient(System *S, int n_node, const int32_t *edge_nodes)
   {
     std::vector<int32_t> cur(ptr.begin(), ptr.end() - 1);
     for (int e = 0; e < S->m; ++e) {
-      item[cur[edge_nodes[2 * e]]++] = (e << 1);          // tail: G = -1
-      item[cur[edge_nodes[2 * e + 1]]++] = (e << 1) | 1;  // head: G = +1
+      item[cur[edge_nodes[2 * e]]++] = (e << 2);          // tail: G = -1
+      item[cur[edge_nodes[2 * e + 1]]++] = (e << 2) | 1;  // head: G = +1   (bit 1: Dirichlet edge, set by k_n2e_dirichlet)
     }
   }
   if ((rc = dev_upload(c, &S->d_n2e_ptr, ptr.data(), ptr.size()))) return rc;
@@ -639,6 +646,8 @@ int efb_system_set_dirichlet(efb_system *sys_, const uint8_t *flags) {
     EFB_CUDA(c, cudaMemsetAsync(S->d_node_dir, 0, (size_t)S->n_node, c->stream));
     k_node_dir<<<(S->m + 255) / 256, 256, 0, c->stream>>>(S->d_edge_nodes, S->d_dir, S->m, S->d_node_dir);
     EFB_CHECK_LAUNCH(c);
+    k_n2e_dirichlet<<<(2 * S->m + 255) / 256, 256, 0, c->stream>>>(S->d_n2e_item, 2ll * S->m, S->d_dir);
+    EFB_CHECK_LAUNCH(c);
   }
   EFB_CUDA(c, cudaStreamSynchronize(c->stream));
   return EFB_OK;
@@ -652,6 +661,8 @@ int efb_system_set_gradient(efb_system *sys_, int32_t n_node, const int32_t *edg
   if (rc) return rc;
   if (S->has_dir) {
     k_node_dir<<<(S->m + 255) / 256, 256, 0, S->ctx->stream>>>(S->d_edge_nodes, S->d_dir, S->m, S->d_node_dir);
+    EFB_CHECK_LAUNCH(S->ctx);
+    k_n2e_dirichlet<<<(2 * S->m + 255) / 256, 256, 0, S->ctx->stream>>>(S->d_n2e_item, 2ll * S->m, S->d_dir);
     EFB_CHECK_LAUNCH(S->ctx);
     EFB_CUDA(S->ctx, cudaStreamSynchronize(S->ctx->stream));
   }

@@ -131,7 +131,7 @@ struct System {
   // gradient (aux preconditioner)
   int2 *d_edge_nodes = nullptr;    // [m]
   int32_t *d_n2e_ptr = nullptr;    // [n_node+1]
-  int32_t *d_n2e_item = nullptr;   // [2m]  edge<<1 | (1 if node is n1 (head, +1) else 0 (tail, -1))
+  int32_t *d_n2e_item = nullptr;   // [2m]  edge<<2 | (Dirichlet edge)<<1 | (1 if node is n1 (head, +1) else 0 (tail, -1))
   uint8_t *d_node_dir = nullptr;   // [n_node] node touches a Dirichlet edge
   // solver workspace (lazy)
   c128 *d_work = nullptr;      // [n_vec][n_sys][m]

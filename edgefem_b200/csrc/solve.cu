@@ -359,8 +359,8 @@ __global__ void k_prec_node(SolveDev D, int first_sys, const c128 *__restrict__ 
     if (li.x != 0.0 || li.y != 0.0) {
       for (int k = D.n2e_ptr[n]; k < D.n2e_ptr[n + 1]; ++k) {
         const int it = D.n2e_item[k];
-        const int e = it >> 1;
-        if (D.dir[e]) continue;
+        if (it & 2) continue;  // Dirichlet edge
+        const int e = it >> 2;
         const c128 a = v[e];
         acc = (it & 1) ? cadd(acc, a) : csub(acc, a);
       }
@@ -661,10 +661,23 @@ k_cocg_small(SolveDev D, const int32_t *__restrict__ sell_ptr, const int32_t *__
         c128 acc[NR];
 #pragma unroll
         for (int r = 0; r < NR; ++r) acc[r] = cmake(0.0, 0.0);
-#pragma unroll 4
-        for (int j = 0; j < width; ++j) {
+        int j = 0;
+        for (; j + 4 <= width; j += 4) {  // four independent 16-byte value loads + column loads in flight per lane
+          c128 a4[4];
+          int c4[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            a4[u] = ldg_stream(vp + 32 * (j + u));
+            c4[u] = ldg_stream(cp + 32 * (j + u));
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int r = 0; r < NR; ++r) acc[r] = cfma(a4[u], p_s[(size_t)r * m + c4[u]], acc[r]);
+        }
+        for (; j < width; ++j) {
           const c128 a = ldg_stream(vp + 32 * j);
-          const int c = __ldg(cp + 32 * j);
+          const int c = ldg_stream(cp + 32 * j);
 #pragma unroll
           for (int r = 0; r < NR; ++r) acc[r] = cfma(a, p_s[(size_t)r * m + c], acc[r]);
         }
@@ -718,36 +731,49 @@ k_cocg_small(SolveDev D, const int32_t *__restrict__ sell_ptr, const int32_t *__
       }
       if (!any) break;
 
-      // (2)+(3) preconditioned COCG until the recursive residual converges
+      // (2)+(3) preconditioned COCG until the recursive residual converges.  Two block reductions per
+      // iteration: (rho_new = r^T z, |r|^2) after the preconditioner and p^T A p after the SpMV.
       bool fresh = true;  // p = z on entry, p = z + beta p afterwards
       for (;;) {
-        // z = M^-1 r  (z parked in q), rho_new = r^T z
+        // z = M^-1 r  (z parked in q), rho_new = r^T z, rr = |r|^2
         if (aux) {
-          for (int n = tid; n < nn; n += nth) {
-            const c128 li = __ldg(&linv[n]);
+          // nodal gather w = diag(G^T A G)^-1 G^T r: 16 lanes cooperate on a node (its ~12 incident edges are
+          // fetched in one parallel step instead of a serial chain), half-warp shuffle reduction
+          const int l16 = tid & 15, g16 = tid >> 4, ng16 = nth >> 4;
+          const unsigned hmask = 0xffffu << (((tid & 31) >> 4) * 16);
+          for (int n = g16; n < nn; n += ng16) {
+            const int kb = __ldg(&D.n2e_ptr[n]), ke = __ldg(&D.n2e_ptr[n + 1]);
             c128 a2[NR];
 #pragma unroll
             for (int r = 0; r < NR; ++r) a2[r] = cmake(0.0, 0.0);
-            if (li.x != 0.0 || li.y != 0.0) {
-              for (int k = __ldg(&D.n2e_ptr[n]); k < __ldg(&D.n2e_ptr[n + 1]); ++k) {
-                const int it = __ldg(&D.n2e_item[k]);
-                const int e = it >> 1;
-                if (D.dir[e]) continue;
+            for (int k = kb + l16; k < ke; k += 16) {
+              const int it = __ldg(&D.n2e_item[k]);
+              if (it & 2) continue;  // Dirichlet edge
+              const int e = it >> 2;
 #pragma unroll
-                for (int r = 0; r < NR; ++r) {
-                  const c128 v = rg[r][e];
-                  a2[r] = (it & 1) ? cadd(a2[r], v) : csub(a2[r], v);
-                }
+              for (int r = 0; r < NR; ++r) {
+                const c128 v = rg[r][e];
+                a2[r] = (it & 1) ? cadd(a2[r], v) : csub(a2[r], v);
               }
             }
 #pragma unroll
-            for (int r = 0; r < NR; ++r) w_s[(size_t)r * nn + n] = cmul(li, a2[r]);
+            for (int r = 0; r < NR; ++r)
+#pragma unroll
+              for (int o = 8; o > 0; o >>= 1) {
+                a2[r].x += __shfl_xor_sync(hmask, a2[r].x, o);
+                a2[r].y += __shfl_xor_sync(hmask, a2[r].y, o);
+              }
+            if (l16 == 0) {
+              const c128 li = __ldg(&linv[n]);
+#pragma unroll
+              for (int r = 0; r < NR; ++r) w_s[(size_t)r * nn + n] = cmul(li, a2[r]);
+            }
           }
           __syncthreads();
         }
-        double dz[2 * NR];
+        double dz[3 * NR];
 #pragma unroll
-        for (int k = 0; k < 2 * NR; ++k) dz[k] = 0.0;
+        for (int k = 0; k < 3 * NR; ++k) dz[k] = 0.0;
         for (int e = tid; e < m; e += nth) {
           const c128 di = __ldg(&dinv[e]);
           int2 ab = make_int2(0, 0);
@@ -760,17 +786,25 @@ k_cocg_small(SolveDev D, const int32_t *__restrict__ sell_ptr, const int32_t *__
             if (g) z = cadd(z, csub(w_s[(size_t)r * nn + ab.y], w_s[(size_t)r * nn + ab.x]));
             qg[r][e] = z;
             const c128 t = cmul(ri, z);
-            dz[2 * r] += t.x; dz[2 * r + 1] += t.y;
+            dz[3 * r] += t.x; dz[3 * r + 1] += t.y;
+            dz[3 * r + 2] += cabs2(ri);
           }
         }
-        block_allreduce<2 * NR>(dz, red);
+        block_allreduce<3 * NR>(dz, red);
+        bool still = false;
         c128 beta[NR];
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
-          const c128 rho_new = cmake(dz[2 * r], dz[2 * r + 1]);
+          const c128 rho_new = cmake(dz[3 * r], dz[3 * r + 1]);
           beta[r] = (fresh || (rho[r].x == 0.0 && rho[r].y == 0.0)) ? cmake(0.0, 0.0) : cdiv(rho_new, rho[r]);
           rho[r] = rho_new;
+          if (act[r]) {
+            rr[r] = dz[3 * r + 2];
+            if (rr[r] <= D.tol2 * bb[r] || iters[r] >= D.max_it || !isfinite(rr[r])) act[r] = false;
+          }
+          still |= act[r];
         }
+        if (!still) break;
         for (int e = tid; e < m; e += nth)
 #pragma unroll
           for (int r = 0; r < NR; ++r) {
@@ -790,31 +824,21 @@ k_cocg_small(SolveDev D, const int32_t *__restrict__ sell_ptr, const int32_t *__
           const bool brk = (pq.x == 0.0 && pq.y == 0.0) || !(isfinite(pq.x) && isfinite(pq.y));
           if (brk) act[r] = false;
           alpha[r] = act[r] ? cdiv(rho[r], pq) : cmake(0.0, 0.0);
+          if (act[r]) iters[r] += 1;
         }
-        // x += alpha p ; r -= alpha q ; rr = |r|^2
-        double dr[NR];
-#pragma unroll
-        for (int r = 0; r < NR; ++r) dr[r] = 0.0;
+        // x += alpha p ; r -= alpha q   (|r|^2 is accumulated by the next preconditioner pass)
         for (int i = tid; i < m; i += nth)
 #pragma unroll
           for (int r = 0; r < NR; ++r) {
             if (!act[r]) continue;
             xg[r][i] = cfma(alpha[r], p_s[(size_t)r * m + i], xg[r][i]);
-            const c128 ri = cfma(cneg(alpha[r]), qg[r][i], rg[r][i]);
-            rg[r][i] = ri;
-            dr[r] += cabs2(ri);
+            rg[r][i] = cfma(cneg(alpha[r]), qg[r][i], rg[r][i]);
           }
-        block_allreduce<NR>(dr, red);
-        bool still = false;
+        bool any2 = false;
 #pragma unroll
-        for (int r = 0; r < NR; ++r) {
-          if (!act[r]) continue;
-          iters[r] += 1;
-          rr[r] = dr[r];
-          if (rr[r] <= D.tol2 * bb[r] || iters[r] >= D.max_it || !isfinite(rr[r])) act[r] = false;
-          still |= act[r];
-        }
-        if (!still) break;
+        for (int r = 0; r < NR; ++r) any2 |= act[r];
+        __syncthreads();
+        if (!any2) break;
       }
     }
     if (tid == 0) {

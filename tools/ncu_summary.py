@@ -58,10 +58,10 @@ def report(src, dst):
                 if k in d:
                     f.write("| %s | %s | %s |\n" % (k, d[k], units[hdr.index(k)]))
             try:
-                rd = float(d["dram__bytes_read.sum"].replace(",", ""))
-                wr = float(d["dram__bytes_write.sum"].replace(",", ""))
-                u = units[hdr.index("dram__bytes_read.sum")]
-                f.write("| **traffic = dram read + write** | %.3f | %s |\n" % (rd + wr, u))
+                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+                rd = float(d["dram__bytes_read.sum"].replace(",", "")) * scale[units[hdr.index("dram__bytes_read.sum")]]
+                wr = float(d["dram__bytes_write.sum"].replace(",", "")) * scale[units[hdr.index("dram__bytes_write.sum")]]
+                f.write("| **traffic = dram read + write** | %.3f | Mbyte |\n" % ((rd + wr) / 1e6))
             except Exception:
                 pass
             f.write("\n")
