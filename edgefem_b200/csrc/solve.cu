@@ -645,42 +645,42 @@ k_cocg_small(SolveDev D, const int32_t *__restrict__ sell_ptr, const int32_t *__
 #pragma unroll
     for (int r = 0; r < NR; ++r) { iters[r] = 0; act[r] = false; conv[r] = false; bb[r] = 0.0; rr[r] = 0.0; rho[r] = cmake(0.0, 0.0); }
 
-    // q = A * (vector in p_s), optional dot p.q.  SELL-32: a lane owns a row, a warp a slice; the slice is
-    // stored column-major so every step is one coalesced 512-byte value load + one 128-byte column load,
-    // all steps of a row are independent (deep memory-level parallelism), no shuffles, no divergence.
+    // q = A * (vector in p_s), optional dot p.q.  SELL-32: a lane owns a row, 32 rows form a slice stored
+    // column-major.  A warp owns a CONTIGUOUS range of slices (balanced by entry count), so its values and
+    // columns are one flat stream: every step is a coalesced 512-byte value load + 128-byte column load,
+    // SPD steps are in flight per lane and the next batch is requested before the current one is consumed
+    // (double buffering in registers); slice ends only flush the row accumulators.  No shuffles.
     const c128 *__restrict__ sv = sell_vals + (size_t)f * (size_t)sell_total;
+    constexpr int SPD = 8;
+    int s_lo, s_hi;
+    {
+      const long long t0 = sell_total * wid / nwarp, t1 = sell_total * (wid + 1) / nwarp;
+      auto lower = [&](long long t) {
+        int lo = 0, hi = n_slices;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if ((long long)__ldg(&sell_ptr[mid]) < t) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+      };
+      s_lo = lower(t0);
+      s_hi = (wid == nwarp - 1) ? n_slices : lower(t1);
+    }
     auto spmv = [&](bool want_dot, double (&dots)[2 * NR]) {
 #pragma unroll
       for (int k = 0; k < 2 * NR; ++k) dots[k] = 0.0;
-      for (int sl = wid; sl < n_slices; sl += nwarp) {
-        const int base = __ldg(&sell_ptr[sl]);
-        const int width = (__ldg(&sell_ptr[sl + 1]) - base) >> 5;
-        const int row = __ldg(&sell_perm[sl * 32 + lane]);
-        const c128 *vp = sv + base + lane;
-        const int32_t *cp = sell_col + base + lane;
-        c128 acc[NR];
+      if (s_lo >= s_hi) return;
+      const c128 *vp = sv + lane;
+      const int32_t *cp = sell_col + lane;
+      int step = __ldg(&sell_ptr[s_lo]) >> 5;
+      const int step_end = __ldg(&sell_ptr[s_hi]) >> 5;
+      int sl = s_lo;
+      int next_b = __ldg(&sell_ptr[sl + 1]) >> 5;
+      int row = __ldg(&sell_perm[sl * 32 + lane]);
+      c128 acc[NR];
 #pragma unroll
-        for (int r = 0; r < NR; ++r) acc[r] = cmake(0.0, 0.0);
-        int j = 0;
-        for (; j + 4 <= width; j += 4) {  // four independent 16-byte value loads + column loads in flight per lane
-          c128 a4[4];
-          int c4[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            a4[u] = ldg_stream(vp + 32 * (j + u));
-            c4[u] = ldg_stream(cp + 32 * (j + u));
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-#pragma unroll
-            for (int r = 0; r < NR; ++r) acc[r] = cfma(a4[u], p_s[(size_t)r * m + c4[u]], acc[r]);
-        }
-        for (; j < width; ++j) {
-          const c128 a = ldg_stream(vp + 32 * j);
-          const int c = ldg_stream(cp + 32 * j);
-#pragma unroll
-          for (int r = 0; r < NR; ++r) acc[r] = cfma(a, p_s[(size_t)r * m + c], acc[r]);
-        }
+      for (int r = 0; r < NR; ++r) acc[r] = cmake(0.0, 0.0);
+      auto flush = [&]() {
         if (row >= 0) {
 #pragma unroll
           for (int r = 0; r < NR; ++r) {
@@ -691,7 +691,57 @@ k_cocg_small(SolveDev D, const int32_t *__restrict__ sell_ptr, const int32_t *__
             }
           }
         }
+#pragma unroll
+        for (int r = 0; r < NR; ++r) acc[r] = cmake(0.0, 0.0);
+        ++sl;
+        if (sl < s_hi) {
+          next_b = __ldg(&sell_ptr[sl + 1]) >> 5;
+          row = __ldg(&sell_perm[sl * 32 + lane]);
+        }
+      };
+      while (sl < s_hi && next_b == step) flush();  // leading empty slices (rows without entries)
+      c128 a0[SPD];
+      int c0[SPD];
+#pragma unroll
+      for (int u = 0; u < SPD; ++u) {
+        const int st = step + u;
+        a0[u] = cmake(0.0, 0.0);
+        c0[u] = 0;
+        if (st < step_end) {
+          a0[u] = ldg_stream(vp + (size_t)32 * st);
+          c0[u] = ldg_stream(cp + (size_t)32 * st);
+        }
       }
+      while (step < step_end) {
+        c128 a1[SPD];
+        int c1[SPD];
+#pragma unroll
+        for (int u = 0; u < SPD; ++u) {
+          const int st = step + SPD + u;
+          a1[u] = cmake(0.0, 0.0);
+          c1[u] = 0;
+          if (st < step_end) {
+            a1[u] = ldg_stream(vp + (size_t)32 * st);
+            c1[u] = ldg_stream(cp + (size_t)32 * st);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < SPD; ++u) {
+          const int st = step + u;
+          if (st < step_end) {
+#pragma unroll
+            for (int r = 0; r < NR; ++r) acc[r] = cfma(a0[u], p_s[(size_t)r * m + c0[u]], acc[r]);
+            while (sl < s_hi && next_b == st + 1) flush();
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < SPD; ++u) {
+          a0[u] = a1[u];
+          c0[u] = c1[u];
+        }
+        step += SPD;
+      }
+      while (sl < s_hi) flush();  // trailing empty slices
     };
 
     for (int cycle = 0;; ++cycle) {
