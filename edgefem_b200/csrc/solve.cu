@@ -579,7 +579,6 @@ k_bicg_x(SolveDev D, int first_sys, c128 *__restrict__ x, c128 *__restrict__ r, 
 // slice of global memory (L2 resident), matrix values stream from HBM once per iteration, every
 // reduction is CTA-local (no tickets, no grid-wide barriers, no kernel launches inside the loop)
 // and CTAs pull the next matrix from an atomic queue when theirs has converged.
-constexpr int SMALL_THREADS = 512;
 constexpr int SMALL_LPR = 16;
 
 template <int N>
@@ -606,8 +605,8 @@ __device__ __forceinline__ void block_allreduce(double (&v)[N], double *red /* s
   __syncthreads();
 }
 
-template <int NR>
-__global__ void __launch_bounds__(SMALL_THREADS, 1)
+template <int NR, int NT, int SPD, bool DB>
+__global__ void __launch_bounds__(NT, 1)
 k_cocg_small(SolveDev D, const int32_t *__restrict__ sell_ptr, const int32_t *__restrict__ sell_col, const int32_t *__restrict__ sell_perm,
              const c128 *__restrict__ sell_vals, long long sell_total, int n_slices, int first_matrix, int n_jobs, int groups_per_matrix,
              int *job_counter, const c128 *__restrict__ bvec, c128 *xvec, c128 *rvec, c128 *qvec, int aux, int zero_x, int max_restarts) {
@@ -651,7 +650,6 @@ k_cocg_small(SolveDev D, const int32_t *__restrict__ sell_ptr, const int32_t *__
     // SPD steps are in flight per lane and the next batch is requested before the current one is consumed
     // (double buffering in registers); slice ends only flush the row accumulators.  No shuffles.
     const c128 *__restrict__ sv = sell_vals + (size_t)f * (size_t)sell_total;
-    constexpr int SPD = 8;
     int s_lo, s_hi;
     {
       const long long t0 = sell_total * wid / nwarp, t1 = sell_total * (wid + 1) / nwarp;
@@ -713,16 +711,18 @@ k_cocg_small(SolveDev D, const int32_t *__restrict__ sell_ptr, const int32_t *__
         }
       }
       while (step < step_end) {
-        c128 a1[SPD];
-        int c1[SPD];
+        c128 a1[DB ? SPD : 1];
+        int c1[DB ? SPD : 1];
+        if (DB) {
 #pragma unroll
-        for (int u = 0; u < SPD; ++u) {
-          const int st = step + SPD + u;
-          a1[u] = cmake(0.0, 0.0);
-          c1[u] = 0;
-          if (st < step_end) {
-            a1[u] = ldg_stream(vp + (size_t)32 * st);
-            c1[u] = ldg_stream(cp + (size_t)32 * st);
+          for (int u = 0; u < SPD; ++u) {
+            const int st = step + SPD + u;
+            a1[DB ? u : 0] = cmake(0.0, 0.0);
+            c1[DB ? u : 0] = 0;
+            if (st < step_end) {
+              a1[DB ? u : 0] = ldg_stream(vp + (size_t)32 * st);
+              c1[DB ? u : 0] = ldg_stream(cp + (size_t)32 * st);
+            }
           }
         }
 #pragma unroll
@@ -734,12 +734,22 @@ k_cocg_small(SolveDev D, const int32_t *__restrict__ sell_ptr, const int32_t *__
             while (sl < s_hi && next_b == st + 1) flush();
           }
         }
+        step += SPD;
 #pragma unroll
         for (int u = 0; u < SPD; ++u) {
-          a0[u] = a1[u];
-          c0[u] = c1[u];
+          if (DB) {
+            a0[u] = a1[DB ? u : 0];
+            c0[u] = c1[DB ? u : 0];
+          } else {
+            const int st = step + u;
+            a0[u] = cmake(0.0, 0.0);
+            c0[u] = 0;
+            if (st < step_end) {
+              a0[u] = ldg_stream(vp + (size_t)32 * st);
+              c0[u] = ldg_stream(cp + (size_t)32 * st);
+            }
+          }
         }
-        step += SPD;
       }
       while (sl < s_hi) flush();  // trailing empty slices
     };
@@ -1198,15 +1208,33 @@ static int run_cocg_small(SolvePlan &P, const efb_solve_opts *o, bool zero_x, bo
   }
   EFB_CUDA(c, cudaEventRecord(S->ev_s0, c->stream));
   const int grid = std::max(1, std::min(n_jobs, c->sm_count));
+  // kernel shape: threads per CTA, loads in flight per lane, register double buffering
+  int variant = 1;
+  if (const char *v = getenv("EDGEFEM_B200_SMALL_VARIANT")) variant = atoi(v);
+  const int mr = o->max_restarts > 0 ? o->max_restarts : 3;
+#define EFB_SMALL_LAUNCH(NRV, NT, SPDV, DBV)                                                                                              \
+  do {                                                                                                                                    \
+    EFB_CUDA(c, cudaFuncSetAttribute(k_cocg_small<NRV, NT, SPDV, DBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
+    k_cocg_small<NRV, NT, SPDV, DBV><<<grid, NT, smem, c->stream>>>(P.D, S->d_sell_ptr, S->d_sell_col, S->d_sell_perm, S->d_sell_vals,    \
+                                                                      S->sell_total, S->n_slices, P.first_matrix, n_jobs, groups, S->d_job, \
+                                                                      S->d_b, S->d_x, P.vec[V_R], P.vec[V_Q], P.aux ? 1 : 0, zero_x ? 1 : 0, mr); \
+  } while (0)
   if (nr == 2) {
-    EFB_CUDA(c, cudaFuncSetAttribute(k_cocg_small<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_cocg_small<2><<<grid, SMALL_THREADS, smem, c->stream>>>(P.D, S->d_sell_ptr, S->d_sell_col, S->d_sell_perm, S->d_sell_vals, S->sell_total, S->n_slices, P.first_matrix, n_jobs, groups, S->d_job, S->d_b, S->d_x, P.vec[V_R], P.vec[V_Q],
-                                                                P.aux ? 1 : 0, zero_x ? 1 : 0, o->max_restarts > 0 ? o->max_restarts : 3);
+    switch (variant) {
+      case 0: EFB_SMALL_LAUNCH(2, 512, 8, true); break;
+      case 2: EFB_SMALL_LAUNCH(2, 768, 4, true); break;
+      case 3: EFB_SMALL_LAUNCH(2, 1024, 2, true); break;
+      default: EFB_SMALL_LAUNCH(2, 1024, 4, false); break;
+    }
   } else {
-    EFB_CUDA(c, cudaFuncSetAttribute(k_cocg_small<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_cocg_small<1><<<grid, SMALL_THREADS, smem, c->stream>>>(P.D, S->d_sell_ptr, S->d_sell_col, S->d_sell_perm, S->d_sell_vals, S->sell_total, S->n_slices, P.first_matrix, n_jobs, groups, S->d_job, S->d_b, S->d_x, P.vec[V_R], P.vec[V_Q],
-                                                                P.aux ? 1 : 0, zero_x ? 1 : 0, o->max_restarts > 0 ? o->max_restarts : 3);
+    switch (variant) {
+      case 0: EFB_SMALL_LAUNCH(1, 512, 8, true); break;
+      case 2: EFB_SMALL_LAUNCH(1, 768, 4, true); break;
+      case 3: EFB_SMALL_LAUNCH(1, 1024, 2, true); break;
+      default: EFB_SMALL_LAUNCH(1, 1024, 4, false); break;
+    }
   }
+#undef EFB_SMALL_LAUNCH
   EFB_CHECK_LAUNCH(c);
   EFB_CUDA(c, cudaEventRecord(S->ev_s1, c->stream));
   S->small_timed = true;
