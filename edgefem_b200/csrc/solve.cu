@@ -664,7 +664,52 @@ k_cocg_small(SolveDev D, const int32_t *__restrict__ sell_ptr, const int32_t *__
       s_lo = lower(t0);
       s_hi = (wid == nwarp - 1) ? n_slices : lower(t1);
     }
-    auto spmv = [&](bool want_dot, double (&dots)[2 * NR]) {
+    // per-slice variant (SPD == 0): slices dealt round-robin to the warps, batches of 4 independent loads
+    auto spmv_slices = [&](bool want_dot, double (&dots)[2 * NR]) {
+#pragma unroll
+      for (int k = 0; k < 2 * NR; ++k) dots[k] = 0.0;
+      for (int sl = wid; sl < n_slices; sl += nwarp) {
+        const int base = __ldg(&sell_ptr[sl]);
+        const int width = (__ldg(&sell_ptr[sl + 1]) - base) >> 5;
+        const int row = __ldg(&sell_perm[sl * 32 + lane]);
+        const c128 *vp = sv + base + lane;
+        const int32_t *cp = sell_col + base + lane;
+        c128 acc[NR];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) acc[r] = cmake(0.0, 0.0);
+        int j = 0;
+        for (; j + 4 <= width; j += 4) {
+          c128 a4[4];
+          int c4[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            a4[u] = ldg_stream(vp + 32 * (j + u));
+            c4[u] = ldg_stream(cp + 32 * (j + u));
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int r = 0; r < NR; ++r) acc[r] = cfma(a4[u], p_s[(size_t)r * m + c4[u]], acc[r]);
+        }
+        for (; j < width; ++j) {
+          const c128 a = ldg_stream(vp + 32 * j);
+          const int c = ldg_stream(cp + 32 * j);
+#pragma unroll
+          for (int r = 0; r < NR; ++r) acc[r] = cfma(a, p_s[(size_t)r * m + c], acc[r]);
+        }
+        if (row >= 0) {
+#pragma unroll
+          for (int r = 0; r < NR; ++r) {
+            qg[r][row] = acc[r];
+            if (want_dot) {
+              const c128 t = cmul(p_s[(size_t)r * m + row], acc[r]);
+              dots[2 * r] += t.x; dots[2 * r + 1] += t.y;
+            }
+          }
+        }
+      }
+    };
+    auto spmv_flat = [&](bool want_dot, double (&dots)[2 * NR]) {
 #pragma unroll
       for (int k = 0; k < 2 * NR; ++k) dots[k] = 0.0;
       if (s_lo >= s_hi) return;
@@ -698,8 +743,9 @@ k_cocg_small(SolveDev D, const int32_t *__restrict__ sell_ptr, const int32_t *__
         }
       };
       while (sl < s_hi && next_b == step) flush();  // leading empty slices (rows without entries)
-      c128 a0[SPD];
-      int c0[SPD];
+      constexpr int SPDX = SPD > 0 ? SPD : 1;
+      c128 a0[SPDX];
+      int c0[SPDX];
 #pragma unroll
       for (int u = 0; u < SPD; ++u) {
         const int st = step + u;
@@ -711,8 +757,8 @@ k_cocg_small(SolveDev D, const int32_t *__restrict__ sell_ptr, const int32_t *__
         }
       }
       while (step < step_end) {
-        c128 a1[DB ? SPD : 1];
-        int c1[DB ? SPD : 1];
+        c128 a1[DB ? SPDX : 1];
+        int c1[DB ? SPDX : 1];
         if (DB) {
 #pragma unroll
           for (int u = 0; u < SPD; ++u) {
@@ -752,6 +798,11 @@ k_cocg_small(SolveDev D, const int32_t *__restrict__ sell_ptr, const int32_t *__
         }
       }
       while (sl < s_hi) flush();  // trailing empty slices
+    };
+
+    auto spmv = [&](bool want_dot, double (&dots)[2 * NR]) {
+      if (SPD == 0) spmv_slices(want_dot, dots);
+      else spmv_flat(want_dot, dots);
     };
 
     for (int cycle = 0;; ++cycle) {
@@ -1222,14 +1273,14 @@ static int run_cocg_small(SolvePlan &P, const efb_solve_opts *o, bool zero_x, bo
   if (nr == 2) {
     switch (variant) {
       case 0: EFB_SMALL_LAUNCH(2, 512, 8, true); break;
-      case 2: EFB_SMALL_LAUNCH(2, 768, 4, true); break;
+      case 2: EFB_SMALL_LAUNCH(2, 1024, 0, false); break;
       case 3: EFB_SMALL_LAUNCH(2, 1024, 2, true); break;
       default: EFB_SMALL_LAUNCH(2, 1024, 4, false); break;
     }
   } else {
     switch (variant) {
       case 0: EFB_SMALL_LAUNCH(1, 512, 8, true); break;
-      case 2: EFB_SMALL_LAUNCH(1, 768, 4, true); break;
+      case 2: EFB_SMALL_LAUNCH(1, 1024, 0, false); break;
       case 3: EFB_SMALL_LAUNCH(1, 1024, 2, true); break;
       default: EFB_SMALL_LAUNCH(1, 1024, 4, false); break;
     }
