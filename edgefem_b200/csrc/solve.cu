@@ -630,19 +630,24 @@ k_cocg_small(SolveDev D, const int32_t *__restrict__ sell_ptr, const int32_t *__
     const c128 *__restrict__ av = D.vals + (size_t)f * D.nnz;
     const c128 *__restrict__ dinv = D.dinv + (size_t)f * m;
     const c128 *__restrict__ linv = D.linv + (size_t)f * (aux ? D.n_node : 0);
-    c128 *xg[NR], *rg[NR], *qg[NR];
-    const c128 *bg[NR];
-#pragma unroll
-    for (int r = 0; r < NR; ++r) {
-      const size_t off = (size_t)(s0 + r) * m;
-      xg[r] = xvec + off; rg[r] = rvec + off; qg[r] = qvec + off; bg[r] = bvec + off;
-    }
-    double bb[NR], rr[NR];
-    c128 rho[NR];
+    // per-rhs vectors are addressed as base + r*m (one base pointer per vector instead of NR pointers)
+    struct VRef {
+      c128 *base;
+      int m;
+      __device__ __forceinline__ c128 *operator[](int r) const { return base + (size_t)r * m; }
+    };
+    const size_t off0 = (size_t)s0 * m;
+    const VRef xg{xvec + off0, m}, rg{rvec + off0, m}, qg{qvec + off0, m}, bg{const_cast<c128 *>(bvec) + off0, m};
+    // block-uniform scalars live in shared memory (written by thread 0 between barriers): bb, rr and a
+    // double-buffered rho per right-hand side
+    double *sc_bb = red + 33 * 8, *sc_rr = sc_bb + NR, *sc_rho = sc_rr + NR;  // sc_rho[parity][r][2]
+    int par = 0;
     int iters[NR];
     bool act[NR], conv[NR];
 #pragma unroll
-    for (int r = 0; r < NR; ++r) { iters[r] = 0; act[r] = false; conv[r] = false; bb[r] = 0.0; rr[r] = 0.0; rho[r] = cmake(0.0, 0.0); }
+    for (int r = 0; r < NR; ++r) { iters[r] = 0; act[r] = false; conv[r] = false; }
+    if (tid < 8 * NR) sc_bb[tid] = 0.0;
+    __syncthreads();
 
     // q = A * (vector in p_s), optional dot p.q.  SELL-32: a lane owns a row, 32 rows form a slice stored
     // column-major.  A warp owns a CONTIGUOUS range of slices (balanced by entry count), so its values and
@@ -835,11 +840,13 @@ k_cocg_small(SolveDev D, const int32_t *__restrict__ sell_ptr, const int32_t *__
       bool any = false;
 #pragma unroll
       for (int r = 0; r < NR; ++r) {
-        rr[r] = d4[2 * r]; bb[r] = d4[2 * r + 1];
-        conv[r] = (rr[r] <= D.tol2 * bb[r]);
-        act[r] = !conv[r] && iters[r] < D.max_it && cycle <= max_restarts && isfinite(rr[r]);
+        const double rr_r = d4[2 * r], bb_r = d4[2 * r + 1];
+        if (tid == 0) { sc_rr[r] = rr_r; sc_bb[r] = bb_r; }
+        conv[r] = (rr_r <= D.tol2 * bb_r);
+        act[r] = !conv[r] && iters[r] < D.max_it && cycle <= max_restarts && isfinite(rr_r);
         any |= act[r];
       }
+      __syncthreads();
       if (!any) break;
 
       // (2)+(3) preconditioned COCG until the recursive residual converges.  Two block reductions per
@@ -907,14 +914,20 @@ k_cocg_small(SolveDev D, const int32_t *__restrict__ sell_ptr, const int32_t *__
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
           const c128 rho_new = cmake(dz[3 * r], dz[3 * r + 1]);
-          beta[r] = (fresh || (rho[r].x == 0.0 && rho[r].y == 0.0)) ? cmake(0.0, 0.0) : cdiv(rho_new, rho[r]);
-          rho[r] = rho_new;
+          const c128 rho_old = cmake(sc_rho[(par * NR + r) * 2], sc_rho[(par * NR + r) * 2 + 1]);
+          beta[r] = (fresh || (rho_old.x == 0.0 && rho_old.y == 0.0)) ? cmake(0.0, 0.0) : cdiv(rho_new, rho_old);
+          if (tid == 0) {
+            sc_rho[((par ^ 1) * NR + r) * 2] = rho_new.x;
+            sc_rho[((par ^ 1) * NR + r) * 2 + 1] = rho_new.y;
+          }
           if (act[r]) {
-            rr[r] = dz[3 * r + 2];
-            if (rr[r] <= D.tol2 * bb[r] || iters[r] >= D.max_it || !isfinite(rr[r])) act[r] = false;
+            const double rr_r = dz[3 * r + 2];
+            if (tid == 0) sc_rr[r] = rr_r;
+            if (rr_r <= D.tol2 * sc_bb[r] || iters[r] >= D.max_it || !isfinite(rr_r)) act[r] = false;
           }
           still |= act[r];
         }
+        par ^= 1;
         if (!still) break;
         for (int e = tid; e < m; e += nth)
 #pragma unroll
@@ -934,7 +947,8 @@ k_cocg_small(SolveDev D, const int32_t *__restrict__ sell_ptr, const int32_t *__
           const c128 pq = cmake(dq[2 * r], dq[2 * r + 1]);
           const bool brk = (pq.x == 0.0 && pq.y == 0.0) || !(isfinite(pq.x) && isfinite(pq.y));
           if (brk) act[r] = false;
-          alpha[r] = act[r] ? cdiv(rho[r], pq) : cmake(0.0, 0.0);
+          const c128 rho_r = cmake(sc_rho[(par * NR + r) * 2], sc_rho[(par * NR + r) * 2 + 1]);
+          alpha[r] = act[r] ? cdiv(rho_r, pq) : cmake(0.0, 0.0);
           if (act[r]) iters[r] += 1;
         }
         // x += alpha p ; r -= alpha q   (|r|^2 is accumulated by the next preconditioner pass)
@@ -958,8 +972,8 @@ k_cocg_small(SolveDev D, const int32_t *__restrict__ sell_ptr, const int32_t *__
         int32_t *st = D.state + (s0 + r) * 4;
         st[ST_ACTIVE] = 0; st[ST_ITERS] = iters[r]; st[ST_CONV] = conv[r] ? 1 : 0; st[ST_REC] = 0;
         c128 *sc = scal_of(D, s0 + r);
-        sc[S_RR] = cmake(rr[r], 0.0);
-        sc[S_BB] = cmake(bb[r], 0.0);
+        sc[S_RR] = cmake(sc_rr[r], 0.0);
+        sc[S_BB] = cmake(sc_bb[r], 0.0);
       }
     }
     __syncthreads();
@@ -986,7 +1000,7 @@ __global__ void k_csr_to_sell(const c128 *__restrict__ vals, long long nnz, cons
   }
 }
 
-static size_t small_smem_bytes(int nr, int m, int nn) { return ((size_t)nr * m + (size_t)nr * nn) * sizeof(c128) + 33 * 8 * sizeof(double) + 64; }
+static size_t small_smem_bytes(int nr, int m, int nn) { return ((size_t)nr * m + (size_t)nr * nn) * sizeof(c128) + (33 * 8 + 8 * nr) * sizeof(double) + 64; }
 
 // FP64 FMA throughput probe (roofline denominator for the assembly kernel; MEASURED_PEAKS.json has
 // no FP64 figure): 8 independent chains x FP64_PROBE_ITERS FMAs per thread.
