@@ -6,8 +6,11 @@
 #include <stdarg.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <mutex>
 #include <thread>
+#include <unordered_map>
 
 #include "common.cuh"
 
@@ -32,10 +35,98 @@ int fail(Ctx *ctx, int code, const char *fmt, ...) {
   return code;
 }
 
+// ---------------------------------------------------------------- caching device allocator
+namespace {
+struct PoolBlock {
+  void *p;
+  size_t bytes;
+};
+std::mutex g_pool_mu;
+std::unordered_map<void *, std::pair<int, size_t>> g_live;       // every dev_alloc'ed pointer -> (device, bytes)
+std::unordered_map<int, std::vector<PoolBlock>> g_free;          // cached blocks per device
+std::unordered_map<int, size_t> g_free_bytes;
+constexpr size_t POOL_MIN_BLOCK = 1 << 20;                       // smaller requests are rounded up to a power of two
+constexpr size_t POOL_MAX_BLOCKS = 4096;                         // cap of cached blocks per device
+constexpr size_t POOL_MAX_BYTES = 16ull << 30;                   // cap of cached bytes per device
+}  // namespace
+
+size_t pool_round(size_t bytes) {
+  if (bytes >= POOL_MIN_BLOCK) return bytes;
+  size_t r = 512;
+  while (r < bytes) r <<= 1;
+  return r;
+}
+
+void *pool_get(int device, size_t bytes) {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  auto &fl = g_free[device];
+  // small requests were rounded up to a power of two by pool_round(); large ones accept up to 25% + 1 MiB of slack
+  const size_t hi = bytes < POOL_MIN_BLOCK ? bytes : bytes + bytes / 4 + (1 << 20);
+  int best = -1;
+  for (int i = 0; i < (int)fl.size(); ++i)
+    if (fl[i].bytes >= bytes && fl[i].bytes <= hi && (best < 0 || fl[i].bytes < fl[best].bytes)) best = i;
+  if (best < 0) return nullptr;
+  void *p = fl[best].p;
+  g_free_bytes[device] -= fl[best].bytes;
+  g_live[p] = {device, fl[best].bytes};
+  fl.erase(fl.begin() + best);
+  return p;
+}
+
+void pool_register(void *p, int device, size_t bytes) {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  g_live[p] = {device, bytes};
+}
+
+void dfree(void *p) {
+  if (!p) return;
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    auto it = g_live.find(p);
+    if (it != g_live.end()) {
+      const int device = it->second.first;
+      const size_t bytes = it->second.second;
+      g_live.erase(it);
+      if (g_free_bytes[device] + bytes <= POOL_MAX_BYTES && g_free[device].size() < POOL_MAX_BLOCKS) {
+        g_free[device].push_back({p, bytes});
+        g_free_bytes[device] += bytes;
+        return;
+      }
+    }
+  }
+  cudaFree(p);
+}
+
+void pool_trim() {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  for (auto &kv : g_free) {
+    for (auto &b : kv.second) cudaFree(b.p);
+    kv.second.clear();
+    g_free_bytes[kv.first] = 0;
+  }
+}
+
+// EDGEFEM_B200_TRACE=2: host-side stage times of system creation on stderr
+struct SubTrace {
+  bool on;
+  std::chrono::steady_clock::time_point t;
+  SubTrace() : on(false) {
+    const char *e = getenv("EDGEFEM_B200_TRACE");
+    on = e && atoi(e) >= 2;
+    t = std::chrono::steady_clock::now();
+  }
+  void mark(const char *what) {
+    if (!on) return;
+    auto n = std::chrono::steady_clock::now();
+    fprintf(stderr, "[edgefem-b200 trace]     . %s: %.3f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+    t = n;
+  }
+};
+
 template <typename F>
 static void parallel_for(int64_t n, F f) {
   unsigned hw = std::thread::hardware_concurrency();
-  int nt = (int)std::min<int64_t>(std::max(1u, std::min(hw, 32u)), std::max<int64_t>(1, n / 4096));
+  int nt = (int)std::min<int64_t>(std::max(1u, std::min(hw, 32u)), std::max<int64_t>(1, n / 512));
   if (nt <= 1) {
     f(0, n);
     return;
@@ -175,6 +266,7 @@ void efb_ctx_destroy(efb_ctx *ctx_) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  pool_trim();
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->tm0) cudaEventDestroy(c->tm0);
@@ -305,7 +397,7 @@ int efb_mesh_create(efb_ctx *ctx_, const efb_mesh_desc *d, efb_mesh **out) {
     k_bbox_decode<<<(M->n_slots * 6 + 63) / 64, 64, 0, c->stream>>>(enc, M->d_slot_bbox, M->n_slots * 6);
     EFB_CHECK_LAUNCH(c);
     EFB_CUDA(c, cudaStreamSynchronize(c->stream));
-    cudaFree(enc);
+    dfree(enc);
   }
   EFB_CUDA(c, cudaStreamSynchronize(c->stream));
   *out = (efb_mesh *)M;
@@ -316,8 +408,9 @@ void efb_mesh_destroy(efb_mesh *mesh_) {
   Mesh *M = (Mesh *)mesh_;
   if (!M) return;
   cudaSetDevice(M->ctx->device);
-  cudaFree(M->d_xyz); cudaFree(M->d_tet_nodes); cudaFree(M->d_tet_sign); cudaFree(M->d_tet_slot);
-  cudaFree(M->d_e2t_ptr); cudaFree(M->d_e2t_item); cudaFree(M->d_slot_bbox); cudaFree(M->d_geom);
+  cudaStreamSynchronize(M->ctx->stream);  // pooled blocks may be handed out again immediately
+  dfree(M->d_xyz); dfree(M->d_tet_nodes); dfree(M->d_tet_sign); dfree(M->d_tet_slot);
+  dfree(M->d_e2t_ptr); dfree(M->d_e2t_item); dfree(M->d_slot_bbox); dfree(M->d_geom);
   delete M;
 }
 
@@ -412,7 +505,8 @@ static int system_set_gradient(System *S, int n_node, const int32_t *edge_nodes)
   Ctx *c = S->ctx;
   int rc;
   S->n_node = n_node;
-  cudaFree(S->d_edge_nodes); cudaFree(S->d_n2e_ptr); cudaFree(S->d_n2e_item); cudaFree(S->d_node_dir);
+  cudaStreamSynchronize(c->stream);  // blocks go back to a pool shared by every context on the device
+  dfree(S->d_edge_nodes); dfree(S->d_n2e_ptr); dfree(S->d_n2e_item); dfree(S->d_node_dir);
   S->d_edge_nodes = nullptr; S->d_n2e_ptr = nullptr; S->d_n2e_item = nullptr; S->d_node_dir = nullptr;
   for (int64_t i = 0; i < 2 * (int64_t)S->m; ++i)
     if (edge_nodes[i] < 0 || edge_nodes[i] >= n_node) return fail(c, EFB_ERR_INVALID, "edge_nodes[%lld] out of range", (long long)i);
@@ -448,6 +542,7 @@ int efb_system_create(efb_mesh *mesh_, int64_t n_extra, const int32_t *extra_row
   for (int64_t i = 0; i < n_extra; ++i)
     if (extra_rows[i] < 0 || extra_rows[i] >= m || extra_cols[i] < 0 || extra_cols[i] >= m)
       return fail(c, EFB_ERR_INVALID, "efb_system_create: extra entry %lld out of range", (long long)i);
+  SubTrace st;
   System *S = new System();
   S->ctx = c;
   S->mesh = M;
@@ -476,12 +571,31 @@ int efb_system_create(efb_mesh *mesh_, int64_t n_extra, const int32_t *extra_row
     std::sort(buf.begin(), buf.end());
     buf.erase(std::unique(buf.begin(), buf.end()), buf.end());
   };
+  // one pass: every worker builds the sorted column lists of its row range into a private buffer and fills the
+  // tet-local -> row-local position map; the buffers are then concatenated at the row offsets
   std::vector<int32_t> rowlen(m);
+  std::vector<uint16_t> pos((size_t)M->h_e2t_item.size() * 6);
+  struct RangeCols {
+    int64_t a = 0, b = 0;
+    std::vector<int32_t> cols;
+  };
+  std::vector<RangeCols> ranges(64);
+  std::atomic<int> n_ranges{0};
   parallel_for(m, [&](int64_t a, int64_t b) {
+    RangeCols &rc_ = ranges[n_ranges.fetch_add(1)];
+    rc_.a = a;
+    rc_.b = b;
+    rc_.cols.reserve((size_t)(b - a) * 20);
     std::vector<int32_t> buf;
     for (int64_t r = a; r < b; ++r) {
       row_cols((int)r, buf);
       rowlen[r] = (int32_t)buf.size();
+      rc_.cols.insert(rc_.cols.end(), buf.begin(), buf.end());
+      for (int32_t k = M->h_e2t_ptr[r]; k < M->h_e2t_ptr[r + 1]; ++k) {
+        const int32_t *e6 = te + 6 * (int64_t)(M->h_e2t_item[k] >> 3);
+        for (int j = 0; j < 6; ++j)
+          pos[(size_t)k * 6 + j] = (uint16_t)(std::lower_bound(buf.begin(), buf.end(), e6[j]) - buf.begin());
+      }
     }
   });
   int64_t nnz = 0;
@@ -498,23 +612,20 @@ int efb_system_create(efb_mesh *mesh_, int64_t n_extra, const int32_t *extra_row
     delete S;
     return fail(c, EFB_ERR_LIMIT, "efb_system_create: a row has %d entries (limit %d)", maxrow, std::min(ASM_CHUNK_NNZ, 32767));
   }
+  st.mark("row column lists + pos map");
   S->nnz = nnz;
   for (int r = 0; r < m; ++r) S->h_rowptr[r + 1] = S->h_rowptr[r] + rowlen[r];
   S->h_colidx.resize((size_t)nnz);
-  std::vector<uint16_t> pos((size_t)M->h_e2t_item.size() * 6);
-  parallel_for(m, [&](int64_t a, int64_t b) {
-    std::vector<int32_t> buf;
-    for (int64_t r = a; r < b; ++r) {
-      row_cols((int)r, buf);
-      int32_t *dst = S->h_colidx.data() + S->h_rowptr[r];
-      std::copy(buf.begin(), buf.end(), dst);
-      for (int32_t k = M->h_e2t_ptr[r]; k < M->h_e2t_ptr[r + 1]; ++k) {
-        const int32_t *e6 = te + 6 * (int64_t)(M->h_e2t_item[k] >> 3);
-        for (int j = 0; j < 6; ++j)
-          pos[(size_t)k * 6 + j] = (uint16_t)(std::lower_bound(buf.begin(), buf.end(), e6[j]) - buf.begin());
-      }
+  {
+    const int nr = n_ranges.load();
+    std::vector<std::thread> th;
+    for (int i = 0; i < nr; ++i) {
+      auto cp = [&, i] { std::copy(ranges[i].cols.begin(), ranges[i].cols.end(), S->h_colidx.data() + S->h_rowptr[ranges[i].a]); };
+      if (nr > 1 && ranges[i].cols.size() > (1u << 20)) th.emplace_back(cp); else cp();
     }
-  });
+    for (auto &x : th) x.join();
+  }
+  st.mark("concatenate");
   // assembly chunks: consecutive rows with <= ASM_CHUNK_NNZ entries and <= ASM_CHUNK_ROWS rows
   std::vector<int32_t> chunk{0};
   {
@@ -534,11 +645,13 @@ int efb_system_create(efb_mesh *mesh_, int64_t n_extra, const int32_t *extra_row
   S->n_chunks = (int)chunk.size() - 1;
   int rc;
   if ((rc = system_alloc_common(S))) return rc;
+  st.mark("diag/SELL/stream structures + device buffers");
   if ((rc = dev_upload(c, &S->d_e2t_pos, pos.data(), pos.size()))) return rc;
   if ((rc = dev_upload(c, &S->d_chunk_row, chunk.data(), chunk.size()))) return rc;
 
   if ((rc = system_set_gradient(S, M->n_node, M->h_edge_nodes.data()))) return rc;
   EFB_CUDA(c, cudaStreamSynchronize(c->stream));
+  st.mark("gradient lists + sync");
   *out = (efb_system *)S;
   return EFB_OK;
 }
@@ -584,11 +697,11 @@ void efb_system_destroy(efb_system *sys_) {
   cudaSetDevice(S->ctx->device);
   cudaStreamSynchronize(S->ctx->stream);
   solver_free(S);
-  cudaFree(S->d_rowptr); cudaFree(S->d_colidx); cudaFree(S->d_diag_pos); cudaFree(S->d_vals);
-  cudaFree(S->d_b); cudaFree(S->d_x); cudaFree(S->d_dir); cudaFree(S->d_e2t_pos); cudaFree(S->d_chunk_row); cudaFree(S->d_sp_chunk);
-  cudaFree(S->d_sell_ptr); cudaFree(S->d_sell_col); cudaFree(S->d_sell_perm); cudaFree(S->d_sell_vals);
-  cudaFree(S->d_edge_nodes); cudaFree(S->d_n2e_ptr); cudaFree(S->d_n2e_item); cudaFree(S->d_node_dir);
-  cudaFree(S->d_mat_blob);
+  dfree(S->d_rowptr); dfree(S->d_colidx); dfree(S->d_diag_pos); dfree(S->d_vals);
+  dfree(S->d_b); dfree(S->d_x); dfree(S->d_dir); dfree(S->d_e2t_pos); dfree(S->d_chunk_row); dfree(S->d_sp_chunk);
+  dfree(S->d_sell_ptr); dfree(S->d_sell_col); dfree(S->d_sell_perm); dfree(S->d_sell_vals);
+  dfree(S->d_edge_nodes); dfree(S->d_n2e_ptr); dfree(S->d_n2e_item); dfree(S->d_node_dir);
+  dfree(S->d_mat_blob);
   delete S;
 }
 

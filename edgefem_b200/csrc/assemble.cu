@@ -304,7 +304,8 @@ int assemble_launch(System *S, int first, int count, int mode) {
   const size_t total = S->last_mat_blob.size();
   const size_t off_om = total - (size_t)count * sizeof(double);
   if (S->mat_blob_bytes < total) {
-    cudaFree(S->d_mat_blob);
+    cudaStreamSynchronize(c->stream);
+    dfree(S->d_mat_blob);
     S->d_mat_blob = nullptr;
     unsigned char *p = nullptr;
     int rc = dev_alloc(c, &p, total);
@@ -540,9 +541,21 @@ static int check_flag(System *S, const char *who) {
 }
 
 // uploads `n` c128 to a temporary device buffer
-struct TmpBuf {
+struct TmpBuf {  // per-call scratch from the caching allocator; the kernels reading it have finished when it goes back
   void *p = nullptr;
-  ~TmpBuf() { cudaFree(p); }
+  Ctx *c = nullptr;
+  int alloc(Ctx *ctx, size_t bytes) {
+    c = ctx;
+    unsigned char *q = nullptr;
+    int rc = dev_alloc(ctx, &q, bytes);
+    p = q;
+    return rc;
+  }
+  ~TmpBuf() {
+    if (!p) return;
+    cudaStreamSynchronize(c->stream);
+    dfree(p);
+  }
 };
 
 }  // namespace efb
@@ -598,7 +611,7 @@ int efb_combine_km(efb_system *sys_, int32_t dst_first, int32_t count, const dou
     return fail(c, EFB_ERR_INVALID, "efb_combine_km: bad arguments (sources must lie outside the destination range)");
   EFB_CUDA(c, cudaSetDevice(c->device));
   TmpBuf tb;
-  EFB_CUDA(c, cudaMalloc(&tb.p, (size_t)count * sizeof(double)));
+  if (int rc_ = tb.alloc(c, (size_t)count * sizeof(double))) return rc_;
   EFB_CUDA(c, cudaMemcpyAsync(tb.p, k0sq, (size_t)count * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   {
     Timed tm(c);
@@ -622,8 +635,8 @@ int efb_add_diag(efb_system *sys_, int32_t first, int32_t count, int32_t n, cons
     if (edges[k] < 0 || edges[k] >= S->m) return fail(c, EFB_ERR_INVALID, "efb_add_diag: edge out of range");
   EFB_CUDA(c, cudaSetDevice(c->device));
   TmpBuf te, tc;
-  EFB_CUDA(c, cudaMalloc(&te.p, (size_t)n * sizeof(int32_t)));
-  EFB_CUDA(c, cudaMalloc(&tc.p, (size_t)count * sizeof(c128)));
+  if (int rc_ = te.alloc(c, (size_t)n * sizeof(int32_t))) return rc_;
+  if (int rc_ = tc.alloc(c, (size_t)count * sizeof(c128))) return rc_;
   EFB_CUDA(c, cudaMemcpyAsync(te.p, edges, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
   EFB_CUDA(c, cudaMemcpyAsync(tc.p, coef, (size_t)count * sizeof(c128), cudaMemcpyHostToDevice, c->stream));
   dim3 grid((unsigned)((n + 127) / 128), (unsigned)count);
@@ -676,8 +689,8 @@ void efb_port_destroy(efb_port *port_) {
   Port *P = (Port *)port_;
   if (!P) return;
   cudaSetDevice(P->sys->ctx->device);
-  cudaFree(P->d_edges); cudaFree(P->d_w); cudaFree(P->d_ms_row); cudaFree(P->d_ms_col); cudaFree(P->d_ms_pos);
-  cudaFree(P->d_ms_val); cudaFree(P->d_e); cudaFree(P->d_tmp); cudaFree(P->d_blk_pos);
+  dfree(P->d_edges); dfree(P->d_w); dfree(P->d_ms_row); dfree(P->d_ms_col); dfree(P->d_ms_pos);
+  dfree(P->d_ms_val); dfree(P->d_e); dfree(P->d_tmp); dfree(P->d_blk_pos);
   delete P;
 }
 
@@ -699,7 +712,7 @@ int efb_port_normalize_mass(efb_port *port_, double *norm_sq) {
 }
 
 static int upload_coef(Ctx *c, TmpBuf &tb, const double *coef, int count) {
-  EFB_CUDA(c, cudaMalloc(&tb.p, (size_t)count * sizeof(c128)));
+  if (int rc_ = tb.alloc(c, (size_t)count * sizeof(c128))) return rc_;
   EFB_CUDA(c, cudaMemcpyAsync(tb.p, coef, (size_t)count * sizeof(c128), cudaMemcpyHostToDevice, c->stream));
   return EFB_OK;
 }
@@ -804,8 +817,8 @@ int efb_port_rhs_batch(efb_system *sys_, efb_port *port_, int32_t count, const i
   Ctx *c = S->ctx;
   EFB_CUDA(c, cudaSetDevice(c->device));
   TmpBuf ti, tc;
-  EFB_CUDA(c, cudaMalloc(&ti.p, (size_t)count * 4));
-  EFB_CUDA(c, cudaMalloc(&tc.p, (size_t)count * 16));
+  if (int rc_ = ti.alloc(c, (size_t)count * 4)) return rc_;
+  if (int rc_ = tc.alloc(c, (size_t)count * 16)) return rc_;
   EFB_CUDA(c, cudaMemcpyAsync(ti.p, rhs_idx, (size_t)count * 4, cudaMemcpyHostToDevice, c->stream));
   EFB_CUDA(c, cudaMemcpyAsync(tc.p, coef, (size_t)count * 16, cudaMemcpyHostToDevice, c->stream));
   if (use_mass) {
@@ -832,8 +845,8 @@ int efb_port_project_batch(efb_system *sys_, efb_port *port_, int32_t count, con
   Ctx *c = S->ctx;
   EFB_CUDA(c, cudaSetDevice(c->device));
   TmpBuf ti, to;
-  EFB_CUDA(c, cudaMalloc(&ti.p, (size_t)count * 4));
-  EFB_CUDA(c, cudaMalloc(&to.p, (size_t)count * 16));
+  if (int rc_ = ti.alloc(c, (size_t)count * 4)) return rc_;
+  if (int rc_ = to.alloc(c, (size_t)count * 16)) return rc_;
   EFB_CUDA(c, cudaMemcpyAsync(ti.p, rhs_idx, (size_t)count * 4, cudaMemcpyHostToDevice, c->stream));
   k_project_batch<<<(unsigned)count, 128, 0, c->stream>>>(S->d_x, S->m, (const int32_t *)ti.p, (c128 *)to.p, use_mass, P->d_edges, P->d_w, P->n_edges,
                                                           S->d_dir, P->d_e, P->d_ms_row, P->d_ms_col, P->d_ms_val, (long long)P->n_ms);
@@ -853,9 +866,9 @@ int efb_x_recover(efb_system *sys_, int32_t rhs, int32_t n, const int32_t *dst, 
     if (dst[k] < 0 || dst[k] >= S->m || src[k] < 0 || src[k] >= S->m) return fail(c, EFB_ERR_INVALID, "efb_x_recover: index out of range");
   EFB_CUDA(c, cudaSetDevice(c->device));
   TmpBuf td, ts, tp;
-  EFB_CUDA(c, cudaMalloc(&td.p, (size_t)n * 4));
-  EFB_CUDA(c, cudaMalloc(&ts.p, (size_t)n * 4));
-  EFB_CUDA(c, cudaMalloc(&tp.p, (size_t)n * 16));
+  if (int rc_ = td.alloc(c, (size_t)n * 4)) return rc_;
+  if (int rc_ = ts.alloc(c, (size_t)n * 4)) return rc_;
+  if (int rc_ = tp.alloc(c, (size_t)n * 16)) return rc_;
   EFB_CUDA(c, cudaMemcpyAsync(td.p, dst, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
   EFB_CUDA(c, cudaMemcpyAsync(ts.p, src, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
   EFB_CUDA(c, cudaMemcpyAsync(tp.p, phase, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));

@@ -189,11 +189,31 @@ int fail(Ctx *ctx, int code, const char *fmt, ...);
                          cudaGetErrorString(_e), __FILE__, __LINE__);                    \
   } while (0)
 
+// Caching device allocator (per device): large buffers released by destroyed handles are kept and
+// handed to the next request of similar size, so repeated driver calls (one system per sweep call)
+// do not pay cudaMalloc/cudaFree -- which cost milliseconds and occasionally tens of milliseconds.
+size_t pool_round(size_t bytes);                   // allocation size for a request (small ones -> power of two)
+void *pool_get(int device, size_t bytes);          // nullptr if no cached block fits
+void pool_register(void *p, int device, size_t bytes);
+void dfree(void *p);                               // returns the block to the pool or cudaFree()s it
+void pool_trim();                                  // cudaFree every cached block
+
 template <typename T>
 int dev_alloc(Ctx *ctx, T **p, size_t n) {
   *p = nullptr;
   if (n == 0) n = 1;
-  cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
+  const size_t bytes = pool_round(n * sizeof(T));
+  if (void *q = pool_get(ctx->device, bytes)) {
+    *p = (T *)q;
+    return EFB_OK;
+  }
+  cudaError_t e = cudaMalloc((void **)p, bytes);
+  if (e == cudaErrorMemoryAllocation) {  // give cached blocks back to the driver and retry once
+    cudaGetLastError();
+    pool_trim();
+    e = cudaMalloc((void **)p, bytes);
+  }
+  if (e == cudaSuccess) pool_register(*p, ctx->device, bytes);
   if (e != cudaSuccess)
     return fail(ctx, e == cudaErrorMemoryAllocation ? EFB_ERR_NOMEM : EFB_ERR_CUDA,
                 "cudaMalloc(%zu bytes) failed: %s", n * sizeof(T), cudaGetErrorString(e));

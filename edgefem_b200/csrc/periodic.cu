@@ -180,7 +180,7 @@ int efb_apply_periodic(efb_system *sys_, int32_t first, int32_t count, int32_t n
   cudaError_t e = cudaStreamSynchronize(c->stream);
   int32_t h = 0;
   if (e == cudaSuccess) e = cudaMemcpy(&h, S->d_flag, sizeof h, cudaMemcpyDeviceToHost);
-  cudaFree(d_slave_of); cudaFree(d_master); cudaFree(d_slave); cudaFree(d_phase);
+  dfree(d_slave_of); dfree(d_master); dfree(d_slave); dfree(d_phase);
   if (e != cudaSuccess) return fail(c, EFB_ERR_CUDA, "efb_apply_periodic: %s", cudaGetErrorString(e));
   if (h) {
     cudaMemset(S->d_flag, 0, sizeof h);

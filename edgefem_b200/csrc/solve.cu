@@ -1036,8 +1036,8 @@ static int pick_lpr(const System *S) {
 }
 
 int solver_free(System *S) {
-  cudaFree(S->d_work); cudaFree(S->d_dinv); cudaFree(S->d_linv); cudaFree(S->d_w); cudaFree(S->d_scal);
-  cudaFree(S->d_partial); cudaFree(S->d_counter); cudaFree(S->d_state); cudaFree(S->d_flag); cudaFree(S->d_job);
+  dfree(S->d_work); dfree(S->d_dinv); dfree(S->d_linv); dfree(S->d_w); dfree(S->d_scal);
+  dfree(S->d_partial); dfree(S->d_counter); dfree(S->d_state); dfree(S->d_flag); dfree(S->d_job);
   if (S->ev_s0) cudaEventDestroy(S->ev_s0);
   if (S->ev_s1) cudaEventDestroy(S->ev_s1);
   S->ev_s0 = nullptr; S->ev_s1 = nullptr;
