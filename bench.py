@@ -265,6 +265,17 @@ def cube_extras(ctx, pe, n: int):
     return out
 
 
+def ncu_traffic(kernel: str, n_matrix: int):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of `kernel` from the committed `ncu --set full`
+    capture of this same command (profiles/ncu_traffic.json); None when no capture matches the workload size."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            rec = json.load(f)[kernel]
+        return float(rec["bytes_per_launch"]) if int(rec["matrices"]) == int(n_matrix) else None
+    except Exception:
+        return None
+
+
 def run_b200(a):
     import numpy as np
 
@@ -345,7 +356,7 @@ def run_b200(a):
         solve_bytes = float(sum(it_per_matrix)) * (nnz * 20.0 + 4.0 * m + P * 192.0 * m)
         roof = {"bound": "hbm", "kernel": "k_cocg_small<2> (persistent COCG + aux-space Jacobi, SELL-32 SpMV from smem-resident p; %d matrices x %d rhs in one launch)" % (F, P),
                 "achieved": solve_bytes / ms_kernel / 1e6, "peak": hbm_peak, "unit": "GB/s", "frac": solve_bytes / ms_kernel / 1e6 / hbm_peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": solve_bytes, "ms_per_launch": ms_kernel,
+                "traffic": ncu_traffic("k_cocg_small", F), "peak_source": peak_src, "algorithmic_bytes_per_launch": solve_bytes, "ms_per_launch": ms_kernel,
                 "launches_per_step": 1, "share_of_step": ms_kernel / ms_step,
                 "note": "vectors r,q,x stay L2-resident per CTA and p lives in shared memory, so part of the algorithmic bytes never reaches HBM"}
     else:  # multi-kernel path (EDGEFEM_B200_NO_PERSISTENT=1): batched CSR SpMV dominates
@@ -391,7 +402,7 @@ def run_b200(a):
         except Exception as e:  # extras never invalidate the headline number
             extras = {"error": repr(e)}
     cores = os.cpu_count() or 1
-    cpu1 = cpu_baseline(a.cpu_sample, 1)
+    cpu1 = cpu_baseline(a.cpu_sample, 1) if a.cpu_sample > 0 else None  # --cpu-sample 0: profiling runs skip the CPU leg
     line = {
         "metric": "wr90_sweep_freq_points_per_s", "value": value, "unit": "points/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",

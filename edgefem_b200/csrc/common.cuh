@@ -144,7 +144,9 @@ struct System {
   unsigned *d_counter = nullptr; // [n_sys]
   int32_t *d_state = nullptr;  // [n_sys][4]: active, iters, flag, pad
   int32_t *d_flag = nullptr;   // [1] device error flag (entry missing from the pattern)
-  int32_t *d_job = nullptr;    // [1] work-queue counter of the persistent small-system solver
+  int32_t *d_job = nullptr;    // [1 + n_sys] work-queue counter of the persistent small-system solver, then the job order
+  std::vector<int32_t> h_job_order;  // longest-expected-first order of the queue (kept alive for the async upload)
+  std::vector<int32_t> last_iters;   // iterations per system of the previous solve (best predictor of the next one)
   // last assembly inputs (for efb_bench_kernel which=3)
   std::vector<double> last_omega;
   bool assembled = false;

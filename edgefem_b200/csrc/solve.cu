@@ -605,8 +605,8 @@ __device__ __forceinline__ void block_allreduce(double (&v)[N], double *red /* s
   __syncthreads();
 }
 
-template <int NR, int NT, int SPD, bool DB>
-__global__ void __launch_bounds__(NT, 1)
+template <int NR, int NT, int SPD, bool DB, int MINB = 1>
+__global__ void __launch_bounds__(NT, MINB)
 k_cocg_small(SolveDev D, const int32_t *__restrict__ sell_ptr, const int32_t *__restrict__ sell_col, const int32_t *__restrict__ sell_perm,
              const c128 *__restrict__ sell_vals, long long sell_total, int n_slices, int first_matrix, int n_jobs, int groups_per_matrix,
              int *job_counter, const c128 *__restrict__ bvec, c128 *xvec, c128 *rvec, c128 *qvec, int aux, int zero_x, int max_restarts) {
@@ -620,7 +620,10 @@ k_cocg_small(SolveDev D, const int32_t *__restrict__ sell_ptr, const int32_t *__
   const int lane = tid & 31, wid = tid >> 5, nwarp = nth >> 5;
 
   for (;;) {
-    if (tid == 0) s_job = atomicAdd(job_counter, 1);
+    if (tid == 0) {
+      const int q = atomicAdd(job_counter, 1);
+      s_job = q < n_jobs ? job_counter[1 + q] : n_jobs;  // queue position -> job (longest expected first)
+    }
     __syncthreads();
     const int job = s_job;
     __syncthreads();
@@ -1057,7 +1060,7 @@ static int solver_alloc(System *S) {
     if ((rc = dev_alloc(c, &S->d_partial, (size_t)S->n_sys * RED_MAX_BLOCKS * 4))) return rc;
     if ((rc = dev_alloc(c, &S->d_counter, (size_t)S->n_sys))) return rc;
     if ((rc = dev_alloc(c, &S->d_state, (size_t)S->n_sys * 4))) return rc;
-    if ((rc = dev_alloc(c, &S->d_job, (size_t)1))) return rc;
+    if ((rc = dev_alloc(c, &S->d_job, (size_t)1 + S->n_sys))) return rc;
     EFB_CUDA(c, cudaMemsetAsync(S->d_counter, 0, (size_t)S->n_sys * sizeof(unsigned), c->stream));
     EFB_CUDA(c, cudaMemsetAsync(S->d_scal, 0, (size_t)S->n_sys * NSCAL * sizeof(c128), c->stream));
     EFB_CUDA(c, cudaMemsetAsync(S->d_state, 0, (size_t)S->n_sys * 4 * sizeof(int32_t), c->stream));
@@ -1251,8 +1254,11 @@ static int run_cocg_small(SolvePlan &P, const efb_solve_opts *o, bool zero_x, bo
   int dev_smem = 0;
   EFB_CUDA(c, cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
   const int nn = P.aux ? S->n_node : 0;
+  int variant = 1;
+  if (const char *v = getenv("EDGEFEM_B200_SMALL_VARIANT")) variant = atoi(v);
   int nr = (S->n_rhs % 2 == 0) ? 2 : 1;
   if (small_smem_bytes(nr, S->m, nn) > (size_t)dev_smem) nr = 1;
+  if (variant >= 4) nr = 1;  // one right-hand side per CTA, two CTAs per SM
   const size_t smem = small_smem_bytes(nr, S->m, nn);
   if (smem > (size_t)dev_smem || !S->d_sell_ptr) return EFB_OK;  // system too large for one CTA: generic multi-kernel path
   if (!S->d_sell_vals) {
@@ -1266,21 +1272,48 @@ static int run_cocg_small(SolvePlan &P, const efb_solve_opts *o, bool zero_x, bo
   }
   const int groups = S->n_rhs / nr;
   const int n_jobs = P.n_matrix * groups;
-  EFB_CUDA(c, cudaMemsetAsync(S->d_job, 0, sizeof(int32_t), c->stream));
+  {
+    // Queue order = longest expected job first (LPT list scheduling): with n_jobs between 1x and 2x the SM count the
+    // makespan is the sum of two jobs on one SM, so long jobs must start first and short ones fill in behind them.
+    // Predictor: iteration counts of the previous solve of this system if there was one, else the assembly frequency
+    // (the indefinite shift k0^2 M grows with frequency and so does the iteration count), else submission order.
+    std::vector<double> w((size_t)n_jobs, 0.0);
+    const bool have_it = (int)S->last_iters.size() == S->n_sys;
+    const bool have_om = (int)S->last_omega.size() == S->n_matrix;
+    for (int j = 0; j < n_jobs; ++j) {
+      const int f = P.first_matrix + j / groups, s0 = f * S->n_rhs + (j % groups) * nr;
+      if (have_it) {
+        for (int k = 0; k < nr; ++k) w[j] = std::max(w[j], (double)S->last_iters[s0 + k]);
+      } else if (have_om) {
+        w[j] = S->last_omega[f];
+      }
+    }
+    S->h_job_order.resize((size_t)n_jobs + 1);
+    S->h_job_order[0] = 0;
+    for (int j = 0; j < n_jobs; ++j) S->h_job_order[1 + j] = j;
+    std::stable_sort(S->h_job_order.begin() + 1, S->h_job_order.end(), [&](int a, int b) { return w[a] > w[b]; });
+    EFB_CUDA(c, cudaMemcpyAsync(S->d_job, S->h_job_order.data(), S->h_job_order.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  }
   if (!S->ev_s0) {
     EFB_CUDA(c, cudaEventCreate(&S->ev_s0));
     EFB_CUDA(c, cudaEventCreate(&S->ev_s1));
   }
   EFB_CUDA(c, cudaEventRecord(S->ev_s0, c->stream));
-  const int grid = std::max(1, std::min(n_jobs, c->sm_count));
+  const bool two_per_sm = variant >= 4 && 2 * (smem + 1024) <= 228 * 1024;
+  const int grid = std::max(1, std::min(n_jobs, (two_per_sm ? 2 : 1) * c->sm_count));
   // kernel shape: threads per CTA, loads in flight per lane, register double buffering
-  int variant = 1;
-  if (const char *v = getenv("EDGEFEM_B200_SMALL_VARIANT")) variant = atoi(v);
   const int mr = o->max_restarts > 0 ? o->max_restarts : 3;
 #define EFB_SMALL_LAUNCH(NRV, NT, SPDV, DBV)                                                                                              \
   do {                                                                                                                                    \
     EFB_CUDA(c, cudaFuncSetAttribute(k_cocg_small<NRV, NT, SPDV, DBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
     k_cocg_small<NRV, NT, SPDV, DBV><<<grid, NT, smem, c->stream>>>(P.D, S->d_sell_ptr, S->d_sell_col, S->d_sell_perm, S->d_sell_vals,    \
+                                                                      S->sell_total, S->n_slices, P.first_matrix, n_jobs, groups, S->d_job, \
+                                                                      S->d_b, S->d_x, P.vec[V_R], P.vec[V_Q], P.aux ? 1 : 0, zero_x ? 1 : 0, mr); \
+  } while (0)
+#define EFB_SMALL_LAUNCH2(NRV, NT, SPDV, DBV)                                                                                             \
+  do {                                                                                                                                    \
+    EFB_CUDA(c, cudaFuncSetAttribute(k_cocg_small<NRV, NT, SPDV, DBV, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+    k_cocg_small<NRV, NT, SPDV, DBV, 2><<<grid, NT, smem, c->stream>>>(P.D, S->d_sell_ptr, S->d_sell_col, S->d_sell_perm, S->d_sell_vals, \
                                                                       S->sell_total, S->n_slices, P.first_matrix, n_jobs, groups, S->d_job, \
                                                                       S->d_b, S->d_x, P.vec[V_R], P.vec[V_Q], P.aux ? 1 : 0, zero_x ? 1 : 0, mr); \
   } while (0)
@@ -1296,10 +1329,13 @@ static int run_cocg_small(SolvePlan &P, const efb_solve_opts *o, bool zero_x, bo
       case 0: EFB_SMALL_LAUNCH(1, 512, 8, true); break;
       case 2: EFB_SMALL_LAUNCH(1, 1024, 0, false); break;
       case 3: EFB_SMALL_LAUNCH(1, 1024, 2, true); break;
+      case 4: EFB_SMALL_LAUNCH2(1, 512, 4, false); break;
+      case 5: EFB_SMALL_LAUNCH2(1, 512, 2, false); break;
       default: EFB_SMALL_LAUNCH(1, 1024, 4, false); break;
     }
   }
 #undef EFB_SMALL_LAUNCH
+#undef EFB_SMALL_LAUNCH2
   EFB_CHECK_LAUNCH(c);
   EFB_CUDA(c, cudaEventRecord(S->ev_s1, c->stream));
   S->small_timed = true;
@@ -1402,6 +1438,8 @@ int efb_solve(efb_system *sys_, int32_t first_matrix, int32_t n_matrix, const ef
     const double rr = hscal[(size_t)i * NSCAL + S_RR].x, bb = hscal[(size_t)i * NSCAL + S_BB].x;
     efb_solve_result &R = results[i];
     R.iters = hiters[i];
+    if ((int)S->last_iters.size() != S->n_sys) S->last_iters.assign((size_t)S->n_sys, 0);
+    S->last_iters[(size_t)P.first_sys + i] = hiters[i];
     R.method = P.method;
     R.precond = P.aux ? EFB_PRECOND_AUX : P.precond;
     R.residual = bb > 0.0 ? sqrt(rr / bb) : sqrt(rr);
