@@ -117,6 +117,13 @@ SIGNATURES = {
     "efb_system_last_solve_kernel_ms": (C.c_int, [C.c_void_p, f64p]),
     "efb_spmv_host": (C.c_int, [C.c_void_p, C.c_int32, f64p, f64p]),
     "efb_bench_kernel": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, f64p]),
+    "efb_system_create_rows": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "efb_dist_unique_id": (C.c_int, [u8p]),
+    "efb_dist_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, u8p]),
+    "efb_dist_finalize": (None, [C.c_void_p]),
+    "efb_dist_row_range": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "efb_dist_solve": (C.c_int, [C.c_void_p, C.POINTER(SolveOpts), C.POINTER(SolveResult), C.c_int32]),
+    "efb_dist_bench": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, f64p]),
 }
 
 _lib: Optional[C.CDLL] = None
@@ -156,6 +163,46 @@ def _i32(a) -> np.ndarray:
     return np.ascontiguousarray(np.asarray(a, dtype=np.int32))
 
 
+_nccl_preloaded = False
+
+
+def _preload_nccl():
+    """Make the NCCL the library dlopen()s the SAME copy torch links against (the wheel's nvidia/nccl/lib/libnccl.so.2):
+    loading the system libnccl first would satisfy torch's later `libnccl.so.2` dependency with an older library."""
+    global _nccl_preloaded
+    if _nccl_preloaded:
+        return
+    _nccl_preloaded = True
+    try:
+        import importlib.util
+
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for base in (spec.submodule_search_locations if spec else []):
+            path = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(path):
+                C.CDLL(path, mode=C.RTLD_GLOBAL)
+                return
+    except Exception:
+        pass  # fall back to whatever libnccl.so.2 the loader finds
+
+
+def dist_unique_id() -> bytes:
+    _preload_nccl()
+    buf = np.zeros(128, dtype=np.uint8)
+    rc = load().efb_dist_unique_id(_p(buf, u8p))
+    if rc:
+        raise EfbError("efb_dist_unique_id failed (%d): %s" % (rc, load().efb_last_error(None).decode()))
+    return buf.tobytes()
+
+
+def dist_row_range(m: int, rank: int, world: int):
+    a, b = C.c_int32(), C.c_int32()
+    rc = load().efb_dist_row_range(m, rank, world, C.byref(a), C.byref(b))
+    if rc:
+        raise EfbError("efb_dist_row_range: bad arguments")
+    return a.value, b.value
+
+
 class Ctx:
     def __init__(self, device: int = 0):
         self.lib = load()
@@ -185,6 +232,13 @@ class Ctx:
         ms = C.c_double()
         self.check(self.lib.efb_timer_stop(self.h, C.byref(ms)), "efb_timer_stop")
         return ms.value
+
+    def dist_init(self, rank: int, world: int, unique_id: bytes):
+        """Join the NCCL communicator of a row-partitioned solve (`unique_id` from dist_unique_id() on rank 0)."""
+        _preload_nccl()
+        buf = np.frombuffer(bytes(unique_id), dtype=np.uint8).copy()
+        assert buf.size == 128
+        self.check(self.lib.efb_dist_init(self.h, rank, world, _p(buf, u8p)), "efb_dist_init")
 
     def close(self):
         if self.h:
@@ -259,6 +313,16 @@ class DeviceSystem:
         return cls(ctx, h, mesh)
 
     @classmethod
+    def from_mesh_rows(cls, mesh: DeviceMesh, row_begin: int, row_end: int, n_matrix=1, n_rhs=1):
+        """Row block [row_begin, row_end) of the mesh's system (row-partitioned multi-GPU solve); `m` is the local row count."""
+        h = C.c_void_p()
+        ctx = mesh.ctx
+        ctx.check(ctx.lib.efb_system_create_rows(mesh.h, row_begin, row_end, n_matrix, n_rhs, C.byref(h)), "efb_system_create_rows")
+        s = cls(ctx, h, mesh)
+        s.row_begin, s.row_end = row_begin, row_end
+        return s
+
+    @classmethod
     def from_csr(cls, ctx: Ctx, rowptr, colidx, vals=None, n_matrix=1, n_rhs=1):
         rp, ci = _i32(rowptr), _i32(colidx)
         v = None if vals is None else _c128(vals)
@@ -286,7 +350,7 @@ class DeviceSystem:
 
     def set_dirichlet(self, flags):
         f = np.ascontiguousarray(np.asarray(flags, dtype=np.uint8))
-        assert f.size == self.m
+        assert f.size == (self.mesh.n_edge if getattr(self, "row_begin", None) is not None else self.m)  # row blocks take GLOBAL flags
         self.ctx.check(self.ctx.lib.efb_system_set_dirichlet(self.h, _p(f, u8p)), "efb_system_set_dirichlet")
 
     def set_gradient(self, n_node, edge_nodes):
@@ -353,6 +417,18 @@ class DeviceSystem:
         y = np.zeros(self.m, dtype=np.complex128)
         self.ctx.check(self.ctx.lib.efb_spmv_host(self.h, matrix, _p(xv.view(np.float64), f64p), _p(y.view(np.float64), f64p)), "efb_spmv_host")
         return y
+
+    def dist_solve(self, tol=1e-10, max_iterations=10000, precond=PRECOND_JACOBI, check_every=0, zero_initial_guess=True, max_restarts=3,
+                   halo_mode=0):
+        o = SolveOpts(METHOD_COCG, precond, tol, max_iterations, check_every, 1, 1 if zero_initial_guess else 0, max_restarts, 0)
+        r = SolveResult()
+        self.ctx.check(self.ctx.lib.efb_dist_solve(self.h, C.byref(o), C.byref(r), halo_mode), "efb_dist_solve")
+        return dict(iters=r.iters, converged=bool(r.converged), method=r.method, precond=r.precond, residual=r.residual)
+
+    def dist_bench(self, which, reps, halo_mode=0) -> float:
+        ms = C.c_double()
+        self.ctx.check(self.ctx.lib.efb_dist_bench(self.h, which, reps, halo_mode, C.byref(ms)), "efb_dist_bench")
+        return ms.value
 
     def bench_kernel(self, which, reps) -> float:
         ms = C.c_double()

@@ -180,14 +180,14 @@ __global__ void k_bbox_decode(unsigned long long *enc, double *out, int n) {
 // bake the Dirichlet COLUMN mask into the assembly map: bit 15 of an incidence's column offset says
 // "this column is a Dirichlet edge" (the entry then stays an explicit zero)
 __global__ void k_pos_dirichlet(const int32_t *__restrict__ e2t_ptr, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
-                                const uint8_t *__restrict__ dir, int m, uint16_t *pos) {
+                                const uint8_t *__restrict__ dir, int m, uint16_t *pos, long long pos_off) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= m) return;
   const int rb = rowptr[r];
   for (int k = e2t_ptr[r]; k < e2t_ptr[r + 1]; ++k)
     for (int j = 0; j < 6; ++j) {
-      const uint16_t p = pos[(size_t)k * 6 + j] & 0x7fffu;
-      pos[(size_t)k * 6 + j] = p | (dir[colidx[rb + p]] ? 0x8000u : 0u);
+      const uint16_t p = pos[(size_t)k * 6 + j - pos_off] & 0x7fffu;
+      pos[(size_t)k * 6 + j - pos_off] = p | (dir[colidx[rb + p]] ? 0x8000u : 0u);
     }
 }
 
@@ -266,6 +266,7 @@ void efb_ctx_destroy(efb_ctx *ctx_) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  efb_dist_finalize(ctx_);
   pool_trim();
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -434,12 +435,13 @@ static int system_alloc_common(System *S) {
   parallel_for(S->m, [&](int64_t a, int64_t b) {
     for (int64_t r = a; r < b; ++r) {
       const int32_t *beg = S->h_colidx.data() + S->h_rowptr[r], *end = S->h_colidx.data() + S->h_rowptr[r + 1];
-      const int32_t *it = std::lower_bound(beg, end, (int32_t)r);
-      if (it != end && *it == r) diag[r] = (int32_t)(it - S->h_colidx.data());
+      const int32_t g = (int32_t)(r + S->row0);  // columns are global ids
+      const int32_t *it = std::lower_bound(beg, end, g);
+      if (it != end && *it == g) diag[r] = (int32_t)(it - S->h_colidx.data());
     }
   });
   if ((rc = dev_upload(c, &S->d_diag_pos, diag.data(), diag.size()))) return rc;
-  if (S->m <= 16384) {  // SELL-32 structure (only systems small enough for the persistent one-CTA solver)
+  if (S->m <= 16384 && S->m == S->m_global) {  // SELL-32 structure (only systems small enough for the persistent one-CTA solver)
     std::vector<int32_t> order(S->m);
     for (int r = 0; r < S->m; ++r) order[r] = r;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
@@ -491,13 +493,14 @@ static int system_alloc_common(System *S) {
   if ((rc = dev_alloc(c, &S->d_vals, (size_t)S->n_matrix * S->nnz))) return rc;
   if ((rc = dev_alloc(c, &S->d_b, (size_t)S->n_sys * S->m))) return rc;
   if ((rc = dev_alloc(c, &S->d_x, (size_t)S->n_sys * S->m))) return rc;
-  if ((rc = dev_alloc(c, &S->d_dir, (size_t)S->m))) return rc;
+  if ((rc = dev_alloc(c, &S->d_dir_all, (size_t)S->m_global))) return rc;  // column flags are global, rows see the local slice
+  S->d_dir = S->d_dir_all + S->row0;
   if ((rc = dev_alloc(c, &S->d_flag, (size_t)1))) return rc;
   EFB_CUDA(c, cudaMemsetAsync(S->d_flag, 0, sizeof(int32_t), c->stream));
   EFB_CUDA(c, cudaMemsetAsync(S->d_vals, 0, (size_t)S->n_matrix * S->nnz * sizeof(c128), c->stream));
   EFB_CUDA(c, cudaMemsetAsync(S->d_b, 0, (size_t)S->n_sys * S->m * sizeof(c128), c->stream));
   EFB_CUDA(c, cudaMemsetAsync(S->d_x, 0, (size_t)S->n_sys * S->m * sizeof(c128), c->stream));
-  EFB_CUDA(c, cudaMemsetAsync(S->d_dir, 0, (size_t)S->m, c->stream));
+  EFB_CUDA(c, cudaMemsetAsync(S->d_dir_all, 0, (size_t)S->m_global, c->stream));
   return EFB_OK;
 }
 
@@ -529,24 +532,21 @@ static int system_set_gradient(System *S, int n_node, const int32_t *edge_nodes)
   return EFB_OK;
 }
 
-int efb_system_create(efb_mesh *mesh_, int64_t n_extra, const int32_t *extra_rows, const int32_t *extra_cols,
-                      int32_t n_matrix, int32_t n_rhs, efb_system **out) {
-  Mesh *M = (Mesh *)mesh_;
-  if (!M || !out) return fail(M ? M->ctx : nullptr, EFB_ERR_INVALID, "efb_system_create: NULL argument");
+}  // extern "C"
+
+// System over the rows [row0, row1) of the mesh's edge space (all rows for the ordinary single-GPU system).  Rows are
+// indexed locally (0 .. row1-row0), columns keep their global edge ids.
+static int system_create_rows(Mesh *M, int row0, int row1, int64_t n_extra, const int32_t *extra_rows, const int32_t *extra_cols,
+                              int32_t n_matrix, int32_t n_rhs, efb_system **out) {
   Ctx *c = M->ctx;
-  *out = nullptr;
-  if (n_matrix <= 0 || n_rhs <= 0 || n_extra < 0 || (n_extra > 0 && (!extra_rows || !extra_cols)))
-    return fail(c, EFB_ERR_INVALID, "efb_system_create: bad arguments");
-  EFB_CUDA(c, cudaSetDevice(c->device));
-  const int m = M->m;
-  for (int64_t i = 0; i < n_extra; ++i)
-    if (extra_rows[i] < 0 || extra_rows[i] >= m || extra_cols[i] < 0 || extra_cols[i] >= m)
-      return fail(c, EFB_ERR_INVALID, "efb_system_create: extra entry %lld out of range", (long long)i);
+  const int m = row1 - row0;
   SubTrace st;
   System *S = new System();
   S->ctx = c;
   S->mesh = M;
   S->m = m;
+  S->m_global = M->m;
+  S->row0 = row0;
   S->n_matrix = n_matrix;
   S->n_rhs = n_rhs;
   // extras bucketed by row
@@ -561,9 +561,10 @@ int efb_system_create(efb_mesh *mesh_, int64_t n_extra, const int32_t *extra_row
   // pass 1: row lengths ; pass 2: fill
   S->h_rowptr.assign((size_t)m + 1, 0);
   const int32_t *te = M->h_tet_edges.data();
+  const int64_t kpos0 = M->h_e2t_ptr[row0];  // first incidence of the local rows: origin of the position map
   auto row_cols = [&](int r, std::vector<int32_t> &buf) {
     buf.clear();
-    for (int32_t k = M->h_e2t_ptr[r]; k < M->h_e2t_ptr[r + 1]; ++k) {
+    for (int32_t k = M->h_e2t_ptr[row0 + r]; k < M->h_e2t_ptr[row0 + r + 1]; ++k) {
       const int32_t *e6 = te + 6 * (int64_t)(M->h_e2t_item[k] >> 3);
       buf.insert(buf.end(), e6, e6 + 6);
     }
@@ -574,7 +575,7 @@ int efb_system_create(efb_mesh *mesh_, int64_t n_extra, const int32_t *extra_row
   // one pass: every worker builds the sorted column lists of its row range into a private buffer and fills the
   // tet-local -> row-local position map; the buffers are then concatenated at the row offsets
   std::vector<int32_t> rowlen(m);
-  std::vector<uint16_t> pos((size_t)M->h_e2t_item.size() * 6);
+  std::vector<uint16_t> pos((size_t)(M->h_e2t_ptr[row1] - kpos0) * 6);
   struct RangeCols {
     int64_t a = 0, b = 0;
     std::vector<int32_t> cols;
@@ -591,10 +592,10 @@ int efb_system_create(efb_mesh *mesh_, int64_t n_extra, const int32_t *extra_row
       row_cols((int)r, buf);
       rowlen[r] = (int32_t)buf.size();
       rc_.cols.insert(rc_.cols.end(), buf.begin(), buf.end());
-      for (int32_t k = M->h_e2t_ptr[r]; k < M->h_e2t_ptr[r + 1]; ++k) {
+      for (int32_t k = M->h_e2t_ptr[row0 + r]; k < M->h_e2t_ptr[row0 + r + 1]; ++k) {
         const int32_t *e6 = te + 6 * (int64_t)(M->h_e2t_item[k] >> 3);
         for (int j = 0; j < 6; ++j)
-          pos[(size_t)k * 6 + j] = (uint16_t)(std::lower_bound(buf.begin(), buf.end(), e6[j]) - buf.begin());
+          pos[(size_t)(k - kpos0) * 6 + j] = (uint16_t)(std::lower_bound(buf.begin(), buf.end(), e6[j]) - buf.begin());
       }
     }
   });
@@ -649,11 +650,41 @@ int efb_system_create(efb_mesh *mesh_, int64_t n_extra, const int32_t *extra_row
   if ((rc = dev_upload(c, &S->d_e2t_pos, pos.data(), pos.size()))) return rc;
   if ((rc = dev_upload(c, &S->d_chunk_row, chunk.data(), chunk.size()))) return rc;
 
-  if ((rc = system_set_gradient(S, M->n_node, M->h_edge_nodes.data()))) return rc;
+  // the discrete gradient (auxiliary-space preconditioner) is only kept for whole-mesh systems
+  if (m == M->m && (rc = system_set_gradient(S, M->n_node, M->h_edge_nodes.data()))) return rc;
   EFB_CUDA(c, cudaStreamSynchronize(c->stream));
   st.mark("gradient lists + sync");
   *out = (efb_system *)S;
   return EFB_OK;
+}
+
+extern "C" {
+
+int efb_system_create(efb_mesh *mesh_, int64_t n_extra, const int32_t *extra_rows, const int32_t *extra_cols,
+                      int32_t n_matrix, int32_t n_rhs, efb_system **out) {
+  Mesh *M = (Mesh *)mesh_;
+  if (!M || !out) return fail(M ? M->ctx : nullptr, EFB_ERR_INVALID, "efb_system_create: NULL argument");
+  Ctx *c = M->ctx;
+  *out = nullptr;
+  if (n_matrix <= 0 || n_rhs <= 0 || n_extra < 0 || (n_extra > 0 && (!extra_rows || !extra_cols)))
+    return fail(c, EFB_ERR_INVALID, "efb_system_create: bad arguments");
+  EFB_CUDA(c, cudaSetDevice(c->device));
+  const int m = M->m;
+  for (int64_t i = 0; i < n_extra; ++i)
+    if (extra_rows[i] < 0 || extra_rows[i] >= m || extra_cols[i] < 0 || extra_cols[i] >= m)
+      return fail(c, EFB_ERR_INVALID, "efb_system_create: extra entry %lld out of range", (long long)i);
+  return system_create_rows(M, 0, m, n_extra, extra_rows, extra_cols, n_matrix, n_rhs, out);
+}
+
+int efb_system_create_rows(efb_mesh *mesh_, int32_t row_begin, int32_t row_end, int32_t n_matrix, int32_t n_rhs, efb_system **out) {
+  Mesh *M = (Mesh *)mesh_;
+  if (!M || !out) return fail(M ? M->ctx : nullptr, EFB_ERR_INVALID, "efb_system_create_rows: NULL argument");
+  Ctx *c = M->ctx;
+  *out = nullptr;
+  if (n_matrix <= 0 || n_rhs <= 0 || row_begin < 0 || row_end > M->m || row_begin >= row_end)
+    return fail(c, EFB_ERR_INVALID, "efb_system_create_rows: bad arguments");
+  EFB_CUDA(c, cudaSetDevice(c->device));
+  return system_create_rows(M, row_begin, row_end, 0, nullptr, nullptr, n_matrix, n_rhs, out);
 }
 
 int efb_system_create_csr(efb_ctx *ctx_, int32_t m, int64_t nnz, const int32_t *rowptr, const int32_t *colidx,
@@ -675,6 +706,7 @@ int efb_system_create_csr(efb_ctx *ctx_, int32_t m, int64_t nnz, const int32_t *
   System *S = new System();
   S->ctx = c;
   S->m = m;
+  S->m_global = m;
   S->nnz = nnz;
   S->n_matrix = n_matrix;
   S->n_rhs = n_rhs;
@@ -696,9 +728,10 @@ void efb_system_destroy(efb_system *sys_) {
   if (!S) return;
   cudaSetDevice(S->ctx->device);
   cudaStreamSynchronize(S->ctx->stream);
+  dist_free(S);
   solver_free(S);
   dfree(S->d_rowptr); dfree(S->d_colidx); dfree(S->d_diag_pos); dfree(S->d_vals);
-  dfree(S->d_b); dfree(S->d_x); dfree(S->d_dir); dfree(S->d_e2t_pos); dfree(S->d_chunk_row); dfree(S->d_sp_chunk);
+  dfree(S->d_b); dfree(S->d_x); dfree(S->d_dir_all); dfree(S->d_e2t_pos); dfree(S->d_chunk_row); dfree(S->d_sp_chunk);
   dfree(S->d_sell_ptr); dfree(S->d_sell_col); dfree(S->d_sell_perm); dfree(S->d_sell_vals);
   dfree(S->d_edge_nodes); dfree(S->d_n2e_ptr); dfree(S->d_n2e_item); dfree(S->d_node_dir);
   dfree(S->d_mat_blob);
@@ -749,10 +782,12 @@ int efb_system_set_dirichlet(efb_system *sys_, const uint8_t *flags) {
   if (!S || !flags) return fail(S ? S->ctx : nullptr, EFB_ERR_INVALID, "efb_system_set_dirichlet: bad argument");
   Ctx *c = S->ctx;
   EFB_CUDA(c, cudaSetDevice(c->device));
-  EFB_CUDA(c, cudaMemcpyAsync(S->d_dir, flags, (size_t)S->m, cudaMemcpyHostToDevice, c->stream));
+  // flags cover ALL edges of the mesh (m_global entries): rows read the local slice, columns the whole array
+  EFB_CUDA(c, cudaMemcpyAsync(S->d_dir_all, flags, (size_t)S->m_global, cudaMemcpyHostToDevice, c->stream));
   S->has_dir = true;
   if (S->d_e2t_pos && S->mesh) {
-    k_pos_dirichlet<<<(S->m + 127) / 128, 128, 0, c->stream>>>(S->mesh->d_e2t_ptr, S->d_rowptr, S->d_colidx, S->d_dir, S->m, S->d_e2t_pos);
+    k_pos_dirichlet<<<(S->m + 127) / 128, 128, 0, c->stream>>>(S->mesh->d_e2t_ptr + S->row0, S->d_rowptr, S->d_colidx, S->d_dir_all, S->m,
+                                                               S->d_e2t_pos, (long long)S->mesh->h_e2t_ptr[S->row0] * 6);
     EFB_CHECK_LAUNCH(c);
   }
   if (S->d_node_dir) {

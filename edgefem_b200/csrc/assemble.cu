@@ -160,7 +160,7 @@ k_assemble_volume(const TetGeom *__restrict__ geom, const double4 *__restrict__ 
                   const uint8_t *__restrict__ dir, const SlotMat *__restrict__ slots,
                   const efb_pole *__restrict__ poles, const double *__restrict__ slot_bbox,
                   const double *__restrict__ omegas, int n_slots, int mode, int first, long long nnz,
-                  c128 *__restrict__ vals) {
+                  c128 *__restrict__ vals, long long pos_off) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // entry i of local row lr lives at acc[i + lr]: the +lr skew spreads the row starts of the 32
   // lanes of a warp (consecutive rows, ~16 entries = 64 words apart) over the shared-memory banks
@@ -242,7 +242,7 @@ k_assemble_volume(const TetGeom *__restrict__ geom, const double4 *__restrict__ 
       const double2 *ra2 = (const double2 *)G->gg[a], *rb2 = (const double2 *)G->gg[b];
       const double2 a01 = ra2[0], a23 = ra2[1], b01 = rb2[0], b23 = rb2[1];
       const double2 tail = *(const double2 *)&G->V;
-      const uint16_t *pp = e2t_pos + (size_t)k * 6;  // 6 x uint16 = 12 bytes, 4-byte aligned
+      const uint16_t *pp = e2t_pos + ((size_t)k * 6 - pos_off);  // 6 x uint16 = 12 bytes, 4-byte aligned
       const uint32_t p01 = *(const uint32_t *)(pp), p23 = *(const uint32_t *)(pp + 2), p45 = *(const uint32_t *)(pp + 4);
       // bit 15 of a position: the column is a Dirichlet edge (entry stays an explicit zero)
       const int pos[6] = {(int)(p01 & 0xffff), (int)(p01 >> 16), (int)(p23 & 0xffff), (int)(p23 >> 16), (int)(p45 & 0xffff), (int)(p45 >> 16)};
@@ -319,9 +319,10 @@ int assemble_launch(System *S, int first, int count, int mode) {
   EFB_CUDA(c, cudaFuncSetAttribute(k_assemble_volume, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)assemble_smem_bytes(MAX_SLOTS)));
   dim3 grid((unsigned)S->n_chunks, (unsigned)count);
   k_assemble_volume<<<grid, ASM_THREADS, smem, c->stream>>>(
-      M->d_geom, M->d_xyz, M->d_tet_nodes, M->d_e2t_ptr, M->d_e2t_item, S->d_e2t_pos,
+      M->d_geom, M->d_xyz, M->d_tet_nodes, M->d_e2t_ptr + S->row0, M->d_e2t_item, S->d_e2t_pos,
       S->d_chunk_row, S->d_rowptr, S->d_diag_pos, S->d_dir, (const SlotMat *)blob, (const efb_pole *)(blob + off_poles),
-      M->d_slot_bbox, (const double *)(blob + off_om), ns, mode, first, (long long)S->nnz, S->d_vals);
+      M->d_slot_bbox, (const double *)(blob + off_om), ns, mode, first, (long long)S->nnz, S->d_vals,
+      (long long)M->h_e2t_ptr[S->row0] * 6);
   EFB_CHECK_LAUNCH(c);
   return EFB_OK;
 }
@@ -626,6 +627,7 @@ int efb_combine_km(efb_system *sys_, int32_t dst_first, int32_t count, const dou
 
 int efb_add_diag(efb_system *sys_, int32_t first, int32_t count, int32_t n, const int32_t *edges, const double *coef) {
   System *S = (System *)sys_;
+  EFB_WHOLE_ONLY(S, "efb_add_diag");
   if (!S) return fail(nullptr, EFB_ERR_INVALID, "efb_add_diag: NULL system");
   Ctx *c = S->ctx;
   if (n < 0 || (n > 0 && !edges) || !coef || first < 0 || count <= 0 || first + count > S->n_matrix)
@@ -649,6 +651,7 @@ int efb_add_diag(efb_system *sys_, int32_t first, int32_t count, int32_t n, cons
 int efb_port_create(efb_system *sys_, int32_t n_edges, const int32_t *edges, const double *weights, int64_t n_ms,
                     const int32_t *ms_rows, const int32_t *ms_cols, const double *ms_vals, efb_port **out) {
   System *S = (System *)sys_;
+  EFB_WHOLE_ONLY(S, "efb_port_create");
   if (!S || !out) return fail(S ? S->ctx : nullptr, EFB_ERR_INVALID, "efb_port_create: NULL argument");
   Ctx *c = S->ctx;
   *out = nullptr;
@@ -858,6 +861,7 @@ int efb_port_project_batch(efb_system *sys_, efb_port *port_, int32_t count, con
 
 int efb_x_recover(efb_system *sys_, int32_t rhs, int32_t n, const int32_t *dst, const int32_t *src, const double *phase) {
   System *S = (System *)sys_;
+  EFB_WHOLE_ONLY(S, "efb_x_recover");
   if (!S || rhs < 0 || rhs >= S->n_sys || n < 0 || (n > 0 && (!dst || !src || !phase)))
     return fail(S ? S->ctx : nullptr, EFB_ERR_INVALID, "efb_x_recover: bad arguments");
   if (n == 0) return EFB_OK;

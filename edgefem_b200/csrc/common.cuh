@@ -75,6 +75,7 @@ struct Ctx {
   int64_t launches = 0;
   int sm_count = 148;
   std::string err;
+  void *dist = nullptr;  // efb::Dist (rank, world, NCCL communicator) once efb_dist_init ran
 };
 
 struct Mesh {
@@ -102,14 +103,16 @@ struct Port;
 struct System {
   Ctx *ctx = nullptr;
   Mesh *mesh = nullptr;  // may be null (generic CSR system)
-  int m = 0, n_matrix = 0, n_rhs = 0, n_sys = 0, n_node = 0;
+  int m = 0, n_matrix = 0, n_rhs = 0, n_sys = 0, n_node = 0;  // m = LOCAL rows
+  int m_global = 0, row0 = 0;  // row-partitioned systems own rows [row0, row0+m) of m_global; columns are global ids
   int64_t nnz = 0;
   std::vector<int32_t> h_rowptr, h_colidx;
   int32_t *d_rowptr = nullptr, *d_colidx = nullptr, *d_diag_pos = nullptr;
   c128 *d_vals = nullptr;      // [n_matrix][nnz]
   c128 *d_b = nullptr;         // [n_sys][m]
   c128 *d_x = nullptr;         // [n_sys][m]
-  uint8_t *d_dir = nullptr;    // [m] Dirichlet flags
+  uint8_t *d_dir_all = nullptr; // [m_global] Dirichlet flags of every edge (column lookups)
+  uint8_t *d_dir = nullptr;    // = d_dir_all + row0: flags of the local rows
   bool has_dir = false;
   // assembly maps (mesh-born systems)
   uint16_t *d_e2t_pos = nullptr;   // [6*n_tet*6] column offsets inside the row (bit 15: Dirichlet column)
@@ -155,6 +158,7 @@ struct System {
   size_t mat_blob_bytes = 0;
   std::vector<uint8_t> last_mat_blob;
   int last_mode = 0;
+  void *dist_state = nullptr;  // efb::DistState of a row-partitioned system (dist.cu)
 };
 
 struct Port {
@@ -180,6 +184,13 @@ int fail(Ctx *ctx, int code, const char *fmt, ...);
     if (_e != cudaSuccess)                                                               \
       return ::efb::fail((ctx), EFB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,            \
                          cudaGetErrorString(_e), __FILE__, __LINE__);                    \
+  } while (0)
+
+// entry points that index vectors by global edge id refuse row-partitioned systems
+#define EFB_WHOLE_ONLY(S, name)                                                                              \
+  do {                                                                                                       \
+    if ((S) && (S)->m != (S)->m_global)                                                                      \
+      return ::efb::fail((S)->ctx, EFB_ERR_STATE, name ": not available on a row-partitioned system (efb_system_create_rows); use the efb_dist_* calls"); \
   } while (0)
 
 #define EFB_CHECK_LAUNCH(ctx)                                                            \
@@ -240,6 +251,7 @@ struct Timed {  // records CUDA events around a compute call on the ctx stream
 
 // internal entry points shared across translation units
 int solver_free(System *s);
+void dist_free(System *s);
 int assemble_launch(System *s, int first, int count, int mode);
 int launch_tet_geometry(Mesh *m);
 

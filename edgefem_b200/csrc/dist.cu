@@ -1,0 +1,650 @@
+// Row-partitioned solve of ONE large system over the GPUs of a node (second bullet: the single-large-mesh
+// case C5).  One process per GPU; rank r owns the contiguous rows [r*chunk, min(m, (r+1)*chunk)) of the global edge
+// space (efb_dist_row_range), assembles them with the ordinary volume kernel (efb_system_create_rows +
+// efb_assemble_volume: the row-gather assembly needs no communication) and solves with COCG + Jacobi.
+//
+// The exchange step of the path is the SpMV input vector.  It is NOT exchanged by a collective: every rank maps the
+// peers' copy of the vector through CUDA IPC and the SpMV kernel loads the off-rank entries it needs straight over
+// NVLink (k_dist_spmv, halo_mode 0) -- compute and transfer are one kernel, only the halo entries move (a slab
+// partition of a first-seen-by-tet numbering touches ~1-2 % remote columns).  halo_mode 1 is the library baseline
+// beside it: ncclAllGather of the whole vector, then a local SpMV.
+//
+// Cross-rank ordering comes from the two scalar all-reduces a CG iteration needs anyway; the recurrence is arranged so
+// that no third synchronisation is required: the SpMV is applied to z (complete on every rank before the all-reduce of
+// r^T z returns) and  q = A z + beta q,  p = z + beta p  are formed in its epilogue.
+//   K1  t = A z (remote z), q = t + beta q, p = z + beta p, partial p^T q        -> F1 -> all-reduce {p^T q}
+//   K2  alpha = rho / p^T q, x += alpha p, r -= alpha q, z = D^-1 r, partial r^T z, |r|^2 -> F2 -> all-reduce {rho, rr}
+// NCCL is resolved at run time (dlopen libnccl.so.2 -- the copy torch already loaded when the caller is Python), so the
+// library itself has no link-time dependency on it.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cmath>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace efb {
+
+namespace {
+
+struct NcclApi {
+  void *lib = nullptr;
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclAllReduce) AllReduce = nullptr;
+  decltype(&ncclAllGather) AllGather = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+};
+
+NcclApi *nccl_api(std::string &err) {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    // EDGEFEM_B200_NCCL_LIB overrides; otherwise the soname -- which resolves to the copy already loaded in the
+    // process (torch's bundled NCCL when the caller is Python, see cabi._preload_nccl) or the system library
+    const char *names[] = {getenv("EDGEFEM_B200_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+      if (!n || !n[0]) continue;
+      api.lib = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+      if (api.lib) break;
+    }
+    if (api.lib) {
+      api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.lib, "ncclGetUniqueId");
+      api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.lib, "ncclCommInitRank");
+      api.AllReduce = (decltype(api.AllReduce))dlsym(api.lib, "ncclAllReduce");
+      api.AllGather = (decltype(api.AllGather))dlsym(api.lib, "ncclAllGather");
+      api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.lib, "ncclCommDestroy");
+      api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.lib, "ncclGetErrorString");
+    }
+  }
+  if (!api.lib || !api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.AllGather || !api.CommDestroy) {
+    err = "libnccl.so.2 not found or incomplete";
+    return nullptr;
+  }
+  return &api;
+}
+
+struct Dist {  // per context
+  int rank = 0, world = 1;
+  ncclComm_t comm = nullptr;
+};
+
+constexpr int DIST_MAX_WORLD = 8;
+constexpr int DIST_RED_BLOCKS = 1184;  // 8 x 148 CTAs carry reduction partials
+constexpr int DIST_VEC_THREADS = 256;
+
+struct XView {  // how a kernel reads entry `col` (global edge id) of the distributed SpMV input
+  const c128 *peer[DIST_MAX_WORLD];  // peer[o] = rank o's copy of its own rows (CUDA IPC mapping)
+  const c128 *local;                 // this rank's own rows
+  const c128 *full;                  // halo_mode 1: the all-gathered vector (index = global id)
+  int chunk, row0, m_loc, mode;
+};
+
+__device__ __forceinline__ c128 xload(const XView &v, int col) {
+  if (v.mode == 1) return v.full[col];
+  const unsigned l = (unsigned)(col - v.row0);
+  if (l < (unsigned)v.m_loc) return __ldg(&v.local[l]);  // on-rank (the vector is constant during the kernel)
+  const int o = col / v.chunk;                            // block partition: owner by division
+  // plain (coherent) load through the peer mapping: one NVLink read per halo entry
+  const c128 *p = v.peer[o] + (col - o * v.chunk);
+  c128 r;
+  asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ c128 ld_stream(const c128 *p) {
+  c128 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int ld_stream(const int32_t *p) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+// device scalars of a distributed solve (doubles)
+enum {
+  DS_PQ = 0,        // [2] p^T q (+1 pad: partial triples are written whole)   (all-reduced after K1)
+  DS_RHO = 3,       // [2] r^T z, then [1] |r|^2   (all-reduced after K2)
+  DS_RR = 5,
+  DS_RHO_PREV = 6,  // [2] rho the current p was built with
+  DS_BB = 8,        // [1] |b|^2 (+2 pad)  (all-reduced once)
+  DS_SYNC = 12,     // [1] always 0: operand of the all-reduces that only order the ranks
+  DS_NUM = 16
+};
+
+// block-level sum of N doubles per thread -> partial[blockIdx][N]   (deterministic: fixed tree)
+template <int N>
+__device__ __forceinline__ void block_partial(double (&v)[N], double *__restrict__ partial) {
+  __shared__ double red[8][N];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < N; ++k)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+  if (lane == 0)
+#pragma unroll
+    for (int k = 0; k < N; ++k) red[wid][k] = v[k];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      double a = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) a += red[w][k];
+      partial[(size_t)blockIdx.x * N + k] = a;
+    }
+  }
+}
+
+// one CTA: sums the block partials in block order, writes them to sc[dst..dst+N); optionally rho -> rho_prev
+template <int N>
+__global__ void __launch_bounds__(256) k_dist_finish(const double *__restrict__ partial, int n_blocks, double *sc, int dst, int save_rho) {
+  __shared__ double red[256][N];
+  double a[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) a[k] = 0.0;
+  for (int b = threadIdx.x; b < n_blocks; b += 256)
+#pragma unroll
+    for (int k = 0; k < N; ++k) a[k] += partial[(size_t)b * N + k];
+#pragma unroll
+  for (int k = 0; k < N; ++k) red[threadIdx.x][k] = a[k];
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s)
+#pragma unroll
+      for (int k = 0; k < N; ++k) red[threadIdx.x][k] += red[threadIdx.x + s][k];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) sc[dst + k] = red[0][k];
+    if (save_rho) {  // K1 of this iteration has consumed rho: it becomes rho_prev for alpha and the next beta
+      sc[DS_RHO_PREV] = sc[DS_RHO];
+      sc[DS_RHO_PREV + 1] = sc[DS_RHO + 1];
+    }
+  }
+}
+
+// K1 (EPI 1): t = A z over the view, q = t + beta q, p = z + beta p, partial p^T q.   beta = rho / rho_prev (0 if first)
+// EPI 0:      r = b - A x over the view, z = dinv r, partial {r^T z, |r|^2}         (true residual / start of a cycle)
+// CSR-stream mapping (see k_spmv_stream in solve.cu): a warp owns <= 256 entries of whole rows.
+template <int EPI>
+__global__ void __launch_bounds__(256)
+k_dist_spmv(const int32_t *__restrict__ sp_chunk, int n_chunks, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
+            const c128 *__restrict__ vals, const __grid_constant__ XView xv, const c128 *__restrict__ bvec, const c128 *__restrict__ dinv, c128 *__restrict__ zloc,
+            c128 *__restrict__ r, c128 *__restrict__ p, c128 *__restrict__ q, const double *__restrict__ sc, int first, double *__restrict__ partial) {
+  __shared__ c128 prod[8][SPMV_STREAM_W];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  c128 beta = cmake(0.0, 0.0);
+  if (EPI == 1 && !first) {
+    const c128 rho = cmake(sc[DS_RHO], sc[DS_RHO + 1]), rp = cmake(sc[DS_RHO_PREV], sc[DS_RHO_PREV + 1]);
+    if (rp.x != 0.0 || rp.y != 0.0) beta = cdiv(rho, rp);
+  }
+  double d[3] = {0.0, 0.0, 0.0};
+  for (int ch = blockIdx.x * 8 + wid; ch < n_chunks; ch += gridDim.x * 8) {
+    const int r0 = __ldg(&sp_chunk[ch]), r1 = __ldg(&sp_chunk[ch + 1]);
+    const int nrow = r1 - r0;
+    int rs = 0;
+    if (lane <= nrow) rs = __ldg(&rowptr[r0 + lane]);
+    const int k0 = __shfl_sync(0xffffffffu, rs, 0);
+    const int k1 = __shfl_sync(0xffffffffu, rs, nrow);
+    const int re = __shfl_down_sync(0xffffffffu, rs, 1);
+    c128 a[SPMV_STREAM_W / 32];
+    int c[SPMV_STREAM_W / 32];
+#pragma unroll
+    for (int j = 0; j < SPMV_STREAM_W / 32; ++j) {
+      const int k = k0 + lane + 32 * j;
+      const bool in = k < k1;
+      a[j] = in ? ld_stream(&vals[k]) : cmake(0.0, 0.0);
+      c[j] = in ? ld_stream(&colidx[k]) : -1;
+    }
+#pragma unroll
+    for (int j = 0; j < SPMV_STREAM_W / 32; ++j)
+      if (c[j] >= 0) prod[wid][lane + 32 * j] = cmul(a[j], xload(xv, c[j]));
+    __syncwarp();
+    if (lane < nrow) {
+      const int row = r0 + lane;
+      c128 acc = cmake(0.0, 0.0);
+      for (int k = rs - k0; k < re - k0; ++k) acc = cadd(acc, prod[wid][k]);
+      if (EPI == 1) {
+        const c128 zi = zloc[row];
+        c128 qi = acc, pi = zi;
+        if (!first) {
+          qi = cfma(beta, q[row], acc);
+          pi = cfma(beta, p[row], zi);
+        }
+        q[row] = qi;
+        p[row] = pi;
+        const c128 t = cmul(pi, qi);
+        d[0] += t.x; d[1] += t.y;
+      } else {
+        const c128 ri = csub(bvec[row], acc);
+        const c128 zi = cmul(dinv[row], ri);
+        r[row] = ri;
+        q[row] = zi;  // parked: z may still be read by peers if it aliases the SpMV input; the caller copies q -> z
+        const c128 t = cmul(ri, zi);
+        d[0] += t.x; d[1] += t.y;
+        d[2] += cabs2(ri);
+      }
+    }
+    __syncwarp();
+  }
+  block_partial<3>(d, partial);
+}
+
+// K2: alpha = rho_prev / p^T q ; x += alpha p ; r -= alpha q ; z = dinv r ; partial {r^T z, |r|^2}
+__global__ void __launch_bounds__(DIST_VEC_THREADS)
+k_dist_update(int m, const double *__restrict__ sc, const c128 *__restrict__ dinv, const c128 *__restrict__ p, const c128 *__restrict__ q,
+              c128 *__restrict__ x, c128 *__restrict__ r, c128 *__restrict__ z, double *__restrict__ partial) {
+  const c128 pq = cmake(sc[DS_PQ], sc[DS_PQ + 1]), rho = cmake(sc[DS_RHO_PREV], sc[DS_RHO_PREV + 1]);
+  c128 alpha = cmake(0.0, 0.0);
+  if ((pq.x != 0.0 || pq.y != 0.0) && isfinite(pq.x) && isfinite(pq.y)) alpha = cdiv(rho, pq);
+  double d[3] = {0.0, 0.0, 0.0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+    x[i] = cfma(alpha, p[i], x[i]);
+    const c128 ri = cfma(cneg(alpha), q[i], r[i]);
+    const c128 zi = cmul(dinv[i], ri);
+    r[i] = ri;
+    z[i] = zi;
+    const c128 t = cmul(ri, zi);
+    d[0] += t.x; d[1] += t.y;
+    d[2] += cabs2(ri);
+  }
+  block_partial<3>(d, partial);
+}
+
+__global__ void k_dist_dinv(int m, const int32_t *__restrict__ diag_pos, const c128 *__restrict__ vals, c128 *__restrict__ dinv, int jacobi) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+    c128 v = cmake(1.0, 0.0);
+    const int pp = diag_pos[i];
+    if (jacobi && pp >= 0) {
+      const c128 a = vals[pp];
+      if (a.x != 0.0 || a.y != 0.0) v = cdiv(cmake(1.0, 0.0), a);
+    }
+    dinv[i] = v;
+  }
+}
+
+__global__ void k_dist_copy(int m, const c128 *__restrict__ src, c128 *__restrict__ dst) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+__global__ void k_dist_norm2(int m, const c128 *__restrict__ v, double *__restrict__ partial) {
+  double d[3] = {0.0, 0.0, 0.0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) d[0] += cabs2(v[i]);
+  block_partial<3>(d, partial);
+}
+
+struct DistState {  // per row-partitioned system
+  int world = 1, rank = 0, chunk = 0;
+  c128 *d_z = nullptr;      // [chunk] SpMV input of the iteration (IPC-shared)
+  c128 *d_xs = nullptr;     // [chunk] solution copy the peers read for the true residual (IPC-shared)
+  c128 *d_r = nullptr, *d_p = nullptr, *d_q = nullptr, *d_dinv = nullptr;  // [m_loc]
+  c128 *d_full = nullptr;   // [world*chunk] halo_mode 1 gather buffer (lazy)
+  double *d_sc = nullptr;   // [DS_NUM]
+  double *d_partial = nullptr;  // [DIST_RED_BLOCKS*3]
+  unsigned char *d_handles = nullptr;  // [world][2][64] IPC handles (all-gathered)
+  c128 *peer_z[DIST_MAX_WORLD] = {}, *peer_x[DIST_MAX_WORLD] = {};
+  bool opened = false;
+};
+
+}  // namespace
+
+static int nccl_fail(Ctx *c, NcclApi *api, ncclResult_t r, const char *what) {
+  return fail(c, EFB_ERR_CUDA, "%s failed: %s", what, api->GetErrorString ? api->GetErrorString(r) : "NCCL error");
+}
+
+#define EFB_NCCL(c, api, expr)                                   \
+  do {                                                           \
+    ncclResult_t _r = (expr);                                    \
+    if (_r != ncclSuccess) return nccl_fail((c), (api), _r, #expr); \
+  } while (0)
+
+void dist_free(System *S) {
+  DistState *T = (DistState *)S->dist_state;
+  if (!T) return;
+  cudaStreamSynchronize(S->ctx->stream);
+  if (T->opened)
+    for (int o = 0; o < T->world; ++o)
+      if (o != T->rank) {
+        if (T->peer_z[o]) cudaIpcCloseMemHandle(T->peer_z[o]);
+        if (T->peer_x[o]) cudaIpcCloseMemHandle(T->peer_x[o]);
+      }
+  // IPC-exported allocations go straight back to the driver (a pooled block must not be re-issued while a peer maps it)
+  cudaFree(T->d_z);
+  cudaFree(T->d_xs);
+  dfree(T->d_r); dfree(T->d_p); dfree(T->d_q); dfree(T->d_dinv); dfree(T->d_full); dfree(T->d_sc); dfree(T->d_partial);
+  dfree(T->d_handles);
+  delete T;
+  S->dist_state = nullptr;
+}
+
+static int dist_prepare(System *S, DistState **out) {
+  Ctx *c = S->ctx;
+  Dist *dd = (Dist *)c->dist;
+  if (!dd) return fail(c, EFB_ERR_STATE, "efb_dist_*: call efb_dist_init on the context first");
+  if (S->n_matrix != 1 || S->n_rhs != 1) return fail(c, EFB_ERR_INVALID, "efb_dist_*: row-partitioned systems carry one matrix and one right-hand side");
+  if (!S->d_sp_chunk) return fail(c, EFB_ERR_LIMIT, "efb_dist_*: a row has more than %d entries", SPMV_STREAM_W);
+  if (S->dist_state) {
+    *out = (DistState *)S->dist_state;
+    return EFB_OK;
+  }
+  std::string err;
+  NcclApi *api = nccl_api(err);
+  if (!api) return fail(c, EFB_ERR_STATE, "efb_dist_*: %s", err.c_str());
+  const int world = dd->world, rank = dd->rank;
+  const int chunk = (S->m_global + world - 1) / world;
+  if (S->row0 != std::min(S->m_global, rank * chunk) || S->row0 + S->m != std::min(S->m_global, (rank + 1) * chunk))
+    return fail(c, EFB_ERR_INVALID, "efb_dist_*: rank %d must own rows [%d, %d) (efb_dist_row_range), system has [%d, %d)", rank,
+                std::min(S->m_global, rank * chunk), std::min(S->m_global, (rank + 1) * chunk), S->row0, S->row0 + S->m);
+  DistState *T = new DistState();
+  S->dist_state = T;
+  T->world = world;
+  T->rank = rank;
+  T->chunk = chunk;
+  int rc;
+  // exported vectors: their own cudaMalloc blocks (never pooled), padded to `chunk` so an all-gather has equal counts
+  EFB_CUDA(c, cudaMalloc((void **)&T->d_z, (size_t)chunk * sizeof(c128)));
+  EFB_CUDA(c, cudaMalloc((void **)&T->d_xs, (size_t)chunk * sizeof(c128)));
+  EFB_CUDA(c, cudaMemsetAsync(T->d_z, 0, (size_t)chunk * sizeof(c128), c->stream));
+  EFB_CUDA(c, cudaMemsetAsync(T->d_xs, 0, (size_t)chunk * sizeof(c128), c->stream));
+  if ((rc = dev_alloc(c, &T->d_r, (size_t)S->m))) return rc;
+  if ((rc = dev_alloc(c, &T->d_p, (size_t)S->m))) return rc;
+  if ((rc = dev_alloc(c, &T->d_q, (size_t)S->m))) return rc;
+  if ((rc = dev_alloc(c, &T->d_dinv, (size_t)S->m))) return rc;
+  if ((rc = dev_alloc(c, &T->d_sc, (size_t)DS_NUM))) return rc;
+  if ((rc = dev_alloc(c, &T->d_partial, (size_t)DIST_RED_BLOCKS * 3))) return rc;
+  if ((rc = dev_alloc(c, &T->d_handles, (size_t)world * 2 * sizeof(cudaIpcMemHandle_t)))) return rc;
+  EFB_CUDA(c, cudaMemsetAsync(T->d_sc, 0, DS_NUM * sizeof(double), c->stream));
+  T->peer_z[rank] = T->d_z;
+  T->peer_x[rank] = T->d_xs;
+  if (world > 1) {
+    cudaIpcMemHandle_t mine[2];
+    EFB_CUDA(c, cudaIpcGetMemHandle(&mine[0], T->d_z));
+    EFB_CUDA(c, cudaIpcGetMemHandle(&mine[1], T->d_xs));
+    EFB_CUDA(c, cudaMemcpyAsync(T->d_handles + (size_t)rank * sizeof(mine), mine, sizeof(mine), cudaMemcpyHostToDevice, c->stream));
+    EFB_NCCL(c, api, api->AllGather(T->d_handles + (size_t)rank * sizeof(mine), T->d_handles, sizeof(mine), ncclUint8, dd->comm, c->stream));
+    std::vector<cudaIpcMemHandle_t> all((size_t)world * 2);
+    EFB_CUDA(c, cudaMemcpyAsync(all.data(), T->d_handles, all.size() * sizeof(cudaIpcMemHandle_t), cudaMemcpyDeviceToHost, c->stream));
+    EFB_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int o = 0; o < world; ++o) {
+      if (o == rank) continue;
+      EFB_CUDA(c, cudaIpcOpenMemHandle((void **)&T->peer_z[o], all[(size_t)o * 2], cudaIpcMemLazyEnablePeerAccess));
+      EFB_CUDA(c, cudaIpcOpenMemHandle((void **)&T->peer_x[o], all[(size_t)o * 2 + 1], cudaIpcMemLazyEnablePeerAccess));
+    }
+    T->opened = true;
+  }
+  EFB_CUDA(c, cudaStreamSynchronize(c->stream));
+  *out = T;
+  return EFB_OK;
+}
+
+static XView make_view(const System *S, const DistState *T, c128 *const *peers, const c128 *local, int mode) {
+  XView v;
+  for (int o = 0; o < DIST_MAX_WORLD; ++o) v.peer[o] = o < T->world ? peers[o] : nullptr;
+  v.local = local;
+  v.full = T->d_full;
+  v.chunk = T->chunk;
+  v.row0 = S->row0;
+  v.m_loc = S->m;
+  v.mode = mode;
+  return v;
+}
+
+static int spmv_grid(const Ctx *c, int n_chunks) { return std::max(1, std::min((n_chunks + 7) / 8, DIST_RED_BLOCKS)); }
+static int vec_blocks(const Ctx *c, int m) { return std::max(1, std::min((m + DIST_VEC_THREADS - 1) / DIST_VEC_THREADS, DIST_RED_BLOCKS)); }
+
+// halo_mode 1: gather the exported vector of every rank into d_full
+static int gather_full(System *S, DistState *T, NcclApi *api, const c128 *mine) {
+  Ctx *c = S->ctx;
+  Dist *dd = (Dist *)c->dist;
+  if (!T->d_full) {
+    int rc = dev_alloc(c, &T->d_full, (size_t)T->world * T->chunk);
+    if (rc) return rc;
+  }
+  EFB_NCCL(c, api, api->AllGather(mine, T->d_full, (size_t)T->chunk * 2, ncclFloat64, dd->comm, c->stream));
+  return EFB_OK;
+}
+
+struct DistRun {
+  System *S;
+  DistState *T;
+  NcclApi *api;
+  Dist *dd;
+  int mode;
+};
+
+// r = b - A x (x read through the view of the exported solution copy), z = dinv r, all-reduce {rho, rr}
+static int dist_residual(const DistRun &R) {
+  System *S = R.S;
+  DistState *T = R.T;
+  Ctx *c = S->ctx;
+  const int nb = spmv_grid(c, S->n_sp_chunks);
+  k_dist_copy<<<vec_blocks(c, S->m), DIST_VEC_THREADS, 0, c->stream>>>(S->m, S->d_x, T->d_xs);
+  EFB_CHECK_LAUNCH(c);
+  // every rank's copy must be complete before anybody reads it: the {bb}/{rho,rr} all-reduce of the previous step
+  // orders the kernels of one rank, an explicit tiny all-reduce orders the ranks
+  EFB_NCCL(c, R.api, R.api->AllReduce(T->d_sc + DS_SYNC, T->d_sc + DS_SYNC, 1, ncclFloat64, ncclSum, R.dd->comm, c->stream));
+  if (R.mode == 1) {
+    int rc = gather_full(S, T, R.api, T->d_xs);
+    if (rc) return rc;
+  }
+  const XView xv = make_view(S, T, T->peer_x, T->d_xs, R.mode);
+  k_dist_spmv<0><<<nb, 256, 0, c->stream>>>(S->d_sp_chunk, S->n_sp_chunks, S->d_rowptr, S->d_colidx, S->d_vals, xv, S->d_b, T->d_dinv, T->d_z,
+                                            T->d_r, T->d_p, T->d_q, T->d_sc, 1, T->d_partial);
+  EFB_CHECK_LAUNCH(c);
+  k_dist_finish<3><<<1, 256, 0, c->stream>>>(T->d_partial, nb, T->d_sc, DS_RHO, 0);
+  EFB_CHECK_LAUNCH(c);
+  EFB_NCCL(c, R.api, R.api->AllReduce(T->d_sc + DS_RHO, T->d_sc + DS_RHO, 3, ncclFloat64, ncclSum, R.dd->comm, c->stream));
+  // z (parked in q by the kernel) -> exported z; peers finished reading the old z before the all-reduce returned
+  k_dist_copy<<<vec_blocks(c, S->m), DIST_VEC_THREADS, 0, c->stream>>>(S->m, T->d_q, T->d_z);
+  EFB_CHECK_LAUNCH(c);
+  // ... and the new z must be complete everywhere before the first K1 reads it
+  EFB_NCCL(c, R.api, R.api->AllReduce(T->d_sc + DS_SYNC, T->d_sc + DS_SYNC, 1, ncclFloat64, ncclSum, R.dd->comm, c->stream));
+  return EFB_OK;
+}
+
+// one COCG iteration (K1, F1, all-reduce, K2, F2, all-reduce)
+static int dist_iteration(const DistRun &R, int first) {
+  System *S = R.S;
+  DistState *T = R.T;
+  Ctx *c = S->ctx;
+  const int nb = spmv_grid(c, S->n_sp_chunks), vb = vec_blocks(c, S->m);
+  if (R.mode == 1) {
+    int rc = gather_full(S, T, R.api, T->d_z);
+    if (rc) return rc;
+  }
+  const XView zv = make_view(S, T, T->peer_z, T->d_z, R.mode);
+  k_dist_spmv<1><<<nb, 256, 0, c->stream>>>(S->d_sp_chunk, S->n_sp_chunks, S->d_rowptr, S->d_colidx, S->d_vals, zv, S->d_b, T->d_dinv, T->d_z,
+                                            T->d_r, T->d_p, T->d_q, T->d_sc, first, T->d_partial);
+  EFB_CHECK_LAUNCH(c);
+  k_dist_finish<3><<<1, 256, 0, c->stream>>>(T->d_partial, nb, T->d_sc, DS_PQ, 1);  // partial[2] is unused by K1 (zero)
+  EFB_CHECK_LAUNCH(c);
+  EFB_NCCL(c, R.api, R.api->AllReduce(T->d_sc + DS_PQ, T->d_sc + DS_PQ, 2, ncclFloat64, ncclSum, R.dd->comm, c->stream));
+  k_dist_update<<<vb, DIST_VEC_THREADS, 0, c->stream>>>(S->m, T->d_sc, T->d_dinv, T->d_p, T->d_q, S->d_x, T->d_r, T->d_z, T->d_partial);
+  EFB_CHECK_LAUNCH(c);
+  k_dist_finish<3><<<1, 256, 0, c->stream>>>(T->d_partial, vb, T->d_sc, DS_RHO, 0);
+  EFB_CHECK_LAUNCH(c);
+  EFB_NCCL(c, R.api, R.api->AllReduce(T->d_sc + DS_RHO, T->d_sc + DS_RHO, 3, ncclFloat64, ncclSum, R.dd->comm, c->stream));
+  return EFB_OK;
+}
+
+}  // namespace efb
+
+using namespace efb;
+
+extern "C" {
+
+int efb_dist_unique_id(uint8_t *id128) {
+  if (!id128) return EFB_ERR_INVALID;
+  std::string err;
+  NcclApi *api = nccl_api(err);
+  if (!api) return fail(nullptr, EFB_ERR_STATE, "efb_dist_unique_id: %s", err.c_str());
+  ncclUniqueId id;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclResult_t r = api->GetUniqueId(&id);
+  if (r != ncclSuccess) return nccl_fail(nullptr, api, r, "ncclGetUniqueId");
+  memcpy(id128, &id, 128);
+  return EFB_OK;
+}
+
+int efb_dist_init(efb_ctx *ctx_, int32_t rank, int32_t world, const uint8_t *id128) {
+  Ctx *c = (Ctx *)ctx_;
+  if (!c || !id128 || world < 1 || world > DIST_MAX_WORLD || rank < 0 || rank >= world)
+    return fail(c, EFB_ERR_INVALID, "efb_dist_init: bad arguments (world <= %d)", DIST_MAX_WORLD);
+  if (c->dist) return fail(c, EFB_ERR_STATE, "efb_dist_init: context already initialised");
+  std::string err;
+  NcclApi *api = nccl_api(err);
+  if (!api) return fail(c, EFB_ERR_STATE, "efb_dist_init: %s", err.c_str());
+  EFB_CUDA(c, cudaSetDevice(c->device));
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  Dist *dd = new Dist();
+  dd->rank = rank;
+  dd->world = world;
+  ncclResult_t r = api->CommInitRank(&dd->comm, world, id, rank);
+  if (r != ncclSuccess) {
+    delete dd;
+    return nccl_fail(c, api, r, "ncclCommInitRank");
+  }
+  c->dist = dd;
+  return EFB_OK;
+}
+
+void efb_dist_finalize(efb_ctx *ctx_) {
+  Ctx *c = (Ctx *)ctx_;
+  if (!c || !c->dist) return;
+  Dist *dd = (Dist *)c->dist;
+  std::string err;
+  NcclApi *api = nccl_api(err);
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (api && dd->comm) api->CommDestroy(dd->comm);
+  delete dd;
+  c->dist = nullptr;
+}
+
+int efb_dist_row_range(int32_t m, int32_t rank, int32_t world, int32_t *row_begin, int32_t *row_end) {
+  if (m <= 0 || world < 1 || rank < 0 || rank >= world || !row_begin || !row_end) return EFB_ERR_INVALID;
+  const int chunk = (m + world - 1) / world;
+  *row_begin = std::min(m, rank * chunk);
+  *row_end = std::min(m, (rank + 1) * chunk);
+  return EFB_OK;
+}
+
+int efb_dist_solve(efb_system *sys_, const efb_solve_opts *opts, efb_solve_result *result, int32_t halo_mode) {
+  System *S = (System *)sys_;
+  if (!S || !opts || !result) return fail(S ? S->ctx : nullptr, EFB_ERR_INVALID, "efb_dist_solve: NULL argument");
+  Ctx *c = S->ctx;
+  if (!S->assembled) return fail(c, EFB_ERR_STATE, "efb_dist_solve: matrix values were never assembled or set");
+  if (!(opts->tolerance > 0.0) || opts->max_iterations < 0 || halo_mode < 0 || halo_mode > 1) return fail(c, EFB_ERR_INVALID, "efb_dist_solve: bad options");
+  if (opts->method != EFB_METHOD_COCG && opts->method != EFB_METHOD_AUTO)
+    return fail(c, EFB_ERR_INVALID, "efb_dist_solve: the row-partitioned solver is COCG (complex symmetric systems)");
+  if (opts->precond == EFB_PRECOND_AUX) return fail(c, EFB_ERR_INVALID, "efb_dist_solve: preconditioner must be Jacobi or none");
+  EFB_CUDA(c, cudaSetDevice(c->device));
+  DistState *T = nullptr;
+  int rc = dist_prepare(S, &T);
+  if (rc) return rc;
+  std::string err;
+  DistRun R{S, T, nccl_api(err), (Dist *)c->dist, halo_mode};
+  const int vb = vec_blocks(c, S->m);
+  k_dist_dinv<<<vb, DIST_VEC_THREADS, 0, c->stream>>>(S->m, S->d_diag_pos, S->d_vals, T->d_dinv, opts->precond != EFB_PRECOND_NONE ? 1 : 0);
+  EFB_CHECK_LAUNCH(c);
+  if (opts->zero_initial_guess) EFB_CUDA(c, cudaMemsetAsync(S->d_x, 0, (size_t)S->m * sizeof(c128), c->stream));
+  // |b|^2
+  k_dist_norm2<<<vb, DIST_VEC_THREADS, 0, c->stream>>>(S->m, S->d_b, T->d_partial);
+  EFB_CHECK_LAUNCH(c);
+  k_dist_finish<3><<<1, 256, 0, c->stream>>>(T->d_partial, vb, T->d_sc, DS_BB, 0);
+  EFB_CHECK_LAUNCH(c);
+  EFB_NCCL(c, R.api, R.api->AllReduce(T->d_sc + DS_BB, T->d_sc + DS_BB, 1, ncclFloat64, ncclSum, R.dd->comm, c->stream));
+  const double tol2 = opts->tolerance * opts->tolerance;
+  const int check_every = opts->check_every > 0 ? opts->check_every : 32;
+  const int max_restarts = opts->max_restarts > 0 ? opts->max_restarts : 3;
+  int iters = 0;
+  double rr = 0.0, bb = 0.0;
+  bool conv = false;
+  double h[DS_NUM];
+  auto read_scalars = [&]() -> int {
+    EFB_CUDA(c, cudaMemcpyAsync(h, T->d_sc, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    EFB_CUDA(c, cudaStreamSynchronize(c->stream));
+    rr = h[DS_RR];
+    bb = h[DS_BB];
+    return EFB_OK;
+  };
+  for (int cycle = 0; cycle <= max_restarts; ++cycle) {
+    // true residual of the current iterate (every rank takes the same branch: the scalars are all-reduced)
+    if ((rc = dist_residual(R))) return rc;
+    if ((rc = read_scalars())) return rc;
+    const double lim = bb > 0.0 ? tol2 * bb : tol2;
+    conv = rr <= lim;
+    if (conv || iters >= opts->max_iterations || !std::isfinite(rr)) break;
+    bool first = true, stop = false;
+    while (!stop) {
+      const int n = std::min(check_every, opts->max_iterations - iters);
+      for (int k = 0; k < n; ++k) {
+        if ((rc = dist_iteration(R, first ? 1 : 0))) return rc;
+        first = false;
+      }
+      iters += n;
+      if ((rc = read_scalars())) return rc;
+      stop = rr <= lim || iters >= opts->max_iterations || !std::isfinite(rr) || n == 0;
+    }
+  }
+  result->iters = iters;
+  result->method = EFB_METHOD_COCG;
+  result->precond = opts->precond == EFB_PRECOND_NONE ? EFB_PRECOND_NONE : EFB_PRECOND_JACOBI;
+  result->residual = bb > 0.0 ? sqrt(rr / bb) : sqrt(rr);
+  result->converged = conv ? 1 : 0;
+  return EFB_OK;
+}
+
+// which 0: K1 alone (distributed SpMV + fused epilogue; halo_mode 1 includes the all-gather); 1: one full COCG iteration
+int efb_dist_bench(efb_system *sys_, int32_t which, int32_t reps, int32_t halo_mode, double *avg_ms) {
+  System *S = (System *)sys_;
+  if (!S || !avg_ms || reps <= 0 || which < 0 || which > 1 || halo_mode < 0 || halo_mode > 1)
+    return fail(S ? S->ctx : nullptr, EFB_ERR_INVALID, "efb_dist_bench: bad arguments");
+  Ctx *c = S->ctx;
+  if (!S->assembled) return fail(c, EFB_ERR_STATE, "efb_dist_bench: matrix values were never assembled or set");
+  EFB_CUDA(c, cudaSetDevice(c->device));
+  DistState *T = nullptr;
+  int rc = dist_prepare(S, &T);
+  if (rc) return rc;
+  std::string err;
+  DistRun R{S, T, nccl_api(err), (Dist *)c->dist, halo_mode};
+  const int vb = vec_blocks(c, S->m), nb = spmv_grid(c, S->n_sp_chunks);
+  k_dist_dinv<<<vb, DIST_VEC_THREADS, 0, c->stream>>>(S->m, S->d_diag_pos, S->d_vals, T->d_dinv, 1);
+  EFB_CHECK_LAUNCH(c);
+  if ((rc = dist_residual(R))) return rc;
+  cudaEvent_t e0, e1;
+  EFB_CUDA(c, cudaEventCreate(&e0));
+  EFB_CUDA(c, cudaEventCreate(&e1));
+  for (int pass = 0; pass < 2; ++pass) {  // pass 0 warms up
+    const int n = pass == 0 ? std::min(reps, 3) : reps;
+    EFB_CUDA(c, cudaEventRecord(e0, c->stream));
+    for (int k = 0; k < n; ++k) {
+      if (which == 1) {
+        if ((rc = dist_iteration(R, 0))) return rc;
+      } else {
+        if (halo_mode == 1 && (rc = gather_full(S, T, R.api, T->d_z))) return rc;
+        const XView zv = make_view(S, T, T->peer_z, T->d_z, halo_mode);
+        k_dist_spmv<1><<<nb, 256, 0, c->stream>>>(S->d_sp_chunk, S->n_sp_chunks, S->d_rowptr, S->d_colidx, S->d_vals, zv, S->d_b, T->d_dinv,
+                                                  T->d_z, T->d_r, T->d_p, T->d_q, T->d_sc, 1, T->d_partial);
+        EFB_CHECK_LAUNCH(c);
+      }
+    }
+    EFB_CUDA(c, cudaEventRecord(e1, c->stream));
+    EFB_CUDA(c, cudaEventSynchronize(e1));
+    float ms = 0.f;
+    EFB_CUDA(c, cudaEventElapsedTime(&ms, e0, e1));
+    *avg_ms = (double)ms / n;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return EFB_OK;
+}
+
+}  // extern "C"

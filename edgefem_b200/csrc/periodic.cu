@@ -142,6 +142,7 @@ int efb_periodic_extra(const efb_mesh *mesh_, int64_t n_base, const int32_t *bas
 int efb_apply_periodic(efb_system *sys_, int32_t first, int32_t count, int32_t n_pairs, const int32_t *master, const int32_t *slave,
                        const double *phase) {
   System *S = (System *)sys_;
+  EFB_WHOLE_ONLY(S, "efb_apply_periodic");
   if (!S) return fail(nullptr, EFB_ERR_INVALID, "efb_apply_periodic: NULL system");
   Ctx *c = S->ctx;
   if (first < 0 || count <= 0 || first + count > S->n_matrix || n_pairs < 0 || (n_pairs > 0 && (!master || !slave || !phase)))

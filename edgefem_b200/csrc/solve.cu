@@ -1351,6 +1351,7 @@ extern "C" {
 
 int efb_solve(efb_system *sys_, int32_t first_matrix, int32_t n_matrix, const efb_solve_opts *opts, efb_solve_result *results) {
   System *S = (System *)sys_;
+  EFB_WHOLE_ONLY(S, "efb_solve");
   if (!S) return fail(nullptr, EFB_ERR_INVALID, "efb_solve: NULL system");
   Ctx *c = S->ctx;
   if (!opts || !results || first_matrix < 0 || n_matrix <= 0 || first_matrix + n_matrix > S->n_matrix)
@@ -1462,6 +1463,7 @@ int efb_system_last_solve_kernel_ms(efb_system *sys_, double *ms) {
 
 int efb_spmv_host(efb_system *sys_, int32_t matrix, const double *x, double *y) {
   System *S = (System *)sys_;
+  EFB_WHOLE_ONLY(S, "efb_spmv_host");
   if (!S || !x || !y || matrix < 0 || matrix >= S->n_matrix) return fail(S ? S->ctx : nullptr, EFB_ERR_INVALID, "efb_spmv_host: bad arguments");
   Ctx *c = S->ctx;
   EFB_CUDA(c, cudaSetDevice(c->device));
@@ -1483,6 +1485,7 @@ int efb_spmv_host(efb_system *sys_, int32_t matrix, const double *x, double *y) 
 
 int efb_bench_kernel(efb_system *sys_, int32_t which, int32_t reps, double *avg_ms) {
   System *S = (System *)sys_;
+  EFB_WHOLE_ONLY(S, "efb_bench_kernel");
   if (!S || !avg_ms || reps <= 0 || which < 0 || which > 4) return fail(S ? S->ctx : nullptr, EFB_ERR_INVALID, "efb_bench_kernel: bad arguments");
   Ctx *c = S->ctx;
   EFB_CUDA(c, cudaSetDevice(c->device));

@@ -41,3 +41,37 @@ def gather_sweep(local_S: np.ndarray, n_points: int, rank: int, world: int, dist
         a = parts[r].cpu().numpy()
         out[idx] = a[: idx.size, ..., 0] + 1j * a[: idx.size, ..., 1]
     return out
+
+
+def row_range(m: int, rank: int, world: int):
+    """Row block of rank `rank` in the row-partitioned single-system solve (same rule as efb_dist_row_range):
+    chunk = ceil(m / world), rows [rank*chunk, min(m, (rank+1)*chunk)) -- every rank but the last owns exactly
+    `chunk` rows, so the owner of a global row is row // chunk."""
+    if m <= 0 or world < 1 or not (0 <= rank < world):
+        raise ValueError("bad m/rank/world")
+    chunk = (m + world - 1) // world
+    return min(m, rank * chunk), min(m, (rank + 1) * chunk)
+
+
+def gather_rows(local_x: np.ndarray, m: int, rank: int, world: int, dist=None, device=None) -> np.ndarray:
+    """All-gather the row blocks of a distributed vector into the full length-m vector (tests / post-processing)."""
+    local_x = np.asarray(local_x, dtype=np.complex128)
+    if world == 1 or dist is None:
+        return local_x.copy()
+    import torch
+
+    chunk = (m + world - 1) // world
+    buf = np.zeros((chunk, 2), dtype=np.float64)
+    buf[: local_x.size, 0] = local_x.real
+    buf[: local_x.size, 1] = local_x.imag
+    t = torch.from_numpy(buf)
+    if device is not None:
+        t = t.to(device)
+    parts = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(parts, t)
+    out = np.zeros(m, dtype=np.complex128)
+    for r in range(world):
+        a, b = row_range(m, r, world)
+        p = parts[r].cpu().numpy()
+        out[a:b] = p[: b - a, 0] + 1j * p[: b - a, 1]
+    return out

@@ -263,6 +263,30 @@ int efb_spmv_host(efb_system *sys, int32_t matrix, const double *x_c128, double 
  * 4 = FP64 FMA throughput probe (sm_count*8 CTAs x 256 threads x 8 chains x 4096 FMAs per launch). */
 int efb_bench_kernel(efb_system *sys, int32_t which, int32_t reps, double *avg_ms);
 
+/* ------------------------------------------------------------------ row-partitioned single large system
+ * One process per GPU.  Rank r owns rows [r*chunk, min(m,(r+1)*chunk)), chunk = ceil(m/world), of the global edge
+ * space; every rank holds the whole mesh (efb_mesh_create) and creates its block with efb_system_create_rows, sets
+ * the GLOBAL Dirichlet flags (efb_system_set_dirichlet, m_global bytes), assembles it with efb_assemble_volume (no
+ * communication: the row-gather kernel only needs the tets incident to its rows) and fills its slice of the
+ * right-hand side with efb_rhs_set (local length).  Replaces: the reference has no multi-GPU path; this is the
+ * SpMV + Krylov part of solve_linear (src/solver.cpp:11-193) for matrices larger than one GPU should carry.
+ *
+ * efb_dist_unique_id / efb_dist_init wrap ncclGetUniqueId / ncclCommInitRank (libnccl.so.2 is resolved with dlopen at
+ * the first call): rank 0 creates the 128-byte id, the caller ships it to the other ranks by any means
+ * (torch.distributed broadcast, MPI, a file) and every rank calls efb_dist_init(ctx, rank, world, id).
+ * efb_dist_solve: COCG + Jacobi.  halo_mode 0: the SpMV kernel loads off-rank vector entries directly from the peers'
+ * memory (CUDA IPC mappings over NVLink) -- no exchange collective; halo_mode 1: ncclAllGather of the vector + local
+ * SpMV (the library baseline).  Two scalar all-reduces per iteration in both modes.  Every rank must make the same
+ * sequence of efb_dist_* calls.  efb_x_get returns the local slice of the solution. */
+int efb_system_create_rows(efb_mesh *mesh, int32_t row_begin, int32_t row_end, int32_t n_matrix, int32_t n_rhs, efb_system **out);
+int efb_dist_unique_id(uint8_t *id128);
+int efb_dist_init(efb_ctx *ctx, int32_t rank, int32_t world, const uint8_t *id128);
+void efb_dist_finalize(efb_ctx *ctx);
+int efb_dist_row_range(int32_t m, int32_t rank, int32_t world, int32_t *row_begin, int32_t *row_end);
+int efb_dist_solve(efb_system *sys, const efb_solve_opts *opts, efb_solve_result *result, int32_t halo_mode);
+/* which 0: distributed SpMV + fused epilogue alone; 1: one full COCG iteration (2 kernels + 2 all-reduces) */
+int efb_dist_bench(efb_system *sys, int32_t which, int32_t reps, int32_t halo_mode, double *avg_ms);
+
 #ifdef __cplusplus
 }
 #endif
