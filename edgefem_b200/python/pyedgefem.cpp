@@ -12,6 +12,7 @@
 
 #include "edgefem/bc.hpp"
 #include "edgefem/edge_basis.hpp"
+#include "edgefem/io/touchstone.hpp"
 #include "edgefem/maxwell.hpp"
 #include "edgefem/mesh.hpp"
 #include "edgefem/periodic.hpp"
@@ -168,6 +169,17 @@ PYBIND11_MODULE(pyedgefem, m) {
       .def("num_tris", [](const Mesh &me) { return me.tris.size(); })
       .def("num_edges", [](const Mesh &me) { return me.edges.size(); })
       // bulk numpy views (extension; the per-object lists above are O(N) Python objects)
+      .def("boundary_lines_array",
+           [](const Mesh &me) {  // [l,3] = (n0, n1, phys); filled by extract_surface_mesh
+             py::array_t<std::int64_t> a({(py::ssize_t)me.boundary_lines.size(), (py::ssize_t)3});
+             auto r = a.mutable_unchecked<2>();
+             for (size_t i = 0; i < me.boundary_lines.size(); ++i) {
+               r(i, 0) = me.boundary_lines[i].n0;
+               r(i, 1) = me.boundary_lines[i].n1;
+               r(i, 2) = me.boundary_lines[i].phys;
+             }
+             return a;
+           })
       .def("tet_edges_array",
            [](const Mesh &me) {
              py::array_t<int> a({(py::ssize_t)me.tets.size(), (py::ssize_t)6});
@@ -418,6 +430,64 @@ PYBIND11_MODULE(pyedgefem, m) {
       .def_readwrite("e_direction", &LumpedPortConfig::e_direction)
       .def_readwrite("weight_mode", &LumpedPortConfig::weight_mode);
   m.def("build_lumped_port", &build_lumped_port, py::arg("mesh"), py::arg("config"));
+  // ---- nodal port eigenmodes and modal line-integral ports (reference python/pyedgefem.cpp:392-420,488-494,595-598)
+  m.def("solve_port_eigens", &solve_port_eigens, "Solve 2D eigenmode problem on port cross-section.", py::arg("mesh"), py::arg("num_modes"),
+        py::arg("omega"), py::arg("eps_r"), py::arg("mu_r"), py::arg("pol"));
+  py::class_<SParams2>(m, "SParams2", "2-port S-parameter data.")
+      .def(py::init<>())
+      .def_readwrite("s11", &SParams2::s11)
+      .def_readwrite("s21", &SParams2::s21)
+      .def_readwrite("s12", &SParams2::s12)
+      .def_readwrite("s22", &SParams2::s22);
+  m.def("straight_waveguide_sparams", &straight_waveguide_sparams, py::arg("port"), py::arg("length"), py::arg("freq"));
+  py::class_<PortSurfaceMesh>(m, "PortSurfaceMesh", "Surface mesh extracted from a volume port.")
+      .def(py::init<>())
+      .def_property_readonly("mesh", [](PortSurfaceMesh &s) -> Mesh & { return s.mesh; }, py::return_value_policy::reference_internal)
+      .def_readonly("volume_tri_indices", &PortSurfaceMesh::volume_tri_indices);
+  m.def("extract_surface_mesh", &extract_surface_mesh, "Extract a surface mesh for a port.", py::arg("mesh"), py::arg("surface_tag"));
+  m.def("build_wave_port", &build_wave_port, "Project a modal field onto port edges.", py::arg("volume_mesh"), py::arg("surface"),
+        py::arg("mode"));
+  m.def(
+      "populate_te10_field",
+      [](const PortSurfaceMesh &surface, const RectWaveguidePort &port, PortMode &mode) { populate_te10_field(surface, port, mode); },
+      "Populate TE10 mode field on a surface mesh using analytical formula.", py::arg("surface"), py::arg("port"), py::arg("mode"));
+  m.def(
+      "build_wave_port_from_eigenvector",
+      [](const Mesh &mesh, const PortSurfaceMesh &surface, py::array_t<double, py::array::c_style | py::array::forcecast> ev,
+         const PortMode &mode, const std::unordered_set<int> &pec) {
+        VectorXd v((size_t)ev.size());
+        for (py::ssize_t i = 0; i < ev.size(); ++i) v[(size_t)i] = ev.data()[i];
+        return build_wave_port_from_eigenvector(mesh, surface, v, mode, pec);
+      },
+      "Build wave port using 3D FEM eigenvector as weights.", py::arg("mesh"), py::arg("surface"), py::arg("eigenvector"), py::arg("mode"),
+      py::arg("pec_edges"));
+  // ---- Touchstone writers (reference python/pyedgefem.cpp:630-656)
+  m.def("write_touchstone", &write_touchstone, "Writes S-parameters to a Touchstone file.", py::arg("path"), py::arg("freq"), py::arg("data"));
+  py::enum_<TouchstoneFormat>(m, "TouchstoneFormat")
+      .value("RI", TouchstoneFormat::RI, "Real/Imaginary format")
+      .value("MA", TouchstoneFormat::MA, "Magnitude/Angle format")
+      .value("DB", TouchstoneFormat::DB, "dB/Angle format");
+  py::class_<TouchstoneOptions>(m, "TouchstoneOptions", "Options for Touchstone export.")
+      .def(py::init<>())
+      .def_readwrite("format", &TouchstoneOptions::format)
+      .def_readwrite("z0", &TouchstoneOptions::z0);
+  m.def(
+      "write_touchstone_nport",
+      [](const std::string &path, const std::vector<double> &freq,
+         const std::vector<py::array_t<std::complex<double>, py::array::c_style | py::array::forcecast>> &mats, const TouchstoneOptions &opts) {
+        std::vector<MatrixXcd> S;
+        for (const auto &a : mats) {
+          if (a.ndim() != 2) throw std::runtime_error("S matrices must be 2-D");
+          MatrixXcd M((int)a.shape(0), (int)a.shape(1));
+          for (int i = 0; i < M.rows(); ++i)
+            for (int j = 0; j < M.cols(); ++j) M(i, j) = a.at(i, j);
+          S.push_back(std::move(M));
+        }
+        write_touchstone_nport(path, freq, S, opts);
+      },
+      "Writes N-port S-parameters to a Touchstone file.", py::arg("path"), py::arg("freq"), py::arg("S_matrices"),
+      py::arg("opts") = TouchstoneOptions());
+  m.def("touchstone_extension", &touchstone_extension, py::arg("num_ports"));
   m.def("build_wave_port_2d", &build_wave_port_2d, py::arg("mesh"), py::arg("surface_tag"), py::arg("mode"), py::arg("pec_edges"),
         py::arg("target_kc_sq"));
   m.def(

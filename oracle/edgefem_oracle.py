@@ -1313,3 +1313,220 @@ def wr90_sparams(mesh: Mesh, pec: Set[int], freq: float, ports=None, port_abc_sc
         ports = wr90_ports(mesh, pec, freq)
     p = MaxwellParams(omega=2.0 * math.pi * freq, port_abc_scale=port_abc_scale)
     return calculate_sparams_eigenmode(mesh, p, pec, ports)
+
+
+# =====================================================================================================
+# nodal port eigenmodes, port-face extraction, modal line-integral ports,
+# Touchstone text.  Test infrastructure like the rest of this file.
+# =====================================================================================================
+@dataclass
+class PortSurface:  # ports/wave_port.hpp:14-17 (PortSurfaceMesh): 2-D mesh of the port face + source tri indices
+    node_ids: np.ndarray  # int64 [n]   first-seen order over the face's tris
+    xy: np.ndarray  # float64 [n,2]
+    tri_conn: np.ndarray  # int64 [k,3] node ids
+    volume_tri_indices: np.ndarray  # int64 [k]
+    boundary_lines: np.ndarray  # int64 [l,2] (n0<n1) edges seen once, phys 1
+    phys: int = 0
+
+    def idx(self, ids):
+        lut = {int(n): i for i, n in enumerate(self.node_ids)}
+        return np.vectorize(lut.__getitem__)(np.asarray(ids))
+
+
+def extract_surface_mesh(mesh: Mesh, surface_tag: int) -> PortSurface:  # src/ports/wave_port.cpp:54-112
+    sel = np.nonzero(mesh.tri_phys == surface_tag)[0]
+    order, seen = [], set()
+    for t in sel:
+        for nid in mesh.tri_conn[t]:
+            if int(nid) not in seen:
+                seen.add(int(nid))
+                order.append(int(nid))
+    node_ids = np.array(order, dtype=np.int64)
+    xy = mesh.xyz[mesh.node_idx_of(node_ids)][:, :2] if node_ids.size else np.zeros((0, 2))
+    cnt: Dict[Tuple[int, int], int] = {}
+    for t in sel:
+        c = mesh.tri_conn[t]
+        for e in range(3):
+            a, b = int(c[e]), int(c[(e + 1) % 3])
+            k = (min(a, b), max(a, b))
+            cnt[k] = cnt.get(k, 0) + 1
+    bl = np.array(sorted(k for k, v in cnt.items() if v == 1), dtype=np.int64).reshape(-1, 2)
+    return PortSurface(node_ids, xy, mesh.tri_conn[sel].copy(), sel.astype(np.int64), bl, int(surface_tag) if sel.size else 0)
+
+
+def _tri_shape(xy3: np.ndarray):
+    """P1 gradients (rows = nodes, cols = d/dx, d/dy) = columns 1..2 of inv([[1,x,y]]) and |area| (port_eigensolve.cpp:139-146)."""
+    C = np.column_stack([np.ones(3), xy3[:, 0], xy3[:, 1]])
+    return np.linalg.inv(C)[1:3, :].T.copy(), 0.5 * abs(np.linalg.det(C))
+
+
+def solve_port_eigens(surf: PortSurface, num_modes: int, omega: float, eps_r: complex, mu_r: complex, tm: bool = False):
+    """src/ports/port_eigensolve.cpp:97-275.  Returns list of (PortMode, field[n]).  Sign: largest sample positive."""
+    if surf.tri_conn.shape[0] == 0:
+        raise RuntimeError("Port eigensolver requires a 2D mesh.")
+    if omega == 0.0:
+        raise RuntimeError("Port eigensolver requires non-zero frequency.")
+    import scipy.linalg as sla
+
+    nn = surf.node_ids.size
+    pec = np.zeros(nn, dtype=bool)
+    if tm and surf.boundary_lines.size:
+        pec[surf.idx(surf.boundary_lines.reshape(-1))] = True
+    dof = np.full(nn, -1)
+    dof[~pec] = np.arange(int((~pec).sum()))
+    nd = int((~pec).sum())
+    A = np.zeros((nd, nd))
+    B = np.zeros((nd, nd))
+    tri_idx = surf.idx(surf.tri_conn)
+    shapes = [_tri_shape(surf.xy[tri_idx[t]]) for t in range(tri_idx.shape[0])]
+    for t in range(tri_idx.shape[0]):
+        G, area = shapes[t]
+        ke = area * G @ G.T
+        me = (area / 12.0) * (np.ones((3, 3)) + np.eye(3))
+        d = dof[tri_idx[t]]
+        for i in range(3):
+            for j in range(3):
+                if d[i] >= 0 and d[j] >= 0:
+                    A[d[i], d[j]] += ke[i, j]
+                    B[d[i], d[j]] += me[i, j]
+    w, V = sla.eigh(A, B)
+    eps, mu = EPS0 * eps_r, MU0 * mu_r
+    k = omega * np.sqrt(complex(mu * eps))
+    out = []
+    # reference: `kc2 < 1e-12` (port_eigensolve.cpp:201).  The TE null mode lands at ~1e-16*lambda_max from a dense
+    # eigen-solver, above or below that absolute constant depending on the solver; both sides of the parity test use
+    # the scale-aware cut max(1e-12, 1e-9*lambda_max) so the null mode is always dropped.
+    null_cut = max(1e-12, 1e-9 * float(np.max(np.abs(w[np.isfinite(w)]))))
+    for i in range(nd):
+        kc2 = float(w[i])
+        if not np.isfinite(kc2) or kc2 < null_cut:
+            continue
+        kc = np.sqrt(kc2)
+        m = PortMode()
+        m.pol = 1 if tm else 0
+        m.fc, m.kc, m.omega, m.eps, m.mu = kc * C0 / (2 * np.pi), kc, omega, eps, mu
+        beta = np.sqrt(complex(k * k - kc2))
+        m.beta = beta
+        m.Z0 = 0.0 if beta == 0 else ((omega * mu / beta) if not tm else (beta / (omega * eps)))
+        f = np.zeros(nn, dtype=np.complex128)
+        f[~pec] = V[:, i]
+        if f[np.argmax(np.abs(f))].real < 0:
+            f = -f
+        power = 0.0 + 0.0j
+        for t in range(tri_idx.shape[0]):
+            G, area = shapes[t]
+            g = G.T @ f[tri_idx[t]]
+            if not tm:
+                fe, fh = 1j * omega * mu / kc2, beta / kc2
+                Ex, Ey, Hx, Hy = -fe * g[1], fe * g[0], fh * g[0], fh * g[1]
+            else:
+                fe, fh = -beta / kc2, 1.0 / (1j * omega * mu)
+                Ex, Ey, Hx, Hy = fe * g[0], fe * g[1], -fh * g[1], fh * g[0]
+            power += 0.5 * area * (Ex * np.conj(Hy) - Ey * np.conj(Hx))
+        pr = power.real if power.real > 0 else abs(power)
+        if pr <= 0:
+            continue
+        out.append((m, f / np.sqrt(pr)))
+        if len(out) >= num_modes:
+            break
+    out.sort(key=lambda mf: mf[0].fc)
+    return out[:num_modes]
+
+
+def populate_te10_field(surf: PortSurface, a: float, b: float, mode: PortMode) -> np.ndarray:  # wave_port.cpp:214-262
+    x = surf.xy[:, 0] - surf.xy[:, 0].min()
+    A_sq = 4.0 * mode.kc ** 4 * a / (mode.omega * np.real(mode.mu) * np.real(mode.beta) * np.pi ** 2 * b)
+    return (np.cos(np.pi * x / a) * np.sqrt(A_sq)).astype(np.complex128)
+
+
+def build_wave_port(mesh: Mesh, surf: PortSurface, mode: PortMode, fld: np.ndarray) -> WavePort:  # wave_port.cpp:114-212
+    if fld.size != surf.node_ids.size:
+        raise RuntimeError("Port mode field size does not match surface mesh nodes")
+    accum: Dict[int, complex] = {}
+    counts: Dict[int, int] = {}
+    normal = 0.0
+    tri_idx = surf.idx(surf.tri_conn)
+    for t in range(tri_idx.shape[0]):
+        G, _ = _tri_shape(surf.xy[tri_idx[t]])
+        g = G.T @ fld[tri_idx[t]]
+        if mode.kc == 0.0:
+            raise RuntimeError("Port mode has zero cutoff wavenumber")
+        if mode.pol == 0:
+            f = 1j * mode.omega * mode.mu / (mode.kc ** 2)
+            Ex, Ey = f * g[1], -f * g[0]
+        else:
+            f = -mode.beta / (mode.kc ** 2)
+            Ex, Ey = f * g[0], f * g[1]
+        vt = int(surf.volume_tri_indices[t])
+        P = mesh.xyz[mesh.node_idx_of(mesh.tri_conn[vt])]
+        normal += np.cross(P[1] - P[0], P[2] - P[0])[2]
+        for e in range(3):
+            ei = int(mesh.tri_edges[vt, e])
+            pa, pb = mesh.xyz[mesh.node_idx_of(mesh.edges[ei])]
+            ev = pb - pa
+            accum[ei] = accum.get(ei, 0.0) + Ex * ev[0] + Ey * ev[1]
+            counts[ei] = counts.get(ei, 0) + 1
+    sign = 1.0 if normal >= 0 else -1.0
+    edges = sorted(accum)
+    port = WavePort()
+    port.surface_tag = surf.phys
+    port.mode = mode
+    port.edges = edges
+    port.weights = np.array([sign * accum[e] / counts[e] for e in edges], dtype=np.complex128)
+    return port
+
+
+def build_wave_port_from_eigenvector(mesh: Mesh, surf: PortSurface, ev: np.ndarray, mode: PortMode, pec: Set[int]) -> WavePort:
+    """src/ports/wave_port.cpp:264-309: weights = j * eigenvector on the port's free edges, ||w||^2 = sqrt(Re Z0)."""
+    edges = sorted({int(e) for t in surf.volume_tri_indices for e in mesh.tri_edges[int(t)]})
+    w = np.array([0.0 if e in pec else 1j * ev[e] for e in edges], dtype=np.complex128)
+    norm_sq = float(sum(ev[e] ** 2 for e in edges if e not in pec))
+    if norm_sq > 1e-15 and np.real(mode.Z0) > 1e-15:
+        w = w * np.sqrt(np.sqrt(np.real(mode.Z0)) / norm_sq)
+    port = WavePort()
+    port.surface_tag, port.mode, port.edges, port.weights = surf.phys, mode, edges, w
+    return port
+
+
+def straight_waveguide_sparams(a: float, length: float, freq: float):  # port_eigensolve.cpp:67-88 -> (s11, s21, s12, s22)
+    k, kc = 2 * np.pi * freq / C0, np.pi / a
+    if k <= kc:
+        return 1.0 + 0j, 0j, 0j, 1.0 + 0j
+    ph = np.exp(-1j * np.sqrt(k * k - kc * kc) * length)
+    return 0j, ph, ph, 0j
+
+
+def _g12(x: float) -> str:
+    """C++ ostream << double with setprecision(12) (default float field = %g)."""
+    return "%.12g" % x
+
+
+def touchstone_nport_text(freq, S_list, fmt: str = "RI", z0: float = 50.0) -> str:  # src/io/touchstone.cpp:65-139
+    def val(v):
+        if fmt == "RI":
+            return _g12(v.real) + " " + _g12(v.imag)
+        ang = np.angle(v) * 180.0 / np.pi
+        if fmt == "MA":
+            return _g12(abs(v)) + " " + _g12(ang)
+        return _g12(20.0 * np.log10(max(abs(v), 1e-20))) + " " + _g12(ang)
+
+    n = S_list[0].shape[0]
+    out = ["! Touchstone file generated by EdgeFEM\n", "! Number of ports: %d\n" % n, "# Hz S %s R %s\n" % (fmt, _g12(z0))]
+    for f, S in zip(freq, S_list):
+        line = _g12(f)
+        cnt = 0
+        for i in range(n):
+            for j in range(n):
+                if n > 2 and cnt > 0 and cnt % 4 == 0:
+                    line += "\n"
+                line += " " + val(complex(S[i, j]))
+                cnt += 1
+        out.append(line + "\n")
+    return "".join(out)
+
+
+def touchstone_legacy_text(freq, sp) -> str:  # src/io/touchstone.cpp:50-62; sp = list of (s11, s21, s12, s22)
+    out = ["# Hz S RI R 50\n"]
+    for f, s in zip(freq, sp):
+        out.append(" ".join([_g12(f)] + [_g12(x) for v in s for x in (complex(v).real, complex(v).imag)]) + "\n")
+    return "".join(out)

@@ -294,3 +294,29 @@ def test_km_and_frequency_sweep():
     for fi in range(3):
         assert np.max(np.abs(sw2.S_matrices[fi] - S_o2[fi])) <= 1e-6
     assert len(pe.frequency_sweep(hm, ph, bc, [], freqs).S_matrices) == 0  # src/sweep.cpp:183-185
+
+
+def test_calculate_sparams_modal_line_integral_ports():
+    """SURVEY 8f-f1 feeding the path: ports built by extract_surface_mesh + solve_port_eigens (nodal TE mode) +
+    build_wave_port, then the dense-port-block path calculate_sparams on the device vs the oracle with ITS OWN
+    restatement of the same builders."""
+    hm, om = both_meshes("rect_waveguide")
+    bc = pe.build_edge_pec(hm, 1)
+    pec = orc.build_edge_pec(om, 1)
+    omega = 2 * math.pi * 10e9
+    ports_h, ports_o = [], []
+    for tag in (2, 3):
+        hs, os_ = pe.extract_surface_mesh(hm, tag), orc.extract_surface_mesh(om, tag)
+        hmode = pe.solve_port_eigens(hs.mesh, 1, omega, 1.0, 1.0, pe.ModePolarization.TE)[0]
+        omode, ofld = orc.solve_port_eigens(os_, 1, omega, 1.0, 1.0)[0]
+        ports_h.append(pe.build_wave_port(hm, hs, hmode))
+        ports_o.append(orc.build_wave_port(om, os_, omode, ofld))
+        wh, wo = np.asarray(ports_h[-1].weights), ports_o[-1].weights
+        assert list(ports_h[-1].edges) == ports_o[-1].edges
+        assert np.max(np.abs(wh - wo)) <= 1e-7 * np.max(np.abs(wo))
+    po = orc.MaxwellParams(omega=omega)
+    ph = make_params(po)
+    check_assembly(hm, om, ph, po, bc, pec, ports_h, ports_o, active=0, tol=1e-9)  # port block follows the 1e-7 weights
+    S_h = pe.calculate_sparams(hm, ph, bc, ports_h)
+    S_o = orc.calculate_sparams(om, po, pec, ports_o)
+    assert np.max(np.abs(S_h - S_o)) <= 1e-5 * max(1.0, np.max(np.abs(S_o)))
