@@ -441,36 +441,6 @@ static int system_alloc_common(System *S) {
     }
   });
   if ((rc = dev_upload(c, &S->d_diag_pos, diag.data(), diag.size()))) return rc;
-  if (S->m <= 16384 && S->m == S->m_global) {  // SELL-32 structure (only systems small enough for the persistent one-CTA solver)
-    std::vector<int32_t> order(S->m);
-    for (int r = 0; r < S->m; ++r) order[r] = r;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-      return (S->h_rowptr[a + 1] - S->h_rowptr[a]) > (S->h_rowptr[b + 1] - S->h_rowptr[b]);
-    });
-    const int ns = (S->m + 31) / 32;
-    std::vector<int32_t> sptr((size_t)ns + 1, 0), perm((size_t)ns * 32, -1);
-    for (int i = 0; i < S->m; ++i) perm[i] = order[i];
-    for (int sl = 0; sl < ns; ++sl) {
-      int w = 0;
-      for (int l = 0; l < 32; ++l) {
-        const int r = perm[(size_t)sl * 32 + l];
-        if (r >= 0) w = std::max(w, S->h_rowptr[r + 1] - S->h_rowptr[r]);
-      }
-      sptr[sl + 1] = sptr[sl] + 32 * w;
-    }
-    std::vector<int32_t> scol((size_t)sptr[ns], 0);
-    for (int sl = 0; sl < ns; ++sl)
-      for (int l = 0; l < 32; ++l) {
-        const int r = perm[(size_t)sl * 32 + l];
-        if (r < 0) continue;
-        for (int k = S->h_rowptr[r], j = 0; k < S->h_rowptr[r + 1]; ++k, ++j) scol[(size_t)sptr[sl] + (size_t)j * 32 + l] = S->h_colidx[k];
-      }
-    S->n_slices = ns;
-    S->sell_total = sptr[ns];
-    if ((rc = dev_upload(c, &S->d_sell_ptr, sptr.data(), sptr.size()))) return rc;
-    if ((rc = dev_upload(c, &S->d_sell_col, scol.data(), scol.size()))) return rc;
-    if ((rc = dev_upload(c, &S->d_sell_perm, perm.data(), perm.size()))) return rc;
-  }
   {  // CSR-stream chunks: consecutive whole rows with <= SPMV_STREAM_W entries per warp
     std::vector<int32_t> ch{0};
     bool ok = true;
@@ -504,10 +474,105 @@ static int system_alloc_common(System *S) {
   return EFB_OK;
 }
 
+}  // extern "C"
+
+// Host build of the persistent small-system solver's structures (see System): compact numbering of the free
+// unknowns, SELL-32 pattern over them, compact gradient lists.  Cheap (m <= 16384), runs once per system state.
+int efb::build_small_structs(System *S) {
+  Ctx *c = S->ctx;
+  const int m = S->m;
+  cudaStreamSynchronize(c->stream);
+  dfree(S->d_sell_ptr); dfree(S->d_sell_col); dfree(S->d_sell_src); dfree(S->d_sell_perm); dfree(S->d_sell_vals);
+  dfree(S->d_c_orig); dfree(S->d_c_edge_nodes); dfree(S->d_c_n2e_ptr); dfree(S->d_c_n2e_item);
+  S->d_sell_ptr = S->d_sell_col = S->d_sell_src = S->d_sell_perm = nullptr;
+  S->d_sell_vals = nullptr;
+  S->d_c_orig = nullptr; S->d_c_edge_nodes = nullptr; S->d_c_n2e_ptr = nullptr; S->d_c_n2e_item = nullptr;
+  const bool have_dir = (int)S->h_dir.size() == m;
+  auto is_dir = [&](int e) { return have_dir && S->h_dir[e] != 0; };
+  std::vector<int32_t> orig, comp((size_t)m, -1);
+  orig.reserve(m);
+  for (int r = 0; r < m; ++r)
+    if (!is_dir(r)) {
+      comp[r] = (int32_t)orig.size();
+      orig.push_back(r);
+    }
+  const int mc = (int)orig.size();
+  S->m_c = mc;
+  std::vector<int32_t> len((size_t)mc, 0);
+  for (int i = 0; i < mc; ++i) {
+    const int r = orig[i];
+    for (int k = S->h_rowptr[r]; k < S->h_rowptr[r + 1]; ++k) len[i] += !is_dir(S->h_colidx[k]);
+  }
+  std::vector<int32_t> order((size_t)mc);
+  for (int i = 0; i < mc; ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return len[a] > len[b]; });
+  const int ns = (mc + 31) / 32;
+  std::vector<int32_t> sptr((size_t)ns + 1, 0), perm((size_t)std::max(ns, 1) * 32, -1);
+  for (int i = 0; i < mc; ++i) perm[i] = order[i];
+  for (int sl = 0; sl < ns; ++sl) {
+    int w = 0;
+    for (int l = 0; l < 32; ++l) {
+      const int i = perm[(size_t)sl * 32 + l];
+      if (i >= 0) w = std::max(w, len[i]);
+    }
+    sptr[sl + 1] = sptr[sl] + 32 * w;
+  }
+  std::vector<int32_t> scol((size_t)std::max(sptr[ns], 1), 0), ssrc((size_t)std::max(sptr[ns], 1), -1);
+  for (int sl = 0; sl < ns; ++sl)
+    for (int l = 0; l < 32; ++l) {
+      const int i = perm[(size_t)sl * 32 + l];
+      if (i < 0) continue;
+      const int r = orig[i];
+      int j = 0;
+      for (int k = S->h_rowptr[r]; k < S->h_rowptr[r + 1]; ++k) {
+        const int cc = S->h_colidx[k];
+        if (is_dir(cc)) continue;
+        scol[(size_t)sptr[sl] + (size_t)j * 32 + l] = comp[cc];
+        ssrc[(size_t)sptr[sl] + (size_t)j * 32 + l] = k;
+        ++j;
+      }
+    }
+  S->n_slices = ns;
+  S->sell_total = sptr[ns];
+  int rc;
+  if ((rc = dev_upload(c, &S->d_c_orig, orig.data(), (size_t)std::max(mc, 1)))) return rc;
+  if ((rc = dev_upload(c, &S->d_sell_ptr, sptr.data(), sptr.size()))) return rc;
+  if ((rc = dev_upload(c, &S->d_sell_col, scol.data(), scol.size()))) return rc;
+  if ((rc = dev_upload(c, &S->d_sell_src, ssrc.data(), ssrc.size()))) return rc;
+  if ((rc = dev_upload(c, &S->d_sell_perm, perm.data(), perm.size()))) return rc;
+  if (S->n_node > 0 && (int)S->h_edge_nodes.size() == 2 * m) {
+    const int nn = S->n_node;
+    std::vector<int32_t> ptr((size_t)nn + 1, 0), item((size_t)std::max(2 * mc, 1));
+    std::vector<int2> en((size_t)std::max(mc, 1));
+    for (int i = 0; i < mc; ++i) {
+      const int a = S->h_edge_nodes[2 * (size_t)orig[i]], b = S->h_edge_nodes[2 * (size_t)orig[i] + 1];
+      en[i] = make_int2(a, b);
+      ptr[a + 1]++;
+      ptr[b + 1]++;
+    }
+    for (int n = 0; n < nn; ++n) ptr[n + 1] += ptr[n];
+    std::vector<int32_t> cur(ptr.begin(), ptr.end() - 1);
+    for (int i = 0; i < mc; ++i) {
+      item[cur[en[i].x]++] = (i << 1);      // tail: G = -1
+      item[cur[en[i].y]++] = (i << 1) | 1;  // head: G = +1
+    }
+    if ((rc = dev_upload(c, &S->d_c_edge_nodes, en.data(), en.size()))) return rc;
+    if ((rc = dev_upload(c, &S->d_c_n2e_ptr, ptr.data(), ptr.size()))) return rc;
+    if ((rc = dev_upload(c, &S->d_c_n2e_item, item.data(), item.size()))) return rc;
+  }
+  EFB_CUDA(c, cudaStreamSynchronize(c->stream));  // the host vectors above are locals
+  S->small_dirty = false;
+  return EFB_OK;
+}
+
+extern "C" {
+
 static int system_set_gradient(System *S, int n_node, const int32_t *edge_nodes) {
   Ctx *c = S->ctx;
   int rc;
   S->n_node = n_node;
+  S->h_edge_nodes.assign(edge_nodes, edge_nodes + 2 * (size_t)S->m);
+  S->small_dirty = true;
   cudaStreamSynchronize(c->stream);  // blocks go back to a pool shared by every context on the device
   dfree(S->d_edge_nodes); dfree(S->d_n2e_ptr); dfree(S->d_n2e_item); dfree(S->d_node_dir);
   S->d_edge_nodes = nullptr; S->d_n2e_ptr = nullptr; S->d_n2e_item = nullptr; S->d_node_dir = nullptr;
@@ -732,7 +797,8 @@ void efb_system_destroy(efb_system *sys_) {
   solver_free(S);
   dfree(S->d_rowptr); dfree(S->d_colidx); dfree(S->d_diag_pos); dfree(S->d_vals);
   dfree(S->d_b); dfree(S->d_x); dfree(S->d_dir_all); dfree(S->d_e2t_pos); dfree(S->d_chunk_row); dfree(S->d_sp_chunk);
-  dfree(S->d_sell_ptr); dfree(S->d_sell_col); dfree(S->d_sell_perm); dfree(S->d_sell_vals);
+  dfree(S->d_sell_ptr); dfree(S->d_sell_col); dfree(S->d_sell_perm); dfree(S->d_sell_vals); dfree(S->d_sell_src);
+  dfree(S->d_c_orig); dfree(S->d_c_edge_nodes); dfree(S->d_c_n2e_ptr); dfree(S->d_c_n2e_item);
   dfree(S->d_edge_nodes); dfree(S->d_n2e_ptr); dfree(S->d_n2e_item); dfree(S->d_node_dir);
   dfree(S->d_mat_blob);
   delete S;
@@ -785,6 +851,8 @@ int efb_system_set_dirichlet(efb_system *sys_, const uint8_t *flags) {
   // flags cover ALL edges of the mesh (m_global entries): rows read the local slice, columns the whole array
   EFB_CUDA(c, cudaMemcpyAsync(S->d_dir_all, flags, (size_t)S->m_global, cudaMemcpyHostToDevice, c->stream));
   S->has_dir = true;
+  S->h_dir.assign(flags + S->row0, flags + S->row0 + S->m);
+  S->small_dirty = true;
   if (S->d_e2t_pos && S->mesh) {
     k_pos_dirichlet<<<(S->m + 127) / 128, 128, 0, c->stream>>>(S->mesh->d_e2t_ptr + S->row0, S->d_rowptr, S->d_colidx, S->d_dir_all, S->m,
                                                                S->d_e2t_pos, (long long)S->mesh->h_e2t_ptr[S->row0] * 6);

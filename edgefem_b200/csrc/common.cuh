@@ -121,14 +121,26 @@ struct System {
   // CSR-stream SpMV: row-aligned chunks of <= SPMV_STREAM_W entries (one warp each); null if a row is longer
   int32_t *d_sp_chunk = nullptr;   // [n_sp_chunks+1]
   int n_sp_chunks = 0;
-  // SELL-32 copy of the pattern for the persistent small-system solver: rows sorted by length (desc),
-  // slices of 32 rows stored column-major and padded to the slice's longest row
+  // Structures of the persistent small-system solver (built lazily by build_small_structs, rebuilt when the
+  // Dirichlet flags or the gradient change).  The solver works on the FREE unknowns only: Dirichlet rows are identity
+  // rows (x_e = b_e / A_ee) and Dirichlet columns hold explicit zeros, so both are dropped -- "compact" ids number
+  // the free edges in ascending original order.  SELL-32 copy of the compact pattern: rows sorted by length (desc),
+  // slices of 32 rows stored column-major and padded to the slice's longest row.
+  bool small_dirty = true;
+  int m_c = 0;                     // free unknowns
+  int32_t *d_c_orig = nullptr;     // [m_c] compact id -> original edge id
+  int2 *d_c_edge_nodes = nullptr;  // [m_c] (tail, head) node of the compact edge
+  int32_t *d_c_n2e_ptr = nullptr;  // [n_node+1]
+  int32_t *d_c_n2e_item = nullptr; // [<=2 m_c]  compact edge << 1 | (1 if the node is the head (+1) else 0 (-1))
   int32_t *d_sell_ptr = nullptr;   // [n_slices+1] entry offsets (multiples of 32)
-  int32_t *d_sell_col = nullptr;   // [sell_total] column of every slot (0 for padding)
-  int32_t *d_sell_perm = nullptr;  // [n_slices*32] original row of every SELL row (-1 for padding rows)
+  int32_t *d_sell_col = nullptr;   // [sell_total] compact column of every slot (0 for padding)
+  int32_t *d_sell_src = nullptr;   // [sell_total] CSR position the slot's value comes from (-1 for padding)
+  int32_t *d_sell_perm = nullptr;  // [n_slices*32] compact row of every SELL row (-1 for padding rows)
   c128 *d_sell_vals = nullptr;     // [n_matrix][sell_total] (lazy)
   int n_slices = 0;
   long long sell_total = 0;
+  std::vector<uint8_t> h_dir;         // host copy of the Dirichlet flags of the local rows (empty: none set)
+  std::vector<int32_t> h_edge_nodes;  // host copy of the gradient (2 per edge; empty: none set)
   cudaEvent_t ev_s0 = nullptr, ev_s1 = nullptr;  // around the persistent solver kernel
   bool small_timed = false;
   // gradient (aux preconditioner)
@@ -251,6 +263,7 @@ struct Timed {  // records CUDA events around a compute call on the ctx stream
 
 // internal entry points shared across translation units
 int solver_free(System *s);
+int build_small_structs(System *s);  // abi.cu
 void dist_free(System *s);
 int assemble_launch(System *s, int first, int count, int mode);
 int launch_tet_geometry(Mesh *m);

@@ -609,11 +609,15 @@ template <int NR, int NT, int SPD, bool DB, int MINB = 1>
 __global__ void __launch_bounds__(NT, MINB)
 k_cocg_small(SolveDev D, const int32_t *__restrict__ sell_ptr, const int32_t *__restrict__ sell_col, const int32_t *__restrict__ sell_perm,
              const c128 *__restrict__ sell_vals, long long sell_total, int n_slices, int first_matrix, int n_jobs, int groups_per_matrix,
-             int *job_counter, const c128 *__restrict__ bvec, c128 *xvec, c128 *rvec, c128 *qvec, int aux, int zero_x, int max_restarts) {
+             int *job_counter, const c128 *__restrict__ bvec, c128 *xvec, c128 *rvec, c128 *qvec, int aux, int zero_x, int max_restarts,
+             int mc, const int32_t *__restrict__ c_orig, const int2 *__restrict__ c_edge_nodes, const int32_t *__restrict__ c_n2e_ptr,
+             const int32_t *__restrict__ c_n2e_item) {
+  // The solver runs on the mc FREE unknowns ("compact" ids, c_orig maps them to edge ids): r, q, p and the SELL
+  // structure are compact, b, x, dinv keep the original layout (stride m).
   extern __shared__ __align__(16) unsigned char sm_raw[];
   const int m = D.m, nn = aux ? D.n_node : 0;
-  c128 *p_s = (c128 *)sm_raw;                 // [NR][m]
-  c128 *w_s = p_s + (size_t)NR * m;           // [NR][nn]
+  c128 *p_s = (c128 *)sm_raw;                 // [NR][mc]
+  c128 *w_s = p_s + (size_t)NR * mc;          // [NR][nn]
   double *red = (double *)(w_s + (size_t)NR * nn);  // [33*8]
   __shared__ int s_job;
   const int tid = threadIdx.x, nth = blockDim.x;
@@ -650,6 +654,14 @@ k_cocg_small(SolveDev D, const int32_t *__restrict__ sell_ptr, const int32_t *__
 #pragma unroll
     for (int r = 0; r < NR; ++r) { iters[r] = 0; act[r] = false; conv[r] = false; }
     if (tid < 8 * NR) sc_bb[tid] = 0.0;
+    // Dirichlet rows are decoupled identity rows: x_e = b_e / A_ee, once
+    if (mc < m)
+      for (int e = tid; e < m; e += nth)
+        if (D.dir[e]) {
+          const c128 de = __ldg(&dinv[e]);
+#pragma unroll
+          for (int r = 0; r < NR; ++r) xg[r][e] = cmul(de, bg[r][e]);
+        }
     __syncthreads();
 
     // q = A * (vector in p_s), optional dot p.q.  SELL-32: a lane owns a row, 32 rows form a slice stored
@@ -697,20 +709,20 @@ k_cocg_small(SolveDev D, const int32_t *__restrict__ sell_ptr, const int32_t *__
 #pragma unroll
           for (int u = 0; u < 4; ++u)
 #pragma unroll
-            for (int r = 0; r < NR; ++r) acc[r] = cfma(a4[u], p_s[(size_t)r * m + c4[u]], acc[r]);
+            for (int r = 0; r < NR; ++r) acc[r] = cfma(a4[u], p_s[(size_t)r * mc + c4[u]], acc[r]);
         }
         for (; j < width; ++j) {
           const c128 a = ldg_stream(vp + 32 * j);
           const int c = ldg_stream(cp + 32 * j);
 #pragma unroll
-          for (int r = 0; r < NR; ++r) acc[r] = cfma(a, p_s[(size_t)r * m + c], acc[r]);
+          for (int r = 0; r < NR; ++r) acc[r] = cfma(a, p_s[(size_t)r * mc + c], acc[r]);
         }
         if (row >= 0) {
 #pragma unroll
           for (int r = 0; r < NR; ++r) {
             qg[r][row] = acc[r];
             if (want_dot) {
-              const c128 t = cmul(p_s[(size_t)r * m + row], acc[r]);
+              const c128 t = cmul(p_s[(size_t)r * mc + row], acc[r]);
               dots[2 * r] += t.x; dots[2 * r + 1] += t.y;
             }
           }
@@ -737,7 +749,7 @@ k_cocg_small(SolveDev D, const int32_t *__restrict__ sell_ptr, const int32_t *__
           for (int r = 0; r < NR; ++r) {
             qg[r][row] = acc[r];
             if (want_dot) {
-              const c128 t = cmul(p_s[(size_t)r * m + row], acc[r]);
+              const c128 t = cmul(p_s[(size_t)r * mc + row], acc[r]);
               dots[2 * r] += t.x; dots[2 * r + 1] += t.y;
             }
           }
@@ -784,7 +796,7 @@ k_cocg_small(SolveDev D, const int32_t *__restrict__ sell_ptr, const int32_t *__
           const int st = step + u;
           if (st < step_end) {
 #pragma unroll
-            for (int r = 0; r < NR; ++r) acc[r] = cfma(a0[u], p_s[(size_t)r * m + c0[u]], acc[r]);
+            for (int r = 0; r < NR; ++r) acc[r] = cfma(a0[u], p_s[(size_t)r * mc + c0[u]], acc[r]);
             while (sl < s_hi && next_b == st + 1) flush();
           }
         }
@@ -817,28 +829,34 @@ k_cocg_small(SolveDev D, const int32_t *__restrict__ sell_ptr, const int32_t *__
       // (1) true residual r = b - A x from the current iterate
       double d4[2 * NR];
       if (cycle == 0 && zero_x) {
-        for (int i = tid; i < m; i += nth)
+        for (int i = tid; i < mc; i += nth) {
+          const int e = __ldg(&c_orig[i]);
 #pragma unroll
-          for (int r = 0; r < NR; ++r) { xg[r][i] = cmake(0.0, 0.0); qg[r][i] = cmake(0.0, 0.0); }
+          for (int r = 0; r < NR; ++r) { xg[r][e] = cmake(0.0, 0.0); qg[r][i] = cmake(0.0, 0.0); }
+        }
       } else {
-        for (int i = tid; i < m; i += nth)
+        for (int i = tid; i < mc; i += nth) {
+          const int e = __ldg(&c_orig[i]);
 #pragma unroll
-          for (int r = 0; r < NR; ++r) p_s[(size_t)r * m + i] = xg[r][i];
+          for (int r = 0; r < NR; ++r) p_s[(size_t)r * mc + i] = xg[r][e];
+        }
         __syncthreads();
         spmv(false, d4);
       }
       __syncthreads();
 #pragma unroll
       for (int k = 0; k < 2 * NR; ++k) d4[k] = 0.0;
-      for (int i = tid; i < m; i += nth)
+      for (int i = tid; i < mc; i += nth) {
+        const int e = __ldg(&c_orig[i]);
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
-          const c128 bi = bg[r][i];
+          const c128 bi = bg[r][e];
           const c128 ri = csub(bi, qg[r][i]);
           rg[r][i] = ri;
           d4[2 * r] += cabs2(ri);
           d4[2 * r + 1] += cabs2(bi);
         }
+      }
       block_allreduce<2 * NR>(d4, red);
       bool any = false;
 #pragma unroll
@@ -863,14 +881,13 @@ k_cocg_small(SolveDev D, const int32_t *__restrict__ sell_ptr, const int32_t *__
           const int l16 = tid & 15, g16 = tid >> 4, ng16 = nth >> 4;
           const unsigned hmask = 0xffffu << (((tid & 31) >> 4) * 16);
           for (int n = g16; n < nn; n += ng16) {
-            const int kb = __ldg(&D.n2e_ptr[n]), ke = __ldg(&D.n2e_ptr[n + 1]);
+            const int kb = __ldg(&c_n2e_ptr[n]), ke = __ldg(&c_n2e_ptr[n + 1]);
             c128 a2[NR];
 #pragma unroll
             for (int r = 0; r < NR; ++r) a2[r] = cmake(0.0, 0.0);
             for (int k = kb + l16; k < ke; k += 16) {
-              const int it = __ldg(&D.n2e_item[k]);
-              if (it & 2) continue;  // Dirichlet edge
-              const int e = it >> 2;
+              const int it = __ldg(&c_n2e_item[k]);  // compact edge << 1 | head (Dirichlet edges are not in the lists)
+              const int e = it >> 1;
 #pragma unroll
               for (int r = 0; r < NR; ++r) {
                 const c128 v = rg[r][e];
@@ -895,11 +912,11 @@ k_cocg_small(SolveDev D, const int32_t *__restrict__ sell_ptr, const int32_t *__
         double dz[3 * NR];
 #pragma unroll
         for (int k = 0; k < 3 * NR; ++k) dz[k] = 0.0;
-        for (int e = tid; e < m; e += nth) {
-          const c128 di = __ldg(&dinv[e]);
+        for (int e = tid; e < mc; e += nth) {
+          const c128 di = __ldg(&dinv[__ldg(&c_orig[e])]);
           int2 ab = make_int2(0, 0);
-          const bool g = aux && !D.dir[e];
-          if (g) ab = D.edge_nodes[e];
+          const bool g = aux != 0;
+          if (g) ab = __ldg(&c_edge_nodes[e]);
 #pragma unroll
           for (int r = 0; r < NR; ++r) {
             const c128 ri = rg[r][e];
@@ -932,11 +949,11 @@ k_cocg_small(SolveDev D, const int32_t *__restrict__ sell_ptr, const int32_t *__
         }
         par ^= 1;
         if (!still) break;
-        for (int e = tid; e < m; e += nth)
+        for (int e = tid; e < mc; e += nth)
 #pragma unroll
           for (int r = 0; r < NR; ++r) {
             const c128 z = qg[r][e];
-            p_s[(size_t)r * m + e] = fresh ? z : cfma(beta[r], p_s[(size_t)r * m + e], z);
+            p_s[(size_t)r * mc + e] = fresh ? z : cfma(beta[r], p_s[(size_t)r * mc + e], z);
           }
         fresh = false;
         __syncthreads();
@@ -955,13 +972,15 @@ k_cocg_small(SolveDev D, const int32_t *__restrict__ sell_ptr, const int32_t *__
           if (act[r]) iters[r] += 1;
         }
         // x += alpha p ; r -= alpha q   (|r|^2 is accumulated by the next preconditioner pass)
-        for (int i = tid; i < m; i += nth)
+        for (int i = tid; i < mc; i += nth) {
+          const int e = __ldg(&c_orig[i]);
 #pragma unroll
           for (int r = 0; r < NR; ++r) {
             if (!act[r]) continue;
-            xg[r][i] = cfma(alpha[r], p_s[(size_t)r * m + i], xg[r][i]);
+            xg[r][e] = cfma(alpha[r], p_s[(size_t)r * mc + i], xg[r][e]);
             rg[r][i] = cfma(cneg(alpha[r]), qg[r][i], rg[r][i]);
           }
+        }
         bool any2 = false;
 #pragma unroll
         for (int r = 0; r < NR; ++r) any2 |= act[r];
@@ -983,23 +1002,17 @@ k_cocg_small(SolveDev D, const int32_t *__restrict__ sell_ptr, const int32_t *__
   }
 }
 
-// vals (CSR order) -> SELL-32 order, zero padding; grid (slices, matrices), 256 threads
-__global__ void k_csr_to_sell(const c128 *__restrict__ vals, long long nnz, const int32_t *__restrict__ rowptr,
-                              const int32_t *__restrict__ sell_ptr, const int32_t *__restrict__ sell_perm, c128 *__restrict__ sell_vals,
-                              long long sell_total, int first_matrix) {
+// vals (CSR order) -> SELL-32 order of the compact pattern: a pure gather through the slot -> CSR position map
+// (-1 = padding); grid (slices, matrices), 256 threads
+__global__ void k_csr_to_sell(const c128 *__restrict__ vals, long long nnz, const int32_t *__restrict__ sell_ptr,
+                              const int32_t *__restrict__ sell_src, c128 *__restrict__ sell_vals, long long sell_total, int first_matrix) {
   const int sl = blockIdx.x, f = first_matrix + blockIdx.y;
   const int base = sell_ptr[sl], cnt = sell_ptr[sl + 1] - base;
   const c128 *__restrict__ src = vals + (size_t)f * nnz;
   c128 *dst = sell_vals + (size_t)f * sell_total + base;
   for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
-    const int l = i & 31, j = i >> 5;
-    const int row = sell_perm[sl * 32 + l];
-    c128 v = cmake(0.0, 0.0);
-    if (row >= 0) {
-      const int k = rowptr[row] + j;
-      if (k < rowptr[row + 1]) v = src[k];
-    }
-    dst[i] = v;
+    const int k = sell_src[base + i];
+    dst[i] = k >= 0 ? src[k] : cmake(0.0, 0.0);
   }
 }
 
@@ -1256,10 +1269,18 @@ static int run_cocg_small(SolvePlan &P, const efb_solve_opts *o, bool zero_x, bo
   const int nn = P.aux ? S->n_node : 0;
   int variant = 1;
   if (const char *v = getenv("EDGEFEM_B200_SMALL_VARIANT")) variant = atoi(v);
+  if (S->m > 16384 || S->m != S->m_global) return EFB_OK;  // large or row-partitioned: generic multi-kernel path
+  if (P.aux && (int)S->h_edge_nodes.size() != 2 * S->m) return EFB_OK;
+  if (S->small_dirty) {
+    int rcs = build_small_structs(S);
+    if (rcs) return rcs;
+  }
+  const int mc = S->m_c;
+  if (mc == 0) return EFB_OK;
   int nr = (S->n_rhs % 2 == 0) ? 2 : 1;
-  if (small_smem_bytes(nr, S->m, nn) > (size_t)dev_smem) nr = 1;
+  if (small_smem_bytes(nr, mc, nn) > (size_t)dev_smem) nr = 1;
   if (variant >= 4) nr = 1;  // one right-hand side per CTA, two CTAs per SM
-  const size_t smem = small_smem_bytes(nr, S->m, nn);
+  const size_t smem = small_smem_bytes(nr, mc, nn);
   if (smem > (size_t)dev_smem || !S->d_sell_ptr) return EFB_OK;  // system too large for one CTA: generic multi-kernel path
   if (!S->d_sell_vals) {
     int rc0 = dev_alloc(c, &S->d_sell_vals, (size_t)S->n_matrix * (size_t)S->sell_total);
@@ -1267,7 +1288,7 @@ static int run_cocg_small(SolvePlan &P, const efb_solve_opts *o, bool zero_x, bo
   }
   {
     dim3 g((unsigned)S->n_slices, (unsigned)P.n_matrix);
-    k_csr_to_sell<<<g, 256, 0, c->stream>>>(S->d_vals, (long long)S->nnz, S->d_rowptr, S->d_sell_ptr, S->d_sell_perm, S->d_sell_vals, S->sell_total, P.first_matrix);
+    k_csr_to_sell<<<g, 256, 0, c->stream>>>(S->d_vals, (long long)S->nnz, S->d_sell_ptr, S->d_sell_src, S->d_sell_vals, S->sell_total, P.first_matrix);
     EFB_CHECK_LAUNCH(c);
   }
   const int groups = S->n_rhs / nr;
@@ -1308,14 +1329,16 @@ static int run_cocg_small(SolvePlan &P, const efb_solve_opts *o, bool zero_x, bo
     EFB_CUDA(c, cudaFuncSetAttribute(k_cocg_small<NRV, NT, SPDV, DBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
     k_cocg_small<NRV, NT, SPDV, DBV><<<grid, NT, smem, c->stream>>>(P.D, S->d_sell_ptr, S->d_sell_col, S->d_sell_perm, S->d_sell_vals,    \
                                                                       S->sell_total, S->n_slices, P.first_matrix, n_jobs, groups, S->d_job, \
-                                                                      S->d_b, S->d_x, P.vec[V_R], P.vec[V_Q], P.aux ? 1 : 0, zero_x ? 1 : 0, mr); \
+                                                                      S->d_b, S->d_x, P.vec[V_R], P.vec[V_Q], P.aux ? 1 : 0, zero_x ? 1 : 0, mr, \
+                                                                      mc, S->d_c_orig, S->d_c_edge_nodes, S->d_c_n2e_ptr, S->d_c_n2e_item); \
   } while (0)
 #define EFB_SMALL_LAUNCH2(NRV, NT, SPDV, DBV)                                                                                             \
   do {                                                                                                                                    \
     EFB_CUDA(c, cudaFuncSetAttribute(k_cocg_small<NRV, NT, SPDV, DBV, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
     k_cocg_small<NRV, NT, SPDV, DBV, 2><<<grid, NT, smem, c->stream>>>(P.D, S->d_sell_ptr, S->d_sell_col, S->d_sell_perm, S->d_sell_vals, \
                                                                       S->sell_total, S->n_slices, P.first_matrix, n_jobs, groups, S->d_job, \
-                                                                      S->d_b, S->d_x, P.vec[V_R], P.vec[V_Q], P.aux ? 1 : 0, zero_x ? 1 : 0, mr); \
+                                                                      S->d_b, S->d_x, P.vec[V_R], P.vec[V_Q], P.aux ? 1 : 0, zero_x ? 1 : 0, mr, \
+                                                                      mc, S->d_c_orig, S->d_c_edge_nodes, S->d_c_n2e_ptr, S->d_c_n2e_item); \
   } while (0)
   if (nr == 2) {
     switch (variant) {
