@@ -194,6 +194,12 @@ class ResidentSweep:
         self.idx = [np.arange(self.F, dtype=np.int32) * self.P + a for a in range(self.P)]
         self.all_idx = np.arange(self.F * self.P, dtype=np.int32)
         self.nnz, self.m = self.sys.nnz, self.sys.m
+        # the persistent solver iterates on the FREE unknowns only (Dirichlet rows/columns dropped): its byte model
+        rp, ci = self.sys.pattern()
+        free = flags == 0
+        rows = np.repeat(np.arange(self.m), np.diff(rp))
+        self.m_free = int(free.sum())
+        self.nnz_free = int(np.count_nonzero(free[rows] & free[ci]))
         self.last = None
 
     def step(self):
@@ -350,15 +356,18 @@ def run_b200(a):
     # right-hand sides.  Algorithmic bytes per COCG iteration of one matrix with P rhs (B_spmv + 10*16*m per
     # system; the P systems of a matrix share the value/index stream): nnz*20 + 4m + P*(32m + 160m).
     F, P, nnz, m = rs.F, rs.P, rs.nnz, rs.m
+    nnz_f, m_f = rs.nnz_free, rs.m_free  # what the persistent kernel streams: entries / rows of the free unknowns
     ms_kernel = rs.sys.last_solve_kernel_ms()
     it_per_matrix = [max(iters[f * P:(f + 1) * P]) for f in range(F)]
     if ms_kernel > 0:
-        solve_bytes = float(sum(it_per_matrix)) * (nnz * 20.0 + 4.0 * m + P * 192.0 * m)
+        solve_bytes = float(sum(it_per_matrix)) * (nnz_f * 20.0 + 4.0 * m_f + P * 192.0 * m_f)
         roof = {"bound": "hbm", "kernel": "k_cocg_small<2> (persistent COCG + aux-space Jacobi, SELL-32 SpMV from smem-resident p; %d matrices x %d rhs in one launch)" % (F, P),
                 "achieved": solve_bytes / ms_kernel / 1e6, "peak": hbm_peak, "unit": "GB/s", "frac": solve_bytes / ms_kernel / 1e6 / hbm_peak,
                 "traffic": ncu_traffic("k_cocg_small", F), "peak_source": peak_src, "algorithmic_bytes_per_launch": solve_bytes, "ms_per_launch": ms_kernel,
                 "launches_per_step": 1, "share_of_step": ms_kernel / ms_step,
-                "note": "vectors r,q,x stay L2-resident per CTA and p lives in shared memory, so part of the algorithmic bytes never reaches HBM"}
+                "free_unknowns": m_f, "free_nnz": nnz_f,
+                "note": "byte model over the %d free unknowns / %d free entries the kernel iterates on (Dirichlet rows and columns are dropped); "
+                        "vectors r,q,x stay L2-resident per CTA and p lives in shared memory, so part of the algorithmic bytes never reaches HBM" % (m_f, nnz_f)}
     else:  # multi-kernel path (EDGEFEM_B200_NO_PERSISTENT=1): batched CSR SpMV dominates
         ms_spmv = rs.sys.bench_kernel(0, 50)
         spmv_bytes = F * nnz * 16.0 + nnz * 4.0 + (m + 1) * 4.0 + F * P * m * 32.0
