@@ -117,6 +117,7 @@ SIGNATURES = {
     "efb_system_last_solve_kernel_ms": (C.c_int, [C.c_void_p, f64p]),
     "efb_spmv_host": (C.c_int, [C.c_void_p, C.c_int32, f64p, f64p]),
     "efb_bench_kernel": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, f64p]),
+    "efb_build_edges": (C.c_int, [C.c_void_p, C.c_int64, i64p, C.c_int64, i64p, i32p, i8p, i32p, i8p, i64p, i64p, C.c_int64]),
     "efb_system_create_rows": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
     "efb_dist_unique_id": (C.c_int, [u8p]),
     "efb_dist_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, u8p]),
@@ -246,6 +247,23 @@ class Ctx:
             self.h = None
 
 
+def build_edges_device(ctx: "Ctx", tet_conn, tri_conn=None):
+    """Global edge numbering on the GPU (efb_build_edges), bit-exact with the reference's build_edges.
+    tet_conn [t,4] / tri_conn [k,3] hold node IDS.  Returns (tet_edges [t,6] i32, tet_orient [t,6] i8,
+    tri_edges [k,3] i32, tri_orient [k,3] i8, edges [m,2] i64)."""
+    tc = np.ascontiguousarray(np.asarray(tet_conn, dtype=np.int64).reshape(-1, 4))
+    rc_ = np.ascontiguousarray(np.asarray(tri_conn if tri_conn is not None else np.zeros((0, 3)), dtype=np.int64).reshape(-1, 3))
+    nt, nk = tc.shape[0], rc_.shape[0]
+    te, to = np.zeros((nt, 6), dtype=np.int32), np.zeros((nt, 6), dtype=np.int8)
+    re_, ro = np.zeros((nk, 3), dtype=np.int32), np.zeros((nk, 3), dtype=np.int8)
+    cap = 6 * nt + 3 * nk
+    edges = np.zeros((max(cap, 1), 2), dtype=np.int64)
+    m = C.c_int64()
+    ctx.check(ctx.lib.efb_build_edges(ctx.h, nt, _p(tc, i64p), nk, _p(rc_, i64p), _p(te, i32p), _p(to, i8p), _p(re_, i32p), _p(ro, i8p),
+                                      C.byref(m), _p(edges, i64p), cap), "efb_build_edges")
+    return te, to, re_, ro, edges[: m.value].copy()
+
+
 class DeviceMesh:
     def __init__(self, ctx: Ctx, xyz, tet_nodes, tet_edges, tet_orient, tet_phys, edge_nodes):
         self.ctx = ctx
@@ -273,6 +291,32 @@ class DeviceMesh:
         if self.h:
             self.ctx.lib.efb_mesh_destroy(self.h)
             self.h = None
+
+
+def device_mesh_from_conn(ctx: "Ctx", xyz, tet_conn, tet_phys, tri_conn=None, node_ids=None):
+    """Large-mesh ingest without the per-element host Mesh: number the edges on the GPU (efb_build_edges) and upload.
+    tet_conn / tri_conn hold node IDS; node_ids (default 1..n) gives the id of every xyz row.
+    Returns (DeviceMesh, info) with info = dict(tet_edges, tet_orient, tri_edges, tri_orient, edges (ids), edge_nodes (indices))."""
+    xyz = np.ascontiguousarray(np.asarray(xyz, dtype=np.float64).reshape(-1, 3))
+    tc = np.asarray(tet_conn, dtype=np.int64).reshape(-1, 4)
+    te, to, re_, ro, edges = build_edges_device(ctx, tc, tri_conn)
+    if node_ids is None:
+        tet_nodes, edge_nodes = (tc - 1).astype(np.int32), (edges - 1).astype(np.int32)
+    else:
+        ids = np.asarray(node_ids, dtype=np.int64)
+        lut = np.full(int(ids.max()) + 1, -1, dtype=np.int64)
+        lut[ids] = np.arange(ids.size)
+        tet_nodes, edge_nodes = lut[tc].astype(np.int32), lut[edges].astype(np.int32)
+    dm = DeviceMesh(ctx, xyz, tet_nodes, te, to, tet_phys, edge_nodes)
+    return dm, dict(tet_edges=te, tet_orient=to, tri_edges=re_, tri_orient=ro, edges=edges, edge_nodes=edge_nodes)
+
+
+def pec_flags_from_tris(n_edges: int, tri_edges, tri_phys, pec_tag: int):
+    """Dirichlet flags = edges of the boundary triangles tagged pec_tag (build_edge_pec, src/bc.cpp:47-80)."""
+    flags = np.zeros(n_edges, dtype=np.uint8)
+    sel = np.asarray(tri_phys) == pec_tag
+    flags[np.asarray(tri_edges)[sel].reshape(-1)] = 1
+    return flags
 
 
 def make_materials(n_slots: int, eps=None, mu=None, eps_models=None, poles=None, pml=None):

@@ -263,6 +263,16 @@ int efb_spmv_host(efb_system *sys, int32_t matrix, const double *x_c128, double 
  * 4 = FP64 FMA throughput probe (sm_count*8 CTAs x 256 threads x 8 chains x 4096 FMAs per launch). */
 int efb_bench_kernel(efb_system *sys, int32_t which, int32_t reps, double *avg_ms);
 
+/* ------------------------------------------------------------------ edge numbering on the device
+ * Replaces the sequential unordered_map walk of build_edges (src/mesh_gmsh.cpp:104-146) for large meshes, bit-exact:
+ * first-seen ids over tets x (01,02,03,12,13,23) then tris x (01,12,20), orient = +1 iff conn[a] < conn[b],
+ * edges[id] = (min, max) node ids.  conn arrays hold node IDS (as in the .msh file), 0 <= id < 2^32.  Call once to
+ * size (`edges` NULL), or pass an `edges` buffer of edges_capacity pairs (6*n_tet + 3*n_tri always suffices).
+ * Two radix sorts + a few passes over 6*n_tet + 3*n_tri keys. */
+int efb_build_edges(efb_ctx *ctx, int64_t n_tet, const int64_t *tet_conn /* [4t] */, int64_t n_tri, const int64_t *tri_conn /* [3k] */,
+                    int32_t *tet_edges /* [6t] */, int8_t *tet_orient /* [6t] */, int32_t *tri_edges /* [3k] */,
+                    int8_t *tri_orient /* [3k] */, int64_t *n_edges, int64_t *edges /* [2*capacity] or NULL */, int64_t edges_capacity);
+
 /* ------------------------------------------------------------------ row-partitioned single large system
  * One process per GPU.  Rank r owns rows [r*chunk, min(m,(r+1)*chunk)), chunk = ceil(m/world), of the global edge
  * space; every rank holds the whole mesh (efb_mesh_create) and creates its block with efb_system_create_rows, sets

@@ -46,7 +46,6 @@ def main():
     import edgefem_b200
     from edgefem_b200 import cabi, meshgen, sharding
 
-    pe = edgefem_b200.load_pyedgefem()
     ctx = cabi.Ctx(local)
     uid = [cabi.dist_unique_id() if rank == 0 else None]
     if dist is not None:
@@ -56,14 +55,10 @@ def main():
     t0 = time.perf_counter()
     n = a.n
     xyz, tets, tp, tris, trp = meshgen.cube_cavity(n, jitter=0.1)
-    hm = pe.mesh_from_arrays(xyz, tets, tp, tris, trp)
-    bc = pe.build_edge_pec(hm, 1)
-    arr = dict(xyz=hm.xyz_array(), tet_nodes=hm.tet_nodes_array(), tet_edges=hm.tet_edges_array(), tet_orient=hm.tet_orient_array(),
-               tet_phys=hm.tet_phys_array(), edge_nodes=hm.edge_nodes_array())
-    dm = cabi.DeviceMesh(ctx, arr["xyz"], arr["tet_nodes"], arr["tet_edges"], arr["tet_orient"], arr["tet_phys"], arr["edge_nodes"])
-    m = hm.num_edges()
-    flags = np.zeros(m, dtype=np.uint8)
-    flags[np.asarray(bc.dirichlet_edges, dtype=np.int64)] = 1
+    # large-mesh ingest: edges numbered on the GPU (bit-exact with build_edges), no per-element host Mesh
+    dm, info = cabi.device_mesh_from_conn(ctx, xyz, tets, tp, tris)
+    m = int(info["edges"].shape[0])
+    flags = cabi.pec_flags_from_tris(m, info["tri_edges"], trp, 1)
     r0, r1 = cabi.dist_row_range(m, rank, world)
     assert (r0, r1) == sharding.row_range(m, rank, world)
     sysd = cabi.DeviceSystem.from_mesh_rows(dm, r0, r1)
@@ -97,7 +92,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    out = {"n": n, "world": world, "tets": hm.num_tets(), "edges": m, "nnz_total": int(sumr(sysd.nnz)), "rows_local": r1 - r0,
+    out = {"n": n, "world": world, "tets": int(tets.shape[0]), "edges": m, "nnz_total": int(sumr(sysd.nnz)), "rows_local": r1 - r0,
            "host_setup_s": round(setup_s, 2), "assembly_ms": maxr(ms_asm)}
     nnz_tot = out["nnz_total"]
     b_spmv = nnz_tot * 20.0 + m * 36.0
