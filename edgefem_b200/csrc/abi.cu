@@ -343,9 +343,17 @@ int efb_mesh_create(efb_ctx *ctx_, const efb_mesh_desc *d, efb_mesh **out) {
     }
   // slots = distinct tags ascending
   {
-    std::vector<int32_t> tags(d->tet_phys, d->tet_phys + nt);
-    std::sort(tags.begin(), tags.end());
-    tags.erase(std::unique(tags.begin(), tags.end()), tags.end());
+    std::vector<int32_t> tags;  // a handful of distinct values: one pass with a last-tag cache, not a 20 M-element sort
+    int32_t last = 0;
+    bool have_last = false;
+    for (int64_t t = 0; t < nt && tags.size() <= (size_t)MAX_SLOTS; ++t) {
+      const int32_t g = d->tet_phys[t];
+      if (have_last && g == last) continue;
+      last = g;
+      have_last = true;
+      auto it = std::lower_bound(tags.begin(), tags.end(), g);
+      if (it == tags.end() || *it != g) tags.insert(it, g);
+    }
     if ((int)tags.size() > MAX_SLOTS) {
       delete M;
       return fail(c, EFB_ERR_LIMIT, "efb_mesh_create: %zu distinct physical tags > %d", tags.size(), MAX_SLOTS);
@@ -354,21 +362,25 @@ int efb_mesh_create(efb_ctx *ctx_, const efb_mesh_desc *d, efb_mesh **out) {
     M->n_slots = (int)tags.size();
   }
   std::vector<uint8_t> slot(nt), sign(nt);
-  for (int64_t t = 0; t < nt; ++t) {
-    slot[t] = (uint8_t)(std::lower_bound(M->slot_tags.begin(), M->slot_tags.end(), d->tet_phys[t]) - M->slot_tags.begin());
-    uint8_t s = 0;
-    for (int k = 0; k < 6; ++k)
-      if (d->tet_orient[6 * t + k] < 0) s |= (uint8_t)(1u << k);
-    sign[t] = s;
-  }
+  parallel_for(nt, [&](int64_t ta, int64_t tb) {
+    for (int64_t t = ta; t < tb; ++t) {
+      slot[t] = (uint8_t)(std::lower_bound(M->slot_tags.begin(), M->slot_tags.end(), d->tet_phys[t]) - M->slot_tags.begin());
+      uint8_t s = 0;
+      for (int k = 0; k < 6; ++k)
+        if (d->tet_orient[6 * t + k] < 0) s |= (uint8_t)(1u << k);
+      sign[t] = s;
+    }
+  });
   M->h_tet_edges.assign(d->tet_edges, d->tet_edges + 6 * nt);
   M->h_edge_nodes.assign(d->edge_nodes, d->edge_nodes + 2 * (int64_t)d->n_edge);
-  // edge -> incident (tet, local) lists, ascending tet (deterministic summation order)
-  M->h_e2t_ptr.assign((size_t)M->m + 1, 0);
-  for (int64_t i = 0; i < 6 * nt; ++i) M->h_e2t_ptr[d->tet_edges[i] + 1]++;
-  for (int e = 0; e < M->m; ++e) M->h_e2t_ptr[e + 1] += M->h_e2t_ptr[e];
-  M->h_e2t_item.resize((size_t)6 * nt);
-  {
+  // edge -> incident (tet, local) lists, ascending tet (deterministic summation order): counting sort on the host,
+  // or a stable radix sort on the device for large meshes (same lists)
+  const bool dev_setup = device_setup_enabled(nt) && nt > 0;
+  if (!dev_setup) {
+    M->h_e2t_ptr.assign((size_t)M->m + 1, 0);
+    for (int64_t i = 0; i < 6 * nt; ++i) M->h_e2t_ptr[d->tet_edges[i] + 1]++;
+    for (int e = 0; e < M->m; ++e) M->h_e2t_ptr[e + 1] += M->h_e2t_ptr[e];
+    M->h_e2t_item.resize((size_t)6 * nt);
     std::vector<int32_t> cur(M->h_e2t_ptr.begin(), M->h_e2t_ptr.end() - 1);
     for (int64_t t = 0; t < nt; ++t)
       for (int k = 0; k < 6; ++k) M->h_e2t_item[cur[d->tet_edges[6 * t + k]]++] = (int32_t)((t << 3) | k);
@@ -380,8 +392,12 @@ int efb_mesh_create(efb_ctx *ctx_, const efb_mesh_desc *d, efb_mesh **out) {
   if ((rc = dev_upload(c, &M->d_tet_nodes, (const int4 *)d->tet_nodes, (size_t)nt))) return rc;
   if ((rc = dev_upload(c, &M->d_tet_sign, sign.data(), sign.size()))) return rc;
   if ((rc = dev_upload(c, &M->d_tet_slot, slot.data(), slot.size()))) return rc;
-  if ((rc = dev_upload(c, &M->d_e2t_ptr, M->h_e2t_ptr.data(), M->h_e2t_ptr.size()))) return rc;
-  if ((rc = dev_upload(c, &M->d_e2t_item, M->h_e2t_item.data(), M->h_e2t_item.size()))) return rc;
+  if (dev_setup) {
+    if ((rc = device_e2t(M, d->tet_edges, nt))) return rc;
+  } else {
+    if ((rc = dev_upload(c, &M->d_e2t_ptr, M->h_e2t_ptr.data(), M->h_e2t_ptr.size()))) return rc;
+    if ((rc = dev_upload(c, &M->d_e2t_item, M->h_e2t_item.data(), M->h_e2t_item.size()))) return rc;
+  }
   if ((rc = dev_alloc(c, &M->d_geom, (size_t)std::max<int64_t>(1, nt)))) return rc;
   if ((rc = launch_tet_geometry(M))) return rc;
   // per-slot bounding boxes (PML profile, src/assemble_maxwell.cpp:66-89) on device
@@ -411,7 +427,7 @@ void efb_mesh_destroy(efb_mesh *mesh_) {
   cudaSetDevice(M->ctx->device);
   cudaStreamSynchronize(M->ctx->stream);  // pooled blocks may be handed out again immediately
   dfree(M->d_xyz); dfree(M->d_tet_nodes); dfree(M->d_tet_sign); dfree(M->d_tet_slot);
-  dfree(M->d_e2t_ptr); dfree(M->d_e2t_item); dfree(M->d_slot_bbox); dfree(M->d_geom);
+  dfree(M->d_e2t_ptr); dfree(M->d_e2t_item); dfree(M->d_slot_bbox); dfree(M->d_geom); dfree(M->d_tet_edges);
   delete M;
 }
 
@@ -429,8 +445,10 @@ static int system_alloc_common(System *S) {
   Ctx *c = S->ctx;
   int rc;
   S->n_sys = S->n_matrix * S->n_rhs;
-  if ((rc = dev_upload(c, &S->d_rowptr, S->h_rowptr.data(), S->h_rowptr.size()))) return rc;
-  if ((rc = dev_upload(c, &S->d_colidx, S->h_colidx.data(), S->h_colidx.size()))) return rc;
+  if (!S->d_rowptr) {  // (the device pattern builder leaves both arrays in place)
+    if ((rc = dev_upload(c, &S->d_rowptr, S->h_rowptr.data(), S->h_rowptr.size()))) return rc;
+    if ((rc = dev_upload(c, &S->d_colidx, S->h_colidx.data(), S->h_colidx.size()))) return rc;
+  }
   std::vector<int32_t> diag(S->m, -1);
   parallel_for(S->m, [&](int64_t a, int64_t b) {
     for (int64_t r = a; r < b; ++r) {
@@ -614,6 +632,49 @@ static int system_create_rows(Mesh *M, int row0, int row1, int64_t n_extra, cons
   S->row0 = row0;
   S->n_matrix = n_matrix;
   S->n_rhs = n_rhs;
+  // large meshes: pattern + position map on the device (same arrays as the host code below)
+  bool dev_done = false;
+  if (n_extra == 0 && device_setup_enabled(M->n_tet) && M->d_tet_edges) {
+    int rcd = device_pattern(S, &dev_done);
+    if (rcd) return rcd;
+  }
+  if (dev_done) {
+    st.mark("device pattern + position map");
+    int32_t maxrow = 0;
+    for (int r = 0; r < m; ++r) maxrow = std::max(maxrow, S->h_rowptr[r + 1] - S->h_rowptr[r]);
+    if (maxrow > ASM_CHUNK_NNZ || maxrow > 32767) {
+      delete S;
+      return fail(c, EFB_ERR_LIMIT, "efb_system_create: a row has %d entries (limit %d)", maxrow, std::min(ASM_CHUNK_NNZ, 32767));
+    }
+    std::vector<int32_t> chunk{0};
+    int64_t acc = 0;
+    int rows = 0;
+    for (int r = 0; r < m; ++r) {
+      const int len = S->h_rowptr[r + 1] - S->h_rowptr[r];
+      if (acc + len > ASM_CHUNK_NNZ || rows >= ASM_CHUNK_ROWS) {
+        chunk.push_back(r);
+        acc = 0;
+        rows = 0;
+      }
+      acc += len;
+      rows++;
+    }
+    chunk.push_back(m);
+    S->n_chunks = (int)chunk.size() - 1;
+    int rc;
+    if ((rc = system_alloc_common(S))) return rc;
+    st.mark("diag/stream structures + device buffers");
+    if ((rc = dev_upload(c, &S->d_chunk_row, chunk.data(), chunk.size()))) return rc;
+    if (m == M->m && (rc = system_set_gradient(S, M->n_node, M->h_edge_nodes.data()))) return rc;
+    EFB_CUDA(c, cudaStreamSynchronize(c->stream));
+    st.mark("gradient lists + sync");
+    *out = (efb_system *)S;
+    return EFB_OK;
+  }
+  {
+    int rch = mesh_host_e2t_item(M);
+    if (rch) return rch;
+  }
   // extras bucketed by row
   std::vector<int64_t> xptr((size_t)m + 1, 0);
   for (int64_t i = 0; i < n_extra; ++i) xptr[extra_rows[i] + 1]++;

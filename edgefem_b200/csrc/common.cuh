@@ -94,6 +94,7 @@ struct Mesh {
   uint8_t *d_tet_slot = nullptr;     // [n_tet]
   int32_t *d_e2t_ptr = nullptr;      // [m+1]
   int32_t *d_e2t_item = nullptr;     // [6*n_tet]
+  int32_t *d_tet_edges = nullptr;    // [6*n_tet] (large meshes only: input of the device pattern builder)
   double *d_slot_bbox = nullptr;     // [n_slots*6] min xyz, max xyz over the slot's tets
   TetGeom *d_geom = nullptr;         // [n_tet] frequency-independent element geometry
 };
@@ -264,6 +265,11 @@ struct Timed {  // records CUDA events around a compute call on the ctx stream
 // internal entry points shared across translation units
 int solver_free(System *s);
 int build_small_structs(System *s);  // abi.cu
+// numbering.cu: large-mesh set-up on the device
+bool device_setup_enabled(long long n_tet);
+int device_e2t(Mesh *M, const int32_t *h_tet_edges, long long nt);
+int mesh_host_e2t_item(Mesh *M);
+int device_pattern(System *S, bool *done);
 void dist_free(System *s);
 int assemble_launch(System *s, int first, int count, int mode);
 int launch_tet_geometry(Mesh *m);

@@ -179,3 +179,187 @@ extern "C" int efb_build_edges(efb_ctx *ctx_, int64_t n_tet, const int64_t *tet_
   EFB_CUDA(c, cudaStreamSynchronize(st));
   return EFB_OK;
 }
+
+// =====================================================================================================
+// Large-mesh set-up on the device: edge -> (tet, local) incidence lists and the CSR pattern + position map
+// of a row block.  Same results as the host code in abi.cu (tested bit for bit); used from efb_mesh_create /
+// system_create_rows when the mesh is large (device_setup_enabled()).
+// =====================================================================================================
+namespace efb {
+namespace {
+
+__global__ void k_e2t_pairs(const int32_t *__restrict__ tet_edges, long long n6, unsigned *__restrict__ key, unsigned *__restrict__ item) {
+  const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (p >= n6) return;
+  key[p] = (unsigned)tet_edges[p];
+  item[p] = (unsigned)(((p / 6) << 3) | (p % 6));
+}
+
+__global__ void k_count_keys(const unsigned *__restrict__ key, long long n6, int32_t *__restrict__ cnt) {
+  const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (p < n6) atomicAdd(&cnt[key[p]], 1);  // integer counts: order-independent
+}
+
+constexpr int PAT_MAX_ROW = 256;  // longest row the device pattern builder handles (longer: host path)
+
+// sorted, duplicate-free column list of one row in thread-local storage; returns its length or -1 on overflow
+__device__ __forceinline__ int row_columns(const int32_t *__restrict__ e2t_ptr, const int32_t *__restrict__ e2t_item,
+                                           const int32_t *__restrict__ tet_edges, int g, int32_t (&buf)[PAT_MAX_ROW]) {
+  int L = 0;
+  for (int k = e2t_ptr[g]; k < e2t_ptr[g + 1]; ++k) {
+    const int32_t *e6 = tet_edges + 6ll * (e2t_item[k] >> 3);
+#pragma unroll 1
+    for (int j = 0; j < 6; ++j) {
+      const int32_t cnew = e6[j];
+      int lo = 0, hi = L;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (buf[mid] < cnew) lo = mid + 1; else hi = mid;
+      }
+      if (lo < L && buf[lo] == cnew) continue;
+      if (L == PAT_MAX_ROW) return -1;
+      for (int i = L; i > lo; --i) buf[i] = buf[i - 1];
+      buf[lo] = cnew;
+      ++L;
+    }
+  }
+  return L;
+}
+
+__global__ void __launch_bounds__(128)
+k_pattern_count(const int32_t *__restrict__ e2t_ptr, const int32_t *__restrict__ e2t_item, const int32_t *__restrict__ tet_edges, int row0,
+                int m_loc, int32_t *__restrict__ rowlen, int32_t *__restrict__ overflow) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= m_loc) return;
+  int32_t buf[PAT_MAX_ROW];
+  const int L = row_columns(e2t_ptr, e2t_item, tet_edges, row0 + r, buf);
+  if (L < 0) {
+    atomicExch(overflow, 1);
+    rowlen[r] = 0;
+  } else {
+    rowlen[r] = L;
+  }
+}
+
+__global__ void __launch_bounds__(128)
+k_pattern_fill(const int32_t *__restrict__ e2t_ptr, const int32_t *__restrict__ e2t_item, const int32_t *__restrict__ tet_edges, int row0,
+               int m_loc, const int32_t *__restrict__ rowptr, int32_t *__restrict__ colidx, uint16_t *__restrict__ pos, long long kpos0) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= m_loc) return;
+  int32_t buf[PAT_MAX_ROW];
+  const int g = row0 + r;
+  const int L = row_columns(e2t_ptr, e2t_item, tet_edges, g, buf);
+  int32_t *dst = colidx + rowptr[r];
+  for (int i = 0; i < L; ++i) dst[i] = buf[i];
+  for (int k = e2t_ptr[g]; k < e2t_ptr[g + 1]; ++k) {
+    const int32_t *e6 = tet_edges + 6ll * (e2t_item[k] >> 3);
+    for (int j = 0; j < 6; ++j) {
+      int lo = 0, hi = L;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (buf[mid] < e6[j]) lo = mid + 1; else hi = mid;
+      }
+      pos[((long long)k - kpos0) * 6 + j] = (uint16_t)lo;
+    }
+  }
+}
+
+}  // namespace
+
+bool device_setup_enabled(long long n_tet) {
+  if (const char *e = getenv("EDGEFEM_B200_DEVICE_SETUP")) return e[0] == '1';
+  return n_tet >= 200000;
+}
+
+// fills M->d_tet_edges, d_e2t_ptr, d_e2t_item and M->h_e2t_ptr (h_e2t_item stays empty: mesh_host_e2t_item fetches it)
+int device_e2t(Mesh *M, const int32_t *h_tet_edges, long long nt) {
+  Ctx *c = M->ctx;
+  cudaStream_t st = c->stream;
+  const long long n6 = 6 * nt;
+  int rc;
+  if ((rc = dev_upload(c, &M->d_tet_edges, h_tet_edges, (size_t)n6))) return rc;
+  if ((rc = dev_alloc(c, &M->d_e2t_ptr, (size_t)M->m + 1))) return rc;
+  if ((rc = dev_alloc(c, &M->d_e2t_item, (size_t)std::max<long long>(n6, 1)))) return rc;
+  Scratch<unsigned> k0, k1, v0;
+  Scratch<int32_t> cnt;
+  Scratch<unsigned char> tmp;
+  EFB_CUDA(c, k0.alloc(n6)); EFB_CUDA(c, k1.alloc(n6)); EFB_CUDA(c, v0.alloc(n6)); EFB_CUDA(c, cnt.alloc((size_t)M->m + 1));
+  const unsigned nb = (unsigned)((n6 + 255) / 256);
+  k_e2t_pairs<<<nb, 256, 0, st>>>(M->d_tet_edges, n6, k0.p, v0.p);
+  EFB_CHECK_LAUNCH(c);
+  EFB_CUDA(c, cudaMemsetAsync(cnt.p, 0, ((size_t)M->m + 1) * sizeof(int32_t), st));
+  k_count_keys<<<nb, 256, 0, st>>>(k0.p, n6, cnt.p);
+  EFB_CHECK_LAUNCH(c);
+  int bits = 1;
+  while ((1ll << bits) < (long long)M->m) ++bits;
+  size_t tb = 0, tb2 = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tb, k0.p, k1.p, v0.p, (unsigned *)M->d_e2t_item, (int)n6, 0, bits, st);
+  cub::DeviceScan::ExclusiveSum(nullptr, tb2, cnt.p, M->d_e2t_ptr, M->m + 1, st);
+  EFB_CUDA(c, tmp.alloc(std::max(tb, tb2)));
+  // stable sort by edge id: items of an edge stay in ascending (tet, local) order = the host's counting sort
+  EFB_CUDA(c, cub::DeviceRadixSort::SortPairs(tmp.p, tb, k0.p, k1.p, v0.p, (unsigned *)M->d_e2t_item, (int)n6, 0, bits, st));
+  EFB_CUDA(c, cub::DeviceScan::ExclusiveSum(tmp.p, tb2, cnt.p, M->d_e2t_ptr, M->m + 1, st));
+  c->launches += 2;
+  M->h_e2t_ptr.resize((size_t)M->m + 1);
+  EFB_CUDA(c, cudaMemcpyAsync(M->h_e2t_ptr.data(), M->d_e2t_ptr, ((size_t)M->m + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  EFB_CUDA(c, cudaStreamSynchronize(st));
+  return EFB_OK;
+}
+
+int mesh_host_e2t_item(Mesh *M) {  // host copy of the incidence items for the host-side pattern builder
+  if (!M->h_e2t_item.empty() || M->n_tet == 0) return EFB_OK;
+  Ctx *c = M->ctx;
+  M->h_e2t_item.resize((size_t)6 * M->n_tet);
+  EFB_CUDA(c, cudaMemcpyAsync(M->h_e2t_item.data(), M->d_e2t_item, M->h_e2t_item.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  EFB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return EFB_OK;
+}
+
+// CSR pattern + position map of the rows [S->row0, S->row0 + S->m) on the device; fills d_rowptr, d_colidx, d_e2t_pos,
+// h_rowptr, h_colidx, nnz.  *done = false (nothing allocated) when a row is too long for the device builder.
+int device_pattern(System *S, bool *done) {
+  Ctx *c = S->ctx;
+  Mesh *M = S->mesh;
+  cudaStream_t st = c->stream;
+  *done = false;
+  const int m = S->m;
+  Scratch<int32_t> rowlen, ovf;
+  Scratch<unsigned char> tmp;
+  EFB_CUDA(c, rowlen.alloc((size_t)m + 1)); EFB_CUDA(c, ovf.alloc(1));
+  EFB_CUDA(c, cudaMemsetAsync(ovf.p, 0, sizeof(int32_t), st));
+  EFB_CUDA(c, cudaMemsetAsync(rowlen.p + m, 0, sizeof(int32_t), st));
+  const unsigned nb = (unsigned)((m + 127) / 128);
+  k_pattern_count<<<nb, 128, 0, st>>>(M->d_e2t_ptr, M->d_e2t_item, M->d_tet_edges, S->row0, m, rowlen.p, ovf.p);
+  EFB_CHECK_LAUNCH(c);
+  int32_t h_ovf = 0;
+  EFB_CUDA(c, cudaMemcpyAsync(&h_ovf, ovf.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  EFB_CUDA(c, cudaStreamSynchronize(st));
+  if (h_ovf) return EFB_OK;
+  int rc;
+  if ((rc = dev_alloc(c, &S->d_rowptr, (size_t)m + 1))) return rc;
+  size_t tb = 0;
+  // 64-bit safe: row lengths sum below 2^31 is checked right after
+  cub::DeviceScan::ExclusiveSum(nullptr, tb, rowlen.p, S->d_rowptr, m + 1, st);
+  EFB_CUDA(c, tmp.alloc(tb));
+  EFB_CUDA(c, cub::DeviceScan::ExclusiveSum(tmp.p, tb, rowlen.p, S->d_rowptr, m + 1, st));
+  c->launches++;
+  S->h_rowptr.resize((size_t)m + 1);
+  EFB_CUDA(c, cudaMemcpyAsync(S->h_rowptr.data(), S->d_rowptr, ((size_t)m + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  EFB_CUDA(c, cudaStreamSynchronize(st));
+  // overflow of the int32 scan shows up as a non-monotone / negative total
+  const long long nnz = S->h_rowptr[m];
+  if (nnz < 0) return fail(c, EFB_ERR_LIMIT, "efb_system_create: nnz >= 2^31 (int32 CSR like Eigen's default index)");
+  S->nnz = nnz;
+  const long long kpos0 = M->h_e2t_ptr[S->row0], n_inc = M->h_e2t_ptr[S->row0 + m] - kpos0;
+  if ((rc = dev_alloc(c, &S->d_colidx, (size_t)std::max<long long>(nnz, 1)))) return rc;
+  if ((rc = dev_alloc(c, &S->d_e2t_pos, (size_t)std::max<long long>(n_inc * 6, 1)))) return rc;
+  k_pattern_fill<<<nb, 128, 0, st>>>(M->d_e2t_ptr, M->d_e2t_item, M->d_tet_edges, S->row0, m, S->d_rowptr, S->d_colidx, S->d_e2t_pos, kpos0);
+  EFB_CHECK_LAUNCH(c);
+  S->h_colidx.resize((size_t)nnz);
+  EFB_CUDA(c, cudaMemcpyAsync(S->h_colidx.data(), S->d_colidx, (size_t)nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  EFB_CUDA(c, cudaStreamSynchronize(st));
+  *done = true;
+  return EFB_OK;
+}
+
+}  // namespace efb

@@ -1,18 +1,36 @@
-import time, numpy as np, sys, os
-sys.path.insert(0, os.getcwd())
-import edgefem_b200
-from edgefem_b200 import meshgen, cabi
-pe = edgefem_b200.load_pyedgefem()
-n=int(sys.argv[1])
-T=time.perf_counter
-t=T(); xyz,tets,tp,tris,trp = meshgen.cube_cavity(n, jitter=0.1); t1=T(); print("meshgen", round(t1-t,3))
-hm = pe.mesh_from_arrays(xyz,tets,tp,tris,trp); t2=T(); print("mesh_from_arrays+build_edges", round(t2-t1,3))
-bc = pe.build_edge_pec(hm,1); t3=T(); print("build_edge_pec", round(t3-t2,3))
-a = [hm.xyz_array(), hm.tet_nodes_array(), hm.tet_edges_array(), hm.tet_orient_array(), hm.tet_phys_array(), hm.edge_nodes_array()]; t4=T(); print("arrays", round(t4-t3,3))
-flags = np.zeros(hm.num_edges(), dtype=np.uint8); flags[np.asarray(bc.dirichlet_edges, dtype=np.int64)] = 1
-ctx = cabi.Ctx(0); t5=T()
-dm = cabi.DeviceMesh(ctx, *a); t6=T(); print("DeviceMesh", round(t6-t5,3))
-pe_idx = np.nonzero(flags)[0].astype(np.int32)
-s = cabi.DeviceSystem.from_mesh(dm, pe_idx, pe_idx); t7=T(); print("system create", round(t7-t6,3))
-s.set_dirichlet(flags); t8=T(); print("set_dirichlet", round(t8-t7,3))
-print(hm.num_tets(), hm.num_edges(), s.nnz)
+#!/usr/bin/env python
+"""Stage times of the large-mesh set-up (array-only ingest).  python tools/setup_prof.py [n]"""
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from edgefem_b200 import cabi, meshgen  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+T = time.perf_counter
+t = T()
+xyz, tets, tp, tris, trp = meshgen.cube_cavity(n, jitter=0.1)
+print("meshgen (test fixture, numpy)", round(T() - t, 3))
+ctx = cabi.Ctx(0)
+cabi.build_edges_device(ctx, tets[:1000], tris[:10])
+t = T()
+te, to, re_, ro, edges = cabi.build_edges_device(ctx, tets, tris)
+t1 = T()
+print("edge numbering (device)", round(t1 - t, 3))
+tet_nodes, edge_nodes = (tets - 1).astype(np.int32), (edges - 1).astype(np.int32)
+flags = cabi.pec_flags_from_tris(edges.shape[0], re_, trp, 1)
+t2 = T()
+print("index arrays + PEC flags (numpy)", round(t2 - t1, 3))
+dm = cabi.DeviceMesh(ctx, xyz, tet_nodes, te, to, tp, edge_nodes)
+t3 = T()
+print("DeviceMesh", round(t3 - t2, 3))
+s = cabi.DeviceSystem.from_mesh(dm)
+t4 = T()
+print("system create", round(t4 - t3, 3))
+s.set_dirichlet(flags)
+t5 = T()
+print("set_dirichlet", round(t5 - t4, 3))
+print("total set-up after mesh generation", round(t5 - t, 3), "s;", tets.shape[0], "tets", edges.shape[0], "edges", s.nnz, "nnz")
