@@ -44,7 +44,7 @@ def build_host(verbose=False):
 
     os.makedirs(LIBDIR, exist_ok=True)
     inc = ["-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(HERE, "host")]
-    host_srcs = [os.path.join(HERE, "host", f) for f in ("mesh_ports.cpp", "device_path.cpp", "port_modes_io.cpp")]
+    host_srcs = [os.path.join(HERE, "host", f) for f in ("mesh_ports.cpp", "device_path.cpp", "port_modes_io.cpp", "post.cpp")]
     hdrs = []
     for d, _, fs in os.walk(os.path.join(ROOT, "include")):
         hdrs += [os.path.join(d, f) for f in fs]

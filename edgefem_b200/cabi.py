@@ -117,6 +117,8 @@ SIGNATURES = {
     "efb_system_last_solve_kernel_ms": (C.c_int, [C.c_void_p, f64p]),
     "efb_spmv_host": (C.c_int, [C.c_void_p, C.c_int32, f64p, f64p]),
     "efb_bench_kernel": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, f64p]),
+    "efb_huygens_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, f64p, C.c_int32, i32p, i32p, i32p, C.c_double, f64p, f64p, f64p, f64p, f64p, f64p]),
+    "efb_stratton_chu": (C.c_int, [C.c_void_p, C.c_int32, f64p, f64p, f64p, f64p, f64p, C.c_int32, f64p, f64p, C.c_double, f64p, f64p]),
     "efb_build_edges": (C.c_int, [C.c_void_p, C.c_int64, i64p, C.c_int64, i64p, i32p, i8p, i32p, i8p, i64p, i64p, C.c_int64]),
     "efb_system_create_rows": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
     "efb_dist_unique_id": (C.c_int, [u8p]),
@@ -245,6 +247,20 @@ class Ctx:
         if self.h:
             self.lib.efb_ctx_destroy(self.h)
             self.h = None
+
+
+def stratton_chu(ctx: "Ctx", r, n, E, H, area, theta, phi, k0):
+    """Far-field E_theta, E_phi at the direction list (theta[i], phi[i]) from Huygens-surface samples (efb_stratton_chu)."""
+    r_, n_ = np.ascontiguousarray(r, dtype=np.float64).reshape(-1, 3), np.ascontiguousarray(n, dtype=np.float64).reshape(-1, 3)
+    E_, H_ = _c128(E).reshape(-1, 3), _c128(H).reshape(-1, 3)
+    a_ = np.ascontiguousarray(area, dtype=np.float64).reshape(-1)
+    th, ph = np.ascontiguousarray(theta, dtype=np.float64).reshape(-1), np.ascontiguousarray(phi, dtype=np.float64).reshape(-1)
+    assert th.size == ph.size and r_.shape[0] == n_.shape[0] == E_.shape[0] == H_.shape[0] == a_.size
+    et, ep = np.zeros(th.size, dtype=np.complex128), np.zeros(th.size, dtype=np.complex128)
+    ctx.check(ctx.lib.efb_stratton_chu(ctx.h, a_.size, _p(r_, f64p), _p(n_, f64p), _p(E_.view(np.float64), f64p), _p(H_.view(np.float64), f64p),
+                                       _p(a_, f64p), th.size, _p(th, f64p), _p(ph, f64p), float(k0), _p(et.view(np.float64), f64p),
+                                       _p(ep.view(np.float64), f64p)), "efb_stratton_chu")
+    return et, ep
 
 
 def build_edges_device(ctx: "Ctx", tet_conn, tri_conn=None):
@@ -473,6 +489,20 @@ class DeviceSystem:
         ms = C.c_double()
         self.ctx.check(self.ctx.lib.efb_dist_bench(self.h, which, reps, halo_mode, C.byref(ms)), "efb_dist_bench")
         return ms.value
+
+    def huygens_eval(self, rhs, tri_nodes, tri_tet, tri_tet_edges, omega, mu_r=1.0):
+        """Tangential E, H at the centroids of surface triangles from solution `rhs` (efb_huygens_eval).
+        Returns dict(r [n,3], n [n,3], E_tan [n,3] c128, H_tan [n,3] c128, area [n])."""
+        tn, tt, te = _i32(tri_nodes).reshape(-1, 3), _i32(tri_tet).reshape(-1), _i32(tri_tet_edges).reshape(-1, 6)
+        n = tt.size
+        r, nn = np.zeros((n, 3)), np.zeros((n, 3))
+        E, H = np.zeros((n, 3), dtype=np.complex128), np.zeros((n, 3), dtype=np.complex128)
+        area = np.zeros(n)
+        mu = np.array([complex(mu_r)], dtype=np.complex128)
+        self.ctx.check(self.ctx.lib.efb_huygens_eval(self.mesh.h, self.h, rhs, None, n, _p(tn, i32p), _p(tt, i32p), _p(te, i32p), float(omega), _p(mu.view(np.float64), f64p),
+                                                     _p(r, f64p), _p(nn, f64p), _p(E.view(np.float64), f64p), _p(H.view(np.float64), f64p),
+                                                     _p(area, f64p)), "efb_huygens_eval")
+        return dict(r=r, n=nn, E_tan=E, H_tan=H, area=area)
 
     def bench_kernel(self, which, reps) -> float:
         ms = C.c_double()

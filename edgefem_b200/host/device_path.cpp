@@ -156,6 +156,14 @@ std::shared_ptr<DeviceMesh> device_mesh_for(const Mesh &mesh) {
   return dm;
 }
 
+}  // namespace
+
+namespace detail {
+efb_mesh *device_mesh_handle(const Mesh &mesh) { return device_mesh_for(mesh)->h; }
+}  // namespace detail
+
+namespace {
+
 std::vector<uint8_t> dirichlet_flags(const Mesh &mesh, const BC &bc) {
   std::vector<uint8_t> f(mesh.edges.size(), 0);
   for (int e : bc.dirichlet_edges)

@@ -16,6 +16,7 @@ efb_ctx *device_ctx();                 // lazily created; throws std::runtime_er
 void check(int rc, const char *what);  // throws with efb_last_error text
 void clear_device_cache();
 long long launch_count();
+efb_mesh *device_mesh_handle(const Mesh &mesh);  // cached device copy of the mesh (valid until the cache drops it)
 
 } // namespace detail
 } // namespace edgefem

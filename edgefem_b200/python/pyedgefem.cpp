@@ -16,6 +16,7 @@
 #include "edgefem/maxwell.hpp"
 #include "edgefem/mesh.hpp"
 #include "edgefem/periodic.hpp"
+#include "edgefem/post/ntf.hpp"
 #include "edgefem/ports/lumped_port.hpp"
 #include "edgefem/ports/wave_port.hpp"
 #include "edgefem/solver.hpp"
@@ -140,6 +141,43 @@ py::array_t<T> to_dense(const SparseMatrix<T> &A) {
 }
 
 } // namespace
+
+// ---- f3 helpers: [n,3] numpy arrays <-> vectors of 3-vectors
+static py::array_t<double> v3_to_numpy(const std::vector<Vector3d> &v) {
+  py::array_t<double> a({(py::ssize_t)v.size(), (py::ssize_t)3});
+  auto r = a.mutable_unchecked<2>();
+  for (size_t i = 0; i < v.size(); ++i)
+    for (int k = 0; k < 3; ++k) r(i, k) = v[i][k];
+  return a;
+}
+static py::array_t<std::complex<double>> c3_to_numpy(const std::vector<Vector3cd> &v) {
+  py::array_t<std::complex<double>> a({(py::ssize_t)v.size(), (py::ssize_t)3});
+  auto r = a.mutable_unchecked<2>();
+  for (size_t i = 0; i < v.size(); ++i)
+    for (int k = 0; k < 3; ++k) r(i, k) = v[i][k];
+  return a;
+}
+static std::vector<Vector3d> v3_from_numpy(py::array_t<double, py::array::c_style | py::array::forcecast> a) {
+  if (a.ndim() != 2 || a.shape(1) != 3) throw std::invalid_argument("expected an [n,3] float array");
+  std::vector<Vector3d> v((size_t)a.shape(0));
+  auto r = a.unchecked<2>();
+  for (size_t i = 0; i < v.size(); ++i) v[i] = Vector3d(r(i, 0), r(i, 1), r(i, 2));
+  return v;
+}
+static std::vector<Vector3cd> c3_from_numpy(py::array_t<std::complex<double>, py::array::c_style | py::array::forcecast> a) {
+  if (a.ndim() != 2 || a.shape(1) != 3) throw std::invalid_argument("expected an [n,3] complex array");
+  std::vector<Vector3cd> v((size_t)a.shape(0));
+  auto r = a.unchecked<2>();
+  for (size_t i = 0; i < v.size(); ++i) v[i] = {r(i, 0), r(i, 1), r(i, 2)};
+  return v;
+}
+static py::array_t<double> md_to_numpy(const MatrixXd &M) {
+  py::array_t<double> a({(py::ssize_t)M.rows(), (py::ssize_t)M.cols()});
+  auto r = a.mutable_unchecked<2>();
+  for (int i = 0; i < M.rows(); ++i)
+    for (int j = 0; j < M.cols(); ++j) r(i, j) = M(i, j);
+  return a;
+}
 
 PYBIND11_MODULE(pyedgefem, m) {
   m.doc() = "EdgeFEM frequency-domain hot path on NVIDIA B200 (sm_100a): drop-in subset of the reference pyedgefem module";
@@ -461,6 +499,73 @@ PYBIND11_MODULE(pyedgefem, m) {
       },
       "Build wave port using 3D FEM eigenvector as weights.", py::arg("mesh"), py::arg("surface"), py::arg("eigenvector"), py::arg("mode"),
       py::arg("pec_edges"));
+  // ---- field post-processing (reference python/pyedgefem.cpp:451-482, 975-1040)
+  using CArr = py::array_t<std::complex<double>, py::array::c_style | py::array::forcecast>;
+  using DArr = py::array_t<double, py::array::c_style | py::array::forcecast>;
+  m.def(
+      "evaluate_edge_field",
+      [](const std::array<Vector3d, 4> &vertices, const std::array<int, 6> &edge_orient, CArr dofs, const Vector3d &point) {
+        if (dofs.size() != 6) throw std::invalid_argument("edge_dofs must hold 6 values");
+        std::array<std::complex<double>, 6> d;
+        for (int i = 0; i < 6; ++i) d[i] = dofs.data()[i];
+        const auto E = evaluate_edge_field(vertices, edge_orient, d, point);
+        py::array_t<std::complex<double>> a(3);
+        for (int k = 0; k < 3; ++k) a.mutable_data()[k] = E[k];
+        return a;
+      },
+      "Evaluate E-field at a point inside a tetrahedron from edge DOFs.", py::arg("vertices"), py::arg("edge_orient"), py::arg("edge_dofs"),
+      py::arg("point"));
+  m.def(
+      "compute_barycentric",
+      [](const std::array<Vector3d, 4> &v, const Vector3d &p) {
+        const auto l = compute_barycentric(v, p);
+        return py::make_tuple(l[0], l[1], l[2], l[3]);
+      },
+      py::arg("vertices"), py::arg("point"));
+  m.def("whitney_edge_curls", [](const std::array<Vector3d, 4> &v) {
+    const auto c = whitney_edge_curls(v);
+    return v3_to_numpy(std::vector<Vector3d>(c.begin(), c.end()));
+  }, py::arg("vertices"));
+  py::class_<HuygensSurfaceData>(m, "HuygensSurfaceData", "Extracted Huygens surface data for near-to-far field transformation.")
+      .def(py::init<>())
+      .def_property_readonly("r", [](const HuygensSurfaceData &d) { return v3_to_numpy(d.r); }, "Triangle centroids [n,3]")
+      .def_property_readonly("n", [](const HuygensSurfaceData &d) { return v3_to_numpy(d.n); }, "Outward normals [n,3]")
+      .def_property_readonly("E_tan", [](const HuygensSurfaceData &d) { return c3_to_numpy(d.E_tan); }, "Tangential E-field [n,3]")
+      .def_property_readonly("H_tan", [](const HuygensSurfaceData &d) { return c3_to_numpy(d.H_tan); }, "Tangential H-field [n,3]")
+      .def_readonly("area", &HuygensSurfaceData::area, "Triangle areas");
+  m.def(
+      "extract_huygens_surface",
+      [](const Mesh &mesh, const VecC &x, int tag, double omega, std::complex<double> mu_r) { return extract_huygens_surface(mesh, x, tag, omega, mu_r); },
+      "Extract Huygens surface fields from FEM solution.", py::arg("mesh"), py::arg("solution"), py::arg("surface_tag"), py::arg("omega"),
+      py::arg("mu_r") = std::complex<double>(1.0, 0.0));
+  py::class_<NTFPoint2D>(m, "NTFPoint2D")
+      .def(py::init<>())
+      .def_readwrite("theta_deg", &NTFPoint2D::theta_deg)
+      .def_readwrite("e_theta", &NTFPoint2D::e_theta)
+      .def_readwrite("e_phi", &NTFPoint2D::e_phi);
+  m.def(
+      "stratton_chu_2d",
+      [](DArr r, DArr n, CArr E, CArr H, const std::vector<double> &area, const std::vector<double> &theta, double phi, double k0) {
+        return stratton_chu_2d(v3_from_numpy(r), v3_from_numpy(n), c3_from_numpy(E), c3_from_numpy(H), area, theta, phi, k0);
+      },
+      py::arg("r"), py::arg("n"), py::arg("E"), py::arg("H"), py::arg("area"), py::arg("theta_rad"), py::arg("phi_rad"), py::arg("k0"));
+  py::class_<FFPattern3D>(m, "FFPattern3D", "3D far-field pattern over a (theta, phi) grid.")
+      .def(py::init<>())
+      .def_property_readonly("theta_grid", [](const FFPattern3D &p) { return md_to_numpy(p.theta_grid); })
+      .def_property_readonly("phi_grid", [](const FFPattern3D &p) { return md_to_numpy(p.phi_grid); })
+      .def_readonly("E_theta", &FFPattern3D::E_theta)
+      .def_readonly("E_phi", &FFPattern3D::E_phi)
+      .def("total_magnitude", [](const FFPattern3D &p) { return md_to_numpy(p.total_magnitude()); })
+      .def("power_pattern", [](const FFPattern3D &p) { return md_to_numpy(p.power_pattern()); })
+      .def("pattern_dB", [](const FFPattern3D &p) { return md_to_numpy(p.pattern_dB()); });
+  m.def(
+      "stratton_chu_3d",
+      [](DArr r, DArr n, CArr E, CArr H, const std::vector<double> &area, const std::vector<double> &theta, const std::vector<double> &phi,
+         double k0) { return stratton_chu_3d(v3_from_numpy(r), v3_from_numpy(n), c3_from_numpy(E), c3_from_numpy(H), area, theta, phi, k0); },
+      py::arg("r"), py::arg("n"), py::arg("E"), py::arg("H"), py::arg("area"), py::arg("theta_rad"), py::arg("phi_rad"), py::arg("k0"));
+  m.def("compute_directivity", &compute_directivity, py::arg("pattern"));
+  m.def("compute_max_gain", &compute_max_gain, py::arg("pattern"), py::arg("efficiency") = 1.0);
+  m.def("compute_hpbw", &compute_hpbw, py::arg("pattern"));
   // ---- Touchstone writers (reference python/pyedgefem.cpp:630-656)
   m.def("write_touchstone", &write_touchstone, "Writes S-parameters to a Touchstone file.", py::arg("path"), py::arg("freq"), py::arg("data"));
   py::enum_<TouchstoneFormat>(m, "TouchstoneFormat")

@@ -263,6 +263,21 @@ int efb_spmv_host(efb_system *sys, int32_t matrix, const double *x_c128, double 
  * 4 = FP64 FMA throughput probe (sm_count*8 CTAs x 256 threads x 8 chains x 4096 FMAs per launch). */
 int efb_bench_kernel(efb_system *sys, int32_t which, int32_t reps, double *avg_ms);
 
+/* ------------------------------------------------------------------ field post-processing
+ * efb_huygens_eval: per surface triangle i (node INDICES tri_nodes[3i..], parent tet tri_tet[i], that tet's six global
+ * edge ids tri_tet_edges[6i..]) the centroid r, the unit normal n pointing away from the parent tet, the area, and the
+ * tangential E and H = curl E / (j omega mu0 mu_r) of the solution (x[rhs] of `sys`, or a host vector) at the centroid -- the body of the triangle loop
+ * of extract_huygens_surface (src/post/huygens_surface.cpp:59-135) incl. its projection E - conj(E.n) n.
+ * efb_stratton_chu: far field of the Love currents J = n x H, M = -n x E,
+ *   E_far = (j k0 / 4 pi) sum_s [ Z0 (rhat x J) x rhat - rhat x M ] exp(-j k0 rhat.r_s) area_s
+ * projected on theta_hat / phi_hat for n_dir directions (theta[i], phi[i]) -- src/post/ntf.cpp:86-203.           */
+int efb_huygens_eval(efb_mesh *mesh, efb_system *sys /* or NULL */, int32_t rhs, const double *x_host_c128 /* [m] or NULL */,
+                     int32_t n_tri, const int32_t *tri_nodes, const int32_t *tri_tet, const int32_t *tri_tet_edges, double omega, const double *mu_r_c128, double *r_out /* [3n] */,
+                     double *n_out /* [3n] */, double *E_tan_c128 /* [3n] */, double *H_tan_c128 /* [3n] */, double *area_out /* [n] */);
+int efb_stratton_chu(efb_ctx *ctx, int32_t n_s, const double *r, const double *n, const double *E_c128, const double *H_c128,
+                     const double *area, int32_t n_dir, const double *theta, const double *phi, double k0,
+                     double *e_theta_c128 /* [n_dir] */, double *e_phi_c128 /* [n_dir] */);
+
 /* ------------------------------------------------------------------ edge numbering on the device
  * Replaces the sequential unordered_map walk of build_edges (src/mesh_gmsh.cpp:104-146) for large meshes, bit-exact:
  * first-seen ids over tets x (01,02,03,12,13,23) then tris x (01,12,20), orient = +1 iff conn[a] < conn[b],

@@ -1530,3 +1530,105 @@ def touchstone_legacy_text(freq, sp) -> str:  # src/io/touchstone.cpp:50-62; sp 
     for f, s in zip(freq, sp):
         out.append(" ".join([_g12(f)] + [_g12(x) for v in s for x in (complex(v).real, complex(v).imag)]) + "\n")
     return "".join(out)
+
+
+# =====================================================================================================
+# field post-processing (test infrastructure)
+# =====================================================================================================
+_EDGE_PAIRS = ((0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3))
+
+
+def compute_barycentric(X: np.ndarray, p: np.ndarray) -> np.ndarray:  # src/edge_basis.cpp:132-151
+    T = np.column_stack([X[0] - X[3], X[1] - X[3], X[2] - X[3]])
+    l = np.linalg.inv(T) @ (np.asarray(p, dtype=float) - X[3])
+    return np.array([l[0], l[1], l[2], 1.0 - l[0] - l[1] - l[2]])
+
+
+def whitney_edge_curls(X: np.ndarray) -> np.ndarray:  # src/edge_basis.cpp:33-46 -> [6,3]
+    g, _ = gradients_and_volume(X)
+    return np.array([2.0 * np.cross(g[a], g[b]) for a, b in _EDGE_PAIRS])
+
+
+def evaluate_edge_field(X: np.ndarray, orient, dofs, p) -> np.ndarray:  # src/edge_basis.cpp:161-190
+    lam = compute_barycentric(X, p)
+    g, _ = gradients_and_volume(X)
+    E = np.zeros(3, dtype=np.complex128)
+    for e, (a, b) in enumerate(_EDGE_PAIRS):
+        E += dofs[e] * float(orient[e]) * (lam[a] * g[b] - lam[b] * g[a])
+    return E
+
+
+def extract_huygens_surface(mesh: Mesh, x: np.ndarray, surface_tag: int, omega: float, mu_r: complex = 1.0):
+    """src/post/huygens_surface.cpp:29-149 -> dict(r, n, E_tan, H_tan, area).  Eigen's `a.dot(b)` conjugates a, so the
+    'tangential' projection subtracts conj(E.n) n (restated as written)."""
+    jwmu = 1j * omega * (4.0e-7 * np.pi) * mu_r
+    faces = ((1, 2, 3), (0, 2, 3), (0, 1, 3), (0, 1, 2))
+    tri_to_tet: Dict[Tuple[int, int, int], int] = {}
+    for t in range(mesh.tet_conn.shape[0]):
+        c = mesh.tet_conn[t]
+        for f in faces:
+            tri_to_tet[tuple(sorted((int(c[f[0]]), int(c[f[1]]), int(c[f[2]]))))] = t  # later tets overwrite
+    out = dict(r=[], n=[], E_tan=[], H_tan=[], area=[])
+    for i in range(mesh.tri_conn.shape[0]):
+        if mesh.tri_phys[i] != surface_tag:
+            continue
+        v = mesh.xyz[mesh.node_idx_of(mesh.tri_conn[i])]
+        cen = (v[0] + v[1] + v[2]) / 3.0
+        cr = np.cross(v[1] - v[0], v[2] - v[0])
+        area = 0.5 * np.linalg.norm(cr)
+        if area < 1e-30:
+            continue
+        normal = cr / np.linalg.norm(cr)
+        t = tri_to_tet.get(tuple(sorted(int(q) for q in mesh.tri_conn[i])))
+        if t is None:
+            continue
+        X = mesh.xyz[mesh.node_idx_of(mesh.tet_conn[t])]
+        if normal @ (cen - X.mean(axis=0)) < 0:
+            normal = -normal
+        dofs = x[mesh.tet_edges[t]]
+        E = evaluate_edge_field(X, mesh.tet_orient[t], dofs, cen)
+        curl = (dofs * mesh.tet_orient[t].astype(float)) @ whitney_edge_curls(X)
+        H = curl / jwmu
+        E_tan = E - np.conj(E @ normal) * normal
+        H_tan = H - np.conj(H @ normal) * normal
+        for k, val in zip(("r", "n", "E_tan", "H_tan", "area"), (cen, normal, E_tan, H_tan, area)):
+            out[k].append(val)
+    if not out["r"]:
+        raise RuntimeError("extract_huygens_surface: no triangles found with surface_tag = %d" % surface_tag)
+    return {k: np.array(v) for k, v in out.items()}
+
+
+Z0_FREE = 376.730313668  # src/post/ntf.cpp:11
+
+
+def stratton_chu(r, n, E, H, area, theta, phi, k0):
+    """E_theta, E_phi at the direction list (theta[i], phi[i]); src/post/ntf.cpp:86-203 (2-D and 3-D share the kernel)."""
+    r, n, E, H, area = (np.asarray(a) for a in (r, n, E, H, area))
+    et, ep = np.zeros(len(theta), dtype=np.complex128), np.zeros(len(theta), dtype=np.complex128)
+    J = np.cross(n, H)
+    M = -np.cross(n, E)
+    for i, (th, ph) in enumerate(zip(theta, phi)):
+        rhat = np.array([np.sin(th) * np.cos(ph), np.sin(th) * np.sin(ph), np.cos(th)])
+        th_hat = np.array([np.cos(th) * np.cos(ph), np.cos(th) * np.sin(ph), -np.sin(th)])
+        ph_hat = np.array([-np.sin(ph), np.cos(ph), 0.0])
+        phase = np.exp(-1j * k0 * (r @ rhat))
+        term = Z0_FREE * np.cross(np.cross(rhat, J), rhat) - np.cross(rhat, M)
+        Efar = ((1j * k0 / (4 * np.pi)) * term * (phase * area)[:, None]).sum(axis=0)
+        et[i], ep[i] = Efar @ th_hat, Efar @ ph_hat
+    return et, ep
+
+
+def compute_directivity(theta, phi, E_theta, E_phi) -> float:  # src/post/ntf.cpp:209-262 (theta rows, phi columns)
+    pwr = np.abs(E_theta) ** 2 + np.abs(E_phi) ** 2
+    U_max = pwr.max() / (2 * Z0_FREE)
+    if U_max < np.finfo(float).eps:
+        return 0.0
+    Nth, Nph = pwr.shape
+    if Nth < 2 or Nph < 2:
+        return 1.0
+    dth, dph = (theta[-1] - theta[0]) / (Nth - 1), (phi[-1] - phi[0]) / (Nph - 1)
+    wt, wp = np.ones(Nth), np.ones(Nph)
+    wt[[0, -1]] = 0.5
+    wp[[0, -1]] = 0.5
+    P = ((pwr / (2 * Z0_FREE)) * (np.sin(theta) * wt)[:, None] * wp[None, :]).sum() * dth * dph
+    return 0.0 if P < np.finfo(float).eps else float(4 * np.pi * U_max / P)
