@@ -398,7 +398,11 @@ int efb_mesh_create(efb_ctx *ctx_, const efb_mesh_desc *d, efb_mesh **out) {
     if ((rc = dev_upload(c, &M->d_e2t_ptr, M->h_e2t_ptr.data(), M->h_e2t_ptr.size()))) return rc;
     if ((rc = dev_upload(c, &M->d_e2t_item, M->h_e2t_item.data(), M->h_e2t_item.size()))) return rc;
   }
-  if ((rc = dev_alloc(c, &M->d_geom, (size_t)std::max<int64_t>(1, nt)))) return rc;
+  if (asm_use_row_kernel()) {
+    if ((rc = dev_alloc(c, &M->d_geom, (size_t)std::max<int64_t>(1, nt)))) return rc;
+  }
+  if ((rc = dev_alloc(c, &M->d_rec, (size_t)std::max<int64_t>(1, nt)))) return rc;
+  if ((rc = dev_alloc(c, &M->d_e2t_ss, (size_t)std::max<int64_t>(1, 6 * nt)))) return rc;
   if ((rc = launch_tet_geometry(M))) return rc;
   // per-slot bounding boxes (PML profile, src/assemble_maxwell.cpp:66-89) on device
   if ((rc = dev_alloc(c, &M->d_slot_bbox, (size_t)std::max(1, M->n_slots) * 6))) return rc;
@@ -427,7 +431,7 @@ void efb_mesh_destroy(efb_mesh *mesh_) {
   cudaSetDevice(M->ctx->device);
   cudaStreamSynchronize(M->ctx->stream);  // pooled blocks may be handed out again immediately
   dfree(M->d_xyz); dfree(M->d_tet_nodes); dfree(M->d_tet_sign); dfree(M->d_tet_slot);
-  dfree(M->d_e2t_ptr); dfree(M->d_e2t_item); dfree(M->d_slot_bbox); dfree(M->d_geom); dfree(M->d_tet_edges);
+  dfree(M->d_e2t_ptr); dfree(M->d_e2t_item); dfree(M->d_slot_bbox); dfree(M->d_geom); dfree(M->d_rec); dfree(M->d_e2t_ss); dfree(M->d_tet_edges);
   delete M;
 }
 
@@ -642,16 +646,19 @@ static int system_create_rows(Mesh *M, int row0, int row1, int64_t n_extra, cons
     st.mark("device pattern + position map");
     int32_t maxrow = 0;
     for (int r = 0; r < m; ++r) maxrow = std::max(maxrow, S->h_rowptr[r + 1] - S->h_rowptr[r]);
-    if (maxrow > ASM_CHUNK_NNZ || maxrow > 32767) {
+    int lim_nnz, lim_rows;
+    asm_chunk_limits(&lim_nnz, &lim_rows);
+    S->asm_row_kernel = asm_use_row_kernel();
+    if (maxrow > lim_nnz || maxrow > 32767) {
       delete S;
-      return fail(c, EFB_ERR_LIMIT, "efb_system_create: a row has %d entries (limit %d)", maxrow, std::min(ASM_CHUNK_NNZ, 32767));
+      return fail(c, EFB_ERR_LIMIT, "efb_system_create: a row has %d entries (limit %d)", maxrow, std::min(lim_nnz, 32767));
     }
     std::vector<int32_t> chunk{0};
     int64_t acc = 0;
     int rows = 0;
     for (int r = 0; r < m; ++r) {
       const int len = S->h_rowptr[r + 1] - S->h_rowptr[r];
-      if (acc + len > ASM_CHUNK_NNZ || rows >= ASM_CHUNK_ROWS) {
+      if (acc + len > lim_nnz || rows >= lim_rows) {
         chunk.push_back(r);
         acc = 0;
         rows = 0;
@@ -735,9 +742,12 @@ static int system_create_rows(Mesh *M, int row0, int row1, int64_t n_extra, cons
     delete S;
     return fail(c, EFB_ERR_LIMIT, "efb_system_create: nnz %lld >= 2^31 (int32 CSR like Eigen's default index)", (long long)nnz);
   }
-  if (maxrow > ASM_CHUNK_NNZ || maxrow > 32767) {
+  int lim_nnz, lim_rows;
+  asm_chunk_limits(&lim_nnz, &lim_rows);
+  S->asm_row_kernel = asm_use_row_kernel();
+  if (maxrow > lim_nnz || maxrow > 32767) {
     delete S;
-    return fail(c, EFB_ERR_LIMIT, "efb_system_create: a row has %d entries (limit %d)", maxrow, std::min(ASM_CHUNK_NNZ, 32767));
+    return fail(c, EFB_ERR_LIMIT, "efb_system_create: a row has %d entries (limit %d)", maxrow, std::min(lim_nnz, 32767));
   }
   st.mark("row column lists + pos map");
   S->nnz = nnz;
@@ -753,13 +763,13 @@ static int system_create_rows(Mesh *M, int row0, int row1, int64_t n_extra, cons
     for (auto &x : th) x.join();
   }
   st.mark("concatenate");
-  // assembly chunks: consecutive rows with <= ASM_CHUNK_NNZ entries and <= ASM_CHUNK_ROWS rows
+  // assembly chunks: consecutive rows with <= lim_nnz entries and <= lim_rows rows
   std::vector<int32_t> chunk{0};
   {
     int64_t acc = 0;
     int rows = 0;
     for (int r = 0; r < m; ++r) {
-      if (acc + rowlen[r] > ASM_CHUNK_NNZ || rows >= ASM_CHUNK_ROWS) {
+      if (acc + rowlen[r] > lim_nnz || rows >= lim_rows) {
         chunk.push_back(r);
         acc = 0;
         rows = 0;

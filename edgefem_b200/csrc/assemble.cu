@@ -3,6 +3,7 @@
 // contraction).  Reference semantics: src/assemble_maxwell.cpp:114-347,
 // src/edge_basis.cpp:14-86, include/edgefem/materials/dispersive.hpp, src/sweep.cpp:82-172.
 #include <algorithm>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -72,7 +73,7 @@ __device__ __forceinline__ V3 vscale(double s, V3 a) { return {s * a.x, s * a.y,
 // so the per-frequency assembly never touches coordinates (except for tensor-PML tets).
 __global__ void k_tet_geometry(const double4 *__restrict__ xyz, const int4 *__restrict__ tet_nodes,
                                const uint8_t *__restrict__ tet_sign, const uint8_t *__restrict__ tet_slot, int n_tet,
-                               TetGeom *__restrict__ geom) {
+                               TetGeom *__restrict__ geom, TetRec *__restrict__ rec) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_tet) return;
   const int4 nd = tet_nodes[t];
@@ -99,13 +100,34 @@ __global__ void k_tet_geometry(const double4 *__restrict__ xyz, const int4 *__re
   G.V = fabs(det) / 6.0;
   G.sign_slot = (uint32_t)tet_sign[t] | ((uint32_t)tet_slot[t] << 8);
   G.pad = 0;
-  geom[t] = G;
+  if (geom) geom[t] = G;
+  TetRec R;
+  int q = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = i; j < 4; ++j) R.g[q++] = G.gg[i][j];
+  R.V = G.V;
+  R.Ieq = G.V / 10.0;
+  rec[t] = R;
+}
+
+// sign|slot word of every (edge, tet) incidence, in the order of the incidence list (coalesced for the assembly)
+__global__ void k_incidence_ss(const int32_t *__restrict__ e2t_item, const uint8_t *__restrict__ tet_sign,
+                               const uint8_t *__restrict__ tet_slot, long long n_inc, uint16_t *__restrict__ ss) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_inc) return;
+  const int t = e2t_item[i] >> 3;
+  ss[i] = (uint16_t)((unsigned)tet_sign[t] | ((unsigned)tet_slot[t] << 8));
 }
 
 int launch_tet_geometry(Mesh *M) {
   Ctx *c = M->ctx;
   if (M->n_tet == 0) return EFB_OK;
-  k_tet_geometry<<<(M->n_tet + 127) / 128, 128, 0, c->stream>>>(M->d_xyz, M->d_tet_nodes, M->d_tet_sign, M->d_tet_slot, M->n_tet, M->d_geom);
+  k_tet_geometry<<<(M->n_tet + 127) / 128, 128, 0, c->stream>>>(M->d_xyz, M->d_tet_nodes, M->d_tet_sign, M->d_tet_slot, M->n_tet, M->d_geom, M->d_rec);
+  EFB_CHECK_LAUNCH(c);
+  const long long n_inc = 6ll * M->n_tet;
+  k_incidence_ss<<<(unsigned)((n_inc + 255) / 256), 256, 0, c->stream>>>(M->d_e2t_item, M->d_tet_sign, M->d_tet_slot, n_inc, M->d_e2t_ss);
   EFB_CHECK_LAUNCH(c);
   return EFB_OK;
 }
@@ -148,7 +170,8 @@ __device__ __noinline__ c128 pml_stretch_of_tet(const efb_pml &pm, const double 
 }
 
 // ---------------------------------------------------------------- K1: volume assembly
-// grid (n_chunks, count).  One CTA owns a contiguous row chunk (<= ASM_CHUNK_NNZ entries): every
+// (thread-per-row variant, EDGEFEM_B200_ASM_KERNEL=row; superseded by k_assemble_volume_g below)
+// grid (n_chunks, count).  One CTA owns a contiguous row chunk (<= ASMR_CHUNK_NNZ entries): every
 // thread walks the incident tets of its rows (ascending tet index => deterministic sums), forms
 // the needed element-matrix row from the cached Gram record and accumulates into shared memory;
 // the chunk is then written ONCE, fully coalesced, with the Dirichlet mask applied.  No atomics.
@@ -167,9 +190,9 @@ k_assemble_volume(const TetGeom *__restrict__ geom, const double4 *__restrict__ 
   c128 *acc = (c128 *)smem_raw;                                   // [ASM_ACC_ENTRIES]
   c128 *s_kf = acc + ASM_ACC_ENTRIES;                             // [n_slots]
   c128 *s_mf = s_kf + n_slots;                                    // [n_slots]
-  int32_t *s_rowptr = (int32_t *)(s_mf + n_slots);                // [ASM_CHUNK_ROWS+1]
-  uint16_t *s_rowid = (uint16_t *)(s_rowptr + ASM_CHUNK_ROWS + 1); // [ASM_CHUNK_NNZ] local row of every entry
-  uint8_t *s_pml = (uint8_t *)(s_rowid + ASM_CHUNK_NNZ);          // [n_slots]
+  int32_t *s_rowptr = (int32_t *)(s_mf + n_slots);                // [ASMR_CHUNK_ROWS+1]
+  uint16_t *s_rowid = (uint16_t *)(s_rowptr + ASMR_CHUNK_ROWS + 1); // [ASMR_CHUNK_NNZ] local row of every entry
+  uint8_t *s_pml = (uint8_t *)(s_rowid + ASMR_CHUNK_NNZ);          // [n_slots]
 
   const int chunk = blockIdx.x, fi = blockIdx.y;
   const int r0 = chunk_row[chunk], r1 = chunk_row[chunk + 1];
@@ -291,8 +314,316 @@ k_assemble_volume(const TetGeom *__restrict__ geom, const double4 *__restrict__ 
 }
 
 size_t assemble_smem_bytes(int n_slots) {
-  return (size_t)ASM_ACC_ENTRIES * sizeof(c128) + 2 * (size_t)n_slots * sizeof(c128) + (ASM_CHUNK_ROWS + 1) * sizeof(int32_t) +
-         (size_t)ASM_CHUNK_NNZ * sizeof(uint16_t) + (size_t)n_slots + 16;
+  return (size_t)ASM_ACC_ENTRIES * sizeof(c128) + 2 * (size_t)n_slots * sizeof(c128) + (ASMR_CHUNK_ROWS + 1) * sizeof(int32_t) +
+         (size_t)ASMR_CHUNK_NNZ * sizeof(uint16_t) + (size_t)n_slots + 16;
+}
+
+// ---------------------------------------------------------------- K1 (batched): volume assembly
+// Same row-gather scheme and the same summation order as k_assemble_volume (bit-identical sums), with the lanes of a
+// warp mapped to 32 CONSECUTIVE (edge, tet) incidences of the row-sorted incidence list instead of to 32 rows:
+//   * a warp owns a contiguous range of the chunk's rows (ranges balanced by incidence count) and walks the flat
+//     incidence stream of those rows in batches of 32 -- every lane has work in every batch (no valence imbalance),
+//     the tet ids, sign|slot words and position blocks of a batch are contiguous in memory (coalesced), and only the
+//     96-byte tet records are gathered: three 256-bit loads per lane, each one whole 32-byte sector;
+//   * every lane forms its 6 entries in registers; the adds into the shared-memory chunk image are then done in
+//     rounds: in round r the r-th incidence (of this batch) of every row goes, so no two lanes of a round share a row
+//     and the adds into an entry happen in ascending tet order -- deterministic, no atomics.
+__host__ __device__ constexpr int asm_sym(int p, int q) {  // index of g(p,q) in TetRec::g (packed upper triangle)
+  return (p <= q) ? (p * (9 - p)) / 2 + (q - p) : (q * (9 - q)) / 2 + (p - q);
+}
+__device__ __forceinline__ void ldg256(const double *p, double &a, double &b, double &c, double &d) {
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+
+// REAL: every slot's 1/mu and eps are real and no PML is present (lossless media, the common case): the chunk image
+// holds doubles, the shared-memory adds move half the bytes, the imaginary parts are written as +0.0 -- exactly what
+// the complex path produces for such materials.
+template <bool PML, bool REAL>
+__global__ void __launch_bounds__(ASMB_THREADS, ASMB_CTAS_PER_SM)
+k_assemble_volume_b(const TetRec *__restrict__ rec, const double4 *__restrict__ xyz, const int4 *__restrict__ tet_nodes,
+                    const int32_t *__restrict__ e2t_ptr, const int32_t *__restrict__ e2t_item,
+                    const uint16_t *__restrict__ e2t_ss, const uint16_t *__restrict__ e2t_pos,
+                    const int32_t *__restrict__ chunk_row, const int32_t *__restrict__ rowptr,
+                    const int32_t *__restrict__ diag_pos, const uint8_t *__restrict__ dir,
+                    const SlotMat *__restrict__ slots, const efb_pole *__restrict__ poles,
+                    const double *__restrict__ slot_bbox, const double *__restrict__ omegas, int n_slots, int mode,
+                    int first, long long nnz, c128 *__restrict__ vals, long long pos_off) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  using acc_t = typename std::conditional<REAL, double, c128>::type;
+  acc_t *acc = (acc_t *)smem_raw;                               // [ASM_CHUNK_NNZ]
+  c128 *s_kf = (c128 *)(acc + ASM_CHUNK_NNZ);                   // [n_slots]
+  c128 *s_mf = s_kf + n_slots;                                  // [n_slots]
+  int32_t *s_rowptr = (int32_t *)(s_mf + n_slots);              // [ASM_CHUNK_ROWS+1]
+  int32_t *s_inc = s_rowptr + ASM_CHUNK_ROWS + 1;               // [ASM_CHUNK_ROWS+1]
+  uint8_t *s_dir = (uint8_t *)(s_inc + ASM_CHUNK_ROWS + 1);     // [ASM_CHUNK_ROWS]
+  uint8_t *s_pml = s_dir + ASM_CHUNK_ROWS;                      // [n_slots]
+  auto make_acc = [](double re) -> acc_t {
+    if constexpr (REAL) return re; else return cmake(re, 0.0);
+  };
+
+  const int chunk = blockIdx.x, fi = blockIdx.y;
+  const int r0 = chunk_row[chunk], r1 = chunk_row[chunk + 1];
+  const int base = rowptr[r0];
+  const int cnt = rowptr[r1] - base;
+  const int nrow = r1 - r0;
+  const double omega = omegas[fi];
+  const double k0 = omega / C0;
+  const double k0sq = k0 * k0;
+  const int tid = threadIdx.x;
+
+  for (int i = tid; i < cnt; i += ASMB_THREADS) acc[i] = make_acc(0.0);
+  for (int i = tid; i <= nrow; i += ASMB_THREADS) {
+    s_rowptr[i] = rowptr[r0 + i] - base;
+    s_inc[i] = e2t_ptr[r0 + i];
+  }
+  for (int i = tid; i < nrow; i += ASMB_THREADS) s_dir[i] = dir[r0 + i];
+  for (int s = tid; s < n_slots; s += ASMB_THREADS) {
+    const SlotMat sm = slots[s];
+    c128 eps = sm.eps_s, mu = sm.mu_s;
+    if (mode == 0) {
+      if (sm.em.kind != EFB_MODEL_NONE) eps = eval_model_eps(sm.em, poles, omega);
+      // every shipped model's eval_mu is the base-class 1.0 (dispersive.hpp:28-31)
+      if (sm.mm.kind != EFB_MODEL_NONE) mu = cmake(1.0, 0.0);
+    }
+    c128 kf, mf;
+    if (mode == 0) {
+      kf = cdiv(cmake(1.0, 0.0), mu);
+      mf = cscale(-k0sq, eps);
+    } else if (mode == 1) {
+      kf = cdiv(cmake(1.0, 0.0), mu);
+      mf = cmake(0.0, 0.0);
+    } else {
+      kf = cmake(0.0, 0.0);
+      mf = eps;
+    }
+    s_kf[s] = kf;
+    s_mf[s] = mf;
+    if (PML) s_pml[s] = (mode == 0) ? (uint8_t)sm.pml.kind : (uint8_t)0;
+  }
+  __syncthreads();
+
+  // Dirichlet rows: zeros (kept in the pattern) and the unit diagonal; no incidence of theirs is accumulated
+  const double diag_one = (mode == 2) ? 0.0 : 1.0;
+  for (int lr = tid; lr < nrow; lr += ASMB_THREADS) {
+    if (s_dir[lr]) {
+      const int dp = diag_pos[r0 + lr];
+      if (dp >= 0) acc[dp - base] = make_acc(diag_one);
+    }
+  }
+
+  const int lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = ASMB_THREADS / 32;
+  // row range of this warp: boundaries at equal shares of the chunk's incidences (whole rows)
+  const int inc0 = s_inc[0], inc_total = s_inc[nrow] - inc0;
+  int lr_a, lr_b;
+  {
+    int bound[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int wi = warp + q;
+      if (wi >= NW) {
+        bound[q] = nrow;
+      } else {
+        const int target = inc0 + (int)(((long long)inc_total * wi) / NW);
+        int lo = 0, hi = nrow;  // first row with s_inc[row] >= target
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (s_inc[mid] < target) lo = mid + 1; else hi = mid;
+        }
+        bound[q] = lo;
+      }
+    }
+    lr_a = bound[0];
+    lr_b = bound[1];
+  }
+  const int k_begin = s_inc[lr_a], k_end = s_inc[lr_b];
+  constexpr int PA[6] = {0, 0, 0, 1, 1, 2}, PB[6] = {1, 2, 3, 2, 3, 3};
+
+  // does a row of this warp's range own no incidence (an edge outside every tet)?  Then two rows start at the same
+  // incidence and the ballot look-up below cannot tell them apart: such warps use the binary search.
+  bool any_empty = false;
+  for (int r = lr_a + lane; r < lr_b; r += 32) any_empty |= (s_inc[r + 1] == s_inc[r]);
+  any_empty = __any_sync(0xffffffffu, any_empty);
+  int lr_prev = lr_a - 1;  // row of the last incidence before the current batch
+
+  for (int kb = k_begin; kb < k_end; kb += 32) {
+    const int k = kb + lane;
+    const bool in = k < k_end;
+    int item = 0;
+    unsigned ss = 0, p01 = 0x80008000u, p23 = 0x80008000u, p45 = 0x80008000u;
+    if (in) {
+      item = __ldg(e2t_item + k);
+      ss = __ldg(e2t_ss + k);
+      const uint32_t *pp = (const uint32_t *)(e2t_pos + ((size_t)k * 6 - pos_off));  // 12 bytes, 4-byte aligned
+      p01 = __ldg(pp);
+      p23 = __ldg(pp + 1);
+      p45 = __ldg(pp + 2);
+    }
+    // row of this incidence: last row of the warp's range whose first incidence is <= k
+    int lr;
+    if (!any_empty) {
+      // rows starting inside this batch, as a bit mask over the lanes: lane t looks at row lr_prev + 1 + t
+      const int cand = lr_prev + 1 + lane;
+      unsigned bit = 0;
+      if (cand < lr_b) {
+        const int st = s_inc[cand] - kb;
+        if (st < 32) bit = 1u << st;  // st >= 0: cand starts after the last incidence of the previous batch
+      }
+      const unsigned starts = __reduce_or_sync(0xffffffffu, bit);
+      lr = lr_prev + __popc(starts & (0xffffffffu >> (31 - lane)));
+      lr_prev += __popc(starts);
+    } else {
+      int lo = lr_a, hi = lr_b - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (s_inc[mid] <= k) lo = mid; else hi = mid - 1;
+      }
+      lr = lo;
+    }
+    const bool live = in && !s_dir[lr];
+    // rank of this incidence among the ones of its row inside this batch (rows are contiguous runs of lanes)
+    const int rb = lane - max(0, s_inc[lr] - kb);
+    acc_t v[6];
+    int pos[6] = {(int)(p01 & 0xffff), (int)(p01 >> 16), (int)(p23 & 0xffff), (int)(p23 >> 16), (int)(p45 & 0xffff), (int)(p45 >> 16)};
+    if (live) {
+      const int t = item >> 3, li = item & 7;
+      double g[12];
+      const double *rp = (const double *)(rec + t);
+      ldg256(rp, g[0], g[1], g[2], g[3]);
+      ldg256(rp + 4, g[4], g[5], g[6], g[7]);
+      ldg256(rp + 8, g[8], g[9], g[10], g[11]);
+      const double V = g[10], Ieq = g[11];
+      const unsigned sg = ss & 0xffu;
+      const int slot = (int)((ss >> 8) & 0xffu);
+      c128 kf = s_kf[slot], mf = s_mf[slot];
+      if (PML) {
+        if (s_pml[slot]) {
+          const c128 sv = pml_stretch_of_tet(slots[slot].pml, slot_bbox + slot * 6, xyz, tet_nodes, t, omega);
+          kf = cdiv(kf, sv);
+          mf = cmul(mf, sv);
+        }
+      }
+      const int a = (li < 3) ? 0 : (li < 5 ? 1 : 2);
+      const int b = (li == 0) ? 1 : ((li == 1 || li == 3) ? 2 : 3);
+      // rows a and b of the Gram matrix out of the packed upper triangle
+      double ra[4], rb4[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        double xa = 0.0, xb = 0.0;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const double gv = g[asm_sym(p, q)];
+          if (a == p) xa = gv;
+          if (b == p) xb = gv;
+        }
+        ra[q] = xa;
+        rb4[q] = xb;
+      }
+      const double V4 = 4.0 * V, Ine = 0.5 * Ieq;
+      const unsigned si = (sg >> li) & 1u;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const int c = PA[j], d = PB[j];
+        const double Kj = V4 * (ra[c] * rb4[d] - ra[d] * rb4[c]);
+        double Mj = 0.0;
+        Mj += rb4[d] * ((a == c) ? Ieq : Ine);
+        Mj -= rb4[c] * ((a == d) ? Ieq : Ine);
+        Mj -= ra[d] * ((b == c) ? Ieq : Ine);
+        Mj += ra[c] * ((b == d) ? Ieq : Ine);
+        const double sgn = (((sg >> j) & 1u) ^ si) ? -1.0 : 1.0;
+        const double kk = Kj * sgn, mm = Mj * sgn;
+        if constexpr (REAL) v[j] = kk * kf.x + mm * mf.x;
+        else v[j] = cmake(kk * kf.x + mm * mf.x, kk * kf.y + mm * mf.y);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        v[j] = make_acc(0.0);
+        pos[j] = 0x8000;
+      }
+    }
+    // rounds: bit 15 of a position = the column is a Dirichlet edge (entry stays an explicit zero)
+    acc_t *arow = acc + s_rowptr[lr];
+    const int n_round = __reduce_max_sync(0xffffffffu, live ? rb + 1 : 0);
+    for (int r = 0; r < n_round; ++r) {
+      if (live && rb == r) {
+        acc_t o[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) o[j] = arow[pos[j] & 0x7fff];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          if (!(pos[j] & 0x8000)) {
+            if constexpr (REAL) arow[pos[j]] = o[j] + v[j];
+            else arow[pos[j]] = cadd(o[j], v[j]);
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+
+  // write-out: a pure shared -> global copy, fully coalesced 16-byte streaming stores
+  c128 *__restrict__ out = vals + (size_t)(first + fi) * (size_t)nnz + base;
+#pragma unroll 4
+  for (int i = tid; i < cnt; i += ASMB_THREADS) {
+    if constexpr (REAL) __stcs(&out[i], cmake(acc[i], 0.0));
+    else __stcs(&out[i], acc[i]);
+  }
+}
+
+size_t assemble_b_smem_bytes(int n_slots) {
+  return (size_t)ASM_CHUNK_NNZ * sizeof(c128) + 2 * (size_t)n_slots * sizeof(c128) + 2 * (size_t)(ASM_CHUNK_ROWS + 1) * sizeof(int32_t) +
+         ASM_CHUNK_ROWS + (size_t)n_slots + 16;
+}
+
+bool asm_use_row_kernel() {
+  static const bool v = [] {
+    const char *e = getenv("EDGEFEM_B200_ASM_KERNEL");
+    return e && strcmp(e, "row") == 0;
+  }();
+  return v;
+}
+void asm_chunk_limits(int *max_nnz, int *max_rows) {
+  if (asm_use_row_kernel()) {
+    *max_nnz = ASMR_CHUNK_NNZ;
+    *max_rows = ASMR_CHUNK_ROWS;
+  } else {
+    *max_nnz = ASM_CHUNK_NNZ;
+    *max_rows = ASM_CHUNK_ROWS;
+  }
+}
+
+template <bool PML, bool REAL>
+static int launch_assemble_b2(System *S, int first, int count, int mode, const unsigned char *blob, size_t off_poles, size_t off_om) {
+  Ctx *c = S->ctx;
+  Mesh *M = S->mesh;
+  const int ns = M->n_slots;
+  const size_t smem = assemble_b_smem_bytes(ns);
+  EFB_CUDA(c, cudaFuncSetAttribute(k_assemble_volume_b<PML, REAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)assemble_b_smem_bytes(MAX_SLOTS)));
+  dim3 grid((unsigned)S->n_chunks, (unsigned)count);
+  const long long k_off = (long long)M->h_e2t_ptr[S->row0];
+  k_assemble_volume_b<PML, REAL><<<grid, ASMB_THREADS, smem, c->stream>>>(
+      M->d_rec, M->d_xyz, M->d_tet_nodes, M->d_e2t_ptr + S->row0, M->d_e2t_item, M->d_e2t_ss, S->d_e2t_pos, S->d_chunk_row,
+      S->d_rowptr, S->d_diag_pos, S->d_dir, (const SlotMat *)blob, (const efb_pole *)(blob + off_poles), M->d_slot_bbox,
+      (const double *)(blob + off_om), ns, mode, first, (long long)S->nnz, S->d_vals, k_off * 6);
+  EFB_CHECK_LAUNCH(c);
+  return EFB_OK;
+}
+static int launch_assemble_b(System *S, int first, int count, int mode, const unsigned char *blob, size_t off_poles, size_t off_om) {
+  // the PML variant (per-tet stretch from the coordinates) only when a slot of this call carries a PML
+  // and the real-image variant when every factor 1/mu, eps of this call is real
+  bool any_pml = false, all_real = true;
+  const SlotMat *hs = (const SlotMat *)S->last_mat_blob.data();
+  for (int i = 0; i < S->mesh->n_slots; ++i) {
+    if (mode == 0) any_pml |= hs[i].pml.kind != EFB_PML_NONE;
+    all_real &= hs[i].eps_s.y == 0.0 && hs[i].mu_s.y == 0.0;
+    if (mode == 0) all_real &= hs[i].em.kind == EFB_MODEL_NONE;  // a dispersive model evaluates to a complex eps
+  }
+  static const bool no_real = getenv("EDGEFEM_B200_ASM_NO_REAL") != nullptr;
+  if (any_pml) return launch_assemble_b2<true, false>(S, first, count, mode, blob, off_poles, off_om);
+  if (all_real && !no_real) return launch_assemble_b2<false, true>(S, first, count, mode, blob, off_poles, off_om);
+  return launch_assemble_b2<false, false>(S, first, count, mode, blob, off_poles, off_om);
 }
 
 // blob layout: [SlotMat x n_slots][efb_pole x n_poles][double omega x count]
@@ -315,6 +646,8 @@ int assemble_launch(System *S, int first, int count, int mode) {
   }
   EFB_CUDA(c, cudaMemcpyAsync(S->d_mat_blob, S->last_mat_blob.data(), total, cudaMemcpyHostToDevice, c->stream));
   const unsigned char *blob = (const unsigned char *)S->d_mat_blob;
+  if (!S->asm_row_kernel) return launch_assemble_b(S, first, count, mode, blob, off_poles, off_om);
+  if (!M->d_geom) return fail(c, EFB_ERR_STATE, "assembly: the mesh was uploaded without the thread-per-row geometry cache");
   const size_t smem = assemble_smem_bytes(ns);
   EFB_CUDA(c, cudaFuncSetAttribute(k_assemble_volume, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)assemble_smem_bytes(MAX_SLOTS)));
   dim3 grid((unsigned)S->n_chunks, (unsigned)count);

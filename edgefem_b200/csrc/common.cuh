@@ -46,10 +46,36 @@ __host__ __device__ __forceinline__ c128 cfma(c128 a, c128 b, c128 acc) {  // ac
   return acc;
 }
 
+// ------------------------------------------------------------------ cp.async (LDGSTS) helpers
+// predicated in PTX so that the lanes of a warp stay converged (one LDGSTS per call, no branches)
+__device__ __forceinline__ void cp_async16_if(bool p, unsigned smem_dst, const void *gsrc) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q cp.async.cg.shared.global [%0], [%1], 16;\n\t}" ::"r"(smem_dst), "l"(gsrc), "r"((unsigned)p) : "memory");
+}
+__device__ __forceinline__ void cp_async4_if(bool p, unsigned smem_dst, const void *gsrc) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q cp.async.ca.shared.global [%0], [%1], 4;\n\t}" ::"r"(smem_dst), "l"(gsrc), "r"((unsigned)p) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// 16-byte copy that reads only the first src_bytes (<= 16) bytes of the source and zero-fills the rest
+__device__ __forceinline__ void cp_async16_zfill_if(bool p, unsigned smem_dst, const void *gsrc, unsigned src_bytes) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q cp.async.cg.shared.global [%0], [%1], 16, %3;\n\t}" ::"r"(smem_dst), "l"(gsrc), "r"((unsigned)p), "r"(src_bytes) : "memory");
+}
+
 // ------------------------------------------------------------------ limits
-constexpr int ASM_CHUNK_NNZ = 5376;   // matrix entries per assembly CTA
-constexpr int ASM_CHUNK_ROWS = 768;   // rows per assembly CTA (rowptr slice in smem; also the bank-skew padding)
-constexpr int ASM_ACC_ENTRIES = ASM_CHUNK_NNZ + ASM_CHUNK_ROWS;  // 96 KB of c128 accumulators
+// Row-gather volume assembly, batched variant (k_assemble_volume_b, the default): a CTA owns a chunk of consecutive
+// rows with <= ASM_CHUNK_NNZ entries; the lanes of a warp take 32 consecutive (edge, tet) incidences per step.  The older
+// thread-per-row kernel (k_assemble_volume, EDGEFEM_B200_ASM_KERNEL=row) uses the larger ASMR_* chunks.
+constexpr int ASM_CHUNK_NNZ = 3840;   // matrix entries per assembly CTA (60 KB of c128 accumulators)
+constexpr int ASM_CHUNK_ROWS = 512;   // rows per assembly CTA (rowptr / incidence-pointer slices in smem)
+constexpr int ASMB_THREADS = 256;
+constexpr int ASMB_CTAS_PER_SM = 3;
+constexpr int ASMR_CHUNK_NNZ = 5376;  // thread-per-row kernel: entries per CTA
+constexpr int ASMR_CHUNK_ROWS = 768;  // thread-per-row kernel: rows per CTA (also the bank-skew padding)
+constexpr int ASM_ACC_ENTRIES = ASMR_CHUNK_NNZ + ASMR_CHUNK_ROWS;  // 96 KB of c128 accumulators
 constexpr int ASM_THREADS = 384;
 constexpr int MAX_SLOTS = 256;        // distinct physical tags
 constexpr int NSCAL = 16;             // per-system device scalars (c128)
@@ -64,6 +90,15 @@ struct alignas(16) TetGeom {
   uint32_t pad;
 };
 static_assert(sizeof(TetGeom) == 144, "TetGeom layout");
+
+// the same information in 96 B = three 32-byte sectors (one 256-bit load each): the 10 distinct Gram products
+// (row-major upper triangle: 00 01 02 03 11 12 13 22 23 33), the volume and V/10; sign|slot lives in Mesh::d_e2t_ss
+struct alignas(32) TetRec {
+  double g[10];
+  double V;
+  double Ieq;          // V / 10 (the division of src/edge_basis.cpp:28-30 done once per tet); V / 20 = Ieq / 2 exactly
+};
+static_assert(sizeof(TetRec) == 96, "TetRec layout");
 
 // ------------------------------------------------------------------ handles
 struct Ctx {
@@ -96,7 +131,9 @@ struct Mesh {
   int32_t *d_e2t_item = nullptr;     // [6*n_tet]
   int32_t *d_tet_edges = nullptr;    // [6*n_tet] (large meshes only: input of the device pattern builder)
   double *d_slot_bbox = nullptr;     // [n_slots*6] min xyz, max xyz over the slot's tets
-  TetGeom *d_geom = nullptr;         // [n_tet] frequency-independent element geometry
+  TetGeom *d_geom = nullptr;         // [n_tet] frequency-independent element geometry (thread-per-row kernel only)
+  TetRec *d_rec = nullptr;           // [n_tet] the same, packed (batched kernel)
+  uint16_t *d_e2t_ss = nullptr;      // [6*n_tet] sign | slot << 8 of the incidence's tet
 };
 
 struct Port;
@@ -119,6 +156,7 @@ struct System {
   uint16_t *d_e2t_pos = nullptr;   // [6*n_tet*6] column offsets inside the row (bit 15: Dirichlet column)
   int32_t *d_chunk_row = nullptr;  // [n_chunks+1]
   int n_chunks = 0;
+  bool asm_row_kernel = false;     // chunks were cut for the thread-per-row kernel (ASMR_* limits)
   // CSR-stream SpMV: row-aligned chunks of <= SPMV_STREAM_W entries (one warp each); null if a row is longer
   int32_t *d_sp_chunk = nullptr;   // [n_sp_chunks+1]
   int n_sp_chunks = 0;
@@ -228,7 +266,7 @@ template <typename T>
 int dev_alloc(Ctx *ctx, T **p, size_t n) {
   *p = nullptr;
   if (n == 0) n = 1;
-  const size_t bytes = pool_round(n * sizeof(T));
+  const size_t bytes = pool_round(n * sizeof(T) + 16);  // 16 B of slack: 16-byte bulk copies of aligned supersets may read past the last element
   if (void *q = pool_get(ctx->device, bytes)) {
     *p = (T *)q;
     return EFB_OK;
@@ -273,5 +311,7 @@ int device_pattern(System *S, bool *done);
 void dist_free(System *s);
 int assemble_launch(System *s, int first, int count, int mode);
 int launch_tet_geometry(Mesh *m);
+bool asm_use_row_kernel();   // EDGEFEM_B200_ASM_KERNEL=row selects the older thread-per-row assembly kernel
+void asm_chunk_limits(int *max_nnz, int *max_rows);
 
 }  // namespace efb

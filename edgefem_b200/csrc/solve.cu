@@ -211,6 +211,12 @@ k_spmv(SolveDev D, int first_matrix, const c128 *__restrict__ x, c128 *__restric
   }
 }
 
+// Product i of a chunk is parked at slot i + i/16: the row sums read the products with one lane per row, i.e. at a
+// stride of one row length (~16 entries = 256 B), which without the skew lands every lane of a 16-byte access phase
+// in the same bank group (measured: 12 M bank conflicts, 60 % of all L1 data-pipe wavefronts of the SpMV).
+__device__ __forceinline__ int spmv_slot(int i) { return i + (i >> 4); }
+constexpr int SPMV_SLOTS = SPMV_STREAM_W + SPMV_STREAM_W / 16;  // 272
+
 // CSR-stream SpMV (large matrices): a warp owns a row-aligned chunk of <= SPMV_STREAM_W entries and at
 // most 32 rows.  Phase 1 streams the chunk's values/columns with fully coalesced, independent
 // 16-byte loads (8 in flight per lane), gathers x and parks the products in shared memory;
@@ -219,7 +225,7 @@ template <int NR, int DOT>
 __global__ void __launch_bounds__(256)
 k_spmv_stream(SolveDev D, const int32_t *__restrict__ sp_chunk, int n_chunks, int first_matrix, const c128 *__restrict__ x,
               c128 *__restrict__ y, const c128 *__restrict__ wv, int slot0, int slot1, int use_active) {
-  __shared__ c128 prod[8][NR][SPMV_STREAM_W];
+  __shared__ c128 prod[8][NR][SPMV_SLOTS];
   const int f = first_matrix + blockIdx.y;
   const int s0 = f * D.n_rhs + blockIdx.z * NR;
   bool any = false;
@@ -254,7 +260,7 @@ k_spmv_stream(SolveDev D, const int32_t *__restrict__ sp_chunk, int n_chunks, in
     for (int j = 0; j < SPMV_STREAM_W / 32; ++j) {
       if (c[j] >= 0) {
 #pragma unroll
-        for (int r = 0; r < NR; ++r) prod[wid][r][lane + 32 * j] = cmul(a[j], __ldg(&x[(size_t)(s0 + r) * D.m + c[j]]));
+        for (int r = 0; r < NR; ++r) prod[wid][r][spmv_slot(lane + 32 * j)] = cmul(a[j], __ldg(&x[(size_t)(s0 + r) * D.m + c[j]]));
       }
     }
     __syncwarp();
@@ -263,7 +269,7 @@ k_spmv_stream(SolveDev D, const int32_t *__restrict__ sp_chunk, int n_chunks, in
 #pragma unroll
       for (int r = 0; r < NR; ++r) {
         c128 acc = cmake(0.0, 0.0);
-        for (int k = rs - k0; k < re - k0; ++k) acc = cadd(acc, prod[wid][r][k]);
+        for (int k = rs - k0; k < re - k0; ++k) acc = cadd(acc, prod[wid][r][spmv_slot(k)]);
         const size_t idx = (size_t)(s0 + r) * D.m + row;
         y[idx] = acc;
         if (DOT == 1) {
@@ -291,6 +297,285 @@ k_spmv_stream(SolveDev D, const int32_t *__restrict__ sp_chunk, int n_chunks, in
         sc[slot0] = cmake(tot[0], tot[1]);
         if (DOT == 3) sc[slot1] = cmake(tot[2], 0.0);
       }
+    }
+  }
+}
+
+// CSR-stream SpMV, software-pipelined through shared memory (the default for large matrices).  Same chunks, same
+// products and the same in-order row sums as k_spmv_stream (bit-identical y), but the matrix stream never sits in
+// registers: while a warp gathers x and reduces chunk i, the values / columns / row pointers of chunk i+1 are already
+// on their way into the other stage of its shared-memory ring (cp.async, 16-byte pieces; the column slice is fetched
+// as the 16-byte-aligned superset).  2 CTAs x 8 warps per SM, every warp always has ~5 KB of the stream in flight.
+constexpr int SPMV_PIPE_COLS = SPMV_STREAM_W + 4;  // aligned superset of the column slice
+constexpr int SPMV_VAL_BYTES = SPMV_SLOTS * 16;  // value area of a stage, sized for the skewed products written in place
+constexpr int SPMV_PIPE_STAGE = SPMV_VAL_BYTES + SPMV_PIPE_COLS * 4 + 36 * 4;  // 5536 B
+struct ChunkDesc {
+  int r0, nrow, k0, k1;
+};
+__device__ __forceinline__ ChunkDesc load_chunk_desc(const int32_t *__restrict__ sp_chunk, const int32_t *__restrict__ rowptr, int ch,
+                                                      int n_chunks) {
+  ChunkDesc d{0, 0, 0, 0};
+  if (ch < n_chunks) {
+    d.r0 = __ldg(&sp_chunk[ch]);
+    const int r1 = __ldg(&sp_chunk[ch + 1]);
+    d.nrow = r1 - d.r0;
+    d.k0 = __ldg(&rowptr[d.r0]);
+    d.k1 = __ldg(&rowptr[r1]);
+  }
+  return d;
+}
+
+template <int DOT>
+__global__ void __launch_bounds__(256, 2)
+k_spmv_pipe(SolveDev D, const int32_t *__restrict__ sp_chunk, int n_chunks, int first_matrix, const c128 *__restrict__ x,
+            c128 *__restrict__ y, const c128 *__restrict__ wv, int slot0, int slot1, int use_active) {
+  extern __shared__ __align__(16) unsigned char pipe_smem[];
+  const int f = first_matrix + blockIdx.y;
+  const int s0 = f * D.n_rhs;
+  if (use_active && !D.state[s0 * 4 + ST_ACTIVE]) return;
+  const c128 *__restrict__ av = D.vals + (size_t)f * D.nnz;
+  const c128 *__restrict__ xs = x + (size_t)s0 * D.m;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  unsigned char *wbase = pipe_smem + (size_t)wid * 2 * SPMV_PIPE_STAGE;
+  const unsigned wbase_s = (unsigned)__cvta_generic_to_shared(wbase);
+  double dots[4] = {0.0, 0.0, 0.0, 0.0};
+  const int stride = gridDim.x * 8;
+  int ch = blockIdx.x * 8 + wid;
+
+  auto issue = [&](int stage, const ChunkDesc &d) {
+    const unsigned sb = wbase_s + (unsigned)stage * SPMV_PIPE_STAGE;
+    const int n = d.k1 - d.k0;
+#pragma unroll
+    for (int j = 0; j < SPMV_STREAM_W / 32; ++j) {
+      const int i = lane + 32 * j;
+      cp_async16_if(i < n, sb + 16u * (unsigned)i, av + d.k0 + i);
+    }
+    const int ka = d.k0 & ~3;  // 16-byte aligned start of the column slice
+    const int np = (d.k1 - ka + 3) >> 2;  // 16-byte pieces (<= 65)
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const int pc = lane + 32 * q;
+      const long long rem = D.nnz - ((long long)ka + 4 * pc);  // ints left in the array (the last piece may be short)
+      cp_async16_zfill_if(pc < np, sb + SPMV_VAL_BYTES + 16u * (unsigned)pc, D.colidx + ka + 4 * pc,
+                          rem >= 4 ? 16u : (unsigned)(rem > 0 ? 4 * rem : 0));
+    }
+    cp_async4_if(lane <= d.nrow && d.nrow > 0, sb + SPMV_VAL_BYTES + SPMV_PIPE_COLS * 4 + 4u * (unsigned)lane, D.rowptr + d.r0 + lane);
+  };
+
+  ChunkDesc cur = load_chunk_desc(sp_chunk, D.rowptr, ch, n_chunks);
+  ChunkDesc nxt = load_chunk_desc(sp_chunk, D.rowptr, ch + stride, n_chunks);
+  issue(0, cur);
+  cp_async_commit();
+  int st = 0;
+  for (; ch < n_chunks; ch += stride) {
+    issue(st ^ 1, nxt);  // an exhausted descriptor (nrow = 0, k0 = k1 = 0) issues nothing
+    cp_async_commit();
+    const ChunkDesc nn = load_chunk_desc(sp_chunk, D.rowptr, ch + 2 * stride, n_chunks);
+    cp_async_wait<1>();
+    __syncwarp();
+    unsigned char *sb = wbase + (size_t)st * SPMV_PIPE_STAGE;
+    c128 *sv = (c128 *)sb;
+    const int32_t *sc = (const int32_t *)(sb + SPMV_VAL_BYTES) + (cur.k0 & 3);
+    const int32_t *rp = (const int32_t *)(sb + SPMV_VAL_BYTES + SPMV_PIPE_COLS * 4);
+    const int n = cur.k1 - cur.k0;
+    int c[SPMV_STREAM_W / 32];
+    c128 xv[SPMV_STREAM_W / 32];
+#pragma unroll
+    for (int j = 0; j < SPMV_STREAM_W / 32; ++j) {
+      const int i = lane + 32 * j;
+      c[j] = (i < n) ? sc[i] : -1;
+    }
+#pragma unroll
+    for (int j = 0; j < SPMV_STREAM_W / 32; ++j) xv[j] = (c[j] >= 0) ? __ldg(&xs[c[j]]) : cmake(0.0, 0.0);
+    // products in place, at the skewed slots: every lane reads its values first (slot(i) >= i would run into values
+    // another lane has not read yet)
+#pragma unroll
+    for (int j = 0; j < SPMV_STREAM_W / 32; ++j) {
+      const int i = lane + 32 * j;
+      if (c[j] >= 0) xv[j] = cmul(sv[i], xv[j]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < SPMV_STREAM_W / 32; ++j) {
+      if (c[j] >= 0) sv[spmv_slot(lane + 32 * j)] = xv[j];
+    }
+    __syncwarp();
+    if (lane < cur.nrow) {
+      const int row = cur.r0 + lane;
+      const int rs = rp[lane] - cur.k0, re = rp[lane + 1] - cur.k0;
+      c128 acc = cmake(0.0, 0.0);
+      for (int k = rs; k < re; ++k) acc = cadd(acc, sv[spmv_slot(k)]);
+      const size_t idx = (size_t)s0 * D.m + row;
+      y[idx] = acc;
+      if (DOT == 1) {
+        const c128 q = cmul(wv[idx], acc);
+        dots[0] += q.x; dots[1] += q.y;
+      } else if (DOT == 2) {
+        const c128 q = cmulconj(wv[idx], acc);
+        dots[0] += q.x; dots[1] += q.y;
+      } else if (DOT == 3) {
+        const c128 q = cmulconj(acc, wv[idx]);
+        dots[0] += q.x; dots[1] += q.y;
+        dots[2] += cabs2(acc);
+      }
+    }
+    __syncwarp();
+    cur = nxt;
+    nxt = nn;
+    st ^= 1;
+  }
+  cp_async_wait<0>();
+  if (DOT != 0) {
+    double tot[4];
+    if (reduce_and_ticket<4>(dots, partial_of(D, s0), D.counter + s0, tot)) {
+      c128 *sc = scal_of(D, s0);
+      sc[slot0] = cmake(tot[0], tot[1]);
+      if (DOT == 3) sc[slot1] = cmake(tot[2], 0.0);
+    }
+  }
+}
+
+// CSR-stream SpMV with the matrix stream moved by the TMA engine (the default for large matrices).  The SpMV is bound
+// by the L1/LSU wavefront rate, not by HBM: the x gather costs one wavefront per distinct 128-byte line of every load,
+// and in k_spmv_stream / k_spmv_pipe the value and column streams go through the same pipe.  Here lane 0 of a warp
+// issues two bulk copies per chunk (cp.async.bulk global -> shared: <= 4 KB of values, <= 1 KB of columns as the
+// 16-byte-aligned superset) that complete on an mbarrier; the copies bypass L1 entirely, run one chunk ahead of the
+// warp (2-stage ring) and leave the LSU to the x gather, the in-place products and the in-order row sums.
+// Same chunks, products and summation order as k_spmv_stream: bit-identical y.
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
+  unsigned ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+constexpr int SPMV_TMA_STAGE = SPMV_VAL_BYTES + SPMV_PIPE_COLS * 4;  // 5392 B (16-byte multiple)
+
+template <int DOT>
+__global__ void __launch_bounds__(256, 2)
+k_spmv_tma(SolveDev D, const int32_t *__restrict__ sp_chunk, int n_chunks, int first_matrix, const c128 *__restrict__ x,
+           c128 *__restrict__ y, const c128 *__restrict__ wv, int slot0, int slot1, int use_active) {
+  extern __shared__ __align__(128) unsigned char tma_smem[];
+  const int f = first_matrix + blockIdx.y;
+  const int s0 = f * D.n_rhs;
+  if (use_active && !D.state[s0 * 4 + ST_ACTIVE]) return;
+  const c128 *__restrict__ av = D.vals + (size_t)f * D.nnz;
+  const c128 *__restrict__ xs = x + (size_t)s0 * D.m;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  unsigned char *wbase = tma_smem + (size_t)wid * 2 * SPMV_TMA_STAGE;
+  const unsigned wbase_s = (unsigned)__cvta_generic_to_shared(wbase);
+  const unsigned bar_s = (unsigned)__cvta_generic_to_shared(tma_smem + (size_t)8 * 2 * SPMV_TMA_STAGE) + (unsigned)wid * 16u;
+  if (lane == 0) {
+    mbar_init(bar_s, 1);
+    mbar_init(bar_s + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  double dots[4] = {0.0, 0.0, 0.0, 0.0};
+  const int stride = gridDim.x * 8;
+  int ch = blockIdx.x * 8 + wid;
+
+  // lane 0: one arrive.expect_tx and two bulk copies per chunk (an exhausted descriptor copies nothing)
+  auto issue = [&](int stage, const ChunkDesc &d) {
+    if (lane == 0 && d.nrow > 0) {
+      const unsigned sb = wbase_s + (unsigned)stage * SPMV_TMA_STAGE;
+      const unsigned bar = bar_s + 8u * (unsigned)stage;
+      const int ka = d.k0 & ~3;
+      const unsigned vbytes = (unsigned)(d.k1 - d.k0) * 16u;
+      const unsigned cbytes = (unsigned)((d.k1 - ka + 3) >> 2) * 16u;
+      fence_proxy_async();  // the stage was last touched by ordinary shared-memory accesses of this warp
+      mbar_expect_tx(bar, vbytes + cbytes);
+      if (vbytes) bulk_g2s(sb, av + d.k0, vbytes, bar);
+      if (cbytes) bulk_g2s(sb + SPMV_VAL_BYTES, D.colidx + ka, cbytes, bar);
+    }
+  };
+
+  ChunkDesc cur = load_chunk_desc(sp_chunk, D.rowptr, ch, n_chunks);
+  ChunkDesc nxt = load_chunk_desc(sp_chunk, D.rowptr, ch + stride, n_chunks);
+  int rs_cur = (lane <= cur.nrow && cur.nrow > 0) ? __ldg(&D.rowptr[cur.r0 + lane]) : 0;
+  issue(0, cur);
+  int st = 0;
+  unsigned phase0 = 0, phase1 = 0;  // parity each stage's barrier completes next
+  for (; ch < n_chunks; ch += stride) {
+    issue(st ^ 1, nxt);
+    const ChunkDesc nn = load_chunk_desc(sp_chunk, D.rowptr, ch + 2 * stride, n_chunks);
+    const int rs_nxt = (lane <= nxt.nrow && nxt.nrow > 0) ? __ldg(&D.rowptr[nxt.r0 + lane]) : 0;
+    {
+      const unsigned bar = bar_s + 8u * (unsigned)st;
+      const unsigned par = st ? phase1 : phase0;
+      while (!mbar_try_wait(bar, par)) {
+      }
+      if (st) phase1 ^= 1u; else phase0 ^= 1u;
+    }
+    unsigned char *sb = wbase + (size_t)st * SPMV_TMA_STAGE;
+    c128 *sv = (c128 *)sb;
+    const int32_t *sc = (const int32_t *)(sb + SPMV_VAL_BYTES) + (cur.k0 & 3);
+    const int n = cur.k1 - cur.k0;
+    int c[SPMV_STREAM_W / 32];
+    c128 xv[SPMV_STREAM_W / 32];
+#pragma unroll
+    for (int j = 0; j < SPMV_STREAM_W / 32; ++j) {
+      const int i = lane + 32 * j;
+      c[j] = (i < n) ? sc[i] : -1;
+    }
+#pragma unroll
+    for (int j = 0; j < SPMV_STREAM_W / 32; ++j) xv[j] = (c[j] >= 0) ? __ldg(&xs[c[j]]) : cmake(0.0, 0.0);
+    // products in place, at the skewed slots: every lane reads its values first (slot(i) >= i would run into values
+    // another lane has not read yet)
+#pragma unroll
+    for (int j = 0; j < SPMV_STREAM_W / 32; ++j) {
+      const int i = lane + 32 * j;
+      if (c[j] >= 0) xv[j] = cmul(sv[i], xv[j]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < SPMV_STREAM_W / 32; ++j) {
+      if (c[j] >= 0) sv[spmv_slot(lane + 32 * j)] = xv[j];
+    }
+    __syncwarp();
+    const int re_cur = __shfl_down_sync(0xffffffffu, rs_cur, 1);
+    if (lane < cur.nrow) {
+      const int row = cur.r0 + lane;
+      const int rs = rs_cur - cur.k0, re = re_cur - cur.k0;
+      c128 acc = cmake(0.0, 0.0);
+      for (int k = rs; k < re; ++k) acc = cadd(acc, sv[spmv_slot(k)]);
+      const size_t idx = (size_t)s0 * D.m + row;
+      y[idx] = acc;
+      if (DOT == 1) {
+        const c128 q = cmul(wv[idx], acc);
+        dots[0] += q.x; dots[1] += q.y;
+      } else if (DOT == 2) {
+        const c128 q = cmulconj(wv[idx], acc);
+        dots[0] += q.x; dots[1] += q.y;
+      } else if (DOT == 3) {
+        const c128 q = cmulconj(acc, wv[idx]);
+        dots[0] += q.x; dots[1] += q.y;
+        dots[2] += cabs2(acc);
+      }
+    }
+    __syncwarp();
+    cur = nxt;
+    nxt = nn;
+    rs_cur = rs_nxt;
+    st ^= 1;
+  }
+  if (DOT != 0) {
+    double tot[4];
+    if (reduce_and_ticket<4>(dots, partial_of(D, s0), D.counter + s0, tot)) {
+      c128 *sc = scal_of(D, s0);
+      sc[slot0] = cmake(tot[0], tot[1]);
+      if (DOT == 3) sc[slot1] = cmake(tot[2], 0.0);
     }
   }
 }
@@ -1113,6 +1398,39 @@ static int launch_spmv(System *S, const SolveDev &D, int first, int count, const
                        int slot1, int use_active) {
   Ctx *c = S->ctx;
   if (S->d_sp_chunk && S->n_rhs == 1 && !getenv("EDGEFEM_B200_NO_STREAM_SPMV")) {
+    static const int variant = [] {  // 0: TMA bulk stream (default) | 1: cp.async stream | 2: register stream
+      const char *e = getenv("EDGEFEM_B200_SPMV_KERNEL");
+      if (e && strcmp(e, "regs") == 0) return 2;
+      if (e && strcmp(e, "pipe") == 0) return 1;
+      return 0;
+    }();
+    if (variant != 2) {
+      // persistent: 2 CTAs per SM (shared-memory ring of 2 stages per warp), every warp walks chunks with the grid stride
+      const size_t smem = variant == 0 ? (size_t)8 * 2 * SPMV_TMA_STAGE + 8 * 16 : (size_t)8 * 2 * SPMV_PIPE_STAGE;
+      const int nb = std::max(1, std::min((S->n_sp_chunks + 7) / 8, std::min(RED_MAX_BLOCKS, c->sm_count * 2)));
+      dim3 grid((unsigned)nb, (unsigned)count, 1u);
+#define EFB_SPMV_PIPE(K, DOT)                                                                                 \
+  EFB_CUDA(c, cudaFuncSetAttribute(K<DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
+  K<DOT><<<grid, 256, smem, c->stream>>>(D, S->d_sp_chunk, S->n_sp_chunks, first, x, y, w, slot0, slot1, use_active)
+      if (variant == 0) {
+        switch (dot) {
+          case 0: EFB_SPMV_PIPE(k_spmv_tma, 0); break;
+          case 1: EFB_SPMV_PIPE(k_spmv_tma, 1); break;
+          case 2: EFB_SPMV_PIPE(k_spmv_tma, 2); break;
+          default: EFB_SPMV_PIPE(k_spmv_tma, 3); break;
+        }
+      } else {
+        switch (dot) {
+          case 0: EFB_SPMV_PIPE(k_spmv_pipe, 0); break;
+          case 1: EFB_SPMV_PIPE(k_spmv_pipe, 1); break;
+          case 2: EFB_SPMV_PIPE(k_spmv_pipe, 2); break;
+          default: EFB_SPMV_PIPE(k_spmv_pipe, 3); break;
+        }
+      }
+#undef EFB_SPMV_PIPE
+      EFB_CHECK_LAUNCH(c);
+      return EFB_OK;
+    }
     const int nb = std::max(1, std::min((S->n_sp_chunks + 7) / 8, std::min(RED_MAX_BLOCKS, c->sm_count * 8)));
     dim3 grid((unsigned)nb, (unsigned)count, 1u);
     switch (dot) {
