@@ -261,8 +261,12 @@ def cube_extras(ctx, pe, n: int):
         "mesh": {"n": n, "tets": n_tet, "nodes": n_node, "edges": m, "nnz": nnz, "host_setup_s": round(setup_s, 2)},
         "fp64_fma_probe_tflops": fp64_tflops,
         "assembly": {"ms": ms_asm, "mtets_per_s": n_tet / ms_asm / 1e3, "algorithmic_gb": b_asm / 1e9, "gbs": b_asm / ms_asm / 1e6,
-                     "fp64_gflop_model": 6 * n_tet * 300 / 1e9, "note": "row-gather recomputes each element row per incident edge (~300 FP64 flop x 6 per tet)"},
-        "spmv": {"ms": ms_spmv, "algorithmic_gb": b_spmv / 1e9, "gbs": b_spmv / ms_spmv / 1e6},
+                     "fp64_gflop_model": 6 * n_tet * 300 / 1e9,
+                     "kernel": "k_assemble_volume_s (rank-major schedule, real chunk image)",
+                     "note": "row-gather: one element row per (edge, tet) incidence (~300 FP64 flop x 6 per tet) added into a shared-memory "
+                             "chunk image; bound by gather latency and the L1 data pipe, not by HBM (profiles/prof_asm_r01s.md)"},
+        "spmv": {"ms": ms_spmv, "algorithmic_gb": b_spmv / 1e9, "gbs": b_spmv / ms_spmv / 1e6,
+                 "kernel": "k_spmv_tma (CSR-stream, matrix stream by cp.async.bulk + mbarrier, bank-skewed products)"},
         "bicgstab_jacobi_iteration": {"ms": ms_bicg, "algorithmic_gb": b_bicg / 1e9, "gbs": b_bicg / ms_bicg / 1e6},
         "cocg_jacobi_iteration": {"ms": ms_cocg, "algorithmic_gb": b_cocg / 1e9, "gbs": b_cocg / ms_cocg / 1e6},
     }

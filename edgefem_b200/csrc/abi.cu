@@ -868,6 +868,7 @@ void efb_system_destroy(efb_system *sys_) {
   solver_free(S);
   dfree(S->d_rowptr); dfree(S->d_colidx); dfree(S->d_diag_pos); dfree(S->d_vals);
   dfree(S->d_b); dfree(S->d_x); dfree(S->d_dir_all); dfree(S->d_e2t_pos); dfree(S->d_chunk_row); dfree(S->d_sp_chunk);
+  dfree(S->d_sch_item); dfree(S->d_sch_ss); dfree(S->d_sch_row); dfree(S->d_sch_pos); dfree(S->d_sch_sec); dfree(S->d_sch_flag);
   dfree(S->d_sell_ptr); dfree(S->d_sell_col); dfree(S->d_sell_perm); dfree(S->d_sell_vals); dfree(S->d_sell_src);
   dfree(S->d_c_orig); dfree(S->d_c_edge_nodes); dfree(S->d_c_n2e_ptr); dfree(S->d_c_n2e_item);
   dfree(S->d_edge_nodes); dfree(S->d_n2e_ptr); dfree(S->d_n2e_item); dfree(S->d_node_dir);
@@ -924,6 +925,7 @@ int efb_system_set_dirichlet(efb_system *sys_, const uint8_t *flags) {
   S->has_dir = true;
   S->h_dir.assign(flags + S->row0, flags + S->row0 + S->m);
   S->small_dirty = true;
+  S->sched_dirty = true;
   if (S->d_e2t_pos && S->mesh) {
     k_pos_dirichlet<<<(S->m + 127) / 128, 128, 0, c->stream>>>(S->mesh->d_e2t_ptr + S->row0, S->d_rowptr, S->d_colidx, S->d_dir_all, S->m,
                                                                S->d_e2t_pos, (long long)S->mesh->h_e2t_ptr[S->row0] * 6);

@@ -69,10 +69,13 @@ __device__ __forceinline__ void cp_async16_zfill_if(bool p, unsigned smem_dst, c
 // Row-gather volume assembly, batched variant (k_assemble_volume_b, the default): a CTA owns a chunk of consecutive
 // rows with <= ASM_CHUNK_NNZ entries; the lanes of a warp take 32 consecutive (edge, tet) incidences per step.  The older
 // thread-per-row kernel (k_assemble_volume, EDGEFEM_B200_ASM_KERNEL=row) uses the larger ASMR_* chunks.
-constexpr int ASM_CHUNK_NNZ = 3840;   // matrix entries per assembly CTA (60 KB of c128 accumulators)
-constexpr int ASM_CHUNK_ROWS = 512;   // rows per assembly CTA (rowptr / incidence-pointer slices in smem)
-constexpr int ASMB_THREADS = 256;
-constexpr int ASMB_CTAS_PER_SM = 3;
+constexpr int ASM_CHUNK_NNZ = 1920;   // matrix entries per assembly CTA (60 KB of c128 accumulators)
+constexpr int ASM_CHUNK_ROWS = 128;   // rows per assembly CTA = threads per CTA: one row per thread in every rank
+constexpr int ASM_MAX_RANK = 62;      // scheduled kernel: most incident tets of an edge (else the batched kernel runs)
+constexpr int ASM_SEC_STRIDE = ASM_MAX_RANK + 2;
+constexpr int ASMB_THREADS = 128;
+static_assert(ASM_CHUNK_ROWS <= ASMB_THREADS, "the scheduled kernel gives every row of a rank its own thread");
+constexpr int ASMB_CTAS_PER_SM = 6;
 constexpr int ASMR_CHUNK_NNZ = 5376;  // thread-per-row kernel: entries per CTA
 constexpr int ASMR_CHUNK_ROWS = 768;  // thread-per-row kernel: rows per CTA (also the bank-skew padding)
 constexpr int ASM_ACC_ENTRIES = ASMR_CHUNK_NNZ + ASMR_CHUNK_ROWS;  // 96 KB of c128 accumulators
@@ -157,6 +160,15 @@ struct System {
   int32_t *d_chunk_row = nullptr;  // [n_chunks+1]
   int n_chunks = 0;
   bool asm_row_kernel = false;     // chunks were cut for the thread-per-row kernel (ASMR_* limits)
+  // rank-major assembly schedule (k_assemble_volume_s): per chunk, the r-th incidence of every non-Dirichlet row with
+  // more than r incident tets, rows ascending, ranks ascending.  Built lazily; rebuilt when the Dirichlet flags change.
+  bool sched_dirty = true, sched_ok = false;
+  int32_t *d_sch_item = nullptr;   // [n_inc] tet << 3 | local edge, schedule order (chunk regions = incidence regions)
+  uint16_t *d_sch_ss = nullptr;    // [n_inc] sign | slot << 8
+  uint16_t *d_sch_row = nullptr;   // [n_inc] row inside the chunk
+  uint16_t *d_sch_pos = nullptr;   // [n_inc*6] row-local positions (copy of d_e2t_pos in schedule order)
+  int32_t *d_sch_sec = nullptr;    // [n_chunks][ASM_SEC_STRIDE]: number of ranks, then the section offsets
+  int32_t *d_sch_flag = nullptr;   // [1] a chunk has a row with more than ASM_MAX_RANK incident tets
   // CSR-stream SpMV: row-aligned chunks of <= SPMV_STREAM_W entries (one warp each); null if a row is longer
   int32_t *d_sp_chunk = nullptr;   // [n_sp_chunks+1]
   int n_sp_chunks = 0;
@@ -311,6 +323,7 @@ int device_pattern(System *S, bool *done);
 void dist_free(System *s);
 int assemble_launch(System *s, int first, int count, int mode);
 int launch_tet_geometry(Mesh *m);
+int assemble_build_schedule(System *s);  // assemble.cu
 bool asm_use_row_kernel();   // EDGEFEM_B200_ASM_KERNEL=row selects the older thread-per-row assembly kernel
 void asm_chunk_limits(int *max_nnz, int *max_rows);
 

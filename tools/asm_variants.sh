@@ -17,5 +17,5 @@ except Exception as e:
 PY
 }
 run default A=1
-run pipe_cplx EDGEFEM_B200_SPMV_KERNEL=pipe EDGEFEM_B200_ASM_NO_REAL=1
-run regs_row EDGEFEM_B200_ASM_KERNEL=row EDGEFEM_B200_SPMV_KERNEL=regs
+run sched_cplx EDGEFEM_B200_ASM_NO_REAL=1
+run sched_3cta EDGEFEM_B200_ASM_CTAS=3
