@@ -408,8 +408,9 @@ __device__ __forceinline__ void record_entries(const double (&g)[12], int item, 
     Mj += ra[c] * ((b == d) ? Ieq : Ine);
     const double sgn = (((sg >> j) & 1u) ^ si) ? -1.0 : 1.0;
     const double kk = Kj * sgn, mm = Mj * sgn;
-    if constexpr (REAL) v[j] = kk * kf.x + mm * mf.x;
-    else v[j] = cmake(kk * kf.x + mm * mf.x, kk * kf.y + mm * mf.y);
+    // explicit fma: the real and the complex image, and every kernel variant, round the same way
+    if constexpr (REAL) v[j] = fma(kk, kf.x, mm * mf.x);
+    else v[j] = cmake(fma(kk, kf.x, mm * mf.x), fma(kk, kf.y, mm * mf.y));
   }
 }
 

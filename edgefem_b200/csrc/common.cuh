@@ -46,30 +46,14 @@ __host__ __device__ __forceinline__ c128 cfma(c128 a, c128 b, c128 acc) {  // ac
   return acc;
 }
 
-// ------------------------------------------------------------------ cp.async (LDGSTS) helpers
-// predicated in PTX so that the lanes of a warp stay converged (one LDGSTS per call, no branches)
-__device__ __forceinline__ void cp_async16_if(bool p, unsigned smem_dst, const void *gsrc) {
-  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q cp.async.cg.shared.global [%0], [%1], 16;\n\t}" ::"r"(smem_dst), "l"(gsrc), "r"((unsigned)p) : "memory");
-}
-__device__ __forceinline__ void cp_async4_if(bool p, unsigned smem_dst, const void *gsrc) {
-  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q cp.async.ca.shared.global [%0], [%1], 4;\n\t}" ::"r"(smem_dst), "l"(gsrc), "r"((unsigned)p) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-// 16-byte copy that reads only the first src_bytes (<= 16) bytes of the source and zero-fills the rest
-__device__ __forceinline__ void cp_async16_zfill_if(bool p, unsigned smem_dst, const void *gsrc, unsigned src_bytes) {
-  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q cp.async.cg.shared.global [%0], [%1], 16, %3;\n\t}" ::"r"(smem_dst), "l"(gsrc), "r"((unsigned)p), "r"(src_bytes) : "memory");
-}
-
 // ------------------------------------------------------------------ limits
-// Row-gather volume assembly, batched variant (k_assemble_volume_b, the default): a CTA owns a chunk of consecutive
-// rows with <= ASM_CHUNK_NNZ entries; the lanes of a warp take 32 consecutive (edge, tet) incidences per step.  The older
-// thread-per-row kernel (k_assemble_volume, EDGEFEM_B200_ASM_KERNEL=row) uses the larger ASMR_* chunks.
-constexpr int ASM_CHUNK_NNZ = 1920;   // matrix entries per assembly CTA (60 KB of c128 accumulators)
+// Row-gather volume assembly.  A CTA owns a chunk of consecutive rows with <= ASM_CHUNK_NNZ entries and accumulates it in
+// a shared-memory image.  Default: k_assemble_volume_s (rank-major schedule, one row per thread in every rank);
+// fallback for meshes with an edge in more than ASM_MAX_RANK tets and EDGEFEM_B200_ASM_KERNEL=batch:
+// k_assemble_volume_b (lanes = 32 consecutive incidences, adds in rounds).  The first-generation thread-per-row kernel
+// (k_assemble_volume, EDGEFEM_B200_ASM_KERNEL=row) uses the larger ASMR_* chunks.  Measured on the 1.57 M-tet cube:
+// 128-thread CTAs x 6 per SM 0.335 ms, 256 x 3 0.364 ms, 64 x 12 0.346 ms.
+constexpr int ASM_CHUNK_NNZ = 1920;   // matrix entries per assembly CTA (30 KB of c128 / 15 KB of double accumulators)
 constexpr int ASM_CHUNK_ROWS = 128;   // rows per assembly CTA = threads per CTA: one row per thread in every rank
 constexpr int ASM_MAX_RANK = 62;      // scheduled kernel: most incident tets of an edge (else the batched kernel runs)
 constexpr int ASM_SEC_STRIDE = ASM_MAX_RANK + 2;

@@ -301,14 +301,9 @@ k_spmv_stream(SolveDev D, const int32_t *__restrict__ sp_chunk, int n_chunks, in
   }
 }
 
-// CSR-stream SpMV, software-pipelined through shared memory (the default for large matrices).  Same chunks, same
-// products and the same in-order row sums as k_spmv_stream (bit-identical y), but the matrix stream never sits in
-// registers: while a warp gathers x and reduces chunk i, the values / columns / row pointers of chunk i+1 are already
-// on their way into the other stage of its shared-memory ring (cp.async, 16-byte pieces; the column slice is fetched
-// as the 16-byte-aligned superset).  2 CTAs x 8 warps per SM, every warp always has ~5 KB of the stream in flight.
+// chunk descriptors and stage geometry of the TMA-streamed SpMV below
 constexpr int SPMV_PIPE_COLS = SPMV_STREAM_W + 4;  // aligned superset of the column slice
 constexpr int SPMV_VAL_BYTES = SPMV_SLOTS * 16;  // value area of a stage, sized for the skewed products written in place
-constexpr int SPMV_PIPE_STAGE = SPMV_VAL_BYTES + SPMV_PIPE_COLS * 4 + 36 * 4;  // 5536 B
 struct ChunkDesc {
   int r0, nrow, k0, k1;
 };
@@ -325,119 +320,11 @@ __device__ __forceinline__ ChunkDesc load_chunk_desc(const int32_t *__restrict__
   return d;
 }
 
-template <int DOT>
-__global__ void __launch_bounds__(256, 2)
-k_spmv_pipe(SolveDev D, const int32_t *__restrict__ sp_chunk, int n_chunks, int first_matrix, const c128 *__restrict__ x,
-            c128 *__restrict__ y, const c128 *__restrict__ wv, int slot0, int slot1, int use_active) {
-  extern __shared__ __align__(16) unsigned char pipe_smem[];
-  const int f = first_matrix + blockIdx.y;
-  const int s0 = f * D.n_rhs;
-  if (use_active && !D.state[s0 * 4 + ST_ACTIVE]) return;
-  const c128 *__restrict__ av = D.vals + (size_t)f * D.nnz;
-  const c128 *__restrict__ xs = x + (size_t)s0 * D.m;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  unsigned char *wbase = pipe_smem + (size_t)wid * 2 * SPMV_PIPE_STAGE;
-  const unsigned wbase_s = (unsigned)__cvta_generic_to_shared(wbase);
-  double dots[4] = {0.0, 0.0, 0.0, 0.0};
-  const int stride = gridDim.x * 8;
-  int ch = blockIdx.x * 8 + wid;
-
-  auto issue = [&](int stage, const ChunkDesc &d) {
-    const unsigned sb = wbase_s + (unsigned)stage * SPMV_PIPE_STAGE;
-    const int n = d.k1 - d.k0;
-#pragma unroll
-    for (int j = 0; j < SPMV_STREAM_W / 32; ++j) {
-      const int i = lane + 32 * j;
-      cp_async16_if(i < n, sb + 16u * (unsigned)i, av + d.k0 + i);
-    }
-    const int ka = d.k0 & ~3;  // 16-byte aligned start of the column slice
-    const int np = (d.k1 - ka + 3) >> 2;  // 16-byte pieces (<= 65)
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      const int pc = lane + 32 * q;
-      const long long rem = D.nnz - ((long long)ka + 4 * pc);  // ints left in the array (the last piece may be short)
-      cp_async16_zfill_if(pc < np, sb + SPMV_VAL_BYTES + 16u * (unsigned)pc, D.colidx + ka + 4 * pc,
-                          rem >= 4 ? 16u : (unsigned)(rem > 0 ? 4 * rem : 0));
-    }
-    cp_async4_if(lane <= d.nrow && d.nrow > 0, sb + SPMV_VAL_BYTES + SPMV_PIPE_COLS * 4 + 4u * (unsigned)lane, D.rowptr + d.r0 + lane);
-  };
-
-  ChunkDesc cur = load_chunk_desc(sp_chunk, D.rowptr, ch, n_chunks);
-  ChunkDesc nxt = load_chunk_desc(sp_chunk, D.rowptr, ch + stride, n_chunks);
-  issue(0, cur);
-  cp_async_commit();
-  int st = 0;
-  for (; ch < n_chunks; ch += stride) {
-    issue(st ^ 1, nxt);  // an exhausted descriptor (nrow = 0, k0 = k1 = 0) issues nothing
-    cp_async_commit();
-    const ChunkDesc nn = load_chunk_desc(sp_chunk, D.rowptr, ch + 2 * stride, n_chunks);
-    cp_async_wait<1>();
-    __syncwarp();
-    unsigned char *sb = wbase + (size_t)st * SPMV_PIPE_STAGE;
-    c128 *sv = (c128 *)sb;
-    const int32_t *sc = (const int32_t *)(sb + SPMV_VAL_BYTES) + (cur.k0 & 3);
-    const int32_t *rp = (const int32_t *)(sb + SPMV_VAL_BYTES + SPMV_PIPE_COLS * 4);
-    const int n = cur.k1 - cur.k0;
-    int c[SPMV_STREAM_W / 32];
-    c128 xv[SPMV_STREAM_W / 32];
-#pragma unroll
-    for (int j = 0; j < SPMV_STREAM_W / 32; ++j) {
-      const int i = lane + 32 * j;
-      c[j] = (i < n) ? sc[i] : -1;
-    }
-#pragma unroll
-    for (int j = 0; j < SPMV_STREAM_W / 32; ++j) xv[j] = (c[j] >= 0) ? __ldg(&xs[c[j]]) : cmake(0.0, 0.0);
-    // products in place, at the skewed slots: every lane reads its values first (slot(i) >= i would run into values
-    // another lane has not read yet)
-#pragma unroll
-    for (int j = 0; j < SPMV_STREAM_W / 32; ++j) {
-      const int i = lane + 32 * j;
-      if (c[j] >= 0) xv[j] = cmul(sv[i], xv[j]);
-    }
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < SPMV_STREAM_W / 32; ++j) {
-      if (c[j] >= 0) sv[spmv_slot(lane + 32 * j)] = xv[j];
-    }
-    __syncwarp();
-    if (lane < cur.nrow) {
-      const int row = cur.r0 + lane;
-      const int rs = rp[lane] - cur.k0, re = rp[lane + 1] - cur.k0;
-      c128 acc = cmake(0.0, 0.0);
-      for (int k = rs; k < re; ++k) acc = cadd(acc, sv[spmv_slot(k)]);
-      const size_t idx = (size_t)s0 * D.m + row;
-      y[idx] = acc;
-      if (DOT == 1) {
-        const c128 q = cmul(wv[idx], acc);
-        dots[0] += q.x; dots[1] += q.y;
-      } else if (DOT == 2) {
-        const c128 q = cmulconj(wv[idx], acc);
-        dots[0] += q.x; dots[1] += q.y;
-      } else if (DOT == 3) {
-        const c128 q = cmulconj(acc, wv[idx]);
-        dots[0] += q.x; dots[1] += q.y;
-        dots[2] += cabs2(acc);
-      }
-    }
-    __syncwarp();
-    cur = nxt;
-    nxt = nn;
-    st ^= 1;
-  }
-  cp_async_wait<0>();
-  if (DOT != 0) {
-    double tot[4];
-    if (reduce_and_ticket<4>(dots, partial_of(D, s0), D.counter + s0, tot)) {
-      c128 *sc = scal_of(D, s0);
-      sc[slot0] = cmake(tot[0], tot[1]);
-      if (DOT == 3) sc[slot1] = cmake(tot[2], 0.0);
-    }
-  }
-}
-
 // CSR-stream SpMV with the matrix stream moved by the TMA engine (the default for large matrices).  The SpMV is bound
-// by the L1/LSU wavefront rate, not by HBM: the x gather costs one wavefront per distinct 128-byte line of every load,
-// and in k_spmv_stream / k_spmv_pipe the value and column streams go through the same pipe.  Here lane 0 of a warp
+// by the L1 data pipe (LSU wavefronts: 82 % of peak in ncu), not by HBM: the x gather costs one wavefront per distinct
+// 128-byte line of every load, the products and row sums go through shared memory, and in k_spmv_stream the value and
+// column streams use the same pipe (a cp.async variant of the stream was measured no faster: LDGSTS still goes through
+// L1).  Here lane 0 of a warp
 // issues two bulk copies per chunk (cp.async.bulk global -> shared: <= 4 KB of values, <= 1 KB of columns as the
 // 16-byte-aligned superset) that complete on an mbarrier; the copies bypass L1 entirely, run one chunk ahead of the
 // warp (2-stage ring) and leave the LSU to the x gather, the in-place products and the in-order row sums.
@@ -1398,36 +1285,25 @@ static int launch_spmv(System *S, const SolveDev &D, int first, int count, const
                        int slot1, int use_active) {
   Ctx *c = S->ctx;
   if (S->d_sp_chunk && S->n_rhs == 1 && !getenv("EDGEFEM_B200_NO_STREAM_SPMV")) {
-    static const int variant = [] {  // 0: TMA bulk stream (default) | 1: cp.async stream | 2: register stream
+    static const bool use_regs = [] {  // EDGEFEM_B200_SPMV_KERNEL=regs: the register-streamed kernel
       const char *e = getenv("EDGEFEM_B200_SPMV_KERNEL");
-      if (e && strcmp(e, "regs") == 0) return 2;
-      if (e && strcmp(e, "pipe") == 0) return 1;
-      return 0;
+      return e && strcmp(e, "regs") == 0;
     }();
-    if (variant != 2) {
+    if (!use_regs) {
       // persistent: 2 CTAs per SM (shared-memory ring of 2 stages per warp), every warp walks chunks with the grid stride
-      const size_t smem = variant == 0 ? (size_t)8 * 2 * SPMV_TMA_STAGE + 8 * 16 : (size_t)8 * 2 * SPMV_PIPE_STAGE;
+      const size_t smem = (size_t)8 * 2 * SPMV_TMA_STAGE + 8 * 16;
       const int nb = std::max(1, std::min((S->n_sp_chunks + 7) / 8, std::min(RED_MAX_BLOCKS, c->sm_count * 2)));
       dim3 grid((unsigned)nb, (unsigned)count, 1u);
-#define EFB_SPMV_PIPE(K, DOT)                                                                                 \
-  EFB_CUDA(c, cudaFuncSetAttribute(K<DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
-  K<DOT><<<grid, 256, smem, c->stream>>>(D, S->d_sp_chunk, S->n_sp_chunks, first, x, y, w, slot0, slot1, use_active)
-      if (variant == 0) {
-        switch (dot) {
-          case 0: EFB_SPMV_PIPE(k_spmv_tma, 0); break;
-          case 1: EFB_SPMV_PIPE(k_spmv_tma, 1); break;
-          case 2: EFB_SPMV_PIPE(k_spmv_tma, 2); break;
-          default: EFB_SPMV_PIPE(k_spmv_tma, 3); break;
-        }
-      } else {
-        switch (dot) {
-          case 0: EFB_SPMV_PIPE(k_spmv_pipe, 0); break;
-          case 1: EFB_SPMV_PIPE(k_spmv_pipe, 1); break;
-          case 2: EFB_SPMV_PIPE(k_spmv_pipe, 2); break;
-          default: EFB_SPMV_PIPE(k_spmv_pipe, 3); break;
-        }
+#define EFB_SPMV_TMA(DOT)                                                                                         \
+  EFB_CUDA(c, cudaFuncSetAttribute(k_spmv_tma<DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+  k_spmv_tma<DOT><<<grid, 256, smem, c->stream>>>(D, S->d_sp_chunk, S->n_sp_chunks, first, x, y, w, slot0, slot1, use_active)
+      switch (dot) {
+        case 0: EFB_SPMV_TMA(0); break;
+        case 1: EFB_SPMV_TMA(1); break;
+        case 2: EFB_SPMV_TMA(2); break;
+        default: EFB_SPMV_TMA(3); break;
       }
-#undef EFB_SPMV_PIPE
+#undef EFB_SPMV_TMA
       EFB_CHECK_LAUNCH(c);
       return EFB_OK;
     }
