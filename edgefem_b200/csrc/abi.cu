@@ -6,6 +6,7 @@
 #include <stdarg.h>
 
 #include <algorithm>
+#include <functional>
 #include <atomic>
 #include <chrono>
 #include <mutex>
@@ -498,6 +499,112 @@ static int system_alloc_common(System *S) {
 
 }  // extern "C"
 
+// Slots of the SELL-32 structure of the persistent small-system solver.  The order of the entries inside a SELL row is
+// free.  The solver gathers p from shared memory with one 16-byte load per entry, and the 8 lanes of a quarter warp are
+// served together only if their columns fall in 8 different bank groups (column mod 8): in CSR order they collide like
+// random numbers (2.64 wavefronts per quarter on WR-90).  One thread per (slice, quarter): at every step the 8 rows pick,
+// fewest choices first, an unused bank group among the entries they have left (their fullest one), else their fullest
+// group (1.65 wavefronts; a maximum matching per step gives 1.56 at ten times the work).  Rows longer than
+// SELL_FILL_MAX entries keep the CSR order.
+constexpr int SELL_FILL_MAX = 160;
+__global__ void __launch_bounds__(64)
+k_sell_fill(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx, const int32_t *__restrict__ comp,
+            const int32_t *__restrict__ orig, const int32_t *__restrict__ perm, const int32_t *__restrict__ sptr, int n_slices,
+            int32_t *__restrict__ scol, int32_t *__restrict__ ssrc) {
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= n_slices * 4) return;
+  const int sl = id >> 2, q = id & 3;
+  const int base = sptr[sl], width = (sptr[sl + 1] - base) >> 5;
+  int16_t ent[8][SELL_FILL_MAX];  // CSR offsets (relative to the row start) of the free entries, bucketed by bank group
+  int beg[8][8], cnt[8][8], left[8], rstart[8];
+  bool fits = true;
+  for (int t = 0; t < 8; ++t) {
+    const int i = perm[sl * 32 + 8 * q + t];
+    left[t] = 0;
+    rstart[t] = 0;
+    for (int g = 0; g < 8; ++g) cnt[t][g] = 0;
+    if (i < 0) continue;
+    const int r = orig[i];
+    rstart[t] = rowptr[r];
+    for (int k = rowptr[r]; k < rowptr[r + 1]; ++k) {
+      const int cc = comp[colidx[k]];
+      if (cc < 0) continue;
+      cnt[t][cc & 7]++;
+      left[t]++;
+    }
+    if (left[t] > SELL_FILL_MAX || rowptr[r + 1] - rowptr[r] > 32767) fits = false;
+  }
+  if (!fits) {  // CSR order
+    for (int t = 0; t < 8; ++t) {
+      const int i = perm[sl * 32 + 8 * q + t];
+      int j = 0;
+      if (i >= 0) {
+        const int r = orig[i];
+        for (int k = rowptr[r]; k < rowptr[r + 1]; ++k) {
+          const int cc = comp[colidx[k]];
+          if (cc < 0) continue;
+          scol[base + j * 32 + 8 * q + t] = cc;
+          ssrc[base + j * 32 + 8 * q + t] = k;
+          ++j;
+        }
+      }
+      for (; j < width; ++j) {
+        scol[base + j * 32 + 8 * q + t] = 0;
+        ssrc[base + j * 32 + 8 * q + t] = -1;
+      }
+    }
+    return;
+  }
+  for (int t = 0; t < 8; ++t) {
+    int run = 0;
+    for (int g = 0; g < 8; ++g) {
+      beg[t][g] = run;
+      run += cnt[t][g];
+      cnt[t][g] = 0;
+    }
+    if (left[t] == 0) continue;
+    const int r = orig[perm[sl * 32 + 8 * q + t]];
+    for (int k = rowptr[r]; k < rowptr[r + 1]; ++k) {
+      const int cc = comp[colidx[k]];
+      if (cc < 0) continue;
+      const int g = cc & 7;
+      ent[t][beg[t][g] + cnt[t][g]++] = (int16_t)(k - rstart[t]);
+    }
+  }
+  for (int j = 0; j < width; ++j) {
+    unsigned used = 0, served = 0;
+    int ng[8];
+    for (int t = 0; t < 8; ++t) {
+      ng[t] = 0;
+      for (int g = 0; g < 8; ++g) ng[t] += cnt[t][g] > 0;
+    }
+    for (int u = 0; u < 8; ++u) {
+      int t = -1;  // rows with fewer bank groups left choose first
+      for (int v = 0; v < 8; ++v)
+        if (!(served >> v & 1u) && left[v] > 0 && (t < 0 || ng[v] < ng[t])) t = v;
+      if (t < 0) break;
+      int best = -1, bc = 0, any = -1, ac = 0;
+      for (int g = 0; g < 8; ++g) {
+        const int cg = cnt[t][g];
+        if (cg > ac) { ac = cg; any = g; }
+        if (!(used >> g & 1u) && cg > bc) { bc = cg; best = g; }
+      }
+      const int g = best >= 0 ? best : any;
+      used |= 1u << g;
+      served |= 1u << t;
+      const int k = rstart[t] + ent[t][beg[t][g] + --cnt[t][g]];
+      left[t]--;
+      scol[base + j * 32 + 8 * q + t] = comp[colidx[k]];
+      ssrc[base + j * 32 + 8 * q + t] = k;
+    }
+    for (int t = 0; t < 8; ++t)
+      if (!(served >> t & 1u)) {
+        scol[base + j * 32 + 8 * q + t] = 0;
+        ssrc[base + j * 32 + 8 * q + t] = -1;
+      }
+  }
+}
+
 // Host build of the persistent small-system solver's structures (see System): compact numbering of the free
 // unknowns, SELL-32 pattern over them, compact gradient lists.  Cheap (m <= 16384), runs once per system state.
 int efb::build_small_structs(System *S) {
@@ -539,29 +646,30 @@ int efb::build_small_structs(System *S) {
     }
     sptr[sl + 1] = sptr[sl] + 32 * w;
   }
-  std::vector<int32_t> scol((size_t)std::max(sptr[ns], 1), 0), ssrc((size_t)std::max(sptr[ns], 1), -1);
-  for (int sl = 0; sl < ns; ++sl)
-    for (int l = 0; l < 32; ++l) {
-      const int i = perm[(size_t)sl * 32 + l];
-      if (i < 0) continue;
-      const int r = orig[i];
-      int j = 0;
-      for (int k = S->h_rowptr[r]; k < S->h_rowptr[r + 1]; ++k) {
-        const int cc = S->h_colidx[k];
-        if (is_dir(cc)) continue;
-        scol[(size_t)sptr[sl] + (size_t)j * 32 + l] = comp[cc];
-        ssrc[(size_t)sptr[sl] + (size_t)j * 32 + l] = k;
-        ++j;
-      }
-    }
   S->n_slices = ns;
   S->sell_total = sptr[ns];
   int rc;
   if ((rc = dev_upload(c, &S->d_c_orig, orig.data(), (size_t)std::max(mc, 1)))) return rc;
   if ((rc = dev_upload(c, &S->d_sell_ptr, sptr.data(), sptr.size()))) return rc;
-  if ((rc = dev_upload(c, &S->d_sell_col, scol.data(), scol.size()))) return rc;
-  if ((rc = dev_upload(c, &S->d_sell_src, ssrc.data(), ssrc.size()))) return rc;
   if ((rc = dev_upload(c, &S->d_sell_perm, perm.data(), perm.size()))) return rc;
+  {
+    // slots of the SELL structure on the device (bank-aware order of the entries inside a row: k_sell_fill)
+    const size_t total = (size_t)std::max(sptr[ns], 1);
+    if ((rc = dev_alloc(c, &S->d_sell_col, total))) return rc;
+    if ((rc = dev_alloc(c, &S->d_sell_src, total))) return rc;
+    int32_t *d_comp = nullptr;
+    if ((rc = dev_upload(c, &d_comp, comp.data(), (size_t)std::max(m, 1)))) return rc;
+    if (ns > 0) {
+      k_sell_fill<<<(ns * 4 + 63) / 64, 64, 0, c->stream>>>(S->d_rowptr, S->d_colidx, d_comp, S->d_c_orig, S->d_sell_perm, S->d_sell_ptr, ns,
+                                                          S->d_sell_col, S->d_sell_src);
+      EFB_CHECK_LAUNCH(c);
+    } else {
+      EFB_CUDA(c, cudaMemsetAsync(S->d_sell_col, 0, sizeof(int32_t), c->stream));
+      EFB_CUDA(c, cudaMemsetAsync(S->d_sell_src, 0xff, sizeof(int32_t), c->stream));
+    }
+    EFB_CUDA(c, cudaStreamSynchronize(c->stream));
+    dfree(d_comp);
+  }
   if (S->n_node > 0 && (int)S->h_edge_nodes.size() == 2 * m) {
     const int nn = S->n_node;
     std::vector<int32_t> ptr((size_t)nn + 1, 0), item((size_t)std::max(2 * mc, 1));

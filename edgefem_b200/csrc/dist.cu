@@ -177,7 +177,8 @@ __global__ void __launch_bounds__(256)
 k_dist_spmv(const int32_t *__restrict__ sp_chunk, int n_chunks, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
             const c128 *__restrict__ vals, const __grid_constant__ XView xv, const c128 *__restrict__ bvec, const c128 *__restrict__ dinv, c128 *__restrict__ zloc,
             c128 *__restrict__ r, c128 *__restrict__ p, c128 *__restrict__ q, const double *__restrict__ sc, int first, double *__restrict__ partial) {
-  __shared__ c128 prod[8][SPMV_STREAM_W];
+  // products parked at skewed slots i + i/16 (the row sums read at a stride of one row: see spmv_slot in solve.cu)
+  __shared__ c128 prod[8][SPMV_STREAM_W + SPMV_STREAM_W / 16];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   c128 beta = cmake(0.0, 0.0);
   if (EPI == 1 && !first) {
@@ -204,12 +205,12 @@ k_dist_spmv(const int32_t *__restrict__ sp_chunk, int n_chunks, const int32_t *_
     }
 #pragma unroll
     for (int j = 0; j < SPMV_STREAM_W / 32; ++j)
-      if (c[j] >= 0) prod[wid][lane + 32 * j] = cmul(a[j], xload(xv, c[j]));
+      if (c[j] >= 0) prod[wid][(lane + 32 * j) + ((lane + 32 * j) >> 4)] = cmul(a[j], xload(xv, c[j]));
     __syncwarp();
     if (lane < nrow) {
       const int row = r0 + lane;
       c128 acc = cmake(0.0, 0.0);
-      for (int k = rs - k0; k < re - k0; ++k) acc = cadd(acc, prod[wid][k]);
+      for (int k = rs - k0; k < re - k0; ++k) acc = cadd(acc, prod[wid][k + (k >> 4)]);
       if (EPI == 1) {
         const c128 zi = zloc[row];
         c128 qi = acc, pi = zi;
