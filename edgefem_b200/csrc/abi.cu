@@ -108,22 +108,6 @@ void pool_trim() {
 }
 
 // EDGEFEM_B200_TRACE=2: host-side stage times of system creation on stderr
-struct SubTrace {
-  bool on;
-  std::chrono::steady_clock::time_point t;
-  SubTrace() : on(false) {
-    const char *e = getenv("EDGEFEM_B200_TRACE");
-    on = e && atoi(e) >= 2;
-    t = std::chrono::steady_clock::now();
-  }
-  void mark(const char *what) {
-    if (!on) return;
-    auto n = std::chrono::steady_clock::now();
-    fprintf(stderr, "[edgefem-b200 trace]     . %s: %.3f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
-    t = n;
-  }
-};
-
 template <typename F>
 static void parallel_for(int64_t n, F f) {
   unsigned hw = std::thread::hardware_concurrency();

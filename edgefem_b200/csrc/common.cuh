@@ -3,8 +3,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -293,6 +295,23 @@ struct Timed {  // records CUDA events around a compute call on the ctx stream
   ~Timed() {
     cudaEventRecord(c->ev1, c->stream);
     c->ev_valid = true;
+  }
+};
+
+// EDGEFEM_B200_TRACE=2: host-side stage times inside the library calls (stderr)
+struct SubTrace {
+  bool on;
+  std::chrono::steady_clock::time_point t;
+  SubTrace() : on(false) {
+    const char *e = getenv("EDGEFEM_B200_TRACE");
+    on = e && atoi(e) >= 2;
+    t = std::chrono::steady_clock::now();
+  }
+  void mark(const char *what) {
+    if (!on) return;
+    auto n = std::chrono::steady_clock::now();
+    fprintf(stderr, "[edgefem-b200 trace]     . %s: %.3f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+    t = n;
   }
 };
 

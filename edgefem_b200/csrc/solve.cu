@@ -328,7 +328,8 @@ __device__ __forceinline__ ChunkDesc load_chunk_desc(const int32_t *__restrict__
 // issues two bulk copies per chunk (cp.async.bulk global -> shared: <= 4 KB of values, <= 1 KB of columns as the
 // 16-byte-aligned superset) that complete on an mbarrier; the copies bypass L1 entirely, run one chunk ahead of the
 // warp (2-stage ring) and leave the LSU to the x gather, the in-place products and the in-order row sums.
-// Same chunks, products and summation order as k_spmv_stream: bit-identical y.
+// Same chunks and products as k_spmv_stream; rows of chunks with <= 16 rows are summed as (first half) + (second half),
+// each half in order -- deterministic, but not the bit pattern of k_spmv_stream.
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
@@ -431,12 +432,26 @@ k_spmv_tma(SolveDev D, const int32_t *__restrict__ sp_chunk, int n_chunks, int f
       if (c[j] >= 0) sv[spmv_slot(lane + 32 * j)] = xv[j];
     }
     __syncwarp();
-    const int re_cur = __shfl_down_sync(0xffffffffu, rs_cur, 1);
-    if (lane < cur.nrow) {
-      const int row = cur.r0 + lane;
-      const int rs = rs_cur - cur.k0, re = re_cur - cur.k0;
-      c128 acc = cmake(0.0, 0.0);
+    // row sums: one lane per row, or -- when the chunk has at most 16 rows (the usual case: ~16 entries per row) -- two
+    // lanes per row, each summing one half in order, so that all 32 lanes read shared memory
+    const bool two = cur.nrow <= 16;
+    const int rl = two ? (lane >> 1) : lane;  // row of this lane inside the chunk
+    const int rs_row = __shfl_sync(0xffffffffu, rs_cur, rl), re_row = __shfl_sync(0xffffffffu, rs_cur, min(rl + 1, 31));
+    c128 acc = cmake(0.0, 0.0);
+    if (rl < cur.nrow) {
+      int rs = rs_row - cur.k0, re = re_row - cur.k0;
+      if (two) {
+        const int mid = rs + ((re - rs + 1) >> 1);
+        if (lane & 1) rs = mid; else re = mid;
+      }
       for (int k = rs; k < re; ++k) acc = cadd(acc, sv[spmv_slot(k)]);
+    }
+    if (two) {  // first half + second half
+      const double ox = __shfl_down_sync(0xffffffffu, acc.x, 1), oy = __shfl_down_sync(0xffffffffu, acc.y, 1);
+      acc = cadd(acc, cmake(ox, oy));
+    }
+    if (rl < cur.nrow && !(two && (lane & 1))) {
+      const int row = cur.r0 + rl;
       const size_t idx = (size_t)s0 * D.m + row;
       y[idx] = acc;
       if (DOT == 1) {
@@ -1465,9 +1480,11 @@ static int run_cocg_small(SolvePlan &P, const efb_solve_opts *o, bool zero_x, bo
   if (const char *v = getenv("EDGEFEM_B200_SMALL_VARIANT")) variant = atoi(v);
   if (S->m > 16384 || S->m != S->m_global) return EFB_OK;  // large or row-partitioned: generic multi-kernel path
   if (P.aux && (int)S->h_edge_nodes.size() != 2 * S->m) return EFB_OK;
+  SubTrace st;
   if (S->small_dirty) {
     int rcs = build_small_structs(S);
     if (rcs) return rcs;
+    st.mark("  small structs (compact numbering, SELL, lists)");
   }
   const int mc = S->m_c;
   if (mc == 0) return EFB_OK;
@@ -1578,9 +1595,11 @@ int efb_solve(efb_system *sys_, int32_t first_matrix, int32_t n_matrix, const ef
   if (opts->method < 0 || opts->method > EFB_METHOD_COCG || opts->precond < 0 || opts->precond > EFB_PRECOND_NONE)
     return fail(c, EFB_ERR_INVALID, "efb_solve: unknown method / preconditioner");
   EFB_CUDA(c, cudaSetDevice(c->device));
+  SubTrace st;
   SolvePlan P;
   int rc = make_plan(S, first_matrix, n_matrix, opts, P);
   if (rc) return rc;
+  st.mark("solve: plan + workspace");
   const int check_every = opts->check_every > 0 ? opts->check_every : 32;
   const int max_restarts = opts->max_restarts > 0 ? opts->max_restarts : 3;
   const int nsys = P.n_sys;
@@ -1607,9 +1626,12 @@ int efb_solve(efb_system *sys_, int32_t first_matrix, int32_t n_matrix, const ef
   };
   bool ran_small = false;
   S->small_timed = false;
+  st.mark("solve: preconditioner launches");
   if (P.method == EFB_METHOD_COCG && opts->max_iterations > 0) {
     if ((rc = run_cocg_small(P, opts, zero_x, &ran_small))) return rc;
+    st.mark("solve: persistent-solver set-up + launch (host)");
     if (ran_small && (rc = read_state())) return rc;
+    st.mark("solve: wait for the device");
   }
   for (int cycle = 0; !ran_small && cycle <= max_restarts; ++cycle) {
     if ((rc = init_cycle(P, zero_x))) return rc;
@@ -1652,6 +1674,7 @@ int efb_solve(efb_system *sys_, int32_t first_matrix, int32_t n_matrix, const ef
   std::vector<c128> hscal((size_t)nsys * NSCAL);
   EFB_CUDA(c, cudaMemcpyAsync(hscal.data(), S->d_scal + (size_t)P.first_sys * NSCAL, hscal.size() * sizeof(c128), cudaMemcpyDeviceToHost, c->stream));
   EFB_CUDA(c, cudaStreamSynchronize(c->stream));
+  st.mark("solve: final residuals + read-back");
   for (int i = 0; i < nsys; ++i) {
     const double rr = hscal[(size_t)i * NSCAL + S_RR].x, bb = hscal[(size_t)i * NSCAL + S_BB].x;
     efb_solve_result &R = results[i];
