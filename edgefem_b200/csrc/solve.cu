@@ -328,8 +328,7 @@ __device__ __forceinline__ ChunkDesc load_chunk_desc(const int32_t *__restrict__
 // issues two bulk copies per chunk (cp.async.bulk global -> shared: <= 4 KB of values, <= 1 KB of columns as the
 // 16-byte-aligned superset) that complete on an mbarrier; the copies bypass L1 entirely, run one chunk ahead of the
 // warp (2-stage ring) and leave the LSU to the x gather, the in-place products and the in-order row sums.
-// Same chunks and products as k_spmv_stream; rows of chunks with <= 16 rows are summed as (first half) + (second half),
-// each half in order -- deterministic, but not the bit pattern of k_spmv_stream.
+// Same chunks, products and summation order as k_spmv_stream: bit-identical y.
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
@@ -432,26 +431,12 @@ k_spmv_tma(SolveDev D, const int32_t *__restrict__ sp_chunk, int n_chunks, int f
       if (c[j] >= 0) sv[spmv_slot(lane + 32 * j)] = xv[j];
     }
     __syncwarp();
-    // row sums: one lane per row, or -- when the chunk has at most 16 rows (the usual case: ~16 entries per row) -- two
-    // lanes per row, each summing one half in order, so that all 32 lanes read shared memory
-    const bool two = cur.nrow <= 16;
-    const int rl = two ? (lane >> 1) : lane;  // row of this lane inside the chunk
-    const int rs_row = __shfl_sync(0xffffffffu, rs_cur, rl), re_row = __shfl_sync(0xffffffffu, rs_cur, min(rl + 1, 31));
-    c128 acc = cmake(0.0, 0.0);
-    if (rl < cur.nrow) {
-      int rs = rs_row - cur.k0, re = re_row - cur.k0;
-      if (two) {
-        const int mid = rs + ((re - rs + 1) >> 1);
-        if (lane & 1) rs = mid; else re = mid;
-      }
+    const int re_cur = __shfl_down_sync(0xffffffffu, rs_cur, 1);
+    if (lane < cur.nrow) {
+      const int row = cur.r0 + lane;
+      const int rs = rs_cur - cur.k0, re = re_cur - cur.k0;
+      c128 acc = cmake(0.0, 0.0);
       for (int k = rs; k < re; ++k) acc = cadd(acc, sv[spmv_slot(k)]);
-    }
-    if (two) {  // first half + second half
-      const double ox = __shfl_down_sync(0xffffffffu, acc.x, 1), oy = __shfl_down_sync(0xffffffffu, acc.y, 1);
-      acc = cadd(acc, cmake(ox, oy));
-    }
-    if (rl < cur.nrow && !(two && (lane & 1))) {
-      const int row = cur.r0 + rl;
       const size_t idx = (size_t)s0 * D.m + row;
       y[idx] = acc;
       if (DOT == 1) {
