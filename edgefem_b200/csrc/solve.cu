@@ -8,6 +8,8 @@
 #include <algorithm>
 #include <cstdlib>
 
+#include <queue>
+
 #include "common.cuh"
 
 namespace efb {
@@ -777,400 +779,427 @@ __device__ __forceinline__ void block_allreduce(double (&v)[N], double *red /* s
   __syncthreads();
 }
 
+// One job of the persistent solver: matrix f, the NR right-hand sides starting at system s0, solved to convergence by
+// the whole CTA (see k_cocg_small below).
+template <int NR, int SPD, bool DB>
+__device__ __forceinline__ void cocg_small_job(const SolveDev &D, const int32_t *__restrict__ sell_ptr, const int32_t *__restrict__ sell_col,
+                                               const int32_t *__restrict__ sell_perm, const c128 *__restrict__ sell_vals, long long sell_total,
+                                               int n_slices, const c128 *__restrict__ bvec, c128 *xvec, c128 *rvec, c128 *qvec, int aux, int zero_x,
+                                               int max_restarts, int mc, const int32_t *__restrict__ c_orig,
+                                               const int2 *__restrict__ c_edge_nodes, const int32_t *__restrict__ c_n2e_ptr,
+                                               const int32_t *__restrict__ c_n2e_item, unsigned char *sm_raw, int f, int s0) {
+  const int m = D.m, nn = aux ? D.n_node : 0;
+  c128 *p_s = (c128 *)sm_raw;                 // [NR][mc]
+  c128 *w_s = p_s + (size_t)NR * mc;          // [NR][nn]
+  double *red = (double *)(w_s + (size_t)NR * nn);  // [33*8]
+  const int tid = threadIdx.x, nth = blockDim.x;
+  const int lane = tid & 31, wid = tid >> 5, nwarp = nth >> 5;
+  const c128 *__restrict__ av = D.vals + (size_t)f * D.nnz;
+  const c128 *__restrict__ dinv = D.dinv + (size_t)f * m;
+  const c128 *__restrict__ linv = D.linv + (size_t)f * (aux ? D.n_node : 0);
+  // per-rhs vectors are addressed as base + r*m (one base pointer per vector instead of NR pointers)
+  struct VRef {
+    c128 *base;
+    int m;
+    __device__ __forceinline__ c128 *operator[](int r) const { return base + (size_t)r * m; }
+  };
+  const size_t off0 = (size_t)s0 * m;
+  const VRef xg{xvec + off0, m}, rg{rvec + off0, m}, qg{qvec + off0, m}, bg{const_cast<c128 *>(bvec) + off0, m};
+  // block-uniform scalars live in shared memory (written by thread 0 between barriers): bb, rr and a
+  // double-buffered rho per right-hand side
+  double *sc_bb = red + 33 * 8, *sc_rr = sc_bb + NR, *sc_rho = sc_rr + NR;  // sc_rho[parity][r][2]
+  int par = 0;
+  int iters[NR];
+  bool act[NR], conv[NR];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) { iters[r] = 0; act[r] = false; conv[r] = false; }
+  if (tid < 8 * NR) sc_bb[tid] = 0.0;
+  // Dirichlet rows are decoupled identity rows: x_e = b_e / A_ee, once
+  if (mc < m)
+    for (int e = tid; e < m; e += nth)
+      if (D.dir[e]) {
+        const c128 de = __ldg(&dinv[e]);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) xg[r][e] = cmul(de, bg[r][e]);
+      }
+  __syncthreads();
+
+  // q = A * (vector in p_s), optional dot p.q.  SELL-32: a lane owns a row, 32 rows form a slice stored
+  // column-major.  A warp owns a CONTIGUOUS range of slices (balanced by entry count), so its values and
+  // columns are one flat stream: every step is a coalesced 512-byte value load + 128-byte column load,
+  // SPD steps are in flight per lane and the next batch is requested before the current one is consumed
+  // (double buffering in registers); slice ends only flush the row accumulators.  No shuffles.
+  const c128 *__restrict__ sv = sell_vals + (size_t)f * (size_t)sell_total;
+  int s_lo, s_hi;
+  {
+    const long long t0 = sell_total * wid / nwarp, t1 = sell_total * (wid + 1) / nwarp;
+    auto lower = [&](long long t) {
+      int lo = 0, hi = n_slices;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((long long)__ldg(&sell_ptr[mid]) < t) lo = mid + 1; else hi = mid;
+      }
+      return lo;
+    };
+    s_lo = lower(t0);
+    s_hi = (wid == nwarp - 1) ? n_slices : lower(t1);
+  }
+  // per-slice variant (SPD == 0): slices dealt round-robin to the warps, batches of 4 independent loads
+  auto spmv_slices = [&](bool want_dot, double (&dots)[2 * NR]) {
+#pragma unroll
+    for (int k = 0; k < 2 * NR; ++k) dots[k] = 0.0;
+    for (int sl = wid; sl < n_slices; sl += nwarp) {
+      const int base = __ldg(&sell_ptr[sl]);
+      const int width = (__ldg(&sell_ptr[sl + 1]) - base) >> 5;
+      const int row = __ldg(&sell_perm[sl * 32 + lane]);
+      const c128 *vp = sv + base + lane;
+      const int32_t *cp = sell_col + base + lane;
+      c128 acc[NR];
+#pragma unroll
+      for (int r = 0; r < NR; ++r) acc[r] = cmake(0.0, 0.0);
+      int j = 0;
+      for (; j + 4 <= width; j += 4) {
+        c128 a4[4];
+        int c4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          a4[u] = ldg_stream(vp + 32 * (j + u));
+          c4[u] = ldg_stream(cp + 32 * (j + u));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int r = 0; r < NR; ++r) acc[r] = cfma(a4[u], p_s[(size_t)r * mc + c4[u]], acc[r]);
+      }
+      for (; j < width; ++j) {
+        const c128 a = ldg_stream(vp + 32 * j);
+        const int c = ldg_stream(cp + 32 * j);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) acc[r] = cfma(a, p_s[(size_t)r * mc + c], acc[r]);
+      }
+      if (row >= 0) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          qg[r][row] = acc[r];
+          if (want_dot) {
+            const c128 t = cmul(p_s[(size_t)r * mc + row], acc[r]);
+            dots[2 * r] += t.x; dots[2 * r + 1] += t.y;
+          }
+        }
+      }
+    }
+  };
+  auto spmv_flat = [&](bool want_dot, double (&dots)[2 * NR]) {
+#pragma unroll
+    for (int k = 0; k < 2 * NR; ++k) dots[k] = 0.0;
+    if (s_lo >= s_hi) return;
+    const c128 *vp = sv + lane;
+    const int32_t *cp = sell_col + lane;
+    int step = __ldg(&sell_ptr[s_lo]) >> 5;
+    const int step_end = __ldg(&sell_ptr[s_hi]) >> 5;
+    int sl = s_lo;
+    int next_b = __ldg(&sell_ptr[sl + 1]) >> 5;
+    int row = __ldg(&sell_perm[sl * 32 + lane]);
+    c128 acc[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) acc[r] = cmake(0.0, 0.0);
+    auto flush = [&]() {
+      if (row >= 0) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          qg[r][row] = acc[r];
+          if (want_dot) {
+            const c128 t = cmul(p_s[(size_t)r * mc + row], acc[r]);
+            dots[2 * r] += t.x; dots[2 * r + 1] += t.y;
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < NR; ++r) acc[r] = cmake(0.0, 0.0);
+      ++sl;
+      if (sl < s_hi) {
+        next_b = __ldg(&sell_ptr[sl + 1]) >> 5;
+        row = __ldg(&sell_perm[sl * 32 + lane]);
+      }
+    };
+    while (sl < s_hi && next_b == step) flush();  // leading empty slices (rows without entries)
+    constexpr int SPDX = SPD > 0 ? SPD : 1;
+    c128 a0[SPDX];
+    int c0[SPDX];
+#pragma unroll
+    for (int u = 0; u < SPD; ++u) {
+      const int st = step + u;
+      a0[u] = cmake(0.0, 0.0);
+      c0[u] = 0;
+      if (st < step_end) {
+        a0[u] = ldg_stream(vp + (size_t)32 * st);
+        c0[u] = ldg_stream(cp + (size_t)32 * st);
+      }
+    }
+    while (step < step_end) {
+      c128 a1[DB ? SPDX : 1];
+      int c1[DB ? SPDX : 1];
+      if (DB) {
+#pragma unroll
+        for (int u = 0; u < SPD; ++u) {
+          const int st = step + SPD + u;
+          a1[DB ? u : 0] = cmake(0.0, 0.0);
+          c1[DB ? u : 0] = 0;
+          if (st < step_end) {
+            a1[DB ? u : 0] = ldg_stream(vp + (size_t)32 * st);
+            c1[DB ? u : 0] = ldg_stream(cp + (size_t)32 * st);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < SPD; ++u) {
+        const int st = step + u;
+        if (st < step_end) {
+#pragma unroll
+          for (int r = 0; r < NR; ++r) acc[r] = cfma(a0[u], p_s[(size_t)r * mc + c0[u]], acc[r]);
+          while (sl < s_hi && next_b == st + 1) flush();
+        }
+      }
+      step += SPD;
+#pragma unroll
+      for (int u = 0; u < SPD; ++u) {
+        if (DB) {
+          a0[u] = a1[DB ? u : 0];
+          c0[u] = c1[DB ? u : 0];
+        } else {
+          const int st = step + u;
+          a0[u] = cmake(0.0, 0.0);
+          c0[u] = 0;
+          if (st < step_end) {
+            a0[u] = ldg_stream(vp + (size_t)32 * st);
+            c0[u] = ldg_stream(cp + (size_t)32 * st);
+          }
+        }
+      }
+    }
+    while (sl < s_hi) flush();  // trailing empty slices
+  };
+
+  auto spmv = [&](bool want_dot, double (&dots)[2 * NR]) {
+    if (SPD == 0) spmv_slices(want_dot, dots);
+    else spmv_flat(want_dot, dots);
+  };
+
+  for (int cycle = 0;; ++cycle) {
+    // (1) true residual r = b - A x from the current iterate
+    double d4[2 * NR];
+    if (cycle == 0 && zero_x) {
+      for (int i = tid; i < mc; i += nth) {
+        const int e = __ldg(&c_orig[i]);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) { xg[r][e] = cmake(0.0, 0.0); qg[r][i] = cmake(0.0, 0.0); }
+      }
+    } else {
+      for (int i = tid; i < mc; i += nth) {
+        const int e = __ldg(&c_orig[i]);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) p_s[(size_t)r * mc + i] = xg[r][e];
+      }
+      __syncthreads();
+      spmv(false, d4);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 2 * NR; ++k) d4[k] = 0.0;
+    for (int i = tid; i < mc; i += nth) {
+      const int e = __ldg(&c_orig[i]);
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        const c128 bi = bg[r][e];
+        const c128 ri = csub(bi, qg[r][i]);
+        rg[r][i] = ri;
+        d4[2 * r] += cabs2(ri);
+        d4[2 * r + 1] += cabs2(bi);
+      }
+    }
+    block_allreduce<2 * NR>(d4, red);
+    bool any = false;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      const double rr_r = d4[2 * r], bb_r = d4[2 * r + 1];
+      if (tid == 0) { sc_rr[r] = rr_r; sc_bb[r] = bb_r; }
+      conv[r] = (rr_r <= D.tol2 * bb_r);
+      act[r] = !conv[r] && iters[r] < D.max_it && cycle <= max_restarts && isfinite(rr_r);
+      any |= act[r];
+    }
+    __syncthreads();
+    if (!any) break;
+
+    // (2)+(3) preconditioned COCG until the recursive residual converges.  Two block reductions per
+    // iteration: (rho_new = r^T z, |r|^2) after the preconditioner and p^T A p after the SpMV.
+    bool fresh = true;  // p = z on entry, p = z + beta p afterwards
+    for (;;) {
+      // z = M^-1 r  (z parked in q), rho_new = r^T z, rr = |r|^2
+      if (aux) {
+        // nodal gather w = diag(G^T A G)^-1 G^T r: 16 lanes cooperate on a node (its ~12 incident edges are
+        // fetched in one parallel step instead of a serial chain), half-warp shuffle reduction
+        const int l16 = tid & 15, g16 = tid >> 4, ng16 = nth >> 4;
+        const unsigned hmask = 0xffffu << (((tid & 31) >> 4) * 16);
+        for (int n = g16; n < nn; n += ng16) {
+          const int kb = __ldg(&c_n2e_ptr[n]), ke = __ldg(&c_n2e_ptr[n + 1]);
+          c128 a2[NR];
+#pragma unroll
+          for (int r = 0; r < NR; ++r) a2[r] = cmake(0.0, 0.0);
+          for (int k = kb + l16; k < ke; k += 16) {
+            const int it = __ldg(&c_n2e_item[k]);  // compact edge << 1 | head (Dirichlet edges are not in the lists)
+            const int e = it >> 1;
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+              const c128 v = rg[r][e];
+              a2[r] = (it & 1) ? cadd(a2[r], v) : csub(a2[r], v);
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < NR; ++r)
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+              a2[r].x += __shfl_xor_sync(hmask, a2[r].x, o);
+              a2[r].y += __shfl_xor_sync(hmask, a2[r].y, o);
+            }
+          if (l16 == 0) {
+            const c128 li = __ldg(&linv[n]);
+#pragma unroll
+            for (int r = 0; r < NR; ++r) w_s[(size_t)r * nn + n] = cmul(li, a2[r]);
+          }
+        }
+        __syncthreads();
+      }
+      double dz[3 * NR];
+#pragma unroll
+      for (int k = 0; k < 3 * NR; ++k) dz[k] = 0.0;
+      for (int e = tid; e < mc; e += nth) {
+        const c128 di = __ldg(&dinv[__ldg(&c_orig[e])]);
+        int2 ab = make_int2(0, 0);
+        const bool g = aux != 0;
+        if (g) ab = __ldg(&c_edge_nodes[e]);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          const c128 ri = rg[r][e];
+          c128 z = cmul(di, ri);
+          if (g) z = cadd(z, csub(w_s[(size_t)r * nn + ab.y], w_s[(size_t)r * nn + ab.x]));
+          qg[r][e] = z;
+          const c128 t = cmul(ri, z);
+          dz[3 * r] += t.x; dz[3 * r + 1] += t.y;
+          dz[3 * r + 2] += cabs2(ri);
+        }
+      }
+      block_allreduce<3 * NR>(dz, red);
+      bool still = false;
+      c128 beta[NR];
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        const c128 rho_new = cmake(dz[3 * r], dz[3 * r + 1]);
+        const c128 rho_old = cmake(sc_rho[(par * NR + r) * 2], sc_rho[(par * NR + r) * 2 + 1]);
+        beta[r] = (fresh || (rho_old.x == 0.0 && rho_old.y == 0.0)) ? cmake(0.0, 0.0) : cdiv(rho_new, rho_old);
+        if (tid == 0) {
+          sc_rho[((par ^ 1) * NR + r) * 2] = rho_new.x;
+          sc_rho[((par ^ 1) * NR + r) * 2 + 1] = rho_new.y;
+        }
+        if (act[r]) {
+          const double rr_r = dz[3 * r + 2];
+          if (tid == 0) sc_rr[r] = rr_r;
+          if (rr_r <= D.tol2 * sc_bb[r] || iters[r] >= D.max_it || !isfinite(rr_r)) act[r] = false;
+        }
+        still |= act[r];
+      }
+      par ^= 1;
+      if (!still) break;
+      for (int e = tid; e < mc; e += nth)
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          const c128 z = qg[r][e];
+          p_s[(size_t)r * mc + e] = fresh ? z : cfma(beta[r], p_s[(size_t)r * mc + e], z);
+        }
+      fresh = false;
+      __syncthreads();
+      // q = A p ; alpha = rho / p^T q
+      double dq[2 * NR];
+      spmv(true, dq);
+      block_allreduce<2 * NR>(dq, red);
+      c128 alpha[NR];
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        const c128 pq = cmake(dq[2 * r], dq[2 * r + 1]);
+        const bool brk = (pq.x == 0.0 && pq.y == 0.0) || !(isfinite(pq.x) && isfinite(pq.y));
+        if (brk) act[r] = false;
+        const c128 rho_r = cmake(sc_rho[(par * NR + r) * 2], sc_rho[(par * NR + r) * 2 + 1]);
+        alpha[r] = act[r] ? cdiv(rho_r, pq) : cmake(0.0, 0.0);
+        if (act[r]) iters[r] += 1;
+      }
+      // x += alpha p ; r -= alpha q   (|r|^2 is accumulated by the next preconditioner pass)
+      for (int i = tid; i < mc; i += nth) {
+        const int e = __ldg(&c_orig[i]);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          if (!act[r]) continue;
+          xg[r][e] = cfma(alpha[r], p_s[(size_t)r * mc + i], xg[r][e]);
+          rg[r][i] = cfma(cneg(alpha[r]), qg[r][i], rg[r][i]);
+        }
+      }
+      bool any2 = false;
+#pragma unroll
+      for (int r = 0; r < NR; ++r) any2 |= act[r];
+      __syncthreads();
+      if (!any2) break;
+    }
+  }
+  if (tid == 0) {
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      int32_t *st = D.state + (s0 + r) * 4;
+      st[ST_ACTIVE] = 0; st[ST_ITERS] = iters[r]; st[ST_CONV] = conv[r] ? 1 : 0; st[ST_REC] = 0;
+      c128 *sc = scal_of(D, s0 + r);
+      sc[S_RR] = cmake(sc_rr[r], 0.0);
+      sc[S_BB] = cmake(sc_bb[r], 0.0);
+    }
+  }
+  __syncthreads();
+}
+
 template <int NR, int NT, int SPD, bool DB, int MINB = 1>
 __global__ void __launch_bounds__(NT, MINB)
 k_cocg_small(SolveDev D, const int32_t *__restrict__ sell_ptr, const int32_t *__restrict__ sell_col, const int32_t *__restrict__ sell_perm,
-             const c128 *__restrict__ sell_vals, long long sell_total, int n_slices, int first_matrix, int n_jobs, int groups_per_matrix,
+             const c128 *__restrict__ sell_vals, long long sell_total, int n_slices, int first_matrix, int n_jobs, int groups_per_matrix, int mixed,
              int *job_counter, const c128 *__restrict__ bvec, c128 *xvec, c128 *rvec, c128 *qvec, int aux, int zero_x, int max_restarts,
              int mc, const int32_t *__restrict__ c_orig, const int2 *__restrict__ c_edge_nodes, const int32_t *__restrict__ c_n2e_ptr,
              const int32_t *__restrict__ c_n2e_item) {
   // The solver runs on the mc FREE unknowns ("compact" ids, c_orig maps them to edge ids): r, q, p and the SELL
   // structure are compact, b, x, dinv keep the original layout (stride m).
+  // Job codes: plain index (matrix = code / groups, NR right-hand sides of group code % groups), or -- mixed mode, two
+  // right-hand sides per matrix -- matrix * 4 + kind: kind 0 = both right-hand sides together, 1 / 2 = one of them alone.
+  // The host splits the matrices expected to finish last into single jobs so that the SMs that would idle through the
+  // second round of jobs share its tail (run_cocg_small).
   extern __shared__ __align__(16) unsigned char sm_raw[];
-  const int m = D.m, nn = aux ? D.n_node : 0;
-  c128 *p_s = (c128 *)sm_raw;                 // [NR][mc]
-  c128 *w_s = p_s + (size_t)NR * mc;          // [NR][nn]
-  double *red = (double *)(w_s + (size_t)NR * nn);  // [33*8]
   __shared__ int s_job;
-  const int tid = threadIdx.x, nth = blockDim.x;
-  const int lane = tid & 31, wid = tid >> 5, nwarp = nth >> 5;
-
+  const int tid = threadIdx.x;
   for (;;) {
     if (tid == 0) {
       const int q = atomicAdd(job_counter, 1);
-      s_job = q < n_jobs ? job_counter[1 + q] : n_jobs;  // queue position -> job (longest expected first)
+      s_job = q < n_jobs ? job_counter[1 + q] : -1;  // queue position -> job (longest expected first)
     }
     __syncthreads();
     const int job = s_job;
     __syncthreads();
-    if (job >= n_jobs) break;
-    const int f = first_matrix + job / groups_per_matrix;
-    const int s0 = f * D.n_rhs + (job % groups_per_matrix) * NR;
-    const c128 *__restrict__ av = D.vals + (size_t)f * D.nnz;
-    const c128 *__restrict__ dinv = D.dinv + (size_t)f * m;
-    const c128 *__restrict__ linv = D.linv + (size_t)f * (aux ? D.n_node : 0);
-    // per-rhs vectors are addressed as base + r*m (one base pointer per vector instead of NR pointers)
-    struct VRef {
-      c128 *base;
-      int m;
-      __device__ __forceinline__ c128 *operator[](int r) const { return base + (size_t)r * m; }
-    };
-    const size_t off0 = (size_t)s0 * m;
-    const VRef xg{xvec + off0, m}, rg{rvec + off0, m}, qg{qvec + off0, m}, bg{const_cast<c128 *>(bvec) + off0, m};
-    // block-uniform scalars live in shared memory (written by thread 0 between barriers): bb, rr and a
-    // double-buffered rho per right-hand side
-    double *sc_bb = red + 33 * 8, *sc_rr = sc_bb + NR, *sc_rho = sc_rr + NR;  // sc_rho[parity][r][2]
-    int par = 0;
-    int iters[NR];
-    bool act[NR], conv[NR];
-#pragma unroll
-    for (int r = 0; r < NR; ++r) { iters[r] = 0; act[r] = false; conv[r] = false; }
-    if (tid < 8 * NR) sc_bb[tid] = 0.0;
-    // Dirichlet rows are decoupled identity rows: x_e = b_e / A_ee, once
-    if (mc < m)
-      for (int e = tid; e < m; e += nth)
-        if (D.dir[e]) {
-          const c128 de = __ldg(&dinv[e]);
-#pragma unroll
-          for (int r = 0; r < NR; ++r) xg[r][e] = cmul(de, bg[r][e]);
-        }
-    __syncthreads();
-
-    // q = A * (vector in p_s), optional dot p.q.  SELL-32: a lane owns a row, 32 rows form a slice stored
-    // column-major.  A warp owns a CONTIGUOUS range of slices (balanced by entry count), so its values and
-    // columns are one flat stream: every step is a coalesced 512-byte value load + 128-byte column load,
-    // SPD steps are in flight per lane and the next batch is requested before the current one is consumed
-    // (double buffering in registers); slice ends only flush the row accumulators.  No shuffles.
-    const c128 *__restrict__ sv = sell_vals + (size_t)f * (size_t)sell_total;
-    int s_lo, s_hi;
-    {
-      const long long t0 = sell_total * wid / nwarp, t1 = sell_total * (wid + 1) / nwarp;
-      auto lower = [&](long long t) {
-        int lo = 0, hi = n_slices;
-        while (lo < hi) {
-          const int mid = (lo + hi) >> 1;
-          if ((long long)__ldg(&sell_ptr[mid]) < t) lo = mid + 1; else hi = mid;
-        }
-        return lo;
-      };
-      s_lo = lower(t0);
-      s_hi = (wid == nwarp - 1) ? n_slices : lower(t1);
+    if (job < 0) break;
+    if (mixed && NR == 2) {
+      const int f = first_matrix + (job >> 2), kind = job & 3;
+      if (kind == 0)
+        cocg_small_job<2, SPD, DB>(D, sell_ptr, sell_col, sell_perm, sell_vals, sell_total, n_slices, bvec, xvec, rvec, qvec, aux, zero_x,
+                                   max_restarts, mc, c_orig, c_edge_nodes, c_n2e_ptr, c_n2e_item, sm_raw, f, f * D.n_rhs);
+      else
+        cocg_small_job<1, SPD, DB>(D, sell_ptr, sell_col, sell_perm, sell_vals, sell_total, n_slices, bvec, xvec, rvec, qvec, aux, zero_x,
+                                   max_restarts, mc, c_orig, c_edge_nodes, c_n2e_ptr, c_n2e_item, sm_raw, f, f * D.n_rhs + kind - 1);
+    } else {
+      const int f = first_matrix + job / groups_per_matrix;
+      cocg_small_job<NR, SPD, DB>(D, sell_ptr, sell_col, sell_perm, sell_vals, sell_total, n_slices, bvec, xvec, rvec, qvec, aux, zero_x,
+                                  max_restarts, mc, c_orig, c_edge_nodes, c_n2e_ptr, c_n2e_item, sm_raw, f,
+                                  f * D.n_rhs + (job % groups_per_matrix) * NR);
     }
-    // per-slice variant (SPD == 0): slices dealt round-robin to the warps, batches of 4 independent loads
-    auto spmv_slices = [&](bool want_dot, double (&dots)[2 * NR]) {
-#pragma unroll
-      for (int k = 0; k < 2 * NR; ++k) dots[k] = 0.0;
-      for (int sl = wid; sl < n_slices; sl += nwarp) {
-        const int base = __ldg(&sell_ptr[sl]);
-        const int width = (__ldg(&sell_ptr[sl + 1]) - base) >> 5;
-        const int row = __ldg(&sell_perm[sl * 32 + lane]);
-        const c128 *vp = sv + base + lane;
-        const int32_t *cp = sell_col + base + lane;
-        c128 acc[NR];
-#pragma unroll
-        for (int r = 0; r < NR; ++r) acc[r] = cmake(0.0, 0.0);
-        int j = 0;
-        for (; j + 4 <= width; j += 4) {
-          c128 a4[4];
-          int c4[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            a4[u] = ldg_stream(vp + 32 * (j + u));
-            c4[u] = ldg_stream(cp + 32 * (j + u));
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-#pragma unroll
-            for (int r = 0; r < NR; ++r) acc[r] = cfma(a4[u], p_s[(size_t)r * mc + c4[u]], acc[r]);
-        }
-        for (; j < width; ++j) {
-          const c128 a = ldg_stream(vp + 32 * j);
-          const int c = ldg_stream(cp + 32 * j);
-#pragma unroll
-          for (int r = 0; r < NR; ++r) acc[r] = cfma(a, p_s[(size_t)r * mc + c], acc[r]);
-        }
-        if (row >= 0) {
-#pragma unroll
-          for (int r = 0; r < NR; ++r) {
-            qg[r][row] = acc[r];
-            if (want_dot) {
-              const c128 t = cmul(p_s[(size_t)r * mc + row], acc[r]);
-              dots[2 * r] += t.x; dots[2 * r + 1] += t.y;
-            }
-          }
-        }
-      }
-    };
-    auto spmv_flat = [&](bool want_dot, double (&dots)[2 * NR]) {
-#pragma unroll
-      for (int k = 0; k < 2 * NR; ++k) dots[k] = 0.0;
-      if (s_lo >= s_hi) return;
-      const c128 *vp = sv + lane;
-      const int32_t *cp = sell_col + lane;
-      int step = __ldg(&sell_ptr[s_lo]) >> 5;
-      const int step_end = __ldg(&sell_ptr[s_hi]) >> 5;
-      int sl = s_lo;
-      int next_b = __ldg(&sell_ptr[sl + 1]) >> 5;
-      int row = __ldg(&sell_perm[sl * 32 + lane]);
-      c128 acc[NR];
-#pragma unroll
-      for (int r = 0; r < NR; ++r) acc[r] = cmake(0.0, 0.0);
-      auto flush = [&]() {
-        if (row >= 0) {
-#pragma unroll
-          for (int r = 0; r < NR; ++r) {
-            qg[r][row] = acc[r];
-            if (want_dot) {
-              const c128 t = cmul(p_s[(size_t)r * mc + row], acc[r]);
-              dots[2 * r] += t.x; dots[2 * r + 1] += t.y;
-            }
-          }
-        }
-#pragma unroll
-        for (int r = 0; r < NR; ++r) acc[r] = cmake(0.0, 0.0);
-        ++sl;
-        if (sl < s_hi) {
-          next_b = __ldg(&sell_ptr[sl + 1]) >> 5;
-          row = __ldg(&sell_perm[sl * 32 + lane]);
-        }
-      };
-      while (sl < s_hi && next_b == step) flush();  // leading empty slices (rows without entries)
-      constexpr int SPDX = SPD > 0 ? SPD : 1;
-      c128 a0[SPDX];
-      int c0[SPDX];
-#pragma unroll
-      for (int u = 0; u < SPD; ++u) {
-        const int st = step + u;
-        a0[u] = cmake(0.0, 0.0);
-        c0[u] = 0;
-        if (st < step_end) {
-          a0[u] = ldg_stream(vp + (size_t)32 * st);
-          c0[u] = ldg_stream(cp + (size_t)32 * st);
-        }
-      }
-      while (step < step_end) {
-        c128 a1[DB ? SPDX : 1];
-        int c1[DB ? SPDX : 1];
-        if (DB) {
-#pragma unroll
-          for (int u = 0; u < SPD; ++u) {
-            const int st = step + SPD + u;
-            a1[DB ? u : 0] = cmake(0.0, 0.0);
-            c1[DB ? u : 0] = 0;
-            if (st < step_end) {
-              a1[DB ? u : 0] = ldg_stream(vp + (size_t)32 * st);
-              c1[DB ? u : 0] = ldg_stream(cp + (size_t)32 * st);
-            }
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < SPD; ++u) {
-          const int st = step + u;
-          if (st < step_end) {
-#pragma unroll
-            for (int r = 0; r < NR; ++r) acc[r] = cfma(a0[u], p_s[(size_t)r * mc + c0[u]], acc[r]);
-            while (sl < s_hi && next_b == st + 1) flush();
-          }
-        }
-        step += SPD;
-#pragma unroll
-        for (int u = 0; u < SPD; ++u) {
-          if (DB) {
-            a0[u] = a1[DB ? u : 0];
-            c0[u] = c1[DB ? u : 0];
-          } else {
-            const int st = step + u;
-            a0[u] = cmake(0.0, 0.0);
-            c0[u] = 0;
-            if (st < step_end) {
-              a0[u] = ldg_stream(vp + (size_t)32 * st);
-              c0[u] = ldg_stream(cp + (size_t)32 * st);
-            }
-          }
-        }
-      }
-      while (sl < s_hi) flush();  // trailing empty slices
-    };
-
-    auto spmv = [&](bool want_dot, double (&dots)[2 * NR]) {
-      if (SPD == 0) spmv_slices(want_dot, dots);
-      else spmv_flat(want_dot, dots);
-    };
-
-    for (int cycle = 0;; ++cycle) {
-      // (1) true residual r = b - A x from the current iterate
-      double d4[2 * NR];
-      if (cycle == 0 && zero_x) {
-        for (int i = tid; i < mc; i += nth) {
-          const int e = __ldg(&c_orig[i]);
-#pragma unroll
-          for (int r = 0; r < NR; ++r) { xg[r][e] = cmake(0.0, 0.0); qg[r][i] = cmake(0.0, 0.0); }
-        }
-      } else {
-        for (int i = tid; i < mc; i += nth) {
-          const int e = __ldg(&c_orig[i]);
-#pragma unroll
-          for (int r = 0; r < NR; ++r) p_s[(size_t)r * mc + i] = xg[r][e];
-        }
-        __syncthreads();
-        spmv(false, d4);
-      }
-      __syncthreads();
-#pragma unroll
-      for (int k = 0; k < 2 * NR; ++k) d4[k] = 0.0;
-      for (int i = tid; i < mc; i += nth) {
-        const int e = __ldg(&c_orig[i]);
-#pragma unroll
-        for (int r = 0; r < NR; ++r) {
-          const c128 bi = bg[r][e];
-          const c128 ri = csub(bi, qg[r][i]);
-          rg[r][i] = ri;
-          d4[2 * r] += cabs2(ri);
-          d4[2 * r + 1] += cabs2(bi);
-        }
-      }
-      block_allreduce<2 * NR>(d4, red);
-      bool any = false;
-#pragma unroll
-      for (int r = 0; r < NR; ++r) {
-        const double rr_r = d4[2 * r], bb_r = d4[2 * r + 1];
-        if (tid == 0) { sc_rr[r] = rr_r; sc_bb[r] = bb_r; }
-        conv[r] = (rr_r <= D.tol2 * bb_r);
-        act[r] = !conv[r] && iters[r] < D.max_it && cycle <= max_restarts && isfinite(rr_r);
-        any |= act[r];
-      }
-      __syncthreads();
-      if (!any) break;
-
-      // (2)+(3) preconditioned COCG until the recursive residual converges.  Two block reductions per
-      // iteration: (rho_new = r^T z, |r|^2) after the preconditioner and p^T A p after the SpMV.
-      bool fresh = true;  // p = z on entry, p = z + beta p afterwards
-      for (;;) {
-        // z = M^-1 r  (z parked in q), rho_new = r^T z, rr = |r|^2
-        if (aux) {
-          // nodal gather w = diag(G^T A G)^-1 G^T r: 16 lanes cooperate on a node (its ~12 incident edges are
-          // fetched in one parallel step instead of a serial chain), half-warp shuffle reduction
-          const int l16 = tid & 15, g16 = tid >> 4, ng16 = nth >> 4;
-          const unsigned hmask = 0xffffu << (((tid & 31) >> 4) * 16);
-          for (int n = g16; n < nn; n += ng16) {
-            const int kb = __ldg(&c_n2e_ptr[n]), ke = __ldg(&c_n2e_ptr[n + 1]);
-            c128 a2[NR];
-#pragma unroll
-            for (int r = 0; r < NR; ++r) a2[r] = cmake(0.0, 0.0);
-            for (int k = kb + l16; k < ke; k += 16) {
-              const int it = __ldg(&c_n2e_item[k]);  // compact edge << 1 | head (Dirichlet edges are not in the lists)
-              const int e = it >> 1;
-#pragma unroll
-              for (int r = 0; r < NR; ++r) {
-                const c128 v = rg[r][e];
-                a2[r] = (it & 1) ? cadd(a2[r], v) : csub(a2[r], v);
-              }
-            }
-#pragma unroll
-            for (int r = 0; r < NR; ++r)
-#pragma unroll
-              for (int o = 8; o > 0; o >>= 1) {
-                a2[r].x += __shfl_xor_sync(hmask, a2[r].x, o);
-                a2[r].y += __shfl_xor_sync(hmask, a2[r].y, o);
-              }
-            if (l16 == 0) {
-              const c128 li = __ldg(&linv[n]);
-#pragma unroll
-              for (int r = 0; r < NR; ++r) w_s[(size_t)r * nn + n] = cmul(li, a2[r]);
-            }
-          }
-          __syncthreads();
-        }
-        double dz[3 * NR];
-#pragma unroll
-        for (int k = 0; k < 3 * NR; ++k) dz[k] = 0.0;
-        for (int e = tid; e < mc; e += nth) {
-          const c128 di = __ldg(&dinv[__ldg(&c_orig[e])]);
-          int2 ab = make_int2(0, 0);
-          const bool g = aux != 0;
-          if (g) ab = __ldg(&c_edge_nodes[e]);
-#pragma unroll
-          for (int r = 0; r < NR; ++r) {
-            const c128 ri = rg[r][e];
-            c128 z = cmul(di, ri);
-            if (g) z = cadd(z, csub(w_s[(size_t)r * nn + ab.y], w_s[(size_t)r * nn + ab.x]));
-            qg[r][e] = z;
-            const c128 t = cmul(ri, z);
-            dz[3 * r] += t.x; dz[3 * r + 1] += t.y;
-            dz[3 * r + 2] += cabs2(ri);
-          }
-        }
-        block_allreduce<3 * NR>(dz, red);
-        bool still = false;
-        c128 beta[NR];
-#pragma unroll
-        for (int r = 0; r < NR; ++r) {
-          const c128 rho_new = cmake(dz[3 * r], dz[3 * r + 1]);
-          const c128 rho_old = cmake(sc_rho[(par * NR + r) * 2], sc_rho[(par * NR + r) * 2 + 1]);
-          beta[r] = (fresh || (rho_old.x == 0.0 && rho_old.y == 0.0)) ? cmake(0.0, 0.0) : cdiv(rho_new, rho_old);
-          if (tid == 0) {
-            sc_rho[((par ^ 1) * NR + r) * 2] = rho_new.x;
-            sc_rho[((par ^ 1) * NR + r) * 2 + 1] = rho_new.y;
-          }
-          if (act[r]) {
-            const double rr_r = dz[3 * r + 2];
-            if (tid == 0) sc_rr[r] = rr_r;
-            if (rr_r <= D.tol2 * sc_bb[r] || iters[r] >= D.max_it || !isfinite(rr_r)) act[r] = false;
-          }
-          still |= act[r];
-        }
-        par ^= 1;
-        if (!still) break;
-        for (int e = tid; e < mc; e += nth)
-#pragma unroll
-          for (int r = 0; r < NR; ++r) {
-            const c128 z = qg[r][e];
-            p_s[(size_t)r * mc + e] = fresh ? z : cfma(beta[r], p_s[(size_t)r * mc + e], z);
-          }
-        fresh = false;
-        __syncthreads();
-        // q = A p ; alpha = rho / p^T q
-        double dq[2 * NR];
-        spmv(true, dq);
-        block_allreduce<2 * NR>(dq, red);
-        c128 alpha[NR];
-#pragma unroll
-        for (int r = 0; r < NR; ++r) {
-          const c128 pq = cmake(dq[2 * r], dq[2 * r + 1]);
-          const bool brk = (pq.x == 0.0 && pq.y == 0.0) || !(isfinite(pq.x) && isfinite(pq.y));
-          if (brk) act[r] = false;
-          const c128 rho_r = cmake(sc_rho[(par * NR + r) * 2], sc_rho[(par * NR + r) * 2 + 1]);
-          alpha[r] = act[r] ? cdiv(rho_r, pq) : cmake(0.0, 0.0);
-          if (act[r]) iters[r] += 1;
-        }
-        // x += alpha p ; r -= alpha q   (|r|^2 is accumulated by the next preconditioner pass)
-        for (int i = tid; i < mc; i += nth) {
-          const int e = __ldg(&c_orig[i]);
-#pragma unroll
-          for (int r = 0; r < NR; ++r) {
-            if (!act[r]) continue;
-            xg[r][e] = cfma(alpha[r], p_s[(size_t)r * mc + i], xg[r][e]);
-            rg[r][i] = cfma(cneg(alpha[r]), qg[r][i], rg[r][i]);
-          }
-        }
-        bool any2 = false;
-#pragma unroll
-        for (int r = 0; r < NR; ++r) any2 |= act[r];
-        __syncthreads();
-        if (!any2) break;
-      }
-    }
-    if (tid == 0) {
-#pragma unroll
-      for (int r = 0; r < NR; ++r) {
-        int32_t *st = D.state + (s0 + r) * 4;
-        st[ST_ACTIVE] = 0; st[ST_ITERS] = iters[r]; st[ST_CONV] = conv[r] ? 1 : 0; st[ST_REC] = 0;
-        c128 *sc = scal_of(D, s0 + r);
-        sc[S_RR] = cmake(sc_rr[r], 0.0);
-        sc[S_BB] = cmake(sc_bb[r], 0.0);
-      }
-    }
-    __syncthreads();
   }
 }
 
@@ -1488,7 +1517,8 @@ static int run_cocg_small(SolvePlan &P, const efb_solve_opts *o, bool zero_x, bo
     EFB_CHECK_LAUNCH(c);
   }
   const int groups = S->n_rhs / nr;
-  const int n_jobs = P.n_matrix * groups;
+  int n_jobs = P.n_matrix * groups;
+  int mixed = 0;
   {
     // Queue order = longest expected job first (LPT list scheduling): with n_jobs between 1x and 2x the SM count the
     // makespan is the sum of two jobs on one SM, so long jobs must start first and short ones fill in behind them.
@@ -1505,10 +1535,83 @@ static int run_cocg_small(SolvePlan &P, const efb_solve_opts *o, bool zero_x, bo
         w[j] = S->last_omega[f];
       }
     }
+    std::vector<int32_t> order((size_t)n_jobs);
+    for (int j = 0; j < n_jobs; ++j) order[j] = j;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return w[a] > w[b]; });
+    std::vector<int32_t> codes(order);
+    // Tail split (two right-hand sides per matrix, more matrices than SMs): 256 two-rhs jobs on 148 SMs leave 40 SMs
+    // idle through the second round.  The X matrices expected to finish last are queued as two one-rhs jobs each (a
+    // one-rhs job streams the matrix for itself: cost rho ~ 0.7-0.8 of a two-rhs job), X chosen by simulating the queue.
+    static const bool no_split = [] {  // EDGEFEM_B200_TAIL_SPLIT=0|1 (default below)
+      const char *e = getenv("EDGEFEM_B200_TAIL_SPLIT");
+      return e ? atoi(e) == 0 : false;
+    }();
+    // Only with iteration counts of a previous solve of this system: with frequencies as the only predictor the split
+    // was measured slower than no split (54.5 against 53.7 ms per end-to-end sweep).
+    if (nr == 2 && S->n_rhs == 2 && n_jobs > c->sm_count && variant < 4 && !no_split && have_it) {
+      double rho = 0.8;  // WR-90, same box: no split 48.0 / 49.7 ms, rho 0.5 57.1, 0.6 46.7, 0.7 46.4 / 46.7, 0.8 46.7 ms
+      if (const char *e = getenv("EDGEFEM_B200_TAIL_RHO")) rho = atof(e);
+      std::vector<double> cost((size_t)n_jobs);
+      double wmin = 0.0;
+      for (int j = 0; j < n_jobs; ++j) wmin = (j == 0) ? w[j] : std::min(wmin, w[j]);
+      // weights are only a ranking when they are frequencies: map them to a plausible cost spread (+-15 %)
+      double wmax = 0.0;
+      for (int j = 0; j < n_jobs; ++j) wmax = std::max(wmax, w[j]);
+      for (int j = 0; j < n_jobs; ++j)
+        cost[j] = have_it ? std::max(1.0, w[j]) : (wmax > wmin ? 0.85 + 0.3 * (w[j] - wmin) / (wmax - wmin) : 1.0);
+      auto makespan = [&](int X) {
+        // queue: the n_jobs - X heaviest as two-rhs jobs, then 2X one-rhs jobs, all in descending cost; every SM takes
+        // the next job when it becomes free (min-heap of SM finish times)
+        std::vector<double> q;
+        q.reserve((size_t)n_jobs + X);
+        for (int i = 0; i < n_jobs - X; ++i) q.push_back(cost[order[i]]);
+        for (int i = n_jobs - X; i < n_jobs; ++i) {
+          q.push_back(rho * cost[order[i]]);
+          q.push_back(rho * cost[order[i]]);
+        }
+        std::sort(q.begin(), q.end(), [](double a, double b) { return a > b; });
+        std::priority_queue<double, std::vector<double>, std::greater<double>> busy;
+        for (int i = 0; i < c->sm_count; ++i) busy.push(0.0);
+        double end = 0.0;
+        for (double t : q) {
+          const double b = busy.top() + t;
+          busy.pop();
+          busy.push(b);
+          end = std::max(end, b);
+        }
+        return end;
+      };
+      int bestX = 0;
+      double best = makespan(0);
+      for (int X = 8; X <= std::min(n_jobs, c->sm_count); X += 8) {
+        const double t = makespan(X);
+        if (t < best * 0.999) {
+          best = t;
+          bestX = X;
+        }
+      }
+      if (bestX > 0) {
+        mixed = 1;
+        struct Q {
+          double cost;
+          int32_t code;
+        };
+        std::vector<Q> q;
+        for (int i = 0; i < n_jobs - bestX; ++i) q.push_back({cost[order[i]], (int32_t)(order[i] * 4)});
+        for (int i = n_jobs - bestX; i < n_jobs; ++i) {
+          q.push_back({rho * cost[order[i]], (int32_t)(order[i] * 4 + 1)});
+          q.push_back({rho * cost[order[i]], (int32_t)(order[i] * 4 + 2)});
+        }
+        std::stable_sort(q.begin(), q.end(), [](const Q &a, const Q &b) { return a.cost > b.cost; });
+        codes.resize(q.size());
+        for (size_t i = 0; i < q.size(); ++i) codes[i] = q[i].code;
+        n_jobs = (int)codes.size();
+      }
+    }
+    if ((size_t)n_jobs + 1 > (size_t)S->n_sys + 1) return fail(c, EFB_ERR_STATE, "persistent solver: job queue overflow");
     S->h_job_order.resize((size_t)n_jobs + 1);
     S->h_job_order[0] = 0;
-    for (int j = 0; j < n_jobs; ++j) S->h_job_order[1 + j] = j;
-    std::stable_sort(S->h_job_order.begin() + 1, S->h_job_order.end(), [&](int a, int b) { return w[a] > w[b]; });
+    for (int j = 0; j < n_jobs; ++j) S->h_job_order[1 + j] = codes[j];
     EFB_CUDA(c, cudaMemcpyAsync(S->d_job, S->h_job_order.data(), S->h_job_order.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
   }
   if (!S->ev_s0) {
@@ -1524,7 +1627,7 @@ static int run_cocg_small(SolvePlan &P, const efb_solve_opts *o, bool zero_x, bo
   do {                                                                                                                                    \
     EFB_CUDA(c, cudaFuncSetAttribute(k_cocg_small<NRV, NT, SPDV, DBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
     k_cocg_small<NRV, NT, SPDV, DBV><<<grid, NT, smem, c->stream>>>(P.D, S->d_sell_ptr, S->d_sell_col, S->d_sell_perm, S->d_sell_vals,    \
-                                                                      S->sell_total, S->n_slices, P.first_matrix, n_jobs, groups, S->d_job, \
+                                                                      S->sell_total, S->n_slices, P.first_matrix, n_jobs, groups, mixed, S->d_job, \
                                                                       S->d_b, S->d_x, P.vec[V_R], P.vec[V_Q], P.aux ? 1 : 0, zero_x ? 1 : 0, mr, \
                                                                       mc, S->d_c_orig, S->d_c_edge_nodes, S->d_c_n2e_ptr, S->d_c_n2e_item); \
   } while (0)
@@ -1532,7 +1635,7 @@ static int run_cocg_small(SolvePlan &P, const efb_solve_opts *o, bool zero_x, bo
   do {                                                                                                                                    \
     EFB_CUDA(c, cudaFuncSetAttribute(k_cocg_small<NRV, NT, SPDV, DBV, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
     k_cocg_small<NRV, NT, SPDV, DBV, 2><<<grid, NT, smem, c->stream>>>(P.D, S->d_sell_ptr, S->d_sell_col, S->d_sell_perm, S->d_sell_vals, \
-                                                                      S->sell_total, S->n_slices, P.first_matrix, n_jobs, groups, S->d_job, \
+                                                                      S->sell_total, S->n_slices, P.first_matrix, n_jobs, groups, mixed, S->d_job, \
                                                                       S->d_b, S->d_x, P.vec[V_R], P.vec[V_Q], P.aux ? 1 : 0, zero_x ? 1 : 0, mr, \
                                                                       mc, S->d_c_orig, S->d_c_edge_nodes, S->d_c_n2e_ptr, S->d_c_n2e_item); \
   } while (0)
