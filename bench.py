@@ -295,6 +295,9 @@ def run_b200(a):
     os.environ.setdefault("EDGEFEM_B200_DEVICE", str(local))
     dist = None
     if world > 1:
+        # stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) out of it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch
         import torch.distributed as dist
 
