@@ -304,7 +304,7 @@ k_spmv_stream(SolveDev D, const int32_t *__restrict__ sp_chunk, int n_chunks, in
 }
 
 // chunk descriptors and stage geometry of the TMA-streamed SpMV below
-constexpr int SPMV_PIPE_COLS = SPMV_STREAM_W + 4;  // aligned superset of the column slice
+constexpr int SPMV_STAGE_COLS = SPMV_STREAM_W + 4;  // aligned superset of the column slice
 constexpr int SPMV_VAL_BYTES = SPMV_SLOTS * 16;  // value area of a stage, sized for the skewed products written in place
 struct ChunkDesc {
   int r0, nrow, k0, k1;
@@ -349,7 +349,7 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-constexpr int SPMV_TMA_STAGE = SPMV_VAL_BYTES + SPMV_PIPE_COLS * 4;  // 5392 B (16-byte multiple)
+constexpr int SPMV_TMA_STAGE = SPMV_VAL_BYTES + SPMV_STAGE_COLS * 4;  // 5392 B (16-byte multiple)
 
 template <int DOT>
 __global__ void __launch_bounds__(256, 2)
