@@ -35,6 +35,8 @@ WR90_A, WR90_B = 0.02286, 0.01016
 F_LO, F_HI, N_POINTS = 8e9, 12e9, 256
 
 
+_LINE = []  # the one JSON line of this process (rank 0 only), printed by main() after stdout is restored
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -155,7 +157,7 @@ def run_reference(a):
         "e2e": {"value": v, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    _LINE.append(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------ B200 arm
@@ -437,17 +439,30 @@ def run_b200(a):
         "clocks": clocks,
         "extras": extras,
     }
-    print(json.dumps(line))
+    _LINE.append(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
 
 
 def main():
     a = parse()
-    if a.impl == "reference":
-        run_reference(a)
-    else:
-        run_b200(a)
+    # stdout carries exactly one JSON line.  Libraries write banners to file descriptor 1 behind Python's back (NCCL prints
+    # "NCCL version ..." when the box sets NCCL_DEBUG=VERSION, and reads that variable before Python can change it in every
+    # rank), so fd 1 points at stderr while the benchmark runs and is restored for the final print.
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        if a.impl == "reference":
+            run_reference(a)
+        else:
+            run_b200(a)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+    if _LINE:
+        print(_LINE[0], flush=True)
 
 
 if __name__ == "__main__":
