@@ -499,9 +499,12 @@ k_sell_fill(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ coli
   if (id >= n_slices * 4) return;
   const int sl = id >> 2, q = id & 3;
   const int base = sptr[sl], width = (sptr[sl + 1] - base) >> 5;
-  int16_t ent[8][SELL_FILL_MAX];  // CSR offsets (relative to the row start) of the free entries, bucketed by bank group
+  int16_t ent[8][SELL_FILL_MAX];   // CSR offsets (relative to the row start) of the free entries, bucketed by bank group
+  int16_t ecol[8][SELL_FILL_MAX];  // their compact columns (m_c <= 16384)
   int beg[8][8], cnt[8][8], left[8], rstart[8];
   bool fits = true;
+  // The CSR walks are chains of dependent loads (column -> compact id): four entries are fetched per step so that the
+  // loads of a step overlap.
   for (int t = 0; t < 8; ++t) {
     const int i = perm[sl * 32 + 8 * q + t];
     left[t] = 0;
@@ -509,14 +512,22 @@ k_sell_fill(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ coli
     for (int g = 0; g < 8; ++g) cnt[t][g] = 0;
     if (i < 0) continue;
     const int r = orig[i];
-    rstart[t] = rowptr[r];
-    for (int k = rowptr[r]; k < rowptr[r + 1]; ++k) {
-      const int cc = comp[colidx[k]];
-      if (cc < 0) continue;
-      cnt[t][cc & 7]++;
-      left[t]++;
+    const int k0 = rowptr[r], k1 = rowptr[r + 1];
+    rstart[t] = k0;
+    for (int k = k0; k < k1; k += 4) {
+      int c4[4], m4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) c4[u] = (k + u < k1) ? colidx[k + u] : -1;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) m4[u] = (c4[u] >= 0) ? comp[c4[u]] : -1;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (m4[u] >= 0) {
+          cnt[t][m4[u] & 7]++;
+          left[t]++;
+        }
     }
-    if (left[t] > SELL_FILL_MAX || rowptr[r + 1] - rowptr[r] > 32767) fits = false;
+    if (left[t] > SELL_FILL_MAX || k1 - k0 > 32767) fits = false;
   }
   if (!fits) {  // CSR order
     for (int t = 0; t < 8; ++t) {
@@ -548,11 +559,20 @@ k_sell_fill(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ coli
     }
     if (left[t] == 0) continue;
     const int r = orig[perm[sl * 32 + 8 * q + t]];
-    for (int k = rowptr[r]; k < rowptr[r + 1]; ++k) {
-      const int cc = comp[colidx[k]];
-      if (cc < 0) continue;
-      const int g = cc & 7;
-      ent[t][beg[t][g] + cnt[t][g]++] = (int16_t)(k - rstart[t]);
+    const int k0 = rowptr[r], k1 = rowptr[r + 1];
+    for (int k = k0; k < k1; k += 4) {
+      int c4[4], m4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) c4[u] = (k + u < k1) ? colidx[k + u] : -1;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) m4[u] = (c4[u] >= 0) ? comp[c4[u]] : -1;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (m4[u] >= 0) {
+          const int g = m4[u] & 7, at = beg[t][g] + cnt[t][g]++;
+          ent[t][at] = (int16_t)(k + u - rstart[t]);
+          ecol[t][at] = (int16_t)m4[u];
+        }
     }
   }
   for (int j = 0; j < width; ++j) {
@@ -576,10 +596,10 @@ k_sell_fill(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ coli
       const int g = best >= 0 ? best : any;
       used |= 1u << g;
       served |= 1u << t;
-      const int k = rstart[t] + ent[t][beg[t][g] + --cnt[t][g]];
+      const int at = beg[t][g] + --cnt[t][g];
       left[t]--;
-      scol[base + j * 32 + 8 * q + t] = comp[colidx[k]];
-      ssrc[base + j * 32 + 8 * q + t] = k;
+      scol[base + j * 32 + 8 * q + t] = ecol[t][at];
+      ssrc[base + j * 32 + 8 * q + t] = rstart[t] + ent[t][at];
     }
     for (int t = 0; t < 8; ++t)
       if (!(served >> t & 1u)) {
