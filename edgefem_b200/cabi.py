@@ -115,6 +115,10 @@ SIGNATURES = {
     "efb_x_recover": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, i32p, i32p, f64p]),
     "efb_solve": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(SolveOpts), C.POINTER(SolveResult)]),
     "efb_system_last_solve_kernel_ms": (C.c_int, [C.c_void_p, f64p]),
+    "efb_system_last_solve_shape": (C.c_int, [C.c_void_p, i32p, i32p, i32p]),
+    "efb_debug_cluster_plan_build": (C.c_int, [C.c_int32, i32p, i32p, u8p, C.c_int32, i32p, C.c_int32, C.POINTER(C.c_void_p)]),
+    "efb_debug_cluster_plan_free": (None, [C.c_void_p]),
+    "efb_debug_cluster_plan_get": (C.c_int64, [C.c_void_p, C.c_char_p, i64p, C.c_int64]),
     "efb_spmv_host": (C.c_int, [C.c_void_p, C.c_int32, f64p, f64p]),
     "efb_bench_kernel": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, f64p]),
     "efb_huygens_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, f64p, C.c_int32, i32p, i32p, i32p, C.c_double, f64p, f64p, f64p, f64p, f64p, f64p]),
@@ -204,6 +208,29 @@ def dist_row_range(m: int, rank: int, world: int):
     if rc:
         raise EfbError("efb_dist_row_range: bad arguments")
     return a.value, b.value
+
+
+def cluster_plan_arrays(rowptr, colidx, dir_flags=None, n_node=0, edge_nodes=None, cluster_ctas=8) -> dict:
+    """Host-only diagnostics: the cluster split of a CSR pattern as a dict of int64 arrays (efb_debug_cluster_plan_*)."""
+    lib = load()
+    rp, ci = _i32(rowptr), _i32(colidx)
+    d = None if dir_flags is None else np.ascontiguousarray(np.asarray(dir_flags, dtype=np.uint8))
+    en = None if edge_nodes is None else _i32(edge_nodes)
+    h = C.c_void_p()
+    rc = lib.efb_debug_cluster_plan_build(rp.size - 1, _p(rp, i32p), _p(ci, i32p), _p(d, u8p), int(n_node), _p(en, i32p), int(cluster_ctas), C.byref(h))
+    if rc != EFB_OK:
+        raise EfbError("efb_debug_cluster_plan_build failed (%d): %s" % (rc, (lib.efb_last_error(None) or b"").decode()))
+    out = {}
+    try:
+        for name in ("dims", "c_orig", "cta_info", "row_edge", "row_ws", "row_n0", "row_n1", "blk_off", "slot_src", "slot_col", "halo_ws",
+                     "halo_src", "node_id", "n2e_ptr", "n2e_item", "nsrc_ptr", "nsrc_item"):
+            n = lib.efb_debug_cluster_plan_get(h, name.encode(), None, 0)
+            buf = np.zeros(max(int(n), 1), dtype=np.int64)
+            lib.efb_debug_cluster_plan_get(h, name.encode(), _p(buf, i64p), buf.size)
+            out[name] = buf[:int(n)]
+    finally:
+        lib.efb_debug_cluster_plan_free(h)
+    return out
 
 
 class Ctx:
@@ -471,6 +498,12 @@ class DeviceSystem:
         ms = C.c_double()
         self.ctx.check(self.ctx.lib.efb_system_last_solve_kernel_ms(self.h, C.byref(ms)), "efb_system_last_solve_kernel_ms")
         return ms.value
+
+    def last_solve_shape(self):
+        """(CTAs per cluster, rhs per job, resident clusters) of the last solve; (0, 0, 0) if it did not use the cluster kernel."""
+        a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+        self.ctx.check(self.ctx.lib.efb_system_last_solve_shape(self.h, C.byref(a), C.byref(b), C.byref(c)), "efb_system_last_solve_shape")
+        return a.value, b.value, c.value
 
     def spmv(self, matrix, x) -> np.ndarray:
         xv = _c128(x)

@@ -707,6 +707,7 @@ static int system_set_gradient(System *S, int n_node, const int32_t *edge_nodes)
   S->n_node = n_node;
   S->h_edge_nodes.assign(edge_nodes, edge_nodes + 2 * (size_t)S->m);
   S->small_dirty = true;
+  S->cl_dirty = true;
   cudaStreamSynchronize(c->stream);  // blocks go back to a pool shared by every context on the device
   dfree(S->d_edge_nodes); dfree(S->d_n2e_ptr); dfree(S->d_n2e_item); dfree(S->d_node_dir);
   S->d_edge_nodes = nullptr; S->d_n2e_ptr = nullptr; S->d_n2e_item = nullptr; S->d_node_dir = nullptr;
@@ -978,6 +979,7 @@ void efb_system_destroy(efb_system *sys_) {
   cudaStreamSynchronize(S->ctx->stream);
   dist_free(S);
   solver_free(S);
+  cluster_plan_free(S);
   dfree(S->d_rowptr); dfree(S->d_colidx); dfree(S->d_diag_pos); dfree(S->d_vals);
   dfree(S->d_b); dfree(S->d_x); dfree(S->d_dir_all); dfree(S->d_e2t_pos); dfree(S->d_chunk_row); dfree(S->d_sp_chunk);
   dfree(S->d_sch_item); dfree(S->d_sch_ss); dfree(S->d_sch_row); dfree(S->d_sch_pos); dfree(S->d_sch_sec); dfree(S->d_sch_flag);
@@ -1037,6 +1039,7 @@ int efb_system_set_dirichlet(efb_system *sys_, const uint8_t *flags) {
   S->has_dir = true;
   S->h_dir.assign(flags + S->row0, flags + S->row0 + S->m);
   S->small_dirty = true;
+  S->cl_dirty = true;
   S->sched_dirty = true;
   if (S->d_e2t_pos && S->mesh) {
     k_pos_dirichlet<<<(S->m + 127) / 128, 128, 0, c->stream>>>(S->mesh->d_e2t_ptr + S->row0, S->d_rowptr, S->d_colidx, S->d_dir_all, S->m,

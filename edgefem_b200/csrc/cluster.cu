@@ -1,0 +1,779 @@
+// Cluster-split persistent COCG: one thread-block CLUSTER (C <= 8 CTAs = C SMs) per matrix, the whole Krylov solve
+// of that matrix in one kernel, everything on chip.
+//
+// Why (round-1 profile of k_cocg_small, one CTA per matrix): the matrix (1.2 MB for WR-90) was streamed from L2/HBM
+// every iteration -- 85 us per matrix-iteration, 3x above even its HBM floor, bound by the load path.  Here CTA c of
+// the cluster owns a contiguous band of rows of the RCM-ordered free unknowns and keeps their values in SHARED
+// MEMORY for the whole solve (loaded once per job); r, x, p of the own rows live in registers (thread per row); the
+// SpMV input is a window of p in shared memory whose halo is pulled from the neighbours' shared memory through
+// DSMEM; the auxiliary-space preconditioner keeps G^T r per CTA by recurrence (G^T r -= alpha G^T q) so that its
+// nodal exchange rides on the same barrier as the p^T q reduction.  Two cluster barriers per iteration:
+//   A  q = A p (own rows), partial p^T q, nodal partial of q          -> push partials          -> barrier 1
+//   B  alpha; x += alpha p; r -= alpha q; g -= alpha G^T q (pull nodal partials); z = D^-1 r + G L^-1 g;
+//      partial r^T z, |r|^2; z parked in shared memory                -> push partials          -> barrier 2
+//   D  beta; p = z + beta p for own rows and (pulling z from the owners) for the halo of the window.
+// Every CTA sums the partials of all CTAs in rank order, so all CTAs see bit-identical scalars and take identical
+// branches.  One solve of WR-90 (4 308 free unknowns, ~300 iterations) drops from 22 ms on one SM to ~1.5 ms on 8.
+// Host side of the split (RCM, partition, windows, halo and nodal lists): cluster_plan.hpp.
+// Replaces Eigen's BiCGSTAB/ILUT behind solve_linear (src/solver.cpp:35-193) for complex symmetric systems.
+#include <cooperative_groups.h>
+
+#include <algorithm>
+
+#include "cluster_plan.hpp"
+#include "solve_internal.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace efb {
+
+constexpr int CL_THREADS_MAX = 640;
+
+struct ClusterDev {
+  int C, mc, aux;
+  int max_own, max_w, max_my, max_slots;
+  const int32_t *cta_info, *row_edge;
+  const uint16_t *row_ws, *row_n0, *row_n1;
+  const int32_t *blk_off, *slot_src;
+  const uint16_t *slot_col, *halo_ws;
+  const uint32_t *halo_src;
+  const int32_t *node_id, *n2e_ptr;
+  const uint32_t *n2e_item;
+  const int32_t *nsrc_ptr;
+  const uint32_t *nsrc_item;
+};
+
+struct ClusterPlanDev {  // owned by a System (cl_plan)
+  ClusterPlanHost h;
+  ClusterDev d{};
+  std::vector<void *> blocks;
+};
+
+static size_t cluster_smem_bytes(int nr, const ClusterPlanHost &P) {
+  size_t b = 0;
+  b += (size_t)P.max_slots * 16;            // mat_v
+  b += (size_t)P.max_w * nr * 16;           // p_w
+  b += (size_t)P.max_own * nr * 16 * 2;     // q_own, z_own
+  b += (size_t)P.max_my * nr * 16 * 3;      // wp, g, w
+  b += (size_t)P.max_my * 16;               // linv
+  b += 2 * CL_MAX_C * 8 * 8;                // partial banks
+  b += 33 * 8 * 8;                          // block reduction scratch
+  b += 16;                                  // job slot
+  b += ((size_t)P.max_slots * 2 + 15) / 16 * 16;  // mat_c
+  return b + 16;
+}
+
+__device__ __forceinline__ c128 ldg_stream16(const c128 *p) {
+  c128 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+
+// block-wide sums of N doubles; thread (c*N + k) then stores sum k into bank[crank*8 + k] of CTA c of the cluster
+template <int N>
+__device__ __forceinline__ void reduce_push(cg::cluster_group &cluster, double (&v)[N], double *red, double *bank, int C, int crank) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    double a = v[k];
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) red[wid * N + k] = a;
+  }
+  __syncthreads();
+  if (wid == 0) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      double a = (lane < nw) ? red[lane * N + k] : 0.0;
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (lane == 0) red[32 * N + k] = a;
+    }
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < N * C) {
+    const int k = threadIdx.x % N, c = threadIdx.x / N;
+    double *dst = cluster.map_shared_rank(bank, c);
+    dst[crank * 8 + k] = red[32 * N + k];
+  }
+}
+
+template <int N>
+__device__ __forceinline__ void bank_totals(const double *bank, int C, double (&tot)[N]) {
+#pragma unroll
+  for (int k = 0; k < N; ++k) tot[k] = 0.0;
+  for (int c = 0; c < C; ++c)
+#pragma unroll
+    for (int k = 0; k < N; ++k) tot[k] += bank[c * 8 + k];
+}
+
+template <int NR, int RPT>
+__global__ void __launch_bounds__(CL_THREADS_MAX, 1)
+k_cocg_cluster(const SolveDev D, const ClusterDev K, int first_matrix, int n_jobs, int groups, int *job_counter, const c128 *__restrict__ bvec,
+               c128 *xvec, int zero_x, int max_restarts) {
+  static_assert(3 * NR <= 8, "partial banks hold 8 doubles per CTA");
+  cg::cluster_group cluster = cg::this_cluster();
+  const int C = K.C;
+  const int crank = (int)cluster.block_rank();
+  const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31;
+  extern __shared__ __align__(16) unsigned char sm[];
+  c128 *mat_v = (c128 *)sm;
+  c128 *p_w = mat_v + K.max_slots;
+  c128 *q_own = p_w + (size_t)K.max_w * NR;
+  c128 *z_own = q_own + (size_t)K.max_own * NR;
+  c128 *wp = z_own + (size_t)K.max_own * NR;
+  c128 *g_s = wp + (size_t)K.max_my * NR;
+  c128 *w_s = g_s + (size_t)K.max_my * NR;
+  c128 *linv_s = w_s + (size_t)K.max_my * NR;
+  double *part = (double *)(linv_s + K.max_my);  // [2][CL_MAX_C][8]
+  double *red = part + 2 * CL_MAX_C * 8;         // [33*8]
+  int *s_job = (int *)(red + 33 * 8);
+  uint16_t *mat_c = (uint16_t *)(s_job + 4);
+  double *bank0 = part, *bank1 = part + CL_MAX_C * 8;
+
+  const int32_t *I = K.cta_info + crank * CL_INFO_STRIDE;
+  const int n_own = I[CI_N_OWN], n_my = I[CI_N_MY], n_halo = I[CI_N_HALO], n_blk = I[CI_N_BLK], n_slots = I[CI_N_SLOTS];
+  const int off_row = I[CI_OFF_ROW], off_slot = I[CI_OFF_SLOT], off_blk = I[CI_OFF_BLK], off_halo = I[CI_OFF_HALO];
+  const int off_node = I[CI_OFF_NODE], off_n2e = I[CI_OFF_N2E], off_nsrc = I[CI_OFF_NSRC];
+  const int32_t *n2e_ptr = K.n2e_ptr + off_node + crank, *nsrc_ptr = K.nsrc_ptr + off_node + crank;
+  const int m = D.m;
+
+  // per-thread rows: local row t = u * nth + tid (a warp = one 32-row ELL block)
+  bool valid[RPT];
+  int edge[RPT], ws[RPT], n0[RPT], n1[RPT], base[RPT], width[RPT];
+#pragma unroll
+  for (int u = 0; u < RPT; ++u) {
+    const int t = u * nth + tid;
+    valid[u] = t < n_own;
+    edge[u] = valid[u] ? K.row_edge[off_row + t] : 0;
+    ws[u] = valid[u] ? K.row_ws[off_row + t] : 0;
+    n0[u] = valid[u] ? K.row_n0[off_row + t] : 0;
+    n1[u] = valid[u] ? K.row_n1[off_row + t] : 0;
+    const int b = t >> 5;
+    base[u] = 0;
+    width[u] = 0;
+    if (b < n_blk) {
+      base[u] = K.blk_off[off_blk + b];
+      width[u] = (K.blk_off[off_blk + b + 1] - base[u]) >> 5;
+    }
+  }
+  for (int i = tid; i < n_slots; i += nth) mat_c[i] = K.slot_col[off_slot + i];
+  __syncthreads();
+
+  // q = A p over the own rows (p from the window in shared memory)
+  auto spmv = [&](c128 (&out)[RPT][NR]) {
+#pragma unroll
+    for (int u = 0; u < RPT; ++u) {
+      c128 acc[NR];
+#pragma unroll
+      for (int r = 0; r < NR; ++r) acc[r] = cmake(0.0, 0.0);
+      const c128 *mv = mat_v + base[u] + lane;
+      const uint16_t *mc_ = mat_c + base[u] + lane;
+      int k = 0;
+      for (; k + 4 <= width[u]; k += 4) {
+        c128 a4[4];
+        int c4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          a4[j] = mv[(k + j) * 32];
+          c4[j] = mc_[(k + j) * 32];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int r = 0; r < NR; ++r) acc[r] = cfma(a4[j], p_w[c4[j] * NR + r], acc[r]);
+      }
+      for (; k < width[u]; ++k) {
+        const c128 a = mv[k * 32];
+        const int c = mc_[k * 32];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) acc[r] = cfma(a, p_w[c * NR + r], acc[r]);
+      }
+#pragma unroll
+      for (int r = 0; r < NR; ++r) out[u][r] = acc[r];
+    }
+  };
+  // window halo: p_w[h] = z(owner) (+ beta p_w[h])
+  auto pull_halo = [&](const c128 (&beta)[NR], bool use_beta) {
+    for (int h = tid; h < n_halo; h += nth) {
+      const int hw = K.halo_ws[off_halo + h];
+      const uint32_t src = K.halo_src[off_halo + h];
+      const c128 *rz = cluster.map_shared_rank(z_own, src >> 16) + (size_t)(src & 0xffffu) * NR;
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        const c128 z = rz[r];
+        p_w[hw * NR + r] = use_beta ? cfma(beta[r], p_w[hw * NR + r], z) : z;
+      }
+    }
+  };
+  // wp[n] = sum over the own edges at my node n of +-q_own
+  auto nodal_partial = [&]() {
+    if (!K.aux) return;
+    for (int j = tid; j < n_my; j += nth) {
+      const int kb = n2e_ptr[j], ke = n2e_ptr[j + 1];
+      c128 a[NR];
+#pragma unroll
+      for (int r = 0; r < NR; ++r) a[r] = cmake(0.0, 0.0);
+      for (int k = kb; k < ke; ++k) {
+        const uint32_t it = K.n2e_item[off_n2e + k];
+        const c128 *v = q_own + (size_t)(it >> 1) * NR;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) a[r] = (it & 1u) ? cadd(a[r], v[r]) : csub(a[r], v[r]);
+      }
+#pragma unroll
+      for (int r = 0; r < NR; ++r) wp[j * NR + r] = a[r];
+    }
+  };
+  // g[n] (-)= alpha * sum over every CTA touching n of its partial; w[n] = linv[n] g[n]
+  auto nodal_combine = [&](bool set, const c128 (&alpha)[NR]) {
+    if (!K.aux) return;
+    for (int j = tid; j < n_my; j += nth) {
+      const int kb = nsrc_ptr[j], ke = nsrc_ptr[j + 1];
+      c128 a[NR];
+#pragma unroll
+      for (int r = 0; r < NR; ++r) a[r] = cmake(0.0, 0.0);
+      for (int k = kb; k < ke; ++k) {
+        const uint32_t it = K.nsrc_item[off_nsrc + k];
+        const c128 *v = cluster.map_shared_rank(wp, it >> 16) + (size_t)(it & 0xffffu) * NR;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) a[r] = cadd(a[r], v[r]);
+      }
+      const c128 li = linv_s[j];
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        const c128 gn = set ? a[r] : cfma(cneg(alpha[r]), a[r], g_s[j * NR + r]);
+        g_s[j * NR + r] = gn;
+        w_s[j * NR + r] = cmul(li, gn);
+      }
+    }
+  };
+
+  for (;;) {  // jobs
+    if (crank == 0 && tid == 0) {
+      const int q = atomicAdd(job_counter, 1);
+      const int jb = q < n_jobs ? job_counter[1 + q] : -1;
+      for (int c = 0; c < C; ++c) *cluster.map_shared_rank(s_job, c) = jb;
+    }
+    cluster.sync();
+    const int job = *s_job;
+    if (job < 0) break;
+    const int f = first_matrix + job / groups;
+    const int s0 = f * D.n_rhs + (job % groups) * NR;
+    const c128 *__restrict__ av = D.vals + (size_t)f * D.nnz;
+    const c128 *__restrict__ dinv = D.dinv + (size_t)f * m;
+    for (int i = tid; i < n_slots; i += nth) {
+      const int src = K.slot_src[off_slot + i];
+      mat_v[i] = src >= 0 ? ldg_stream16(&av[src]) : cmake(0.0, 0.0);
+    }
+    if (K.aux)
+      for (int j = tid; j < n_my; j += nth) linv_s[j] = D.linv[(size_t)f * D.n_node + K.node_id[off_node + j]];
+    const size_t off0 = (size_t)s0 * m;
+    const c128 *bg = bvec + off0;
+    c128 *xg = xvec + off0;
+    // Dirichlet rows are decoupled identity rows: x_e = b_e / A_ee
+    if (K.mc < m)
+      for (int e = crank * nth + tid; e < m; e += C * nth)
+        if (D.dir[e]) {
+          const c128 de = dinv[e];
+#pragma unroll
+          for (int r = 0; r < NR; ++r) xg[(size_t)r * m + e] = cmul(de, bg[(size_t)r * m + e]);
+        }
+    c128 di[RPT], xr[RPT][NR], rv[RPT][NR], pr[RPT][NR];
+#pragma unroll
+    for (int u = 0; u < RPT; ++u) {
+      di[u] = valid[u] ? dinv[edge[u]] : cmake(0.0, 0.0);
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        xr[u][r] = (valid[u] && !zero_x) ? xg[(size_t)r * m + edge[u]] : cmake(0.0, 0.0);
+        rv[u][r] = cmake(0.0, 0.0);
+        pr[u][r] = cmake(0.0, 0.0);
+      }
+    }
+    int iters[NR];
+    bool act[NR], conv[NR];
+    double bb[NR], rrn[NR];
+    c128 rho[NR], zero_nr[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      iters[r] = 0; act[r] = false; conv[r] = false; bb[r] = 0.0; rrn[r] = 0.0;
+      rho[r] = cmake(0.0, 0.0);
+      zero_nr[r] = cmake(0.0, 0.0);
+    }
+    __syncthreads();
+
+    for (int cycle = 0;; ++cycle) {
+      // (1) true residual r = b - A x of the current iterate
+      c128 qv[RPT][NR];
+      if (cycle == 0 && zero_x) {
+#pragma unroll
+        for (int u = 0; u < RPT; ++u)
+#pragma unroll
+          for (int r = 0; r < NR; ++r) qv[u][r] = cmake(0.0, 0.0);
+      } else {
+#pragma unroll
+        for (int u = 0; u < RPT; ++u)
+          if (valid[u])
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+              p_w[ws[u] * NR + r] = xr[u][r];
+              z_own[(size_t)(u * nth + tid) * NR + r] = xr[u][r];
+            }
+        cluster.sync();
+        pull_halo(zero_nr, false);
+        __syncthreads();
+        spmv(qv);
+      }
+      {
+        double d[2 * NR];
+#pragma unroll
+        for (int k = 0; k < 2 * NR; ++k) d[k] = 0.0;
+#pragma unroll
+        for (int u = 0; u < RPT; ++u)
+          if (valid[u])
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+              const c128 bi = bg[(size_t)r * m + edge[u]];
+              const c128 ri = csub(bi, qv[u][r]);
+              rv[u][r] = ri;
+              q_own[(size_t)(u * nth + tid) * NR + r] = ri;
+              d[2 * r] += cabs2(ri);
+              d[2 * r + 1] += cabs2(bi);
+            }
+        __syncthreads();
+        nodal_partial();
+        reduce_push<2 * NR>(cluster, d, red, bank0, C, crank);
+        cluster.sync();
+        double tot[2 * NR];
+        bank_totals<2 * NR>(bank0, C, tot);
+        nodal_combine(true, zero_nr);
+        bool any = false;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          rrn[r] = tot[2 * r];
+          bb[r] = tot[2 * r + 1];
+          conv[r] = rrn[r] <= D.tol2 * bb[r];
+          act[r] = !conv[r] && iters[r] < D.max_it && cycle <= max_restarts && isfinite(rrn[r]);
+          any |= act[r];
+        }
+        if (!any) break;
+      }
+      __syncthreads();
+      // (2) z = M^-1 r, rho = r^T z, p = z
+      c128 zv[RPT][NR];
+      {
+        double d[3 * NR];
+#pragma unroll
+        for (int k = 0; k < 3 * NR; ++k) d[k] = 0.0;
+#pragma unroll
+        for (int u = 0; u < RPT; ++u)
+          if (valid[u])
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+              c128 z = cmul(di[u], rv[u][r]);
+              if (K.aux) z = cadd(z, csub(w_s[n1[u] * NR + r], w_s[n0[u] * NR + r]));
+              zv[u][r] = z;
+              z_own[(size_t)(u * nth + tid) * NR + r] = z;
+              const c128 t = cmul(rv[u][r], z);
+              d[3 * r] += t.x; d[3 * r + 1] += t.y;
+              d[3 * r + 2] += cabs2(rv[u][r]);
+            }
+        reduce_push<3 * NR>(cluster, d, red, bank1, C, crank);
+        cluster.sync();
+        double tot[3 * NR];
+        bank_totals<3 * NR>(bank1, C, tot);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) rho[r] = cmake(tot[3 * r], tot[3 * r + 1]);
+      }
+#pragma unroll
+      for (int u = 0; u < RPT; ++u)
+        if (valid[u])
+#pragma unroll
+          for (int r = 0; r < NR; ++r) {
+            pr[u][r] = zv[u][r];
+            p_w[ws[u] * NR + r] = zv[u][r];
+          }
+      pull_halo(zero_nr, false);
+      __syncthreads();
+      // (3) iterations until the recursive residual converges
+      for (;;) {
+        // A
+        spmv(qv);
+        {
+          double d[2 * NR];
+#pragma unroll
+          for (int k = 0; k < 2 * NR; ++k) d[k] = 0.0;
+#pragma unroll
+          for (int u = 0; u < RPT; ++u)
+            if (valid[u])
+#pragma unroll
+              for (int r = 0; r < NR; ++r) {
+                q_own[(size_t)(u * nth + tid) * NR + r] = qv[u][r];
+                const c128 t = cmul(pr[u][r], qv[u][r]);
+                d[2 * r] += t.x; d[2 * r + 1] += t.y;
+              }
+          __syncthreads();
+          nodal_partial();
+          reduce_push<2 * NR>(cluster, d, red, bank0, C, crank);
+        }
+        cluster.sync();  // barrier 1
+        // B
+        c128 alpha[NR];
+        {
+          double tot[2 * NR];
+          bank_totals<2 * NR>(bank0, C, tot);
+#pragma unroll
+          for (int r = 0; r < NR; ++r) {
+            const c128 pq = cmake(tot[2 * r], tot[2 * r + 1]);
+            const bool brk = (pq.x == 0.0 && pq.y == 0.0) || !(isfinite(pq.x) && isfinite(pq.y));
+            if (brk) act[r] = false;
+            alpha[r] = act[r] ? cdiv(rho[r], pq) : cmake(0.0, 0.0);
+            if (act[r]) iters[r] += 1;
+          }
+        }
+        nodal_combine(false, alpha);
+#pragma unroll
+        for (int u = 0; u < RPT; ++u)
+#pragma unroll
+          for (int r = 0; r < NR; ++r) {
+            xr[u][r] = cfma(alpha[r], pr[u][r], xr[u][r]);
+            rv[u][r] = cfma(cneg(alpha[r]), qv[u][r], rv[u][r]);
+          }
+        __syncthreads();
+        {
+          double d[3 * NR];
+#pragma unroll
+          for (int k = 0; k < 3 * NR; ++k) d[k] = 0.0;
+#pragma unroll
+          for (int u = 0; u < RPT; ++u)
+            if (valid[u])
+#pragma unroll
+              for (int r = 0; r < NR; ++r) {
+                c128 z = cmul(di[u], rv[u][r]);
+                if (K.aux) z = cadd(z, csub(w_s[n1[u] * NR + r], w_s[n0[u] * NR + r]));
+                zv[u][r] = z;
+                z_own[(size_t)(u * nth + tid) * NR + r] = z;
+                const c128 t = cmul(rv[u][r], z);
+                d[3 * r] += t.x; d[3 * r + 1] += t.y;
+                d[3 * r + 2] += cabs2(rv[u][r]);
+              }
+          reduce_push<3 * NR>(cluster, d, red, bank1, C, crank);
+        }
+        cluster.sync();  // barrier 2
+        // D
+        c128 beta[NR];
+        bool still = false;
+        {
+          double tot[3 * NR];
+          bank_totals<3 * NR>(bank1, C, tot);
+#pragma unroll
+          for (int r = 0; r < NR; ++r) {
+            const c128 rho_new = cmake(tot[3 * r], tot[3 * r + 1]);
+            if (act[r]) {
+              rrn[r] = tot[3 * r + 2];
+              if (rrn[r] <= D.tol2 * bb[r] || iters[r] >= D.max_it || !isfinite(rrn[r])) act[r] = false;
+            }
+            beta[r] = (act[r] && (rho[r].x != 0.0 || rho[r].y != 0.0)) ? cdiv(rho_new, rho[r]) : cmake(0.0, 0.0);
+            rho[r] = rho_new;
+            still |= act[r];
+          }
+        }
+        if (!still) break;
+#pragma unroll
+        for (int u = 0; u < RPT; ++u)
+          if (valid[u])
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+              pr[u][r] = cfma(beta[r], pr[u][r], zv[u][r]);
+              p_w[ws[u] * NR + r] = pr[u][r];
+            }
+        pull_halo(beta, true);
+        __syncthreads();
+      }
+      __syncthreads();
+    }
+    // results
+#pragma unroll
+    for (int u = 0; u < RPT; ++u)
+      if (valid[u])
+#pragma unroll
+        for (int r = 0; r < NR; ++r) xg[(size_t)r * m + edge[u]] = xr[u][r];
+    if (crank == 0 && tid == 0) {
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        int32_t *st = D.state + (s0 + r) * 4;
+        st[ST_ACTIVE] = 0; st[ST_ITERS] = iters[r]; st[ST_CONV] = conv[r] ? 1 : 0; st[ST_REC] = 0;
+        c128 *sc = D.scal + (size_t)(s0 + r) * NSCAL;
+        sc[S_RR] = cmake(rrn[r], 0.0);
+        sc[S_BB] = cmake(bb[r], 0.0);
+      }
+    }
+    // the next job's first barrier orders the reuse of the shared-memory buffers across the cluster
+  }
+}
+
+// ---------------------------------------------------------------- host side
+void cluster_plan_free(System *S) {
+  ClusterPlanDev *P = (ClusterPlanDev *)S->cl_plan;
+  if (!P) return;
+  for (void *b : P->blocks) dfree(b);
+  delete P;
+  S->cl_plan = nullptr;
+}
+
+template <typename T>
+static int up(Ctx *c, ClusterPlanDev *P, const T **dst, const std::vector<T> &v) {
+  T *d = nullptr;
+  int rc = dev_upload(c, &d, v.data(), std::max<size_t>(v.size(), 1));
+  if (rc) return rc;
+  P->blocks.push_back(d);
+  *dst = d;
+  return EFB_OK;
+}
+
+static int cluster_plan_upload(System *S, ClusterPlanDev *P) {
+  Ctx *c = S->ctx;
+  ClusterPlanHost &H = P->h;
+  // uploads read the host vectors asynchronously: give every vector at least one element and sync at the end
+  auto pad = [](auto &v) { if (v.empty()) v.resize(1); };
+  pad(H.row_edge); pad(H.row_ws); pad(H.row_n0); pad(H.row_n1); pad(H.blk_off); pad(H.slot_src); pad(H.slot_col);
+  pad(H.halo_ws); pad(H.halo_src); pad(H.node_id); pad(H.n2e_ptr); pad(H.n2e_item); pad(H.nsrc_ptr); pad(H.nsrc_item);
+  ClusterDev &d = P->d;
+  d.C = H.C; d.mc = H.mc; d.aux = H.aux ? 1 : 0;
+  d.max_own = H.max_own; d.max_w = H.max_w; d.max_my = std::max(H.max_my, 1); d.max_slots = H.max_slots;
+  int rc;
+  if ((rc = up(c, P, &d.cta_info, H.cta_info))) return rc;
+  if ((rc = up(c, P, &d.row_edge, H.row_edge))) return rc;
+  if ((rc = up(c, P, &d.row_ws, H.row_ws))) return rc;
+  if ((rc = up(c, P, &d.row_n0, H.row_n0))) return rc;
+  if ((rc = up(c, P, &d.row_n1, H.row_n1))) return rc;
+  if ((rc = up(c, P, &d.blk_off, H.blk_off))) return rc;
+  if ((rc = up(c, P, &d.slot_src, H.slot_src))) return rc;
+  if ((rc = up(c, P, &d.slot_col, H.slot_col))) return rc;
+  if ((rc = up(c, P, &d.halo_ws, H.halo_ws))) return rc;
+  if ((rc = up(c, P, &d.halo_src, H.halo_src))) return rc;
+  if ((rc = up(c, P, &d.node_id, H.node_id))) return rc;
+  if ((rc = up(c, P, &d.n2e_ptr, H.n2e_ptr))) return rc;
+  if ((rc = up(c, P, &d.n2e_item, H.n2e_item))) return rc;
+  if ((rc = up(c, P, &d.nsrc_ptr, H.nsrc_ptr))) return rc;
+  if ((rc = up(c, P, &d.nsrc_item, H.nsrc_item))) return rc;
+  EFB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return EFB_OK;
+}
+
+template <int NR, int RPT>
+static int launch_cluster(Ctx *c, const SolveDev &D, const ClusterDev &K, int nth, size_t smem, int first_matrix, int n_jobs, int groups,
+                          int *job_counter, const c128 *b, c128 *x, int zero_x, int mr, int *clusters_out) {
+  auto kern = k_cocg_cluster<NR, RPT>;
+  EFB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3((unsigned)nth, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = c->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)K.C;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cfg.gridDim = dim3((unsigned)K.C, 1, 1);
+  int max_clusters = 0;
+  cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg);
+  if (e != cudaSuccess || max_clusters < 1) {
+    cudaGetLastError();
+    return fail(c, EFB_ERR_LIMIT, "cluster solver: no cluster of %d CTAs x %zu B of shared memory can be resident (%s)", K.C, smem,
+                e != cudaSuccess ? cudaGetErrorString(e) : "0 clusters");
+  }
+  const int n_clusters = std::max(1, std::min(n_jobs, max_clusters));
+  cfg.gridDim = dim3((unsigned)(n_clusters * K.C), 1, 1);
+  *clusters_out = n_clusters;
+  EFB_CUDA(c, cudaLaunchKernelEx(&cfg, kern, D, K, first_matrix, n_jobs, groups, job_counter, b, x, zero_x, mr));
+  EFB_CHECK_LAUNCH(c);
+  return EFB_OK;
+}
+
+// Used whenever the system is symmetric (COCG), whole (not row-partitioned) and a split into <= 8 CTAs fits in shared
+// memory.  EDGEFEM_B200_CLUSTER=0 disables it, =C forces the cluster size.
+int run_krylov_cluster(SolvePlan &P, const efb_solve_opts *o, bool zero_x, bool *ran) {
+  System *S = P.S;
+  Ctx *c = S->ctx;
+  *ran = false;
+  int forced = -1;
+  if (const char *e = getenv("EDGEFEM_B200_CLUSTER")) forced = atoi(e);
+  if (forced == 0) return EFB_OK;
+  if (S->m != S->m_global || S->m > 65535 * CL_MAX_C) return EFB_OK;
+  if ((int)S->h_rowptr.size() != S->m + 1) return EFB_OK;
+  const bool want_aux = P.aux && (int)S->h_edge_nodes.size() == 2 * S->m;
+  if (P.aux && !want_aux) return EFB_OK;
+  int dev_smem = 0;
+  EFB_CUDA(c, cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+  SubTrace st;
+  const int n_rhs = S->n_rhs;
+  int nr_want = (n_rhs % 2 == 0) ? 2 : 1;
+  if (const char *e = getenv("EDGEFEM_B200_CLUSTER_NR")) nr_want = std::max(1, std::min(nr_want, atoi(e)));
+  ClusterPlanDev *PL = (ClusterPlanDev *)S->cl_plan;
+  const uint8_t *dirp = (int)S->h_dir.size() == S->m ? S->h_dir.data() : nullptr;
+  auto fits = [&](const ClusterPlanHost &H, int nr, int *rpt_out, int *nth_out) {
+    if (cluster_smem_bytes(nr, H) > (size_t)dev_smem) return false;
+    for (int rpt : {1, 2, 4}) {
+      const int nth = std::max(64, ((H.max_own + rpt - 1) / rpt + 31) / 32 * 32);
+      if (nth <= CL_THREADS_MAX) {
+        *rpt_out = rpt;
+        *nth_out = nth;
+        return true;
+      }
+    }
+    return false;
+  };
+  int nr = 0, rpt = 1, nth = 0;
+  const int n_matrix = P.n_matrix;
+  if (S->cl_dirty || !PL || PL->h.aux != want_aux || (forced > 0 && PL->h.C != forced)) {
+    cluster_plan_free(S);
+    PL = nullptr;
+    // smallest cluster that fits with both right-hand sides, else with one; few jobs: grow the cluster for latency
+    ClusterPlanHost best;
+    bool have = false;
+    for (int pass = 0; pass < 2 && !have; ++pass) {
+      const int nrp = pass == 0 ? nr_want : 1;
+      if (pass == 1 && nr_want == 1) break;
+      for (int C = (forced > 0 ? forced : 1); C <= (forced > 0 ? forced : CL_MAX_C); C *= 2) {
+        ClusterPlanHost H;
+        if (!build_cluster_plan(S->m, S->h_rowptr.data(), S->h_colidx.data(), dirp, want_aux ? S->n_node : 0,
+                                want_aux ? S->h_edge_nodes.data() : nullptr, C, H))
+          continue;
+        int r1, t1;
+        if (!fits(H, nrp, &r1, &t1)) continue;
+        best = std::move(H);
+        have = true;
+        // latency: with few jobs a larger cluster costs nothing (idle SMs otherwise)
+        if (forced <= 0)
+          while (best.C * 2 <= CL_MAX_C && (long long)n_matrix * (n_rhs / nrp) * best.C * 2 <= c->sm_count) {
+            ClusterPlanHost H2;
+            int r2, t2;
+            if (!build_cluster_plan(S->m, S->h_rowptr.data(), S->h_colidx.data(), dirp, want_aux ? S->n_node : 0,
+                                    want_aux ? S->h_edge_nodes.data() : nullptr, best.C * 2, H2) || !fits(H2, nrp, &r2, &t2))
+              break;
+            best = std::move(H2);
+          }
+        break;
+      }
+    }
+    if (!have) return EFB_OK;  // does not fit: the other solver paths take it
+    PL = new ClusterPlanDev();
+    PL->h = std::move(best);
+    S->cl_plan = PL;
+    int rc = cluster_plan_upload(S, PL);
+    if (rc) return rc;
+    S->cl_dirty = false;
+    st.mark("  cluster plan (RCM, partition, windows, lists)");
+  }
+  nr = nr_want;
+  if (!fits(PL->h, nr, &rpt, &nth)) {
+    nr = 1;
+    if (!fits(PL->h, nr, &rpt, &nth)) return EFB_OK;
+  }
+  const size_t smem = cluster_smem_bytes(nr, PL->h);
+  const int groups = n_rhs / nr;
+  const int n_jobs = P.n_matrix * groups;
+  {
+    // queue order = longest expected job first (iteration counts of the previous solve, else frequency)
+    std::vector<double> w((size_t)n_jobs, 0.0);
+    const bool have_it = (int)S->last_iters.size() == S->n_sys;
+    const bool have_om = (int)S->last_omega.size() == S->n_matrix;
+    for (int j = 0; j < n_jobs; ++j) {
+      const int f = P.first_matrix + j / groups, s0 = f * n_rhs + (j % groups) * nr;
+      if (have_it)
+        for (int k = 0; k < nr; ++k) w[j] = std::max(w[j], (double)S->last_iters[s0 + k]);
+      else if (have_om)
+        w[j] = S->last_omega[f];
+    }
+    std::vector<int32_t> order((size_t)n_jobs);
+    for (int j = 0; j < n_jobs; ++j) order[j] = j;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return w[a] > w[b]; });
+    if ((size_t)n_jobs + 1 > (size_t)S->n_sys + 1) return fail(c, EFB_ERR_STATE, "cluster solver: job queue overflow");
+    S->h_job_order.resize((size_t)n_jobs + 1);
+    S->h_job_order[0] = 0;
+    for (int j = 0; j < n_jobs; ++j) S->h_job_order[1 + j] = order[j];
+    EFB_CUDA(c, cudaMemcpyAsync(S->d_job, S->h_job_order.data(), S->h_job_order.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  }
+  if (!S->ev_s0) {
+    EFB_CUDA(c, cudaEventCreate(&S->ev_s0));
+    EFB_CUDA(c, cudaEventCreate(&S->ev_s1));
+  }
+  EFB_CUDA(c, cudaEventRecord(S->ev_s0, c->stream));
+  const int mr = o->max_restarts > 0 ? o->max_restarts : 3;
+  int rc = EFB_OK, ncl = 0;
+#define EFB_CL(NRV, RPTV)                                                                                                             \
+  rc = launch_cluster<NRV, RPTV>(c, P.D, PL->d, nth, smem, P.first_matrix, n_jobs, groups, S->d_job, S->d_b, S->d_x, zero_x ? 1 : 0, mr, &ncl)
+  if (nr == 2) {
+    if (rpt == 1) EFB_CL(2, 1); else if (rpt == 2) EFB_CL(2, 2); else EFB_CL(2, 4);
+  } else {
+    if (rpt == 1) EFB_CL(1, 1); else if (rpt == 2) EFB_CL(1, 2); else EFB_CL(1, 4);
+  }
+#undef EFB_CL
+  if (rc) return rc;
+  EFB_CUDA(c, cudaEventRecord(S->ev_s1, c->stream));
+  S->small_timed = true;
+  S->last_cluster_c = PL->h.C;
+  S->last_cluster_nr = nr;
+  S->last_cluster_n = ncl;
+  *ran = true;
+  return EFB_OK;
+}
+
+}  // namespace efb
+
+using namespace efb;
+
+// ---------------------------------------------------------------- debug / test hooks (host only, no GPU needed)
+extern "C" {
+
+struct efb_cluster_plan_dbg {
+  ClusterPlanHost h;
+};
+
+int efb_debug_cluster_plan_build(int32_t m, const int32_t *rowptr, const int32_t *colidx, const uint8_t *dir, int32_t n_node,
+                                 const int32_t *edge_nodes, int32_t C, void **out) {
+  if (!rowptr || !colidx || !out || m <= 0) return EFB_ERR_INVALID;
+  auto *d = new efb_cluster_plan_dbg();
+  if (!build_cluster_plan(m, rowptr, colidx, dir, n_node, edge_nodes, C, d->h)) {
+    set_global_error("efb_debug_cluster_plan_build: " + d->h.error);
+    delete d;
+    return EFB_ERR_LIMIT;
+  }
+  *out = d;
+  return EFB_OK;
+}
+
+void efb_debug_cluster_plan_free(void *p) { delete (efb_cluster_plan_dbg *)p; }
+
+// copies the named array (converted to int64) into buf (capacity cap); returns its length, or -1 for an unknown name
+int64_t efb_debug_cluster_plan_get(void *p, const char *name, int64_t *buf, int64_t cap) {
+  if (!p || !name) return -1;
+  const ClusterPlanHost &H = ((efb_cluster_plan_dbg *)p)->h;
+  std::vector<int64_t> v;
+  auto put = [&](const auto &src) { v.assign(src.begin(), src.end()); };
+  const std::string n = name;
+  if (n == "dims") v = {H.C, H.mc, H.m, H.aux ? 1 : 0, H.max_own, H.max_w, H.max_my, H.max_slots, H.max_halo,
+                        (int64_t)cluster_smem_bytes(1, H), (int64_t)cluster_smem_bytes(2, H)};
+  else if (n == "c_orig") put(H.c_orig);
+  else if (n == "cta_info") put(H.cta_info);
+  else if (n == "row_edge") put(H.row_edge);
+  else if (n == "row_ws") put(H.row_ws);
+  else if (n == "row_n0") put(H.row_n0);
+  else if (n == "row_n1") put(H.row_n1);
+  else if (n == "blk_off") put(H.blk_off);
+  else if (n == "slot_src") put(H.slot_src);
+  else if (n == "slot_col") put(H.slot_col);
+  else if (n == "halo_ws") put(H.halo_ws);
+  else if (n == "halo_src") put(H.halo_src);
+  else if (n == "node_id") put(H.node_id);
+  else if (n == "n2e_ptr") put(H.n2e_ptr);
+  else if (n == "n2e_item") put(H.n2e_item);
+  else if (n == "nsrc_ptr") put(H.nsrc_ptr);
+  else if (n == "nsrc_item") put(H.nsrc_item);
+  else return -1;
+  if (buf)
+    for (int64_t i = 0; i < (int64_t)v.size() && i < cap; ++i) buf[i] = v[i];
+  return (int64_t)v.size();
+}
+
+}  // extern "C"

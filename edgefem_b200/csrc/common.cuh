@@ -164,6 +164,10 @@ struct System {
   // the free edges in ascending original order.  SELL-32 copy of the compact pattern: rows sorted by length (desc),
   // slices of 32 rows stored column-major and padded to the slice's longest row.
   bool small_dirty = true;
+  // cluster-split persistent solver (cluster.cu): plan of the split, rebuilt with the small structures
+  bool cl_dirty = true;
+  void *cl_plan = nullptr;
+  int last_cluster_c = 0, last_cluster_nr = 0, last_cluster_n = 0;  // shape of the last cluster launch (0: not used)
   int m_c = 0;                     // free unknowns
   int32_t *d_c_orig = nullptr;     // [m_c] compact id -> original edge id
   int2 *d_c_edge_nodes = nullptr;  // [m_c] (tail, head) node of the compact edge
@@ -317,6 +321,7 @@ struct SubTrace {
 
 // internal entry points shared across translation units
 int solver_free(System *s);
+void cluster_plan_free(System *s);  // cluster.cu
 int build_small_structs(System *s);  // abi.cu
 // numbering.cu: large-mesh set-up on the device
 bool device_setup_enabled(long long n_tet);

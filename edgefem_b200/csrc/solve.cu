@@ -11,12 +11,9 @@
 #include <queue>
 
 #include "common.cuh"
+#include "solve_internal.cuh"
 
 namespace efb {
-
-enum Scal { S_RHO0 = 0, S_RHO1 = 1, S_PQ = 2, S_RR = 3, S_BB = 4, S_R0V = 5, S_TS = 6, S_TT = 7, S_ALPHA = 8, S_OMEGA = 9 };
-enum State { ST_ACTIVE = 0, ST_ITERS = 1, ST_CONV = 2, ST_REC = 3 };
-enum Vecs { V_R = 0, V_P = 1, V_Q = 2, V_Z = 3, V_R0 = 4, V_T = 5, V_Y = 6, V_NUM = 7 };
 
 constexpr int VEC_THREADS = 256;
 
@@ -75,23 +72,6 @@ __device__ bool reduce_and_ticket(double (&v)[NV], double *partial_sys, unsigned
   }
   return false;
 }
-
-struct SolveDev {  // kernel-side view of the solver workspace
-  int m, n_rhs, n_node;
-  long long nnz;
-  const int32_t *rowptr, *colidx;
-  const c128 *vals;
-  const uint8_t *dir, *node_dir;
-  const int2 *edge_nodes;
-  const int32_t *n2e_ptr, *n2e_item;
-  c128 *dinv, *linv, *w;
-  c128 *scal;
-  double *partial;
-  unsigned *counter;
-  int32_t *state;
-  double tol2;
-  int max_it;
-};
 
 __device__ __forceinline__ c128 *scal_of(const SolveDev &D, int s) { return D.scal + (size_t)s * NSCAL; }
 __device__ __forceinline__ double *partial_of(const SolveDev &D, int s) { return D.partial + (size_t)s * RED_MAX_BLOCKS * 4; }
@@ -755,30 +735,6 @@ k_bicg_x(SolveDev D, int first_sys, c128 *__restrict__ x, c128 *__restrict__ r, 
 // and CTAs pull the next matrix from an atomic queue when theirs has converged.
 constexpr int SMALL_LPR = 16;
 
-template <int N>
-__device__ __forceinline__ void block_allreduce(double (&v)[N], double *red /* smem [33*N] */) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-#pragma unroll
-  for (int k = 0; k < N; ++k) {
-    double a = v[k];
-    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    if (lane == 0) red[wid * N + k] = a;
-  }
-  __syncthreads();
-  if (wid == 0) {
-#pragma unroll
-    for (int k = 0; k < N; ++k) {
-      double a = (lane < nw) ? red[lane * N + k] : 0.0;
-      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-      if (lane == 0) red[32 * N + k] = a;
-    }
-  }
-  __syncthreads();
-#pragma unroll
-  for (int k = 0; k < N; ++k) v[k] = red[32 * N + k];
-  __syncthreads();
-}
-
 // One job of the persistent solver: matrix f, the NR right-hand sides starting at system s0, solved to convergence by
 // the whole CTA (see k_cocg_small below).
 template <int NR, int SPD, bool DB>
@@ -1367,16 +1323,6 @@ static int launch_spmv(System *S, const SolveDev &D, int first, int count, const
   return EFB_OK;
 }
 
-struct SolvePlan {
-  System *S;
-  SolveDev D;
-  int first_matrix, n_matrix, first_sys, n_sys;
-  int method, precond;
-  bool aux;
-  c128 *vec[V_NUM];
-  dim3 vgrid, ngrid;
-};
-
 static int apply_precond(SolvePlan &P, const c128 *in, c128 *out, c128 *out2, int dot_slot) {
   Ctx *c = P.S->ctx;
   if (P.aux) {
@@ -1716,7 +1662,9 @@ int efb_solve(efb_system *sys_, int32_t first_matrix, int32_t n_matrix, const ef
   S->small_timed = false;
   st.mark("solve: preconditioner launches");
   if (P.method == EFB_METHOD_COCG && opts->max_iterations > 0) {
-    if ((rc = run_cocg_small(P, opts, zero_x, &ran_small))) return rc;
+    S->last_cluster_c = 0;
+    if ((rc = run_krylov_cluster(P, opts, zero_x, &ran_small))) return rc;
+    if (!ran_small && (rc = run_cocg_small(P, opts, zero_x, &ran_small))) return rc;
     st.mark("solve: persistent-solver set-up + launch (host)");
     if (ran_small && (rc = read_state())) return rc;
     st.mark("solve: wait for the device");
@@ -1786,6 +1734,15 @@ int efb_system_last_solve_kernel_ms(efb_system *sys_, double *ms) {
   float f = 0.f;
   EFB_CUDA(S->ctx, cudaEventElapsedTime(&f, S->ev_s0, S->ev_s1));
   *ms = (double)f;
+  return EFB_OK;
+}
+
+int efb_system_last_solve_shape(efb_system *sys_, int32_t *cluster_ctas, int32_t *rhs_per_job, int32_t *n_clusters) {
+  System *S = (System *)sys_;
+  if (!S) return fail(nullptr, EFB_ERR_INVALID, "efb_system_last_solve_shape: NULL system");
+  if (cluster_ctas) *cluster_ctas = S->last_cluster_c;
+  if (rhs_per_job) *rhs_per_job = S->last_cluster_c ? S->last_cluster_nr : 0;
+  if (n_clusters) *n_clusters = S->last_cluster_c ? S->last_cluster_n : 0;
   return EFB_OK;
 }
 

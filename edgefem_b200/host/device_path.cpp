@@ -80,22 +80,26 @@ std::uint64_t mesh_fingerprint(const Mesh &mesh) {
     h ^= v;
     h *= 1099511628211ull;
   };
-  const size_t nt = mesh.tets.size();
-  const size_t step = std::max<size_t>(1, nt / 64);
-  for (size_t t = 0; t < nt; t += step) {
-    for (int k = 0; k < 4; ++k) mix((std::uint64_t)mesh.tets[t].conn[k]);
-    mix((std::uint64_t)mesh.tets[t].phys);
-    mix((std::uint64_t)mesh.tets[t].edges[5]);
+  // EVERY input of the device mesh goes into the key (coordinates, connectivity, tags, edge ids, orientations,
+  // edge end nodes): a mesh edited in place, or a new one at the same address with the same counts, must miss.
+  // O(N) and cheap next to the marshalling + upload it guards (20 M tets: ~0.3 s against 3 s).
+  for (const Element &e : mesh.tets) {
+    for (int k = 0; k < 4; ++k) mix((std::uint64_t)e.conn[k]);
+    mix((std::uint64_t)(std::int64_t)e.phys);
+    for (int k = 0; k < 6; ++k) mix(((std::uint64_t)(std::uint32_t)e.edges[k] << 2) | (std::uint64_t)(e.edge_orient[k] > 0 ? 1 : 0));
   }
-  const size_t nn = mesh.nodes.size();
-  const size_t nstep = std::max<size_t>(1, nn / 64);
-  for (size_t i = 0; i < nn; i += nstep) {
+  for (const Node &n : mesh.nodes) {
     std::uint64_t b;
+    mix((std::uint64_t)n.id);
     for (int a = 0; a < 3; ++a) {
-      const double d = mesh.nodes[i].xyz[a];
+      const double d = n.xyz[a];
       memcpy(&b, &d, 8);
       mix(b);
     }
+  }
+  for (const Edge &e : mesh.edges) {
+    mix((std::uint64_t)e.n0);
+    mix((std::uint64_t)e.n1);
   }
   return h;
 }
@@ -673,7 +677,7 @@ SolveResult solve_linear(const SpMatC &A, const VecC &b, const SolveOptions &opt
     for (int i = 0; i < A.rows() && symmetric; ++i)
       for (int k = rp[i]; k < rp[i + 1]; ++k) {
         const int j = ci[k];
-        if (j <= i) continue;
+        if (j == i) continue;  // both triangles: an entry stored only below the diagonal must be seen too
         const cplx t = A.coeff(j, i);
         if (std::abs(t - va[k]) > 1e-10 * std::max(std::max(std::abs(t), std::abs(va[k])), 1e-3 * amax)) {
           symmetric = false;
