@@ -19,6 +19,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <cmath>
 
 #include "cluster_plan.hpp"
 #include "solve_internal.cuh"
@@ -31,7 +32,11 @@ constexpr int CL_THREADS_MAX = 640;
 
 struct ClusterDev {
   int C, mc, aux;
-  int max_own, max_w, max_my, max_slots;
+  int max_own, max_w, max_my, max_slots, max_halo, max_n2e, max_nsrc;
+  int ndeg, sdeg;  // widths of the per-node ELL lists below (own edges at a node / CTAs touching a node)
+  const uint16_t *n2e_ell;  // [C][ndeg][max_my] own local row << 1 | head, 0xffff = none
+  const uint32_t *nsrc_ell; // [C][sdeg][max_my] CTA << 16 | that CTA's node slot, 0xffffffff = none
+  long long *prof;  // [C][16] cycle counters per phase (EDGEFEM_B200_CLUSTER_PROF=1), else null
   const int32_t *cta_info, *row_edge;
   const uint16_t *row_ws, *row_n0, *row_n1;
   const int32_t *blk_off, *slot_src;
@@ -45,21 +50,45 @@ struct ClusterDev {
 
 struct ClusterPlanDev {  // owned by a System (cl_plan)
   ClusterPlanHost h;
+  std::vector<uint16_t> n2e_ell;
+  std::vector<uint32_t> nsrc_ell;
+  int ndeg = 0, sdeg = 0;
   ClusterDev d{};
   std::vector<void *> blocks;
 };
 
+static void plan_degrees(const ClusterPlanHost &H, int *ndeg_out, int *sdeg_out) {
+  int ndeg = 0, sdeg = 0;
+  for (int cta = 0; cta < H.C; ++cta) {
+    const int32_t *I = &H.cta_info[(size_t)cta * CL_INFO_STRIDE];
+    const int32_t *np_ = &H.n2e_ptr[I[CI_OFF_NODE] + cta], *sp_ = &H.nsrc_ptr[I[CI_OFF_NODE] + cta];
+    for (int j = 0; j < I[CI_N_MY]; ++j) {
+      ndeg = std::max(ndeg, np_[j + 1] - np_[j]);
+      sdeg = std::max(sdeg, sp_[j + 1] - sp_[j]);
+    }
+  }
+  *ndeg_out = ndeg;
+  *sdeg_out = sdeg;
+}
+
 static size_t cluster_smem_bytes(int nr, const ClusterPlanHost &P) {
+  int ndeg, sdeg;
+  plan_degrees(P, &ndeg, &sdeg);
   size_t b = 0;
   b += (size_t)P.max_slots * 16;            // mat_v
   b += (size_t)P.max_w * nr * 16;           // p_w
   b += (size_t)P.max_own * nr * 16 * 2;     // q_own, z_own
-  b += (size_t)P.max_my * nr * 16 * 3;      // wp, g, w
-  b += (size_t)P.max_my * 16;               // linv
+  b += (size_t)std::max(P.max_my, 1) * nr * 16 * 3;  // wp, g, w
+  b += (size_t)std::max(P.max_my, 1) * 16;  // linv
   b += 2 * CL_MAX_C * 8 * 8;                // partial banks
   b += 33 * 8 * 8;                          // block reduction scratch
   b += 16;                                  // job slot
   b += ((size_t)P.max_slots * 2 + 15) / 16 * 16;  // mat_c
+  b += ((size_t)std::max(P.max_halo, 1) * 4 + 15) / 16 * 16;   // halo_src
+  b += ((size_t)std::max(P.max_halo, 1) * 2 + 15) / 16 * 16;   // halo_ws
+  b += ((size_t)ndeg * std::max(P.max_my, 1) * 2 + 15) / 16 * 16;  // n2e_ell
+  b += ((size_t)sdeg * std::max(P.max_my, 1) * 4 + 15) / 16 * 16;  // nsrc_ell
+  b += 16 * 8;                                                 // phase counters
   return b + 16;
 }
 
@@ -69,7 +98,15 @@ __device__ __forceinline__ c128 ldg_stream16(const c128 *p) {
   return v;
 }
 
-// block-wide sums of N doubles; thread (c*N + k) then stores sum k into bank[crank*8 + k] of CTA c of the cluster
+// complex division through one reciprocal (the scalars of the recurrence are far from over/underflow; a zero or
+// non-finite denominator is caught by the callers as a breakdown)
+__device__ __forceinline__ c128 cdiv_fast(c128 a, c128 b) {
+  const double inv = 1.0 / fma(b.x, b.x, b.y * b.y);
+  return make_double2(fma(a.x, b.x, a.y * b.y) * inv, fma(a.y, b.x, -a.x * b.y) * inv);
+}
+
+// Block-wide sums of N doubles pushed to every CTA of the cluster: warp shuffles, one block barrier, then thread
+// (c*N + k) adds the warp partials of sum k in warp order and stores the result into bank[crank*8 + k] of CTA c.
 template <int N>
 __device__ __forceinline__ void reduce_push(cg::cluster_group &cluster, double (&v)[N], double *red, double *bank, int C, int crank) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -80,29 +117,30 @@ __device__ __forceinline__ void reduce_push(cg::cluster_group &cluster, double (
     if (lane == 0) red[wid * N + k] = a;
   }
   __syncthreads();
-  if (wid == 0) {
-#pragma unroll
-    for (int k = 0; k < N; ++k) {
-      double a = (lane < nw) ? red[lane * N + k] : 0.0;
-      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-      if (lane == 0) red[32 * N + k] = a;
-    }
-  }
-  __syncthreads();
   if ((int)threadIdx.x < N * C) {
     const int k = threadIdx.x % N, c = threadIdx.x / N;
-    double *dst = cluster.map_shared_rank(bank, c);
-    dst[crank * 8 + k] = red[32 * N + k];
+    double a0 = 0.0, a1 = 0.0;
+    int w = 0;
+    for (; w + 2 <= nw; w += 2) {
+      a0 += red[w * N + k];
+      a1 += red[(w + 1) * N + k];
+    }
+    if (w < nw) a0 += red[w * N + k];
+    double *dst = c == crank ? bank : cluster.map_shared_rank(bank, c);
+    dst[crank * 8 + k] = a0 + a1;
   }
 }
 
+// Totals over the ranks of a bank [CL_MAX_C][8], the same fixed tree in every warp of every CTA (bit-identical
+// scalars everywhere): lane l holds entries (l/8, l%8) and (4 + l/8, l%8), then xor-shuffles over 8 and 16.
 template <int N>
 __device__ __forceinline__ void bank_totals(const double *bank, int C, double (&tot)[N]) {
+  const int lane = threadIdx.x & 31;
+  double v = bank[lane] + bank[lane + 32];
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 16);
 #pragma unroll
-  for (int k = 0; k < N; ++k) tot[k] = 0.0;
-  for (int c = 0; c < C; ++c)
-#pragma unroll
-    for (int k = 0; k < N; ++k) tot[k] += bank[c * 8 + k];
+  for (int k = 0; k < N; ++k) tot[k] = __shfl_sync(0xffffffffu, v, k);
 }
 
 template <int NR, int RPT>
@@ -127,13 +165,20 @@ k_cocg_cluster(const SolveDev D, const ClusterDev K, int first_matrix, int n_job
   double *red = part + 2 * CL_MAX_C * 8;         // [33*8]
   int *s_job = (int *)(red + 33 * 8);
   uint16_t *mat_c = (uint16_t *)(s_job + 4);
+  auto up16 = [](size_t b) { return (b + 15) / 16 * 16; };
+  // the index lists live in shared memory: every cluster barrier invalidates L1 (CCTL.IVALL behind the cluster-scope
+  // acquire), so lists read from global memory would come from L2 again in every phase of every iteration
+  uint32_t *halo_src_s = (uint32_t *)((unsigned char *)mat_c + up16((size_t)K.max_slots * 2));
+  uint16_t *halo_ws_s = (uint16_t *)((unsigned char *)halo_src_s + up16((size_t)max(K.max_halo, 1) * 4));
+  uint16_t *n2e_ell_s = (uint16_t *)((unsigned char *)halo_ws_s + up16((size_t)max(K.max_halo, 1) * 2));
+  uint32_t *nsrc_ell_s = (uint32_t *)((unsigned char *)n2e_ell_s + up16((size_t)K.ndeg * K.max_my * 2));
+  long long *prof_s = (long long *)((unsigned char *)nsrc_ell_s + up16((size_t)K.sdeg * K.max_my * 4));
   double *bank0 = part, *bank1 = part + CL_MAX_C * 8;
 
   const int32_t *I = K.cta_info + crank * CL_INFO_STRIDE;
   const int n_own = I[CI_N_OWN], n_my = I[CI_N_MY], n_halo = I[CI_N_HALO], n_blk = I[CI_N_BLK], n_slots = I[CI_N_SLOTS];
   const int off_row = I[CI_OFF_ROW], off_slot = I[CI_OFF_SLOT], off_blk = I[CI_OFF_BLK], off_halo = I[CI_OFF_HALO];
-  const int off_node = I[CI_OFF_NODE], off_n2e = I[CI_OFF_N2E], off_nsrc = I[CI_OFF_NSRC];
-  const int32_t *n2e_ptr = K.n2e_ptr + off_node + crank, *nsrc_ptr = K.nsrc_ptr + off_node + crank;
+  const int off_node = I[CI_OFF_NODE];
   const int m = D.m;
 
   // per-thread rows: local row t = u * nth + tid (a warp = one 32-row ELL block)
@@ -156,7 +201,25 @@ k_cocg_cluster(const SolveDev D, const ClusterDev K, int first_matrix, int n_job
     }
   }
   for (int i = tid; i < n_slots; i += nth) mat_c[i] = K.slot_col[off_slot + i];
+  for (int i = tid; i < n_halo; i += nth) {
+    halo_ws_s[i] = K.halo_ws[off_halo + i];
+    halo_src_s[i] = K.halo_src[off_halo + i];
+  }
+  for (int i = tid; i < K.ndeg * K.max_my; i += nth) n2e_ell_s[i] = K.n2e_ell[(size_t)crank * K.ndeg * K.max_my + i];
+  for (int i = tid; i < K.sdeg * K.max_my; i += nth) nsrc_ell_s[i] = K.nsrc_ell[(size_t)crank * K.sdeg * K.max_my + i];
+  for (int i = tid; i < 2 * CL_MAX_C * 8; i += nth) part[i] = 0.0;  // banks of absent ranks (C < 8) stay zero
+  if (tid < 16) prof_s[tid] = 0;
   __syncthreads();
+  long long t_last = 0;
+  const bool prof_on = K.prof != nullptr && tid == 0;
+  if (prof_on) t_last = clock64();
+  auto PROF = [&](int k) {
+    if (prof_on) {
+      const long long t = clock64();
+      prof_s[k] += t - t_last;
+      t_last = t;
+    }
+  };
 
   // q = A p over the own rows (p from the window in shared memory)
   auto spmv = [&](c128 (&out)[RPT][NR]) {
@@ -194,8 +257,8 @@ k_cocg_cluster(const SolveDev D, const ClusterDev K, int first_matrix, int n_job
   // window halo: p_w[h] = z(owner) (+ beta p_w[h])
   auto pull_halo = [&](const c128 (&beta)[NR], bool use_beta) {
     for (int h = tid; h < n_halo; h += nth) {
-      const int hw = K.halo_ws[off_halo + h];
-      const uint32_t src = K.halo_src[off_halo + h];
+      const int hw = halo_ws_s[h];
+      const uint32_t src = halo_src_s[h];
       const c128 *rz = cluster.map_shared_rank(z_own, src >> 16) + (size_t)(src & 0xffffu) * NR;
 #pragma unroll
       for (int r = 0; r < NR; ++r) {
@@ -204,35 +267,47 @@ k_cocg_cluster(const SolveDev D, const ClusterDev K, int first_matrix, int n_job
       }
     }
   };
-  // wp[n] = sum over the own edges at my node n of +-q_own
+  // wp[n] = sum over the own edges at my node n of +-q_own: 4 lanes per node walk the node's ELL list with stride 4
+  // (independent loads, ~2 items per lane), two shuffle steps, fixed order
   auto nodal_partial = [&]() {
     if (!K.aux) return;
-    for (int j = tid; j < n_my; j += nth) {
-      const int kb = n2e_ptr[j], ke = n2e_ptr[j + 1];
+    const int l4 = lane & 3;
+    for (int jb = (tid >> 5) * 8; jb < n_my; jb += (nth >> 5) * 8) {
+      const int j = jb + (lane >> 2);
       c128 a[NR];
 #pragma unroll
       for (int r = 0; r < NR; ++r) a[r] = cmake(0.0, 0.0);
-      for (int k = kb; k < ke; ++k) {
-        const uint32_t it = K.n2e_item[off_n2e + k];
-        const c128 *v = q_own + (size_t)(it >> 1) * NR;
+      if (j < n_my)
+        for (int k = l4; k < K.ndeg; k += 4) {
+          const uint32_t it = n2e_ell_s[k * K.max_my + j];
+          if (it == 0xffffu) break;  // items are packed at the front
+          const c128 *v = q_own + (size_t)(it >> 1) * NR;
 #pragma unroll
-        for (int r = 0; r < NR; ++r) a[r] = (it & 1u) ? cadd(a[r], v[r]) : csub(a[r], v[r]);
-      }
+          for (int r = 0; r < NR; ++r) a[r] = (it & 1u) ? cadd(a[r], v[r]) : csub(a[r], v[r]);
+        }
 #pragma unroll
-      for (int r = 0; r < NR; ++r) wp[j * NR + r] = a[r];
+      for (int r = 0; r < NR; ++r)
+#pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {
+          a[r].x += __shfl_xor_sync(0xffffffffu, a[r].x, o);
+          a[r].y += __shfl_xor_sync(0xffffffffu, a[r].y, o);
+        }
+      if (j < n_my && l4 == 0)
+#pragma unroll
+        for (int r = 0; r < NR; ++r) wp[j * NR + r] = a[r];
     }
   };
   // g[n] (-)= alpha * sum over every CTA touching n of its partial; w[n] = linv[n] g[n]
   auto nodal_combine = [&](bool set, const c128 (&alpha)[NR]) {
     if (!K.aux) return;
     for (int j = tid; j < n_my; j += nth) {
-      const int kb = nsrc_ptr[j], ke = nsrc_ptr[j + 1];
       c128 a[NR];
 #pragma unroll
       for (int r = 0; r < NR; ++r) a[r] = cmake(0.0, 0.0);
-      for (int k = kb; k < ke; ++k) {
-        const uint32_t it = K.nsrc_item[off_nsrc + k];
-        const c128 *v = cluster.map_shared_rank(wp, it >> 16) + (size_t)(it & 0xffffu) * NR;
+      for (int k = 0; k < K.sdeg; ++k) {
+        const uint32_t it = nsrc_ell_s[k * K.max_my + j];
+        if (it == 0xffffffffu) break;  // sources are packed at the front, ascending rank
+        const c128 *v = ((int)(it >> 16) == crank ? wp : cluster.map_shared_rank(wp, it >> 16)) + (size_t)(it & 0xffffu) * NR;
 #pragma unroll
         for (int r = 0; r < NR; ++r) a[r] = cadd(a[r], v[r]);
       }
@@ -395,7 +470,9 @@ k_cocg_cluster(const SolveDev D, const ClusterDev K, int first_matrix, int n_job
       // (3) iterations until the recursive residual converges
       for (;;) {
         // A
+        PROF(0);
         spmv(qv);
+        PROF(1);
         {
           double d[2 * NR];
 #pragma unroll
@@ -410,10 +487,14 @@ k_cocg_cluster(const SolveDev D, const ClusterDev K, int first_matrix, int n_job
                 d[2 * r] += t.x; d[2 * r + 1] += t.y;
               }
           __syncthreads();
+          PROF(2);
           nodal_partial();
+          PROF(3);
           reduce_push<2 * NR>(cluster, d, red, bank0, C, crank);
+          PROF(4);
         }
         cluster.sync();  // barrier 1
+        PROF(5);
         // B
         c128 alpha[NR];
         {
@@ -424,11 +505,13 @@ k_cocg_cluster(const SolveDev D, const ClusterDev K, int first_matrix, int n_job
             const c128 pq = cmake(tot[2 * r], tot[2 * r + 1]);
             const bool brk = (pq.x == 0.0 && pq.y == 0.0) || !(isfinite(pq.x) && isfinite(pq.y));
             if (brk) act[r] = false;
-            alpha[r] = act[r] ? cdiv(rho[r], pq) : cmake(0.0, 0.0);
+            alpha[r] = act[r] ? cdiv_fast(rho[r], pq) : cmake(0.0, 0.0);
             if (act[r]) iters[r] += 1;
           }
         }
+        PROF(6);
         nodal_combine(false, alpha);
+        PROF(7);
 #pragma unroll
         for (int u = 0; u < RPT; ++u)
 #pragma unroll
@@ -437,6 +520,7 @@ k_cocg_cluster(const SolveDev D, const ClusterDev K, int first_matrix, int n_job
             rv[u][r] = cfma(cneg(alpha[r]), qv[u][r], rv[u][r]);
           }
         __syncthreads();
+        PROF(8);
         {
           double d[3 * NR];
 #pragma unroll
@@ -454,9 +538,12 @@ k_cocg_cluster(const SolveDev D, const ClusterDev K, int first_matrix, int n_job
                 d[3 * r] += t.x; d[3 * r + 1] += t.y;
                 d[3 * r + 2] += cabs2(rv[u][r]);
               }
+          PROF(9);
           reduce_push<3 * NR>(cluster, d, red, bank1, C, crank);
+          PROF(10);
         }
         cluster.sync();  // barrier 2
+        PROF(11);
         // D
         c128 beta[NR];
         bool still = false;
@@ -470,12 +557,13 @@ k_cocg_cluster(const SolveDev D, const ClusterDev K, int first_matrix, int n_job
               rrn[r] = tot[3 * r + 2];
               if (rrn[r] <= D.tol2 * bb[r] || iters[r] >= D.max_it || !isfinite(rrn[r])) act[r] = false;
             }
-            beta[r] = (act[r] && (rho[r].x != 0.0 || rho[r].y != 0.0)) ? cdiv(rho_new, rho[r]) : cmake(0.0, 0.0);
+            beta[r] = (act[r] && (rho[r].x != 0.0 || rho[r].y != 0.0)) ? cdiv_fast(rho_new, rho[r]) : cmake(0.0, 0.0);
             rho[r] = rho_new;
             still |= act[r];
           }
         }
         if (!still) break;
+        PROF(12);
 #pragma unroll
         for (int u = 0; u < RPT; ++u)
           if (valid[u])
@@ -484,7 +572,9 @@ k_cocg_cluster(const SolveDev D, const ClusterDev K, int first_matrix, int n_job
               pr[u][r] = cfma(beta[r], pr[u][r], zv[u][r]);
               p_w[ws[u] * NR + r] = pr[u][r];
             }
+        PROF(13);
         pull_halo(beta, true);
+        PROF(14);
         __syncthreads();
       }
       __syncthreads();
@@ -507,6 +597,8 @@ k_cocg_cluster(const SolveDev D, const ClusterDev K, int first_matrix, int n_job
     }
     // the next job's first barrier orders the reuse of the shared-memory buffers across the cluster
   }
+  if (prof_on)
+    for (int k = 0; k < 16; ++k) atomicAdd((unsigned long long *)&K.prof[crank * 16 + k], (unsigned long long)prof_s[k]);
 }
 
 // ---------------------------------------------------------------- host side
@@ -538,6 +630,40 @@ static int cluster_plan_upload(System *S, ClusterPlanDev *P) {
   ClusterDev &d = P->d;
   d.C = H.C; d.mc = H.mc; d.aux = H.aux ? 1 : 0;
   d.max_own = H.max_own; d.max_w = H.max_w; d.max_my = std::max(H.max_my, 1); d.max_slots = H.max_slots;
+  d.max_halo = H.max_halo; d.max_n2e = H.max_n2e; d.max_nsrc = H.max_nsrc;
+  {
+    // per-node lists as ELL (thread per node in the kernel, independent loads): own edges at a node, CTAs touching a node
+    int ndeg, sdeg;
+    plan_degrees(H, &ndeg, &sdeg);
+    P->ndeg = ndeg;
+    P->sdeg = sdeg;
+    P->n2e_ell.assign((size_t)H.C * ndeg * d.max_my + 1, (uint16_t)0xffffu);
+    P->nsrc_ell.assign((size_t)H.C * sdeg * d.max_my + 1, 0xffffffffu);
+    for (int cta = 0; cta < H.C; ++cta) {
+      const int32_t *I = &H.cta_info[(size_t)cta * CL_INFO_STRIDE];
+      const int32_t *np_ = &H.n2e_ptr[I[CI_OFF_NODE] + cta], *sp_ = &H.nsrc_ptr[I[CI_OFF_NODE] + cta];
+      for (int j = 0; j < I[CI_N_MY]; ++j) {
+        for (int k = np_[j]; k < np_[j + 1]; ++k)
+          P->n2e_ell[((size_t)cta * ndeg + (k - np_[j])) * d.max_my + j] = (uint16_t)H.n2e_item[I[CI_OFF_N2E] + k];
+        for (int k = sp_[j]; k < sp_[j + 1]; ++k)
+          P->nsrc_ell[((size_t)cta * sdeg + (k - sp_[j])) * d.max_my + j] = H.nsrc_item[I[CI_OFF_NSRC] + k];
+      }
+    }
+    d.ndeg = ndeg;
+    d.sdeg = sdeg;
+    int rce;
+    if ((rce = up(c, P, &d.n2e_ell, P->n2e_ell))) return rce;
+    if ((rce = up(c, P, &d.nsrc_ell, P->nsrc_ell))) return rce;
+  }
+  d.prof = nullptr;
+  if (const char *e = getenv("EDGEFEM_B200_CLUSTER_PROF"))
+    if (atoi(e) > 0) {
+      long long *pb = nullptr;
+      int rcp = dev_alloc(c, &pb, (size_t)CL_MAX_C * 16);
+      if (rcp) return rcp;
+      P->blocks.push_back(pb);
+      d.prof = pb;
+    }
   int rc;
   if ((rc = up(c, P, &d.cta_info, H.cta_info))) return rc;
   if ((rc = up(c, P, &d.row_edge, H.row_edge))) return rc;
@@ -673,6 +799,20 @@ int run_krylov_cluster(SolvePlan &P, const efb_solve_opts *o, bool zero_x, bool 
   const size_t smem = cluster_smem_bytes(nr, PL->h);
   const int groups = n_rhs / nr;
   const int n_jobs = P.n_matrix * groups;
+  if (forced < 0) {
+    // Latency or throughput?  A cluster job is ~10x faster than a one-CTA job of k_cocg_small (measured on WR-90:
+    // 7.9 us per rhs-iteration on 8 SMs against 85 us per two-rhs iteration on one), but only ~15 clusters of 8 are
+    // resident against 148 CTAs, and a one-CTA job carries both right-hand sides: big batches (the 256-point sweep)
+    // stay on the one-CTA kernel when it applies, small ones (one frequency, the shards of a strong-scaled sweep) run
+    // here.  Systems the one-CTA kernel cannot take (p does not fit in its shared memory) always run here.
+    const int C = PL->h.C;
+    const int resident = std::max(1, c->sm_count / C - (C == 8 ? 3 : C == 4 ? 4 : 0));
+    const double rounds_cl = std::ceil((double)n_jobs / resident) * (nr == 2 ? 1.6 : 1.0);
+    const double rounds_1 = std::ceil((double)P.n_matrix / c->sm_count) * 10.0 * (n_rhs >= 2 ? 1.0 : 0.6);
+    const int nn1 = want_aux ? S->n_node : 0;
+    const bool one_cta_ok = S->m <= 16384 && ((size_t)PL->h.mc * 16 + (size_t)nn1 * 16 + 4096) <= (size_t)dev_smem;
+    if (one_cta_ok && rounds_cl > rounds_1) return EFB_OK;
+  }
   {
     // queue order = longest expected job first (iteration counts of the previous solve, else frequency)
     std::vector<double> w((size_t)n_jobs, 0.0);
@@ -698,6 +838,7 @@ int run_krylov_cluster(SolvePlan &P, const efb_solve_opts *o, bool zero_x, bool 
     EFB_CUDA(c, cudaEventCreate(&S->ev_s0));
     EFB_CUDA(c, cudaEventCreate(&S->ev_s1));
   }
+  if (PL->d.prof) EFB_CUDA(c, cudaMemsetAsync(PL->d.prof, 0, (size_t)CL_MAX_C * 16 * sizeof(long long), c->stream));
   EFB_CUDA(c, cudaEventRecord(S->ev_s0, c->stream));
   const int mr = o->max_restarts > 0 ? o->max_restarts : 3;
   int rc = EFB_OK, ncl = 0;
@@ -711,6 +852,19 @@ int run_krylov_cluster(SolvePlan &P, const efb_solve_opts *o, bool zero_x, bool 
 #undef EFB_CL
   if (rc) return rc;
   EFB_CUDA(c, cudaEventRecord(S->ev_s1, c->stream));
+  if (PL->d.prof) {  // EDGEFEM_B200_CLUSTER_PROF=1: cycles of thread 0 of every CTA rank between the phase marks
+    std::vector<long long> hp((size_t)CL_MAX_C * 16);
+    EFB_CUDA(c, cudaMemcpyAsync(hp.data(), PL->d.prof, hp.size() * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    EFB_CUDA(c, cudaStreamSynchronize(c->stream));
+    static const char *names[16] = {"D->A", "spmv", "q store+bar", "nodal partial", "reduce+push 1", "cluster barrier 1", "totals+alpha",
+                                    "nodal combine", "x,r update+bar", "z+dots", "reduce+push 2", "cluster barrier 2", "totals+beta",
+                                    "p update", "halo pull", ""};
+    for (int k = 0; k < 15; ++k) {
+      fprintf(stderr, "[cluster prof] %-18s", names[k]);
+      for (int r = 0; r < PL->h.C; ++r) fprintf(stderr, " %10lld", hp[(size_t)r * 16 + k]);
+      fprintf(stderr, "\n");
+    }
+  }
   S->small_timed = true;
   S->last_cluster_c = PL->h.C;
   S->last_cluster_nr = nr;

@@ -33,7 +33,7 @@ enum ClInfo {
 struct ClusterPlanHost {
   int C = 0, mc = 0, m = 0;
   bool aux = false;
-  int max_own = 0, max_w = 0, max_my = 0, max_slots = 0, max_halo = 0;
+  int max_own = 0, max_w = 0, max_my = 0, max_slots = 0, max_halo = 0, max_n2e = 0, max_nsrc = 0;
   std::vector<int32_t> c_orig;     // [mc] position -> original edge id
   std::vector<int32_t> cta_info;   // [C][CL_INFO_STRIDE]
   // per own row, local order (sorted by length, descending), concatenated over CTAs at CI_OFF_ROW
@@ -297,11 +297,52 @@ inline bool build_cluster_plan(int m, const int32_t *rowptr, const int32_t *coli
         const int t = b * 32 + l;
         const uint16_t self = t < n_own ? (uint16_t)(L[t] - wlo) : (uint16_t)0;
         for (int k = 0; k < width; ++k) P.slot_col[base + (size_t)k * 32 + l] = self;  // padding reads a valid slot
-        if (t >= n_own) continue;
-        const int p = L[t];
-        for (int k = rptr[p]; k < rptr[p + 1]; ++k) {
-          P.slot_src[base + (size_t)(k - rptr[p]) * 32 + l] = rsrc[k];
-          P.slot_col[base + (size_t)(k - rptr[p]) * 32 + l] = (uint16_t)(rcol[k] - wlo);
+      }
+      // The order of the entries inside a row is free, and the kernel gathers p from shared memory with one 16-byte
+      // load per entry: the 8 lanes of a quarter warp are served in one wavefront only if their window slots fall in
+      // 8 different bank groups (slot mod 8).  Per quarter and step, the rows pick -- fewest choices first -- an unused
+      // bank group among the entries they have left (their fullest one), else their fullest group.
+      for (int q = 0; q < 4; ++q) {
+        std::vector<std::pair<int32_t, int32_t>> ent[8][8];  // [lane][bank group] -> (col slot, src)
+        int left[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int u = 0; u < 8; ++u) {
+          const int t = b * 32 + 8 * q + u;
+          if (t >= n_own) continue;
+          const int p = L[t];
+          for (int k = rptr[p]; k < rptr[p + 1]; ++k) {
+            const int cs = rcol[k] - wlo;
+            ent[u][cs & 7].emplace_back(cs, rsrc[k]);
+            left[u]++;
+          }
+          for (int g = 0; g < 8; ++g) std::reverse(ent[u][g].begin(), ent[u][g].end());  // pop_back takes the lowest column first
+        }
+        for (int k = 0; k < width; ++k) {
+          unsigned used = 0, served = 0;
+          for (int pick = 0; pick < 8; ++pick) {
+            int u = -1, ung = 0;
+            for (int v = 0; v < 8; ++v) {
+              if ((served >> v & 1u) || left[v] == 0) continue;
+              int ng = 0;
+              for (int g = 0; g < 8; ++g) ng += !ent[v][g].empty();
+              if (u < 0 || ng < ung) { u = v; ung = ng; }
+            }
+            if (u < 0) break;
+            int best = -1, any = -1;
+            size_t bc = 0, ac = 0;
+            for (int g = 0; g < 8; ++g) {
+              const size_t cg = ent[u][g].size();
+              if (cg > ac) { ac = cg; any = g; }
+              if (!(used >> g & 1u) && cg > bc) { bc = cg; best = g; }
+            }
+            const int g = best >= 0 ? best : any;
+            used |= 1u << g;
+            served |= 1u << u;
+            const auto e = ent[u][g].back();
+            ent[u][g].pop_back();
+            left[u]--;
+            P.slot_col[base + (size_t)k * 32 + 8 * q + u] = (uint16_t)e.first;
+            P.slot_src[base + (size_t)k * 32 + 8 * q + u] = e.second;
+          }
         }
       }
       slots += width * 32;
@@ -344,6 +385,8 @@ inline bool build_cluster_plan(int m, const int32_t *rowptr, const int32_t *coli
     P.max_my = std::max(P.max_my, n_my);
     P.max_slots = std::max(P.max_slots, slots);
     P.max_halo = std::max(P.max_halo, n_halo);
+    P.max_n2e = std::max(P.max_n2e, P.n2e_ptr.back());
+    P.max_nsrc = std::max(P.max_nsrc, P.nsrc_ptr.back());
   }
   return true;
 }

@@ -10,6 +10,7 @@ block carry identical triangulations, so periodic face pairs are node-matched by
 from __future__ import annotations
 
 import itertools
+import math
 from typing import Callable, Dict, Optional, Sequence, Tuple
 
 import numpy as np
@@ -162,3 +163,91 @@ def unit_cell(px: float = 0.005, py: float = 0.005, h_sub: float = 0.0005, h_air
         tris = np.concatenate([tris, f[inside]], axis=0)
         tri_phys = np.concatenate([tri_phys, np.full(int(inside.sum()), t["patch"], dtype=np.int32)])
     return xyz, tets, tet_phys, tris, tri_phys
+
+
+def _lines(breaks: Sequence[float], hmax: float) -> np.ndarray:
+    """Grid lines through every break point with uniform spacing <= hmax inside each interval."""
+    b = sorted(set(float(round(x, 12)) for x in breaks))
+    out = [b[0]]
+    for lo, hi in zip(b[:-1], b[1:]):
+        n = max(1, int(math.ceil((hi - lo) / hmax - 1e-9)))
+        out.extend(lo + (hi - lo) * (k + 1) / n for k in range(n))
+    return np.array(out)
+
+
+def _unique_faces(tets: np.ndarray) -> np.ndarray:
+    """Every face of the mesh once (first-seen orientation), boundary and interior."""
+    f = np.concatenate([tets[:, [0, 1, 2]], tets[:, [0, 1, 3]], tets[:, [0, 2, 3]], tets[:, [1, 2, 3]]], axis=0)
+    key = np.sort(f, axis=1)
+    _, idx = np.unique(key, axis=0, return_index=True)
+    return f[np.sort(idx)]
+
+
+def patch_antenna(patch_length: float = 28.6e-3, patch_width: float = 37.3e-3, substrate_height: float = 1.6e-3, probe_y_offset: float = -9.0e-3,
+                  probe_x_offset: float = 0.0, design_freq: float = 2.45e9, density: float = 12.0, ground_plane_size: Optional[float] = None,
+                  air_box_height: Optional[float] = None, cavity_depth: float = 5e-3, probe_radius: float = 0.5e-3, nz_sub: int = 2,
+                  nz_cavity: int = 2, hmax_scale: float = 1.0, huygens: bool = True):
+    """Probe-fed patch antenna on a grounded substrate (BASELINE config 3), structured Kuhn tets with the geometry and
+    the physical tags of the reference's gmsh model (python/edgefem/designs/stacked_patch.py:63-73,184-330 as driven by
+    patch_antenna.py:213-243 and examples/run_patch_fullwave.py:19-29; gmsh itself is not available here):
+    domain [0,gp]^2 x [-cavity_depth, h + h_air], gp = 3 x max(patch side), h_air = lambda/4 at the design frequency;
+    ground plane z=0 -> 1 (minus the square probe hole of half-width pw), cavity walls (sides below ground) -> 2, cavity
+    bottom -> 3, probe conductor (square column of half-width pr from the bottom to the patch) side faces -> 4, lumped
+    port strip [cx+pr, cx+pw] x [cy-pr, cy+pr] at z=0 -> 5, patch (width along x, length along y, centred) at z=h -> 10,
+    top + sides above ground -> 50 (ABC), Huygens surface at mid air height, inset 0.1 gp -> 60; volumes: cavity 100,
+    substrate 110, air 150.  pr = max(probe_radius, lc/8, 0.5 mm), pw = max(2.5 pr, lc/4, 2 mm), lc = lambda/density
+    (stacked_patch.py:190-195).  Returns (xyz, tets, tet_phys, tris, tri_phys, info)."""
+    c0 = 299792458.0
+    lam = c0 / design_freq
+    lc = lam / density
+    gp = ground_plane_size or 3.0 * max(patch_length, patch_width)
+    h_air = air_box_height or lam / 4.0
+    h = substrate_height
+    pr = max(probe_radius, lc / 8.0, 0.5e-3)
+    pw = max(2.5 * pr, lc / 4.0, 2e-3)
+    cx, cy = gp / 2 + probe_x_offset, gp / 2 + probe_y_offset
+    px0, px1 = gp / 2 - patch_width / 2, gp / 2 + patch_width / 2
+    py0, py1 = gp / 2 - patch_length / 2, gp / 2 + patch_length / 2
+    z_bot, z_top = -cavity_depth, h + h_air
+    z_huy = h + 0.5 * h_air
+    inset = 0.1 * gp
+    hm = lc * hmax_scale
+    xs = _lines([0.0, gp, px0, px1, cx - pw, cx - pr, cx + pr, cx + pw] + ([inset, gp - inset] if huygens else []), hm)
+    ys = _lines([0.0, gp, py0, py1, cy - pw, cy - pr, cy + pr, cy + pw] + ([inset, gp - inset] if huygens else []), hm)
+    zs = np.concatenate([np.linspace(z_bot, 0.0, nz_cavity + 1), np.linspace(0.0, h, nz_sub + 1)[1:],
+                         _lines([h, z_huy, z_top] if huygens else [h, z_top], hm)[1:]])
+    xyz, tets, cells = box_grid(xs, ys, zs)
+    zc = 0.5 * (zs[cells[:, 2]] + zs[cells[:, 2] + 1])
+    tet_phys = np.where(zc < 0.0, 100, np.where(zc < h, 110, 150)).astype(np.int32)
+    faces = _unique_faces(tets)
+    P = xyz[faces - 1]                      # [k,3 nodes,3]
+    cen = P.mean(axis=1)
+    tol = 1e-9
+
+    def on_plane(axis, v):
+        return np.all(np.abs(P[:, :, axis] - v) < tol, axis=1)
+
+    def inside(x0, x1, y0, y1):
+        return (cen[:, 0] > x0) & (cen[:, 0] < x1) & (cen[:, 1] > y0) & (cen[:, 1] < y1)
+
+    tag = np.zeros(faces.shape[0], dtype=np.int32)
+    z0 = on_plane(2, 0.0)
+    hole = inside(cx - pw, cx + pw, cy - pw, cy + pw)
+    tag[z0 & ~hole] = 1
+    tag[z0 & inside(cx + pr, cx + pw, cy - pr, cy + pr)] = 5
+    side = on_plane(0, 0.0) | on_plane(0, gp) | on_plane(1, 0.0) | on_plane(1, gp)
+    tag[side & (cen[:, 2] < 0.0)] = 2
+    tag[on_plane(2, z_bot)] = 3
+    col_z = (cen[:, 2] > z_bot) & (cen[:, 2] < h)
+    in_y = (cen[:, 1] > cy - pr) & (cen[:, 1] < cy + pr)
+    in_x = (cen[:, 0] > cx - pr) & (cen[:, 0] < cx + pr)
+    tag[(on_plane(0, cx - pr) | on_plane(0, cx + pr)) & in_y & col_z] = 4
+    tag[(on_plane(1, cy - pr) | on_plane(1, cy + pr)) & in_x & col_z] = 4
+    tag[on_plane(2, h) & inside(px0, px1, py0, py1)] = 10
+    tag[on_plane(2, z_top)] = 50
+    tag[side & (cen[:, 2] > 0.0)] = 50
+    if huygens:
+        tag[on_plane(2, z_huy) & inside(inset, gp - inset, inset, gp - inset)] = 60
+    keep = tag != 0
+    info = dict(gp=gp, h_air=h_air, lc=lc, pr=pr, pw=pw, cx=cx, cy=cy, grid=(len(xs) - 1, len(ys) - 1, len(zs) - 1))
+    return xyz, tets, tet_phys, faces[keep], tag[keep], info
