@@ -10,8 +10,11 @@ solve, S-parameter projection.
   value : points/s with the mesh, CSR pattern and port operators already resident in HBM
   e2e   : points/s through the public API (pyedgefem.calculate_sparams_eigenmode_sweep) from host
           buffers: mesh upload, pattern build, port upload and S read-back inside the timed region
-Multi-GPU (torchrun, one rank per GPU): the sweep shards by frequency with no data-path
-collective; every rank sweeps its own 256-point sub-band ("weak"), S is all-gathered at the end.
+Multi-GPU (torchrun, one rank per GPU): the sweep shards by frequency with no data-path collective.
+Default "strong" scaling = BASELINE.json configs[1] as written: the 256 points are dealt round-robin to the ranks
+(freqs[rank::world]) and the P x P S-matrices are all-gathered (NCCL) INSIDE the timed region of every step;
+--scaling weak gives every rank its own 256-point sub-band instead.
+Other named workloads: --workload c1 | patch | unitcell | cube print their own JSON line (profiles/ keeps one each).
 Timing: CUDA events on the library's stream (efb_timer_*), barrier + synchronize on both sides,
 max over ranks.  Working set per step (349 MB of matrix values + 330 MB of Krylov vectors) is
 larger than the 126 MB L2, so no explicit L2 flush is needed between timed iterations.
@@ -44,7 +47,11 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--points", type=int, default=N_POINTS)
-    ap.add_argument("--cube-n", type=int, default=64, help="synthetic cube (n^3 boxes x 6 tets) for the assembly / SpMV roofline extras; 0 = skip")
+    ap.add_argument("--cube-n", type=int, default=150, help="synthetic cube (n^3 boxes x 6 tets) of the C5 extras: assembly / SpMV roofline and a converged "
+                    "solve; 150 = BASELINE configs[4] (20.25 M tets); 0 = skip")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--workload", default="wr90", choices=["wr90", "c1", "patch", "unitcell", "cube"])
+    ap.add_argument("--cube-freq", type=float, default=240e6, help="frequency of the C5 solve (between the 212.0 and 259.6 MHz modes of the 1 m cube)")
     ap.add_argument("--cpu-sample", type=int, default=12, help="frequency points of the CPU baseline sample")
     return ap.parse_args()
 
@@ -148,7 +155,7 @@ def run_reference(a):
     v = sum(vals) / len(vals)
     line = {
         "impl": "reference", "metric": "wr90_sweep_freq_points_per_s", "value": v, "unit": "points/s", "n_gpus": a.gpus, "steps": a.steps,
-        "warmup": a.warmup, "ms_per_step": 1000.0 * wall / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": a.warmup, "ms_per_step": 1000.0 * wall / a.steps, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "WR-90 eigenmode sweep 8-12 GHz (rect_waveguide fixture, 4227 tets, 2 ports), bounded sample of %d points per step" % sample},
         "cpu_baseline": {"value": v, "unit": "points/s", "cores": cores, "kind": "port",
@@ -204,6 +211,12 @@ class ResidentSweep:
         self.nnz_free = int(np.count_nonzero(free[rows] & free[ci]))
         self.last = None
 
+    def close(self):
+        for dp in self.dports:
+            dp.close()
+        self.sys.close()
+        self.dm.close()
+
     def step(self):
         np = self.np
         self.sys.assemble_volume(self.omegas, self.mats)
@@ -222,23 +235,27 @@ class ResidentSweep:
         return S, res
 
 
-def cube_extras(ctx, pe, n: int):
-    """Assembly Mtets/s and SpMV GB/s on a synthetic PEC cube (Kuhn split, jittered), single frequency."""
+def cube_extras(ctx, n: int, solve_freq: float, hbm_peak: float):
+    """C5 (BASELINE configs[4]): refined PEC cube cavity (the reference's cavity test object, tests/test_cavity_eigenmodes.cpp,
+    Kuhn split n^3 x 6 tets, jittered), single frequency: assembly Mtets/s, SpMV / Krylov-iteration GB/s at k0 h = 2 pi / 10
+    (SURVEY 8d), and a CONVERGED solve (COCG + auxiliary-space Jacobi, tol 1e-10, random complex b, seed 1234) at
+    `solve_freq`.  The solve frequency is fixed in Hz, not in k0 h: at k0 h = 2 pi / 10 the 20 M-tet lossless cavity is
+    15 wavelengths across with ~28 000 resonances below k0 and no Krylov method without a multilevel preconditioner gets
+    there (measured on n = 6..16: iterations grow like n^2.6)."""
     import numpy as np
     from edgefem_b200 import cabi, meshgen
 
     t0 = time.perf_counter()
     xyz, tets, tp, tris, trp = meshgen.cube_cavity(n, jitter=0.1)
-    hm = pe.mesh_from_arrays(xyz, tets, tp, tris, trp)
-    bc = pe.build_edge_pec(hm, 1)
-    arr = mesh_arrays(hm)
-    dm = cabi.DeviceMesh(ctx, arr["xyz"], arr["tet_nodes"], arr["tet_edges"], arr["tet_orient"], arr["tet_phys"], arr["edge_nodes"])
-    flags = np.zeros(hm.num_edges(), dtype=np.uint8)
-    flags[np.asarray(bc.dirichlet_edges, dtype=np.int64)] = 1
-    pe_idx = np.nonzero(flags)[0].astype(np.int32)
-    sysd = cabi.DeviceSystem.from_mesh(dm, pe_idx, pe_idx, n_matrix=1, n_rhs=1)
+    t_gen = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    dm, info = cabi.device_mesh_from_conn(ctx, xyz, tets, tp, tris)
+    flags = cabi.pec_flags_from_tris(info["edges"].shape[0], info["tri_edges"], trp, 1)
+    sysd = cabi.DeviceSystem.from_mesh(dm, n_matrix=1, n_rhs=1)
     sysd.set_dirichlet(flags)
     setup_s = time.perf_counter() - t0
+    n_tet, n_node = int(tets.shape[0]), int(xyz.shape[0])
+    del xyz, tets, tris, info
     h = 1.0 / n
     omega = (2 * math.pi / (10 * h)) * C0  # k0 h = 2 pi / 10
     mats, keep = cabi.make_materials(len(dm.slot_tags))
@@ -248,7 +265,7 @@ def cube_extras(ctx, pe, n: int):
     b[flags == 1] = 0
     sysd.rhs_set(0, b)
     sysd.x_set(0, b)
-    n_tet, n_node, m, nnz = hm.num_tets(), hm.num_nodes(), sysd.m, sysd.nnz
+    m, nnz = sysd.m, sysd.nnz
     ms_asm = sysd.bench_kernel(3, 10)
     ms_spmv = sysd.bench_kernel(0, 20)
     ms_bicg = sysd.bench_kernel(1, 10)
@@ -260,18 +277,35 @@ def cube_extras(ctx, pe, n: int):
     b_bicg = 2 * b_spmv + 21 * 16.0 * m
     b_cocg = b_spmv + 10 * 16.0 * m
     out = {
-        "mesh": {"n": n, "tets": n_tet, "nodes": n_node, "edges": m, "nnz": nnz, "host_setup_s": round(setup_s, 2)},
+        "mesh": {"n": n, "tets": n_tet, "nodes": n_node, "edges": m, "nnz": nnz, "free_unknowns": int((flags == 0).sum()),
+                 "mesh_generation_s": round(t_gen, 2), "device_setup_s": round(setup_s, 2)},
         "fp64_fma_probe_tflops": fp64_tflops,
         "assembly": {"ms": ms_asm, "mtets_per_s": n_tet / ms_asm / 1e3, "algorithmic_gb": b_asm / 1e9, "gbs": b_asm / ms_asm / 1e6,
-                     "fp64_gflop_model": 6 * n_tet * 300 / 1e9,
-                     "kernel": "k_assemble_volume_s (rank-major schedule, real chunk image)",
-                     "note": "row-gather: one element row per (edge, tet) incidence (~300 FP64 flop x 6 per tet) added into a shared-memory "
-                             "chunk image; bound by gather latency and the L1 data pipe, not by HBM (profiles/prof_asm_r01s.md)"},
+                     "fp64_gflop_model": 6 * n_tet * 300 / 1e9, "kernel": "k_assemble_volume_s (rank-major schedule, real chunk image)"},
         "spmv": {"ms": ms_spmv, "algorithmic_gb": b_spmv / 1e9, "gbs": b_spmv / ms_spmv / 1e6,
                  "kernel": "k_spmv_tma (CSR-stream, matrix stream by cp.async.bulk + mbarrier, bank-skewed products)"},
         "bicgstab_jacobi_iteration": {"ms": ms_bicg, "algorithmic_gb": b_bicg / 1e9, "gbs": b_bicg / ms_bicg / 1e6},
         "cocg_jacobi_iteration": {"ms": ms_cocg, "algorithmic_gb": b_cocg / 1e9, "gbs": b_cocg / ms_cocg / 1e6},
     }
+    for k in ("assembly", "spmv", "bicgstab_jacobi_iteration", "cocg_jacobi_iteration"):
+        out[k]["frac_of_hbm_peak"] = out[k]["gbs"] / hbm_peak
+    if solve_freq > 0:
+        om_s = 2 * math.pi * solve_freq
+        sysd.assemble_volume([om_s], mats)
+        sysd.rhs_set(0, b)
+        ctx.sync()
+        ctx.timer_start()
+        res = sysd.solve(precond=cabi.PRECOND_AUX, tol=1e-10, max_iterations=40000, symmetric=True)[0]
+        ms_solve = ctx.timer_stop()
+        x = sysd.x_get(0)
+        y = sysd.spmv(0, x)
+        b_aux = b_spmv + (10 * 16.0 + 2 * 16.0) * m + 3 * 16.0 * n_node + 2 * m * 8.0  # + w gather/scatter, gradient index lists
+        it = max(1, res["iters"])
+        out["solve"] = {"frequency_hz": solve_freq, "k0h": om_s / C0 * h, "method": "COCG + auxiliary-space Jacobi (multi-kernel path, device-side scalars)",
+                        "tolerance": 1e-10, "iters": res["iters"], "converged": bool(res["converged"]), "residual": res["residual"],
+                        "true_residual_host_check": float(np.linalg.norm(b - y) / np.linalg.norm(b)), "seconds": ms_solve / 1e3,
+                        "ms_per_iteration": ms_solve / it, "algorithmic_gb_per_iteration": b_aux / 1e9, "gbs": b_aux / (ms_solve / it) / 1e6,
+                        "frac_of_hbm_peak": b_aux / (ms_solve / it) / 1e6 / hbm_peak}
     sysd.close()
     dm.close()
     return out
@@ -288,6 +322,37 @@ def ncu_traffic(kernel: str, n_matrix: int):
         return None
 
 
+def wr90_setup(pe):
+    import numpy as np
+
+    z = np.load(os.path.join(ROOT, "tests", "golden", "rect_waveguide.npz"))
+    hm = pe.mesh_from_arrays(z["xyz"], z["tet_conn"], z["tet_phys"], z["tri_conn"], z["tri_phys"], z["node_ids"].tolist())
+    bc = pe.build_edge_pec(hm, 1)
+    dims = pe.RectWaveguidePort(WR90_A, WR90_B)
+    kc_sq = (math.pi / WR90_A) ** 2
+    ports = [pe.build_wave_port_2d(hm, tag, pe.solve_te10_mode(dims, 10e9), set(bc.dirichlet_edges), kc_sq) for tag in (2, 3)]
+    return hm, bc, ports
+
+
+def c1_latency(pe, hm, bc, ports, reps=20):
+    """C1 (BASELINE configs[0], tests/benchmark_wr90.cpp:97-180): ONE frequency, 10 GHz, through the reference's own
+    per-frequency API calculate_sparams_eigenmode (what waveguide.py:394-433 loops over): latency, iterations, us/iteration."""
+    p = pe.MaxwellParams()
+    p.omega = 2 * math.pi * 10e9
+    for _ in range(3):
+        S = pe.calculate_sparams_eigenmode(hm, p, bc, ports)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        S = pe.calculate_sparams_eigenmode(hm, p, bc, ports)
+    dt = (time.perf_counter() - t0) / reps
+    S2, st = pe.calculate_sparams_eigenmode_sweep(hm, p, bc, ports, [10e9])
+    it = max(1, max(st.iterations))
+    return {"api": "pyedgefem.calculate_sparams_eigenmode (host buffers in, S out; device mesh cached after the first call)",
+            "frequency_hz": 10e9, "ms_per_point": 1e3 * dt, "points_per_s": 1.0 / dt, "krylov_iterations": [int(v) for v in st.iterations],
+            "device_ms": st.device_ms, "us_per_iteration_device": 1e3 * st.device_ms / it,
+            "abs_s11": abs(S[0][0]), "abs_s21": abs(S[1][0]), "kernel_launches": int(st.kernel_launches)}
+
+
 def run_b200(a):
     import numpy as np
 
@@ -297,15 +362,12 @@ def run_b200(a):
     os.environ.setdefault("EDGEFEM_B200_DEVICE", str(local))
     dist = None
     if world > 1:
-        # stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) out of it
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
         import torch
         import torch.distributed as dist
 
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    from edgefem_b200 import cabi, load_pyedgefem
+    from edgefem_b200 import cabi, load_pyedgefem, sharding
 
     pe = load_pyedgefem()  # fails loudly if the extension was not built
     ctx = cabi.Ctx(local)
@@ -315,33 +377,42 @@ def run_b200(a):
             peaks = json.load(fjs)
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    if a.workload != "wr90":
+        return run_workload(a, ctx, pe, hbm_peak, peak_src, rank, world, dist)
 
-    z = np.load(os.path.join(ROOT, "tests", "golden", "rect_waveguide.npz"))
-    hm = pe.mesh_from_arrays(z["xyz"], z["tet_conn"], z["tet_phys"], z["tri_conn"], z["tri_phys"], z["node_ids"].tolist())
-    bc = pe.build_edge_pec(hm, 1)
-    dims = pe.RectWaveguidePort(WR90_A, WR90_B)
-    kc_sq = (math.pi / WR90_A) ** 2
-    ports = [pe.build_wave_port_2d(hm, tag, pe.solve_te10_mode(dims, 10e9), set(bc.dirichlet_edges), kc_sq) for tag in (2, 3)]
-    # weak scaling: rank r sweeps its own 256-point sub-band of 8-12 GHz
-    allf = np.linspace(F_LO, F_HI, a.points * world)
-    freqs = list(allf[rank::world])  # == sharding.shard_indices(len(allf), rank, world)
+    hm, bc, ports = wr90_setup(pe)
+    strong = a.scaling == "strong"
+    n_total = a.points if strong else a.points * world
+    allf = np.linspace(F_LO, F_HI, n_total)
+    freqs = list(allf[rank::world])  # == sharding.shard_indices(len(allf), rank, world): round-robin keeps iteration counts balanced
+    dev = None
+    if dist is not None:
+        import torch
+
+        dev = torch.device("cuda", local)
 
     def barrier():
         ctx.sync()
         if dist is not None:
             dist.barrier()
 
+    def step_resident():
+        S, res = rs.step()
+        # the one collective of the path: gather of the P x P S-matrices (16 P^2 bytes per point), inside the timed region
+        S_all = sharding.gather_sweep(S, n_total, rank, world, dist=dist, device=dev) if dist is not None else S
+        return S, S_all, res
+
     # ---------------- resident ("value") ----------------
     rs = ResidentSweep(ctx, pe, hm, bc, ports, freqs)
     for _ in range(a.warmup):
-        rs.step()
+        step_resident()
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = ctx.launch_count()
     ctx.timer_start()
     for _ in range(a.steps):
-        S, res = rs.step()
+        S, S_all, res = step_resident()
     ms_total = ctx.timer_stop()
     launches = ctx.launch_count() - launches0
     barrier()
@@ -352,32 +423,39 @@ def run_b200(a):
         t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
-        from edgefem_b200 import sharding
-
-        S_all = sharding.gather_sweep(S, a.points * world, rank, world, dist=dist, device=torch.device("cuda", local))  # NCCL all-gather
-        assert S_all.shape[0] == a.points * world and np.all(np.isfinite(S_all))
+        assert S_all.shape[0] == n_total and np.all(np.isfinite(S_all))
     ms_step = ms_total / a.steps
-    value = a.points * world / (ms_step / 1000.0)
+    value = n_total / (ms_step / 1000.0)
     iters = [r["iters"] for r in res]
     assert all(r["converged"] for r in res), "a solve did not converge"
     # roofline of the dominant kernel, timed live with CUDA events on the launching stream (the library's ctx stream).
-    # The whole batched solve is ONE launch of the persistent kernel k_cocg_small<2>: one CTA per matrix, both
-    # right-hand sides.  Algorithmic bytes per COCG iteration of one matrix with P rhs (B_spmv + 10*16*m per
-    # system; the P systems of a matrix share the value/index stream): nnz*20 + 4m + P*(32m + 160m).
+    # The whole batched solve is ONE launch of a persistent kernel.  Algorithmic bytes per COCG iteration of one matrix with
+    # P rhs (B_spmv + 10*16*m per system; the P systems of a matrix share the value/index stream):
+    # nnz*20 + 4m + P*(32m + 160m), over the free unknowns the kernels iterate on.
     F, P, nnz, m = rs.F, rs.P, rs.nnz, rs.m
-    nnz_f, m_f = rs.nnz_free, rs.m_free  # what the persistent kernel streams: entries / rows of the free unknowns
+    nnz_f, m_f = rs.nnz_free, rs.m_free
     ms_kernel = rs.sys.last_solve_kernel_ms()
+    cl_c, cl_nr, cl_n = rs.sys.last_solve_shape()
     it_per_matrix = [max(iters[f * P:(f + 1) * P]) for f in range(F)]
     if ms_kernel > 0:
-        solve_bytes = float(sum(it_per_matrix)) * (nnz_f * 20.0 + 4.0 * m_f + P * 192.0 * m_f)
-        roof = {"bound": "hbm", "kernel": "k_cocg_small<2> (persistent COCG + aux-space Jacobi, SELL-32 SpMV from smem-resident p; %d matrices x %d rhs in one launch)" % (F, P),
-                "achieved": solve_bytes / ms_kernel / 1e6, "peak": hbm_peak, "unit": "GB/s", "frac": solve_bytes / ms_kernel / 1e6 / hbm_peak,
-                "traffic": ncu_traffic("k_cocg_small", F), "peak_source": peak_src, "algorithmic_bytes_per_launch": solve_bytes, "ms_per_launch": ms_kernel,
-                "launches_per_step": 1, "share_of_step": ms_kernel / ms_step,
-                "free_unknowns": m_f, "free_nnz": nnz_f,
-                "note": "byte model over the %d free unknowns / %d free entries the kernel iterates on (Dirichlet rows and columns are dropped); "
-                        "vectors r,q,x stay L2-resident per CTA and p lives in shared memory, so part of the algorithmic bytes never reaches HBM" % (m_f, nnz_f)}
-    else:  # multi-kernel path (EDGEFEM_B200_NO_PERSISTENT=1): batched CSR SpMV dominates
+        if cl_c:
+            kname, kkey = ("k_cocg_cluster<%d> (persistent COCG + aux-space Jacobi, one cluster of %d CTAs per job, matrix slice resident in shared memory, "
+                           "DSMEM halo/nodal exchange; %d resident clusters)" % (cl_nr, cl_c, cl_n)), "k_cocg_cluster"
+            per_job = nnz_f * 20.0 + 4.0 * m_f + cl_nr * 192.0 * m_f
+            jobs_it = float(sum(it_per_matrix)) if cl_nr == P else float(sum(iters))
+            solve_bytes = jobs_it * per_job
+            note = ("byte model of the same iteration streamed from memory; this kernel keeps matrix, vectors and index lists on chip (shared memory + "
+                    "registers), so HBM sees only the per-job matrix load and b/x: it is bound by shared-memory wavefronts and cluster barriers, not HBM")
+        else:
+            kname, kkey = ("k_cocg_small<2> (persistent COCG + aux-space Jacobi, SELL-32 SpMV from smem-resident p; %d matrices x %d rhs in one launch)" % (F, P)), "k_cocg_small"
+            solve_bytes = float(sum(it_per_matrix)) * (nnz_f * 20.0 + 4.0 * m_f + P * 192.0 * m_f)
+            note = ("byte model over the %d free unknowns / %d free entries the kernel iterates on (Dirichlet rows and columns are dropped); vectors r,q,x stay "
+                    "L2-resident per CTA and p lives in shared memory, so part of the algorithmic bytes never reaches HBM (see traffic)" % (m_f, nnz_f))
+        roof = {"bound": "hbm", "kernel": kname, "achieved": solve_bytes / ms_kernel / 1e6, "peak": hbm_peak, "unit": "GB/s",
+                "frac": solve_bytes / ms_kernel / 1e6 / hbm_peak, "traffic": ncu_traffic(kkey, F), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": solve_bytes, "ms_per_launch": ms_kernel, "launches_per_step": 1, "share_of_step": ms_kernel / ms_step,
+                "free_unknowns": m_f, "free_nnz": nnz_f, "note": note}
+    else:  # multi-kernel path (EDGEFEM_B200_NO_PERSISTENT=1 and EDGEFEM_B200_CLUSTER=0): batched CSR SpMV dominates
         ms_spmv = rs.sys.bench_kernel(0, 50)
         spmv_bytes = F * nnz * 16.0 + nnz * 4.0 + (m + 1) * 4.0 + F * P * m * 32.0
         roof = {"bound": "hbm", "kernel": "k_spmv<16,2,*> (batched CSR complex128 SpMV, %d matrices x %d rhs)" % (F, P),
@@ -386,16 +464,22 @@ def run_b200(a):
 
     # ---------------- end to end through the public API ----------------
     p = pe.MaxwellParams()
-    for _ in range(max(1, min(a.warmup, 2))):
+
+    def step_e2e():
         pe.b200_clear_cache()
-        pe.calculate_sparams_eigenmode_sweep(hm, p, bc, ports, freqs)
+        S2, st = pe.calculate_sparams_eigenmode_sweep(hm, p, bc, ports, freqs)
+        S2 = np.array(S2)
+        S2_all = sharding.gather_sweep(S2, n_total, rank, world, dist=dist, device=dev) if dist is not None else S2
+        return S2, S2_all, st
+
+    for _ in range(max(1, min(a.warmup, 2))):
+        step_e2e()
     barrier()
     t0 = time.perf_counter()
     e2e_steps = max(1, min(a.steps, 3))
     h2d = d2h = 0
     for _ in range(e2e_steps):
-        pe.b200_clear_cache()
-        S2, st = pe.calculate_sparams_eigenmode_sweep(hm, p, bc, ports, freqs)
+        S2, S2_all, st = step_e2e()
         h2d, d2h = st.h2d_bytes, st.d2h_bytes
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
@@ -405,40 +489,142 @@ def run_b200(a):
         t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    assert np.max(np.abs(np.array(S2) - S)) < 1e-6, "public API and resident path disagree"
+    assert np.max(np.abs(S2 - S)) < 1e-6, "public API and resident path disagree"
+
+    extras = {}
+    if rank == 0:
+        try:
+            extras["c1_single_frequency"] = c1_latency(pe, hm, bc, ports)
+        except Exception as e:
+            extras["c1_single_frequency"] = {"error": repr(e)}
+    rs.close()
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    if a.cube_n > 0 and world == 1:
+        try:
+            extras["c5_cube"] = cube_extras(ctx, a.cube_n, a.cube_freq, hbm_peak)
+        except Exception as e:  # extras never invalidate the headline number
+            extras["c5_cube"] = {"error": repr(e)}
+    cores = os.cpu_count() or 1
+    cpu1 = cpu_baseline(a.cpu_sample, 1) if a.cpu_sample > 0 else None  # --cpu-sample 0: profiling runs skip the CPU leg
+    line = {
+        "metric": "wr90_sweep_freq_points_per_s", "value": value, "unit": "points/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "WR-90 eigenmode S-parameter sweep 8-12 GHz, %d points total x 2 ports, %s over %d GPU(s) (rect_waveguide fixture: 4227 tets, "
+                               "5745 edges, nnz 85113), tol 1e-10, COCG + auxiliary-space Jacobi; S all-gather inside the timed region" %
+                               (n_total, "sharded round-robin" if strong else "one 256-point sub-band per GPU", world),
+                   "points_per_gpu": len(freqs), "total_points": n_total, "solves_per_step": n_total * 2,
+                   "l2": "no flush: the per-step working set (matrix values + Krylov vectors of %d systems, %.0f MB per GPU) is %s" %
+                         (len(freqs) * 2, (len(freqs) * nnz * 16.0 * 2 + len(freqs) * 2 * m * 16.0 * 9) / 1e6,
+                          "larger than the 126 MB L2" if len(freqs) >= 64 else "re-assembled from the mesh every step (values are rewritten, not re-read)"),
+                   "krylov_iterations": {"min": int(min(iters)), "median": int(sorted(iters)[len(iters) // 2]), "max": int(max(iters))},
+                   "solver_launch": {"cluster_ctas": cl_c, "rhs_per_job": cl_nr, "resident_clusters": cl_n}},
+        "roofline": roof,
+        "cpu_baseline": {"value": cpu1, "unit": "points/s", "cores": 1, "kind": "port",
+                         "sample": "%d of 256 points, 1 process: CPU oracle (numpy/scipy restatement of the reference path, SuperLU solves; a stand-in, "
+                                   "not Eigen -- Eigen is not installable here); host has %d cores" % (a.cpu_sample, cores)},
+        "e2e": {"value": n_total / e2e_s, "unit": "points/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": 1000.0 * e2e_s, "api": "pyedgefem.calculate_sparams_eigenmode_sweep (mesh cache cleared every step) + S all-gather"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "extras": extras,
+    }
+    _LINE.append(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def run_workload(a, ctx, pe, hbm_peak, peak_src, rank, world, dist):
+    """The other named workloads of BASELINE.json, one JSON line each (rank 0; replicas only -- these are single-GPU lines)."""
+    import numpy as np
+    from edgefem_b200 import meshgen
 
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
-    extras = {}
-    if a.cube_n > 0:
-        try:
-            extras = cube_extras(ctx, pe, a.cube_n)
-            for k in ("assembly", "spmv", "bicgstab_jacobi_iteration", "cocg_jacobi_iteration"):
-                extras[k]["frac_of_hbm_peak"] = extras[k]["gbs"] / hbm_peak
-        except Exception as e:  # extras never invalidate the headline number
-            extras = {"error": repr(e)}
-    cores = os.cpu_count() or 1
-    cpu1 = cpu_baseline(a.cpu_sample, 1) if a.cpu_sample > 0 else None  # --cpu-sample 0: profiling runs skip the CPU leg
-    line = {
-        "metric": "wr90_sweep_freq_points_per_s", "value": value, "unit": "points/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "WR-90 eigenmode S-parameter sweep 8-12 GHz, %d points/GPU x 2 ports (rect_waveguide fixture: 4227 tets, 5745 edges, "
-                               "nnz 85113), tol 1e-10, COCG + auxiliary-space Jacobi" % a.points,
-                   "points_per_gpu": a.points, "total_points": a.points * world, "solves_per_step": a.points * 2 * world,
-                   "l2": "inputs larger than L2 (349 MB values + 330 MB vectors per GPU); no flush",
-                   "krylov_iterations": {"min": int(min(iters)), "median": int(sorted(iters)[len(iters) // 2]), "max": int(max(iters))}},
-        "roofline": roof,
-        "cpu_baseline": {"value": cpu1, "unit": "points/s", "cores": 1, "kind": "port",
-                         "sample": "%d of 256 points, 1 process: oracle (numpy/scipy restatement of the reference path, SuperLU solves); "
-                                   "host has %d cores" % (a.cpu_sample, cores)},
-        "e2e": {"value": a.points * world / e2e_s, "unit": "points/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": 1000.0 * e2e_s, "api": "pyedgefem.calculate_sparams_eigenmode_sweep (mesh cache cleared every step)"},
-        "gpu_launches": int(launches),
-        "clocks": clocks,
-        "extras": extras,
-    }
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    sampler.start()
+    line = {"n_gpus": 1, "steps": a.steps, "warmup": a.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "cpu_baseline": None, "roofline": None}
+    if a.workload == "c1":
+        hm, bc, ports = wr90_setup(pe)
+        r = c1_latency(pe, hm, bc, ports, reps=max(5, a.steps))
+        line.update({"metric": "wr90_single_frequency_points_per_s", "value": r["points_per_s"], "unit": "points/s", "ms_per_step": r["ms_per_point"],
+                     "config": {"workload": "C1: WR-90 S-parameters at 10 GHz (tests/benchmark_wr90.cpp) through calculate_sparams_eigenmode"},
+                     "e2e": {"value": r["points_per_s"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 64}, "extras": r,
+                     "gpu_launches": r["kernel_launches"]})
+    elif a.workload == "cube":
+        ex = cube_extras(ctx, a.cube_n, a.cube_freq, hbm_peak)
+        line.update({"metric": "c5_assembly_mtets_per_s", "value": ex["assembly"]["mtets_per_s"], "unit": "Mtets/s", "ms_per_step": ex["assembly"]["ms"],
+                     "config": {"workload": "C5: refined PEC cube cavity n=%d, single frequency: assembly + SpMV + converged Krylov solve" % a.cube_n},
+                     "roofline": {"bound": "hbm", "kernel": ex["assembly"]["kernel"], "achieved": ex["assembly"]["gbs"], "peak": hbm_peak, "unit": "GB/s",
+                                  "frac": ex["assembly"]["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src},
+                     "e2e": None, "extras": ex, "gpu_launches": 10})
+    else:
+        launches0 = pe.b200_launch_count()
+        if a.workload == "patch":
+            xyz, tets, tp, tris, trp, info = meshgen.patch_antenna(hmax_scale=0.7)
+            hm = pe.mesh_from_arrays(xyz, tets, tp, tris, trp)
+            bc = pe.BC()
+            for tag in (1, 2, 3, 4, 10):
+                bc.merge(pe.build_edge_pec(hm, tag))
+            freqs = list(np.linspace(2.2e9, 2.7e9, 11))
+            opts = pe.SolveOptions()
+            opts.use_direct = True
+
+            def point(f):
+                ph = pe.MaxwellParams()
+                ph.omega = 2 * math.pi * f
+                ph.use_abc = True
+                ph.abc_surface_tags = {50}
+                ph.set_eps_r_region(110, complex(4.4, -4.4 * 0.02))
+                cfg = pe.LumpedPortConfig()
+                cfg.surface_tag, cfg.z0, cfg.e_direction = 5, 50.0, [1.0, 0.0, 0.0]
+                ports = pe.normalize_port_weights(hm, ph, bc, [pe.build_lumped_port(hm, cfg)], opts)
+                return pe.calculate_sparams(hm, ph, bc, ports, opts)[0][0]
+
+            name = ("C3: probe-fed patch antenna on FR-4 (28.6 x 37.3 mm, h 1.6 mm, probe -9 mm), lumped port + ABC, 11 points 2.2-2.7 GHz, normalize_port_weights "
+                    "+ calculate_sparams per point (stacked_patch.py:503-561); structured mesh %d tets, %d edges" % (hm.num_tets(), hm.num_edges()))
+        else:
+            h_air = C0 / 10e9 / 2
+            xyz, tets, tp, tris, trp = meshgen.unit_cell(px=5e-3, py=5e-3, h_sub=0.5e-3, h_air=h_air, nx=8, ny=8, nz_sub=2, nz_air=8, patch=(4e-3, 4e-3))
+            hm = pe.mesh_from_arrays(xyz, tets, tp, tris, trp)
+            bc = pe.build_edge_pec(hm, 1)
+            freqs = list(np.linspace(8e9, 12e9, 5))
+
+            def point(f):
+                omega = 2 * math.pi * f
+                pbc = pe.build_periodic_pairs(hm, 5, 6, [5e-3, 0.0, 0.0])
+                pe.set_floquet_phase(pbc, [0.0, 0.0])
+                ph = pe.MaxwellParams()
+                ph.omega = omega
+                ph.eps_r_regions = {100: complex(3.5, 0.0), 101: complex(1.0, 0.0)}
+                ph.use_port_abc = True
+                mdl = pe.materials.DrudeLorentzMaterial(3.5, 2 * math.pi * 4e9, 2 * math.pi * 0.5e9)
+                mdl.add_lorentz_pole(0.8, 2 * math.pi * 15e9, 2 * math.pi * 1e9)
+                ph.set_eps_model(100, mdl)
+                hs = pe.extract_surface_mesh(hm, 4)
+                mode = pe.solve_port_eigens(hs.mesh, 1, omega, 1.0, 1.0, pe.ModePolarization.TE)[0]
+                return pe.calculate_sparams_periodic(hm, ph, bc, pbc, [pe.build_wave_port(hm, hs, mode)])[0][0]
+
+            name = ("C4: periodic unit cell 5 x 5 mm, Bloch phase along x (normal incidence), Drude-Lorentz substrate, modal top port + port ABC, 5 points "
+                    "8-12 GHz (unit_cell.py:691-770); %d tets, %d edges" % (hm.num_tets(), hm.num_edges()))
+        for _ in range(max(1, min(a.warmup, 2))):
+            vals = [point(f) for f in freqs]
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            vals = [point(f) for f in freqs]
+        dt = (time.perf_counter() - t0) / a.steps
+        assert all(np.isfinite(v) for v in vals), "a solve did not converge"
+        line.update({"metric": "%s_sweep_freq_points_per_s" % a.workload, "value": len(freqs) / dt, "unit": "points/s", "ms_per_step": 1e3 * dt,
+                     "config": {"workload": name},
+                     "e2e": {"value": len(freqs) / dt, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 16 * len(freqs),
+                             "api": "public per-frequency API from host buffers (wall clock)"},
+                     "extras": {"abs_s11": [abs(v) for v in vals]}, "gpu_launches": int((pe.b200_launch_count() - launches0) / (a.steps + max(1, min(a.warmup, 2))))})
+    line["clocks"] = sampler.stop()
     _LINE.append(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libedgefem_b200.so")
 
 EFB_OK = 0
-METHOD_AUTO, METHOD_BICGSTAB, METHOD_COCG = 0, 1, 2
+METHOD_AUTO, METHOD_BICGSTAB, METHOD_COCG, METHOD_DIRECT = 0, 1, 2, 3
 PRECOND_JACOBI, PRECOND_AUX, PRECOND_NONE = 0, 1, 2
 MODEL_NONE, MODEL_DEBYE, MODEL_LORENTZ, MODEL_DRUDE, MODEL_DRUDE_LORENTZ = 0, 1, 2, 3, 4
 PML_NONE, PML_UNIFORM, PML_TENSOR = 0, 1, 2
@@ -114,6 +114,9 @@ SIGNATURES = {
     "efb_x_set": (C.c_int, [C.c_void_p, C.c_int32, f64p]),
     "efb_x_recover": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, i32p, i32p, f64p]),
     "efb_solve": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(SolveOpts), C.POINTER(SolveResult)]),
+    "efb_solve_direct": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(SolveResult)]),
+    "efb_solve_direct_limit": (C.c_int, []),
+    "efb_clear_caches": (None, []),
     "efb_system_last_solve_kernel_ms": (C.c_int, [C.c_void_p, f64p]),
     "efb_system_last_solve_shape": (C.c_int, [C.c_void_p, i32p, i32p, i32p]),
     "efb_debug_cluster_plan_build": (C.c_int, [C.c_int32, i32p, i32p, u8p, C.c_int32, i32p, C.c_int32, C.POINTER(C.c_void_p)]),
@@ -492,6 +495,13 @@ class DeviceSystem:
         o = SolveOpts(method, precond, tol, max_iterations, check_every, 1 if symmetric else 0, 1 if zero_initial_guess else 0, max_restarts, 0)
         res = (SolveResult * (count * self.n_rhs))()
         self.ctx.check(self.ctx.lib.efb_solve(self.h, first, count, C.byref(o), res), "efb_solve")
+        return [dict(iters=r.iters, converged=bool(r.converged), method=r.method, precond=r.precond, residual=r.residual) for r in res]
+
+    def solve_direct(self, first=0, count=None):
+        """Dense LU with partial pivoting on the device (efb_solve_direct): the robust fallback for small systems."""
+        count = self.n_matrix - first if count is None else count
+        res = (SolveResult * (count * self.n_rhs))()
+        self.ctx.check(self.ctx.lib.efb_solve_direct(self.h, first, count, res), "efb_solve_direct")
         return [dict(iters=r.iters, converged=bool(r.converged), method=r.method, precond=r.precond, residual=r.residual) for r in res]
 
     def last_solve_kernel_ms(self) -> float:

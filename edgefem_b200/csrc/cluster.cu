@@ -20,6 +20,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <memory>
+#include <mutex>
 
 #include "cluster_plan.hpp"
 #include "solve_internal.cuh"
@@ -48,7 +50,10 @@ struct ClusterDev {
   const uint32_t *nsrc_item;
 };
 
-struct ClusterPlanDev {  // owned by a System (cl_plan)
+struct ClusterPlanDev {  // shared by the systems with the same pattern / flags / gradient and the plan cache
+  ~ClusterPlanDev() {
+    for (void *b : blocks) dfree(b);
+  }
   ClusterPlanHost h;
   std::vector<uint16_t> n2e_ell;
   std::vector<uint32_t> nsrc_ell;
@@ -603,11 +608,37 @@ k_cocg_cluster(const SolveDev D, const ClusterDev K, int first_matrix, int n_job
 
 // ---------------------------------------------------------------- host side
 void cluster_plan_free(System *S) {
-  ClusterPlanDev *P = (ClusterPlanDev *)S->cl_plan;
-  if (!P) return;
-  for (void *b : P->blocks) dfree(b);
-  delete P;
+  if (!S->cl_plan) return;
+  delete (std::shared_ptr<ClusterPlanDev> *)S->cl_plan;  // the device arrays go when the last holder (system or cache) lets go
   S->cl_plan = nullptr;
+}
+
+namespace {
+struct PlanCacheEntry {
+  int device, m, C;
+  long long nnz;
+  uint64_t hash;
+  bool aux;
+  std::shared_ptr<ClusterPlanDev> plan;
+};
+std::mutex g_plan_mu;
+std::vector<PlanCacheEntry> g_plan_cache;  // most recent first, at most 6
+}  // namespace
+
+static std::shared_ptr<ClusterPlanDev> plan_cache_find(int device, uint64_t hash, int m, long long nnz, int C, bool aux) {
+  std::lock_guard<std::mutex> lk(g_plan_mu);
+  for (auto &e : g_plan_cache)
+    if (e.device == device && e.hash == hash && e.m == m && e.nnz == nnz && e.C == C && e.aux == aux) return e.plan;
+  return nullptr;
+}
+static void plan_cache_put(int device, uint64_t hash, int m, long long nnz, int C, bool aux, std::shared_ptr<ClusterPlanDev> p) {
+  std::lock_guard<std::mutex> lk(g_plan_mu);
+  g_plan_cache.insert(g_plan_cache.begin(), PlanCacheEntry{device, m, C, nnz, hash, aux, std::move(p)});
+  if (g_plan_cache.size() > 6) g_plan_cache.pop_back();
+}
+void cluster_plan_cache_clear() {
+  std::lock_guard<std::mutex> lk(g_plan_mu);
+  g_plan_cache.clear();
 }
 
 template <typename T>
@@ -735,7 +766,7 @@ int run_krylov_cluster(SolvePlan &P, const efb_solve_opts *o, bool zero_x, bool 
   const int n_rhs = S->n_rhs;
   int nr_want = (n_rhs % 2 == 0) ? 2 : 1;
   if (const char *e = getenv("EDGEFEM_B200_CLUSTER_NR")) nr_want = std::max(1, std::min(nr_want, atoi(e)));
-  ClusterPlanDev *PL = (ClusterPlanDev *)S->cl_plan;
+  ClusterPlanDev *PL = S->cl_plan ? ((std::shared_ptr<ClusterPlanDev> *)S->cl_plan)->get() : nullptr;
   const uint8_t *dirp = (int)S->h_dir.size() == S->m ? S->h_dir.data() : nullptr;
   auto fits = [&](const ClusterPlanHost &H, int nr, int *rpt_out, int *nth_out) {
     if (cluster_smem_bytes(nr, H) > (size_t)dev_smem) return false;
@@ -751,45 +782,88 @@ int run_krylov_cluster(SolvePlan &P, const efb_solve_opts *o, bool zero_x, bool 
   };
   int nr = 0, rpt = 1, nth = 0;
   const int n_matrix = P.n_matrix;
-  if (S->cl_dirty || !PL || PL->h.aux != want_aux || (forced > 0 && PL->h.C != forced)) {
+  // free unknowns / free entries: cheap size estimate of the smallest cluster that can hold the system
+  int mc = 0;
+  long long nnz_free = 0;
+  for (int r = 0; r < S->m; ++r) {
+    if (dirp && dirp[r]) continue;
+    ++mc;
+    for (int k = S->h_rowptr[r]; k < S->h_rowptr[r + 1]; ++k) nnz_free += !(dirp && dirp[S->h_colidx[k]]);
+  }
+  if (mc == 0) return EFB_OK;
+  auto est_bytes = [&](int C, int nrp) {  // per CTA: matrix slice (+10 % padding) + window (own + ~0.8 own of halo) + q, z + lists
+    const double own = (double)mc / C, halo = C > 1 ? 0.8 * own + 64 : 0.0;
+    return nnz_free * 1.1 * 18.0 / C + (own + halo) * nrp * 16.0 + own * nrp * 32.0 + (want_aux ? own * 0.4 * (nrp * 48.0 + 80.0) : 0.0) + halo * 6.0 + 6000.0;
+  };
+  int C_est = 0;
+  for (int C = 1; C <= CL_MAX_C; C *= 2)
+    if (est_bytes(C, 1) <= 0.97 * dev_smem && (mc + C - 1) / C <= 4 * CL_THREADS_MAX) {
+      C_est = C;
+      break;
+    }
+  if (forced > 0) C_est = forced;
+  if (C_est == 0) return EFB_OK;  // does not fit in 8 SMs: the other solver paths take it
+  const int nn1 = want_aux ? S->n_node : 0;
+  const bool one_cta_ok = S->m <= 16384 && ((size_t)mc * 16 + (size_t)nn1 * 16 + 4096) <= (size_t)dev_smem;
+  auto resident_est = [&](int C) { return std::max(1, c->sm_count / C - (C == 8 ? 3 : C == 4 ? 4 : 0)); };
+  if (forced < 0 && one_cta_ok) {
+    // Latency or throughput?  A cluster job is ~10x faster than a one-CTA job of k_cocg_small (measured on WR-90:
+    // 7.9 us per rhs-iteration on 8 SMs against 85 us per two-rhs iteration on one), but only ~15 clusters of 8 are
+    // resident against 148 CTAs, and a one-CTA job carries both right-hand sides: big batches (the 256-point sweep)
+    // stay on the one-CTA kernel when it applies, small ones (one frequency, the shards of a strong-scaled sweep) run
+    // here.  Systems the one-CTA kernel cannot take (p does not fit in its shared memory) always run here.  Decided
+    // BEFORE any plan is built: the plan costs milliseconds of host time.
+    const double rounds_cl = std::ceil((double)n_matrix * n_rhs / resident_est(C_est));
+    const double rounds_1 = std::ceil((double)n_matrix / c->sm_count) * 10.0 * (n_rhs >= 2 ? 1.0 : 0.6);
+    if (rounds_cl > rounds_1) return EFB_OK;
+  }
+  // few jobs: a larger cluster costs nothing (idle SMs otherwise) and shortens every job
+  int C_want = C_est;
+  if (forced <= 0)
+    while (C_want * 2 <= CL_MAX_C && (long long)n_matrix * n_rhs * C_want * 2 <= c->sm_count) C_want *= 2;
+  if (S->cl_dirty || !PL || PL->h.aux != want_aux || PL->h.C < C_want || (forced > 0 && PL->h.C != forced)) {
     cluster_plan_free(S);
     PL = nullptr;
-    // smallest cluster that fits with both right-hand sides, else with one; few jobs: grow the cluster for latency
-    ClusterPlanHost best;
-    bool have = false;
-    for (int pass = 0; pass < 2 && !have; ++pass) {
-      const int nrp = pass == 0 ? nr_want : 1;
-      if (pass == 1 && nr_want == 1) break;
-      for (int C = (forced > 0 ? forced : 1); C <= (forced > 0 ? forced : CL_MAX_C); C *= 2) {
-        ClusterPlanHost H;
-        if (!build_cluster_plan(S->m, S->h_rowptr.data(), S->h_colidx.data(), dirp, want_aux ? S->n_node : 0,
-                                want_aux ? S->h_edge_nodes.data() : nullptr, C, H))
-          continue;
-        int r1, t1;
-        if (!fits(H, nrp, &r1, &t1)) continue;
-        best = std::move(H);
-        have = true;
-        // latency: with few jobs a larger cluster costs nothing (idle SMs otherwise)
-        if (forced <= 0)
-          while (best.C * 2 <= CL_MAX_C && (long long)n_matrix * (n_rhs / nrp) * best.C * 2 <= c->sm_count) {
-            ClusterPlanHost H2;
-            int r2, t2;
-            if (!build_cluster_plan(S->m, S->h_rowptr.data(), S->h_colidx.data(), dirp, want_aux ? S->n_node : 0,
-                                    want_aux ? S->h_edge_nodes.data() : nullptr, best.C * 2, H2) || !fits(H2, nrp, &r2, &t2))
-              break;
-            best = std::move(H2);
-          }
-        break;
+    // plans are shared between systems with the same pattern, Dirichlet flags and gradient (a driver that creates one
+    // system per call -- calculate_sparams_eigenmode in a frequency loop -- builds the plan once)
+    uint64_t hsh = 1469598103934665603ull;
+    auto mix = [&hsh](const void *ptr, size_t bytes) {
+      const uint32_t *w = (const uint32_t *)ptr;
+      for (size_t i = 0; i < bytes / 4; ++i) {
+        hsh ^= w[i];
+        hsh *= 1099511628211ull;
       }
+      const unsigned char *t = (const unsigned char *)ptr + (bytes / 4) * 4;
+      for (size_t i = 0; i < bytes % 4; ++i) {
+        hsh ^= t[i];
+        hsh *= 1099511628211ull;
+      }
+    };
+    mix(S->h_rowptr.data(), S->h_rowptr.size() * 4);
+    mix(S->h_colidx.data(), S->h_colidx.size() * 4);
+    if (dirp) mix(dirp, (size_t)S->m);
+    if (want_aux) mix(S->h_edge_nodes.data(), S->h_edge_nodes.size() * 4);
+    std::shared_ptr<ClusterPlanDev> sp;
+    for (int C = C_want; C <= (forced > 0 ? forced : CL_MAX_C) && !sp; C *= 2) {
+      sp = plan_cache_find(c->device, hsh, S->m, (long long)S->nnz, C, want_aux);
+      if (sp) break;
+      ClusterPlanHost H;
+      if (!build_cluster_plan(S->m, S->h_rowptr.data(), S->h_colidx.data(), dirp, want_aux ? S->n_node : 0,
+                              want_aux ? S->h_edge_nodes.data() : nullptr, C, H))
+        continue;
+      int r1, t1;
+      if (!fits(H, 1, &r1, &t1)) continue;
+      sp = std::make_shared<ClusterPlanDev>();
+      sp->h = std::move(H);
+      int rc = cluster_plan_upload(S, sp.get());
+      if (rc) return rc;
+      plan_cache_put(c->device, hsh, S->m, (long long)S->nnz, C, want_aux, sp);
+      st.mark("  cluster plan (RCM, partition, windows, lists)");
     }
-    if (!have) return EFB_OK;  // does not fit: the other solver paths take it
-    PL = new ClusterPlanDev();
-    PL->h = std::move(best);
-    S->cl_plan = PL;
-    int rc = cluster_plan_upload(S, PL);
-    if (rc) return rc;
+    if (!sp) return EFB_OK;  // does not fit: the other solver paths take it
+    S->cl_plan = new std::shared_ptr<ClusterPlanDev>(sp);
+    PL = sp.get();
     S->cl_dirty = false;
-    st.mark("  cluster plan (RCM, partition, windows, lists)");
   }
   nr = nr_want;
   if (!fits(PL->h, nr, &rpt, &nth)) {
@@ -799,20 +873,6 @@ int run_krylov_cluster(SolvePlan &P, const efb_solve_opts *o, bool zero_x, bool 
   const size_t smem = cluster_smem_bytes(nr, PL->h);
   const int groups = n_rhs / nr;
   const int n_jobs = P.n_matrix * groups;
-  if (forced < 0) {
-    // Latency or throughput?  A cluster job is ~10x faster than a one-CTA job of k_cocg_small (measured on WR-90:
-    // 7.9 us per rhs-iteration on 8 SMs against 85 us per two-rhs iteration on one), but only ~15 clusters of 8 are
-    // resident against 148 CTAs, and a one-CTA job carries both right-hand sides: big batches (the 256-point sweep)
-    // stay on the one-CTA kernel when it applies, small ones (one frequency, the shards of a strong-scaled sweep) run
-    // here.  Systems the one-CTA kernel cannot take (p does not fit in its shared memory) always run here.
-    const int C = PL->h.C;
-    const int resident = std::max(1, c->sm_count / C - (C == 8 ? 3 : C == 4 ? 4 : 0));
-    const double rounds_cl = std::ceil((double)n_jobs / resident) * (nr == 2 ? 1.6 : 1.0);
-    const double rounds_1 = std::ceil((double)P.n_matrix / c->sm_count) * 10.0 * (n_rhs >= 2 ? 1.0 : 0.6);
-    const int nn1 = want_aux ? S->n_node : 0;
-    const bool one_cta_ok = S->m <= 16384 && ((size_t)PL->h.mc * 16 + (size_t)nn1 * 16 + 4096) <= (size_t)dev_smem;
-    if (one_cta_ok && rounds_cl > rounds_1) return EFB_OK;
-  }
   {
     // queue order = longest expected job first (iteration counts of the previous solve, else frequency)
     std::vector<double> w((size_t)n_jobs, 0.0);
@@ -900,6 +960,8 @@ int efb_debug_cluster_plan_build(int32_t m, const int32_t *rowptr, const int32_t
 void efb_debug_cluster_plan_free(void *p) { delete (efb_cluster_plan_dbg *)p; }
 
 // copies the named array (converted to int64) into buf (capacity cap); returns its length, or -1 for an unknown name
+void efb_clear_caches(void) { cluster_plan_cache_clear(); }
+
 int64_t efb_debug_cluster_plan_get(void *p, const char *name, int64_t *buf, int64_t cap) {
   if (!p || !name) return -1;
   const ClusterPlanHost &H = ((efb_cluster_plan_dbg *)p)->h;

@@ -18,6 +18,7 @@
 #include <numeric>
 #include <queue>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace efb {
@@ -143,28 +144,17 @@ inline bool build_cluster_plan(int m, const int32_t *rowptr, const int32_t *coli
     P.error = "no free unknowns";
     return false;
   }
-  // free-free adjacency (no self loops), symmetrised defensively
+  // free-free adjacency (no self loops) straight from the rows: FEM patterns are structurally symmetric; for a
+  // non-symmetric pattern the order is merely less good (windows are computed from the actual rows below)
   std::vector<int32_t> aptr((size_t)mc + 1, 0), adj;
-  {
-    std::vector<std::pair<int32_t, int32_t>> pr;
-    for (int i = 0; i < mc; ++i) {
-      const int r = orig0[i];
-      for (int k = rowptr[r]; k < rowptr[r + 1]; ++k) {
-        const int j = comp0[colidx[k]];
-        if (j >= 0 && j != i) {
-          pr.emplace_back(i, j);
-          pr.emplace_back(j, i);
-        }
-      }
+  adj.reserve((size_t)rowptr[m]);
+  for (int i = 0; i < mc; ++i) {
+    const int r = orig0[i];
+    for (int k = rowptr[r]; k < rowptr[r + 1]; ++k) {
+      const int j = comp0[colidx[k]];
+      if (j >= 0 && j != i) adj.push_back(j);
     }
-    std::sort(pr.begin(), pr.end());
-    pr.erase(std::unique(pr.begin(), pr.end()), pr.end());
-    adj.resize(pr.size());
-    for (size_t k = 0; k < pr.size(); ++k) {
-      aptr[pr[k].first + 1]++;
-      adj[k] = pr[k].second;
-    }
-    for (int i = 0; i < mc; ++i) aptr[i + 1] += aptr[i];
+    aptr[i + 1] = (int32_t)adj.size();
   }
   const std::vector<int32_t> rcm = rcm_order(mc, aptr, adj);  // position -> compact0 id
   std::vector<int32_t> pos_of((size_t)mc);
@@ -243,9 +233,11 @@ inline bool build_cluster_plan(int m, const int32_t *rowptr, const int32_t *coli
     for (int c = 0; c < C; ++c)
       for (size_t s = 0; s < my_nodes[c].size(); ++s) touch[my_nodes[c][s]].push_back((uint32_t)c << 16 | (uint32_t)s);
   }
-  P.cta_info.assign((size_t)C * CL_INFO_STRIDE, 0);
-  for (int c = 0; c < C; ++c) {
-    int32_t *I = &P.cta_info[(size_t)c * CL_INFO_STRIDE];
+  std::vector<ClusterPlanHost> parts(C);
+  auto build_cta = [&](int c) {
+    ClusterPlanHost &Q = parts[c];
+    Q.cta_info.assign(CL_INFO_STRIDE, 0);
+    int32_t *I = Q.cta_info.data();
     const auto &L = local_rows[c];
     const int n_own = (int)L.size();
     int wlo = lo[c], whi = lo[c + 1];
@@ -258,28 +250,28 @@ inline bool build_cluster_plan(int m, const int32_t *rowptr, const int32_t *coli
     const int Wn = whi - wlo;
     const int n_my = (int)my_nodes[c].size();
     if (n_own > 65535 || Wn > 65535 || n_my > 65535) {
-      P.error = "slice too large for 16-bit slots";
-      return false;
+      Q.error = "slice too large for 16-bit slots";
+      return;
     }
     I[CI_N_OWN] = n_own; I[CI_LO] = lo[c]; I[CI_WLO] = wlo; I[CI_WN] = Wn; I[CI_N_MY] = n_my;
-    I[CI_OFF_ROW] = (int32_t)P.row_edge.size();
-    I[CI_OFF_SLOT] = (int32_t)P.slot_src.size();
-    I[CI_OFF_BLK] = (int32_t)P.blk_off.size();
-    I[CI_OFF_HALO] = (int32_t)P.halo_ws.size();
-    I[CI_OFF_NODE] = (int32_t)P.node_id.size();
-    I[CI_OFF_N2E] = (int32_t)P.n2e_item.size();
-    I[CI_OFF_NSRC] = (int32_t)P.nsrc_item.size();
+    I[CI_OFF_ROW] = (int32_t)Q.row_edge.size();
+    I[CI_OFF_SLOT] = (int32_t)Q.slot_src.size();
+    I[CI_OFF_BLK] = (int32_t)Q.blk_off.size();
+    I[CI_OFF_HALO] = (int32_t)Q.halo_ws.size();
+    I[CI_OFF_NODE] = (int32_t)Q.node_id.size();
+    I[CI_OFF_N2E] = (int32_t)Q.n2e_item.size();
+    I[CI_OFF_NSRC] = (int32_t)Q.nsrc_item.size();
     // rows
     for (int t = 0; t < n_own; ++t) {
       const int p = L[t], e = P.c_orig[p];
-      P.row_edge.push_back(e);
-      P.row_ws.push_back((uint16_t)(p - wlo));
+      Q.row_edge.push_back(e);
+      Q.row_ws.push_back((uint16_t)(p - wlo));
       if (P.aux) {
-        P.row_n0.push_back((uint16_t)slot_of_node(c, edge_nodes[2 * (size_t)e]));
-        P.row_n1.push_back((uint16_t)slot_of_node(c, edge_nodes[2 * (size_t)e + 1]));
+        Q.row_n0.push_back((uint16_t)slot_of_node(c, edge_nodes[2 * (size_t)e]));
+        Q.row_n1.push_back((uint16_t)slot_of_node(c, edge_nodes[2 * (size_t)e + 1]));
       } else {
-        P.row_n0.push_back(0);
-        P.row_n1.push_back(0);
+        Q.row_n0.push_back(0);
+        Q.row_n1.push_back(0);
       }
     }
     // ELL blocks of 32 local rows
@@ -287,74 +279,91 @@ inline bool build_cluster_plan(int m, const int32_t *rowptr, const int32_t *coli
     I[CI_N_BLK] = n_blk;
     int slots = 0;
     for (int b = 0; b < n_blk; ++b) {
-      P.blk_off.push_back(slots);
+      Q.blk_off.push_back(slots);
       int width = 0;
       for (int l = 0; l < 32 && b * 32 + l < n_own; ++l) width = std::max(width, rptr[L[b * 32 + l] + 1] - rptr[L[b * 32 + l]]);
-      const size_t base = P.slot_src.size();
-      P.slot_src.resize(base + (size_t)width * 32, -1);
-      P.slot_col.resize(base + (size_t)width * 32, 0);
+      const size_t base = Q.slot_src.size();
+      Q.slot_src.resize(base + (size_t)width * 32, -1);
+      Q.slot_col.resize(base + (size_t)width * 32, 0);
       for (int l = 0; l < 32; ++l) {
         const int t = b * 32 + l;
         const uint16_t self = t < n_own ? (uint16_t)(L[t] - wlo) : (uint16_t)0;
-        for (int k = 0; k < width; ++k) P.slot_col[base + (size_t)k * 32 + l] = self;  // padding reads a valid slot
+        for (int k = 0; k < width; ++k) Q.slot_col[base + (size_t)k * 32 + l] = self;  // padding reads a valid slot
       }
       // The order of the entries inside a row is free, and the kernel gathers p from shared memory with one 16-byte
       // load per entry: the 8 lanes of a quarter warp are served in one wavefront only if their window slots fall in
       // 8 different bank groups (slot mod 8).  Per quarter and step, the rows pick -- fewest choices first -- an unused
       // bank group among the entries they have left (their fullest one), else their fullest group.
-      for (int q = 0; q < 4; ++q) {
-        std::vector<std::pair<int32_t, int32_t>> ent[8][8];  // [lane][bank group] -> (col slot, src)
-        int left[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      constexpr int FILL_MAX = 96;  // rows longer than this keep the column order
+      for (int q = 0; q < 4 && width <= FILL_MAX; ++q) {
+        int32_t ecs[8][FILL_MAX], esrc[8][FILL_MAX];  // entries bucketed by bank group (lane-local arrays)
+        int beg[8][8], cnt[8][8], left[8], ng[8];
         for (int u = 0; u < 8; ++u) {
+          left[u] = 0;
+          ng[u] = 0;
+          for (int g = 0; g < 8; ++g) cnt[u][g] = 0;
           const int t = b * 32 + 8 * q + u;
           if (t >= n_own) continue;
           const int p = L[t];
-          for (int k = rptr[p]; k < rptr[p + 1]; ++k) {
-            const int cs = rcol[k] - wlo;
-            ent[u][cs & 7].emplace_back(cs, rsrc[k]);
+          for (int k = rptr[p]; k < rptr[p + 1]; ++k) cnt[u][(rcol[k] - wlo) & 7]++;
+          int run = 0;
+          for (int g = 0; g < 8; ++g) {
+            beg[u][g] = run;
+            run += cnt[u][g];
+            ng[u] += cnt[u][g] > 0;
+            cnt[u][g] = 0;
+          }
+          for (int k = rptr[p + 1] - 1; k >= rptr[p]; --k) {  // descending: taking from the back yields ascending columns
+            const int cs = rcol[k] - wlo, g = cs & 7, at = beg[u][g] + cnt[u][g]++;
+            ecs[u][at] = cs;
+            esrc[u][at] = rsrc[k];
             left[u]++;
           }
-          for (int g = 0; g < 8; ++g) std::reverse(ent[u][g].begin(), ent[u][g].end());  // pop_back takes the lowest column first
         }
         for (int k = 0; k < width; ++k) {
           unsigned used = 0, served = 0;
           for (int pick = 0; pick < 8; ++pick) {
-            int u = -1, ung = 0;
+            int u = -1;
             for (int v = 0; v < 8; ++v) {
               if ((served >> v & 1u) || left[v] == 0) continue;
-              int ng = 0;
-              for (int g = 0; g < 8; ++g) ng += !ent[v][g].empty();
-              if (u < 0 || ng < ung) { u = v; ung = ng; }
+              if (u < 0 || ng[v] < ng[u]) u = v;
             }
             if (u < 0) break;
-            int best = -1, any = -1;
-            size_t bc = 0, ac = 0;
+            int best = -1, any = -1, bc = 0, ac = 0;
             for (int g = 0; g < 8; ++g) {
-              const size_t cg = ent[u][g].size();
+              const int cg = cnt[u][g];
               if (cg > ac) { ac = cg; any = g; }
               if (!(used >> g & 1u) && cg > bc) { bc = cg; best = g; }
             }
             const int g = best >= 0 ? best : any;
             used |= 1u << g;
             served |= 1u << u;
-            const auto e = ent[u][g].back();
-            ent[u][g].pop_back();
+            const int at = beg[u][g] + --cnt[u][g];
+            if (cnt[u][g] == 0) ng[u]--;
             left[u]--;
-            P.slot_col[base + (size_t)k * 32 + 8 * q + u] = (uint16_t)e.first;
-            P.slot_src[base + (size_t)k * 32 + 8 * q + u] = e.second;
+            Q.slot_col[base + (size_t)k * 32 + 8 * q + u] = (uint16_t)ecs[u][at];
+            Q.slot_src[base + (size_t)k * 32 + 8 * q + u] = esrc[u][at];
           }
         }
       }
+      if (width > FILL_MAX)
+        for (int l = 0; l < 32 && b * 32 + l < n_own; ++l) {
+          const int p = L[b * 32 + l];
+          for (int k = rptr[p]; k < rptr[p + 1]; ++k) {
+            Q.slot_src[base + (size_t)(k - rptr[p]) * 32 + l] = rsrc[k];
+            Q.slot_col[base + (size_t)(k - rptr[p]) * 32 + l] = (uint16_t)(rcol[k] - wlo);
+          }
+        }
       slots += width * 32;
     }
-    P.blk_off.push_back(slots);
+    Q.blk_off.push_back(slots);
     I[CI_N_SLOTS] = slots;
     // halo
     int n_halo = 0;
     for (int p = wlo; p < whi; ++p) {
       if (p >= lo[c] && p < lo[c + 1]) continue;
-      P.halo_ws.push_back((uint16_t)(p - wlo));
-      P.halo_src.push_back((uint32_t)part_of[p] << 16 | (uint32_t)local_of[p]);
+      Q.halo_ws.push_back((uint16_t)(p - wlo));
+      Q.halo_src.push_back((uint32_t)part_of[p] << 16 | (uint32_t)local_of[p]);
       ++n_halo;
     }
     I[CI_N_HALO] = n_halo;
@@ -369,24 +378,56 @@ inline bool build_cluster_plan(int m, const int32_t *rowptr, const int32_t *coli
         }
       int acc = 0, acc2 = 0;
       for (int s = 0; s < n_my; ++s) {
-        P.node_id.push_back(my_nodes[c][s]);
-        P.n2e_ptr.push_back(acc);
-        P.nsrc_ptr.push_back(acc2);
-        for (uint32_t it : items[s]) P.n2e_item.push_back(it);
+        Q.node_id.push_back(my_nodes[c][s]);
+        Q.n2e_ptr.push_back(acc);
+        Q.nsrc_ptr.push_back(acc2);
+        for (uint32_t it : items[s]) Q.n2e_item.push_back(it);
         acc += (int)items[s].size();
-        for (uint32_t it : touch[my_nodes[c][s]]) P.nsrc_item.push_back(it);
+        for (uint32_t it : touch[my_nodes[c][s]]) Q.nsrc_item.push_back(it);
         acc2 += (int)touch[my_nodes[c][s]].size();
       }
-      P.n2e_ptr.push_back(acc);   // one extra entry per CTA: pointer arrays live at CI_OFF_NODE + c
-      P.nsrc_ptr.push_back(acc2);
+      Q.n2e_ptr.push_back(acc);   // one extra entry per CTA: pointer arrays live at CI_OFF_NODE + c
+      Q.nsrc_ptr.push_back(acc2);
     }
-    P.max_own = std::max(P.max_own, n_own);
-    P.max_w = std::max(P.max_w, Wn);
-    P.max_my = std::max(P.max_my, n_my);
-    P.max_slots = std::max(P.max_slots, slots);
-    P.max_halo = std::max(P.max_halo, n_halo);
-    P.max_n2e = std::max(P.max_n2e, P.n2e_ptr.back());
-    P.max_nsrc = std::max(P.max_nsrc, P.nsrc_ptr.back());
+    Q.max_own = std::max(Q.max_own, n_own);
+    Q.max_w = std::max(Q.max_w, Wn);
+    Q.max_my = std::max(Q.max_my, n_my);
+    Q.max_slots = std::max(Q.max_slots, slots);
+    Q.max_halo = std::max(Q.max_halo, n_halo);
+    Q.max_n2e = std::max(Q.max_n2e, Q.n2e_ptr.back());
+    Q.max_nsrc = std::max(Q.max_nsrc, Q.nsrc_ptr.back());
+  };
+  if (C > 1) {  // the CTAs are independent (the bank-aware fill dominates): one host thread each
+    std::vector<std::thread> th;
+    for (int c = 0; c < C; ++c) th.emplace_back(build_cta, c);
+    for (auto &t : th) t.join();
+  } else {
+    build_cta(0);
+  }
+  P.cta_info.assign((size_t)C * CL_INFO_STRIDE, 0);
+  auto app = [](auto &dst, const auto &src) { dst.insert(dst.end(), src.begin(), src.end()); };
+  for (int c = 0; c < C; ++c) {
+    const ClusterPlanHost &Q = parts[c];
+    if (!Q.error.empty()) {
+      P.error = Q.error;
+      return false;
+    }
+    int32_t *I = &P.cta_info[(size_t)c * CL_INFO_STRIDE];
+    for (int k = 0; k < CL_INFO_STRIDE; ++k) I[k] = Q.cta_info[k];
+    I[CI_OFF_ROW] = (int32_t)P.row_edge.size();
+    I[CI_OFF_SLOT] = (int32_t)P.slot_src.size();
+    I[CI_OFF_BLK] = (int32_t)P.blk_off.size();
+    I[CI_OFF_HALO] = (int32_t)P.halo_ws.size();
+    I[CI_OFF_NODE] = (int32_t)P.node_id.size();
+    I[CI_OFF_N2E] = (int32_t)P.n2e_item.size();
+    I[CI_OFF_NSRC] = (int32_t)P.nsrc_item.size();
+    app(P.row_edge, Q.row_edge); app(P.row_ws, Q.row_ws); app(P.row_n0, Q.row_n0); app(P.row_n1, Q.row_n1);
+    app(P.blk_off, Q.blk_off); app(P.slot_src, Q.slot_src); app(P.slot_col, Q.slot_col);
+    app(P.halo_ws, Q.halo_ws); app(P.halo_src, Q.halo_src); app(P.node_id, Q.node_id);
+    app(P.n2e_ptr, Q.n2e_ptr); app(P.n2e_item, Q.n2e_item); app(P.nsrc_ptr, Q.nsrc_ptr); app(P.nsrc_item, Q.nsrc_item);
+    P.max_own = std::max(P.max_own, Q.max_own); P.max_w = std::max(P.max_w, Q.max_w); P.max_my = std::max(P.max_my, Q.max_my);
+    P.max_slots = std::max(P.max_slots, Q.max_slots); P.max_halo = std::max(P.max_halo, Q.max_halo);
+    P.max_n2e = std::max(P.max_n2e, Q.max_n2e); P.max_nsrc = std::max(P.max_nsrc, Q.max_nsrc);
   }
   return true;
 }

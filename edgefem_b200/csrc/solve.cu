@@ -1611,6 +1611,40 @@ static int run_cocg_small(SolvePlan &P, const efb_solve_opts *o, bool zero_x, bo
   return EFB_OK;
 }
 
+int solver_alloc_public(System *S) { return solver_alloc(S); }
+
+// ||b - A x|| / ||b|| of every system of the matrices [first, first+n): fills residual and converged (iters, method and
+// precond are the caller's)
+int true_residuals(System *S, int first_matrix, int n_matrix, double tol, efb_solve_result *results) {
+  Ctx *c = S->ctx;
+  int rc = solver_alloc(S);
+  if (rc) return rc;
+  efb_solve_opts o;
+  memset(&o, 0, sizeof o);
+  o.tolerance = tol;
+  o.max_iterations = 0;
+  o.precond = EFB_PRECOND_JACOBI;
+  o.method = EFB_METHOD_COCG;
+  SolvePlan P;
+  if ((rc = make_plan(S, first_matrix, n_matrix, &o, P))) return rc;
+  const int nsys = P.n_sys;
+  std::vector<int32_t> act((size_t)nsys * 4);
+  for (int i = 0; i < nsys; ++i) { act[i * 4 + ST_ACTIVE] = 1; act[i * 4 + ST_ITERS] = 0; act[i * 4 + ST_CONV] = 0; act[i * 4 + ST_REC] = 0; }
+  EFB_CUDA(c, cudaMemcpyAsync(S->d_state + (size_t)P.first_sys * 4, act.data(), act.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  if ((rc = launch_spmv(S, P.D, P.first_matrix, P.n_matrix, S->d_x, P.vec[V_Q], nullptr, 0, 0, 0, 0))) return rc;
+  k_init_residual<0><<<P.vgrid, VEC_THREADS, 0, c->stream>>>(P.D, P.first_sys, S->d_b, P.vec[V_Q], P.vec[V_R], P.vec[V_R0], 0);
+  EFB_CHECK_LAUNCH(c);
+  std::vector<c128> hscal((size_t)nsys * NSCAL);
+  EFB_CUDA(c, cudaMemcpyAsync(hscal.data(), S->d_scal + (size_t)P.first_sys * NSCAL, hscal.size() * sizeof(c128), cudaMemcpyDeviceToHost, c->stream));
+  EFB_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < nsys; ++i) {
+    const double rr = hscal[(size_t)i * NSCAL + S_RR].x, bb = hscal[(size_t)i * NSCAL + S_BB].x;
+    results[i].residual = bb > 0.0 ? sqrt(rr / bb) : sqrt(rr);
+    results[i].converged = (rr <= P.D.tol2 * bb * (1.0 + 1e-6)) && std::isfinite(rr) ? 1 : 0;
+  }
+  return EFB_OK;
+}
+
 }  // namespace efb
 
 using namespace efb;
@@ -1696,32 +1730,15 @@ int efb_solve(efb_system *sys_, int32_t first_matrix, int32_t n_matrix, const ef
     }
   }
   // final true residuals: r = b - A x for every system (cheap, and independent of the path taken)
-  std::vector<int32_t> hiters(nsys), hconv(nsys);
-  for (int i = 0; i < nsys; ++i) { hiters[i] = hstate[i * 4 + ST_ITERS]; hconv[i] = hstate[i * 4 + ST_CONV]; }
-  {
-    // activate all, recompute residual norms
-    std::vector<int32_t> act((size_t)nsys * 4);
-    for (int i = 0; i < nsys; ++i) { act[i * 4 + ST_ACTIVE] = 1; act[i * 4 + ST_ITERS] = hiters[i]; act[i * 4 + ST_CONV] = 0; act[i * 4 + ST_REC] = 0; }
-    EFB_CUDA(c, cudaMemcpyAsync(S->d_state + (size_t)P.first_sys * 4, act.data(), act.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-    if ((rc = launch_spmv(S, P.D, P.first_matrix, P.n_matrix, S->d_x, P.vec[V_Q], nullptr, 0, 0, 0, 0))) return rc;
-    k_init_residual<0><<<P.vgrid, VEC_THREADS, 0, c->stream>>>(P.D, P.first_sys, S->d_b, P.vec[V_Q], P.vec[V_R], P.vec[V_R0], 0);
-    EFB_CHECK_LAUNCH(c);
-  }
-  std::vector<c128> hscal((size_t)nsys * NSCAL);
-  EFB_CUDA(c, cudaMemcpyAsync(hscal.data(), S->d_scal + (size_t)P.first_sys * NSCAL, hscal.size() * sizeof(c128), cudaMemcpyDeviceToHost, c->stream));
-  EFB_CUDA(c, cudaStreamSynchronize(c->stream));
-  st.mark("solve: final residuals + read-back");
   for (int i = 0; i < nsys; ++i) {
-    const double rr = hscal[(size_t)i * NSCAL + S_RR].x, bb = hscal[(size_t)i * NSCAL + S_BB].x;
-    efb_solve_result &R = results[i];
-    R.iters = hiters[i];
-    if ((int)S->last_iters.size() != S->n_sys) S->last_iters.assign((size_t)S->n_sys, 0);
-    S->last_iters[(size_t)P.first_sys + i] = hiters[i];
-    R.method = P.method;
-    R.precond = P.aux ? EFB_PRECOND_AUX : P.precond;
-    R.residual = bb > 0.0 ? sqrt(rr / bb) : sqrt(rr);
-    R.converged = (rr <= P.D.tol2 * bb * (1.0 + 1e-6)) && std::isfinite(rr) ? 1 : 0;
+    results[i].iters = hstate[i * 4 + ST_ITERS];
+    results[i].method = P.method;
+    results[i].precond = P.aux ? EFB_PRECOND_AUX : P.precond;
   }
+  if ((rc = true_residuals(S, first_matrix, n_matrix, opts->tolerance, results))) return rc;
+  st.mark("solve: final residuals + read-back");
+  if ((int)S->last_iters.size() != S->n_sys) S->last_iters.assign((size_t)S->n_sys, 0);
+  for (int i = 0; i < nsys; ++i) S->last_iters[(size_t)P.first_sys + i] = results[i].iters;
   return EFB_OK;
 }
 

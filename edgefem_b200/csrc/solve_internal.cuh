@@ -66,5 +66,9 @@ struct SolvePlan {
 // cluster.cu: persistent Krylov solver with one thread-block CLUSTER per matrix (matrix slice resident in shared memory)
 int run_krylov_cluster(SolvePlan &P, const efb_solve_opts *o, bool zero_x, bool *ran);
 void cluster_plan_free(System *S);
+void cluster_plan_cache_clear();
+// solve.cu: workspace allocation and the final true-residual pass, shared with dense.cu
+int solver_alloc_public(System *S);
+int true_residuals(System *S, int first_matrix, int n_matrix, double tol, efb_solve_result *results);
 
 }  // namespace efb

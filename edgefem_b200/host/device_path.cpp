@@ -392,14 +392,38 @@ SolveOutcome solve_on_device(DeviceSystem &sys, int first, int count, const Solv
     return true;
   };
   out.method = method_name(out.res[0].method, out.res[0].precond);
-  if (!all_ok() && opt.auto_fallback && symmetric) {
-    // second attempt on the device with the general method, continuing from the current iterate
-    std::vector<efb_solve_result> first_try = out.res;
-    o.method = EFB_METHOD_BICGSTAB;
-    o.zero_initial_guess = 0;
-    detail::check(efb_solve(sys.h, first, count, &o, out.res.data()), "efb_solve");
-    for (size_t i = 0; i < out.res.size(); ++i) out.res[i].iters += first_try[i].iters;
-    out.method += "->" + method_name(out.res[0].method, out.res[0].precond);
+  if (!all_ok() && opt.auto_fallback) {
+    // The reference falls back to SparseLU (src/solver.cpp:55-80, method "<failed>->SparseLU").  Here: every matrix with an
+    // unconverged right-hand side is re-solved by the dense LU on the device (efb_solve_direct) when it is small enough for
+    // it; larger symmetric systems get a second Krylov attempt with the general method, continuing from the current iterate.
+    bool direct_done = false;
+    for (int f = 0; f < count; ++f) {
+      bool bad = false;
+      for (int k = 0; k < sys.n_rhs; ++k) {
+        const efb_solve_result &r = out.res[(size_t)f * sys.n_rhs + k];
+        bad = bad || (!r.converged && !(opt.use_direct && r.residual <= opt.tolerance));
+      }
+      if (!bad) continue;
+      std::vector<efb_solve_result> dr((size_t)sys.n_rhs);
+      const int rc = efb_solve_direct(sys.h, first + f, 1, dr.data());
+      if (rc == EFB_ERR_LIMIT) break;  // too large for the dense factorisation
+      detail::check(rc, "efb_solve_direct");
+      for (int k = 0; k < sys.n_rhs; ++k) {
+        dr[k].iters += out.res[(size_t)f * sys.n_rhs + k].iters;
+        out.res[(size_t)f * sys.n_rhs + k] = dr[k];
+      }
+      direct_done = true;
+    }
+    if (direct_done) {
+      out.method += "->B200:DenseLU";
+    } else if (symmetric) {
+      std::vector<efb_solve_result> first_try = out.res;
+      o.method = EFB_METHOD_BICGSTAB;
+      o.zero_initial_guess = 0;
+      detail::check(efb_solve(sys.h, first, count, &o, out.res.data()), "efb_solve");
+      for (size_t i = 0; i < out.res.size(); ++i) out.res[i].iters += first_try[i].iters;
+      out.method += "->" + method_name(out.res[0].method, out.res[0].precond);
+    }
   }
   if (opt.use_direct)
     for (auto &r : out.res)
@@ -633,6 +657,7 @@ void check(int rc, const char *what) {
 void clear_device_cache() {
   std::lock_guard<std::mutex> lk(g_mu);
   g_mesh_cache.clear();
+  efb_clear_caches();  // derived structures shared between systems (cluster-split plans)
 }
 
 long long launch_count() { return g_ctx ? (long long)efb_launch_count(g_ctx) : 0; }

@@ -224,7 +224,8 @@ int efb_x_recover(efb_system *sys, int32_t rhs, int32_t n, const int32_t *dst,
  * Replaces solve_linear (src/solver.cpp:35-193).  Eigen's BiCGSTAB/IncompleteLUT/SparseLU
  * are not reproduced; the contract kept is SolveResult's: iterations, relative residual
  * ||b-Ax||/||b|| (TRUE residual, recomputed), converged flag.                           */
-typedef enum { EFB_METHOD_AUTO = 0, EFB_METHOD_BICGSTAB = 1, EFB_METHOD_COCG = 2 } efb_method;
+typedef enum { EFB_METHOD_AUTO = 0, EFB_METHOD_BICGSTAB = 1, EFB_METHOD_COCG = 2,
+               EFB_METHOD_DIRECT = 3 /* reported by efb_solve_direct only */ } efb_method;
 typedef enum { EFB_PRECOND_JACOBI = 0, EFB_PRECOND_AUX = 1 /* Jacobi + nodal gradient-space Jacobi */,
                EFB_PRECOND_NONE = 2 } efb_precond;
 
@@ -250,6 +251,15 @@ typedef struct {
 
 int efb_solve(efb_system *sys, int32_t first_matrix, int32_t n_matrix,
               const efb_solve_opts *opts, efb_solve_result *results /* [n_matrix*n_rhs] */);
+/* Direct solve on the device: dense complex LU with partial pivoting over the free unknowns, all right-hand sides
+ * of matrices [first, first+count).  The robust last resort behind solve_linear's contract (src/solver.cpp:11-33
+ * `use_direct`, :55-80 "<method>->SparseLU" when the Krylov solver fails): used by the host layer when a Krylov solve
+ * does not converge and the system has at most efb_solve_direct_limit() free unknowns (16 384 by default,
+ * EDGEFEM_B200_DENSE_MAX); larger systems return EFB_ERR_LIMIT.  results: iters = 1, true relative residual. */
+int efb_solve_direct(efb_system *sys, int32_t first_matrix, int32_t n_matrix, efb_solve_result *results);
+int efb_solve_direct_limit(void);
+/* drop every cached derived structure of the library (cluster-split plans shared between systems) */
+void efb_clear_caches(void);
 /* device time (ms, CUDA events on the ctx stream) of the persistent one-CTA-per-matrix COCG kernel of the
  * most recent efb_solve on this system, or -1 if that solve used the multi-kernel path */
 int efb_system_last_solve_kernel_ms(efb_system *sys, double *ms);
