@@ -181,6 +181,7 @@ struct System {
   int n_slices = 0;
   long long sell_total = 0;
   std::vector<uint8_t> h_dir;         // host copy of the Dirichlet flags of the local rows (empty: none set)
+  std::vector<uint8_t> h_dir_all;     // row-partitioned systems: host copy of ALL flags (nodal lists of the distributed preconditioner)
   std::vector<int32_t> h_edge_nodes;  // host copy of the gradient (2 per edge; empty: none set)
   cudaEvent_t ev_s0 = nullptr, ev_s1 = nullptr;  // around the persistent solver kernel
   bool small_timed = false;

@@ -114,6 +114,7 @@ enum {
   DS_RHO_PREV = 6,  // [2] rho the current p was built with
   DS_BB = 8,        // [1] |b|^2 (+2 pad)  (all-reduced once)
   DS_SYNC = 12,     // [1] always 0: operand of the all-reduces that only order the ranks
+  DS_RR2 = 13,      // [1] |r|^2 of the aux path (all-reduced on its own: orders the ranks before the nodal gather)
   DS_NUM = 16
 };
 
@@ -280,6 +281,105 @@ __global__ void k_dist_norm2(int m, const c128 *__restrict__ v, double *__restri
   block_partial<3>(d, partial);
 }
 
+// ---- auxiliary-space pieces
+// K2a: alpha = rho_prev / p^T q ; x += alpha p ; r -= alpha q ; partial |r|^2   (r lives in the exported buffer)
+__global__ void __launch_bounds__(DIST_VEC_THREADS)
+k_dist_update_r(int m, const double *__restrict__ sc, const c128 *__restrict__ p, const c128 *__restrict__ q, c128 *__restrict__ x,
+                c128 *__restrict__ r, double *__restrict__ partial) {
+  const c128 pq = cmake(sc[DS_PQ], sc[DS_PQ + 1]), rho = cmake(sc[DS_RHO_PREV], sc[DS_RHO_PREV + 1]);
+  c128 alpha = cmake(0.0, 0.0);
+  if ((pq.x != 0.0 || pq.y != 0.0) && isfinite(pq.x) && isfinite(pq.y)) alpha = cdiv(rho, pq);
+  double d[3] = {0.0, 0.0, 0.0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+    x[i] = cfma(alpha, p[i], x[i]);
+    const c128 ri = cfma(cneg(alpha), q[i], r[i]);
+    r[i] = ri;
+    d[0] += cabs2(ri);
+  }
+  block_partial<3>(d, partial);
+}
+
+// N1: w[slot] = linv[slot] * sum over the free edges at my node of +-r (off-rank entries through the peer mappings)
+__global__ void __launch_bounds__(DIST_VEC_THREADS)
+k_dist_node(int n_my, const int32_t *__restrict__ mn_ptr, const int32_t *__restrict__ mn_item, const c128 *__restrict__ linv,
+            const __grid_constant__ XView rv, c128 *__restrict__ w) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_my; j += gridDim.x * blockDim.x) {
+    const c128 li = linv[j];
+    c128 a = cmake(0.0, 0.0);
+    if (li.x != 0.0 || li.y != 0.0) {
+      for (int k = mn_ptr[j]; k < mn_ptr[j + 1]; ++k) {
+        const int it = mn_item[k];
+        const c128 v = xload(rv, it >> 1);
+        a = (it & 1) ? cadd(a, v) : csub(a, v);
+      }
+      a = cmul(li, a);
+    }
+    w[j] = a;
+  }
+}
+
+// E1: z = dinv r + (w[head] - w[tail]) on free edges ; partial {r^T z}
+__global__ void __launch_bounds__(DIST_VEC_THREADS)
+k_dist_edge(int m, const c128 *__restrict__ dinv, const c128 *__restrict__ r, const int2 *__restrict__ slot, const uint8_t *__restrict__ dir,
+            const c128 *__restrict__ w, c128 *__restrict__ z, double *__restrict__ partial) {
+  double d[3] = {0.0, 0.0, 0.0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+    const c128 ri = r[i];
+    c128 zi = cmul(dinv[i], ri);
+    if (!dir[i]) {
+      const int2 ab = slot[i];
+      zi = cadd(zi, csub(w[ab.y], w[ab.x]));
+    }
+    z[i] = zi;
+    const c128 t = cmul(ri, zi);
+    d[0] += t.x; d[1] += t.y;
+  }
+  block_partial<3>(d, partial);
+}
+
+// r = b - t (t = A x parked in q by k_dist_spmv<2>) ; partial |r|^2
+__global__ void __launch_bounds__(DIST_VEC_THREADS)
+k_dist_resid(int m, const c128 *__restrict__ b, const c128 *__restrict__ t, c128 *__restrict__ r, double *__restrict__ partial) {
+  double d[3] = {0.0, 0.0, 0.0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+    const c128 ri = csub(b[i], t[i]);
+    r[i] = ri;
+    d[0] += cabs2(ri);
+  }
+  block_partial<3>(d, partial);
+}
+
+// nodal diagonal of G^T A G restricted to the local rows, accumulated into the full nodal array (summed over ranks by NCCL)
+__global__ void k_dist_nodal_diag(int m_loc, int row0, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx, const c128 *__restrict__ vals,
+                                  const uint8_t *__restrict__ dir_all, const int2 *__restrict__ en_all, c128 *L) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m_loc; i += gridDim.x * blockDim.x) {
+    const int e = row0 + i;
+    if (dir_all[e]) continue;
+    const int2 ab = en_all[e];
+    c128 la = cmake(0.0, 0.0), lb = cmake(0.0, 0.0);
+    for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+      const int e2 = colidx[k];
+      if (dir_all[e2]) continue;
+      const int2 cd = en_all[e2];
+      const c128 a = vals[k];
+      if (ab.x == cd.x) la = cadd(la, a);
+      if (ab.x == cd.y) la = csub(la, a);
+      if (ab.y == cd.y) lb = cadd(lb, a);
+      if (ab.y == cd.x) lb = csub(lb, a);
+    }
+    atomicAdd(&L[ab.x].x, la.x); atomicAdd(&L[ab.x].y, la.y);
+    atomicAdd(&L[ab.y].x, lb.x); atomicAdd(&L[ab.y].y, lb.y);
+  }
+}
+__global__ void k_dist_linv(int n_my, const int32_t *__restrict__ my_node, const uint8_t *__restrict__ my_dir, const c128 *__restrict__ L, c128 *linv) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_my; j += gridDim.x * blockDim.x) {
+    const c128 a = L[my_node[j]];
+    c128 v = cmake(0.0, 0.0);
+    if (!my_dir[j] && (a.x != 0.0 || a.y != 0.0)) v = cdiv(cmake(1.0, 0.0), a);
+    linv[j] = v;
+  }
+}
+
 struct DistState {  // per row-partitioned system
   int world = 1, rank = 0, chunk = 0;
   c128 *d_z = nullptr;      // [chunk] SpMV input of the iteration (IPC-shared)
@@ -289,8 +389,23 @@ struct DistState {  // per row-partitioned system
   double *d_sc = nullptr;   // [DS_NUM]
   double *d_partial = nullptr;  // [DIST_RED_BLOCKS*3]
   unsigned char *d_handles = nullptr;  // [world][2][64] IPC handles (all-gathered)
-  c128 *peer_z[DIST_MAX_WORLD] = {}, *peer_x[DIST_MAX_WORLD] = {};
+  c128 *peer_z[DIST_MAX_WORLD] = {}, *peer_x[DIST_MAX_WORLD] = {}, *peer_r[DIST_MAX_WORLD] = {};
   bool opened = false;
+  // auxiliary-space preconditioner z = D^-1 r + G L^-1 G^T r on the row partition: every rank keeps the nodes of its
+  // own edges ("my nodes": owned by it or shared with a neighbour), gathers G^T r for them over ALL their incident
+  // edges -- off-rank residual entries are read from the peers' exported r -- and applies G w with purely local data.
+  bool aux = false;
+  c128 *d_rexp = nullptr;        // [chunk] residual (IPC-shared): replaces d_r when aux
+  int n_my = 0;
+  int32_t *d_my_node = nullptr;  // [n_my] global node id
+  int32_t *d_mn_ptr = nullptr;   // [n_my+1]
+  int32_t *d_mn_item = nullptr;  // global edge id << 1 | head, free edges only
+  int2 *d_edge_slot = nullptr;   // [m_loc] my-node slots of (tail, head)
+  uint8_t *d_my_dir = nullptr;   // [n_my] node touches a Dirichlet edge
+  c128 *d_linv = nullptr;        // [n_my]
+  c128 *d_wloc = nullptr;        // [n_my]
+  c128 *d_Lfull = nullptr;       // [n_node] nodal diagonal of G^T A G, summed over the ranks (set-up only)
+  int2 *d_en_all = nullptr;      // [m_global] end nodes of every edge (set-up only)
 };
 
 }  // namespace
@@ -314,26 +429,33 @@ void dist_free(System *S) {
       if (o != T->rank) {
         if (T->peer_z[o]) cudaIpcCloseMemHandle(T->peer_z[o]);
         if (T->peer_x[o]) cudaIpcCloseMemHandle(T->peer_x[o]);
+        if (T->peer_r[o]) cudaIpcCloseMemHandle(T->peer_r[o]);
       }
   // IPC-exported allocations go straight back to the driver (a pooled block must not be re-issued while a peer maps it)
   cudaFree(T->d_z);
   cudaFree(T->d_xs);
+  cudaFree(T->d_rexp);
+  dfree(T->d_my_node); dfree(T->d_mn_ptr); dfree(T->d_mn_item); dfree(T->d_edge_slot); dfree(T->d_my_dir); dfree(T->d_linv); dfree(T->d_wloc);
+  dfree(T->d_Lfull); dfree(T->d_en_all);
   dfree(T->d_r); dfree(T->d_p); dfree(T->d_q); dfree(T->d_dinv); dfree(T->d_full); dfree(T->d_sc); dfree(T->d_partial);
   dfree(T->d_handles);
   delete T;
   S->dist_state = nullptr;
 }
 
-static int dist_prepare(System *S, DistState **out) {
+static int dist_prepare(System *S, DistState **out, bool want_aux = false) {
   Ctx *c = S->ctx;
   Dist *dd = (Dist *)c->dist;
   if (!dd) return fail(c, EFB_ERR_STATE, "efb_dist_*: call efb_dist_init on the context first");
   if (S->n_matrix != 1 || S->n_rhs != 1) return fail(c, EFB_ERR_INVALID, "efb_dist_*: row-partitioned systems carry one matrix and one right-hand side");
   if (!S->d_sp_chunk) return fail(c, EFB_ERR_LIMIT, "efb_dist_*: a row has more than %d entries", SPMV_STREAM_W);
+  if (S->dist_state && want_aux && !((DistState *)S->dist_state)->aux) dist_free(S);  // rebuild with the nodal lists
   if (S->dist_state) {
     *out = (DistState *)S->dist_state;
     return EFB_OK;
   }
+  if (want_aux && (!S->mesh || (int)S->mesh->h_edge_nodes.size() != 2 * S->m_global || (int)S->h_dir_all.size() != S->m_global))
+    return fail(c, EFB_ERR_STATE, "efb_dist_solve: the auxiliary-space preconditioner needs a mesh-born system with Dirichlet flags set");
   std::string err;
   NcclApi *api = nccl_api(err);
   if (!api) return fail(c, EFB_ERR_STATE, "efb_dist_*: %s", err.c_str());
@@ -351,6 +473,8 @@ static int dist_prepare(System *S, DistState **out) {
   // exported vectors: their own cudaMalloc blocks (never pooled), padded to `chunk` so an all-gather has equal counts
   EFB_CUDA(c, cudaMalloc((void **)&T->d_z, (size_t)chunk * sizeof(c128)));
   EFB_CUDA(c, cudaMalloc((void **)&T->d_xs, (size_t)chunk * sizeof(c128)));
+  EFB_CUDA(c, cudaMalloc((void **)&T->d_rexp, (size_t)chunk * sizeof(c128)));
+  EFB_CUDA(c, cudaMemsetAsync(T->d_rexp, 0, (size_t)chunk * sizeof(c128), c->stream));
   EFB_CUDA(c, cudaMemsetAsync(T->d_z, 0, (size_t)chunk * sizeof(c128), c->stream));
   EFB_CUDA(c, cudaMemsetAsync(T->d_xs, 0, (size_t)chunk * sizeof(c128), c->stream));
   if ((rc = dev_alloc(c, &T->d_r, (size_t)S->m))) return rc;
@@ -359,23 +483,77 @@ static int dist_prepare(System *S, DistState **out) {
   if ((rc = dev_alloc(c, &T->d_dinv, (size_t)S->m))) return rc;
   if ((rc = dev_alloc(c, &T->d_sc, (size_t)DS_NUM))) return rc;
   if ((rc = dev_alloc(c, &T->d_partial, (size_t)DIST_RED_BLOCKS * 3))) return rc;
-  if ((rc = dev_alloc(c, &T->d_handles, (size_t)world * 2 * sizeof(cudaIpcMemHandle_t)))) return rc;
+  if ((rc = dev_alloc(c, &T->d_handles, (size_t)world * 3 * sizeof(cudaIpcMemHandle_t)))) return rc;
+  if (want_aux) {
+    // my nodes = nodes of the own edges; their lists hold ALL incident free edges (global ids)
+    const Mesh *M = S->mesh;
+    const int nn = M->n_node, mg = S->m_global;
+    const int32_t *en = M->h_edge_nodes.data();
+    const uint8_t *dirg = S->h_dir_all.data();
+    std::vector<int32_t> slot_of((size_t)nn, -1), my_node;
+    for (int i = 0; i < S->m; ++i)
+      for (int k = 0; k < 2; ++k) {
+        const int nd = en[2 * (size_t)(S->row0 + i) + k];
+        if (slot_of[nd] < 0) slot_of[nd] = 0;
+      }
+    for (int nd = 0; nd < nn; ++nd)
+      if (slot_of[nd] == 0) {
+        slot_of[nd] = (int32_t)my_node.size();
+        my_node.push_back(nd);
+      }
+    const int n_my = (int)my_node.size();
+    std::vector<int32_t> ptr((size_t)n_my + 1, 0);
+    std::vector<uint8_t> my_dir((size_t)std::max(n_my, 1), 0);
+    for (int e = 0; e < mg; ++e)
+      for (int k = 0; k < 2; ++k) {
+        const int sl = slot_of[en[2 * (size_t)e + k]];
+        if (sl < 0) continue;
+        if (dirg[e]) my_dir[sl] = 1;
+        else ptr[sl + 1]++;
+      }
+    for (int j = 0; j < n_my; ++j) ptr[j + 1] += ptr[j];
+    std::vector<int32_t> item((size_t)std::max(ptr[n_my], 1)), cur(ptr.begin(), ptr.end() - 1);
+    for (int e = 0; e < mg; ++e) {
+      if (dirg[e]) continue;
+      for (int k = 0; k < 2; ++k) {
+        const int sl = slot_of[en[2 * (size_t)e + k]];
+        if (sl >= 0) item[cur[sl]++] = (e << 1) | k;  // k = 1: head (+1)
+      }
+    }
+    std::vector<int2> eslot((size_t)std::max(S->m, 1));
+    for (int i = 0; i < S->m; ++i) eslot[i] = make_int2(slot_of[en[2 * (size_t)(S->row0 + i)]], slot_of[en[2 * (size_t)(S->row0 + i) + 1]]);
+    T->n_my = n_my;
+    if ((rc = dev_upload(c, &T->d_my_node, my_node.data(), (size_t)std::max(n_my, 1)))) return rc;
+    if ((rc = dev_upload(c, &T->d_mn_ptr, ptr.data(), ptr.size()))) return rc;
+    if ((rc = dev_upload(c, &T->d_mn_item, item.data(), item.size()))) return rc;
+    if ((rc = dev_upload(c, &T->d_edge_slot, eslot.data(), eslot.size()))) return rc;
+    if ((rc = dev_upload(c, &T->d_my_dir, my_dir.data(), my_dir.size()))) return rc;
+    if ((rc = dev_upload(c, &T->d_en_all, (const int2 *)en, (size_t)mg))) return rc;
+    if ((rc = dev_alloc(c, &T->d_linv, (size_t)std::max(n_my, 1)))) return rc;
+    if ((rc = dev_alloc(c, &T->d_wloc, (size_t)std::max(n_my, 1)))) return rc;
+    if ((rc = dev_alloc(c, &T->d_Lfull, (size_t)nn))) return rc;
+    EFB_CUDA(c, cudaStreamSynchronize(c->stream));  // the host vectors above are locals
+    T->aux = true;
+  }
   EFB_CUDA(c, cudaMemsetAsync(T->d_sc, 0, DS_NUM * sizeof(double), c->stream));
   T->peer_z[rank] = T->d_z;
   T->peer_x[rank] = T->d_xs;
+  T->peer_r[rank] = T->d_rexp;
   if (world > 1) {
-    cudaIpcMemHandle_t mine[2];
+    cudaIpcMemHandle_t mine[3];
     EFB_CUDA(c, cudaIpcGetMemHandle(&mine[0], T->d_z));
     EFB_CUDA(c, cudaIpcGetMemHandle(&mine[1], T->d_xs));
+    EFB_CUDA(c, cudaIpcGetMemHandle(&mine[2], T->d_rexp));
     EFB_CUDA(c, cudaMemcpyAsync(T->d_handles + (size_t)rank * sizeof(mine), mine, sizeof(mine), cudaMemcpyHostToDevice, c->stream));
     EFB_NCCL(c, api, api->AllGather(T->d_handles + (size_t)rank * sizeof(mine), T->d_handles, sizeof(mine), ncclUint8, dd->comm, c->stream));
-    std::vector<cudaIpcMemHandle_t> all((size_t)world * 2);
+    std::vector<cudaIpcMemHandle_t> all((size_t)world * 3);
     EFB_CUDA(c, cudaMemcpyAsync(all.data(), T->d_handles, all.size() * sizeof(cudaIpcMemHandle_t), cudaMemcpyDeviceToHost, c->stream));
     EFB_CUDA(c, cudaStreamSynchronize(c->stream));
     for (int o = 0; o < world; ++o) {
       if (o == rank) continue;
-      EFB_CUDA(c, cudaIpcOpenMemHandle((void **)&T->peer_z[o], all[(size_t)o * 2], cudaIpcMemLazyEnablePeerAccess));
-      EFB_CUDA(c, cudaIpcOpenMemHandle((void **)&T->peer_x[o], all[(size_t)o * 2 + 1], cudaIpcMemLazyEnablePeerAccess));
+      EFB_CUDA(c, cudaIpcOpenMemHandle((void **)&T->peer_z[o], all[(size_t)o * 3], cudaIpcMemLazyEnablePeerAccess));
+      EFB_CUDA(c, cudaIpcOpenMemHandle((void **)&T->peer_x[o], all[(size_t)o * 3 + 1], cudaIpcMemLazyEnablePeerAccess));
+      EFB_CUDA(c, cudaIpcOpenMemHandle((void **)&T->peer_r[o], all[(size_t)o * 3 + 2], cudaIpcMemLazyEnablePeerAccess));
     }
     T->opened = true;
   }
@@ -417,7 +595,31 @@ struct DistRun {
   NcclApi *api;
   Dist *dd;
   int mode;
+  bool aux = false;
 };
+
+// z = D^-1 r + G L^-1 G^T r with r complete on every rank: nodal gather over the peers' residuals, then the local edge pass
+// (z goes to the exported buffer), all-reduce {r^T z} -- which also orders the ranks before the next SpMV reads z
+static int dist_aux_precond(const DistRun &R) {
+  System *S = R.S;
+  DistState *T = R.T;
+  Ctx *c = S->ctx;
+  const int vb = vec_blocks(c, S->m), nb = vec_blocks(c, std::max(T->n_my, 1));
+  if (R.mode == 1) {
+    int rc = gather_full(S, T, R.api, T->d_rexp);
+    if (rc) return rc;
+  }
+  const XView rv = make_view(S, T, T->peer_r, T->d_rexp, R.mode);
+  k_dist_node<<<nb, DIST_VEC_THREADS, 0, c->stream>>>(T->n_my, T->d_mn_ptr, T->d_mn_item, T->d_linv, rv, T->d_wloc);
+  EFB_CHECK_LAUNCH(c);
+  k_dist_edge<<<vb, DIST_VEC_THREADS, 0, c->stream>>>(S->m, T->d_dinv, T->d_rexp, T->d_edge_slot, S->d_dir, T->d_wloc, T->d_z, T->d_partial);
+  EFB_CHECK_LAUNCH(c);
+  k_dist_finish<3><<<1, 256, 0, c->stream>>>(T->d_partial, vb, T->d_sc, DS_RHO, 0);  // partial[2] is zero: DS_RR is restored below
+  EFB_CHECK_LAUNCH(c);
+  EFB_NCCL(c, R.api, R.api->AllReduce(T->d_sc + DS_RHO, T->d_sc + DS_RHO, 2, ncclFloat64, ncclSum, R.dd->comm, c->stream));
+  EFB_CUDA(c, cudaMemcpyAsync(T->d_sc + DS_RR, T->d_sc + DS_RR2, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  return EFB_OK;
+}
 
 // r = b - A x (x read through the view of the exported solution copy), z = dinv r, all-reduce {rho, rr}
 static int dist_residual(const DistRun &R) {
@@ -435,6 +637,17 @@ static int dist_residual(const DistRun &R) {
     if (rc) return rc;
   }
   const XView xv = make_view(S, T, T->peer_x, T->d_xs, R.mode);
+  if (R.aux) {
+    // r = b - A x into the exported residual, |r|^2 all-reduced (every rank's r is complete after it), then z = M^-1 r
+    k_dist_spmv<0><<<nb, 256, 0, c->stream>>>(S->d_sp_chunk, S->n_sp_chunks, S->d_rowptr, S->d_colidx, S->d_vals, xv, S->d_b, T->d_dinv, T->d_z,
+                                              T->d_rexp, T->d_p, T->d_q, T->d_sc, 1, T->d_partial);
+    EFB_CHECK_LAUNCH(c);
+    k_dist_finish<3><<<1, 256, 0, c->stream>>>(T->d_partial, nb, T->d_sc, DS_RHO, 0);
+    EFB_CHECK_LAUNCH(c);
+    EFB_CUDA(c, cudaMemcpyAsync(T->d_sc + DS_RR2, T->d_sc + DS_RR, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    EFB_NCCL(c, R.api, R.api->AllReduce(T->d_sc + DS_RR2, T->d_sc + DS_RR2, 1, ncclFloat64, ncclSum, R.dd->comm, c->stream));
+    return dist_aux_precond(R);
+  }
   k_dist_spmv<0><<<nb, 256, 0, c->stream>>>(S->d_sp_chunk, S->n_sp_chunks, S->d_rowptr, S->d_colidx, S->d_vals, xv, S->d_b, T->d_dinv, T->d_z,
                                             T->d_r, T->d_p, T->d_q, T->d_sc, 1, T->d_partial);
   EFB_CHECK_LAUNCH(c);
@@ -466,11 +679,35 @@ static int dist_iteration(const DistRun &R, int first) {
   k_dist_finish<3><<<1, 256, 0, c->stream>>>(T->d_partial, nb, T->d_sc, DS_PQ, 1);  // partial[2] is unused by K1 (zero)
   EFB_CHECK_LAUNCH(c);
   EFB_NCCL(c, R.api, R.api->AllReduce(T->d_sc + DS_PQ, T->d_sc + DS_PQ, 2, ncclFloat64, ncclSum, R.dd->comm, c->stream));
+  if (R.aux) {
+    k_dist_update_r<<<vb, DIST_VEC_THREADS, 0, c->stream>>>(S->m, T->d_sc, T->d_p, T->d_q, S->d_x, T->d_rexp, T->d_partial);
+    EFB_CHECK_LAUNCH(c);
+    k_dist_finish<3><<<1, 256, 0, c->stream>>>(T->d_partial, vb, T->d_sc, DS_RR2 - 0, 0);  // writes DS_RR2 .. DS_RR2+2 (pads)
+    EFB_CHECK_LAUNCH(c);
+    EFB_NCCL(c, R.api, R.api->AllReduce(T->d_sc + DS_RR2, T->d_sc + DS_RR2, 1, ncclFloat64, ncclSum, R.dd->comm, c->stream));
+    return dist_aux_precond(R);
+  }
   k_dist_update<<<vb, DIST_VEC_THREADS, 0, c->stream>>>(S->m, T->d_sc, T->d_dinv, T->d_p, T->d_q, S->d_x, T->d_r, T->d_z, T->d_partial);
   EFB_CHECK_LAUNCH(c);
   k_dist_finish<3><<<1, 256, 0, c->stream>>>(T->d_partial, vb, T->d_sc, DS_RHO, 0);
   EFB_CHECK_LAUNCH(c);
   EFB_NCCL(c, R.api, R.api->AllReduce(T->d_sc + DS_RHO, T->d_sc + DS_RHO, 3, ncclFloat64, ncclSum, R.dd->comm, c->stream));
+  return EFB_OK;
+}
+
+// nodal diagonal L = diag(G^T A G): local rows -> full nodal array -> summed over the ranks -> inverted on my nodes
+static int dist_aux_setup(const DistRun &R) {
+  System *S = R.S;
+  DistState *T = R.T;
+  Ctx *c = S->ctx;
+  const int nn = S->mesh->n_node;
+  EFB_CUDA(c, cudaMemsetAsync(T->d_Lfull, 0, (size_t)nn * sizeof(c128), c->stream));
+  k_dist_nodal_diag<<<vec_blocks(c, S->m), DIST_VEC_THREADS, 0, c->stream>>>(S->m, S->row0, S->d_rowptr, S->d_colidx, S->d_vals, S->d_dir_all,
+                                                                             T->d_en_all, T->d_Lfull);
+  EFB_CHECK_LAUNCH(c);
+  EFB_NCCL(c, R.api, R.api->AllReduce(T->d_Lfull, T->d_Lfull, (size_t)nn * 2, ncclFloat64, ncclSum, R.dd->comm, c->stream));
+  k_dist_linv<<<vec_blocks(c, std::max(T->n_my, 1)), DIST_VEC_THREADS, 0, c->stream>>>(T->n_my, T->d_my_node, T->d_my_dir, T->d_Lfull, T->d_linv);
+  EFB_CHECK_LAUNCH(c);
   return EFB_OK;
 }
 
@@ -545,16 +782,17 @@ int efb_dist_solve(efb_system *sys_, const efb_solve_opts *opts, efb_solve_resul
   if (!(opts->tolerance > 0.0) || opts->max_iterations < 0 || halo_mode < 0 || halo_mode > 1) return fail(c, EFB_ERR_INVALID, "efb_dist_solve: bad options");
   if (opts->method != EFB_METHOD_COCG && opts->method != EFB_METHOD_AUTO)
     return fail(c, EFB_ERR_INVALID, "efb_dist_solve: the row-partitioned solver is COCG (complex symmetric systems)");
-  if (opts->precond == EFB_PRECOND_AUX) return fail(c, EFB_ERR_INVALID, "efb_dist_solve: preconditioner must be Jacobi or none");
   EFB_CUDA(c, cudaSetDevice(c->device));
+  const bool aux = opts->precond == EFB_PRECOND_AUX;
   DistState *T = nullptr;
-  int rc = dist_prepare(S, &T);
+  int rc = dist_prepare(S, &T, aux);
   if (rc) return rc;
   std::string err;
-  DistRun R{S, T, nccl_api(err), (Dist *)c->dist, halo_mode};
+  DistRun R{S, T, nccl_api(err), (Dist *)c->dist, halo_mode, aux};
   const int vb = vec_blocks(c, S->m);
   k_dist_dinv<<<vb, DIST_VEC_THREADS, 0, c->stream>>>(S->m, S->d_diag_pos, S->d_vals, T->d_dinv, opts->precond != EFB_PRECOND_NONE ? 1 : 0);
   EFB_CHECK_LAUNCH(c);
+  if (aux && (rc = dist_aux_setup(R))) return rc;
   if (opts->zero_initial_guess) EFB_CUDA(c, cudaMemsetAsync(S->d_x, 0, (size_t)S->m * sizeof(c128), c->stream));
   // |b|^2
   k_dist_norm2<<<vb, DIST_VEC_THREADS, 0, c->stream>>>(S->m, S->d_b, T->d_partial);
@@ -597,7 +835,7 @@ int efb_dist_solve(efb_system *sys_, const efb_solve_opts *opts, efb_solve_resul
   }
   result->iters = iters;
   result->method = EFB_METHOD_COCG;
-  result->precond = opts->precond == EFB_PRECOND_NONE ? EFB_PRECOND_NONE : EFB_PRECOND_JACOBI;
+  result->precond = aux ? EFB_PRECOND_AUX : (opts->precond == EFB_PRECOND_NONE ? EFB_PRECOND_NONE : EFB_PRECOND_JACOBI);
   result->residual = bb > 0.0 ? sqrt(rr / bb) : sqrt(rr);
   result->converged = conv ? 1 : 0;
   return EFB_OK;
@@ -606,19 +844,20 @@ int efb_dist_solve(efb_system *sys_, const efb_solve_opts *opts, efb_solve_resul
 // which 0: K1 alone (distributed SpMV + fused epilogue; halo_mode 1 includes the all-gather); 1: one full COCG iteration
 int efb_dist_bench(efb_system *sys_, int32_t which, int32_t reps, int32_t halo_mode, double *avg_ms) {
   System *S = (System *)sys_;
-  if (!S || !avg_ms || reps <= 0 || which < 0 || which > 1 || halo_mode < 0 || halo_mode > 1)
+  if (!S || !avg_ms || reps <= 0 || which < 0 || which > 2 || halo_mode < 0 || halo_mode > 1)
     return fail(S ? S->ctx : nullptr, EFB_ERR_INVALID, "efb_dist_bench: bad arguments");
   Ctx *c = S->ctx;
   if (!S->assembled) return fail(c, EFB_ERR_STATE, "efb_dist_bench: matrix values were never assembled or set");
   EFB_CUDA(c, cudaSetDevice(c->device));
   DistState *T = nullptr;
-  int rc = dist_prepare(S, &T);
+  int rc = dist_prepare(S, &T, which == 2);
   if (rc) return rc;
   std::string err;
-  DistRun R{S, T, nccl_api(err), (Dist *)c->dist, halo_mode};
+  DistRun R{S, T, nccl_api(err), (Dist *)c->dist, halo_mode, which == 2};
   const int vb = vec_blocks(c, S->m), nb = spmv_grid(c, S->n_sp_chunks);
   k_dist_dinv<<<vb, DIST_VEC_THREADS, 0, c->stream>>>(S->m, S->d_diag_pos, S->d_vals, T->d_dinv, 1);
   EFB_CHECK_LAUNCH(c);
+  if (which == 2 && (rc = dist_aux_setup(R))) return rc;
   if ((rc = dist_residual(R))) return rc;
   cudaEvent_t e0, e1;
   EFB_CUDA(c, cudaEventCreate(&e0));
@@ -627,7 +866,7 @@ int efb_dist_bench(efb_system *sys_, int32_t which, int32_t reps, int32_t halo_m
     const int n = pass == 0 ? std::min(reps, 3) : reps;
     EFB_CUDA(c, cudaEventRecord(e0, c->stream));
     for (int k = 0; k < n; ++k) {
-      if (which == 1) {
+      if (which >= 1) {
         if ((rc = dist_iteration(R, 0))) return rc;
       } else {
         if (halo_mode == 1 && (rc = gather_full(S, T, R.api, T->d_z))) return rc;

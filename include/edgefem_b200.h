@@ -323,7 +323,8 @@ int efb_build_edges(efb_ctx *ctx, int64_t n_tet, const int64_t *tet_conn /* [4t]
  * efb_dist_unique_id / efb_dist_init wrap ncclGetUniqueId / ncclCommInitRank (libnccl.so.2 is resolved with dlopen at
  * the first call): rank 0 creates the 128-byte id, the caller ships it to the other ranks by any means
  * (torch.distributed broadcast, MPI, a file) and every rank calls efb_dist_init(ctx, rank, world, id).
- * efb_dist_solve: COCG + Jacobi.  halo_mode 0: the SpMV kernel loads off-rank vector entries directly from the peers'
+ * efb_dist_solve: COCG + Jacobi or + the auxiliary-space preconditioner (EFB_PRECOND_AUX: every rank gathers G^T r for the nodes of its
+ * own edges over the peers' exported residual, one more scalar all-reduce per iteration).  halo_mode 0: the SpMV kernel loads off-rank vector entries directly from the peers'
  * memory (CUDA IPC mappings over NVLink) -- no exchange collective; halo_mode 1: ncclAllGather of the vector + local
  * SpMV (the library baseline).  Two scalar all-reduces per iteration in both modes.  Every rank must make the same
  * sequence of efb_dist_* calls.  efb_x_get returns the local slice of the solution. */
@@ -333,7 +334,8 @@ int efb_dist_init(efb_ctx *ctx, int32_t rank, int32_t world, const uint8_t *id12
 void efb_dist_finalize(efb_ctx *ctx);
 int efb_dist_row_range(int32_t m, int32_t rank, int32_t world, int32_t *row_begin, int32_t *row_end);
 int efb_dist_solve(efb_system *sys, const efb_solve_opts *opts, efb_solve_result *result, int32_t halo_mode);
-/* which 0: distributed SpMV + fused epilogue alone; 1: one full COCG iteration (2 kernels + 2 all-reduces) */
+/* which 0: distributed SpMV + fused epilogue alone; 1: one full COCG + Jacobi iteration (2 kernels + 2 all-reduces);
+ * 2: one COCG + auxiliary-space iteration (4 kernels + 3 all-reduces) */
 int efb_dist_bench(efb_system *sys, int32_t which, int32_t reps, int32_t halo_mode, double *avg_ms);
 
 #ifdef __cplusplus

@@ -31,6 +31,8 @@ def main():
     ap.add_argument("--tol", type=float, default=1e-8)
     ap.add_argument("--max-it", type=int, default=4000)
     ap.add_argument("--kh", type=float, default=0.2, help="k0*h of the solve (small = well conditioned, SPD-like)")
+    ap.add_argument("--freq", type=float, default=0.0, help="if > 0: solve frequency in Hz (overrides --kh); 240e6 is the C5 solve of bench.py")
+    ap.add_argument("--precond", default="both", choices=["jacobi", "aux", "both"])
     ap.add_argument("--check", action="store_true", help="also solve on one GPU (rank 0) and compare")
     a = ap.parse_args()
     import numpy as np
@@ -64,7 +66,7 @@ def main():
     sysd = cabi.DeviceSystem.from_mesh_rows(dm, r0, r1)
     sysd.set_dirichlet(flags)
     setup_s = time.perf_counter() - t0
-    omega = a.kh * n * C0  # k0 = kh / h, h = 1/n
+    omega = 2 * math.pi * a.freq if a.freq > 0 else a.kh * n * C0  # k0 = kh / h, h = 1/n
     mats, keep = cabi.make_materials(len(dm.slot_tags))
     sysd.assemble_volume([omega], mats)  # first call also builds the rank-major assembly schedule of this system
     ctx.timer_start()
@@ -102,11 +104,27 @@ def main():
         ms_spmv = maxr(sysd.dist_bench(0, a.reps, mode))
         ms_it = maxr(sysd.dist_bench(1, a.reps, mode))
         out[name] = {"spmv_ms": ms_spmv, "spmv_gbs_total": b_spmv / ms_spmv / 1e6, "cocg_iteration_ms": ms_it, "cocg_gbs_total": b_cocg / ms_it / 1e6}
+    ms_aux = maxr(sysd.dist_bench(2, a.reps, 0))
+    b_aux = b_cocg + 2 * 16.0 * m + 3 * 16.0 * int(xyz.shape[0]) + 2 * m * 8.0
+    out["peer_load"]["cocg_aux_iteration_ms"] = ms_aux
+    out["peer_load"]["cocg_aux_gbs_total"] = b_aux / ms_aux / 1e6
     sysd.rhs_set(0, b[r0:r1])
-    t1 = time.perf_counter()
-    res = sysd.dist_solve(tol=a.tol, max_iterations=a.max_it, halo_mode=0)
-    out["solve"] = dict(res, wall_s=round(time.perf_counter() - t1, 3))
-    x_loc = sysd.x_get(0)
+    x_loc = None
+    if a.precond in ("jacobi", "both"):
+        ctx.sync()
+        t1 = time.perf_counter()
+        res = sysd.dist_solve(tol=a.tol, max_iterations=a.max_it, halo_mode=0)
+        out["solve"] = dict(res, wall_s=round(time.perf_counter() - t1, 3))
+        x_loc = sysd.x_get(0)
+    if a.precond in ("aux", "both"):
+        ctx.sync()
+        t1 = time.perf_counter()
+        res_a = sysd.dist_solve(tol=a.tol, max_iterations=a.max_it, halo_mode=0, precond=cabi.PRECOND_AUX)
+        wall = time.perf_counter() - t1
+        out["solve_aux"] = dict(res_a, wall_s=round(wall, 3), ms_per_iteration=1e3 * wall / max(1, res_a["iters"]))
+        x_aux = sysd.x_get(0)
+        if x_loc is None:
+            x_loc = x_aux
     if a.check:
         res1 = sysd.dist_solve(tol=a.tol, max_iterations=a.max_it, halo_mode=1)
         x_loc1 = sysd.x_get(0)
@@ -114,6 +132,7 @@ def main():
         x = sharding.gather_rows(x_loc, m, rank, world, dist=dist)
         x1 = sharding.gather_rows(x_loc1, m, rank, world, dist=dist)
         out["halo_modes_rel_diff"] = float(np.linalg.norm(x - x1) / max(np.linalg.norm(x), 1e-300))
+        xa = sharding.gather_rows(x_aux, m, rank, world, dist=dist) if a.precond in ("aux", "both") else None
         if rank == 0:
             # single-GPU reference of the same system through the ordinary path
             pe_idx = np.nonzero(flags)[0].astype(np.int32)
@@ -128,6 +147,9 @@ def main():
             # true residual of the distributed solution with the single-GPU matrix
             y = s1.spmv(0, x)
             out["true_residual_dist"] = float(np.linalg.norm(b - y) / np.linalg.norm(b))
+            if xa is not None:
+                out["rel_diff_aux_vs_single_gpu"] = float(np.linalg.norm(xa - xs) / np.linalg.norm(xs))
+                out["true_residual_dist_aux"] = float(np.linalg.norm(b - s1.spmv(0, xa)) / np.linalg.norm(b))
             s1.close()
     if rank == 0:
         print(json.dumps(out))
