@@ -1038,7 +1038,7 @@ int efb_system_set_dirichlet(efb_system *sys_, const uint8_t *flags) {
   EFB_CUDA(c, cudaMemcpyAsync(S->d_dir_all, flags, (size_t)S->m_global, cudaMemcpyHostToDevice, c->stream));
   S->has_dir = true;
   S->h_dir.assign(flags + S->row0, flags + S->row0 + S->m);
-  if (S->m != S->m_global) S->h_dir_all.assign(flags, flags + S->m_global);
+  S->h_dir_all.assign(flags, flags + S->m_global);
   if (S->dist_state) dist_free(S);  // the distributed solver's nodal lists depend on the flags
   S->small_dirty = true;
   S->cl_dirty = true;
