@@ -1703,19 +1703,62 @@ int efb_solve(efb_system *sys_, int32_t first_matrix, int32_t n_matrix, const ef
     if (ran_small && (rc = read_state())) return rc;
     st.mark("solve: wait for the device");
   }
+  // Multi-kernel path: 5-7 launches per iteration.  For mid-size systems (10^4..10^6 unknowns) every kernel runs for a few
+  // microseconds and the loop is bound by launch latency, so a batch of `check_every` iterations is captured ONCE into a
+  // CUDA graph and replayed (scalars, activity flags and the convergence test live on the device; an inactive system makes
+  // its kernels return at once).  Parity of the rho double buffer repeats with the (even) batch length; the first two
+  // iterations of a cycle run outside the graph (BiCGSTAB's first iteration is special).  EDGEFEM_B200_NO_GRAPH=1: plain launches.
+  static const bool no_graph = getenv("EDGEFEM_B200_NO_GRAPH") != nullptr;
+  const int batch = (check_every + 1) & ~1;
+  cudaGraphExec_t gexec = nullptr;
+  long long graph_launches = 0;
+  auto iteration = [&](int it) -> int {
+    return P.method == EFB_METHOD_COCG ? cocg_iteration(P, it & 1) : bicg_iteration(P, it & 1, it == 0);
+  };
+  auto run_batch = [&]() -> int {  // `batch` iterations starting at an even iteration number
+    if (no_graph) {
+      for (int k = 0; k < batch; ++k) {
+        const int rcb = iteration(2 + k);
+        if (rcb) return rcb;
+      }
+      return EFB_OK;
+    }
+    if (!gexec) {
+      const long long l0 = c->launches;
+      EFB_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+      int rcb = EFB_OK;
+      for (int k = 0; k < batch && !rcb; ++k) rcb = iteration(2 + k);
+      cudaGraph_t g = nullptr;
+      const cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+      graph_launches = c->launches - l0;
+      c->launches = l0;  // captured, not executed
+      if (rcb) {
+        if (g) cudaGraphDestroy(g);
+        return rcb;
+      }
+      if (e != cudaSuccess) return fail(c, EFB_ERR_CUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
+      const cudaError_t e2 = cudaGraphInstantiate(&gexec, g, 0);
+      cudaGraphDestroy(g);
+      if (e2 != cudaSuccess) return fail(c, EFB_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e2));
+    }
+    EFB_CUDA(c, cudaGraphLaunch(gexec, c->stream));
+    c->launches += graph_launches;
+    return EFB_OK;
+  };
+  struct GraphGuard {
+    cudaGraphExec_t &g;
+    ~GraphGuard() {
+      if (g) cudaGraphExecDestroy(g);
+    }
+  } graph_guard{gexec};
   for (int cycle = 0; !ran_small && cycle <= max_restarts; ++cycle) {
     if ((rc = init_cycle(P, zero_x))) return rc;
     zero_x = false;
     if ((rc = read_state())) return rc;
     if (!any_active() || opts->max_iterations == 0) break;
-    int it = 0;
+    if ((rc = iteration(0)) || (rc = iteration(1))) return rc;
     while (true) {
-      for (int k = 0; k < check_every; ++k, ++it) {
-        const int par = it & 1;
-        if (P.method == EFB_METHOD_COCG) rc = cocg_iteration(P, par);
-        else rc = bicg_iteration(P, par, it == 0);
-        if (rc) return rc;
-      }
+      if ((rc = run_batch())) return rc;
       if ((rc = read_state())) return rc;
       if (!any_active()) break;
     }
