@@ -795,6 +795,27 @@ static int system_create_rows(Mesh *M, int row0, int row1, int64_t n_extra, cons
     int rch = mesh_host_e2t_item(M);
     if (rch) return rch;
   }
+  // The pattern of a (mesh, extras) pair is cached on the mesh: drivers that create one system per call (a Python loop
+  // over calculate_sparams_eigenmode, one call per frequency) rebuild nothing but the value arrays.
+  uint64_t xhash = 1469598103934665603ull;
+  for (int64_t i = 0; i < n_extra; ++i) {
+    xhash = (xhash ^ (uint64_t)(uint32_t)extra_rows[i]) * 1099511628211ull;
+    xhash = (xhash ^ (uint64_t)(uint32_t)extra_cols[i]) * 1099511628211ull;
+  }
+  Mesh::PatternCache &PC = M->pat_cache;
+  const bool pat_hit = PC.valid && PC.row0 == row0 && PC.row1 == row1 && PC.n_extra == n_extra && PC.hash == xhash;
+  std::vector<int32_t> rowlen(m);
+  std::vector<uint16_t> pos;
+  struct RangeCols {
+    int64_t a = 0, b = 0;
+    std::vector<int32_t> cols;
+  };
+  std::vector<RangeCols> ranges(64);
+  std::atomic<int> n_ranges{0};
+  if (pat_hit) {
+    pos = PC.pos;
+    for (int r = 0; r < m; ++r) rowlen[r] = PC.rowptr[r + 1] - PC.rowptr[r];
+  } else {
   // extras bucketed by row
   std::vector<int64_t> xptr((size_t)m + 1, 0);
   for (int64_t i = 0; i < n_extra; ++i) xptr[extra_rows[i] + 1]++;
@@ -805,7 +826,6 @@ static int system_create_rows(Mesh *M, int row0, int row1, int64_t n_extra, cons
     for (int64_t i = 0; i < n_extra; ++i) xcol[cur[extra_rows[i]]++] = extra_cols[i];
   }
   // pass 1: row lengths ; pass 2: fill
-  S->h_rowptr.assign((size_t)m + 1, 0);
   const int32_t *te = M->h_tet_edges.data();
   const int64_t kpos0 = M->h_e2t_ptr[row0];  // first incidence of the local rows: origin of the position map
   auto row_cols = [&](int r, std::vector<int32_t> &buf) {
@@ -820,14 +840,7 @@ static int system_create_rows(Mesh *M, int row0, int row1, int64_t n_extra, cons
   };
   // one pass: every worker builds the sorted column lists of its row range into a private buffer and fills the
   // tet-local -> row-local position map; the buffers are then concatenated at the row offsets
-  std::vector<int32_t> rowlen(m);
-  std::vector<uint16_t> pos((size_t)(M->h_e2t_ptr[row1] - kpos0) * 6);
-  struct RangeCols {
-    int64_t a = 0, b = 0;
-    std::vector<int32_t> cols;
-  };
-  std::vector<RangeCols> ranges(64);
-  std::atomic<int> n_ranges{0};
+  pos.resize((size_t)(M->h_e2t_ptr[row1] - kpos0) * 6);
   parallel_for(m, [&](int64_t a, int64_t b) {
     RangeCols &rc_ = ranges[n_ranges.fetch_add(1)];
     rc_.a = a;
@@ -845,6 +858,8 @@ static int system_create_rows(Mesh *M, int row0, int row1, int64_t n_extra, cons
       }
     }
   });
+  }
+  S->h_rowptr.assign((size_t)m + 1, 0);
   int64_t nnz = 0;
   int32_t maxrow = 0;
   for (int r = 0; r < m; ++r) {
@@ -866,7 +881,9 @@ static int system_create_rows(Mesh *M, int row0, int row1, int64_t n_extra, cons
   S->nnz = nnz;
   for (int r = 0; r < m; ++r) S->h_rowptr[r + 1] = S->h_rowptr[r] + rowlen[r];
   S->h_colidx.resize((size_t)nnz);
-  {
+  if (pat_hit) {
+    S->h_colidx = PC.colidx;
+  } else {
     const int nr = n_ranges.load();
     std::vector<std::thread> th;
     for (int i = 0; i < nr; ++i) {
@@ -874,6 +891,13 @@ static int system_create_rows(Mesh *M, int row0, int row1, int64_t n_extra, cons
       if (nr > 1 && ranges[i].cols.size() > (1u << 20)) th.emplace_back(cp); else cp();
     }
     for (auto &x : th) x.join();
+    if (m <= 400000) {  // small and mid-size meshes only: the cache holds host copies
+      PC.valid = true;
+      PC.row0 = row0; PC.row1 = row1; PC.n_extra = n_extra; PC.hash = xhash;
+      PC.rowptr = S->h_rowptr;
+      PC.colidx = S->h_colidx;
+      PC.pos = pos;
+    }
   }
   st.mark("concatenate");
   // assembly chunks: consecutive rows with <= lim_nnz entries and <= lim_rows rows

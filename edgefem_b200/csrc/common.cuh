@@ -123,6 +123,15 @@ struct Mesh {
   TetGeom *d_geom = nullptr;         // [n_tet] frequency-independent element geometry (thread-per-row kernel only)
   TetRec *d_rec = nullptr;           // [n_tet] the same, packed (batched kernel)
   uint16_t *d_e2t_ss = nullptr;      // [6*n_tet] sign | slot << 8 of the incidence's tet
+  // host copy of the last CSR pattern + position map built on this mesh, keyed by the row range and the extras
+  struct PatternCache {
+    bool valid = false;
+    int row0 = 0, row1 = 0;
+    int64_t n_extra = 0;
+    uint64_t hash = 0;
+    std::vector<int32_t> rowptr, colidx;
+    std::vector<uint16_t> pos;
+  } pat_cache;
 };
 
 struct Port;

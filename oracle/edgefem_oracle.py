@@ -650,6 +650,35 @@ def volume_abs_scale(mesh: Mesh, p: MaxwellParams) -> sp.csr_matrix:
     return triplets_to_csr(gi, gj, val.reshape(-1).astype(np.complex128), mesh.num_edges)
 
 
+def volume_operand_scale(mesh: Mesh, p: MaxwellParams) -> sp.csr_matrix:
+    """Per entry, the magnitude of the OPERANDS of the element arithmetic, summed over tets:
+    V |c_i| |c_j| / |mu s| for the curl-curl dot product of src/edge_basis.cpp:59-61 and
+    k0^2 |eps s| V (|g_b||g_d| I_ac + |g_b||g_c| I_ad + |g_a||g_d| I_bc + |g_a||g_c| I_bd) for the four mass terms of :76-82.
+    Any correct fp64 evaluation (Eigen's included) is accurate to a few ulp of THIS scale: a dot product of
+    near-orthogonal curls, or mass terms that cancel, lose relative accuracy in the result but not against their
+    operands.  Test-side yardstick of the "1e-12 relative (fp64)" bar of north_star."""
+    X = mesh.tet_xyz()
+    g, V = gradients_and_volume(X)
+    s = np.abs(pml_stretch(mesh, p, X))
+    ga = g[..., TET_PAIRS[:, 0], :]
+    gb = g[..., TET_PAIRS[:, 1], :]
+    cn = np.linalg.norm(2.0 * np.cross(ga, gb), axis=-1)          # [t,6]
+    gn = np.linalg.norm(g, axis=-1)                                # [t,4]
+    I = np.where(np.eye(4, dtype=bool), 1.0 / 10.0, 1.0 / 20.0)
+    a = TET_PAIRS[:, 0][:, None]
+    b = TET_PAIRS[:, 1][:, None]
+    c = TET_PAIRS[:, 0][None, :]
+    d = TET_PAIRS[:, 1][None, :]
+    Mb = (gn[:, b] * gn[:, d] * I[a, c] + gn[:, b] * gn[:, c] * I[a, d] + gn[:, a] * gn[:, d] * I[b, c] + gn[:, a] * gn[:, c] * I[b, d]) * V[:, None, None]
+    Kb = cn[:, :, None] * cn[:, None, :] * V[:, None, None]
+    k0 = p.omega / C0
+    eps, mu = material_tables(mesh, p, dispersive=True)
+    val = Kb / (np.abs(mu) * s)[:, None, None] + (k0 * k0 * np.abs(eps) * s)[:, None, None] * Mb
+    gi = np.repeat(mesh.tet_edges[:, :, None], 6, axis=2).reshape(-1)
+    gj = np.repeat(mesh.tet_edges[:, None, :], 6, axis=1).reshape(-1)
+    return triplets_to_csr(gi, gj, val.reshape(-1).astype(np.complex128), mesh.num_edges)
+
+
 def _abc_edges(mesh: Mesh, p: MaxwellParams, pec: Set[int]) -> np.ndarray:
     """src/assemble_maxwell.cpp:249-260 (order irrelevant: diagonal adds)."""
     if p.abc_surface_tags:

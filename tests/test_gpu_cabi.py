@@ -38,9 +38,17 @@ def test_pattern_bit_exact_and_values(ctx, wr90):
     G0 = sp.csr_matrix((v, ci, rp), shape=A.shape)
     serr = H.sum_rel_err(G0, A, orc.volume_abs_scale(mesh, p))
     rerr = H.row_rel_err(G0, A)
-    print("assembly err: row-relative", rerr, " vs entry (floored at 1e-3 median)", err, " vs sum of |contributions|", serr)
-    assert rerr < 1e-12   # fp64 bar stated by north_star: 1e-12 relative (to the row scale, see helpers.row_rel_err)
-    assert err < 1e-11 and serr < 1e-9  # informational, looser: per-entry measures include cancellation noise
+    oerr = H.sum_rel_err(G0, A, orc.volume_operand_scale(mesh, p))
+    print("assembly err: row-relative", rerr, " vs operand scale", oerr, " vs entry (floored at 1e-3 median)", err, " vs sum of |contributions|", serr)
+    # Measured on B200 (round 2): 2.1e-15 row-relative, 8.6e-13 per entry, 2.6e-11 on the sum of |contributions|.  The
+    # asserts sit ~10x above the measurements.  The fp64 bar of north_star ("1e-12 relative") is asserted on the two scales
+    # a correct fp64 evaluation is accurate on: the row, and the operands of the element arithmetic (V |c_i||c_j|, the four
+    # mass terms).  Relative to the RESULT of a cancelling dot product (near-orthogonal curls: c_i . c_j ~ 0) neither this
+    # kernel's g_ac g_bd - g_ad g_bc nor the reference's three-term c_i . c_j is accurate to 1e-12; that scale is
+    # informational.
+    assert rerr < 2e-14
+    assert oerr < 1e-12
+    assert err < 1e-11 and serr < 3e-10
     # explicit zeros are kept and Dirichlet rows are identity
     pm = orc.pec_mask(mesh, pec)
     G = sp.csr_matrix((v, ci, rp), shape=A.shape)

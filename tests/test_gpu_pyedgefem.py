@@ -115,15 +115,29 @@ def test_assemble_maxwell_dispersive_and_pml():
     pec = orc.build_edge_pec(om, 1)
     w = 2 * math.pi * 1.0e9
     m = pe.materials
-    models_h = [m.DebyeMaterial(8.0, 3.0, 2e-10), m.DrudeLorentzMaterial(3.5, 2 * math.pi * 0.4e9, 5e8)]
-    models_o = [orc.DebyeMaterial(8.0, 3.0, 2e-10), orc.DrudeLorentzMaterial(3.5, 2 * math.pi * 0.4e9, 5e8)]
+    # all four device model kinds (EFB_MODEL_DEBYE / DRUDE_LORENTZ / LORENTZ with two poles / DRUDE), one at a time ...
+    models_h = [m.DebyeMaterial(8.0, 3.0, 2e-10), m.DrudeLorentzMaterial(3.5, 2 * math.pi * 0.4e9, 5e8), m.LorentzMaterial(2.2),
+                m.DrudeMaterial(2 * math.pi * 0.6e9, 3e8)]
+    models_o = [orc.DebyeMaterial(8.0, 3.0, 2e-10), orc.DrudeLorentzMaterial(3.5, 2 * math.pi * 0.4e9, 5e8), orc.LorentzMaterial(2.2),
+                orc.DrudeMaterial(2 * math.pi * 0.6e9, 3e8)]
     models_h[1].add_lorentz_pole(0.7, 2 * math.pi * 2.0e9, 4e8)
     models_o[1].add_lorentz_pole(0.7, 2 * math.pi * 2.0e9, 4e8)
-    for k, tag in enumerate(tags[:2]):
+    for mdl in (models_h[2], models_o[2]):
+        mdl.add_pole(1.3, 2 * math.pi * 1.7e9, 2.5e8)
+        mdl.add_pole(0.4, 2 * math.pi * 3.1e9, 6e8)
+    for k in range(4):
+        tag = tags[k % 3]
+        assert abs(models_h[k].eval_eps(w) - models_o[k].eval_eps(w)) <= 1e-14 * abs(models_o[k].eval_eps(w))
         po = orc.MaxwellParams(omega=w, eps_models={tag: models_o[k]})
         ph = make_params(po)
         ph.set_eps_model(tag, models_h[k])
         check_assembly(hm, om, ph, po, bc, pec)
+    # ... and three different kinds in the three layers of one assembly (the per-slot table of the kernel)
+    po = orc.MaxwellParams(omega=w, eps_models={tags[0]: models_o[2], tags[1]: models_o[3], tags[2]: models_o[0]})
+    ph = make_params(po)
+    for tag, mdl in zip(tags, (models_h[2], models_h[3], models_h[0])):
+        ph.set_eps_model(tag, mdl)
+    check_assembly(hm, om, ph, po, bc, pec)
     # uniform PML region + tensor PML region
     po = orc.MaxwellParams(omega=w, pml_sigma=2.0e9, pml_regions={tags[0]})
     check_assembly(hm, om, make_params(po), po, bc, pec)
@@ -318,4 +332,4 @@ def test_calculate_sparams_modal_line_integral_ports():
     ph = make_params(po)
     S_h = pe.calculate_sparams(hm, ph, bc, ports_h)
     S_o = orc.calculate_sparams(om, po, pec, ports_o)
-    assert np.max(np.abs(S_h - S_o)) <= 1e-5 * max(1.0, np.max(np.abs(S_o)))
+    assert np.max(np.abs(S_h - S_o)) <= 1e-6 * max(1.0, np.max(np.abs(S_o)))
