@@ -311,6 +311,74 @@ def cube_extras(ctx, n: int, solve_freq: float, hbm_peak: float):
     return out
 
 
+def cube_extras_dist(ctx, dist, rank, world, n: int, solve_freq: float, hbm_peak: float):
+    """C5 row-partitioned over the ranks (second bullet): every rank assembles its row block (no communication),
+    the SpMV input halo is read from the peers' memory inside the SpMV kernel (CUDA IPC over NVLink), NCCL carries the
+    scalar all-reduces; converged COCG + auxiliary-space solve.  All ranks call this; rank 0 returns the record."""
+    import numpy as np
+    import torch
+    from edgefem_b200 import cabi, meshgen, sharding
+
+    uid = [cabi.dist_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    ctx.dist_init(rank, world, uid[0])
+
+    def maxr(v):
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sumr(v):
+        t = torch.tensor([float(v)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    t0 = time.perf_counter()
+    xyz, tets, tp, tris, trp = meshgen.cube_cavity(n, jitter=0.1)
+    dm, info = cabi.device_mesh_from_conn(ctx, xyz, tets, tp, tris)
+    m = int(info["edges"].shape[0])
+    flags = cabi.pec_flags_from_tris(m, info["tri_edges"], trp, 1)
+    r0, r1 = sharding.row_range(m, rank, world)
+    sysd = cabi.DeviceSystem.from_mesh_rows(dm, r0, r1)
+    sysd.set_dirichlet(flags)
+    setup_s = time.perf_counter() - t0
+    n_tet, n_node = int(tets.shape[0]), int(xyz.shape[0])
+    del xyz, tets, tris, info
+    mats, keep = cabi.make_materials(len(dm.slot_tags))
+    om_s = 2 * math.pi * solve_freq
+    sysd.assemble_volume([om_s], mats)  # first call builds the assembly schedule of the block
+    ctx.timer_start()
+    sysd.assemble_volume([om_s], mats)
+    ms_asm = maxr(ctx.timer_stop())
+    rng = np.random.default_rng(1234)
+    b = rng.standard_normal(m) + 1j * rng.standard_normal(m)
+    b[flags == 1] = 0
+    sysd.rhs_set(0, b[r0:r1])
+    nnz = sumr(sysd.nnz)
+    b_asm = 45.0 * n_tet + 24.0 * n_node + 16.0 * nnz
+    b_spmv = nnz * 20.0 + m * 36.0
+    b_aux = b_spmv + (10 * 16.0 + 2 * 16.0) * m + 3 * 16.0 * n_node + 2 * m * 8.0
+    ms_spmv = maxr(sysd.dist_bench(0, 20, 0))
+    ms_it = maxr(sysd.dist_bench(2, 20, 0))
+    dist.barrier()
+    ctx.sync()
+    t1 = time.perf_counter()
+    res = sysd.dist_solve(tol=1e-10, max_iterations=40000, halo_mode=0, precond=cabi.PRECOND_AUX)
+    ctx.sync()
+    wall = maxr(time.perf_counter() - t1)
+    it = max(1, res["iters"])
+    out = {"mesh": {"n": n, "tets": n_tet, "nodes": n_node, "edges": m, "nnz": int(nnz), "rows_per_rank": r1 - r0, "setup_s_per_rank": round(setup_s, 2)},
+           "partition": "contiguous row blocks of the global edge numbering; every rank holds the whole mesh; halo by peer loads inside the SpMV kernel",
+           "assembly": {"ms": ms_asm, "mtets_per_s": n_tet / ms_asm / 1e3, "gbs_total": b_asm / ms_asm / 1e6, "frac_of_hbm_peak_x_gpus": b_asm / ms_asm / 1e6 / (hbm_peak * world)},
+           "spmv": {"ms": ms_spmv, "gbs_total": b_spmv / ms_spmv / 1e6, "frac_of_hbm_peak_x_gpus": b_spmv / ms_spmv / 1e6 / (hbm_peak * world)},
+           "cocg_aux_iteration": {"ms": ms_it, "gbs_total": b_aux / ms_it / 1e6, "frac_of_hbm_peak_x_gpus": b_aux / ms_it / 1e6 / (hbm_peak * world)},
+           "solve": {"frequency_hz": solve_freq, "method": "COCG + auxiliary-space Jacobi, row-partitioned (3 scalar NCCL all-reduces per iteration)", "tolerance": 1e-10,
+                     "iters": res["iters"], "converged": bool(res["converged"]), "residual": res["residual"], "seconds": wall, "ms_per_iteration": 1e3 * wall / it}}
+    sysd.close()
+    dm.close()
+    return out
+
+
 def ncu_traffic(kernel: str, n_matrix: int):
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of `kernel` from the committed `ncu --set full`
     capture of this same command (profiles/ncu_traffic.json); None when no capture matches the workload size."""
@@ -498,6 +566,14 @@ def run_b200(a):
         except Exception as e:
             extras["c1_single_frequency"] = {"error": repr(e)}
     rs.close()
+    if a.cube_n > 0 and world > 1:
+        try:
+            rec = cube_extras_dist(ctx, dist, rank, world, a.cube_n, a.cube_freq, hbm_peak)
+            if rank == 0:
+                extras["c5_cube_row_partitioned"] = rec
+        except Exception as e:
+            if rank == 0:
+                extras["c5_cube_row_partitioned"] = {"error": repr(e)}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
