@@ -23,6 +23,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "spmv_tma.cuh"
 
 namespace efb {
 
@@ -234,6 +235,124 @@ k_dist_spmv(const int32_t *__restrict__ sp_chunk, int n_chunks, const int32_t *_
       }
     }
     __syncwarp();
+  }
+  block_partial<3>(d, partial);
+}
+
+// The same SpMV with the matrix stream moved by the TMA engine (see k_spmv_tma in solve.cu): lane 0 of a warp issues two
+// bulk copies per chunk (values, columns) that complete on an mbarrier one chunk ahead of the warp (2-stage ring in shared
+// memory), so the LSU only sees the gather of the input vector -- on-rank entries from local memory, halo entries straight
+// from the peers' memory -- the in-place products and the in-order row sums.  Persistent: 2 CTAs x 8 warps per SM.
+// Same chunks, products and summation order as k_dist_spmv: bit-identical results.
+template <int EPI>
+__global__ void __launch_bounds__(256, 2)
+k_dist_spmv_tma(const int32_t *__restrict__ sp_chunk, int n_chunks, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
+                const c128 *__restrict__ vals, const __grid_constant__ XView xv, const c128 *__restrict__ bvec, const c128 *__restrict__ dinv,
+                c128 *__restrict__ zloc, c128 *__restrict__ r, c128 *__restrict__ p, c128 *__restrict__ q, const double *__restrict__ sc, int first,
+                double *__restrict__ partial) {
+  extern __shared__ __align__(128) unsigned char tma_smem[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  unsigned char *wbase = tma_smem + (size_t)wid * 2 * SPMV_TMA_STAGE;
+  const unsigned wbase_s = (unsigned)__cvta_generic_to_shared(wbase);
+  const unsigned bar_s = (unsigned)__cvta_generic_to_shared(tma_smem + (size_t)8 * 2 * SPMV_TMA_STAGE) + (unsigned)wid * 16u;
+  if (lane == 0) {
+    mbar_init(bar_s, 1);
+    mbar_init(bar_s + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  c128 beta = cmake(0.0, 0.0);
+  if (EPI == 1 && !first) {
+    const c128 rho = cmake(sc[DS_RHO], sc[DS_RHO + 1]), rp = cmake(sc[DS_RHO_PREV], sc[DS_RHO_PREV + 1]);
+    if (rp.x != 0.0 || rp.y != 0.0) beta = cdiv(rho, rp);
+  }
+  double d[3] = {0.0, 0.0, 0.0};
+  const int stride = gridDim.x * 8;
+  int ch = blockIdx.x * 8 + wid;
+  auto issue = [&](int stage, const ChunkDesc &cd) {
+    if (lane == 0 && cd.nrow > 0) {
+      const unsigned sb = wbase_s + (unsigned)stage * SPMV_TMA_STAGE;
+      const unsigned bar = bar_s + 8u * (unsigned)stage;
+      const int ka = cd.k0 & ~3;
+      const unsigned vbytes = (unsigned)(cd.k1 - cd.k0) * 16u;
+      const unsigned cbytes = (unsigned)((cd.k1 - ka + 3) >> 2) * 16u;
+      fence_proxy_async();
+      mbar_expect_tx(bar, vbytes + cbytes);
+      if (vbytes) bulk_g2s(sb, vals + cd.k0, vbytes, bar);
+      if (cbytes) bulk_g2s(sb + SPMV_VAL_BYTES, colidx + ka, cbytes, bar);
+    }
+  };
+  ChunkDesc cur = load_chunk_desc(sp_chunk, rowptr, ch, n_chunks);
+  ChunkDesc nxt = load_chunk_desc(sp_chunk, rowptr, ch + stride, n_chunks);
+  int rs_cur = (lane <= cur.nrow && cur.nrow > 0) ? __ldg(&rowptr[cur.r0 + lane]) : 0;
+  issue(0, cur);
+  int st = 0;
+  unsigned phase0 = 0, phase1 = 0;
+  for (; ch < n_chunks; ch += stride) {
+    issue(st ^ 1, nxt);
+    const ChunkDesc nn = load_chunk_desc(sp_chunk, rowptr, ch + 2 * stride, n_chunks);
+    const int rs_nxt = (lane <= nxt.nrow && nxt.nrow > 0) ? __ldg(&rowptr[nxt.r0 + lane]) : 0;
+    {
+      const unsigned bar = bar_s + 8u * (unsigned)st;
+      const unsigned par = st ? phase1 : phase0;
+      while (!mbar_try_wait(bar, par)) {
+      }
+      if (st) phase1 ^= 1u; else phase0 ^= 1u;
+    }
+    unsigned char *sb = wbase + (size_t)st * SPMV_TMA_STAGE;
+    c128 *sv = (c128 *)sb;
+    const int32_t *scol = (const int32_t *)(sb + SPMV_VAL_BYTES) + (cur.k0 & 3);
+    const int n = cur.k1 - cur.k0;
+    int c[SPMV_STREAM_W / 32];
+    c128 xv8[SPMV_STREAM_W / 32];
+#pragma unroll
+    for (int j = 0; j < SPMV_STREAM_W / 32; ++j) {
+      const int i = lane + 32 * j;
+      c[j] = (i < n) ? scol[i] : -1;
+    }
+#pragma unroll
+    for (int j = 0; j < SPMV_STREAM_W / 32; ++j) xv8[j] = (c[j] >= 0) ? xload(xv, c[j]) : cmake(0.0, 0.0);
+#pragma unroll
+    for (int j = 0; j < SPMV_STREAM_W / 32; ++j) {
+      const int i = lane + 32 * j;
+      if (c[j] >= 0) xv8[j] = cmul(sv[i], xv8[j]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < SPMV_STREAM_W / 32; ++j)
+      if (c[j] >= 0) sv[spmv_slot(lane + 32 * j)] = xv8[j];
+    __syncwarp();
+    const int re_cur = __shfl_down_sync(0xffffffffu, rs_cur, 1);
+    if (lane < cur.nrow) {
+      const int row = cur.r0 + lane;
+      c128 acc = cmake(0.0, 0.0);
+      for (int k = rs_cur - cur.k0; k < re_cur - cur.k0; ++k) acc = cadd(acc, sv[spmv_slot(k)]);
+      if (EPI == 1) {
+        const c128 zi = zloc[row];
+        c128 qi = acc, pi = zi;
+        if (!first) {
+          qi = cfma(beta, q[row], acc);
+          pi = cfma(beta, p[row], zi);
+        }
+        q[row] = qi;
+        p[row] = pi;
+        const c128 t = cmul(pi, qi);
+        d[0] += t.x; d[1] += t.y;
+      } else {
+        const c128 ri = csub(bvec[row], acc);
+        const c128 zi = cmul(dinv[row], ri);
+        r[row] = ri;
+        q[row] = zi;
+        const c128 t = cmul(ri, zi);
+        d[0] += t.x; d[1] += t.y;
+        d[2] += cabs2(ri);
+      }
+    }
+    __syncwarp();
+    cur = nxt;
+    nxt = nn;
+    rs_cur = rs_nxt;
+    st ^= 1;
   }
   block_partial<3>(d, partial);
 }
@@ -574,7 +693,35 @@ static XView make_view(const System *S, const DistState *T, c128 *const *peers, 
   return v;
 }
 
-static int spmv_grid(const Ctx *c, int n_chunks) { return std::max(1, std::min((n_chunks + 7) / 8, DIST_RED_BLOCKS)); }
+
+// grid of the distributed SpMV and its launch (TMA ring by default; EDGEFEM_B200_SPMV_KERNEL=regs: register streaming)
+static bool dist_spmv_regs() {
+  static const bool v = [] {
+    const char *e = getenv("EDGEFEM_B200_SPMV_KERNEL");
+    return e && strcmp(e, "regs") == 0;
+  }();
+  return v;
+}
+static int spmv_grid(const Ctx *c, int n_chunks) {
+  if (!dist_spmv_regs()) return std::max(1, std::min((n_chunks + 7) / 8, std::min(DIST_RED_BLOCKS, c->sm_count * 2)));
+  return std::max(1, std::min((n_chunks + 7) / 8, DIST_RED_BLOCKS));
+}
+template <int EPI>
+static int launch_dist_spmv(System *S, DistState *T, const XView &xv, c128 *r, int first) {
+  Ctx *c = S->ctx;
+  const int nb = spmv_grid(c, S->n_sp_chunks);
+  if (dist_spmv_regs()) {
+    k_dist_spmv<EPI><<<nb, 256, 0, c->stream>>>(S->d_sp_chunk, S->n_sp_chunks, S->d_rowptr, S->d_colidx, S->d_vals, xv, S->d_b, T->d_dinv, T->d_z,
+                                                r, T->d_p, T->d_q, T->d_sc, first, T->d_partial);
+  } else {
+    const size_t smem = (size_t)8 * 2 * SPMV_TMA_STAGE + 8 * 16;
+    EFB_CUDA(c, cudaFuncSetAttribute(k_dist_spmv_tma<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_dist_spmv_tma<EPI><<<nb, 256, smem, c->stream>>>(S->d_sp_chunk, S->n_sp_chunks, S->d_rowptr, S->d_colidx, S->d_vals, xv, S->d_b, T->d_dinv,
+                                                       T->d_z, r, T->d_p, T->d_q, T->d_sc, first, T->d_partial);
+  }
+  EFB_CHECK_LAUNCH(c);
+  return EFB_OK;
+}
 static int vec_blocks(const Ctx *c, int m) { return std::max(1, std::min((m + DIST_VEC_THREADS - 1) / DIST_VEC_THREADS, DIST_RED_BLOCKS)); }
 
 // halo_mode 1: gather the exported vector of every rank into d_full
@@ -639,18 +786,14 @@ static int dist_residual(const DistRun &R) {
   const XView xv = make_view(S, T, T->peer_x, T->d_xs, R.mode);
   if (R.aux) {
     // r = b - A x into the exported residual, |r|^2 all-reduced (every rank's r is complete after it), then z = M^-1 r
-    k_dist_spmv<0><<<nb, 256, 0, c->stream>>>(S->d_sp_chunk, S->n_sp_chunks, S->d_rowptr, S->d_colidx, S->d_vals, xv, S->d_b, T->d_dinv, T->d_z,
-                                              T->d_rexp, T->d_p, T->d_q, T->d_sc, 1, T->d_partial);
-    EFB_CHECK_LAUNCH(c);
+    { int rcl = launch_dist_spmv<0>(S, T, xv, T->d_rexp, 1); if (rcl) return rcl; }
     k_dist_finish<3><<<1, 256, 0, c->stream>>>(T->d_partial, nb, T->d_sc, DS_RHO, 0);
     EFB_CHECK_LAUNCH(c);
     EFB_CUDA(c, cudaMemcpyAsync(T->d_sc + DS_RR2, T->d_sc + DS_RR, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     EFB_NCCL(c, R.api, R.api->AllReduce(T->d_sc + DS_RR2, T->d_sc + DS_RR2, 1, ncclFloat64, ncclSum, R.dd->comm, c->stream));
     return dist_aux_precond(R);
   }
-  k_dist_spmv<0><<<nb, 256, 0, c->stream>>>(S->d_sp_chunk, S->n_sp_chunks, S->d_rowptr, S->d_colidx, S->d_vals, xv, S->d_b, T->d_dinv, T->d_z,
-                                            T->d_r, T->d_p, T->d_q, T->d_sc, 1, T->d_partial);
-  EFB_CHECK_LAUNCH(c);
+  { int rcl = launch_dist_spmv<0>(S, T, xv, T->d_r, 1); if (rcl) return rcl; }
   k_dist_finish<3><<<1, 256, 0, c->stream>>>(T->d_partial, nb, T->d_sc, DS_RHO, 0);
   EFB_CHECK_LAUNCH(c);
   EFB_NCCL(c, R.api, R.api->AllReduce(T->d_sc + DS_RHO, T->d_sc + DS_RHO, 3, ncclFloat64, ncclSum, R.dd->comm, c->stream));
@@ -673,9 +816,7 @@ static int dist_iteration(const DistRun &R, int first) {
     if (rc) return rc;
   }
   const XView zv = make_view(S, T, T->peer_z, T->d_z, R.mode);
-  k_dist_spmv<1><<<nb, 256, 0, c->stream>>>(S->d_sp_chunk, S->n_sp_chunks, S->d_rowptr, S->d_colidx, S->d_vals, zv, S->d_b, T->d_dinv, T->d_z,
-                                            T->d_r, T->d_p, T->d_q, T->d_sc, first, T->d_partial);
-  EFB_CHECK_LAUNCH(c);
+  { int rcl = launch_dist_spmv<1>(S, T, zv, T->d_r, first); if (rcl) return rcl; }
   k_dist_finish<3><<<1, 256, 0, c->stream>>>(T->d_partial, nb, T->d_sc, DS_PQ, 1);  // partial[2] is unused by K1 (zero)
   EFB_CHECK_LAUNCH(c);
   EFB_NCCL(c, R.api, R.api->AllReduce(T->d_sc + DS_PQ, T->d_sc + DS_PQ, 2, ncclFloat64, ncclSum, R.dd->comm, c->stream));
@@ -871,9 +1012,7 @@ int efb_dist_bench(efb_system *sys_, int32_t which, int32_t reps, int32_t halo_m
       } else {
         if (halo_mode == 1 && (rc = gather_full(S, T, R.api, T->d_z))) return rc;
         const XView zv = make_view(S, T, T->peer_z, T->d_z, halo_mode);
-        k_dist_spmv<1><<<nb, 256, 0, c->stream>>>(S->d_sp_chunk, S->n_sp_chunks, S->d_rowptr, S->d_colidx, S->d_vals, zv, S->d_b, T->d_dinv,
-                                                  T->d_z, T->d_r, T->d_p, T->d_q, T->d_sc, 1, T->d_partial);
-        EFB_CHECK_LAUNCH(c);
+        if ((rc = launch_dist_spmv<1>(S, T, zv, T->d_r, 1))) return rc;
       }
     }
     EFB_CUDA(c, cudaEventRecord(e1, c->stream));
