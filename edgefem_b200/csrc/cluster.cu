@@ -272,8 +272,9 @@ k_cocg_cluster(const SolveDev D, const ClusterDev K, int first_matrix, int n_job
       }
     }
   };
-  // wp[n] = sum over the own edges at my node n of +-q_own: 4 lanes per node walk the node's ELL list with stride 4
-  // (independent loads, ~2 items per lane), two shuffle steps, fixed order
+  // wp[n] = sum over the own edges at my node n of +-q_own: 4 lanes per node, lane l takes items l, l+4, ... of the
+  // node's ELL list.  All item loads are issued first, then all q loads (no data-dependent loop exit in the common
+  // case of <= 32 own edges at a node), two shuffle steps, fixed order.
   auto nodal_partial = [&]() {
     if (!K.aux) return;
     const int l4 = lane & 3;
@@ -282,14 +283,32 @@ k_cocg_cluster(const SolveDev D, const ClusterDev K, int first_matrix, int n_job
       c128 a[NR];
 #pragma unroll
       for (int r = 0; r < NR; ++r) a[r] = cmake(0.0, 0.0);
-      if (j < n_my)
-        for (int k = l4; k < K.ndeg; k += 4) {
-          const uint32_t it = n2e_ell_s[k * K.max_my + j];
-          if (it == 0xffffu) break;  // items are packed at the front
-          const c128 *v = q_own + (size_t)(it >> 1) * NR;
+      if (j < n_my) {
+        uint32_t it[8];
 #pragma unroll
-          for (int r = 0; r < NR; ++r) a[r] = (it & 1u) ? cadd(a[r], v[r]) : csub(a[r], v[r]);
+        for (int u = 0; u < 8; ++u) {
+          const int k = l4 + 4 * u;
+          it[u] = k < K.ndeg ? (uint32_t)n2e_ell_s[k * K.max_my + j] : 0xffffu;
         }
+        c128 v[8][NR];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+          for (int r = 0; r < NR; ++r) v[u][r] = it[u] != 0xffffu ? q_own[(size_t)(it[u] >> 1) * NR + r] : cmake(0.0, 0.0);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+          for (int r = 0; r < NR; ++r) a[r] = (it[u] & 1u) ? cadd(a[r], v[u][r]) : csub(a[r], v[u][r]);
+        for (int k = l4 + 32; k < K.ndeg; k += 4) {  // nodes with more than 32 own edges (rare)
+          const uint32_t itk = n2e_ell_s[k * K.max_my + j];
+          if (itk == 0xffffu) break;
+#pragma unroll
+          for (int r = 0; r < NR; ++r) {
+            const c128 vv = q_own[(size_t)(itk >> 1) * NR + r];
+            a[r] = (itk & 1u) ? cadd(a[r], vv) : csub(a[r], vv);
+          }
+        }
+      }
 #pragma unroll
       for (int r = 0; r < NR; ++r)
 #pragma unroll
@@ -309,9 +328,26 @@ k_cocg_cluster(const SolveDev D, const ClusterDev K, int first_matrix, int n_job
       c128 a[NR];
 #pragma unroll
       for (int r = 0; r < NR; ++r) a[r] = cmake(0.0, 0.0);
-      for (int k = 0; k < K.sdeg; ++k) {
+      {  // up to four sources with independent (remote) loads, ascending rank; more: the serial tail
+        uint32_t it[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) it[u] = u < K.sdeg ? nsrc_ell_s[u * K.max_my + j] : 0xffffffffu;
+        c128 v[4][NR];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const c128 *src = ((int)(it[u] >> 16) == crank || it[u] == 0xffffffffu ? wp : cluster.map_shared_rank(wp, it[u] >> 16)) +
+                            (size_t)(it[u] == 0xffffffffu ? 0u : (it[u] & 0xffffu)) * NR;
+#pragma unroll
+          for (int r = 0; r < NR; ++r) v[u][r] = it[u] != 0xffffffffu ? src[r] : cmake(0.0, 0.0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int r = 0; r < NR; ++r) a[r] = cadd(a[r], v[u][r]);
+      }
+      for (int k = 4; k < K.sdeg; ++k) {
         const uint32_t it = nsrc_ell_s[k * K.max_my + j];
-        if (it == 0xffffffffu) break;  // sources are packed at the front, ascending rank
+        if (it == 0xffffffffu) break;
         const c128 *v = ((int)(it >> 16) == crank ? wp : cluster.map_shared_rank(wp, it >> 16)) + (size_t)(it & 0xffffu) * NR;
 #pragma unroll
         for (int r = 0; r < NR; ++r) a[r] = cadd(a[r], v[r]);
