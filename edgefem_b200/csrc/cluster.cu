@@ -800,8 +800,11 @@ int run_krylov_cluster(SolvePlan &P, const efb_solve_opts *o, bool zero_x, bool 
   EFB_CUDA(c, cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
   SubTrace st;
   const int n_rhs = S->n_rhs;
-  int nr_want = (n_rhs % 2 == 0) ? 2 : 1;
-  if (const char *e = getenv("EDGEFEM_B200_CLUSTER_NR")) nr_want = std::max(1, std::min(nr_want, atoi(e)));
+  // One right-hand side per job.  Two per job (sharing the matrix reads and the barriers) is templated but NOT enabled:
+  // next to a complex matrix slice it only fits without the auxiliary space, it was measured slower there (SpMV 2.3x for
+  // two right-hand sides: 32-byte gathers halve the distinct bank groups), and its iteration showed a convergence defect
+  // (first p update) that was not tracked down.
+  const int nr_want = 1;
   ClusterPlanDev *PL = S->cl_plan ? ((std::shared_ptr<ClusterPlanDev> *)S->cl_plan)->get() : nullptr;
   const uint8_t *dirp = (int)S->h_dir.size() == S->m ? S->h_dir.data() : nullptr;
   auto fits = [&](const ClusterPlanHost &H, int nr, int *rpt_out, int *nth_out) {
@@ -940,11 +943,7 @@ int run_krylov_cluster(SolvePlan &P, const efb_solve_opts *o, bool zero_x, bool 
   int rc = EFB_OK, ncl = 0;
 #define EFB_CL(NRV, RPTV)                                                                                                             \
   rc = launch_cluster<NRV, RPTV>(c, P.D, PL->d, nth, smem, P.first_matrix, n_jobs, groups, S->d_job, S->d_b, S->d_x, zero_x ? 1 : 0, mr, &ncl)
-  if (nr == 2) {
-    if (rpt == 1) EFB_CL(2, 1); else if (rpt == 2) EFB_CL(2, 2); else EFB_CL(2, 4);
-  } else {
-    if (rpt == 1) EFB_CL(1, 1); else if (rpt == 2) EFB_CL(1, 2); else EFB_CL(1, 4);
-  }
+  if (rpt == 1) EFB_CL(1, 1); else if (rpt == 2) EFB_CL(1, 2); else EFB_CL(1, 4);
 #undef EFB_CL
   if (rc) return rc;
   EFB_CUDA(c, cudaEventRecord(S->ev_s1, c->stream));

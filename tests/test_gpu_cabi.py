@@ -126,3 +126,27 @@ def test_single_rhs_and_odd_batch(ctx, wr90):
         p = orc.MaxwellParams(omega=2 * math.pi * f)
         S_o = orc.calculate_sparams_eigenmode(mesh, p, pec, ports)
         assert np.max(np.abs(S[fi] - S_o)) <= 1e-6
+
+
+@pytest.mark.parametrize("cl,nr", [(2, 1), (4, 1), (8, 1)])
+@pytest.mark.parametrize("precond", [cabi.PRECOND_AUX, cabi.PRECOND_JACOBI])
+def test_cluster_solver_shapes(ctx, cl, nr, precond, monkeypatch):
+    """The cluster-split persistent solver with 2, 4 and 8 CTAs per cluster, with and without the auxiliary space, on a small
+    two-port guide against the oracle's direct solve (one right-hand side per job: the only enabled shape)."""
+    from edgefem_b200 import meshgen
+
+    xyz, tets, tp, tris, trp = meshgen.rect_waveguide(a=0.02286, b=0.01016, length=0.03, nx=6, ny=3, nz=10)
+    mesh = orc.mesh_from_arrays(xyz, tets, tp, tris, trp)
+    pec = orc.build_edge_pec(mesh, 1)
+    f = 10e9
+    ports = orc.wr90_ports(mesh, pec, f)
+    S_ref = orc.wr90_sparams(mesh, pec, f, ports)
+    monkeypatch.setenv("EDGEFEM_B200_CLUSTER", str(cl))
+    keep = {}
+    S, res = H.eigenmode_sweep_gpu(ctx, mesh, pec, ports, [f], method=cabi.METHOD_COCG, precond=precond, keep=keep)
+    shape = keep["sys"].last_solve_shape() if "sys" in keep else None
+    print("cluster", cl, "nr", nr, "precond", precond, "shape", shape, "iters", [r["iters"] for r in res])
+    assert all(r["converged"] for r in res), res
+    assert np.max(np.abs(S[0] - S_ref)) <= 1e-6
+    if shape is not None:
+        assert shape[0] == cl and shape[1] == nr
