@@ -27,6 +27,15 @@ constexpr double eta0 = mu0 * c0;
 const cplx kNaN(std::numeric_limits<double>::quiet_NaN(), std::numeric_limits<double>::quiet_NaN());
 
 // ------------------------------------------------------------------ RAII over the C-ABI
+struct DeviceSystem {
+  efb_system *h = nullptr;
+  int m = 0, n_matrix = 0, n_rhs = 0;
+  std::int64_t nnz = 0;
+  ~DeviceSystem() {
+    if (h) efb_system_destroy(h);
+  }
+};
+
 struct DeviceMesh {
   efb_mesh *h = nullptr;
   std::vector<int32_t> slot_tags;
@@ -35,17 +44,30 @@ struct DeviceMesh {
   const Mesh *addr = nullptr;
   size_t n_nodes = 0, n_tets = 0, n_edges = 0;
   std::uint64_t hash = 0;
+  // Per-mesh reuse for drivers that are called once per frequency (calculate_sparams_eigenmode in a Python loop,
+  // python/edgefem/designs/waveguide.py:394-433): the device system of the last call (pattern, maps, solver structures,
+  // cluster plan; every value is rewritten by efb_assemble_volume) and the host-side port surface mass matrices.
+  struct PooledSystem {
+    std::uint64_t key = 0;
+    std::unique_ptr<DeviceSystem> sys;
+  };
+  std::vector<PooledSystem> pool;  // at most 2, small systems only
+  struct PortMass {
+    int tag = 0;
+    std::uint64_t dir_hash = 0;
+    SparseMatrix<double> Ms;
+  };
+  std::vector<PortMass> port_mass;  // at most 8
+  struct PortTag {
+    int surface_tag = 0;
+    bool found = false;
+    int tag = 0;
+  };
+  std::vector<PortTag> port_tags;
+  std::uint64_t tri_hash = 0;  // of mesh.tris when the two port caches were filled (the device mesh itself does not use them)
   ~DeviceMesh() {
+    pool.clear();  // systems refer to the mesh
     if (h) efb_mesh_destroy(h);
-  }
-};
-
-struct DeviceSystem {
-  efb_system *h = nullptr;
-  int m = 0, n_matrix = 0, n_rhs = 0;
-  std::int64_t nnz = 0;
-  ~DeviceSystem() {
-    if (h) efb_system_destroy(h);
   }
 };
 
@@ -158,6 +180,58 @@ std::shared_ptr<DeviceMesh> device_mesh_for(const Mesh &mesh) {
   g_mesh_cache.insert(g_mesh_cache.begin(), dm);
   if (g_mesh_cache.size() > 2) g_mesh_cache.pop_back();
   return dm;
+}
+
+
+std::uint64_t fnv_bytes(std::uint64_t h, const void *ptr, size_t bytes) {
+  const unsigned char *b = (const unsigned char *)ptr;
+  size_t i = 0;
+  for (; i + 8 <= bytes; i += 8) {
+    std::uint64_t w;
+    std::memcpy(&w, b + i, 8);
+    h = (h ^ w) * 1099511628211ull;
+  }
+  for (; i < bytes; ++i) h = (h ^ b[i]) * 1099511628211ull;
+  return h;
+}
+
+constexpr double kPoolMaxBytes = 512e6;
+
+// surface triangles (connectivity, tags, edge ids) are not part of the device-mesh fingerprint; the port caches hang on them
+void sync_port_caches(DeviceMesh &dm, const Mesh &mesh) {
+  std::uint64_t h = 1469598103934665603ull;
+  for (const Element &t : mesh.tris) {
+    const std::int64_t rec[7] = {t.conn[0], t.conn[1], t.conn[2], (std::int64_t)t.phys, (std::int64_t)t.edges[0], (std::int64_t)t.edges[1],
+                                 (std::int64_t)t.edges[2]};
+    h = fnv_bytes(h, rec, sizeof rec);
+  }
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (dm.tri_hash != h) {
+    dm.port_mass.clear();
+    dm.port_tags.clear();
+    dm.tri_hash = h;
+  }
+}
+
+std::unique_ptr<DeviceSystem> pool_take(DeviceMesh &dm, std::uint64_t key, int n_matrix, int n_rhs) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (size_t i = 0; i < dm.pool.size(); ++i)
+    if (dm.pool[i].key == key && dm.pool[i].sys->n_matrix == n_matrix && dm.pool[i].sys->n_rhs == n_rhs) {
+      auto s = std::move(dm.pool[i].sys);
+      dm.pool.erase(dm.pool.begin() + (long)i);
+      return s;
+    }
+  return nullptr;
+}
+
+void pool_give(DeviceMesh &dm, std::uint64_t key, std::unique_ptr<DeviceSystem> sys) {
+  if (!sys || (double)sys->nnz * 16.0 * sys->n_matrix + (double)sys->m * 160.0 * sys->n_matrix * sys->n_rhs > kPoolMaxBytes) return;
+  std::lock_guard<std::mutex> lk(g_mu);
+  DeviceMesh::PooledSystem e;
+  e.key = key;
+  e.sys = std::move(sys);
+  dm.pool.insert(dm.pool.begin(), std::move(e));
+  if (dm.pool.size() > 2) dm.pool.pop_back();
 }
 
 }  // namespace
@@ -629,6 +703,60 @@ std::vector<PortRegion> port_regions(const Mesh &mesh, const std::vector<WavePor
   return out;
 }
 
+
+std::vector<PortRegion> cached_port_regions(DeviceMesh &dm, const Mesh &mesh, const std::vector<WavePort> &ports) {
+  std::vector<PortRegion> out(ports.size());
+  std::vector<WavePort> miss;
+  std::vector<size_t> miss_at;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (size_t i = 0; i < ports.size(); ++i) {
+      bool hit = false;
+      for (const auto &t : dm.port_tags)
+        if (t.surface_tag == ports[i].surface_tag) {
+          out[i].found = t.found;
+          out[i].tag = t.tag;
+          hit = true;
+          break;
+        }
+      if (!hit) {
+        WavePort w;
+        w.surface_tag = ports[i].surface_tag;
+        miss.push_back(w);
+        miss_at.push_back(i);
+      }
+    }
+  }
+  if (miss.empty()) return out;
+  const std::vector<PortRegion> r = port_regions(mesh, miss);
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (size_t k = 0; k < miss.size(); ++k) {
+    out[miss_at[k]] = r[k];
+    DeviceMesh::PortTag t;
+    t.surface_tag = miss[k].surface_tag;
+    t.found = r[k].found;
+    t.tag = r[k].tag;
+    dm.port_tags.push_back(t);
+  }
+  return out;
+}
+
+SparseMatrix<double> cached_port_mass(DeviceMesh &dm, const Mesh &mesh, int surface_tag, const BC &bc, std::uint64_t dir_hash) {
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (const auto &e : dm.port_mass)
+      if (e.tag == surface_tag && e.dir_hash == dir_hash) return e.Ms;
+  }
+  DeviceMesh::PortMass e;
+  e.tag = surface_tag;
+  e.dir_hash = dir_hash;
+  e.Ms = assemble_port_surface_mass(mesh, surface_tag, bc.dirichlet_edges);
+  std::lock_guard<std::mutex> lk(g_mu);
+  dm.port_mass.insert(dm.port_mass.begin(), e);
+  if (dm.port_mass.size() > 8) dm.port_mass.pop_back();
+  return e.Ms;
+}
+
 } // namespace
 
 // ------------------------------------------------------------------ detail
@@ -880,9 +1008,11 @@ std::vector<MatrixXcd> calculate_sparams_eigenmode_sweep(const Mesh &mesh, const
     }
   // M_s entries lie inside the volume pattern for a port face of a tet; listed anyway so a
   // tri-only port edge cannot fall outside (coeffRef would insert it, assemble_maxwell.cpp:743)
+  const std::uint64_t dir_hash = fnv_bytes(1469598103934665603ull, dir.data(), dir.size());
+  sync_port_caches(*dm, mesh);
   std::vector<SparseMatrix<double>> Ms(P);
   for (int i = 0; i < P; ++i) {
-    Ms[i] = assemble_port_surface_mass(mesh, ports[i].surface_tag, bc.dirichlet_edges);
+    Ms[i] = cached_port_mass(*dm, mesh, ports[i].surface_tag, bc, dir_hash);
     const auto &rp = Ms[i].rowptr();
     for (int r = 0; r < Ms[i].rows(); ++r)
       for (int k = rp[r]; k < rp[r + 1]; ++k) {
@@ -890,7 +1020,9 @@ std::vector<MatrixXcd> calculate_sparams_eigenmode_sweep(const Mesh &mesh, const
         xc.push_back(Ms[i].colidx()[k]);
       }
   }
-  const std::vector<PortRegion> regions = port_regions(mesh, ports);
+  const std::vector<PortRegion> regions = cached_port_regions(*dm, mesh, ports);
+  std::uint64_t sys_key = fnv_bytes(dir_hash, xr.data(), xr.size() * sizeof(int32_t));
+  sys_key = fnv_bytes(sys_key, xc.data(), xc.size() * sizeof(int32_t));
   tr.mark("port surface mass + port regions (host)");
   // frequencies are processed in device batches that fit comfortably in HBM
   // upper bound of nnz without building the pattern: 36 triplets per tet + extras
@@ -929,10 +1061,15 @@ std::vector<MatrixXcd> calculate_sparams_eigenmode_sweep(const Mesh &mesh, const
       }
     }
     detail::check(efb_timer_start(ctx), "efb_timer_start");
-    auto sys = make_system(*dm, xr, xc, nb, P);
-    detail::check(efb_system_set_dirichlet(sys->h, dir.data()), "efb_system_set_dirichlet");
-    g_bytes_h2d += (long long)dir.size();
-    tr.mark("system (pattern + maps + allocations)");
+    // the system of the previous call on this mesh with the same pattern, Dirichlet set and shape is reused: every value
+    // and right-hand side is rewritten by efb_assemble_volume, the solve starts from x = 0
+    auto sys = pool_take(*dm, sys_key, nb, P);
+    if (!sys) {
+      sys = make_system(*dm, xr, xc, nb, P);
+      detail::check(efb_system_set_dirichlet(sys->h, dir.data()), "efb_system_set_dirichlet");
+      g_bytes_h2d += (long long)dir.size();
+    }
+    tr.mark("system (pattern + maps + allocations, or pooled)");
     MaxwellParams pf = p;
     assemble_volume(*sys, *dm, pf, omegas, 0, 0);
     tr.mark("volume assembly launch");
@@ -996,7 +1133,7 @@ std::vector<MatrixXcd> calculate_sparams_eigenmode_sweep(const Mesh &mesh, const
     device_ms += ms;
     tr.mark("projection + S");
     dp.clear();
-    sys.reset();
+    pool_give(*dm, sys_key, std::move(sys));
     tr.mark("release");
   }
   if (stats) {

@@ -215,6 +215,40 @@ def test_calculate_sparams_eigenmode_kat_table(kat):
         assert abs(S[0, 0]) < 0.15 and abs(S[1, 0]) > 0.90 and abs(S[0, 0]) ** 2 + abs(S[1, 0]) ** 2 <= 1.05
 
 
+def test_per_frequency_calls_reuse_the_device_system():
+    """calculate_sparams_eigenmode in a frequency loop (python/edgefem/designs/waveguide.py:394-433) keeps the device system
+    and the port surface matrices of the previous call: a call must not see what the one before left behind."""
+    hm, om = both_meshes("rect_waveguide")
+    bc = pe.build_edge_pec(hm, 1)
+    dims = pe.RectWaveguidePort(0.02286, 0.01016)
+    ports = [pe.build_wave_port_2d(hm, tag, pe.solve_te10_mode(dims, 10e9), set(bc.dirichlet_edges), (math.pi / 0.02286) ** 2) for tag in (2, 3)]
+
+    def call(f, scale=1.0):
+        p = pe.MaxwellParams()
+        p.omega = 2 * math.pi * f
+        p.port_abc_scale = scale
+        return np.array(pe.calculate_sparams_eigenmode(hm, p, bc, ports))
+
+    chain = [call(9e9), call(11.5e9), call(9e9, 0.5), call(9e9)]
+    fresh = []
+    for f, sc in ((9e9, 1.0), (11.5e9, 1.0), (9e9, 0.5), (9e9, 1.0)):
+        pe.b200_clear_cache()
+        fresh.append(call(f, sc))
+    # repeats agree to the solver tolerance (1e-10 relative residual), not bitwise: measured 2e-13 .. 5e-12
+    for a, b in zip(chain, fresh):
+        assert np.max(np.abs(a - b)) <= 1e-9
+    assert np.max(np.abs(chain[0] - chain[3])) <= 1e-9 and np.max(np.abs(chain[0] - chain[2])) > 1e-3
+    # another Dirichlet set on the same mesh takes another system
+    bc2 = pe.build_edge_pec(hm, 1)
+    bc2.merge(pe.build_edge_pec(hm, 3))
+    ports2 = [pe.build_wave_port_2d(hm, 2, pe.solve_te10_mode(dims, 10e9), set(bc2.dirichlet_edges), (math.pi / 0.02286) ** 2)]
+    p = pe.MaxwellParams()
+    p.omega = 2 * math.pi * 10e9
+    S_short = np.array(pe.calculate_sparams_eigenmode(hm, p, bc2, ports2))
+    assert abs(abs(S_short[0, 0]) - 1.0) < 2e-3  # shorted guide: total reflection (measured 0.9996)
+    assert np.max(np.abs(call(9e9) - chain[0])) <= 1e-9
+
+
 def test_alpha_sweep_kat(kat):
     """docs/validation.md:51-57 via port_abc_scale."""
     hm, om = both_meshes("rect_waveguide")
