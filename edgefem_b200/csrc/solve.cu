@@ -691,15 +691,37 @@ k_bicg_x(SolveDev D, int first_sys, c128 *__restrict__ x, c128 *__restrict__ r, 
 // and CTAs pull the next matrix from an atomic queue when theirs has converged.
 constexpr int SMALL_LPR = 16;
 
+// Index lists of the compact numbering (free unknown -> edge id, node -> incident free edges).  They are the same for every
+// job of a launch; when they fit beside p and w they are staged ONCE per CTA in shared memory as 16-bit values: the nodal
+// gather's chain pointer -> item -> r and the chains orig -> x / 1/diag then cost one L2 round trip instead of two or three
+// (the gather alone was 29 % of the iteration from global memory).
+struct SmallLists {
+  long long *prof;  // EDGEFEM_B200_SMALL_PROF=1: cycles per phase of CTA 0 (thread 0), else NULL
+  const int32_t *g_orig, *g_ptr, *g_item;
+  const uint16_t *s_orig, *s_ptr, *s_item;
+  int staged;
+  __device__ __forceinline__ int orig(int i) const { return staged ? (int)s_orig[i] : __ldg(&g_orig[i]); }
+  __device__ __forceinline__ int ptr(int n) const { return staged ? (int)s_ptr[n] : __ldg(&g_ptr[n]); }
+  __device__ __forceinline__ int item(int k) const { return staged ? (int)s_item[k] : __ldg(&g_item[k]); }
+};
+#define EFB_SPROF(k)                                   \
+  do {                                                 \
+    if (L.prof && blockIdx.x == 0 && tid == 0) {       \
+      const long long t_ = clock64();                  \
+      L.prof[k] += t_ - xt;                            \
+      xt = t_;                                         \
+    }                                                  \
+  } while (0)
+static size_t small_lists_bytes(int mc, int nn) { return ((size_t)mc + (nn ? (size_t)nn + 1 + 2 * (size_t)mc : 0) + 8) * sizeof(uint16_t); }
+
 // One job of the persistent solver: matrix f, the NR right-hand sides starting at system s0, solved to convergence by
 // the whole CTA (see k_cocg_small below).
 template <int NR, int SPD, bool DB>
 __device__ __forceinline__ void cocg_small_job(const SolveDev &D, const int32_t *__restrict__ sell_ptr, const int32_t *__restrict__ sell_col,
                                                const int32_t *__restrict__ sell_perm, const c128 *__restrict__ sell_vals, long long sell_total,
                                                int n_slices, const c128 *__restrict__ bvec, c128 *xvec, c128 *rvec, c128 *qvec, int aux, int zero_x,
-                                               int max_restarts, int mc, const int32_t *__restrict__ c_orig,
-                                               const int2 *__restrict__ c_edge_nodes, const int32_t *__restrict__ c_n2e_ptr,
-                                               const int32_t *__restrict__ c_n2e_item, unsigned char *sm_raw, int f, int s0) {
+                                               int max_restarts, int mc, const SmallLists &L,
+                                               const int2 *__restrict__ c_edge_nodes, unsigned char *sm_raw, int f, int s0) {
   const int m = D.m, nn = aux ? D.n_node : 0;
   c128 *p_s = (c128 *)sm_raw;                 // [NR][mc]
   c128 *w_s = p_s + (size_t)NR * mc;          // [NR][nn]
@@ -716,7 +738,14 @@ __device__ __forceinline__ void cocg_small_job(const SolveDev &D, const int32_t 
     __device__ __forceinline__ c128 *operator[](int r) const { return base + (size_t)r * m; }
   };
   const size_t off0 = (size_t)s0 * m;
-  const VRef xg{xvec + off0, m}, rg{rvec + off0, m}, qg{qvec + off0, m}, bg{const_cast<c128 *>(bvec) + off0, m};
+  const VRef xg{xvec + off0, m}, qg{qvec + off0, m}, bg{const_cast<c128 *>(bvec) + off0, m};
+  // r is interleaved by right-hand side, r[i][NR]: the nodal gather of the preconditioner reads it at random, and the NR values of
+  // an edge then share one 32-byte sector instead of wasting half of NR sectors
+  struct RRef {
+    c128 *base;
+    __device__ __forceinline__ c128 &operator()(int r, int i) const { return base[(size_t)i * NR + r]; }
+  };
+  const RRef rg{rvec + off0};
   // block-uniform scalars live in shared memory (written by thread 0 between barriers): bb, rr and a
   // double-buffered rho per right-hand side
   double *sc_bb = red + 33 * 8, *sc_rr = sc_bb + NR, *sc_rho = sc_rr + NR;  // sc_rho[parity][r][2]
@@ -902,13 +931,13 @@ __device__ __forceinline__ void cocg_small_job(const SolveDev &D, const int32_t 
     double d4[2 * NR];
     if (cycle == 0 && zero_x) {
       for (int i = tid; i < mc; i += nth) {
-        const int e = __ldg(&c_orig[i]);
+        const int e = L.orig(i);
 #pragma unroll
         for (int r = 0; r < NR; ++r) { xg[r][e] = cmake(0.0, 0.0); qg[r][i] = cmake(0.0, 0.0); }
       }
     } else {
       for (int i = tid; i < mc; i += nth) {
-        const int e = __ldg(&c_orig[i]);
+        const int e = L.orig(i);
 #pragma unroll
         for (int r = 0; r < NR; ++r) p_s[(size_t)r * mc + i] = xg[r][e];
       }
@@ -919,12 +948,12 @@ __device__ __forceinline__ void cocg_small_job(const SolveDev &D, const int32_t 
 #pragma unroll
     for (int k = 0; k < 2 * NR; ++k) d4[k] = 0.0;
     for (int i = tid; i < mc; i += nth) {
-      const int e = __ldg(&c_orig[i]);
+      const int e = L.orig(i);
 #pragma unroll
       for (int r = 0; r < NR; ++r) {
         const c128 bi = bg[r][e];
         const c128 ri = csub(bi, qg[r][i]);
-        rg[r][i] = ri;
+        rg(r, i) = ri;
         d4[2 * r] += cabs2(ri);
         d4[2 * r + 1] += cabs2(bi);
       }
@@ -945,53 +974,77 @@ __device__ __forceinline__ void cocg_small_job(const SolveDev &D, const int32_t 
     // (2)+(3) preconditioned COCG until the recursive residual converges.  Two block reductions per
     // iteration: (rho_new = r^T z, |r|^2) after the preconditioner and p^T A p after the SpMV.
     bool fresh = true;  // p = z on entry, p = z + beta p afterwards
+    long long xt = L.prof ? clock64() : 0;
     for (;;) {
+      EFB_SPROF(7);
       // z = M^-1 r  (z parked in q), rho_new = r^T z, rr = |r|^2
       if (aux) {
         // nodal gather w = diag(G^T A G)^-1 G^T r: 16 lanes cooperate on a node (its ~12 incident edges are
         // fetched in one parallel step instead of a serial chain), half-warp shuffle reduction
+        // Two nodes per half-warp step: their r loads and shuffle trees are independent chains, and 1/L is requested
+        // before the gather instead of after the reduction (the step was one serial chain r -> shuffles -> 1/L -> store;
+        // 29 % of the iteration).  Lanes and shuffle tree are those of the one-node form: the sums are bit-identical.
         const int l16 = tid & 15, g16 = tid >> 4, ng16 = nth >> 4;
         const unsigned hmask = 0xffffu << (((tid & 31) >> 4) * 16);
-        for (int n = g16; n < nn; n += ng16) {
-          const int kb = __ldg(&c_n2e_ptr[n]), ke = __ldg(&c_n2e_ptr[n + 1]);
-          c128 a2[NR];
+        for (int n0 = 2 * g16; n0 < nn; n0 += 2 * ng16) {
+          const bool two = n0 + 1 < nn;
+          const int kb0 = L.ptr(n0), ke0 = L.ptr(n0 + 1), ke1 = two ? L.ptr(n0 + 2) : ke0;
+          const int it0 = kb0 + l16 < ke0 ? L.item(kb0 + l16) : -1;  // compact edge << 1 | head (Dirichlet edges are not in the lists)
+          const int it1 = ke0 + l16 < ke1 ? L.item(ke0 + l16) : -1;
+          const c128 li = __ldg(&linv[n0 + ((l16 & 1) && two ? 1 : 0)]);  // lane 0 stores node n0, lane 1 node n0 + 1
+          c128 a2[2][NR];
 #pragma unroll
-          for (int r = 0; r < NR; ++r) a2[r] = cmake(0.0, 0.0);
-          for (int k = kb + l16; k < ke; k += 16) {
-            const int it = __ldg(&c_n2e_item[k]);  // compact edge << 1 | head (Dirichlet edges are not in the lists)
-            const int e = it >> 1;
+          for (int r = 0; r < NR; ++r) {
+            c128 v0 = cmake(0.0, 0.0), v1 = cmake(0.0, 0.0);
+            if (it0 >= 0) v0 = rg(r, it0 >> 1);
+            if (it1 >= 0) v1 = rg(r, it1 >> 1);
+            a2[0][r] = (it0 & 1) ? v0 : cneg(v0);
+            a2[1][r] = (it1 & 1) ? v1 : cneg(v1);
+          }
+          for (int k = kb0 + 16 + l16; k < ke0; k += 16) {  // more than 16 incident free edges: rare
+            const int it = L.item(k);
 #pragma unroll
             for (int r = 0; r < NR; ++r) {
-              const c128 v = rg[r][e];
-              a2[r] = (it & 1) ? cadd(a2[r], v) : csub(a2[r], v);
+              const c128 v = rg(r, it >> 1);
+              a2[0][r] = (it & 1) ? cadd(a2[0][r], v) : csub(a2[0][r], v);
+            }
+          }
+          for (int k = ke0 + 16 + l16; k < ke1; k += 16) {
+            const int it = L.item(k);
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+              const c128 v = rg(r, it >> 1);
+              a2[1][r] = (it & 1) ? cadd(a2[1][r], v) : csub(a2[1][r], v);
             }
           }
 #pragma unroll
-          for (int r = 0; r < NR; ++r)
+          for (int o = 8; o > 0; o >>= 1)
 #pragma unroll
-            for (int o = 8; o > 0; o >>= 1) {
-              a2[r].x += __shfl_xor_sync(hmask, a2[r].x, o);
-              a2[r].y += __shfl_xor_sync(hmask, a2[r].y, o);
-            }
-          if (l16 == 0) {
-            const c128 li = __ldg(&linv[n]);
+            for (int u = 0; u < 2; ++u)
 #pragma unroll
-            for (int r = 0; r < NR; ++r) w_s[(size_t)r * nn + n] = cmul(li, a2[r]);
+              for (int r = 0; r < NR; ++r) {
+                a2[u][r].x += __shfl_xor_sync(hmask, a2[u][r].x, o);
+                a2[u][r].y += __shfl_xor_sync(hmask, a2[u][r].y, o);
+              }
+          if (l16 == 0 || (l16 == 1 && two)) {
+#pragma unroll
+            for (int r = 0; r < NR; ++r) w_s[(size_t)r * nn + n0 + l16] = cmul(li, l16 ? a2[1][r] : a2[0][r]);
           }
         }
         __syncthreads();
       }
+      EFB_SPROF(0);
       double dz[3 * NR];
 #pragma unroll
       for (int k = 0; k < 3 * NR; ++k) dz[k] = 0.0;
       for (int e = tid; e < mc; e += nth) {
-        const c128 di = __ldg(&dinv[__ldg(&c_orig[e])]);
+        const c128 di = __ldg(&dinv[L.orig(e)]);
         int2 ab = make_int2(0, 0);
         const bool g = aux != 0;
         if (g) ab = __ldg(&c_edge_nodes[e]);
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
-          const c128 ri = rg[r][e];
+          const c128 ri = rg(r, e);
           c128 z = cmul(di, ri);
           if (g) z = cadd(z, csub(w_s[(size_t)r * nn + ab.y], w_s[(size_t)r * nn + ab.x]));
           qg[r][e] = z;
@@ -1000,7 +1053,9 @@ __device__ __forceinline__ void cocg_small_job(const SolveDev &D, const int32_t 
           dz[3 * r + 2] += cabs2(ri);
         }
       }
+      EFB_SPROF(1);
       block_allreduce<3 * NR>(dz, red);
+      EFB_SPROF(2);
       bool still = false;
       c128 beta[NR];
 #pragma unroll
@@ -1029,10 +1084,13 @@ __device__ __forceinline__ void cocg_small_job(const SolveDev &D, const int32_t 
         }
       fresh = false;
       __syncthreads();
+      EFB_SPROF(3);
       // q = A p ; alpha = rho / p^T q
       double dq[2 * NR];
       spmv(true, dq);
+      EFB_SPROF(4);
       block_allreduce<2 * NR>(dq, red);
+      EFB_SPROF(5);
       c128 alpha[NR];
 #pragma unroll
       for (int r = 0; r < NR; ++r) {
@@ -1045,18 +1103,19 @@ __device__ __forceinline__ void cocg_small_job(const SolveDev &D, const int32_t 
       }
       // x += alpha p ; r -= alpha q   (|r|^2 is accumulated by the next preconditioner pass)
       for (int i = tid; i < mc; i += nth) {
-        const int e = __ldg(&c_orig[i]);
+        const int e = L.orig(i);
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
           if (!act[r]) continue;
           xg[r][e] = cfma(alpha[r], p_s[(size_t)r * mc + i], xg[r][e]);
-          rg[r][i] = cfma(cneg(alpha[r]), qg[r][i], rg[r][i]);
+          rg(r, i) = cfma(cneg(alpha[r]), qg[r][i], rg(r, i));
         }
       }
       bool any2 = false;
 #pragma unroll
       for (int r = 0; r < NR; ++r) any2 |= act[r];
       __syncthreads();
+      EFB_SPROF(6);
       if (!any2) break;
     }
   }
@@ -1079,7 +1138,7 @@ k_cocg_small(SolveDev D, const int32_t *__restrict__ sell_ptr, const int32_t *__
              const c128 *__restrict__ sell_vals, long long sell_total, int n_slices, int first_matrix, int n_jobs, int groups_per_matrix, int mixed,
              int *job_counter, const c128 *__restrict__ bvec, c128 *xvec, c128 *rvec, c128 *qvec, int aux, int zero_x, int max_restarts,
              int mc, const int32_t *__restrict__ c_orig, const int2 *__restrict__ c_edge_nodes, const int32_t *__restrict__ c_n2e_ptr,
-             const int32_t *__restrict__ c_n2e_item) {
+             const int32_t *__restrict__ c_n2e_item, int stage_off, long long *prof) {
   // The solver runs on the mc FREE unknowns ("compact" ids, c_orig maps them to edge ids): r, q, p and the SELL
   // structure are compact, b, x, dinv keep the original layout (stride m).
   // Job codes: plain index (matrix = code / groups, NR right-hand sides of group code % groups), or -- mixed mode, two
@@ -1089,6 +1148,20 @@ k_cocg_small(SolveDev D, const int32_t *__restrict__ sell_ptr, const int32_t *__
   extern __shared__ __align__(16) unsigned char sm_raw[];
   __shared__ int s_job;
   const int tid = threadIdx.x;
+  SmallLists L{prof, c_orig, c_n2e_ptr, c_n2e_item, nullptr, nullptr, nullptr, 0};
+  if (stage_off > 0) {  // 16-bit copies of the lists behind the solver's own shared memory (host checked the ranges)
+    uint16_t *so = (uint16_t *)(sm_raw + stage_off), *sp = so + mc, *si = sp + (aux ? D.n_node + 1 : 0);
+    for (int i = tid; i < mc; i += NT) so[i] = (uint16_t)__ldg(&c_orig[i]);
+    if (aux) {
+      for (int i = tid; i <= D.n_node; i += NT) sp[i] = (uint16_t)__ldg(&c_n2e_ptr[i]);
+      const int n_item = __ldg(&c_n2e_ptr[D.n_node]);
+      for (int i = tid; i < n_item; i += NT) si[i] = (uint16_t)__ldg(&c_n2e_item[i]);
+    }
+    L.s_orig = so;
+    L.s_ptr = sp;
+    L.s_item = si;
+    L.staged = 1;
+  }
   for (;;) {
     if (tid == 0) {
       const int q = atomicAdd(job_counter, 1);
@@ -1102,14 +1175,14 @@ k_cocg_small(SolveDev D, const int32_t *__restrict__ sell_ptr, const int32_t *__
       const int f = first_matrix + (job >> 2), kind = job & 3;
       if (kind == 0)
         cocg_small_job<2, SPD, DB>(D, sell_ptr, sell_col, sell_perm, sell_vals, sell_total, n_slices, bvec, xvec, rvec, qvec, aux, zero_x,
-                                   max_restarts, mc, c_orig, c_edge_nodes, c_n2e_ptr, c_n2e_item, sm_raw, f, f * D.n_rhs);
+                                   max_restarts, mc, L, c_edge_nodes, sm_raw, f, f * D.n_rhs);
       else
         cocg_small_job<1, SPD, DB>(D, sell_ptr, sell_col, sell_perm, sell_vals, sell_total, n_slices, bvec, xvec, rvec, qvec, aux, zero_x,
-                                   max_restarts, mc, c_orig, c_edge_nodes, c_n2e_ptr, c_n2e_item, sm_raw, f, f * D.n_rhs + kind - 1);
+                                   max_restarts, mc, L, c_edge_nodes, sm_raw, f, f * D.n_rhs + kind - 1);
     } else {
       const int f = first_matrix + job / groups_per_matrix;
       cocg_small_job<NR, SPD, DB>(D, sell_ptr, sell_col, sell_perm, sell_vals, sell_total, n_slices, bvec, xvec, rvec, qvec, aux, zero_x,
-                                  max_restarts, mc, c_orig, c_edge_nodes, c_n2e_ptr, c_n2e_item, sm_raw, f,
+                                  max_restarts, mc, L, c_edge_nodes, sm_raw, f,
                                   f * D.n_rhs + (job % groups_per_matrix) * NR);
     }
   }
@@ -1407,8 +1480,21 @@ static int run_cocg_small(SolvePlan &P, const efb_solve_opts *o, bool zero_x, bo
   int nr = (S->n_rhs % 2 == 0) ? 2 : 1;
   if (small_smem_bytes(nr, mc, nn) > (size_t)dev_smem) nr = 1;
   if (variant >= 4) nr = 1;  // one right-hand side per CTA, two CTAs per SM
-  const size_t smem = small_smem_bytes(nr, mc, nn);
+  size_t smem = small_smem_bytes(nr, mc, nn);
   if (smem > (size_t)dev_smem || !S->d_sell_ptr) return EFB_OK;  // system too large for one CTA: generic multi-kernel path
+  long long *d_prof = nullptr;
+  static const bool prof_on = getenv("EDGEFEM_B200_SMALL_PROF") != nullptr;
+  if (prof_on) {
+    int rcp = dev_alloc(c, &d_prof, 8);
+    if (rcp) return rcp;
+    EFB_CUDA(c, cudaMemsetAsync(d_prof, 0, 8 * sizeof(long long), c->stream));
+  }
+  int stage_off = 0;  // 16-bit index lists behind p, w and the reduction scratch, when they fit (SmallLists)
+  if (S->m <= 65535 && 2 * mc <= 65535 && variant < 4 && !getenv("EDGEFEM_B200_NO_STAGE") &&
+      ((smem + 15) / 16 * 16) + small_lists_bytes(mc, nn) <= (size_t)dev_smem) {
+    stage_off = (int)((smem + 15) / 16 * 16);
+    smem = (size_t)stage_off + small_lists_bytes(mc, nn);
+  }
   if (!S->d_sell_vals) {
     int rc0 = dev_alloc(c, &S->d_sell_vals, (size_t)S->n_matrix * (size_t)S->sell_total);
     if (rc0) return rc0;
@@ -1531,7 +1617,7 @@ static int run_cocg_small(SolvePlan &P, const efb_solve_opts *o, bool zero_x, bo
     k_cocg_small<NRV, NT, SPDV, DBV><<<grid, NT, smem, c->stream>>>(P.D, S->d_sell_ptr, S->d_sell_col, S->d_sell_perm, S->d_sell_vals,    \
                                                                       S->sell_total, S->n_slices, P.first_matrix, n_jobs, groups, mixed, S->d_job, \
                                                                       S->d_b, S->d_x, P.vec[V_R], P.vec[V_Q], P.aux ? 1 : 0, zero_x ? 1 : 0, mr, \
-                                                                      mc, S->d_c_orig, S->d_c_edge_nodes, S->d_c_n2e_ptr, S->d_c_n2e_item); \
+                                                                      mc, S->d_c_orig, S->d_c_edge_nodes, S->d_c_n2e_ptr, S->d_c_n2e_item, stage_off, d_prof); \
   } while (0)
 #define EFB_SMALL_LAUNCH2(NRV, NT, SPDV, DBV)                                                                                             \
   do {                                                                                                                                    \
@@ -1539,7 +1625,7 @@ static int run_cocg_small(SolvePlan &P, const efb_solve_opts *o, bool zero_x, bo
     k_cocg_small<NRV, NT, SPDV, DBV, 2><<<grid, NT, smem, c->stream>>>(P.D, S->d_sell_ptr, S->d_sell_col, S->d_sell_perm, S->d_sell_vals, \
                                                                       S->sell_total, S->n_slices, P.first_matrix, n_jobs, groups, mixed, S->d_job, \
                                                                       S->d_b, S->d_x, P.vec[V_R], P.vec[V_Q], P.aux ? 1 : 0, zero_x ? 1 : 0, mr, \
-                                                                      mc, S->d_c_orig, S->d_c_edge_nodes, S->d_c_n2e_ptr, S->d_c_n2e_item); \
+                                                                      mc, S->d_c_orig, S->d_c_edge_nodes, S->d_c_n2e_ptr, S->d_c_n2e_item, stage_off, d_prof); \
   } while (0)
   if (nr == 2) {
     switch (variant) {
@@ -1562,6 +1648,17 @@ static int run_cocg_small(SolvePlan &P, const efb_solve_opts *o, bool zero_x, bo
 #undef EFB_SMALL_LAUNCH2
   EFB_CHECK_LAUNCH(c);
   EFB_CUDA(c, cudaEventRecord(S->ev_s1, c->stream));
+  if (d_prof) {
+    long long h[8];
+    EFB_CUDA(c, cudaMemcpyAsync(h, d_prof, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    EFB_CUDA(c, cudaStreamSynchronize(c->stream));
+    dfree(d_prof);
+    double tot = 0;
+    for (int k = 0; k < 8; ++k) tot += (double)h[k];
+    tot = std::max(tot, 1.0);
+    fprintf(stderr, "[edgefem-b200 small prof] share of CTA 0's iteration cycles: nodal gather %.3f, z pass %.3f, reduce %.3f, p update %.3f, SpMV %.3f, reduce (+ warp imbalance) %.3f, x/r update %.3f, loop %.3f (total %.0f cycles, lists %s)\n",
+            h[0] / tot, h[1] / tot, h[2] / tot, h[3] / tot, h[4] / tot, h[5] / tot, h[6] / tot, h[7] / tot, tot, stage_off ? "in shared memory" : "in global memory");
+  }
   S->small_timed = true;
   *ran = true;
   return EFB_OK;
