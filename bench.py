@@ -390,6 +390,17 @@ def ncu_traffic(kernel: str, n_matrix: int):
         return None
 
 
+def ncu_limiter(kernel: str):
+    """What the committed ncu capture of `kernel` names as the saturated unit (a quotation of profiles/, not a measurement of
+    this run)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            rec = json.load(f)[kernel]
+        return rec["limiter"] + " [" + rec["source"].split(" ")[0] + "]"
+    except Exception:
+        return None
+
+
 def wr90_setup(pe):
     import numpy as np
 
@@ -522,7 +533,7 @@ def run_b200(a):
         roof = {"bound": "hbm", "kernel": kname, "achieved": solve_bytes / ms_kernel / 1e6, "peak": hbm_peak, "unit": "GB/s",
                 "frac": solve_bytes / ms_kernel / 1e6 / hbm_peak, "traffic": ncu_traffic(kkey, F), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": solve_bytes, "ms_per_launch": ms_kernel, "launches_per_step": 1, "share_of_step": ms_kernel / ms_step,
-                "free_unknowns": m_f, "free_nnz": nnz_f, "note": note}
+                "free_unknowns": m_f, "free_nnz": nnz_f, "note": note, "limiter_per_ncu": ncu_limiter(kkey)}
     else:  # multi-kernel path (EDGEFEM_B200_NO_PERSISTENT=1 and EDGEFEM_B200_CLUSTER=0): batched CSR SpMV dominates
         ms_spmv = rs.sys.bench_kernel(0, 50)
         spmv_bytes = F * nnz * 16.0 + nnz * 4.0 + (m + 1) * 4.0 + F * P * m * 32.0

@@ -691,6 +691,12 @@ k_bicg_x(SolveDev D, int first_sys, c128 *__restrict__ x, c128 *__restrict__ r, 
 // and CTAs pull the next matrix from an atomic queue when theirs has converged.
 constexpr int SMALL_LPR = 16;
 
+// 32-byte load (LDG.256, sm_100): both right-hand sides of one interleaved r entry in ONE request -- a random gather costs a
+// wavefront per distinct line whatever its width, so this halves the load-pipe cost of the nodal gather
+__device__ __forceinline__ void ldg256(const c128 *p, c128 &a, c128 &b) {
+  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p) : "memory");
+}
+
 // Index lists of the compact numbering (free unknown -> edge id, node -> incident free edges).  They are the same for every
 // job of a launch; when they fit beside p and w they are staged ONCE per CTA in shared memory as 16-bit values: the nodal
 // gather's chain pointer -> item -> r and the chains orig -> x / 1/diag then cost one L2 round trip instead of two or three
@@ -993,13 +999,23 @@ __device__ __forceinline__ void cocg_small_job(const SolveDev &D, const int32_t 
           const int it1 = ke0 + l16 < ke1 ? L.item(ke0 + l16) : -1;
           const c128 li = __ldg(&linv[n0 + ((l16 & 1) && two ? 1 : 0)]);  // lane 0 stores node n0, lane 1 node n0 + 1
           c128 a2[2][NR];
+          if constexpr (NR == 2) {
+            c128 v00 = cmake(0.0, 0.0), v01 = v00, v10 = v00, v11 = v00;
+            if (it0 >= 0) ldg256(&rg(0, it0 >> 1), v00, v01);
+            if (it1 >= 0) ldg256(&rg(0, it1 >> 1), v10, v11);
+            a2[0][0] = (it0 & 1) ? v00 : cneg(v00);
+            a2[0][NR - 1] = (it0 & 1) ? v01 : cneg(v01);
+            a2[1][0] = (it1 & 1) ? v10 : cneg(v10);
+            a2[1][NR - 1] = (it1 & 1) ? v11 : cneg(v11);
+          } else {
 #pragma unroll
-          for (int r = 0; r < NR; ++r) {
-            c128 v0 = cmake(0.0, 0.0), v1 = cmake(0.0, 0.0);
-            if (it0 >= 0) v0 = rg(r, it0 >> 1);
-            if (it1 >= 0) v1 = rg(r, it1 >> 1);
-            a2[0][r] = (it0 & 1) ? v0 : cneg(v0);
-            a2[1][r] = (it1 & 1) ? v1 : cneg(v1);
+            for (int r = 0; r < NR; ++r) {
+              c128 v0 = cmake(0.0, 0.0), v1 = cmake(0.0, 0.0);
+              if (it0 >= 0) v0 = rg(r, it0 >> 1);
+              if (it1 >= 0) v1 = rg(r, it1 >> 1);
+              a2[0][r] = (it0 & 1) ? v0 : cneg(v0);
+              a2[1][r] = (it1 & 1) ? v1 : cneg(v1);
+            }
           }
           for (int k = kb0 + 16 + l16; k < ke0; k += 16) {  // more than 16 incident free edges: rare
             const int it = L.item(k);
