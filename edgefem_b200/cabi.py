@@ -119,7 +119,7 @@ SIGNATURES = {
     "efb_clear_caches": (None, []),
     "efb_system_last_solve_kernel_ms": (C.c_int, [C.c_void_p, f64p]),
     "efb_system_last_solve_shape": (C.c_int, [C.c_void_p, i32p, i32p, i32p]),
-    "efb_debug_cluster_plan_build": (C.c_int, [C.c_int32, i32p, i32p, u8p, C.c_int32, i32p, C.c_int32, C.POINTER(C.c_void_p)]),
+    "efb_debug_cluster_plan_build": (C.c_int, [C.c_int32, i32p, i32p, u8p, C.c_int32, i32p, u8p, C.c_int32, C.POINTER(C.c_void_p)]),
     "efb_debug_cluster_plan_free": (None, [C.c_void_p]),
     "efb_debug_cluster_plan_get": (C.c_int64, [C.c_void_p, C.c_char_p, i64p, C.c_int64]),
     "efb_spmv_host": (C.c_int, [C.c_void_p, C.c_int32, f64p, f64p]),
@@ -213,19 +213,22 @@ def dist_row_range(m: int, rank: int, world: int):
     return a.value, b.value
 
 
-def cluster_plan_arrays(rowptr, colidx, dir_flags=None, n_node=0, edge_nodes=None, cluster_ctas=8) -> dict:
-    """Host-only diagnostics: the cluster split of a CSR pattern as a dict of int64 arrays (efb_debug_cluster_plan_*)."""
+def cluster_plan_arrays(rowptr, colidx, dir_flags=None, n_node=0, edge_nodes=None, cluster_ctas=8, row_complex=None) -> dict:
+    """Host-only diagnostics: the cluster split of a CSR pattern as a dict of int64 arrays (efb_debug_cluster_plan_*).
+    row_complex: flags of the rows whose values are not all real (None = every row)."""
     lib = load()
     rp, ci = _i32(rowptr), _i32(colidx)
     d = None if dir_flags is None else np.ascontiguousarray(np.asarray(dir_flags, dtype=np.uint8))
     en = None if edge_nodes is None else _i32(edge_nodes)
+    rc_ = None if row_complex is None else np.ascontiguousarray(np.asarray(row_complex, dtype=np.uint8))
     h = C.c_void_p()
-    rc = lib.efb_debug_cluster_plan_build(rp.size - 1, _p(rp, i32p), _p(ci, i32p), _p(d, u8p), int(n_node), _p(en, i32p), int(cluster_ctas), C.byref(h))
+    rc = lib.efb_debug_cluster_plan_build(rp.size - 1, _p(rp, i32p), _p(ci, i32p), _p(d, u8p), int(n_node), _p(en, i32p), _p(rc_, u8p),
+                                          int(cluster_ctas), C.byref(h))
     if rc != EFB_OK:
         raise EfbError("efb_debug_cluster_plan_build failed (%d): %s" % (rc, (lib.efb_last_error(None) or b"").decode()))
     out = {}
     try:
-        for name in ("dims", "c_orig", "cta_info", "row_edge", "row_ws", "row_n0", "row_n1", "blk_off", "slot_src", "slot_col", "halo_ws",
+        for name in ("dims", "c_orig", "cta_info", "row_edge", "row_ws", "row_n0", "row_n1", "blk_off", "blk_voff", "slot_src", "slot_col", "halo_ws",
                      "halo_src", "node_id", "n2e_ptr", "n2e_item", "nsrc_ptr", "nsrc_item"):
             n = lib.efb_debug_cluster_plan_get(h, name.encode(), None, 0)
             buf = np.zeros(max(int(n), 1), dtype=np.int64)

@@ -30,18 +30,21 @@ namespace cg = cooperative_groups;
 
 namespace efb {
 
-constexpr int CL_THREADS_MAX = 640;
+constexpr int CL_THREADS_MAX = 640;   // thread per row up to here at 96 registers
+constexpr int CL_THREADS_WIDE = 768;  // wide CTAs (a 6-CTA split of WR-90 has 745 rows per CTA): 80 registers, a few spills, still
+                                      // faster than two rows per thread (measured 2.9 against 3.8 ms per job)
 
 struct ClusterDev {
   int C, mc, aux;
   int max_own, max_w, max_my, max_slots, max_halo, max_n2e, max_nsrc;
+  int max_vunits;  // value image of a CTA in 8-byte units (real blocks: 1 per slot, complex blocks: 2)
   int ndeg, sdeg;  // widths of the per-node ELL lists below (own edges at a node / CTAs touching a node)
   const uint16_t *n2e_ell;  // [C][ndeg][max_my] own local row << 1 | head, 0xffff = none
   const uint32_t *nsrc_ell; // [C][sdeg][max_my] CTA << 16 | that CTA's node slot, 0xffffffff = none
   long long *prof;  // [C][16] cycle counters per phase (EDGEFEM_B200_CLUSTER_PROF=1), else null
   const int32_t *cta_info, *row_edge;
   const uint16_t *row_ws, *row_n0, *row_n1;
-  const int32_t *blk_off, *slot_src;
+  const int32_t *blk_off, *blk_voff, *slot_src;
   const uint16_t *slot_col, *halo_ws;
   const uint32_t *halo_src;
   const int32_t *node_id, *n2e_ptr;
@@ -55,6 +58,7 @@ struct ClusterPlanDev {  // shared by the systems with the same pattern / flags 
     for (void *b : blocks) dfree(b);
   }
   ClusterPlanHost h;
+  uint64_t flags_hash = 0;  // of the real/complex row flags the plan was built for
   std::vector<uint16_t> n2e_ell;
   std::vector<uint32_t> nsrc_ell;
   int ndeg = 0, sdeg = 0;
@@ -80,7 +84,7 @@ static size_t cluster_smem_bytes(int nr, const ClusterPlanHost &P) {
   int ndeg, sdeg;
   plan_degrees(P, &ndeg, &sdeg);
   size_t b = 0;
-  b += (size_t)P.max_slots * 16;            // mat_v
+  b += ((size_t)P.max_vunits * 8 + 15) / 16 * 16;  // mat_d (real blocks: doubles, complex blocks: complex128)
   b += (size_t)P.max_w * nr * 16;           // p_w
   b += (size_t)P.max_own * nr * 16 * 2;     // q_own, z_own
   b += (size_t)std::max(P.max_my, 1) * nr * 16 * 3;  // wp, g, w
@@ -148,8 +152,8 @@ __device__ __forceinline__ void bank_totals(const double *bank, int C, double (&
   for (int k = 0; k < N; ++k) tot[k] = __shfl_sync(0xffffffffu, v, k);
 }
 
-template <int NR, int RPT>
-__global__ void __launch_bounds__(CL_THREADS_MAX, 1)
+template <int NR, int RPT, int NTMAX = CL_THREADS_MAX>
+__global__ void __launch_bounds__(NTMAX, 1)
 k_cocg_cluster(const SolveDev D, const ClusterDev K, int first_matrix, int n_jobs, int groups, int *job_counter, const c128 *__restrict__ bvec,
                c128 *xvec, int zero_x, int max_restarts) {
   static_assert(3 * NR <= 8, "partial banks hold 8 doubles per CTA");
@@ -158,8 +162,8 @@ k_cocg_cluster(const SolveDev D, const ClusterDev K, int first_matrix, int n_job
   const int crank = (int)cluster.block_rank();
   const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31;
   extern __shared__ __align__(16) unsigned char sm[];
-  c128 *mat_v = (c128 *)sm;
-  c128 *p_w = mat_v + K.max_slots;
+  double *mat_d = (double *)sm;  // value image: per ELL block either doubles (all rows real) or complex128
+  c128 *p_w = (c128 *)(sm + ((size_t)K.max_vunits * 8 + 15) / 16 * 16);
   c128 *q_own = p_w + (size_t)K.max_w * NR;
   c128 *z_own = q_own + (size_t)K.max_own * NR;
   c128 *wp = z_own + (size_t)K.max_own * NR;
@@ -188,7 +192,8 @@ k_cocg_cluster(const SolveDev D, const ClusterDev K, int first_matrix, int n_job
 
   // per-thread rows: local row t = u * nth + tid (a warp = one 32-row ELL block)
   bool valid[RPT];
-  int edge[RPT], ws[RPT], n0[RPT], n1[RPT], base[RPT], width[RPT];
+  int edge[RPT], ws[RPT], n0[RPT], n1[RPT], base[RPT], width[RPT], vbase[RPT];
+  bool cplx[RPT];
 #pragma unroll
   for (int u = 0; u < RPT; ++u) {
     const int t = u * nth + tid;
@@ -200,9 +205,13 @@ k_cocg_cluster(const SolveDev D, const ClusterDev K, int first_matrix, int n_job
     const int b = t >> 5;
     base[u] = 0;
     width[u] = 0;
+    vbase[u] = 0;
+    cplx[u] = true;
     if (b < n_blk) {
       base[u] = K.blk_off[off_blk + b];
       width[u] = (K.blk_off[off_blk + b + 1] - base[u]) >> 5;
+      vbase[u] = K.blk_voff[off_blk + b];
+      cplx[u] = (K.blk_voff[off_blk + b + 1] - vbase[u]) == 2 * (width[u] << 5);  // warp-uniform: a warp is one block
     }
   }
   for (int i = tid; i < n_slots; i += nth) mat_c[i] = K.slot_col[off_slot + i];
@@ -233,27 +242,60 @@ k_cocg_cluster(const SolveDev D, const ClusterDev K, int first_matrix, int n_job
       c128 acc[NR];
 #pragma unroll
       for (int r = 0; r < NR; ++r) acc[r] = cmake(0.0, 0.0);
-      const c128 *mv = mat_v + base[u] + lane;
       const uint16_t *mc_ = mat_c + base[u] + lane;
-      int k = 0;
-      for (; k + 4 <= width[u]; k += 4) {
-        c128 a4[4];
-        int c4[4];
+      if (cplx[u]) {
+        const c128 *mv = (const c128 *)(mat_d + vbase[u]) + lane;
+        int k = 0;
+        for (; k + 4 <= width[u]; k += 4) {
+          c128 a4[4];
+          int c4[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          a4[j] = mv[(k + j) * 32];
-          c4[j] = mc_[(k + j) * 32];
+          for (int j = 0; j < 4; ++j) {
+            a4[j] = mv[(k + j) * 32];
+            c4[j] = mc_[(k + j) * 32];
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int r = 0; r < NR; ++r) acc[r] = cfma(a4[j], p_w[c4[j] * NR + r], acc[r]);
         }
+        for (; k < width[u]; ++k) {
+          const c128 a = mv[k * 32];
+          const int c = mc_[k * 32];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+          for (int r = 0; r < NR; ++r) acc[r] = cfma(a, p_w[c * NR + r], acc[r]);
+        }
+      } else {
+        // real block: 8-byte values (2 shared-memory wavefronts per 32 entries instead of 4), 2 FMAs per entry instead of 4
+        const double *mv = mat_d + vbase[u] + lane;
+        int k = 0;
+        for (; k + 4 <= width[u]; k += 4) {
+          double a4[4];
+          int c4[4];
 #pragma unroll
-          for (int r = 0; r < NR; ++r) acc[r] = cfma(a4[j], p_w[c4[j] * NR + r], acc[r]);
-      }
-      for (; k < width[u]; ++k) {
-        const c128 a = mv[k * 32];
-        const int c = mc_[k * 32];
+          for (int j = 0; j < 4; ++j) {
+            a4[j] = mv[(k + j) * 32];
+            c4[j] = mc_[(k + j) * 32];
+          }
 #pragma unroll
-        for (int r = 0; r < NR; ++r) acc[r] = cfma(a, p_w[c * NR + r], acc[r]);
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+              const c128 pv = p_w[c4[j] * NR + r];
+              acc[r].x = fma(a4[j], pv.x, acc[r].x);
+              acc[r].y = fma(a4[j], pv.y, acc[r].y);
+            }
+        }
+        for (; k < width[u]; ++k) {
+          const double a = mv[k * 32];
+          const int c = mc_[k * 32];
+#pragma unroll
+          for (int r = 0; r < NR; ++r) {
+            const c128 pv = p_w[c * NR + r];
+            acc[r].x = fma(a, pv.x, acc[r].x);
+            acc[r].y = fma(a, pv.y, acc[r].y);
+          }
+        }
       }
 #pragma unroll
       for (int r = 0; r < NR; ++r) out[u][r] = acc[r];
@@ -375,9 +417,15 @@ k_cocg_cluster(const SolveDev D, const ClusterDev K, int first_matrix, int n_job
     const int s0 = f * D.n_rhs + (job % groups) * NR;
     const c128 *__restrict__ av = D.vals + (size_t)f * D.nnz;
     const c128 *__restrict__ dinv = D.dinv + (size_t)f * m;
-    for (int i = tid; i < n_slots; i += nth) {
-      const int src = K.slot_src[off_slot + i];
-      mat_v[i] = src >= 0 ? ldg_stream16(&av[src]) : cmake(0.0, 0.0);
+    for (int b = 0; b < n_blk; ++b) {  // value image of the job, block by block (real blocks keep the real part only)
+      const int o0 = K.blk_off[off_blk + b], o1 = K.blk_off[off_blk + b + 1], v0 = K.blk_voff[off_blk + b];
+      const bool bc = (K.blk_voff[off_blk + b + 1] - v0) == 2 * (o1 - o0);
+      for (int i = o0 + tid; i < o1; i += nth) {
+        const int src = K.slot_src[off_slot + i];
+        const c128 v = src >= 0 ? ldg_stream16(&av[src]) : cmake(0.0, 0.0);
+        if (bc) ((c128 *)(mat_d + v0))[i - o0] = v;
+        else mat_d[v0 + i - o0] = v.x;
+      }
     }
     if (K.aux)
       for (int j = tid; j < n_my; j += nth) linv_s[j] = D.linv[(size_t)f * D.n_node + K.node_id[off_node + j]];
@@ -649,6 +697,21 @@ void cluster_plan_free(System *S) {
   S->cl_plan = nullptr;
 }
 
+// flag[r] = 1 when row r holds a value with a non-zero imaginary part in any of the matrices [first, first+n): a warp per row
+__global__ void __launch_bounds__(256) k_row_complex(const c128 *__restrict__ vals, long long nnz, const int32_t *__restrict__ rowptr, int m,
+                                                    int first, int n, uint8_t *__restrict__ flag) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= m) return;
+  const int k0 = rowptr[r], len = rowptr[r + 1] - k0;
+  bool any = false;
+  for (int i = lane; i < len * n && !any; i += 32) {
+    const int f = i / len, k = i - f * len;
+    any = vals[(size_t)(first + f) * (size_t)nnz + k0 + k].y != 0.0;
+  }
+  any = __any_sync(0xffffffffu, any);
+  if (lane == 0) flag[r] = any ? 1 : 0;
+}
+
 namespace {
 struct PlanCacheEntry {
   int device, m, C;
@@ -692,11 +755,12 @@ static int cluster_plan_upload(System *S, ClusterPlanDev *P) {
   ClusterPlanHost &H = P->h;
   // uploads read the host vectors asynchronously: give every vector at least one element and sync at the end
   auto pad = [](auto &v) { if (v.empty()) v.resize(1); };
-  pad(H.row_edge); pad(H.row_ws); pad(H.row_n0); pad(H.row_n1); pad(H.blk_off); pad(H.slot_src); pad(H.slot_col);
+  pad(H.row_edge); pad(H.row_ws); pad(H.row_n0); pad(H.row_n1); pad(H.blk_off); pad(H.blk_voff); pad(H.slot_src); pad(H.slot_col);
   pad(H.halo_ws); pad(H.halo_src); pad(H.node_id); pad(H.n2e_ptr); pad(H.n2e_item); pad(H.nsrc_ptr); pad(H.nsrc_item);
   ClusterDev &d = P->d;
   d.C = H.C; d.mc = H.mc; d.aux = H.aux ? 1 : 0;
   d.max_own = H.max_own; d.max_w = H.max_w; d.max_my = std::max(H.max_my, 1); d.max_slots = H.max_slots;
+  d.max_vunits = H.max_vunits;
   d.max_halo = H.max_halo; d.max_n2e = H.max_n2e; d.max_nsrc = H.max_nsrc;
   {
     // per-node lists as ELL (thread per node in the kernel, independent loads): own edges at a node, CTAs touching a node
@@ -738,6 +802,7 @@ static int cluster_plan_upload(System *S, ClusterPlanDev *P) {
   if ((rc = up(c, P, &d.row_n0, H.row_n0))) return rc;
   if ((rc = up(c, P, &d.row_n1, H.row_n1))) return rc;
   if ((rc = up(c, P, &d.blk_off, H.blk_off))) return rc;
+  if ((rc = up(c, P, &d.blk_voff, H.blk_voff))) return rc;
   if ((rc = up(c, P, &d.slot_src, H.slot_src))) return rc;
   if ((rc = up(c, P, &d.slot_col, H.slot_col))) return rc;
   if ((rc = up(c, P, &d.halo_ws, H.halo_ws))) return rc;
@@ -751,10 +816,12 @@ static int cluster_plan_upload(System *S, ClusterPlanDev *P) {
   return EFB_OK;
 }
 
-template <int NR, int RPT>
+static int g_cl_resident[CL_MAX_C + 1] = {0};  // measured resident clusters per cluster size (cudaOccupancyMaxActiveClusters)
+
+template <int NR, int RPT, int NTMAX = CL_THREADS_MAX>
 static int launch_cluster(Ctx *c, const SolveDev &D, const ClusterDev &K, int nth, size_t smem, int first_matrix, int n_jobs, int groups,
                           int *job_counter, const c128 *b, c128 *x, int zero_x, int mr, int *clusters_out) {
-  auto kern = k_cocg_cluster<NR, RPT>;
+  auto kern = k_cocg_cluster<NR, RPT, NTMAX>;
   EFB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg{};
   cfg.blockDim = dim3((unsigned)nth, 1, 1);
@@ -775,6 +842,7 @@ static int launch_cluster(Ctx *c, const SolveDev &D, const ClusterDev &K, int nt
     return fail(c, EFB_ERR_LIMIT, "cluster solver: no cluster of %d CTAs x %zu B of shared memory can be resident (%s)", K.C, smem,
                 e != cudaSuccess ? cudaGetErrorString(e) : "0 clusters");
   }
+  g_cl_resident[K.C] = max_clusters;
   const int n_clusters = std::max(1, std::min(n_jobs, max_clusters));
   cfg.gridDim = dim3((unsigned)(n_clusters * K.C), 1, 1);
   *clusters_out = n_clusters;
@@ -811,7 +879,7 @@ int run_krylov_cluster(SolvePlan &P, const efb_solve_opts *o, bool zero_x, bool 
     if (cluster_smem_bytes(nr, H) > (size_t)dev_smem) return false;
     for (int rpt : {1, 2, 4}) {
       const int nth = std::max(64, ((H.max_own + rpt - 1) / rpt + 31) / 32 * 32);
-      if (nth <= CL_THREADS_MAX) {
+      if (nth <= (rpt == 1 ? CL_THREADS_WIDE : CL_THREADS_MAX)) {
         *rpt_out = rpt;
         *nth_out = nth;
         return true;
@@ -830,42 +898,82 @@ int run_krylov_cluster(SolvePlan &P, const efb_solve_opts *o, bool zero_x, bool 
     for (int k = S->h_rowptr[r]; k < S->h_rowptr[r + 1]; ++k) nnz_free += !(dirp && dirp[S->h_colidx[k]]);
   }
   if (mc == 0) return EFB_OK;
-  auto est_bytes = [&](int C, int nrp) {  // per CTA: matrix slice (+10 % padding) + window (own + ~0.8 own of halo) + q, z + lists
+  // per CTA: matrix slice (+10 % padding; 10 B per slot in real blocks, 18 B in complex ones) + window (own + ~0.8 own of
+  // halo) + q, z + nodal arrays + lists
+  auto est_bytes = [&](int C, double cplx_frac) {
     const double own = (double)mc / C, halo = C > 1 ? 0.8 * own + 64 : 0.0;
-    return nnz_free * 1.1 * 18.0 / C + (own + halo) * nrp * 16.0 + own * nrp * 32.0 + (want_aux ? own * 0.4 * (nrp * 48.0 + 80.0) : 0.0) + halo * 6.0 + 6000.0;
+    return nnz_free * 1.1 * (10.0 + 8.0 * cplx_frac) / C + (own + halo) * 16.0 + own * 32.0 + (want_aux ? own * 0.4 * 128.0 : 0.0) + halo * 6.0 + 6000.0;
   };
-  int C_est = 0;
-  for (int C = 1; C <= CL_MAX_C; C *= 2)
-    if (est_bytes(C, 1) <= 0.97 * dev_smem && (mc + C - 1) / C <= 4 * CL_THREADS_MAX) {
-      C_est = C;
-      break;
-    }
-  if (forced > 0) C_est = forced;
-  if (C_est == 0) return EFB_OK;  // does not fit in 8 SMs: the other solver paths take it
+  // resident clusters of C CTAs (one CTA per SM; a cluster lives inside one GPC of ~18 SMs): measured once a launch of that
+  // size has happened, estimated before
+  auto resident_est = [&](int C) {
+    if (g_cl_resident[C] > 0) return g_cl_resident[C];
+    const int per_gpc = std::max(1, 18 / C), gpcs = std::max(1, c->sm_count / 18);
+    return std::max(1, std::min(c->sm_count / C, per_gpc * gpcs) - (C >= 5 ? 1 : 0));
+  };
+  // relative cost of a job on C CTAs: half of the 8-CTA iteration is barriers and reductions (fixed), half scales with the rows per CTA
+  auto job_cost = [](int C) { return 0.5 + 0.5 * 8.0 / C; };
+  const int n_jobs_all = n_matrix * n_rhs;
+  auto batch_cost = [&](int C) { return std::ceil((double)n_jobs_all / resident_est(C)) * job_cost(C); };
   const int nn1 = want_aux ? S->n_node : 0;
   const bool one_cta_ok = S->m <= 16384 && ((size_t)mc * 16 + (size_t)nn1 * 16 + 4096) <= (size_t)dev_smem;
-  auto resident_est = [&](int C) { return std::max(1, c->sm_count / C - (C == 8 ? 3 : C == 4 ? 4 : 0)); };
-  if (forced < 0 && one_cta_ok) {
-    // Latency or throughput?  A cluster job is ~10x faster than a one-CTA job of k_cocg_small (measured on WR-90:
-    // 7.9 us per rhs-iteration on 8 SMs against 85 us per two-rhs iteration on one), but only ~15 clusters of 8 are
-    // resident against 148 CTAs, and a one-CTA job carries both right-hand sides: big batches (the 256-point sweep)
-    // stay on the one-CTA kernel when it applies, small ones (one frequency, the shards of a strong-scaled sweep) run
-    // here.  Systems the one-CTA kernel cannot take (p does not fit in its shared memory) always run here.  Decided
-    // BEFORE any plan is built: the plan costs milliseconds of host time.
-    const double rounds_cl = std::ceil((double)n_matrix * n_rhs / resident_est(C_est));
-    const double rounds_1 = std::ceil((double)n_matrix / c->sm_count) * 10.0 * (n_rhs >= 2 ? 1.0 : 0.6);
-    if (rounds_cl > rounds_1) return EFB_OK;
+  // Latency or throughput?  A cluster job is ~10x faster than a one-CTA job of k_cocg_small (measured on WR-90:
+  // 7.5 us per rhs-iteration on 8 SMs against 85 us per two-rhs iteration on one), but only ~15 clusters of 8 (~24 of 6) are
+  // resident against 148 CTAs, and a one-CTA job carries both right-hand sides: big batches (the 256-point sweep)
+  // stay on the one-CTA kernel when it applies, small ones (one frequency, the shards of a strong-scaled sweep) run
+  // here.  Systems the one-CTA kernel cannot take (p does not fit in its shared memory) always run here.  Decided
+  // BEFORE the value scan and any plan build (first with the most favourable storage, all rows real).
+  const double rounds_1 = std::ceil((double)n_matrix / c->sm_count) * 10.0 * (n_rhs >= 2 ? 1.0 : 0.6);
+  auto candidates = [&](double cplx_frac) {
+    std::vector<int> cs;
+    if (forced > 0) {
+      cs.push_back(std::min(forced, CL_MAX_C));
+      return cs;
+    }
+    for (int C = 1; C <= CL_MAX_C; ++C)
+      if (est_bytes(C, cplx_frac) <= 0.97 * dev_smem && (mc + C - 1) / C <= 4 * CL_THREADS_MAX) cs.push_back(C);
+    std::stable_sort(cs.begin(), cs.end(), [&](int x, int y) {
+      const double cx = batch_cost(x), cy = batch_cost(y);
+      return cx != cy ? cx < cy : x > y;
+    });
+    return cs;
+  };
+  {
+    const std::vector<int> c0 = candidates(0.0);
+    if (c0.empty()) return EFB_OK;  // does not fit in 8 SMs: the other solver paths take it
+    if (forced < 0 && one_cta_ok && batch_cost(c0[0]) > rounds_1) return EFB_OK;
   }
-  // few jobs: a larger cluster costs nothing (idle SMs otherwise) and shortens every job
-  int C_want = C_est;
-  if (forced <= 0)
-    while (C_want * 2 <= CL_MAX_C && (long long)n_matrix * n_rhs * C_want * 2 <= c->sm_count) C_want *= 2;
-  if (S->cl_dirty || !PL || PL->h.aux != want_aux || PL->h.C < C_want || (forced > 0 && PL->h.C != forced)) {
+  // Rows with a value that is not real in any matrix of the range (a lossless system: only the rows of the port faces):
+  // their ELL blocks store complex128, the others doubles.
+  std::vector<uint8_t> row_cplx((size_t)S->m, 1);
+  const bool no_real = getenv("EDGEFEM_B200_CLUSTER_NO_REAL") != nullptr;
+  long long nnz_cplx = 0;
+  if (!no_real) {
+    uint8_t *d_flag = nullptr;
+    int rcf = dev_alloc(c, &d_flag, (size_t)S->m);
+    if (rcf) return rcf;
+    k_row_complex<<<(unsigned)((S->m + 7) / 8), 256, 0, c->stream>>>(S->d_vals, (long long)S->nnz, S->d_rowptr, S->m, P.first_matrix, n_matrix, d_flag);
+    EFB_CHECK_LAUNCH(c);
+    EFB_CUDA(c, cudaMemcpyAsync(row_cplx.data(), d_flag, (size_t)S->m, cudaMemcpyDeviceToHost, c->stream));
+    EFB_CUDA(c, cudaStreamSynchronize(c->stream));
+    dfree(d_flag);
+  }
+  for (int r = 0; r < S->m; ++r)
+    if (row_cplx[r] && !(dirp && dirp[r])) nnz_cplx += S->h_rowptr[r + 1] - S->h_rowptr[r];
+  const double cplx_frac = std::min(1.0, (double)nnz_cplx / std::max<long long>(1, nnz_free));
+  uint64_t flags_hash = 1469598103934665603ull;
+  for (int r = 0; r < S->m; ++r) flags_hash = (flags_hash ^ row_cplx[r]) * 1099511628211ull;
+  const std::vector<int> cand = candidates(cplx_frac);
+  if (cand.empty()) return EFB_OK;
+  if (forced < 0 && one_cta_ok && batch_cost(cand[0]) > rounds_1) return EFB_OK;
+  st.mark("  cluster solver: value scan + shape choice");
+  const bool reuse = !S->cl_dirty && PL && PL->h.aux == want_aux && PL->flags_hash == flags_hash && PL->h.C == cand[0];
+  if (!reuse) {
     cluster_plan_free(S);
     PL = nullptr;
-    // plans are shared between systems with the same pattern, Dirichlet flags and gradient (a driver that creates one
-    // system per call -- calculate_sparams_eigenmode in a frequency loop -- builds the plan once)
-    uint64_t hsh = 1469598103934665603ull;
+    // plans are shared between systems with the same pattern, Dirichlet flags, gradient and real/complex rows (a driver that
+    // creates one system per call -- calculate_sparams_eigenmode in a frequency loop -- builds the plan once)
+    uint64_t hsh = flags_hash;
     auto mix = [&hsh](const void *ptr, size_t bytes) {
       const uint32_t *w = (const uint32_t *)ptr;
       for (size_t i = 0; i < bytes / 4; ++i) {
@@ -883,17 +991,19 @@ int run_krylov_cluster(SolvePlan &P, const efb_solve_opts *o, bool zero_x, bool 
     if (dirp) mix(dirp, (size_t)S->m);
     if (want_aux) mix(S->h_edge_nodes.data(), S->h_edge_nodes.size() * 4);
     std::shared_ptr<ClusterPlanDev> sp;
-    for (int C = C_want; C <= (forced > 0 ? forced : CL_MAX_C) && !sp; C *= 2) {
+    for (size_t ci = 0; ci < cand.size() && !sp; ++ci) {
+      const int C = cand[ci];
       sp = plan_cache_find(c->device, hsh, S->m, (long long)S->nnz, C, want_aux);
       if (sp) break;
       ClusterPlanHost H;
       if (!build_cluster_plan(S->m, S->h_rowptr.data(), S->h_colidx.data(), dirp, want_aux ? S->n_node : 0,
-                              want_aux ? S->h_edge_nodes.data() : nullptr, C, H))
+                              want_aux ? S->h_edge_nodes.data() : nullptr, C, H, row_cplx.data()))
         continue;
       int r1, t1;
       if (!fits(H, 1, &r1, &t1)) continue;
       sp = std::make_shared<ClusterPlanDev>();
       sp->h = std::move(H);
+      sp->flags_hash = flags_hash;
       int rc = cluster_plan_upload(S, sp.get());
       if (rc) return rc;
       plan_cache_put(c->device, hsh, S->m, (long long)S->nnz, C, want_aux, sp);
@@ -943,7 +1053,9 @@ int run_krylov_cluster(SolvePlan &P, const efb_solve_opts *o, bool zero_x, bool 
   int rc = EFB_OK, ncl = 0;
 #define EFB_CL(NRV, RPTV)                                                                                                             \
   rc = launch_cluster<NRV, RPTV>(c, P.D, PL->d, nth, smem, P.first_matrix, n_jobs, groups, S->d_job, S->d_b, S->d_x, zero_x ? 1 : 0, mr, &ncl)
-  if (rpt == 1) EFB_CL(1, 1); else if (rpt == 2) EFB_CL(1, 2); else EFB_CL(1, 4);
+  if (rpt == 1 && nth > CL_THREADS_MAX)
+    rc = launch_cluster<1, 1, CL_THREADS_WIDE>(c, P.D, PL->d, nth, smem, P.first_matrix, n_jobs, groups, S->d_job, S->d_b, S->d_x, zero_x ? 1 : 0, mr, &ncl);
+  else if (rpt == 1) EFB_CL(1, 1); else if (rpt == 2) EFB_CL(1, 2); else EFB_CL(1, 4);
 #undef EFB_CL
   if (rc) return rc;
   EFB_CUDA(c, cudaEventRecord(S->ev_s1, c->stream));
@@ -980,10 +1092,10 @@ struct efb_cluster_plan_dbg {
 };
 
 int efb_debug_cluster_plan_build(int32_t m, const int32_t *rowptr, const int32_t *colidx, const uint8_t *dir, int32_t n_node,
-                                 const int32_t *edge_nodes, int32_t C, void **out) {
+                                 const int32_t *edge_nodes, const uint8_t *row_complex, int32_t C, void **out) {
   if (!rowptr || !colidx || !out || m <= 0) return EFB_ERR_INVALID;
   auto *d = new efb_cluster_plan_dbg();
-  if (!build_cluster_plan(m, rowptr, colidx, dir, n_node, edge_nodes, C, d->h)) {
+  if (!build_cluster_plan(m, rowptr, colidx, dir, n_node, edge_nodes, C, d->h, row_complex)) {
     set_global_error("efb_debug_cluster_plan_build: " + d->h.error);
     delete d;
     return EFB_ERR_LIMIT;
@@ -1004,7 +1116,7 @@ int64_t efb_debug_cluster_plan_get(void *p, const char *name, int64_t *buf, int6
   auto put = [&](const auto &src) { v.assign(src.begin(), src.end()); };
   const std::string n = name;
   if (n == "dims") v = {H.C, H.mc, H.m, H.aux ? 1 : 0, H.max_own, H.max_w, H.max_my, H.max_slots, H.max_halo,
-                        (int64_t)cluster_smem_bytes(1, H), (int64_t)cluster_smem_bytes(2, H)};
+                        (int64_t)cluster_smem_bytes(1, H), (int64_t)cluster_smem_bytes(2, H), H.max_vunits};
   else if (n == "c_orig") put(H.c_orig);
   else if (n == "cta_info") put(H.cta_info);
   else if (n == "row_edge") put(H.row_edge);
@@ -1012,6 +1124,7 @@ int64_t efb_debug_cluster_plan_get(void *p, const char *name, int64_t *buf, int6
   else if (n == "row_n0") put(H.row_n0);
   else if (n == "row_n1") put(H.row_n1);
   else if (n == "blk_off") put(H.blk_off);
+  else if (n == "blk_voff") put(H.blk_voff);
   else if (n == "slot_src") put(H.slot_src);
   else if (n == "slot_col") put(H.slot_col);
   else if (n == "halo_ws") put(H.halo_ws);

@@ -35,6 +35,7 @@ struct ClusterPlanHost {
   int C = 0, mc = 0, m = 0;
   bool aux = false;
   int max_own = 0, max_w = 0, max_my = 0, max_slots = 0, max_halo = 0, max_n2e = 0, max_nsrc = 0;
+  int max_vunits = 0;  // largest value image of a CTA in 8-byte units (real blocks 1 per slot, complex blocks 2)
   std::vector<int32_t> c_orig;     // [mc] position -> original edge id
   std::vector<int32_t> cta_info;   // [C][CL_INFO_STRIDE]
   // per own row, local order (sorted by length, descending), concatenated over CTAs at CI_OFF_ROW
@@ -42,6 +43,9 @@ struct ClusterPlanHost {
   std::vector<uint16_t> row_ws;    // window slot of the row itself
   std::vector<uint16_t> row_n0, row_n1;  // my-node slots of the tail / head node (aux only)
   std::vector<int32_t> blk_off;    // per CTA n_blk+1 slot offsets (multiples of 32), at CI_OFF_BLK
+  std::vector<int32_t> blk_voff;   // same indexing: offsets of the blocks' VALUES in 8-byte units.  A block whose rows are all
+                                   // real (row_complex == 0) stores one double per slot, the others a complex128:
+                                   // voff[b+1] - voff[b] == 2 * (off[b+1] - off[b]) marks a complex block
   std::vector<int32_t> slot_src;   // CSR position of the slot's value (-1: padding), at CI_OFF_SLOT
   std::vector<uint16_t> slot_col;  // window slot of the slot's column
   std::vector<uint16_t> halo_ws;   // window slot of every halo entry, at CI_OFF_HALO
@@ -121,8 +125,11 @@ inline std::vector<int32_t> rcm_order(int n, const std::vector<int32_t> &ptr, co
 }
 
 // rowptr/colidx: m x m CSR pattern (sorted columns); dir: m flags or nullptr; edge_nodes: 2m node indices or nullptr
+// row_complex (or NULL = every row): rows whose values are not all real.  A lossless system is real except for the rows of
+// the port faces; storing the other rows as doubles halves the matrix slice, which is what decides how small a cluster can
+// hold the system in shared memory (WR-90: 8 CTAs with complex values, 6 with mixed ones -> 24 instead of 15 resident).
 inline bool build_cluster_plan(int m, const int32_t *rowptr, const int32_t *colidx, const uint8_t *dir, int n_node, const int32_t *edge_nodes,
-                               int C, ClusterPlanHost &P) {
+                               int C, ClusterPlanHost &P, const uint8_t *row_complex = nullptr) {
   P = ClusterPlanHost();
   P.C = C;
   P.m = m;
@@ -206,7 +213,13 @@ inline bool build_cluster_plan(int m, const int32_t *rowptr, const int32_t *coli
       L.push_back(p);
       part_of[p] = c;
     }
-    std::stable_sort(L.begin(), L.end(), [&](int a, int b) { return rptr[a + 1] - rptr[a] > rptr[b + 1] - rptr[b]; });
+    // complex rows first (their blocks come first: 16-byte alignment of the complex values), each group by length
+    auto is_cplx = [&](int pos) { return row_complex ? (row_complex[P.c_orig[pos]] != 0) : true; };
+    std::stable_sort(L.begin(), L.end(), [&](int a, int b) {
+      const bool ca = is_cplx(a), cb = is_cplx(b);
+      if (ca != cb) return ca;
+      return rptr[a + 1] - rptr[a] > rptr[b + 1] - rptr[b];
+    });
     for (size_t t = 0; t < L.size(); ++t) local_of[L[t]] = (int32_t)t;
   }
   // my nodes per CTA
@@ -277,9 +290,13 @@ inline bool build_cluster_plan(int m, const int32_t *rowptr, const int32_t *coli
     // ELL blocks of 32 local rows
     const int n_blk = (n_own + 31) / 32;
     I[CI_N_BLK] = n_blk;
-    int slots = 0;
+    int slots = 0, vunits = 0;
     for (int b = 0; b < n_blk; ++b) {
       Q.blk_off.push_back(slots);
+      Q.blk_voff.push_back(vunits);
+      bool blk_cplx = false;
+      for (int l = 0; l < 32 && b * 32 + l < n_own; ++l)
+        blk_cplx |= row_complex ? (row_complex[P.c_orig[L[b * 32 + l]]] != 0) : true;
       int width = 0;
       for (int l = 0; l < 32 && b * 32 + l < n_own; ++l) width = std::max(width, rptr[L[b * 32 + l] + 1] - rptr[L[b * 32 + l]]);
       const size_t base = Q.slot_src.size();
@@ -355,8 +372,10 @@ inline bool build_cluster_plan(int m, const int32_t *rowptr, const int32_t *coli
           }
         }
       slots += width * 32;
+      vunits += width * 32 * (blk_cplx ? 2 : 1);
     }
     Q.blk_off.push_back(slots);
+    Q.blk_voff.push_back(vunits);
     I[CI_N_SLOTS] = slots;
     // halo
     int n_halo = 0;
@@ -393,6 +412,7 @@ inline bool build_cluster_plan(int m, const int32_t *rowptr, const int32_t *coli
     Q.max_w = std::max(Q.max_w, Wn);
     Q.max_my = std::max(Q.max_my, n_my);
     Q.max_slots = std::max(Q.max_slots, slots);
+    Q.max_vunits = std::max(Q.max_vunits, vunits);
     Q.max_halo = std::max(Q.max_halo, n_halo);
     Q.max_n2e = std::max(Q.max_n2e, Q.n2e_ptr.back());
     Q.max_nsrc = std::max(Q.max_nsrc, Q.nsrc_ptr.back());
@@ -422,11 +442,12 @@ inline bool build_cluster_plan(int m, const int32_t *rowptr, const int32_t *coli
     I[CI_OFF_N2E] = (int32_t)P.n2e_item.size();
     I[CI_OFF_NSRC] = (int32_t)P.nsrc_item.size();
     app(P.row_edge, Q.row_edge); app(P.row_ws, Q.row_ws); app(P.row_n0, Q.row_n0); app(P.row_n1, Q.row_n1);
-    app(P.blk_off, Q.blk_off); app(P.slot_src, Q.slot_src); app(P.slot_col, Q.slot_col);
+    app(P.blk_off, Q.blk_off); app(P.blk_voff, Q.blk_voff); app(P.slot_src, Q.slot_src); app(P.slot_col, Q.slot_col);
     app(P.halo_ws, Q.halo_ws); app(P.halo_src, Q.halo_src); app(P.node_id, Q.node_id);
     app(P.n2e_ptr, Q.n2e_ptr); app(P.n2e_item, Q.n2e_item); app(P.nsrc_ptr, Q.nsrc_ptr); app(P.nsrc_item, Q.nsrc_item);
     P.max_own = std::max(P.max_own, Q.max_own); P.max_w = std::max(P.max_w, Q.max_w); P.max_my = std::max(P.max_my, Q.max_my);
     P.max_slots = std::max(P.max_slots, Q.max_slots); P.max_halo = std::max(P.max_halo, Q.max_halo);
+    P.max_vunits = std::max(P.max_vunits, Q.max_vunits);
     P.max_n2e = std::max(P.max_n2e, Q.max_n2e); P.max_nsrc = std::max(P.max_nsrc, Q.max_nsrc);
   }
   return true;

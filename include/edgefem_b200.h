@@ -270,11 +270,13 @@ int efb_system_last_solve_shape(efb_system *sys, int32_t *cluster_ctas, int32_t 
 /* ------------------------------------------------------------------ diagnostics of the cluster split (host only, no GPU)
  * The plan that splits one small system over the CTAs of a thread-block cluster (free unknowns in reverse
  * Cuthill-McKee order, contiguous row bands, window/halo and nodal exchange lists; csrc/cluster_plan.hpp), built from
- * a CSR pattern, Dirichlet flags (or NULL) and the edge end nodes (or NULL: no auxiliary space).  `get` copies the
+ * a CSR pattern, Dirichlet flags (or NULL), the edge end nodes (or NULL: no auxiliary space) and the flags of the rows
+ * whose values are not all real (their ELL blocks store complex128, the others doubles).  `get` copies the
  * named index array, widened to int64, and returns its length (-1: unknown name); tests/test_cluster_plan.py runs
  * the kernel's algorithm on these arrays on the CPU. */
 int efb_debug_cluster_plan_build(int32_t m, const int32_t *rowptr, const int32_t *colidx, const uint8_t *dir, int32_t n_node,
-                                 const int32_t *edge_nodes, int32_t cluster_ctas, void **plan);
+                                 const int32_t *edge_nodes, const uint8_t *row_complex /* [m] or NULL = every row */,
+                                 int32_t cluster_ctas, void **plan);
 void efb_debug_cluster_plan_free(void *plan);
 int64_t efb_debug_cluster_plan_get(void *plan, const char *name, int64_t *buf, int64_t capacity);
 /* y = A[matrix] x on device, host in/out (test + diagnostics) */

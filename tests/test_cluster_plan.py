@@ -39,7 +39,17 @@ class Emu:
         for c in range(self.C):
             o, n = self.I(c, "OFF_SLOT"), self.I(c, "N_SLOTS")
             src = self.p["slot_src"][o:o + n]
-            v = np.where(src >= 0, self.vals[np.maximum(src, 0)], 0.0)
+            v = np.where(src >= 0, self.vals[np.maximum(src, 0)], 0.0).astype(complex)
+            # blocks of all-real rows keep the real part only (8-byte values in shared memory)
+            ob = self.I(c, "OFF_BLK")
+            for b in range(self.I(c, "N_BLK")):
+                o0, o1 = int(self.p["blk_off"][ob + b]), int(self.p["blk_off"][ob + b + 1])
+                v0, v1 = int(self.p["blk_voff"][ob + b]), int(self.p["blk_voff"][ob + b + 1])
+                assert v1 - v0 in (o1 - o0, 2 * (o1 - o0))
+                if v1 - v0 != 2 * (o1 - o0):
+                    v[o0:o1] = v[o0:o1].real
+                else:
+                    assert v0 % 2 == 0  # complex128 values stay 16-byte aligned
             self.mat.append((v, self.p["slot_col"][o:o + n]))
 
     def spmv(self, c, p_w):
@@ -173,15 +183,26 @@ def precond_arrays(mesh, A, pm):
     return en, 1.0 / A.diagonal(), linv
 
 
-@pytest.mark.parametrize("C", [1, 2, 4, 8])
+def complex_rows(A):
+    """Flags of the rows with a value that is not real (what k_row_complex computes on the device)."""
+    flag = np.zeros(A.shape[0], np.uint8)
+    rows = np.repeat(np.arange(A.shape[0]), np.diff(A.indptr))
+    flag[rows[A.data.imag != 0]] = 1
+    return flag
+
+
+@pytest.mark.parametrize("C,mixed", [(1, False), (2, False), (4, False), (8, False), (3, True), (6, True), (8, True)])
 @pytest.mark.parametrize("aux", [True, False])
-def test_cluster_plan_emulation_matches_direct_solve(wr90, C, aux):
-    if not aux and C not in (1, 8):
-        pytest.skip("Jacobi needs ~1800 iterations: two cluster sizes are enough")
+def test_cluster_plan_emulation_matches_direct_solve(wr90, C, mixed, aux):
+    if not aux and (C, mixed) not in ((1, False), (8, False), (6, True)):
+        pytest.skip("Jacobi needs ~1800 iterations: three shapes are enough")
     mesh, pec, A, bs = wr90_system(wr90)
     pm = orc.pec_mask(mesh, pec)
     en, dinv, linv = precond_arrays(mesh, A, pm)
-    plan = cabi.cluster_plan_arrays(A.indptr, A.indices, pm.astype(np.uint8), mesh.xyz.shape[0] if aux else 0, en if aux else None, C)
+    rc = complex_rows(A) if mixed else None
+    if mixed:  # the lossless guide is real except for the rows of the two port faces
+        assert 0 < int(rc[~pm].sum()) < 0.1 * int((~pm).sum())
+    plan = cabi.cluster_plan_arrays(A.indptr, A.indices, pm.astype(np.uint8), mesh.xyz.shape[0] if aux else 0, en if aux else None, C, rc)
     d = plan["dims"]
     assert d[0] == C and d[1] == int((~pm).sum())
     info = plan["cta_info"].reshape(C, 16)
@@ -211,6 +232,13 @@ def test_cluster_plan_band_and_footprint(wr90):
     # padding of the ELL blocks stays small (rows sorted by length inside a CTA)
     nnz_free = int(np.count_nonzero((~pm)[np.repeat(np.arange(A.shape[0]), np.diff(A.indptr))] & (~pm)[A.indices]))
     assert info[:, INFO["N_SLOTS"]].sum() <= 1.15 * nnz_free
+    assert plan["dims"][11] == 2 * info[:, INFO["N_SLOTS"]].max()  # every block complex: 2 units per slot
+    # with the real rows stored as doubles the split over SIX CTAs fits too (24 clusters resident instead of 15) ...
+    plan6 = cabi.cluster_plan_arrays(A.indptr, A.indices, pm.astype(np.uint8), mesh.xyz.shape[0], en, 6, complex_rows(A))
+    assert plan6["dims"][9] <= 227 * 1024 and plan6["dims"][4] <= 2 * 640  # two rows per thread
+    # ... which the all-complex storage does not
+    plan6c = cabi.cluster_plan_arrays(A.indptr, A.indices, pm.astype(np.uint8), mesh.xyz.shape[0], en, 6)
+    assert plan6c["dims"][9] > 227 * 1024
 
 
 def test_cluster_plan_tiny_and_no_dirichlet():

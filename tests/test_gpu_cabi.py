@@ -128,11 +128,13 @@ def test_single_rhs_and_odd_batch(ctx, wr90):
         assert np.max(np.abs(S[fi] - S_o)) <= 1e-6
 
 
-@pytest.mark.parametrize("cl,nr", [(2, 1), (4, 1), (8, 1)])
+@pytest.mark.parametrize("cl,nr", [(2, 1), (3, 1), (4, 1), (6, 1), (8, 1)])
 @pytest.mark.parametrize("precond", [cabi.PRECOND_AUX, cabi.PRECOND_JACOBI])
 def test_cluster_solver_shapes(ctx, cl, nr, precond, monkeypatch):
-    """The cluster-split persistent solver with 2, 4 and 8 CTAs per cluster, with and without the auxiliary space, on a small
-    two-port guide against the oracle's direct solve (one right-hand side per job: the only enabled shape)."""
+    """The cluster-split persistent solver with 2, 3, 4, 6 and 8 CTAs per cluster, with and without the auxiliary space, on a
+    small two-port guide against the oracle's direct solve (one right-hand side per job: the only enabled shape).  The guide
+    is lossless: only the rows of the port faces are stored as complex values, and EDGEFEM_B200_CLUSTER_NO_REAL=1 (every row
+    complex) must give the same answer."""
     from edgefem_b200 import meshgen
 
     xyz, tets, tp, tris, trp = meshgen.rect_waveguide(a=0.02286, b=0.01016, length=0.03, nx=6, ny=3, nz=10)
@@ -150,3 +152,7 @@ def test_cluster_solver_shapes(ctx, cl, nr, precond, monkeypatch):
     assert np.max(np.abs(S[0] - S_ref)) <= 1e-6
     if shape is not None:
         assert shape[0] == cl and shape[1] == nr
+    if cl in (3, 8):
+        monkeypatch.setenv("EDGEFEM_B200_CLUSTER_NO_REAL", "1")
+        S2, res2 = H.eigenmode_sweep_gpu(ctx, mesh, pec, ports, [f], method=cabi.METHOD_COCG, precond=precond)
+        assert all(r["converged"] for r in res2) and np.max(np.abs(S2[0] - S[0])) <= 1e-9
