@@ -870,8 +870,9 @@ int run_krylov_cluster(SolvePlan &P, const efb_solve_opts *o, bool zero_x, bool 
   const int n_rhs = S->n_rhs;
   // One right-hand side per job.  Two per job (sharing the matrix reads and the barriers) is templated but NOT enabled:
   // next to a complex matrix slice it only fits without the auxiliary space, it was measured slower there (SpMV 2.3x for
-  // two right-hand sides: 32-byte gathers halve the distinct bank groups), and its iteration showed a convergence defect
-  // (first p update) that was not tracked down.
+  // two right-hand sides: 32-byte gathers halve the distinct bank groups), and it does not converge: with 440 bytes of
+  // register spills a search-direction entry comes back as denormal garbage right after `p = z + beta p` on zeros (the
+  // values printed before the update are correct) -- a spill-slot defect of that instantiation that was not resolved.
   const int nr_want = 1;
   ClusterPlanDev *PL = S->cl_plan ? ((std::shared_ptr<ClusterPlanDev> *)S->cl_plan)->get() : nullptr;
   const uint8_t *dirp = (int)S->h_dir.size() == S->m ? S->h_dir.data() : nullptr;

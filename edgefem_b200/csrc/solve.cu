@@ -1612,6 +1612,22 @@ static int run_cocg_small(SolvePlan &P, const efb_solve_opts *o, bool zero_x, bo
         n_jobs = (int)codes.size();
       }
     }
+    // Head split (one round: fewer matrices than SMs, e.g. the 128-point shard of a sweep over 2 GPUs): the launch lasts as
+    // long as its longest job while sm_count - n_jobs SMs idle.  The X = idle-SM-count matrices expected to take longest are
+    // queued as two one-rhs jobs each (cost ~0.8 of the two-rhs job): makespan max(0.8 * longest, (X+1)-th longest).
+    if (!mixed && nr == 2 && S->n_rhs == 2 && n_jobs <= c->sm_count && 2 * n_jobs > c->sm_count && variant < 4 && !no_split && (have_it || have_om)) {
+      const int X = std::min(c->sm_count - n_jobs, n_jobs);
+      if (X > 0) {
+        mixed = 1;
+        codes.clear();
+        for (int i = 0; i < X; ++i) {
+          codes.push_back((int32_t)(order[i] * 4 + 1));
+          codes.push_back((int32_t)(order[i] * 4 + 2));
+        }
+        for (int i = X; i < n_jobs; ++i) codes.push_back((int32_t)(order[i] * 4));
+        n_jobs = (int)codes.size();
+      }
+    }
     if ((size_t)n_jobs + 1 > (size_t)S->n_sys + 1) return fail(c, EFB_ERR_STATE, "persistent solver: job queue overflow");
     S->h_job_order.resize((size_t)n_jobs + 1);
     S->h_job_order[0] = 0;
