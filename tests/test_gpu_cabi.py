@@ -101,6 +101,23 @@ def test_wr90_sweep_batched(ctx, wr90):
     print("iters", [r["iters"] for r in res])
 
 
+@pytest.mark.parametrize("n_freq", [80, 160])
+def test_wr90_sweep_one_cta_queue_shapes(ctx, wr90, n_freq, monkeypatch):
+    """Job queue shapes of the one-CTA persistent solver: 80 matrices (fewer than SMs: the longest are split into two one-rhs
+    jobs) and 160 (more than SMs: two rounds from the longest-first queue).  Every right-hand side converges; sampled S match
+    the oracle within 1e-6."""
+    mesh, pec = wr90
+    monkeypatch.setenv("EDGEFEM_B200_CLUSTER", "0")
+    freqs = np.linspace(8e9, 12e9, n_freq)
+    ports = orc.wr90_ports(mesh, pec, 10e9)
+    S, res = H.eigenmode_sweep_gpu(ctx, mesh, pec, ports, freqs)
+    assert len(res) == 2 * n_freq and all(r["converged"] for r in res)
+    assert all(r["residual"] <= 1e-10 * 1.001 for r in res)
+    for fi in (0, n_freq // 3, n_freq - 1):
+        S_ref = orc.wr90_sparams(mesh, pec, freqs[fi], ports)
+        assert np.max(np.abs(S[fi] - S_ref)) <= 1e-6
+
+
 def test_generic_multikernel_cocg_path(ctx, wr90, monkeypatch):
     """The large-system (multi-kernel, ticketed reductions) COCG path gives the same S as the persistent one."""
     mesh, pec = wr90
