@@ -30,6 +30,9 @@ namespace cg = cooperative_groups;
 
 namespace efb {
 
+#ifndef EFB_CL_LPN
+#define EFB_CL_LPN 2
+#endif
 constexpr int CL_THREADS_MAX = 640;   // thread per row up to here at 96 registers
 constexpr int CL_THREADS_WIDE = 768;  // wide CTAs (a 6-CTA split of WR-90 has 745 rows per CTA): 80 registers, a few spills, still
                                       // faster than two rows per thread (measured 2.9 against 3.8 ms per job)
@@ -41,7 +44,7 @@ struct ClusterDev {
   int ndeg, sdeg;  // widths of the per-node ELL lists below (own edges at a node / CTAs touching a node)
   const uint16_t *n2e_ell;  // [C][ndeg][max_my] own local row << 1 | head, 0xffff = none
   const uint32_t *nsrc_ell; // [C][sdeg][max_my] CTA << 16 | that CTA's node slot, 0xffffffff = none
-  long long *prof;  // [C][16] cycle counters per phase (EDGEFEM_B200_CLUSTER_PROF=1), else null
+  long long *prof;  // [C][24] cycle counters per phase (EDGEFEM_B200_CLUSTER_PROF=1), else null
   const int32_t *cta_info, *row_edge;
   const uint16_t *row_ws, *row_n0, *row_n1;
   const int32_t *blk_off, *blk_voff, *slot_src;
@@ -97,7 +100,7 @@ static size_t cluster_smem_bytes(int nr, const ClusterPlanHost &P) {
   b += ((size_t)std::max(P.max_halo, 1) * 2 + 15) / 16 * 16;   // halo_ws
   b += ((size_t)ndeg * std::max(P.max_my, 1) * 2 + 15) / 16 * 16;  // n2e_ell
   b += ((size_t)sdeg * std::max(P.max_my, 1) * 4 + 15) / 16 * 16;  // nsrc_ell
-  b += 16 * 8;                                                 // phase counters
+  b += 24 * 8;                                                 // phase counters
   return b + 16;
 }
 
@@ -117,15 +120,19 @@ __device__ __forceinline__ c128 cdiv_fast(c128 a, c128 b) {
 // Block-wide sums of N doubles pushed to every CTA of the cluster: warp shuffles, one block barrier, then thread
 // (c*N + k) adds the warp partials of sum k in warp order and stores the result into bank[crank*8 + k] of CTA c.
 template <int N>
-__device__ __forceinline__ void reduce_push(cg::cluster_group &cluster, double (&v)[N], double *red, double *bank, int C, int crank) {
+__device__ __forceinline__ void reduce_push(cg::cluster_group &cluster, double (&v)[N], double *red, double *bank, int C, int crank, long long *pp = nullptr) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  long long tq0 = 0, tq1 = 0, tq2 = 0;
+  if (pp) tq0 = clock64();
 #pragma unroll
   for (int k = 0; k < N; ++k) {
     double a = v[k];
     for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
     if (lane == 0) red[wid * N + k] = a;
   }
+  if (pp) tq1 = clock64();
   __syncthreads();
+  if (pp) tq2 = clock64();
   if ((int)threadIdx.x < N * C) {
     const int k = threadIdx.x % N, c = threadIdx.x / N;
     double a0 = 0.0, a1 = 0.0;
@@ -138,6 +145,7 @@ __device__ __forceinline__ void reduce_push(cg::cluster_group &cluster, double (
     double *dst = c == crank ? bank : cluster.map_shared_rank(bank, c);
     dst[crank * 8 + k] = a0 + a1;
   }
+  if (pp) { pp[0] += tq1 - tq0; pp[1] += tq2 - tq1; pp[2] += clock64() - tq2; }
 }
 
 // Totals over the ranks of a bank [CL_MAX_C][8], the same fixed tree in every warp of every CTA (bit-identical
@@ -222,7 +230,7 @@ k_cocg_cluster(const SolveDev D, const ClusterDev K, int first_matrix, int n_job
   for (int i = tid; i < K.ndeg * K.max_my; i += nth) n2e_ell_s[i] = K.n2e_ell[(size_t)crank * K.ndeg * K.max_my + i];
   for (int i = tid; i < K.sdeg * K.max_my; i += nth) nsrc_ell_s[i] = K.nsrc_ell[(size_t)crank * K.sdeg * K.max_my + i];
   for (int i = tid; i < 2 * CL_MAX_C * 8; i += nth) part[i] = 0.0;  // banks of absent ranks (C < 8) stay zero
-  if (tid < 16) prof_s[tid] = 0;
+  if (tid < 24) prof_s[tid] = 0;
   __syncthreads();
   long long t_last = 0;
   const bool prof_on = K.prof != nullptr && tid == 0;
@@ -314,14 +322,15 @@ k_cocg_cluster(const SolveDev D, const ClusterDev K, int first_matrix, int n_job
       }
     }
   };
-  // wp[n] = sum over the own edges at my node n of +-q_own: 4 lanes per node, lane l takes items l, l+4, ... of the
+  // wp[n] = sum over the own edges at my node n of +-q_own: LPN lanes per node, lane l takes items l, l+LPN, ... of the
   // node's ELL list.  All item loads are issued first, then all q loads (no data-dependent loop exit in the common
-  // case of <= 32 own edges at a node), two shuffle steps, fixed order.
+  // case of <= 8 LPN own edges at a node), log2(LPN) shuffle steps, fixed order.
+  constexpr int LPN = EFB_CL_LPN, NPW = 32 / LPN;  // lanes per node, nodes per warp step
   auto nodal_partial = [&]() {
     if (!K.aux) return;
-    const int l4 = lane & 3;
-    for (int jb = (tid >> 5) * 8; jb < n_my; jb += (nth >> 5) * 8) {
-      const int j = jb + (lane >> 2);
+    const int ll = lane & (LPN - 1);
+    for (int jb = (tid >> 5) * NPW; jb < n_my; jb += (nth >> 5) * NPW) {
+      const int j = jb + lane / LPN;
       c128 a[NR];
 #pragma unroll
       for (int r = 0; r < NR; ++r) a[r] = cmake(0.0, 0.0);
@@ -329,7 +338,7 @@ k_cocg_cluster(const SolveDev D, const ClusterDev K, int first_matrix, int n_job
         uint32_t it[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          const int k = l4 + 4 * u;
+          const int k = ll + LPN * u;
           it[u] = k < K.ndeg ? (uint32_t)n2e_ell_s[k * K.max_my + j] : 0xffffu;
         }
         c128 v[8][NR];
@@ -341,7 +350,7 @@ k_cocg_cluster(const SolveDev D, const ClusterDev K, int first_matrix, int n_job
         for (int u = 0; u < 8; ++u)
 #pragma unroll
           for (int r = 0; r < NR; ++r) a[r] = (it[u] & 1u) ? cadd(a[r], v[u][r]) : csub(a[r], v[u][r]);
-        for (int k = l4 + 32; k < K.ndeg; k += 4) {  // nodes with more than 32 own edges (rare)
+        for (int k = ll + 8 * LPN; k < K.ndeg; k += LPN) {  // nodes with more than 8 LPN own edges (rare)
           const uint32_t itk = n2e_ell_s[k * K.max_my + j];
           if (itk == 0xffffu) break;
 #pragma unroll
@@ -354,11 +363,11 @@ k_cocg_cluster(const SolveDev D, const ClusterDev K, int first_matrix, int n_job
 #pragma unroll
       for (int r = 0; r < NR; ++r)
 #pragma unroll
-        for (int o = 1; o <= 2; o <<= 1) {
+        for (int o = 1; o < LPN; o <<= 1) {
           a[r].x += __shfl_xor_sync(0xffffffffu, a[r].x, o);
           a[r].y += __shfl_xor_sync(0xffffffffu, a[r].y, o);
         }
-      if (j < n_my && l4 == 0)
+      if (j < n_my && ll == 0)
 #pragma unroll
         for (int r = 0; r < NR; ++r) wp[j * NR + r] = a[r];
     }
@@ -579,7 +588,7 @@ k_cocg_cluster(const SolveDev D, const ClusterDev K, int first_matrix, int n_job
           PROF(2);
           nodal_partial();
           PROF(3);
-          reduce_push<2 * NR>(cluster, d, red, bank0, C, crank);
+          reduce_push<2 * NR>(cluster, d, red, bank0, C, crank, prof_on ? prof_s + 16 : nullptr);
           PROF(4);
         }
         cluster.sync();  // barrier 1
@@ -628,7 +637,7 @@ k_cocg_cluster(const SolveDev D, const ClusterDev K, int first_matrix, int n_job
                 d[3 * r + 2] += cabs2(rv[u][r]);
               }
           PROF(9);
-          reduce_push<3 * NR>(cluster, d, red, bank1, C, crank);
+          reduce_push<3 * NR>(cluster, d, red, bank1, C, crank, prof_on ? prof_s + 19 : nullptr);
           PROF(10);
         }
         cluster.sync();  // barrier 2
@@ -687,7 +696,7 @@ k_cocg_cluster(const SolveDev D, const ClusterDev K, int first_matrix, int n_job
     // the next job's first barrier orders the reuse of the shared-memory buffers across the cluster
   }
   if (prof_on)
-    for (int k = 0; k < 16; ++k) atomicAdd((unsigned long long *)&K.prof[crank * 16 + k], (unsigned long long)prof_s[k]);
+    for (int k = 0; k < 24; ++k) atomicAdd((unsigned long long *)&K.prof[crank * 24 + k], (unsigned long long)prof_s[k]);
 }
 
 // ---------------------------------------------------------------- host side
@@ -790,7 +799,7 @@ static int cluster_plan_upload(System *S, ClusterPlanDev *P) {
   if (const char *e = getenv("EDGEFEM_B200_CLUSTER_PROF"))
     if (atoi(e) > 0) {
       long long *pb = nullptr;
-      int rcp = dev_alloc(c, &pb, (size_t)CL_MAX_C * 16);
+      int rcp = dev_alloc(c, &pb, (size_t)CL_MAX_C * 24);
       if (rcp) return rcp;
       P->blocks.push_back(pb);
       d.prof = pb;
@@ -1048,7 +1057,7 @@ int run_krylov_cluster(SolvePlan &P, const efb_solve_opts *o, bool zero_x, bool 
     EFB_CUDA(c, cudaEventCreate(&S->ev_s0));
     EFB_CUDA(c, cudaEventCreate(&S->ev_s1));
   }
-  if (PL->d.prof) EFB_CUDA(c, cudaMemsetAsync(PL->d.prof, 0, (size_t)CL_MAX_C * 16 * sizeof(long long), c->stream));
+  if (PL->d.prof) EFB_CUDA(c, cudaMemsetAsync(PL->d.prof, 0, (size_t)CL_MAX_C * 24 * sizeof(long long), c->stream));
   EFB_CUDA(c, cudaEventRecord(S->ev_s0, c->stream));
   const int mr = o->max_restarts > 0 ? o->max_restarts : 3;
   int rc = EFB_OK, ncl = 0;
@@ -1061,15 +1070,16 @@ int run_krylov_cluster(SolvePlan &P, const efb_solve_opts *o, bool zero_x, bool 
   if (rc) return rc;
   EFB_CUDA(c, cudaEventRecord(S->ev_s1, c->stream));
   if (PL->d.prof) {  // EDGEFEM_B200_CLUSTER_PROF=1: cycles of thread 0 of every CTA rank between the phase marks
-    std::vector<long long> hp((size_t)CL_MAX_C * 16);
+    std::vector<long long> hp((size_t)CL_MAX_C * 24);
     EFB_CUDA(c, cudaMemcpyAsync(hp.data(), PL->d.prof, hp.size() * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
     EFB_CUDA(c, cudaStreamSynchronize(c->stream));
-    static const char *names[16] = {"D->A", "spmv", "q store+bar", "nodal partial", "reduce+push 1", "cluster barrier 1", "totals+alpha",
+    static const char *names[24] = {"D->A", "spmv", "q store+bar", "nodal partial", "reduce+push 1", "cluster barrier 1", "totals+alpha",
                                     "nodal combine", "x,r update+bar", "z+dots", "reduce+push 2", "cluster barrier 2", "totals+beta",
-                                    "p update", "halo pull", ""};
-    for (int k = 0; k < 15; ++k) {
+                                    "p update", "halo pull", "", " r1: shuffles", " r1: block barrier", " r1: sum + push", " r2: shuffles", " r2: block barrier", " r2: sum + push", "", ""};
+    for (int k = 0; k < 22; ++k) {
+      if (!names[k][0]) continue;
       fprintf(stderr, "[cluster prof] %-18s", names[k]);
-      for (int r = 0; r < PL->h.C; ++r) fprintf(stderr, " %10lld", hp[(size_t)r * 16 + k]);
+      for (int r = 0; r < PL->h.C; ++r) fprintf(stderr, " %10lld", hp[(size_t)r * 24 + k]);
       fprintf(stderr, "\n");
     }
   }

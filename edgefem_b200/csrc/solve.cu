@@ -690,6 +690,12 @@ k_bicg_x(SolveDev D, int first_sys, c128 *__restrict__ x, c128 *__restrict__ r, 
 // reduction is CTA-local (no tickets, no grid-wide barriers, no kernel launches inside the loop)
 // and CTAs pull the next matrix from an atomic queue when theirs has converged.
 constexpr int SMALL_LPR = 16;
+#ifndef EFB_SMALL_GL
+#define EFB_SMALL_GL 2  // lanes per node of the nodal gather
+#endif
+#ifndef EFB_SMALL_GB
+#define EFB_SMALL_GB 4  // items per lane and batch (independent loads)
+#endif
 
 // 32-byte load (LDG.256, sm_100): both right-hand sides of one interleaved r entry in ONE request -- a random gather costs a
 // wavefront per distinct line whatever its width, so this halves the load-pipe cost of the nodal gather
@@ -985,66 +991,55 @@ __device__ __forceinline__ void cocg_small_job(const SolveDev &D, const int32_t 
       EFB_SPROF(7);
       // z = M^-1 r  (z parked in q), rho_new = r^T z, rr = |r|^2
       if (aux) {
-        // nodal gather w = diag(G^T A G)^-1 G^T r: 16 lanes cooperate on a node (its ~12 incident edges are
-        // fetched in one parallel step instead of a serial chain), half-warp shuffle reduction
-        // Two nodes per half-warp step: their r loads and shuffle trees are independent chains, and 1/L is requested
-        // before the gather instead of after the reduction (the step was one serial chain r -> shuffles -> 1/L -> store;
-        // 29 % of the iteration).  Lanes and shuffle tree are those of the one-node form: the sums are bit-identical.
-        const int l16 = tid & 15, g16 = tid >> 4, ng16 = nth >> 4;
-        const unsigned hmask = 0xffffu << (((tid & 31) >> 4) * 16);
-        for (int n0 = 2 * g16; n0 < nn; n0 += 2 * ng16) {
-          const bool two = n0 + 1 < nn;
-          const int kb0 = L.ptr(n0), ke0 = L.ptr(n0 + 1), ke1 = two ? L.ptr(n0 + 2) : ke0;
-          const int it0 = kb0 + l16 < ke0 ? L.item(kb0 + l16) : -1;  // compact edge << 1 | head (Dirichlet edges are not in the lists)
-          const int it1 = ke0 + l16 < ke1 ? L.item(ke0 + l16) : -1;
-          const c128 li = __ldg(&linv[n0 + ((l16 & 1) && two ? 1 : 0)]);  // lane 0 stores node n0, lane 1 node n0 + 1
-          c128 a2[2][NR];
-          if constexpr (NR == 2) {
-            c128 v00 = cmake(0.0, 0.0), v01 = v00, v10 = v00, v11 = v00;
-            if (it0 >= 0) ldg256(&rg(0, it0 >> 1), v00, v01);
-            if (it1 >= 0) ldg256(&rg(0, it1 >> 1), v10, v11);
-            a2[0][0] = (it0 & 1) ? v00 : cneg(v00);
-            a2[0][NR - 1] = (it0 & 1) ? v01 : cneg(v01);
-            a2[1][0] = (it1 & 1) ? v10 : cneg(v10);
-            a2[1][NR - 1] = (it1 & 1) ? v11 : cneg(v11);
-          } else {
+        // nodal gather w = diag(G^T A G)^-1 G^T r.  GL lanes per node, 32/GL nodes per warp step: the whole node set is
+        // covered in nn / (warps * 32/GL) steps (WR-90: 972 nodes, 32 warps, GL = 4 -> 4 steps; the 16-lanes-per-node form
+        // needed 16 and each step is a chain of L2 round trips: 22-29 % of the iteration).  A lane takes items l, l+GL, ...
+        // of its node, GB at a time with independent loads (both right-hand sides of an edge in one LDG.256), then
+        // log2(GL) shuffle steps in a fixed order.
+        constexpr int GL = EFB_SMALL_GL, GB = EFB_SMALL_GB, NPWS = 32 / GL;
+        const int gl = tid & (GL - 1), wsub = (tid & 31) / GL;
+        for (int n0 = (tid >> 5) * NPWS; n0 < nn; n0 += (nth >> 5) * NPWS) {
+          const int n = n0 + wsub;
+          const bool on = n < nn;
+          const int kb = on ? L.ptr(n) : 0, ke = on ? L.ptr(n + 1) : 0;
+          c128 li = cmake(0.0, 0.0);
+          if (on && gl == 0) li = __ldg(&linv[n]);
+          c128 a2[NR];
 #pragma unroll
-            for (int r = 0; r < NR; ++r) {
-              c128 v0 = cmake(0.0, 0.0), v1 = cmake(0.0, 0.0);
-              if (it0 >= 0) v0 = rg(r, it0 >> 1);
-              if (it1 >= 0) v1 = rg(r, it1 >> 1);
-              a2[0][r] = (it0 & 1) ? v0 : cneg(v0);
-              a2[1][r] = (it1 & 1) ? v1 : cneg(v1);
-            }
-          }
-          for (int k = kb0 + 16 + l16; k < ke0; k += 16) {  // more than 16 incident free edges: rare
-            const int it = L.item(k);
+          for (int r = 0; r < NR; ++r) a2[r] = cmake(0.0, 0.0);
+          for (int k0 = kb + gl; k0 < ke; k0 += GL * GB) {
+            int it[GB];
 #pragma unroll
-            for (int r = 0; r < NR; ++r) {
-              const c128 v = rg(r, it >> 1);
-              a2[0][r] = (it & 1) ? cadd(a2[0][r], v) : csub(a2[0][r], v);
-            }
-          }
-          for (int k = ke0 + 16 + l16; k < ke1; k += 16) {
-            const int it = L.item(k);
+            for (int u = 0; u < GB; ++u) it[u] = k0 + GL * u < ke ? L.item(k0 + GL * u) : -1;  // compact edge << 1 | head
+            c128 v[GB][NR];
 #pragma unroll
-            for (int r = 0; r < NR; ++r) {
-              const c128 v = rg(r, it >> 1);
-              a2[1][r] = (it & 1) ? cadd(a2[1][r], v) : csub(a2[1][r], v);
-            }
-          }
+            for (int u = 0; u < GB; ++u) {
 #pragma unroll
-          for (int o = 8; o > 0; o >>= 1)
+              for (int r = 0; r < NR; ++r) v[u][r] = cmake(0.0, 0.0);
+              if (it[u] >= 0) {
+                if constexpr (NR == 2) {
+                  ldg256(&rg(0, it[u] >> 1), v[u][0], v[u][NR - 1]);
+                } else {
 #pragma unroll
-            for (int u = 0; u < 2; ++u)
-#pragma unroll
-              for (int r = 0; r < NR; ++r) {
-                a2[u][r].x += __shfl_xor_sync(hmask, a2[u][r].x, o);
-                a2[u][r].y += __shfl_xor_sync(hmask, a2[u][r].y, o);
+                  for (int r = 0; r < NR; ++r) v[u][r] = rg(r, it[u] >> 1);
+                }
               }
-          if (l16 == 0 || (l16 == 1 && two)) {
+            }
 #pragma unroll
-            for (int r = 0; r < NR; ++r) w_s[(size_t)r * nn + n0 + l16] = cmul(li, l16 ? a2[1][r] : a2[0][r]);
+            for (int u = 0; u < GB; ++u)
+#pragma unroll
+              for (int r = 0; r < NR; ++r) a2[r] = (it[u] & 1) ? cadd(a2[r], v[u][r]) : csub(a2[r], v[u][r]);
+          }
+#pragma unroll
+          for (int o = GL / 2; o > 0; o >>= 1)
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+              a2[r].x += __shfl_xor_sync(0xffffffffu, a2[r].x, o);
+              a2[r].y += __shfl_xor_sync(0xffffffffu, a2[r].y, o);
+            }
+          if (on && gl == 0) {
+#pragma unroll
+            for (int r = 0; r < NR; ++r) w_s[(size_t)r * nn + n] = cmul(li, a2[r]);
           }
         }
         __syncthreads();
