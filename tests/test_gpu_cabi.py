@@ -101,6 +101,23 @@ def test_wr90_sweep_batched(ctx, wr90):
     print("iters", [r["iters"] for r in res])
 
 
+def test_cluster_solver_two_rows_per_thread(ctx, wr90, kat, monkeypatch):
+    """WR-90 split over 5 CTAs without the auxiliary space: 862 rows per CTA, more than the widest CTA has threads, so every
+    thread owns two rows (the RPT = 2 instantiation of the cluster kernel)."""
+    mesh, pec = wr90
+    f = 10e9
+    ports = orc.wr90_ports(mesh, pec, f)
+    S_ref = orc.wr90_sparams(mesh, pec, f, ports)
+    monkeypatch.setenv("EDGEFEM_B200_CLUSTER", "5")
+    keep = {}
+    S, res = H.eigenmode_sweep_gpu(ctx, mesh, pec, ports, [f], method=cabi.METHOD_COCG, precond=cabi.PRECOND_JACOBI, keep=keep)
+    shape = keep["sys"].last_solve_shape()
+    print("shape", shape, "iters", [r["iters"] for r in res])
+    assert shape[0] == 5, "the 5-CTA split was expected to fit in shared memory without the nodal arrays"
+    assert all(r["converged"] for r in res)
+    assert np.max(np.abs(S[0] - S_ref)) <= 1e-6
+
+
 @pytest.mark.parametrize("n_freq", [80, 160])
 def test_wr90_sweep_one_cta_queue_shapes(ctx, wr90, n_freq, monkeypatch):
     """Job queue shapes of the one-CTA persistent solver: 80 matrices (fewer than SMs: the longest are split into two one-rhs
