@@ -229,7 +229,7 @@ def cluster_plan_arrays(rowptr, colidx, dir_flags=None, n_node=0, edge_nodes=Non
     out = {}
     try:
         for name in ("dims", "c_orig", "cta_info", "row_edge", "row_ws", "row_n0", "row_n1", "blk_off", "blk_voff", "slot_src", "slot_col", "halo_ws",
-                     "halo_src", "node_id", "n2e_ptr", "n2e_item", "nsrc_ptr", "nsrc_item"):
+                     "halo_src", "push_row", "push_dst", "node_id", "n2e_ptr", "n2e_item", "nsrc_ptr", "nsrc_item"):
             n = lib.efb_debug_cluster_plan_get(h, name.encode(), None, 0)
             buf = np.zeros(max(int(n), 1), dtype=np.int64)
             lib.efb_debug_cluster_plan_get(h, name.encode(), _p(buf, i64p), buf.size)

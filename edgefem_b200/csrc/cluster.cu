@@ -40,6 +40,7 @@ constexpr int CL_THREADS_WIDE = 768;  // wide CTAs (a 6-CTA split of WR-90 has 7
 struct ClusterDev {
   int C, mc, aux;
   int max_own, max_w, max_my, max_slots, max_halo, max_n2e, max_nsrc;
+  int max_push;    // longest push list (own rows sent into other CTAs' halos)
   int max_vunits;  // value image of a CTA in 8-byte units (real blocks: 1 per slot, complex blocks: 2)
   int ndeg, sdeg;  // widths of the per-node ELL lists below (own edges at a node / CTAs touching a node)
   const uint16_t *n2e_ell;  // [C][ndeg][max_my] own local row << 1 | head, 0xffff = none
@@ -48,8 +49,8 @@ struct ClusterDev {
   const int32_t *cta_info, *row_edge;
   const uint16_t *row_ws, *row_n0, *row_n1;
   const int32_t *blk_off, *blk_voff, *slot_src;
-  const uint16_t *slot_col, *halo_ws;
-  const uint32_t *halo_src;
+  const uint16_t *slot_col, *halo_ws, *push_row;
+  const uint32_t *halo_src, *push_dst;
   const int32_t *node_id, *n2e_ptr;
   const uint32_t *n2e_item;
   const int32_t *nsrc_ptr;
@@ -98,6 +99,9 @@ static size_t cluster_smem_bytes(int nr, const ClusterPlanHost &P) {
   b += ((size_t)P.max_slots * 2 + 15) / 16 * 16;  // mat_c
   b += ((size_t)std::max(P.max_halo, 1) * 4 + 15) / 16 * 16;   // halo_src
   b += ((size_t)std::max(P.max_halo, 1) * 2 + 15) / 16 * 16;   // halo_ws
+  b += (size_t)std::max(P.max_halo, 1) * nr * 16;               // zh: halo staging the owners push z into
+  b += ((size_t)std::max(P.max_push, 1) * 4 + 15) / 16 * 16;   // push_dst
+  b += ((size_t)std::max(P.max_push, 1) * 2 + 15) / 16 * 16;   // push_row
   b += ((size_t)ndeg * std::max(P.max_my, 1) * 2 + 15) / 16 * 16;  // n2e_ell
   b += ((size_t)sdeg * std::max(P.max_my, 1) * 4 + 15) / 16 * 16;  // nsrc_ell
   b += 24 * 8;                                                 // phase counters
@@ -187,7 +191,10 @@ k_cocg_cluster(const SolveDev D, const ClusterDev K, int first_matrix, int n_job
   // acquire), so lists read from global memory would come from L2 again in every phase of every iteration
   uint32_t *halo_src_s = (uint32_t *)((unsigned char *)mat_c + up16((size_t)K.max_slots * 2));
   uint16_t *halo_ws_s = (uint16_t *)((unsigned char *)halo_src_s + up16((size_t)max(K.max_halo, 1) * 4));
-  uint16_t *n2e_ell_s = (uint16_t *)((unsigned char *)halo_ws_s + up16((size_t)max(K.max_halo, 1) * 2));
+  c128 *zh = (c128 *)((unsigned char *)halo_ws_s + up16((size_t)max(K.max_halo, 1) * 2));  // [max_halo][NR]
+  uint32_t *push_dst_s = (uint32_t *)(zh + (size_t)max(K.max_halo, 1) * NR);
+  uint16_t *push_row_s = (uint16_t *)((unsigned char *)push_dst_s + up16((size_t)max(K.max_push, 1) * 4));
+  uint16_t *n2e_ell_s = (uint16_t *)((unsigned char *)push_row_s + up16((size_t)max(K.max_push, 1) * 2));
   uint32_t *nsrc_ell_s = (uint32_t *)((unsigned char *)n2e_ell_s + up16((size_t)K.ndeg * K.max_my * 2));
   long long *prof_s = (long long *)((unsigned char *)nsrc_ell_s + up16((size_t)K.sdeg * K.max_my * 4));
   double *bank0 = part, *bank1 = part + CL_MAX_C * 8;
@@ -196,6 +203,7 @@ k_cocg_cluster(const SolveDev D, const ClusterDev K, int first_matrix, int n_job
   const int n_own = I[CI_N_OWN], n_my = I[CI_N_MY], n_halo = I[CI_N_HALO], n_blk = I[CI_N_BLK], n_slots = I[CI_N_SLOTS];
   const int off_row = I[CI_OFF_ROW], off_slot = I[CI_OFF_SLOT], off_blk = I[CI_OFF_BLK], off_halo = I[CI_OFF_HALO];
   const int off_node = I[CI_OFF_NODE];
+  const int n_push = I[CI_N_PUSH], off_push = I[CI_OFF_PUSH];
   const int m = D.m;
 
   // per-thread rows: local row t = u * nth + tid (a warp = one 32-row ELL block)
@@ -226,6 +234,10 @@ k_cocg_cluster(const SolveDev D, const ClusterDev K, int first_matrix, int n_job
   for (int i = tid; i < n_halo; i += nth) {
     halo_ws_s[i] = K.halo_ws[off_halo + i];
     halo_src_s[i] = K.halo_src[off_halo + i];
+  }
+  for (int i = tid; i < n_push; i += nth) {
+    push_dst_s[i] = K.push_dst[off_push + i];
+    push_row_s[i] = K.push_row[off_push + i];
   }
   for (int i = tid; i < K.ndeg * K.max_my; i += nth) n2e_ell_s[i] = K.n2e_ell[(size_t)crank * K.ndeg * K.max_my + i];
   for (int i = tid; i < K.sdeg * K.max_my; i += nth) nsrc_ell_s[i] = K.nsrc_ell[(size_t)crank * K.sdeg * K.max_my + i];
@@ -320,6 +332,25 @@ k_cocg_cluster(const SolveDev D, const ClusterDev K, int first_matrix, int n_job
         const c128 z = rz[r];
         p_w[hw * NR + r] = use_beta ? cfma(beta[r], p_w[hw * NR + r], z) : z;
       }
+    }
+  };
+  // The iteration does not pull: before barrier 2 every owner PUSHES z of the rows its neighbours read into their halo
+  // staging zh (remote stores are fire-and-forget, a remote load is a 215-cycle round trip), after the barrier the halo of
+  // the window is updated from local shared memory: p_w[h] = zh[h] + beta p_w[h].
+  auto push_halo = [&]() {
+    for (int i = tid; i < n_push; i += nth) {
+      const uint32_t dst = push_dst_s[i];
+      const c128 *zsrc = z_own + (size_t)push_row_s[i] * NR;
+      c128 *zd = cluster.map_shared_rank(zh, dst >> 16) + (size_t)(dst & 0xffffu) * NR;
+#pragma unroll
+      for (int r = 0; r < NR; ++r) zd[r] = zsrc[r];
+    }
+  };
+  auto halo_from_staging = [&](const c128 (&beta)[NR]) {
+    for (int h = tid; h < n_halo; h += nth) {
+      const int hw = halo_ws_s[h];
+#pragma unroll
+      for (int r = 0; r < NR; ++r) p_w[hw * NR + r] = cfma(beta[r], p_w[hw * NR + r], zh[(size_t)h * NR + r]);
     }
   };
   // wp[n] = sum over the own edges at my node n of +-q_own: LPN lanes per node, lane l takes items l, l+LPN, ... of the
@@ -638,6 +669,7 @@ k_cocg_cluster(const SolveDev D, const ClusterDev K, int first_matrix, int n_job
               }
           PROF(9);
           reduce_push<3 * NR>(cluster, d, red, bank1, C, crank, prof_on ? prof_s + 19 : nullptr);
+          push_halo();  // z_own is complete: reduce_push holds a block barrier after the z stores
           PROF(10);
         }
         cluster.sync();  // barrier 2
@@ -671,7 +703,7 @@ k_cocg_cluster(const SolveDev D, const ClusterDev K, int first_matrix, int n_job
               p_w[ws[u] * NR + r] = pr[u][r];
             }
         PROF(13);
-        pull_halo(beta, true);
+        halo_from_staging(beta);
         PROF(14);
         __syncthreads();
       }
@@ -765,11 +797,12 @@ static int cluster_plan_upload(System *S, ClusterPlanDev *P) {
   // uploads read the host vectors asynchronously: give every vector at least one element and sync at the end
   auto pad = [](auto &v) { if (v.empty()) v.resize(1); };
   pad(H.row_edge); pad(H.row_ws); pad(H.row_n0); pad(H.row_n1); pad(H.blk_off); pad(H.blk_voff); pad(H.slot_src); pad(H.slot_col);
-  pad(H.halo_ws); pad(H.halo_src); pad(H.node_id); pad(H.n2e_ptr); pad(H.n2e_item); pad(H.nsrc_ptr); pad(H.nsrc_item);
+  pad(H.halo_ws); pad(H.halo_src); pad(H.push_row); pad(H.push_dst); pad(H.node_id); pad(H.n2e_ptr); pad(H.n2e_item); pad(H.nsrc_ptr); pad(H.nsrc_item);
   ClusterDev &d = P->d;
   d.C = H.C; d.mc = H.mc; d.aux = H.aux ? 1 : 0;
   d.max_own = H.max_own; d.max_w = H.max_w; d.max_my = std::max(H.max_my, 1); d.max_slots = H.max_slots;
   d.max_vunits = H.max_vunits;
+  d.max_push = H.max_push;
   d.max_halo = H.max_halo; d.max_n2e = H.max_n2e; d.max_nsrc = H.max_nsrc;
   {
     // per-node lists as ELL (thread per node in the kernel, independent loads): own edges at a node, CTAs touching a node
@@ -816,6 +849,8 @@ static int cluster_plan_upload(System *S, ClusterPlanDev *P) {
   if ((rc = up(c, P, &d.slot_col, H.slot_col))) return rc;
   if ((rc = up(c, P, &d.halo_ws, H.halo_ws))) return rc;
   if ((rc = up(c, P, &d.halo_src, H.halo_src))) return rc;
+  if ((rc = up(c, P, &d.push_row, H.push_row))) return rc;
+  if ((rc = up(c, P, &d.push_dst, H.push_dst))) return rc;
   if ((rc = up(c, P, &d.node_id, H.node_id))) return rc;
   if ((rc = up(c, P, &d.n2e_ptr, H.n2e_ptr))) return rc;
   if ((rc = up(c, P, &d.n2e_item, H.n2e_item))) return rc;
@@ -1139,6 +1174,8 @@ int64_t efb_debug_cluster_plan_get(void *p, const char *name, int64_t *buf, int6
   else if (n == "slot_src") put(H.slot_src);
   else if (n == "slot_col") put(H.slot_col);
   else if (n == "halo_ws") put(H.halo_ws);
+  else if (n == "push_row") put(H.push_row);
+  else if (n == "push_dst") put(H.push_dst);
   else if (n == "halo_src") put(H.halo_src);
   else if (n == "node_id") put(H.node_id);
   else if (n == "n2e_ptr") put(H.n2e_ptr);

@@ -24,17 +24,19 @@
 namespace efb {
 
 constexpr int CL_MAX_C = 8;       // portable cluster size
-constexpr int CL_INFO_STRIDE = 16;
+constexpr int CL_INFO_STRIDE = 20;
 // cta_info[c][...]
 enum ClInfo {
   CI_N_OWN = 0, CI_LO = 1, CI_WLO = 2, CI_WN = 3, CI_N_MY = 4, CI_N_HALO = 5, CI_N_BLK = 6, CI_N_SLOTS = 7,
-  CI_OFF_ROW = 8, CI_OFF_SLOT = 9, CI_OFF_BLK = 10, CI_OFF_HALO = 11, CI_OFF_NODE = 12, CI_OFF_N2E = 13, CI_OFF_NSRC = 14
+  CI_OFF_ROW = 8, CI_OFF_SLOT = 9, CI_OFF_BLK = 10, CI_OFF_HALO = 11, CI_OFF_NODE = 12, CI_OFF_N2E = 13, CI_OFF_NSRC = 14,
+  CI_N_PUSH = 15, CI_OFF_PUSH = 16
 };
 
 struct ClusterPlanHost {
   int C = 0, mc = 0, m = 0;
   bool aux = false;
   int max_own = 0, max_w = 0, max_my = 0, max_slots = 0, max_halo = 0, max_n2e = 0, max_nsrc = 0;
+  int max_push = 0;    // most own rows (with multiplicity) a CTA sends into other CTAs' halos
   int max_vunits = 0;  // largest value image of a CTA in 8-byte units (real blocks 1 per slot, complex blocks 2)
   std::vector<int32_t> c_orig;     // [mc] position -> original edge id
   std::vector<int32_t> cta_info;   // [C][CL_INFO_STRIDE]
@@ -50,6 +52,10 @@ struct ClusterPlanHost {
   std::vector<uint16_t> slot_col;  // window slot of the slot's column
   std::vector<uint16_t> halo_ws;   // window slot of every halo entry, at CI_OFF_HALO
   std::vector<uint32_t> halo_src;  // owner CTA << 16 | owner local row
+  // the transpose of the halo lists: what a CTA SENDS (the iteration pushes z into the halo staging of the reader before the
+  // barrier instead of the reader pulling it over DSMEM after it), at CI_OFF_PUSH, CI_N_PUSH entries
+  std::vector<uint16_t> push_row;  // own local row
+  std::vector<uint32_t> push_dst;  // reader CTA << 16 | index of the entry in the reader's halo list
   std::vector<int32_t> node_id;    // [n_my] global node id, at CI_OFF_NODE
   std::vector<int32_t> n2e_ptr;    // [n_my+1] relative item offsets, at CI_OFF_NODE + c (one extra per CTA)
   std::vector<uint32_t> n2e_item;  // own local row << 1 | head, at CI_OFF_N2E
@@ -449,6 +455,27 @@ inline bool build_cluster_plan(int m, const int32_t *rowptr, const int32_t *coli
     P.max_slots = std::max(P.max_slots, Q.max_slots); P.max_halo = std::max(P.max_halo, Q.max_halo);
     P.max_vunits = std::max(P.max_vunits, Q.max_vunits);
     P.max_n2e = std::max(P.max_n2e, Q.max_n2e); P.max_nsrc = std::max(P.max_nsrc, Q.max_nsrc);
+  }
+  {  // push lists = halo lists transposed, ordered by (own row, reader)
+    std::vector<std::vector<std::pair<uint16_t, uint32_t>>> out(C);
+    for (int c = 0; c < C; ++c) {
+      const int32_t *I = &P.cta_info[(size_t)c * CL_INFO_STRIDE];
+      for (int h = 0; h < I[CI_N_HALO]; ++h) {
+        const uint32_t src = P.halo_src[(size_t)I[CI_OFF_HALO] + h];
+        out[src >> 16].push_back({(uint16_t)(src & 0xffffu), (uint32_t)c << 16 | (uint32_t)h});
+      }
+    }
+    for (int c = 0; c < C; ++c) {
+      std::sort(out[c].begin(), out[c].end());
+      int32_t *I = &P.cta_info[(size_t)c * CL_INFO_STRIDE];
+      I[CI_OFF_PUSH] = (int32_t)P.push_row.size();
+      I[CI_N_PUSH] = (int32_t)out[c].size();
+      for (auto &e : out[c]) {
+        P.push_row.push_back(e.first);
+        P.push_dst.push_back(e.second);
+      }
+      P.max_push = std::max(P.max_push, (int)out[c].size());
+    }
   }
   return true;
 }

@@ -13,7 +13,8 @@ import edgefem_oracle as orc
 from edgefem_b200 import cabi
 
 INFO = dict(N_OWN=0, LO=1, WLO=2, WN=3, N_MY=4, N_HALO=5, N_BLK=6, N_SLOTS=7, OFF_ROW=8, OFF_SLOT=9, OFF_BLK=10, OFF_HALO=11,
-            OFF_NODE=12, OFF_N2E=13, OFF_NSRC=14)
+            OFF_NODE=12, OFF_N2E=13, OFF_NSRC=14, N_PUSH=15, OFF_PUSH=16)
+STRIDE = 20
 
 
 class Emu:
@@ -23,7 +24,7 @@ class Emu:
         self.p, self.A, self.aux = plan, A_csr, aux
         d = plan["dims"]
         self.C = int(d[0])
-        self.info = plan["cta_info"].reshape(self.C, 16)
+        self.info = plan["cta_info"].reshape(self.C, STRIDE)
         self.vals = A_csr.data
         self.dinv, self.linv = dinv, linv
 
@@ -205,10 +206,24 @@ def test_cluster_plan_emulation_matches_direct_solve(wr90, C, mixed, aux):
     plan = cabi.cluster_plan_arrays(A.indptr, A.indices, pm.astype(np.uint8), mesh.xyz.shape[0] if aux else 0, en if aux else None, C, rc)
     d = plan["dims"]
     assert d[0] == C and d[1] == int((~pm).sum())
-    info = plan["cta_info"].reshape(C, 16)
+    info = plan["cta_info"].reshape(C, STRIDE)
     assert info[:, INFO["N_OWN"]].sum() == d[1]
     # every free edge is owned exactly once; windows contain their own rows
     assert sorted(plan["row_edge"].tolist()) == np.nonzero(~pm)[0].tolist()
+    # the push lists (what the owners send before the barrier) are exactly the halo lists (what the readers need) transposed
+    want = set()
+    for c in range(C):
+        o, n = int(info[c, INFO["OFF_HALO"]]), int(info[c, INFO["N_HALO"]])
+        for h in range(n):
+            src = int(plan["halo_src"][o + h])
+            want.add((src >> 16, src & 0xffff, c, h))
+    got = set()
+    for c in range(C):
+        o, n = int(info[c, INFO["OFF_PUSH"]]), int(info[c, INFO["N_PUSH"]])
+        for i in range(n):
+            dst = int(plan["push_dst"][o + i])
+            got.add((c, int(plan["push_row"][o + i]), dst >> 16, dst & 0xffff))
+    assert got == want and len(got) == int(info[:, INFO["N_PUSH"]].sum())
     b = np.asarray(bs[0]).astype(complex)
     xe, it = Emu(plan, A, dinv, linv, aux).solve(b, tol=1e-10, max_it=6000)
     xd = spla.splu(sp.csc_matrix(A)).solve(b)
@@ -225,7 +240,7 @@ def test_cluster_plan_band_and_footprint(wr90):
     pm = orc.pec_mask(mesh, pec)
     en, dinv, linv = precond_arrays(mesh, A, pm)
     plan = cabi.cluster_plan_arrays(A.indptr, A.indices, pm.astype(np.uint8), mesh.xyz.shape[0], en, 8)
-    info = plan["cta_info"].reshape(8, 16)
+    info = plan["cta_info"].reshape(8, STRIDE)
     own, wn = info[:, INFO["N_OWN"]], info[:, INFO["WN"]]
     assert own.max() <= 640 and (wn <= 2.2 * own).all()
     assert plan["dims"][9] <= 227 * 1024  # NR = 1
