@@ -957,7 +957,7 @@ int run_krylov_cluster(SolvePlan &P, const efb_solve_opts *o, bool zero_x, bool 
     return std::max(1, std::min(c->sm_count / C, per_gpc * gpcs) - (C >= 5 ? 1 : 0));
   };
   // relative cost of a job on C CTAs: half of the 8-CTA iteration is barriers and reductions (fixed), half scales with the rows per CTA
-  auto job_cost = [](int C) { return 0.5 + 0.5 * 8.0 / C; };
+  auto job_cost = [](int C) { return C >= 8 ? 1.0 : 0.5 + 0.75 * (8.0 / C - 1.0) + 0.5; };  // measured: 6 CTAs 1.22-1.25, 7 CTAs ~1.2 (two rounds of the same 15)
   const int n_jobs_all = n_matrix * n_rhs;
   auto batch_cost = [&](int C) { return std::ceil((double)n_jobs_all / resident_est(C)) * job_cost(C); };
   const int nn1 = want_aux ? S->n_node : 0;
@@ -968,7 +968,17 @@ int run_krylov_cluster(SolvePlan &P, const efb_solve_opts *o, bool zero_x, bool 
   // stay on the one-CTA kernel when it applies, small ones (one frequency, the shards of a strong-scaled sweep) run
   // here.  Systems the one-CTA kernel cannot take (p does not fit in its shared memory) always run here.  Decided
   // BEFORE the value scan and any plan build (first with the most favourable storage, all rows real).
-  const double rounds_1 = std::ceil((double)n_matrix / c->sm_count) * 10.0 * (n_rhs >= 2 ? 1.0 : 0.6);
+  // The one-CTA kernel in the same unit (one 8-CTA cluster job, 2.3 ms on WR-90): a two-rhs job is ~10; with up to half as
+  // many matrices as SMs every matrix is split into one-rhs jobs and the launch lasts ~6 (64 matrices: 13.9 ms), between
+  // sm_count / 2 and sm_count only the longest are split (128 matrices: 22.3 ms), beyond that it runs in rounds.
+  double rounds_1;
+  {
+    const double half = 0.5 * c->sm_count;
+    if (n_rhs < 2) rounds_1 = std::ceil((double)n_matrix / c->sm_count) * 6.0;
+    else if (n_matrix <= half) rounds_1 = 6.0;
+    else if (n_matrix <= c->sm_count) rounds_1 = 6.0 + 4.0 * (n_matrix - half) / half;
+    else rounds_1 = std::ceil((double)n_matrix / c->sm_count) * 10.0;
+  }
   auto candidates = [&](double cplx_frac) {
     std::vector<int> cs;
     if (forced > 0) {

@@ -1607,10 +1607,12 @@ static int run_cocg_small(SolvePlan &P, const efb_solve_opts *o, bool zero_x, bo
         n_jobs = (int)codes.size();
       }
     }
-    // Head split (one round: fewer matrices than SMs, e.g. the 128-point shard of a sweep over 2 GPUs): the launch lasts as
-    // long as its longest job while sm_count - n_jobs SMs idle.  The X = idle-SM-count matrices expected to take longest are
-    // queued as two one-rhs jobs each (cost ~0.8 of the two-rhs job): makespan max(0.8 * longest, (X+1)-th longest).
-    if (!mixed && nr == 2 && S->n_rhs == 2 && n_jobs <= c->sm_count && 2 * n_jobs > c->sm_count && variant < 4 && !no_split && (have_it || have_om)) {
+    // Head split (one round: fewer matrices than SMs, e.g. the 128- or 64-point shard of a sweep over 2 or 4 GPUs): the launch
+    // lasts as long as its longest job while sm_count - n_jobs SMs idle.  The X = idle-SM-count matrices expected to take
+    // longest are queued as two one-rhs jobs each; with no more than sm_count / 2 matrices every one is split.  A one-rhs job
+    // running next to idle SMs costs ~0.5 of the two-rhs job (measured: 64 matrices 13.9 ms all split, 128 matrices 22.3 ms
+    // with 20 split, 26 ms unsplit).
+    if (!mixed && nr == 2 && S->n_rhs == 2 && n_jobs <= c->sm_count && variant < 4 && !no_split && (have_it || have_om)) {
       const int X = std::min(c->sm_count - n_jobs, n_jobs);
       if (X > 0) {
         mixed = 1;
