@@ -1063,6 +1063,8 @@ int run_krylov_cluster(SolvePlan &P, const efb_solve_opts *o, bool zero_x, bool 
       if (rc) return rc;
       plan_cache_put(c->device, hsh, S->m, (long long)S->nnz, C, want_aux, sp);
       st.mark("  cluster plan (RCM, partition, windows, lists)");
+      if (st.on)
+        for (auto &tm : sp->h.timing) fprintf(stderr, "[edgefem-b200 trace]     .     plan: %-32s %.3f ms\n", tm.first, tm.second);
     }
     if (!sp) return EFB_OK;  // does not fit: the other solver paths take it
     S->cl_plan = new std::shared_ptr<ClusterPlanDev>(sp);

@@ -15,6 +15,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <chrono>
 #include <numeric>
 #include <queue>
 #include <string>
@@ -62,6 +63,7 @@ struct ClusterPlanHost {
   std::vector<int32_t> nsrc_ptr;   // [n_my+1] relative, same placement as n2e_ptr
   std::vector<uint32_t> nsrc_item; // CTA << 16 | that CTA's my-node slot (ascending CTA, self included), at CI_OFF_NSRC
   std::string error;
+  std::vector<std::pair<const char *, double>> timing;  // host milliseconds per build stage (EDGEFEM_B200_TRACE=2 prints them)
 };
 
 // reverse Cuthill-McKee over a symmetric pattern given as CSR adjacency without self loops
@@ -102,9 +104,10 @@ inline std::vector<int32_t> rcm_order(int n, const std::vector<int32_t> &ptr, co
   std::vector<int32_t> nb;
   for (int s0 : by_deg) {
     if (seen[s0]) continue;
-    // pseudo-peripheral start node: a few sweeps of "go to the farthest node"
+    // pseudo-peripheral start node: two sweeps of "go to the farthest node" (more sweeps rarely move it and each costs a
+    // full BFS of host time on the solve path)
     int start = s0, ecc = -1;
-    for (int it = 0; it < 4; ++it) {
+    for (int it = 0; it < 2; ++it) {
       auto fr = bfs_far(start, mark);
       if (fr.second <= ecc) break;
       ecc = fr.second;
@@ -137,6 +140,12 @@ inline std::vector<int32_t> rcm_order(int n, const std::vector<int32_t> &ptr, co
 inline bool build_cluster_plan(int m, const int32_t *rowptr, const int32_t *colidx, const uint8_t *dir, int n_node, const int32_t *edge_nodes,
                                int C, ClusterPlanHost &P, const uint8_t *row_complex = nullptr) {
   P = ClusterPlanHost();
+  auto t_last = std::chrono::steady_clock::now();
+  auto stage = [&](const char *name) {
+    const auto t = std::chrono::steady_clock::now();
+    P.timing.push_back({name, std::chrono::duration<double, std::milli>(t - t_last).count()});
+    t_last = t;
+  };
   P.C = C;
   P.m = m;
   P.aux = edge_nodes != nullptr && n_node > 0;
@@ -169,7 +178,9 @@ inline bool build_cluster_plan(int m, const int32_t *rowptr, const int32_t *coli
     }
     aptr[i + 1] = (int32_t)adj.size();
   }
+  stage("adjacency");
   const std::vector<int32_t> rcm = rcm_order(mc, aptr, adj);  // position -> compact0 id
+  stage("RCM order");
   std::vector<int32_t> pos_of((size_t)mc);
   P.c_orig.resize(mc);
   for (int p = 0; p < mc; ++p) {
@@ -196,6 +207,7 @@ inline bool build_cluster_plan(int m, const int32_t *rowptr, const int32_t *coli
       ++at;
     }
   }
+  stage("rows in position order");
   // contiguous partition balanced by (entries + 8) per row
   std::vector<int32_t> lo(C + 1, mc);
   {
@@ -252,6 +264,7 @@ inline bool build_cluster_plan(int m, const int32_t *rowptr, const int32_t *coli
     for (int c = 0; c < C; ++c)
       for (size_t s = 0; s < my_nodes[c].size(); ++s) touch[my_nodes[c][s]].push_back((uint32_t)c << 16 | (uint32_t)s);
   }
+  stage("partition, nodes, touch lists");
   std::vector<ClusterPlanHost> parts(C);
   auto build_cta = [&](int c) {
     ClusterPlanHost &Q = parts[c];
@@ -430,6 +443,7 @@ inline bool build_cluster_plan(int m, const int32_t *rowptr, const int32_t *coli
   } else {
     build_cta(0);
   }
+  stage("per-CTA lists (one thread each)");
   P.cta_info.assign((size_t)C * CL_INFO_STRIDE, 0);
   auto app = [](auto &dst, const auto &src) { dst.insert(dst.end(), src.begin(), src.end()); };
   for (int c = 0; c < C; ++c) {
@@ -477,6 +491,7 @@ inline bool build_cluster_plan(int m, const int32_t *rowptr, const int32_t *coli
       P.max_push = std::max(P.max_push, (int)out[c].size());
     }
   }
+  stage("merge + push lists");
   return true;
 }
 
