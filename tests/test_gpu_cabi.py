@@ -118,10 +118,10 @@ def test_cluster_solver_two_rows_per_thread(ctx, wr90, kat, monkeypatch):
     assert np.max(np.abs(S[0] - S_ref)) <= 1e-6
 
 
-@pytest.mark.parametrize("n_freq", [80, 160])
+@pytest.mark.parametrize("n_freq", [40, 80, 160])
 def test_wr90_sweep_one_cta_queue_shapes(ctx, wr90, n_freq, monkeypatch):
-    """Job queue shapes of the one-CTA persistent solver: 80 matrices (fewer than SMs: the longest are split into two one-rhs
-    jobs) and 160 (more than SMs: two rounds from the longest-first queue).  Every right-hand side converges; sampled S match
+    """Job queue shapes of the one-CTA persistent solver: 40 matrices (at most half the SMs: every matrix is split into two
+    one-rhs jobs), 80 (fewer than SMs: the longest are split) and 160 (more than SMs: two rounds from the longest-first queue).  Every right-hand side converges; sampled S match
     the oracle within 1e-6."""
     mesh, pec = wr90
     monkeypatch.setenv("EDGEFEM_B200_CLUSTER", "0")
