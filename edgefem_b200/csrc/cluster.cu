@@ -969,14 +969,14 @@ int run_krylov_cluster(SolvePlan &P, const efb_solve_opts *o, bool zero_x, bool 
   // here.  Systems the one-CTA kernel cannot take (p does not fit in its shared memory) always run here.  Decided
   // BEFORE the value scan and any plan build (first with the most favourable storage, all rows real).
   // The one-CTA kernel in the same unit (one 8-CTA cluster job, 2.3 ms on WR-90): a two-rhs job is ~10; with up to half as
-  // many matrices as SMs every matrix is split into one-rhs jobs and the launch lasts ~6 (64 matrices: 13.9 ms), between
+  // many matrices as SMs every matrix is split into one-rhs jobs and the launch lasts ~5.4 (64 matrices: 12.5 ms), between
   // sm_count / 2 and sm_count only the longest are split (128 matrices: 22.3 ms), beyond that it runs in rounds.
   double rounds_1;
   {
     const double half = 0.5 * c->sm_count;
-    if (n_rhs < 2) rounds_1 = std::ceil((double)n_matrix / c->sm_count) * 6.0;
-    else if (n_matrix <= half) rounds_1 = 6.0;
-    else if (n_matrix <= c->sm_count) rounds_1 = 6.0 + 4.0 * (n_matrix - half) / half;
+    if (n_rhs < 2) rounds_1 = std::ceil((double)n_matrix / c->sm_count) * 5.4;
+    else if (n_matrix <= half) rounds_1 = 5.4;  // resident one-rhs jobs: 12.5 ms
+    else if (n_matrix <= c->sm_count) rounds_1 = 7.8 + 2.2 * (n_matrix - half) / half;  // 80 matrices 18.1 ms ... 128: 22.3 ms
     else rounds_1 = std::ceil((double)n_matrix / c->sm_count) * 10.0;
   }
   auto candidates = [&](double cplx_frac) {

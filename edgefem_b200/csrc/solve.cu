@@ -728,16 +728,21 @@ static size_t small_lists_bytes(int mc, int nn) { return ((size_t)mc + (nn ? (si
 
 // One job of the persistent solver: matrix f, the NR right-hand sides starting at system s0, solved to convergence by
 // the whole CTA (see k_cocg_small below).
-template <int NR, int SPD, bool DB>
+template <int NR, int SPD, bool DB, bool RES = false>
 __device__ __forceinline__ void cocg_small_job(const SolveDev &D, const int32_t *__restrict__ sell_ptr, const int32_t *__restrict__ sell_col,
                                                const int32_t *__restrict__ sell_perm, const c128 *__restrict__ sell_vals, long long sell_total,
                                                int n_slices, const c128 *__restrict__ bvec, c128 *xvec, c128 *rvec, c128 *qvec, int aux, int zero_x,
                                                int max_restarts, int mc, const SmallLists &L,
                                                const int2 *__restrict__ c_edge_nodes, unsigned char *sm_raw, int f, int s0) {
   const int m = D.m, nn = aux ? D.n_node : 0;
+  // RES (one right-hand side): r and q live in shared memory next to p and w -- the vector passes and the nodal gather of
+  // the preconditioner then never leave the SM (x, 1/diag and the matrix stream are what is left of the L2 traffic)
+  static_assert(!RES || NR == 1, "resident r, q: one right-hand side per job");
   c128 *p_s = (c128 *)sm_raw;                 // [NR][mc]
   c128 *w_s = p_s + (size_t)NR * mc;          // [NR][nn]
-  double *red = (double *)(w_s + (size_t)NR * nn);  // [33*8]
+  c128 *r_s = w_s + (size_t)NR * nn;          // RES: [mc]
+  c128 *q_s = r_s + (RES ? mc : 0);           // RES: [mc]
+  double *red = (double *)(q_s + (RES ? mc : 0));  // [33*8]
   const int tid = threadIdx.x, nth = blockDim.x;
   const int lane = tid & 31, wid = tid >> 5, nwarp = nth >> 5;
   const c128 *__restrict__ av = D.vals + (size_t)f * D.nnz;
@@ -750,14 +755,14 @@ __device__ __forceinline__ void cocg_small_job(const SolveDev &D, const int32_t 
     __device__ __forceinline__ c128 *operator[](int r) const { return base + (size_t)r * m; }
   };
   const size_t off0 = (size_t)s0 * m;
-  const VRef xg{xvec + off0, m}, qg{qvec + off0, m}, bg{const_cast<c128 *>(bvec) + off0, m};
+  const VRef xg{xvec + off0, m}, qg{RES ? q_s : qvec + off0, m}, bg{const_cast<c128 *>(bvec) + off0, m};
   // r is interleaved by right-hand side, r[i][NR]: the nodal gather of the preconditioner reads it at random, and the NR values of
   // an edge then share one 32-byte sector instead of wasting half of NR sectors
   struct RRef {
     c128 *base;
     __device__ __forceinline__ c128 &operator()(int r, int i) const { return base[(size_t)i * NR + r]; }
   };
-  const RRef rg{rvec + off0};
+  const RRef rg{RES ? r_s : rvec + off0};
   // block-uniform scalars live in shared memory (written by thread 0 between barriers): bb, rr and a
   // double-buffered rho per right-hand side
   double *sc_bb = red + 33 * 8, *sc_rr = sc_bb + NR, *sc_rho = sc_rr + NR;  // sc_rho[parity][r][2]
@@ -1017,7 +1022,7 @@ __device__ __forceinline__ void cocg_small_job(const SolveDev &D, const int32_t 
 #pragma unroll
               for (int r = 0; r < NR; ++r) v[u][r] = cmake(0.0, 0.0);
               if (it[u] >= 0) {
-                if constexpr (NR == 2) {
+                if constexpr (NR == 2 && !RES) {
                   ldg256(&rg(0, it[u] >> 1), v[u][0], v[u][NR - 1]);
                 } else {
 #pragma unroll
@@ -1143,7 +1148,7 @@ __device__ __forceinline__ void cocg_small_job(const SolveDev &D, const int32_t 
   __syncthreads();
 }
 
-template <int NR, int NT, int SPD, bool DB, int MINB = 1>
+template <int NR, int NT, int SPD, bool DB, int MINB = 1, bool RES = false>
 __global__ void __launch_bounds__(NT, MINB)
 k_cocg_small(SolveDev D, const int32_t *__restrict__ sell_ptr, const int32_t *__restrict__ sell_col, const int32_t *__restrict__ sell_perm,
              const c128 *__restrict__ sell_vals, long long sell_total, int n_slices, int first_matrix, int n_jobs, int groups_per_matrix, int mixed,
@@ -1192,7 +1197,7 @@ k_cocg_small(SolveDev D, const int32_t *__restrict__ sell_ptr, const int32_t *__
                                    max_restarts, mc, L, c_edge_nodes, sm_raw, f, f * D.n_rhs + kind - 1);
     } else {
       const int f = first_matrix + job / groups_per_matrix;
-      cocg_small_job<NR, SPD, DB>(D, sell_ptr, sell_col, sell_perm, sell_vals, sell_total, n_slices, bvec, xvec, rvec, qvec, aux, zero_x,
+      cocg_small_job<NR, SPD, DB, RES>(D, sell_ptr, sell_col, sell_perm, sell_vals, sell_total, n_slices, bvec, xvec, rvec, qvec, aux, zero_x,
                                   max_restarts, mc, L, c_edge_nodes, sm_raw, f,
                                   f * D.n_rhs + (job % groups_per_matrix) * NR);
     }
@@ -1213,6 +1218,7 @@ __global__ void k_csr_to_sell(const c128 *__restrict__ vals, long long nnz, cons
   }
 }
 
+static size_t small_smem_bytes_res(int m, int nn) { return ((size_t)3 * m + (size_t)nn) * sizeof(c128) + (33 * 8 + 8) * sizeof(double) + 64; }
 static size_t small_smem_bytes(int nr, int m, int nn) { return ((size_t)nr * m + (size_t)nr * nn) * sizeof(c128) + (33 * 8 + 8 * nr) * sizeof(double) + 64; }
 
 // FP64 FMA throughput probe (roofline denominator for the assembly kernel; MEASURED_PEAKS.json has
@@ -1491,7 +1497,14 @@ static int run_cocg_small(SolvePlan &P, const efb_solve_opts *o, bool zero_x, bo
   int nr = (S->n_rhs % 2 == 0) ? 2 : 1;
   if (small_smem_bytes(nr, mc, nn) > (size_t)dev_smem) nr = 1;
   if (variant >= 4) nr = 1;  // one right-hand side per CTA, two CTAs per SM
-  size_t smem = small_smem_bytes(nr, mc, nn);
+  // Resident mode: one right-hand side per job with r and q in shared memory too (WR-90: 32 us per iteration against 35 us
+  // with r, q in L2 -- the matrix stream, not shared with a second right-hand side, is half of it).  Used when every
+  // right-hand side gets its own SM anyway (the all-split case of the head split below: 64 matrices 13.9 -> 12.5 ms); with
+  // more work than SMs the two-rhs jobs are cheaper per right-hand side (256 matrices: 39.5 against 46.1 ms).
+  const bool res_mode = variant < 4 && !getenv("EDGEFEM_B200_NO_RESIDENT") && small_smem_bytes_res(mc, nn) <= (size_t)dev_smem &&
+                        (long long)P.n_matrix * S->n_rhs <= c->sm_count;
+  if (res_mode) nr = 1;
+  size_t smem = res_mode ? small_smem_bytes_res(mc, nn) : small_smem_bytes(nr, mc, nn);
   if (smem > (size_t)dev_smem || !S->d_sell_ptr) return EFB_OK;  // system too large for one CTA: generic multi-kernel path
   long long *d_prof = nullptr;
   static const bool prof_on = getenv("EDGEFEM_B200_SMALL_PROF") != nullptr;
@@ -1656,7 +1669,13 @@ static int run_cocg_small(SolvePlan &P, const efb_solve_opts *o, bool zero_x, bo
                                                                       S->d_b, S->d_x, P.vec[V_R], P.vec[V_Q], P.aux ? 1 : 0, zero_x ? 1 : 0, mr, \
                                                                       mc, S->d_c_orig, S->d_c_edge_nodes, S->d_c_n2e_ptr, S->d_c_n2e_item, stage_off, d_prof); \
   } while (0)
-  if (nr == 2) {
+  if (res_mode) {
+    auto kern = k_cocg_small<1, 1024, 4, false, 1, true>;
+    EFB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 1024, smem, c->stream>>>(P.D, S->d_sell_ptr, S->d_sell_col, S->d_sell_perm, S->d_sell_vals, S->sell_total, S->n_slices, P.first_matrix,
+                                          n_jobs, groups, mixed, S->d_job, S->d_b, S->d_x, P.vec[V_R], P.vec[V_Q], P.aux ? 1 : 0, zero_x ? 1 : 0, mr, mc,
+                                          S->d_c_orig, S->d_c_edge_nodes, S->d_c_n2e_ptr, S->d_c_n2e_item, stage_off, d_prof);
+  } else if (nr == 2) {
     switch (variant) {
       case 0: EFB_SMALL_LAUNCH(2, 512, 8, true); break;
       case 2: EFB_SMALL_LAUNCH(2, 1024, 0, false); break;
