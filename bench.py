@@ -526,7 +526,7 @@ def run_b200(a):
             note = ("byte model of the same iteration streamed from memory; this kernel keeps matrix, vectors and index lists on chip (shared memory + "
                     "registers), so HBM sees only the per-job matrix load and b/x: it is bound by shared-memory wavefronts and cluster barriers, not HBM")
         else:
-            kname, kkey = ("k_cocg_small<2> (persistent COCG + aux-space Jacobi, SELL-32 SpMV from smem-resident p; %d matrices x %d rhs in one launch)" % (F, P)), "k_cocg_small"
+            kname, kkey = ("k_cocg_small (persistent COCG + aux-space Jacobi, one CTA per job, SELL-32 SpMV from smem-resident p; %d matrices x %d rhs in one launch; two-rhs jobs, or one-rhs jobs with r, q resident when every system gets its own SM)" % (F, P)), "k_cocg_small"
             solve_bytes = float(sum(it_per_matrix)) * (nnz_f * 20.0 + 4.0 * m_f + P * 192.0 * m_f)
             note = ("byte model over the %d free unknowns / %d free entries the kernel iterates on (Dirichlet rows and columns are dropped); vectors r,q,x stay "
                     "L2-resident per CTA and p lives in shared memory, so part of the algorithmic bytes never reaches HBM (see traffic)" % (m_f, nnz_f))
