@@ -243,7 +243,9 @@ k_cocg_cluster(const SolveDev D, const ClusterDev K, int first_matrix, int n_job
   for (int i = tid; i < K.sdeg * K.max_my; i += nth) nsrc_ell_s[i] = K.nsrc_ell[(size_t)crank * K.sdeg * K.max_my + i];
   for (int i = tid; i < 2 * CL_MAX_C * 8; i += nth) part[i] = 0.0;  // banks of absent ranks (C < 8) stay zero
   if (tid < 24) prof_s[tid] = 0;
-  __syncthreads();
+  // every CTA of the cluster has started (and set up its lists) before anyone touches a neighbour's shared memory: the first
+  // remote access is the job id that rank 0 writes below (compute-sanitizer racecheck flags it without this barrier)
+  cluster.sync();
   long long t_last = 0;
   const bool prof_on = K.prof != nullptr && tid == 0;
   if (prof_on) t_last = clock64();
