@@ -265,3 +265,60 @@ def test_cluster_plan_tiny_and_no_dirichlet():
     b = np.arange(1, n + 1).astype(complex)
     x, it = Emu(plan, A, 1.0 / A.diagonal(), np.zeros(0), False).solve(b, tol=1e-12, max_it=50)
     assert np.allclose(A @ x, b, atol=1e-10)
+
+
+@pytest.mark.parametrize("C", [2, 5, 7])
+def test_cluster_plan_structure_on_a_layered_unit_cell(C):
+    """Structural invariants of the plan on another mesh (layered unit cell, PEC ground + patch, lossy substrate so that most
+    rows are complex): every free edge owned once, windows cover the rows' columns, every own edge appears at both of its
+    end nodes, halo and push lists are each other's transpose, value offsets follow the block kinds."""
+    from edgefem_b200 import meshgen
+
+    xyz, tets, tp, tris, trp = meshgen.unit_cell(px=5e-3, py=5e-3, h_sub=0.5e-3, h_air=6e-3, nx=5, ny=5, nz_sub=2, nz_air=4, patch=(3e-3, 3e-3))
+    mesh = orc.mesh_from_arrays(xyz, tets, tp, tris, trp)
+    pec = orc.build_edge_pec(mesh, 1) | orc.build_edge_pec(mesh, 2)
+    p = orc.MaxwellParams(omega=2 * math.pi * 10e9, eps_r_regions={100: complex(3.5, -0.1), 101: complex(1.0, 0.0)})
+    A = sp.csr_matrix(orc.assemble_maxwell(mesh, p, pec, [])[0])
+    A.sort_indices()
+    pm = orc.pec_mask(mesh, pec)
+    en = mesh.node_idx_of(mesh.edges).astype(np.int32)
+    rc = complex_rows(A)
+    assert 0 < int(rc[~pm].sum()) < int((~pm).sum())  # substrate rows complex, air rows real
+    plan = cabi.cluster_plan_arrays(A.indptr, A.indices, pm.astype(np.uint8), mesh.xyz.shape[0], en, C, rc)
+    info = plan["cta_info"].reshape(C, STRIDE)
+    free = np.nonzero(~pm)[0]
+    assert sorted(plan["row_edge"].tolist()) == free.tolist()
+    c_orig = plan["c_orig"]
+    pos_of = {int(e): i for i, e in enumerate(c_orig)}
+    seen_push, seen_halo = set(), set()
+    for c in range(C):
+        I = {k: int(info[c, v]) for k, v in INFO.items()}
+        rows = plan["row_edge"][I["OFF_ROW"]:I["OFF_ROW"] + I["N_OWN"]]
+        ws = plan["row_ws"][I["OFF_ROW"]:I["OFF_ROW"] + I["N_OWN"]]
+        # the window slot of an own row is its position minus the window start
+        assert all(pos_of[int(e)] - I["WLO"] == int(w) for e, w in zip(rows, ws))
+        # blocks: slots of row t sit at lane t % 32 of block t // 32; their columns are window slots of the row's free columns
+        for t, e in enumerate(rows):
+            b, l = divmod(t, 32)
+            o0, o1 = int(plan["blk_off"][I["OFF_BLK"] + b]), int(plan["blk_off"][I["OFF_BLK"] + b + 1])
+            src = plan["slot_src"][I["OFF_SLOT"] + o0 + l:I["OFF_SLOT"] + o1:32]
+            col = plan["slot_col"][I["OFF_SLOT"] + o0 + l:I["OFF_SLOT"] + o1:32]
+            used = src >= 0
+            want_cols = [j for j in A.indices[A.indptr[e]:A.indptr[e + 1]] if not pm[j]]
+            assert sorted(int(c_orig[I["WLO"] + int(w)]) for w in col[used]) == sorted(int(j) for j in want_cols)
+            assert sorted(int(A.indices[k]) for k in src[used]) == sorted(int(j) for j in want_cols)
+            v0, v1 = int(plan["blk_voff"][I["OFF_BLK"] + b]), int(plan["blk_voff"][I["OFF_BLK"] + b + 1])
+            if rc[e]:
+                assert v1 - v0 == 2 * (o1 - o0)  # a complex row lives in a complex block
+        # nodal lists: every own row appears once as tail (bit 0 clear) and once as head (bit 0 set)
+        n_my = I["N_MY"]
+        ptr = plan["n2e_ptr"][I["OFF_NODE"] + c:I["OFF_NODE"] + c + n_my + 1]
+        items = plan["n2e_item"][I["OFF_N2E"]:I["OFF_N2E"] + int(ptr[-1])]
+        assert sorted(items.tolist()) == sorted([2 * t for t in range(I["N_OWN"])] + [2 * t + 1 for t in range(I["N_OWN"])])
+        for h in range(I["N_HALO"]):
+            src = int(plan["halo_src"][I["OFF_HALO"] + h])
+            seen_halo.add((src >> 16, src & 0xffff, c, h))
+        for i in range(I["N_PUSH"]):
+            dst = int(plan["push_dst"][I["OFF_PUSH"] + i])
+            seen_push.add((c, int(plan["push_row"][I["OFF_PUSH"] + i]), dst >> 16, dst & 0xffff))
+    assert seen_push == seen_halo
