@@ -74,6 +74,7 @@ SIGNATURES = {
     "efb_ctx_destroy": (None, [C.c_void_p]),
     "efb_last_error": (C.c_char_p, [C.c_void_p]),
     "efb_ctx_sync": (C.c_int, [C.c_void_p]),
+    "efb_l2_flush": (C.c_int, [C.c_void_p]),
     "efb_last_kernel_ms": (C.c_double, [C.c_void_p]),
     "efb_launch_count": (C.c_int64, [C.c_void_p]),
     "efb_timer_start": (C.c_int, [C.c_void_p]),
@@ -254,6 +255,10 @@ class Ctx:
 
     def sync(self):
         self.check(self.lib.efb_ctx_sync(self.h), "efb_ctx_sync")
+
+    def l2_flush(self):
+        """Overwrite a 256 MB scratch buffer on the context's stream (evicts L2; measurement helper)."""
+        self.check(self.lib.efb_l2_flush(self.h), "efb_l2_flush")
 
     def last_kernel_ms(self) -> float:
         return float(self.lib.efb_last_kernel_ms(self.h))

@@ -253,12 +253,25 @@ void efb_ctx_destroy(efb_ctx *ctx_) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   efb_dist_finalize(ctx_);
   pool_trim();
+  if (c->d_flush) cudaFree(c->d_flush);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->tm0) cudaEventDestroy(c->tm0);
   if (c->tm1) cudaEventDestroy(c->tm1);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
+}
+
+// Measurement helper: overwrite a 256 MB scratch buffer on the context's stream, i.e. evict the 126 MB L2 (used by bench.py
+// between timed steps whose working set would otherwise stay L2-resident from one step to the next).
+int efb_l2_flush(efb_ctx *ctx_) {
+  Ctx *c = (Ctx *)ctx_;
+  if (!c) return EFB_ERR_INVALID;
+  constexpr size_t FLUSH_BYTES = (size_t)256 << 20;
+  EFB_CUDA(c, cudaSetDevice(c->device));
+  if (!c->d_flush) EFB_CUDA(c, cudaMalloc(&c->d_flush, FLUSH_BYTES));
+  EFB_CUDA(c, cudaMemsetAsync(c->d_flush, 0x5a, FLUSH_BYTES, c->stream));
+  return EFB_OK;
 }
 
 int efb_ctx_sync(efb_ctx *ctx_) {

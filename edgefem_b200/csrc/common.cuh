@@ -100,6 +100,7 @@ struct Ctx {
   int sm_count = 148;
   std::string err;
   void *dist = nullptr;  // efb::Dist (rank, world, NCCL communicator) once efb_dist_init ran
+  void *d_flush = nullptr;  // 256 MB scratch written by efb_l2_flush
 };
 
 struct Mesh {

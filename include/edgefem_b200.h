@@ -50,6 +50,8 @@ int efb_ctx_create(int device, efb_ctx **out);
 void efb_ctx_destroy(efb_ctx *ctx);
 const char *efb_last_error(const efb_ctx *ctx); /* ctx may be NULL: last global error */
 int efb_ctx_sync(efb_ctx *ctx);
+/* measurement helper: overwrite a 256 MB scratch buffer on the context's stream (evicts the 126 MB L2 between timed steps) */
+int efb_l2_flush(efb_ctx *ctx);
 /* time of the most recent efb_* compute call's kernels, ms (CUDA events on the ctx stream) */
 double efb_last_kernel_ms(const efb_ctx *ctx);
 /* number of kernels this ctx has launched since creation */
