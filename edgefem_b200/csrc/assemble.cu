@@ -1081,9 +1081,15 @@ __global__ void k_rhs_weights(c128 *b, const int32_t *__restrict__ edges, const 
 
 __global__ void k_rhs_mass(c128 *b, const int32_t *__restrict__ rows, const int32_t *__restrict__ cols,
                            const double *__restrict__ mv, long long n, const c128 *__restrict__ e_dense, c128 coef) {
+  // the entries are sorted by (row, column) (efb_port_create): the first entry of a row sums the row in order and is the only
+  // writer of b[row] in this launch -- a fixed summation order instead of fp64 atomics, so b is bit-reproducible
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n) return;
-  atomic_cadd(&b[rows[i]], cmul(coef, cscale(mv[i], e_dense[cols[i]])));
+  const int r = rows[i];
+  if (i > 0 && rows[i - 1] == r) return;
+  c128 acc = cmake(0.0, 0.0);
+  for (long long k = i; k < n && rows[k] == r; ++k) acc = cadd(acc, cscale(mv[k], e_dense[cols[k]]));
+  b[r] = cadd(b[r], cmul(coef, acc));
 }
 
 // single-CTA deterministic reductions (ports have O(100) edges)
@@ -1160,7 +1166,12 @@ __global__ void k_rhs_mass_batch(c128 *b, int m, const int32_t *__restrict__ rhs
                                  long long n, const c128 *__restrict__ e_dense) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n) return;
-  atomic_cadd(&b[(size_t)rhs_idx[blockIdx.y] * m + rows[i]], cmul(coef[blockIdx.y], cscale(mv[i], e_dense[cols[i]])));
+  const int r = rows[i];
+  if (i > 0 && rows[i - 1] == r) return;  // see k_rhs_mass
+  c128 acc = cmake(0.0, 0.0);
+  for (long long k = i; k < n && rows[k] == r; ++k) acc = cadd(acc, cscale(mv[k], e_dense[cols[k]]));
+  c128 *dst = &b[(size_t)rhs_idx[blockIdx.y] * m + r];
+  *dst = cadd(*dst, cmul(coef[blockIdx.y], acc));
 }
 
 // one CTA per right-hand side: V = sum conj(w) x (weights) or e^H M_s x (mass)
@@ -1323,9 +1334,25 @@ int efb_port_create(efb_system *sys_, int32_t n_edges, const int32_t *edges, con
   int rc;
   if ((rc = dev_upload(c, &P->d_edges, edges, (size_t)n_edges))) return rc;
   if ((rc = dev_upload(c, &P->d_w, (const c128 *)weights, (size_t)n_edges))) return rc;
-  if ((rc = dev_upload(c, &P->d_ms_row, ms_rows, (size_t)n_ms))) return rc;
-  if ((rc = dev_upload(c, &P->d_ms_col, ms_cols, (size_t)n_ms))) return rc;
-  if ((rc = dev_upload(c, &P->d_ms_val, ms_vals, (size_t)n_ms))) return rc;
+  {
+    // entries sorted by (row, column): the right-hand-side kernels sum a row in this order (k_rhs_mass)
+    std::vector<int64_t> ord((size_t)n_ms);
+    for (int64_t i = 0; i < n_ms; ++i) ord[i] = i;
+    std::stable_sort(ord.begin(), ord.end(), [&](int64_t a, int64_t b2) {
+      return ms_rows[a] != ms_rows[b2] ? ms_rows[a] < ms_rows[b2] : ms_cols[a] < ms_cols[b2];
+    });
+    std::vector<int32_t> sr((size_t)n_ms), sc((size_t)n_ms);
+    std::vector<double> sv((size_t)n_ms);
+    for (int64_t i = 0; i < n_ms; ++i) {
+      sr[i] = ms_rows[ord[i]];
+      sc[i] = ms_cols[ord[i]];
+      sv[i] = ms_vals[ord[i]];
+    }
+    if ((rc = dev_upload(c, &P->d_ms_row, sr.data(), (size_t)n_ms))) return rc;
+    if ((rc = dev_upload(c, &P->d_ms_col, sc.data(), (size_t)n_ms))) return rc;
+    if ((rc = dev_upload(c, &P->d_ms_val, sv.data(), (size_t)n_ms))) return rc;
+    EFB_CUDA(c, cudaStreamSynchronize(c->stream));  // the uploads read the temporaries
+  }
   if ((rc = dev_alloc(c, &P->d_ms_pos, (size_t)n_ms))) return rc;
   if ((rc = dev_alloc(c, &P->d_e, (size_t)S->m))) return rc;
   if ((rc = dev_alloc(c, &P->d_tmp, (size_t)4))) return rc;

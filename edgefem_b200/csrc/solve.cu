@@ -422,27 +422,31 @@ __global__ void k_dinv(SolveDev D, int first_matrix, const int32_t *__restrict__
   }
 }
 
-// nodal diagonal of G^T A G (G = discrete gradient, -1 at the tail node, +1 at the head node)
+// nodal diagonal of G^T A G (G = discrete gradient, -1 at the tail node, +1 at the head node): L[n] = sum over the free edges
+// e, e2 at node n of G[e][n] A[e][e2] G[e2][n].  One thread per node walks its incident edges (list order) and their rows
+// (column order): a fixed summation order, so the preconditioner -- and with it every iterate -- is bit-reproducible from
+// run to run (the first version scattered per-edge partial sums with fp64 atomics).
 __global__ void k_nodal_diag(SolveDev D, int first_matrix) {
   const int f = first_matrix + blockIdx.y;
   c128 *L = D.linv + (size_t)f * D.n_node;
   const c128 *__restrict__ av = D.vals + (size_t)f * D.nnz;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < D.m; e += gridDim.x * blockDim.x) {
-    if (D.dir[e]) continue;
-    const int2 ab = D.edge_nodes[e];
-    c128 la = cmake(0.0, 0.0), lb = cmake(0.0, 0.0);
-    for (int k = D.rowptr[e]; k < D.rowptr[e + 1]; ++k) {
-      const int e2 = D.colidx[k];
-      if (D.dir[e2]) continue;
-      const int2 cd = D.edge_nodes[e2];
-      const c128 a = av[k];
-      if (ab.x == cd.x) la = cadd(la, a);
-      if (ab.x == cd.y) la = csub(la, a);
-      if (ab.y == cd.y) lb = cadd(lb, a);
-      if (ab.y == cd.x) lb = csub(lb, a);
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < D.n_node; n += gridDim.x * blockDim.x) {
+    c128 acc = cmake(0.0, 0.0);
+    for (int q = D.n2e_ptr[n]; q < D.n2e_ptr[n + 1]; ++q) {
+      const int it = D.n2e_item[q];
+      if (it & 2) continue;  // Dirichlet edge
+      const int e = it >> 2;
+      c128 row = cmake(0.0, 0.0);
+      for (int k = D.rowptr[e]; k < D.rowptr[e + 1]; ++k) {
+        const int e2 = D.colidx[k];
+        if (D.dir[e2]) continue;
+        const int2 cd = D.edge_nodes[e2];
+        if (cd.y == n) row = cadd(row, av[k]);
+        else if (cd.x == n) row = csub(row, av[k]);
+      }
+      acc = (it & 1) ? cadd(acc, row) : csub(acc, row);
     }
-    atomicAdd(&L[ab.x].x, la.x); atomicAdd(&L[ab.x].y, la.y);
-    atomicAdd(&L[ab.y].x, lb.x); atomicAdd(&L[ab.y].y, lb.y);
+    L[n] = acc;
   }
 }
 
@@ -1392,10 +1396,9 @@ static int setup_precond(SolvePlan &P) {
   k_dinv<<<g, VEC_THREADS, 0, c->stream>>>(P.D, P.first_matrix, S->d_diag_pos, P.precond != EFB_PRECOND_NONE);
   EFB_CHECK_LAUNCH(c);
   if (P.aux) {
-    EFB_CUDA(c, cudaMemsetAsync(S->d_linv + (size_t)P.first_matrix * S->n_node, 0, (size_t)P.n_matrix * S->n_node * sizeof(c128), c->stream));
-    k_nodal_diag<<<g, VEC_THREADS, 0, c->stream>>>(P.D, P.first_matrix);
-    EFB_CHECK_LAUNCH(c);
     dim3 gn((unsigned)vec_grid(c, S->n_node, P.n_matrix), (unsigned)P.n_matrix);
+    k_nodal_diag<<<gn, VEC_THREADS, 0, c->stream>>>(P.D, P.first_matrix);
+    EFB_CHECK_LAUNCH(c);
     k_linv<<<gn, VEC_THREADS, 0, c->stream>>>(P.D, P.first_matrix);
     EFB_CHECK_LAUNCH(c);
   }
